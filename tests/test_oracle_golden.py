@@ -1,0 +1,120 @@
+"""CPU: pin the oracle against the golden vectors produced by the reference's own code
+(tests/golden/make_golden.py) and against CPython's `random` (the reference RNG)."""
+import random
+from itertools import combinations
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import hits_to_array, rc_py, scan_cases
+
+
+def test_scan_oracle_matches_reference_golden(kmer_tables, golden_reads, scan_golden):
+    n = 0
+    for tag, T, rdat in scan_cases(kmer_tables, golden_reads):
+        KL, ISSUB, CANON = T['KMER_LIST'], T['KMER_ISSUBSTRING'], T['CANONICAL_STRINGS']
+        KL_REV, CANON_REV = [rc_py(k) for k in KL], [rc_py(k) for k in CANON]
+        bc = [oracle.base_count(rdat, CANON), oracle.base_count(rdat, CANON_REV)]
+        assert bc == scan_golden[tag + '|bc'].tolist(), tag
+        ori = oracle.rc(rdat) if bc[0] > bc[1] else rdat
+        assert int(bc[0] > bc[1]) == int(scan_golden[tag + '|flip'][0])
+        if bc[0] > bc[1]:
+            assert ori == rc_py(rdat)
+        for sname, kl in (('p', KL), ('q', KL_REV)):
+            cnt = oracle.density_counts(ori, kl, 100)
+            assert np.array_equal(cnt, scan_golden[tag + '|dens_' + sname].astype(np.int32)), tag
+        for sname, s, kl in (('suffix_q', ori[-6000:], KL_REV), ('full_p', ori[:20000], KL), ('full_q', ori[:20000], KL_REV)):
+            got = hits_to_array(oracle.nonoverlapping_hits(s, kl, ISSUB))
+            assert np.array_equal(got, scan_golden[tag + '|hits_' + sname]), (tag, sname)
+        n += 1
+    assert n > 60
+
+
+def test_issubstring_matches_reference(kmer_tables):
+    for T in kmer_tables.values():
+        assert oracle.kmer_issubstring(T['KMER_LIST']) == T['KMER_ISSUBSTRING']
+
+
+def test_mt19937_matches_cpython_golden(rng_golden):
+    for key, perms in rng_golden.items():
+        seed, n = (int(x) for x in key.split('|'))
+        base = bytes(range(1, 251)) * (n // 250 + 1)
+        s1 = ''.join(chr(33 + (i % 90)) for i in range(n))
+        s2 = ''.join(chr(40 + (i % 80)) for i in range(max(n - 1, 1)))
+        out = oracle.shuffle_stream(seed, [s1, s2, s1])
+        p1, p2, p3 = perms[:n], perms[n:n + max(n - 1, 1)], perms[n + max(n - 1, 1):]
+        assert out[0] == ''.join(s1[i] for i in p1), key
+        assert out[1] == ''.join(s2[i] for i in p2), key
+        assert out[2] == ''.join(s1[i] for i in p3), key
+        del base
+
+
+@pytest.mark.parametrize('seed', [0, 7, 12345, 2 ** 32 + 5, 2 ** 63 + 11])
+def test_mt19937_matches_live_cpython(seed):
+    rng = np.random.default_rng(seed % 1000)
+    seqs = [''.join(rng.choice(list('ACDEFGH'), n)) for n in (1, 17, 1000, 999, 2048, 3)]
+    random.seed(seed)
+    want = [''.join(random.sample(s, len(s))) for s in seqs]
+    assert oracle.shuffle_stream(seed, seqs) == want
+
+
+def test_mt_base_table():
+    t = oracle.mt_base_table()
+    assert t[0] == 19650218 and t.dtype == np.uint32
+    assert int(t[1]) == (1812433253 * (19650218 ^ (19650218 >> 30)) + 1) & 0xffffffff
+
+
+def test_scoring_matrix_quirks():
+    m = oracle.scoring_matrix('C', 'tvr')
+    ix = oracle.ALPHABET.index
+    assert m[ix('A'), ix('A')] == -2          # the '= 2.' is overwritten
+    assert m[ix('C'), ix('C')] == 0 and m[ix('D'), ix('D')] == 5
+    assert m[ix('C'), ix('D')] == -4 and m[ix('A'), ix('D')] == -2 and m[ix('A'), ix('C')] == -2
+    assert oracle.scoring_matrix('C', 'consensus')[ix('C'), ix('C')] == 1
+    assert np.array_equal(m, m.T)
+
+
+def test_nw_c_matches_python_full_matrix():
+    rng = np.random.default_rng(5)
+    letters = list('ACDEFY')
+    for trial in range(60):
+        n, m = int(rng.integers(1, 40)), int(rng.integers(1, 40))
+        a, b = ''.join(rng.choice(letters, n)), ''.join(rng.choice(letters, m))
+        for P in (oracle.AlignerParams(oracle.scoring_matrix('C', 'tvr'), (True, True)),
+                  oracle.AlignerParams(oracle.scoring_matrix('C', 'consensus'), (True, False)),
+                  oracle.AlignerParams(None, (True, False)),
+                  oracle.AlignerParams(None, (False, True)),
+                  oracle.AlignerParams(None, (False, False))):
+            assert oracle.nw_score(a, b, P) == oracle.nw_score_py(a, b, P)
+
+
+def test_nw_known_answers():
+    P = oracle.AlignerParams(None, (True, True))
+    assert oracle.nw_score('ACGT', 'ACGT', P) == 20
+    assert oracle.nw_score('ACGT', 'AGT', P) == 11          # 3 matches, one internal gap
+    assert oracle.nw_score('AAAA', 'TTTT', P) == -16
+    Pr = oracle.AlignerParams(None, (True, False))
+    assert oracle.nw_score('ACGTTTTT', 'ACG', Pr) == 15      # free right end gap
+    assert oracle.nw_score('TTTTTACG', 'ACG', Pr) == -5      # left end gap still costs
+    with pytest.raises(ValueError):
+        oracle.nw_score('', 'ACG', P)
+
+
+def test_dist_matrix_c_matches_python_and_golden(colorvecs, dp_golden):
+    seqs = [c[:1000] for c in colorvecs['colorvecs']['human_ont']][:24]
+    P = oracle.AlignerParams(oracle.scoring_matrix('C', 'tvr'), (True, True))
+    D, aln, rnd, cells = oracle.dist_matrix_c(seqs, P, True, True, 2, 12345, want_scores=True)
+    assert np.array_equal(D, dp_golden['ont24_tvr_R2|D'])
+    assert np.array_equal(aln, dp_golden['ont24_tvr_R2|aln'])
+    assert np.array_equal(rnd, dp_golden['ont24_tvr_R2|rnd'])
+    assert np.array_equal(D, D.T) and (np.diag(D) == 0).all()
+    sub = seqs[:5]
+    Dpy = oracle.dist_matrix_py(sub, P, True, True, 2, 777)
+    Dc = oracle.dist_matrix_c(sub, P, True, True, 2, 777)
+    assert np.array_equal(Dpy, Dc)
+    # a pair range only fills its own entries
+    Dpart = oracle.dist_matrix_c(sub, P, True, True, 2, 777, pair_range=(2, 5))
+    pairs = list(combinations(range(5), 2))
+    for p, (i, j) in enumerate(pairs):
+        assert Dpart[i, j] == (Dc[i, j] if 2 <= p < 5 else 0)
