@@ -1,0 +1,162 @@
+/*
+ * telogator2_b200.h -- C ABI of the B200-native hot path of Telogator2.
+ *
+ * The reference (zstephens/telogator2) has no FFI layer: its hot path is reached through the
+ * Python functions of source/tg_kmer.py and source/tg_align.py.  This header declares the
+ * device entry points those functions bind in telogator2_b200/ (ctypes).
+ * Each entry point cites the reference interface it replaces (file:line in the reference).
+ *
+ * Conventions
+ *   - every pointer whose name starts with d_ is a DEVICE pointer owned by the caller
+ *     (PyTorch tensors in the Python host); h_ pointers are host memory.
+ *   - the library never allocates memory it hands back and never frees caller memory.
+ *   - every function returns 0 on success or a negative TG_E* code; it never throws / exits.
+ *     tg_last_error() returns a static string describing the last failure on this thread.
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream); work is only enqueued.
+ *   - no CPU fallback exists: without a CUDA device every compute entry point returns TG_ECUDA.
+ */
+#ifndef TELOGATOR2_B200_H
+#define TELOGATOR2_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TG_OK        0
+#define TG_EINVAL   -1   /* bad argument / unsupported configuration          */
+#define TG_ECUDA    -2   /* CUDA runtime error (see tg_last_error)            */
+#define TG_ERANGE   -3   /* job outside the envelope of the requested kernel  */
+#define TG_EOVERFLOW -4  /* caller-provided output buffer too small           */
+
+const char *tg_last_error(void);
+int tg_version(void);                       /* ABI version, currently 1 */
+int tg_device_sm_count(int *sm_count);      /* multiprocessor count of the current device */
+
+/* =========================================================================================
+ * Pairwise TVR distance (tg_align.py)
+ * ======================================================================================= */
+
+/* One packed alignment job = up to two independent global alignments ("halves") that the
+ * u16x2 kernel advances in the two 16-bit lanes of every register.  Offsets index d_pool.
+ * out[h] < 0 marks an unused half (its inputs must still be valid; duplicate half 0). */
+typedef struct tg_nw_job {
+    int64_t row_off[2];     /* first code of the row sequence (seq_i side)    */
+    int64_t col_off[2];     /* first code of the column sequence (seq_j side) */
+    int32_t n[2];           /* row sequence length  (>= 1)                    */
+    int32_t m[2];           /* column sequence length (>= 1)                  */
+    int32_t out[2];         /* index into d_scores, or < 0                    */
+    int32_t pad_[2];
+} tg_nw_job;                /* 64 bytes */
+
+/* Scoring of Bio.Align.PairwiseAligner as configured by get_aligner_object()
+ * (tg_align.py:71-106) and get_scoring_matrix() (tg_align.py:32-68), integer valued.
+ * sub[a * alphabet + b] is the substitution score of codes a, b (match/mismatch mode is
+ * expressed as a matrix with match on the diagonal).  gap_* are the linear gap scores
+ * (open == extend at every call site that reaches score()): internal, left end, right end. */
+typedef struct tg_nw_scoring {
+    int32_t alphabet;       /* 1..32 */
+    int32_t gap, gap_left, gap_right;
+    int16_t sub[32 * 32];
+} tg_nw_scoring;
+
+/* Replaces aligner.score(seq_i, seq_j) (tg_align.py:125,142), i.e. Biopython's global
+ * Needleman-Wunsch score with linear gaps and left/right end-gap classes.
+ *
+ * tg_nw_scores_wave: warp-wavefront u16x2 DPX kernel (two alignments per register lane).
+ *   Envelope (else TG_ERANGE): gap_left == gap, gap_right in {gap, >= gap with equal shapes in
+ *   both halves}, 0 <= sub - 2*gap <= 127, max(sub - 2*gap) * min(n, m) <= 65535 per half.
+ *   d_scratch: tg_nw_wave_scratch_bytes(max_n) bytes; d_counter: one zeroed int32.
+ * tg_nw_scores_generic: int32 row-scan kernel, any gap scores, half 0 and half 1 processed
+ *   as separate alignments; max(m) bounded by shared memory (tg_nw_generic_max_m()). */
+size_t tg_nw_wave_scratch_bytes(int max_n);
+int tg_nw_wave_check(const tg_nw_scoring *sc, const tg_nw_job *h_jobs, int64_t n_jobs);
+int tg_nw_scores_wave(const uint8_t *d_pool, const tg_nw_job *d_jobs, int64_t n_jobs, int max_n,
+                      const tg_nw_scoring *sc, int32_t *d_scores, void *d_scratch, int32_t *d_counter,
+                      void *stream);
+int tg_nw_generic_max_m(void);
+int tg_nw_scores_generic(const uint8_t *d_pool, const tg_nw_job *d_jobs, int64_t n_jobs, int max_m,
+                         const tg_nw_scoring *sc, int32_t *d_scores, void *stream);
+
+/* One shuffle job = the null model of one sequence pair: random.seed(seed) followed by
+ * R x (shuffle_seq(seq_i), shuffle_seq(seq_j))  (tg_align.py:110-111,141-142; tg_util.py:451-452),
+ * bit-exact with CPython's MT19937 + random.sample.  The 2R shuffled strings are written
+ * back to back at dst_off: [i_0 (n) | j_0 (m) | i_1 | j_1 | ...]. */
+typedef struct tg_shuffle_job {
+    uint64_t seed;          /* abs(rng_seed + pair_index) */
+    int64_t src_i, src_j;   /* offsets of the (already length-adjusted) sequences in d_pool */
+    int64_t dst_off;        /* offset in d_pool of the 2R outputs */
+    int32_t n, m;
+} tg_shuffle_job;           /* 40 bytes */
+
+int tg_mt_shuffle(uint8_t *d_pool, const tg_shuffle_job *d_jobs, int64_t n_jobs, int R, int max_len,
+                  void *stream);
+
+/* Integer-ALU issue-rate microbenchmark used as the DP roofline denominator:
+ * runs `iters` dependent-chain-free VIMNMX3.U16x2/IADD pairs per thread on the whole device and
+ * returns lane-operations per second for the DPX op and for a plain integer add. */
+int tg_int_alu_peak(int iters, double *dpx_lane_ops_per_s, double *iadd_lane_ops_per_s);
+
+/* =========================================================================================
+ * k-mer scan (tg_kmer.py)
+ * ======================================================================================= */
+
+/* Device table for one k-mer list (KMER_LIST / KMER_LIST_REV / CANONICAL_STRINGS ...):
+ * an Aho-Corasick automaton over the REVERSED k-mers (the kernels walk each chunk right to
+ * left so that a match is reported at its start position), plus per-k-mer metadata.
+ * Built on the host; upload the blob as is.  Limits: K <= 64 k-mers, length <= 32,
+ * alphabet ACGT, <= 32 self-overlapping ("bordered") k-mers, < 4096 automaton states.
+ * Replaces the per-k-mer re.finditer passes of tg_kmer.py:69,96,178. */
+size_t tg_kmer_table_bytes(void);
+int tg_kmer_table_build(const char *kmers_concat, const int32_t *kmer_off, int K,
+                        const int32_t *issub_edges, const int32_t *issub_off, /* KMER_ISSUBSTRING CSR or NULL */
+                        void *h_table);
+
+/* Read layout: read r occupies bases [base_off[r], base_off[r] + len[r]) of a padded base
+ * space; base_off[r] is a multiple of 128.  ASCII input uses one byte per padded base
+ * (pad bytes arbitrary).  Packed form: d_pack2[w] holds bases 16w..16w+15, 2 bits each
+ * (A=0 C=1 T=2 G=3, little end first); d_nmask[w] holds 32 bases, bit set = not ACGT.
+ * Replaces nothing in the reference (it scans Python str) -- this is the HBM layout. */
+int tg_scan_pack(const uint8_t *d_ascii, const int64_t *d_base_off, const int32_t *d_len, int n_reads,
+                 uint32_t *d_pack2, uint32_t *d_nmask, void *stream);
+
+/* get_telomere_base_count(read, kmer_list) (tg_kmer.py:93-102) for two k-mer lists at once
+ * (CANONICAL_STRINGS and CANONICAL_STRINGS_REV, tg_tel.py:262-263): d_counts[2r + s]. */
+int tg_scan_basecount(const uint32_t *d_pack2, const uint32_t *d_nmask, const int64_t *d_base_off,
+                      const int32_t *d_len, int n_reads, const void *d_table_a, const void *d_table_b,
+                      int32_t *d_counts, void *stream);
+
+/* RC(read) (tg_util.py:433-434) applied in place of tg_tel.py:265-266: reads with
+ * d_flip[r] != 0 are reverse-complemented into d_pack2_out / d_nmask_out, others copied. */
+int tg_scan_orient(const uint32_t *d_pack2, const uint32_t *d_nmask, const int64_t *d_base_off,
+                   const int32_t *d_len, const uint8_t *d_flip, int n_reads,
+                   uint32_t *d_pack2_out, uint32_t *d_nmask_out, void *stream);
+
+/* get_telomere_kmer_density(read, kmer_list, tel_window) (tg_kmer.py:66-90) for two k-mer
+ * lists at once (KMER_LIST and KMER_LIST_REV, tg_tel.py:160-161).  Emits the integer window
+ * counts cnt[i] = #covered positions in (i, i + window], i in [0, len - window), as uint8 at
+ * d_cnt_x[base_off[r] + i]; density = cnt / window in float64 on the host.  window <= 255. */
+int tg_scan_density(const uint32_t *d_pack2, const uint32_t *d_nmask, const int64_t *d_base_off,
+                    const int32_t *d_len, int n_reads, const void *d_table_a, const void *d_table_b,
+                    int window, uint8_t *d_cnt_a, uint8_t *d_cnt_b, void *stream);
+
+/* get_nonoverlapping_kmer_hits(seq[lo:hi], KMER_LIST, KMER_ISSUBSTRING) (tg_kmer.py:173-230)
+ * for a batch of slices: slice q = read d_slice_read[q], positions [d_slice_lo[q], d_slice_hi[q]).
+ * d_work: tg_scan_hits_work_bytes(total slice bases) bytes of scratch.  Spans are appended to
+ * d_span_* (slice, k, start, end relative to lo) in no particular order; *d_span_count
+ * receives the number of spans (if it exceeds span_cap the extra spans were dropped and the
+ * caller must retry with a larger buffer). */
+size_t tg_scan_hits_work_bytes(int64_t total_slice_bases, int n_slices);
+int tg_scan_hits(const uint32_t *d_pack2, const uint32_t *d_nmask, const int64_t *d_base_off,
+                 const int32_t *d_slice_read, const int32_t *d_slice_lo, const int32_t *d_slice_hi, int n_slices,
+                 const int64_t *d_slice_work_off, /* exclusive prefix sum of slice lengths padded to 64 */
+                 int64_t total_work_bases, const void *d_table, void *d_work,
+                 int32_t *d_span_slice, int32_t *d_span_k, int32_t *d_span_start, int32_t *d_span_end,
+                 int64_t span_cap, unsigned long long *d_span_count, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TELOGATOR2_B200_H */

@@ -1,0 +1,93 @@
+"""ctypes binding of libtg_b200.so (include/telogator2_b200.h).  Fails loudly: no library or no
+CUDA device means the hot path is unavailable -- there is no CPU fallback."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, 'libtg_b200.so')
+
+TG_OK, TG_EINVAL, TG_ECUDA, TG_ERANGE, TG_EOVERFLOW = 0, -1, -2, -3, -4
+MAXA = 32
+
+# struct tg_nw_job (64 bytes) / tg_shuffle_job (40 bytes) as numpy record dtypes
+NW_JOB = np.dtype([('row_off', '<i8', (2,)), ('col_off', '<i8', (2,)), ('n', '<i4', (2,)), ('m', '<i4', (2,)),
+                   ('out', '<i4', (2,)), ('pad_', '<i4', (2,))], align=True)
+SHUFFLE_JOB = np.dtype([('seed', '<u8'), ('src_i', '<i8'), ('src_j', '<i8'), ('dst_off', '<i8'),
+                        ('n', '<i4'), ('m', '<i4')], align=True)
+assert NW_JOB.itemsize == 64 and SHUFFLE_JOB.itemsize == 40
+
+
+class NwScoring(C.Structure):
+    _fields_ = [('alphabet', C.c_int32), ('gap', C.c_int32), ('gap_left', C.c_int32), ('gap_right', C.c_int32),
+                ('sub', C.c_int16 * (MAXA * MAXA))]
+
+
+class TgError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f'telogator2_b200 error {code}: {msg}')
+        self.code = code
+
+
+_lib = None
+
+EXPORTS = ['tg_last_error', 'tg_version', 'tg_device_sm_count',
+           'tg_nw_wave_scratch_bytes', 'tg_nw_wave_check', 'tg_nw_scores_wave', 'tg_nw_generic_max_m',
+           'tg_nw_scores_generic', 'tg_mt_shuffle', 'tg_int_alu_peak',
+           'tg_kmer_table_bytes', 'tg_kmer_table_build', 'tg_scan_pack', 'tg_scan_basecount', 'tg_scan_orient',
+           'tg_scan_density', 'tg_scan_hits_work_bytes', 'tg_scan_hits']
+
+
+def load():
+    """Load the CUDA library (no device needed to load; compute calls need one)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise ImportError(f'{SO_PATH} is missing: build it with `python -m telogator2_b200.build` '
+                          '(nvcc, sm_100a). telogator2_b200 has no CPU fallback.')
+    L = C.CDLL(SO_PATH)
+    vp, i32, i64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
+    L.tg_last_error.restype = C.c_char_p
+    L.tg_nw_wave_scratch_bytes.restype = sz
+    L.tg_nw_wave_scratch_bytes.argtypes = [i32]
+    L.tg_nw_wave_check.argtypes = [C.POINTER(NwScoring), vp, i64]
+    L.tg_nw_scores_wave.argtypes = [vp, vp, i64, i32, C.POINTER(NwScoring), vp, vp, vp, vp]
+    L.tg_nw_scores_generic.argtypes = [vp, vp, i64, i32, C.POINTER(NwScoring), vp, vp]
+    L.tg_mt_shuffle.argtypes = [vp, vp, i64, i32, i32, vp]
+    L.tg_int_alu_peak.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.tg_device_sm_count.argtypes = [C.POINTER(C.c_int)]
+    L.tg_kmer_table_bytes.restype = sz
+    L.tg_kmer_table_build.argtypes = [C.c_char_p, vp, i32, vp, vp, vp]
+    L.tg_scan_pack.argtypes = [vp, vp, vp, i32, vp, vp, vp]
+    L.tg_scan_basecount.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp]
+    L.tg_scan_orient.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp]
+    L.tg_scan_density.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, vp, vp, vp]
+    L.tg_scan_hits_work_bytes.restype = sz
+    L.tg_scan_hits_work_bytes.argtypes = [i64, i32]
+    L.tg_scan_hits.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, i64, vp, vp, vp, vp, vp, vp, i64, vp, vp]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != TG_OK:
+        raise TgError(rc, load().tg_last_error().decode('utf-8', 'replace'))
+
+
+def require_cuda():
+    """torch + a CUDA device, or a loud failure."""
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError('telogator2_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+    load()
+    return torch
+
+
+def stream_ptr(torch):
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def dptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)

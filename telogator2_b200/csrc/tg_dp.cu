@@ -1,0 +1,564 @@
+// Pairwise TVR distance kernels for sm_100a:
+//   nw_wave_kernel     u16x2 DPX warp-wavefront Needleman-Wunsch score (two alignments per register)
+//   nw_generic_kernel  int32 row-scan Needleman-Wunsch score (any gap scores / lengths)
+//   mt_shuffle_kernel  CPython MT19937 + random.sample null-model generator (bit-exact)
+//   int_peak_kernel    integer-ALU issue-rate microbenchmark (DP roofline denominator)
+//
+// Reference semantics: Bio.Align.PairwiseAligner.score() as configured in tg_align.py:71-106 and called at
+// tg_align.py:125,142; random.seed / shuffle_seq at tg_align.py:110-111, tg_util.py:451-452.
+//
+// Score transform used by the wave kernel.  With linear gap g everywhere inside the matrix,
+//     H[i][j] = max(H[i-1][j-1] + S(a_i,b_j), H[i-1][j] + g, H[i][j-1] + g)
+// substitute H'[i][j] = H[i][j] - g*(i+j):
+//     H'[i][j] = max(H'[i-1][j-1] + (S - 2g), H'[i-1][j], H'[i][j-1])
+// so a cell costs one add and one 3-input max (VIMNMX3.U16x2 handles two alignments at once),
+// all values are non-negative and non-decreasing along rows and columns, and with gap_left == g
+// the whole boundary row/column of H' is zero.  Free right end gaps (gap_right >= g) are
+// recovered afterwards as max over the last row / last column of H (see the epilogue).
+#include "tg_common.cuh"
+#include <limits.h>
+
+namespace {
+
+constexpr int WAVE_C = 16;                 // packed columns held in registers by each lane
+constexpr int WAVE_W = 32 * WAVE_C;        // columns per column block (one warp)
+constexpr int WAVE_WARPS = 4;              // warps (= concurrent jobs) per CTA
+constexpr int WAVE_CTAS_PER_SM = 2;
+constexpr int MAXA = 32;
+
+struct WaveParams {
+    const uint8_t *pool;
+    const tg_nw_job *jobs;
+    long long n_jobs;
+    int32_t *scores;
+    uint32_t *scratch;          // per-warp border column, scratch_stride u32 each
+    unsigned long long *counter;
+    int scratch_stride;
+    int A;                      // alphabet size
+    int g, gr;                  // internal gap, right end gap
+    int right_free;             // gr != g
+    uint8_t sp[MAXA * MAXA];    // S' = S - 2g, row-major [a][b] with stride MAXA
+};
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
+// byte k of p0 -> low half, byte k of p1 -> high half, upper bytes = replicated sign bit (= 0, S' < 128)
+template <int K>
+__device__ __forceinline__ uint32_t merge_scores(uint32_t p0, uint32_t p1)
+{
+    constexpr uint32_t sel = K | ((K | 8) << 4) | ((4 + K) << 8) | (((4 + K) | 8) << 12);
+    return prmt(p0, p1, sel);
+}
+
+__device__ __forceinline__ uint32_t cell(uint32_t diag, uint32_t sc, uint32_t up, uint32_t left)
+{
+    return __vimax3_u16x2(diag + sc, up, left);
+}
+
+__global__ void __launch_bounds__(WAVE_WARPS * 32, WAVE_CTAS_PER_SM)
+nw_wave_kernel(const __grid_constant__ WaveParams P)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int A = P.A;
+    uint8_t *s_sp = smem;                                              // MAXA*MAXA bytes
+    uint8_t *prof = smem + MAXA * MAXA + (size_t)warp * (2 * A * WAVE_W);   // [2][A][WAVE_W]
+    for (int i = threadIdx.x; i < MAXA * MAXA; i += blockDim.x) s_sp[i] = P.sp[i];
+    __syncthreads();
+
+    uint32_t *bord = P.scratch + (size_t)(blockIdx.x * WAVE_WARPS + warp) * P.scratch_stride;
+    const int g = P.g, gr = P.gr;
+
+    for (;;) {
+        unsigned long long jid = 0;
+        if (lane == 0) jid = atomicAdd(P.counter, 1ULL);
+        jid = __shfl_sync(TG_FULL_MASK, jid, 0);
+        if (jid >= (unsigned long long)P.n_jobs) break;
+        const tg_nw_job *J = P.jobs + jid;
+        const long long row0 = J->row_off[0], row1 = J->row_off[1];
+        const long long col0 = J->col_off[0], col1 = J->col_off[1];
+        const int n0 = J->n[0], n1 = J->n[1], m0 = J->m[0], m1 = J->m[1];
+        const int out0 = J->out[0], out1 = J->out[1];
+        const int N = max(n0, n1), M = max(m0, m1);
+        const int nblk = (M + WAVE_W - 1) / WAVE_W;
+        const int pad0 = nblk * WAVE_W - m0, pad1 = nblk * WAVE_W - m1;   // left padding (right-aligned columns)
+        uint32_t res0 = 0, res1 = 0;
+        int rf0 = INT_MIN, rf1 = INT_MIN;
+
+        for (int blk = 0; blk < nblk; blk++) {
+            // ---- query profile of this column block: prof[h][a][x] = S'(a, colseq_h[x]) (0 on padding) ----
+            __syncwarp();
+            for (int x = lane; x < WAVE_W; x += 32) {
+                const int X = blk * WAVE_W + x;
+                const int j0 = X - pad0, j1 = X - pad1;
+                const int b0 = (j0 >= 0) ? (int)__ldg(P.pool + col0 + j0) : -1;
+                const int b1 = (j1 >= 0) ? (int)__ldg(P.pool + col1 + j1) : -1;
+                for (int a = 0; a < A; a++) {
+                    prof[(size_t)a * WAVE_W + x] = (b0 >= 0) ? s_sp[a * MAXA + b0] : (uint8_t)0;
+                    prof[(size_t)(A + a) * WAVE_W + x] = (b1 >= 0) ? s_sp[a * MAXA + b1] : (uint8_t)0;
+                }
+            }
+            __syncwarp();
+
+            uint32_t H[WAVE_C];
+#pragma unroll
+            for (int c = 0; c < WAVE_C; c++) H[c] = 0u;
+            uint32_t prev_left = 0u;
+            // border column of the previous block, 32 rows at a time
+            uint32_t bcur = (blk > 0 && lane < N) ? __ldcg(bord + lane) : 0u;
+            uint32_t bnext = (blk > 0 && 32 + lane < N) ? __ldcg(bord + 32 + lane) : 0u;
+            const uint8_t *pb0 = prof + lane * WAVE_C;
+            const uint8_t *pb1 = prof + (size_t)A * WAVE_W + lane * WAVE_C;
+            int r = -lane;
+            uint32_t a0 = (r == 0) ? (uint32_t)__ldg(P.pool + row0) : 0u;
+            uint32_t a1 = (r == 0) ? (uint32_t)__ldg(P.pool + row1) : 0u;
+            const bool last_blk = (blk == nblk - 1);
+            const int steps = N + 31;
+
+            for (int s = 0; s < steps; s++, r++) {
+                if ((s & 31) == 0 && s > 0) {
+                    bcur = bnext;
+                    const int idx = s + 32 + lane;
+                    bnext = (blk > 0 && idx < N) ? __ldcg(bord + idx) : 0u;
+                }
+                uint32_t left_in = __shfl_up_sync(TG_FULL_MASK, H[WAVE_C - 1], 1);
+                const uint32_t bl = __shfl_sync(TG_FULL_MASK, bcur, s & 31);
+                if (lane == 0) left_in = bl;
+                if (r >= 0 && r < N) {
+                    const uint4 q0 = *reinterpret_cast<const uint4 *>(pb0 + a0 * WAVE_W);
+                    const uint4 q1 = *reinterpret_cast<const uint4 *>(pb1 + a1 * WAVE_W);
+                    uint32_t d = prev_left, l = left_in, up;
+#define TG_CELL(c, qa, qb, k)                        \
+    up = H[c];                                       \
+    l = cell(d, merge_scores<k>(qa, qb), up, l);     \
+    d = up;                                          \
+    H[c] = l;
+                    TG_CELL(0, q0.x, q1.x, 0) TG_CELL(1, q0.x, q1.x, 1) TG_CELL(2, q0.x, q1.x, 2) TG_CELL(3, q0.x, q1.x, 3)
+                    TG_CELL(4, q0.y, q1.y, 0) TG_CELL(5, q0.y, q1.y, 1) TG_CELL(6, q0.y, q1.y, 2) TG_CELL(7, q0.y, q1.y, 3)
+                    TG_CELL(8, q0.z, q1.z, 0) TG_CELL(9, q0.z, q1.z, 1) TG_CELL(10, q0.z, q1.z, 2) TG_CELL(11, q0.z, q1.z, 3)
+                    TG_CELL(12, q0.w, q1.w, 0) TG_CELL(13, q0.w, q1.w, 1) TG_CELL(14, q0.w, q1.w, 2) TG_CELL(15, q0.w, q1.w, 3)
+#undef TG_CELL
+                    if (lane == 31) bord[r] = H[WAVE_C - 1];
+                    if (last_blk) {
+                        if (r == n0 - 1) res0 = H[WAVE_C - 1] & 0xffffu;
+                        if (r == n1 - 1) res1 = H[WAVE_C - 1] >> 16;
+                    }
+                }
+                prev_left = left_in;
+                const int rn = r + 1;
+                a0 = (rn >= 0 && rn < n0) ? (uint32_t)__ldg(P.pool + row0 + rn) : 0u;
+                a1 = (rn >= 0 && rn < n1) ? (uint32_t)__ldg(P.pool + row1 + rn) : 0u;
+            }
+            __syncwarp();
+
+            if (P.right_free) {
+                // last row of H for this block (both halves have the same shape in this mode):
+                // H[n][j] + gr*(m-j) = H'[n][j] + g*(n+j) + gr*(m-j)
+#pragma unroll
+                for (int c = 0; c < WAVE_C; c++) {
+                    const int X = blk * WAVE_W + lane * WAVE_C + c;
+                    const int j0 = X - pad0 + 1, j1 = X - pad1 + 1;     // 1-based column
+                    if (j0 >= 1) rf0 = max(rf0, (int)(H[c] & 0xffffu) + g * (n0 + j0) + gr * (m0 - j0));
+                    if (j1 >= 1) rf1 = max(rf1, (int)(H[c] >> 16) + g * (n1 + j1) + gr * (m1 - j1));
+                }
+            }
+        }
+
+        if (!P.right_free) {
+            if (lane == 31) {
+                if (out0 >= 0) P.scores[out0] = (int)res0 + g * (n0 + m0);
+                if (out1 >= 0) P.scores[out1] = (int)res1 + g * (n1 + m1);
+            }
+        } else {
+            // last column: bord[r] = H'[r+1][m]; H[i][m] + gr*(n-i) = H'[i][m] + g*(i+m) + gr*(n-i)
+            for (int rr = lane; rr < N; rr += 32) {
+                const uint32_t v = __ldcg(bord + rr);
+                const int i = rr + 1;
+                if (i <= n0) rf0 = max(rf0, (int)(v & 0xffffu) + g * (i + m0) + gr * (n0 - i));
+                if (i <= n1) rf1 = max(rf1, (int)(v >> 16) + g * (i + m1) + gr * (n1 - i));
+            }
+            // whole sequence against end gaps only: H[n][0] + gr*m and H[0][m] + gr*n (gap_left == g)
+            rf0 = max(rf0, max(n0 * g + gr * m0, m0 * g + gr * n0));
+            rf1 = max(rf1, max(n1 * g + gr * m1, m1 * g + gr * n1));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                rf0 = max(rf0, __shfl_xor_sync(TG_FULL_MASK, rf0, o));
+                rf1 = max(rf1, __shfl_xor_sync(TG_FULL_MASK, rf1, o));
+            }
+            if (lane == 0) {
+                if (out0 >= 0) P.scores[out0] = rf0;
+                if (out1 >= 0) P.scores[out1] = rf1;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generic int32 kernel: one CTA per alignment, row by row.  For row i with horizontal gap gh
+// (= gap_right in the last row, else gap):
+//   T[j]   = max(H[i-1][j-1] + S, H[i-1][j] + gv(j)),  T[0] = i * gap_left
+//   H[i][j] = max_{k<=j} (T[k] + gh*(j-k)) = gh*j + prefixmax_k (T[k] - gh*k)
+// which turns the left-neighbour dependency into a block-wide prefix max.
+// ------------------------------------------------------------------------------------------------
+constexpr int GEN_THREADS = 256;
+constexpr int NEG_BIG = -(1 << 29);
+
+struct GenParams {
+    const uint8_t *pool;
+    const tg_nw_job *jobs;
+    long long n_items;          // 2 * n_jobs (job, half)
+    int32_t *scores;
+    int A, g, gl, gr;
+    int max_m;
+    int16_t sub[MAXA * MAXA];
+};
+
+__global__ void __launch_bounds__(GEN_THREADS) nw_generic_kernel(const __grid_constant__ GenParams P)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    int32_t *Hrow = reinterpret_cast<int32_t *>(smem);           // max_m + 1
+    int32_t *U = Hrow + (P.max_m + 1);                           // max_m + 1
+    __shared__ int32_t s_sub[MAXA * MAXA];
+    __shared__ int32_t s_wtot[GEN_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < MAXA * MAXA; i += GEN_THREADS) s_sub[i] = P.sub[i];
+    __syncthreads();
+
+    for (long long item = blockIdx.x; item < P.n_items; item += gridDim.x) {
+        const tg_nw_job *J = P.jobs + (item >> 1);
+        const int h = (int)(item & 1);
+        const int out = J->out[h];
+        if (out < 0) continue;
+        const int n = J->n[h], m = J->m[h];
+        const uint8_t *a = P.pool + J->row_off[h], *b = P.pool + J->col_off[h];
+        const int chunk = (m + 1 + GEN_THREADS - 1) / GEN_THREADS;
+        const int jb = min(tid * chunk, m + 1), je = min(jb + chunk, m + 1);
+        __syncthreads();
+        for (int j = tid; j <= m; j += GEN_THREADS) Hrow[j] = j * P.gl;
+        __syncthreads();
+        for (int i = 1; i <= n; i++) {
+            const int ai = __ldg(a + i - 1);
+            const int gh = (i == n) ? P.gr : P.g;
+            int local = NEG_BIG;
+            for (int j = jb; j < je; j++) {
+                int t;
+                if (j == 0) t = i * P.gl;
+                else {
+                    const int gv = (j == m) ? P.gr : P.g;
+                    t = max(Hrow[j - 1] + s_sub[ai * MAXA + __ldg(b + j - 1)], Hrow[j] + gv);
+                }
+                local = max(local, t - gh * j);
+                U[j] = local;
+            }
+            // block-wide exclusive prefix max of `local`
+            int inc = local;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(TG_FULL_MASK, inc, o);
+                if (lane >= o) inc = max(inc, v);
+            }
+            if (lane == 31) s_wtot[warp] = inc;
+            int excl = __shfl_up_sync(TG_FULL_MASK, inc, 1);
+            if (lane == 0) excl = NEG_BIG;
+            __syncthreads();                       // all reads of Hrow done, s_wtot visible
+            for (int w = 0; w < warp; w++) excl = max(excl, s_wtot[w]);
+            for (int j = jb; j < je; j++) Hrow[j] = gh * j + max(excl, U[j]);
+            __syncthreads();
+        }
+        if (tid == 0) P.scores[out] = Hrow[m];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// MT19937 exactly as CPython seeds and consumes it.  One thread per sequence pair; the 624-word
+// state lives in shared memory as mt[word][thread] (bank == thread, conflict free for any word
+// index), regenerated lazily one word per draw (identical to the batch twist because the batch
+// twist updates in place in the same order), so divergent rejection loops never serialise a twist.
+// ------------------------------------------------------------------------------------------------
+constexpr int MT_THREADS = 32;
+__constant__ uint32_t c_mt_base[624];      // init_genrand(19650218)
+
+__global__ void __launch_bounds__(MT_THREADS) mt_shuffle_kernel(uint8_t *pool, const tg_shuffle_job *jobs,
+                                                               long long n_jobs, int R, int pool_stride)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint32_t *mt = reinterpret_cast<uint32_t *>(smem);                 // [624][MT_THREADS]
+    uint8_t *sp = smem + 624 * MT_THREADS * sizeof(uint32_t) + (size_t)threadIdx.x * pool_stride;
+    const int tid = threadIdx.x;
+#define MT(i) mt[(i) * MT_THREADS + tid]
+    for (long long job = (long long)blockIdx.x * MT_THREADS + tid; job < n_jobs;
+         job += (long long)gridDim.x * MT_THREADS) {
+        const tg_shuffle_job J = jobs[job];
+        // ---- random.seed(int): init_by_array(32-bit words of abs(seed)) ----
+        uint32_t key[2] = {(uint32_t)(J.seed & 0xffffffffu), (uint32_t)(J.seed >> 32)};
+        const int klen = key[1] ? 2 : 1;
+        for (int i = 0; i < 624; i++) MT(i) = c_mt_base[i];
+        {
+            int i = 1, j = 0;
+            uint32_t prev = MT(0);
+            for (int k = 624; k; k--) {
+                uint32_t v = (MT(i) ^ ((prev ^ (prev >> 30)) * 1664525u)) + key[j] + (uint32_t)j;
+                MT(i) = v; prev = v;
+                i++; j++;
+                if (i >= 624) { MT(0) = prev; i = 1; }
+                if (j >= klen) j = 0;
+            }
+            for (int k = 623; k; k--) {
+                uint32_t v = (MT(i) ^ ((prev ^ (prev >> 30)) * 1566083941u)) - (uint32_t)i;
+                MT(i) = v; prev = v;
+                i++;
+                if (i >= 624) { MT(0) = prev; i = 1; }
+            }
+            MT(0) = 0x80000000u;
+        }
+        int kk = 0;                                   // next state word to regenerate
+        long long dst = J.dst_off;
+        for (int rep = 0; rep < 2 * R; rep++) {
+            const int len = (rep & 1) ? J.m : J.n;
+            const uint8_t *src = pool + ((rep & 1) ? J.src_j : J.src_i);
+            for (int x = 0; x < len; x++) sp[x] = src[x];         // pool = list(population)
+            int i = 0;
+            while (i < len) {
+                // genrand_uint32, lazy twist of word kk
+                const int k1 = (kk == 623) ? 0 : kk + 1;
+                const int k397 = (kk >= 227) ? kk - 227 : kk + 397;
+                const uint32_t y0 = (MT(kk) & 0x80000000u) | (MT(k1) & 0x7fffffffu);
+                uint32_t y = MT(k397) ^ (y0 >> 1) ^ ((y0 & 1u) ? 0x9908b0dfu : 0u);
+                MT(kk) = y;
+                kk = k1;
+                y ^= (y >> 11);
+                y ^= (y << 7) & 0x9d2c5680u;
+                y ^= (y << 15) & 0xefc60000u;
+                y ^= (y >> 18);
+                // _randbelow(nn): k = nn.bit_length(); r = getrandbits(k); redraw while r >= nn
+                const uint32_t nn = (uint32_t)(len - i);
+                const uint32_t r = y >> __clz(nn);                 // 32 - bit_length(nn) == clz(nn)
+                if (r < nn) {
+                    pool[dst + i] = sp[r];                         // result[i] = pool[j]
+                    sp[r] = sp[nn - 1];                            // pool[j] = pool[n-i-1]
+                    i++;
+                }
+            }
+            dst += len;
+        }
+    }
+#undef MT
+}
+
+// ------------------------------------------------------------------------------------------------
+// Integer-ALU peak: 8 independent accumulator chains of (add, VIMNMX3.U16x2) per thread.
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) int_peak_kernel(uint32_t *out, int iters, uint32_t seed)
+{
+    uint32_t a[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = seed * (threadIdx.x + 1) + k;
+    uint32_t b = seed ^ 0x00030005u, c = seed | 0x00010001u;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (MODE == 0) a[k] = __vimax3_u16x2(a[k], b, c);           // DPX only
+                else a[k] = __vimax3_u16x2(a[k] + b, a[(k + 1) & 7], c);    // add + DPX (cell shape)
+            }
+            b += 0x00010001u;
+            c ^= b;
+        }
+    }
+    uint32_t r = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) r ^= a[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+TG_EXPORT size_t tg_nw_wave_scratch_bytes(int max_n)
+{
+    const int sms = tg_sm_count();
+    const size_t stride = ((size_t)max_n + 63) / 32 * 32;
+    return (size_t)(sms > 0 ? sms : 148) * WAVE_CTAS_PER_SM * WAVE_WARPS * stride * sizeof(uint32_t);
+}
+
+static int wave_envelope(const tg_nw_scoring *sc, int *max_sp_out)
+{
+    if (!sc) return tg_set_err(TG_EINVAL, "scoring is NULL");
+    if (sc->alphabet < 1 || sc->alphabet > MAXA) return tg_set_err(TG_EINVAL, "alphabet %d outside 1..%d", sc->alphabet, MAXA);
+    if (sc->gap_left != sc->gap) return tg_set_err(TG_ERANGE, "wave kernel needs gap_left == gap");
+    if (sc->gap_right < sc->gap) return tg_set_err(TG_ERANGE, "wave kernel needs gap_right >= gap");
+    int max_sp = 0;
+    for (int a = 0; a < sc->alphabet; a++)
+        for (int b = 0; b < sc->alphabet; b++) {
+            const int sp = sc->sub[a * MAXA + b] - 2 * sc->gap;
+            if (sp < 0 || sp > 127) return tg_set_err(TG_ERANGE, "S - 2*gap = %d outside 0..127", sp);
+            if (sp > max_sp) max_sp = sp;
+        }
+    *max_sp_out = max_sp;
+    return TG_OK;
+}
+
+TG_EXPORT int tg_nw_wave_check(const tg_nw_scoring *sc, const tg_nw_job *h_jobs, int64_t n_jobs)
+{
+    int max_sp = 0;
+    int rc = wave_envelope(sc, &max_sp);
+    if (rc != TG_OK) return rc;
+    const bool rf = sc->gap_right != sc->gap;
+    for (int64_t q = 0; q < n_jobs; q++) {
+        const tg_nw_job &J = h_jobs[q];
+        for (int h = 0; h < 2; h++)
+            if (J.n[h] < 1 || J.m[h] < 1) return tg_set_err(TG_EINVAL, "job %lld half %d has an empty sequence", (long long)q, h);
+        const long long N = J.n[0] > J.n[1] ? J.n[0] : J.n[1], M = J.m[0] > J.m[1] ? J.m[0] : J.m[1];
+        if ((long long)max_sp * (N < M ? N : M) > 65535)
+            return tg_set_err(TG_ERANGE, "job %lld (%lld x %lld) overflows 16-bit scores", (long long)q, N, M);
+        if (rf && (J.n[0] != J.n[1] || J.m[0] != J.m[1]))
+            return tg_set_err(TG_ERANGE, "job %lld: free right end gaps need equal shapes in both halves", (long long)q);
+    }
+    return TG_OK;
+}
+
+TG_EXPORT int tg_nw_scores_wave(const uint8_t *d_pool, const tg_nw_job *d_jobs, int64_t n_jobs, int max_n,
+                                const tg_nw_scoring *sc, int32_t *d_scores, void *d_scratch, int32_t *d_counter,
+                                void *stream)
+{
+    if (n_jobs <= 0) return TG_OK;
+    int max_sp = 0;
+    int rc = wave_envelope(sc, &max_sp);
+    if (rc != TG_OK) return rc;
+    if (!d_pool || !d_jobs || !d_scores || !d_scratch || !d_counter) return tg_set_err(TG_EINVAL, "NULL device pointer");
+    const int sms = tg_sm_count();
+    if (sms <= 0) return tg_set_err(TG_ECUDA, "no CUDA device");
+    WaveParams P;
+    P.pool = d_pool; P.jobs = d_jobs; P.n_jobs = n_jobs; P.scores = d_scores;
+    P.scratch = reinterpret_cast<uint32_t *>(d_scratch);
+    P.counter = reinterpret_cast<unsigned long long *>(d_counter);
+    P.scratch_stride = (int)(((size_t)max_n + 63) / 32 * 32);
+    P.A = sc->alphabet; P.g = sc->gap; P.gr = sc->gap_right; P.right_free = (sc->gap_right != sc->gap);
+    for (int a = 0; a < MAXA; a++)
+        for (int b = 0; b < MAXA; b++)
+            P.sp[a * MAXA + b] = (a < sc->alphabet && b < sc->alphabet) ? (uint8_t)(sc->sub[a * MAXA + b] - 2 * sc->gap) : 0;
+    const size_t smem = MAXA * MAXA + (size_t)WAVE_WARPS * 2 * sc->alphabet * WAVE_W;
+    TG_CUDA_CHECK(cudaFuncSetAttribute(nw_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    TG_CUDA_CHECK(cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), st));
+    long long warps_needed = n_jobs;
+    int grid = sms * WAVE_CTAS_PER_SM;
+    const long long ctas_needed = (warps_needed + WAVE_WARPS - 1) / WAVE_WARPS;
+    if (ctas_needed < grid) grid = (int)ctas_needed;
+    nw_wave_kernel<<<grid, WAVE_WARPS * 32, smem, st>>>(P);
+    TG_CUDA_CHECK(cudaGetLastError());
+    return TG_OK;
+}
+
+TG_EXPORT int tg_nw_generic_max_m(void) { return 24000; }
+
+TG_EXPORT int tg_nw_scores_generic(const uint8_t *d_pool, const tg_nw_job *d_jobs, int64_t n_jobs, int max_m,
+                                   const tg_nw_scoring *sc, int32_t *d_scores, void *stream)
+{
+    if (n_jobs <= 0) return TG_OK;
+    if (!sc || sc->alphabet < 1 || sc->alphabet > MAXA) return tg_set_err(TG_EINVAL, "bad scoring");
+    if (max_m < 1 || max_m > tg_nw_generic_max_m()) return tg_set_err(TG_ERANGE, "max_m %d outside 1..%d", max_m, tg_nw_generic_max_m());
+    if (!d_pool || !d_jobs || !d_scores) return tg_set_err(TG_EINVAL, "NULL device pointer");
+    const int sms = tg_sm_count();
+    if (sms <= 0) return tg_set_err(TG_ECUDA, "no CUDA device");
+    GenParams P;
+    P.pool = d_pool; P.jobs = d_jobs; P.n_items = 2 * n_jobs; P.scores = d_scores;
+    P.A = sc->alphabet; P.g = sc->gap; P.gl = sc->gap_left; P.gr = sc->gap_right; P.max_m = max_m;
+    for (int i = 0; i < MAXA * MAXA; i++) P.sub[i] = sc->sub[i];
+    const size_t smem = 2 * (size_t)(max_m + 1) * sizeof(int32_t);
+    TG_CUDA_CHECK(cudaFuncSetAttribute(nw_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = (int)((200 * 1024) / (smem + 8192));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    long long grid = (long long)sms * per_sm;
+    if (grid > P.n_items) grid = P.n_items;
+    nw_generic_kernel<<<(int)grid, GEN_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(P);
+    TG_CUDA_CHECK(cudaGetLastError());
+    return TG_OK;
+}
+
+static void mt_base_table_host(uint32_t *mt)
+{
+    mt[0] = 19650218u;
+    for (int i = 1; i < 624; i++) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+}
+
+TG_EXPORT int tg_mt_shuffle(uint8_t *d_pool, const tg_shuffle_job *d_jobs, int64_t n_jobs, int R, int max_len, void *stream)
+{
+    if (n_jobs <= 0 || R <= 0) return TG_OK;
+    if (!d_pool || !d_jobs) return tg_set_err(TG_EINVAL, "NULL device pointer");
+    if (max_len < 1) return tg_set_err(TG_EINVAL, "max_len < 1");
+    const int sms = tg_sm_count();
+    if (sms <= 0) return tg_set_err(TG_ECUDA, "no CUDA device");
+    // per-thread pool stride: multiple of 4 with odd word count so the 32 lanes start in distinct banks
+    int stride = (max_len + 3) / 4;
+    if ((stride & 1) == 0) stride++;
+    stride *= 4;
+    const size_t smem = 624 * MT_THREADS * sizeof(uint32_t) + (size_t)MT_THREADS * stride;
+    if (smem > 227 * 1024) return tg_set_err(TG_ERANGE, "max_len %d too long for the shuffle kernel", max_len);
+    static thread_local int base_uploaded_dev = -1;
+    int dev = 0;
+    TG_CUDA_CHECK(cudaGetDevice(&dev));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (base_uploaded_dev != dev) {
+        uint32_t base[624];
+        mt_base_table_host(base);
+        TG_CUDA_CHECK(cudaMemcpyToSymbol(c_mt_base, base, sizeof(base)));
+        base_uploaded_dev = dev;
+    }
+    TG_CUDA_CHECK(cudaFuncSetAttribute(mt_shuffle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    long long grid = (long long)sms * per_sm;
+    const long long need = (n_jobs + MT_THREADS - 1) / MT_THREADS;
+    if (grid > need) grid = need;
+    mt_shuffle_kernel<<<(int)grid, MT_THREADS, smem, st>>>(d_pool, d_jobs, n_jobs, R, stride);
+    TG_CUDA_CHECK(cudaGetLastError());
+    return TG_OK;
+}
+
+TG_EXPORT int tg_int_alu_peak(int iters, double *dpx_lane_ops_per_s, double *iadd_lane_ops_per_s)
+{
+    const int sms = tg_sm_count();
+    if (sms <= 0) return tg_set_err(TG_ECUDA, "no CUDA device");
+    const int grid = sms * 8, block = 256;
+    uint32_t *d_out = nullptr;
+    TG_CUDA_CHECK(cudaMalloc(&d_out, (size_t)grid * block * sizeof(uint32_t)));
+    cudaEvent_t e0, e1;
+    TG_CUDA_CHECK(cudaEventCreate(&e0));
+    TG_CUDA_CHECK(cudaEventCreate(&e1));
+    double res[2] = {0, 0};
+    for (int mode = 0; mode < 2; mode++) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; rep++) {
+            TG_CUDA_CHECK(cudaEventRecord(e0));
+            if (mode == 0) int_peak_kernel<0><<<grid, block>>>(d_out, iters, 12345u + rep);
+            else int_peak_kernel<1><<<grid, block>>>(d_out, iters, 12345u + rep);
+            TG_CUDA_CHECK(cudaEventRecord(e1));
+            TG_CUDA_CHECK(cudaEventSynchronize(e1));
+            float ms = 0;
+            TG_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep > 0 && ms < best) best = ms;
+        }
+        // per thread per iteration: 4 * 8 DPX ops (mode 0) or 4 * 8 (add + DPX) pairs (mode 1)
+        const double ops = (double)grid * block * (double)iters * 32.0;
+        res[mode] = ops / (best * 1e-3);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    if (dpx_lane_ops_per_s) *dpx_lane_ops_per_s = res[0];
+    if (iadd_lane_ops_per_s) *iadd_lane_ops_per_s = res[1];
+    return TG_OK;
+}

@@ -1,0 +1,965 @@
+// k-mer scan kernels for sm_100a (reference: source/tg_kmer.py).
+//
+//   pack_kernel        ASCII -> 2-bit codes + N-mask bit plane (the HBM layout of the reads)
+//   orient_kernel      reverse complement of flagged reads in the packed domain (tg_tel.py:265-266)
+//   scan_cov_kernel    union coverage of all k-mers of TWO k-mer lists in one pass:
+//                        MODE_COUNT   -> get_telomere_base_count   (tg_kmer.py:93-102)
+//                        MODE_DENSITY -> get_telomere_kmer_density (tg_kmer.py:66-90), uint8 window counts
+//   hits_*_kernel      get_nonoverlapping_kmer_hits (tg_kmer.py:173-230)
+//
+// Matching: one Aho-Corasick automaton per k-mer list, built over the REVERSED k-mers.  A thread walks
+// its chunk of positions right to left (after max_len-1 warm-up symbols), so the automaton reports at
+// position p exactly the k-mers that START at p.  re.finditer's leftmost-non-overlapping rule only
+// differs from "all occurrences" for k-mers that can overlap themselves ("bordered"); their candidate
+// starts go to a bitmap that one lane per k-mer resolves greedily, left to right, with the blocking
+// position carried from tile to tile (a CTA walks the tiles of a read in order).
+#include "tg_common.cuh"
+#include <string.h>
+#include <vector>
+#include <queue>
+#include <string>
+
+namespace {
+
+constexpr int SC_MAXK = 64;
+constexpr int SC_MAXLEN = 32;
+constexpr int SC_MAXSTATES = 2112;
+constexpr int SC_MAXBORD = 32;
+constexpr uint16_t SC_OUT_FLAG = 0x8000;
+
+struct KmerTable {
+    int32_t K, n_states, max_len, n_bord;
+    int32_t len[SC_MAXK];
+    int32_t bord_kmer[SC_MAXBORD];          // k-mer index of bordered slot b
+    int32_t bord_len[SC_MAXBORD];
+    uint64_t super[SC_MAXK];                // KMER_ISSUBSTRING[k] as a bit mask (k-mers containing k)
+    uint64_t lengt[SC_MAXLEN];              // lengt[d] = k-mers with len > d
+    uint64_t bord_mask;                     // bordered k-mers
+    uint64_t has_super_mask;                // k-mers with a non-empty super[]
+    uint16_t trans[SC_MAXSTATES * 4];       // next state (low 12 bits) | SC_OUT_FLAG
+    uint8_t out_len[SC_MAXSTATES];          // longest NON-bordered k-mer starting here (0 = none)
+    uint32_t out_bord[SC_MAXSTATES];        // bordered slots starting here
+    uint64_t out_mask[SC_MAXSTATES];        // all k-mers starting here
+};
+
+// ---- packed read access ---------------------------------------------------------------------------
+// codes: A=0 C=1 T=2 G=3 ((ascii >> 1) & 3); complement = code ^ 2.
+__device__ __forceinline__ uint32_t ascii_code(uint32_t c) { return (c >> 1) & 3u; }
+__device__ __forceinline__ bool ascii_is_acgt(uint32_t c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
+
+__device__ __forceinline__ int find_read(const int64_t *off, int n, int64_t base)
+{
+    int lo = 0, hi = n;                      // off[lo] <= base < off[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (off[mid] <= base) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256) pack_kernel(const uint8_t *__restrict__ ascii, const int64_t *__restrict__ base_off,
+                                                   const int32_t *__restrict__ len, int n_reads,
+                                                   uint32_t *__restrict__ pack2, uint32_t *__restrict__ nmask)
+{
+    const int64_t total = base_off[n_reads];
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g * 32 < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b0 = g * 32;
+        const int r = find_read(base_off, n_reads, b0);
+        const int64_t rel = b0 - base_off[r];
+        const int L = len[r];
+        const uint4 v0 = *reinterpret_cast<const uint4 *>(ascii + b0);
+        const uint4 v1 = *reinterpret_cast<const uint4 *>(ascii + b0 + 16);
+        const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        uint32_t p[2] = {0u, 0u}, m = 0u;
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+            const uint32_t c = (w[i >> 2] >> ((i & 3) * 8)) & 0xffu;
+            const bool ok = ascii_is_acgt(c) && (rel + i < L);
+            p[i >> 4] |= (ok ? ascii_code(c) : 0u) << ((i & 15) * 2);
+            m |= (ok ? 0u : 1u) << i;
+        }
+        pack2[g * 2] = p[0];
+        pack2[g * 2 + 1] = p[1];
+        nmask[g] = m;
+    }
+}
+
+__device__ __forceinline__ uint32_t base_code(const uint32_t *pack2, int64_t b) { return (pack2[b >> 4] >> ((b & 15) * 2)) & 3u; }
+__device__ __forceinline__ uint32_t base_isn(const uint32_t *nmask, int64_t b) { return (nmask[b >> 5] >> (b & 31)) & 1u; }
+
+__global__ void __launch_bounds__(256) orient_kernel(const uint32_t *__restrict__ pack2, const uint32_t *__restrict__ nmask,
+                                                     const int64_t *__restrict__ base_off, const int32_t *__restrict__ len,
+                                                     const uint8_t *__restrict__ flip, int n_reads,
+                                                     uint32_t *__restrict__ pack2_out, uint32_t *__restrict__ nmask_out)
+{
+    const int64_t total = base_off[n_reads];
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g * 32 < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b0 = g * 32;
+        const int r = find_read(base_off, n_reads, b0);
+        if (!flip[r]) {
+            pack2_out[g * 2] = pack2[g * 2];
+            pack2_out[g * 2 + 1] = pack2[g * 2 + 1];
+            nmask_out[g] = nmask[g];
+            continue;
+        }
+        const int64_t ro = base_off[r];
+        const int64_t rel = b0 - ro;
+        const int L = len[r];
+        uint32_t p[2] = {0u, 0u}, m = 0u;
+        for (int i = 0; i < 32; i++) {
+            const int64_t q = rel + i;               // oriented position
+            if (q < L) {
+                const int64_t src = ro + (L - 1 - q);
+                const uint32_t isn = base_isn(nmask, src);
+                p[i >> 4] |= (isn ? 0u : (base_code(pack2, src) ^ 2u)) << ((i & 15) * 2);
+                m |= isn << i;
+            } else m |= 1u << i;
+        }
+        pack2_out[g * 2] = p[0];
+        pack2_out[g * 2 + 1] = p[1];
+        nmask_out[g] = m;
+    }
+}
+
+// ---- shared pieces of the tile kernels -----------------------------------------------------------
+// Stage bases [t0, t0 + n_bases) of a read (absolute base index = rbase + position) into shared memory;
+// positions outside [lo, hi) are forced to N.  n_bases is a multiple of 32, t0 a multiple of 32.
+__device__ __forceinline__ void stage_tile(const uint32_t *__restrict__ pack2, const uint32_t *__restrict__ nmask, int64_t rbase,
+                                           int64_t padded_len, int t0, int n_bases, int lo, int hi,
+                                           uint32_t *s_pack, uint32_t *s_mask)
+{
+    for (int w = threadIdx.x; w < n_bases / 32; w += blockDim.x) {
+        const int p0 = t0 + w * 32;                               // first position of this mask word
+        uint32_t m = 0xffffffffu, a = 0u, b = 0u;
+        if (p0 >= 0 && p0 < padded_len) {
+            const int64_t g = (rbase + p0) >> 5;
+            m = nmask[g];
+            a = pack2[g * 2];
+            b = pack2[g * 2 + 1];
+        }
+        // clip to [lo, hi)
+        if (p0 < lo) m |= (lo - p0 >= 32) ? 0xffffffffu : ((1u << (lo - p0)) - 1u);
+        if (p0 + 32 > hi) m |= (hi <= p0) ? 0xffffffffu : ~((1u << (hi - p0)) - 1u);
+        s_mask[w] = m;
+        s_pack[w * 2] = a;
+        s_pack[w * 2 + 1] = b;
+    }
+}
+
+__device__ __forceinline__ void smem_byte_max(uint8_t *arr, int idx, uint32_t val)
+{
+    uint32_t *word = reinterpret_cast<uint32_t *>(arr + (idx & ~3));
+    const int sh = (idx & 3) * 8;
+    uint32_t old = *word;
+    for (;;) {
+        if (((old >> sh) & 0xffu) >= val) return;
+        const uint32_t assumed = old;
+        old = atomicCAS(word, assumed, (assumed & ~(0xffu << sh)) | (val << sh));
+        if (old == assumed) return;
+    }
+}
+
+// Device-side view of one automaton held in shared memory.
+struct SmemTable {
+    const uint16_t *trans;
+    const uint8_t *out_len;
+    const uint32_t *out_bord;
+    const uint64_t *out_mask;     // only in hits mode
+    int max_len, n_bord;
+};
+
+__device__ __forceinline__ uint8_t *carve(uint8_t *&p, size_t bytes)
+{
+    uint8_t *r = p;
+    p += (bytes + 15) & ~(size_t)15;
+    return r;
+}
+
+__device__ SmemTable load_table(const KmerTable *__restrict__ T, uint8_t *&sp, bool want_mask)
+{
+    const int ns = T->n_states;
+    uint16_t *tr = reinterpret_cast<uint16_t *>(carve(sp, (size_t)ns * 4 * sizeof(uint16_t)));
+    uint8_t *ol = carve(sp, ns);
+    uint32_t *ob = reinterpret_cast<uint32_t *>(carve(sp, (size_t)ns * sizeof(uint32_t)));
+    uint64_t *om = want_mask ? reinterpret_cast<uint64_t *>(carve(sp, (size_t)ns * sizeof(uint64_t))) : nullptr;
+    for (int i = threadIdx.x; i < ns * 4; i += blockDim.x) tr[i] = T->trans[i];
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+        ol[i] = T->out_len[i];
+        ob[i] = T->out_bord[i];
+        if (want_mask) om[i] = T->out_mask[i];
+    }
+    SmemTable S;
+    S.trans = tr; S.out_len = ol; S.out_bord = ob; S.out_mask = om;
+    S.max_len = T->max_len; S.n_bord = T->n_bord;
+    return S;
+}
+
+// ---- coverage kernel (base count / density) -------------------------------------------------------
+constexpr int COV_THREADS = 128;
+constexpr int COV_CH = 64;                          // positions per thread
+constexpr int COV_TILE = COV_THREADS * COV_CH;      // 8192
+constexpr int COV_LAG = 256;                        // density output lags the tile by this many positions (>= window)
+constexpr int COV_STAGE = COV_TILE + 64;            // staged bases per tile (tile + right halo)
+enum { MODE_COUNT = 0, MODE_DENSITY = 1 };
+
+struct CovParams {
+    const uint32_t *pack2, *nmask;
+    const int64_t *base_off;
+    const int32_t *len;
+    int n_reads;
+    const KmerTable *tab[2];
+    int window;
+    uint8_t *cnt[2];
+    int32_t *counts;
+    unsigned int *next_read;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(COV_THREADS) scan_cov_kernel(const CovParams P)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t *sp = smem;
+    SmemTable tab[2];
+    tab[0] = load_table(P.tab[0], sp, false);
+    tab[1] = load_table(P.tab[1], sp, false);
+    uint32_t *s_pack = reinterpret_cast<uint32_t *>(carve(sp, COV_STAGE / 16 * 4));
+    uint32_t *s_mask = reinterpret_cast<uint32_t *>(carve(sp, COV_STAGE / 32 * 4));
+    uint8_t *s_L[2];
+    uint32_t *s_cov[2], *s_bm[2];
+    for (int s = 0; s < 2; s++) {
+        s_L[s] = carve(sp, COV_TILE);
+        s_cov[s] = reinterpret_cast<uint32_t *>(carve(sp, (COV_LAG + COV_TILE) / 32 * 4));
+        s_bm[s] = reinterpret_cast<uint32_t *>(carve(sp, (size_t)max(tab[s].n_bord, 1) * (COV_TILE / 32) * 4));
+    }
+    __shared__ int s_blocked[2][SC_MAXBORD];
+    __shared__ int s_any[2][SC_MAXBORD];
+    __shared__ int s_carry[2];
+    __shared__ int s_wmax[2][COV_THREADS / 32];
+    __shared__ int s_red[2][COV_THREADS / 32];
+    __shared__ unsigned int s_read;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_read = atomicAdd(P.next_read, 1u);
+        __syncthreads();
+        const int r = (int)s_read;
+        if (r >= P.n_reads) break;
+        const int64_t rbase = P.base_off[r];
+        const int L = P.len[r];
+        const int64_t padded = P.base_off[r + 1] - rbase;
+        const int w = P.window;
+        const int n_out = (MODE == MODE_DENSITY) ? max(L - w, 0) : 0;
+        const int span = (MODE == MODE_DENSITY) ? (n_out > 0 ? n_out + COV_LAG : 0) : L;
+        const int n_tiles = (span + COV_TILE - 1) / COV_TILE;
+        if (tid < SC_MAXBORD) { s_blocked[0][tid] = 0; s_blocked[1][tid] = 0; }
+        if (tid < 2) s_carry[tid] = 0;
+        for (int s = 0; s < 2; s++)
+            for (int i = tid; i < COV_LAG / 32; i += COV_THREADS) s_cov[s][i] = 0u;
+        int my_count[2] = {0, 0};
+
+        for (int tile = 0; tile < n_tiles; tile++) {
+            const int t0 = tile * COV_TILE;
+            __syncthreads();
+            stage_tile(P.pack2, P.nmask, rbase, padded, t0, COV_STAGE, 0, L, s_pack, s_mask);
+            for (int s = 0; s < 2; s++) {
+                for (int i = tid; i < tab[s].n_bord * (COV_TILE / 32); i += COV_THREADS) s_bm[s][i] = 0u;
+                if (tid < SC_MAXBORD) s_any[s][tid] = 0;
+            }
+            __syncthreads();
+
+            // ---- phase B: automata, right to left over [c0, c0 + CH + max_len - 1) ----
+            {
+                const int c0 = tid * COV_CH;                          // tile-relative
+                for (int s = 0; s < 2; s++) {
+                    const SmemTable &T = tab[s];
+                    uint32_t state = 0;
+                    uint32_t lbuf = 0;                                // 4 L bytes being assembled
+                    for (int x = c0 + COV_CH + T.max_len - 2; x >= c0; x--) {
+                        const uint32_t isn = (s_mask[x >> 5] >> (x & 31)) & 1u;
+                        const uint32_t code = (s_pack[x >> 4] >> ((x & 15) * 2)) & 3u;
+                        uint32_t e = isn ? 0u : (uint32_t)T.trans[state * 4 + code];
+                        state = e & 0xfffu;
+                        if (x < c0 + COV_CH) {
+                            uint32_t Lh = 0;
+                            if (e & SC_OUT_FLAG) {
+                                Lh = T.out_len[state];
+                                uint32_t ob = T.out_bord[state];
+                                while (ob) {
+                                    const int b = __ffs(ob) - 1;
+                                    ob &= ob - 1;
+                                    atomicOr(&s_bm[s][b * (COV_TILE / 32) + (x >> 5)], 1u << (x & 31));
+                                    s_any[s][b] = 1;
+                                }
+                            }
+                            lbuf = (lbuf << 8) | Lh;                  // x descending: byte 0 ends up = lowest x
+                            if ((x & 3) == 0) { *reinterpret_cast<uint32_t *>(s_L[s] + x) = lbuf; lbuf = 0; }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+
+            // ---- phase C: greedy resolution of bordered k-mers (one lane per (list, slot)) ----
+            if (warp == 0) {
+                for (int slot = lane; slot < tab[0].n_bord + tab[1].n_bord; slot += 32) {
+                    const int s = slot < tab[0].n_bord ? 0 : 1;
+                    const int b = s == 0 ? slot : slot - tab[0].n_bord;
+                    if (!s_any[s][b]) continue;
+                    const int blen = P.tab[s]->bord_len[b];
+                    int blocked = s_blocked[s][b];
+                    const uint32_t *bm = s_bm[s] + b * (COV_TILE / 32);
+                    for (int wd = 0; wd < COV_TILE / 32; wd++) {
+                        uint32_t word = bm[wd];
+                        while (word) {
+                            const int bit = __ffs(word) - 1;
+                            word &= word - 1;
+                            const int p = t0 + wd * 32 + bit;
+                            if (p >= blocked) {
+                                blocked = p + blen;
+                                smem_byte_max(s_L[s], wd * 32 + bit, (uint32_t)blen);
+                            }
+                        }
+                    }
+                    s_blocked[s][b] = blocked;
+                }
+            }
+            __syncthreads();
+
+            // ---- phase D: coverage = prefix max of (p + L[p]) ----
+            {
+                const int c0 = tid * COV_CH;
+                int lm[2];
+                for (int s = 0; s < 2; s++) {
+                    int m = 0;
+                    for (int i = 0; i < COV_CH; i++) {
+                        const int Lh = s_L[s][c0 + i];
+                        if (Lh) m = max(m, t0 + c0 + i + Lh);
+                    }
+                    lm[s] = m;
+                }
+                int inc[2] = {lm[0], lm[1]};
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v0 = __shfl_up_sync(TG_FULL_MASK, inc[0], o);
+                    const int v1 = __shfl_up_sync(TG_FULL_MASK, inc[1], o);
+                    if (lane >= o) { inc[0] = max(inc[0], v0); inc[1] = max(inc[1], v1); }
+                }
+                if (lane == 31) { s_wmax[0][warp] = inc[0]; s_wmax[1][warp] = inc[1]; }
+                int ex[2];
+                ex[0] = __shfl_up_sync(TG_FULL_MASK, inc[0], 1);
+                ex[1] = __shfl_up_sync(TG_FULL_MASK, inc[1], 1);
+                if (lane == 0) { ex[0] = 0; ex[1] = 0; }
+                __syncthreads();
+                for (int s = 0; s < 2; s++) {
+                    int e = max(ex[s], s_carry[s]);
+                    for (int wq = 0; wq < warp; wq++) e = max(e, s_wmax[s][wq]);
+                    uint32_t cw[2] = {0u, 0u};
+                    for (int i = 0; i < COV_CH; i++) {
+                        const int p = t0 + c0 + i;
+                        const int Lh = s_L[s][c0 + i];
+                        if (Lh) e = max(e, p + Lh);
+                        if (e > p) cw[i >> 5] |= 1u << (i & 31);
+                    }
+                    s_cov[s][(COV_LAG + c0) / 32] = cw[0];
+                    s_cov[s][(COV_LAG + c0) / 32 + 1] = cw[1];
+                    if (MODE == MODE_COUNT) my_count[s] += __popc(cw[0]) + __popc(cw[1]);
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    for (int s = 0; s < 2; s++) {
+                        int e = s_carry[s];
+                        for (int wq = 0; wq < COV_THREADS / 32; wq++) e = max(e, s_wmax[s][wq]);
+                        s_carry[s] = e;
+                    }
+                }
+            }
+
+            // ---- phase E: window counts for outputs i in [t0 - LAG, t0 + TILE - LAG) ----
+            if (MODE == MODE_DENSITY) {
+                // bit j of s_cov <-> position t0 - LAG + j
+                const int j0 = tid * COV_CH;                         // first output of this thread (bit index)
+                const int i0 = t0 - COV_LAG + j0;                    // its read position
+                if (i0 + COV_CH > 0 && i0 < n_out) {
+                    for (int s = 0; s < 2; s++) {
+                        const uint32_t *cv = s_cov[s];
+                        // cnt(i0) = popcount of bits [j0 + 1, j0 + w]
+                        int cnt = 0;
+                        {
+                            const int lo = j0 + 1, hi = j0 + w;       // inclusive
+                            for (int wd = lo >> 5; wd <= (hi >> 5); wd++) {
+                                uint32_t v = cv[wd];
+                                if (wd == (lo >> 5)) v &= 0xffffffffu << (lo & 31);
+                                if (wd == (hi >> 5)) v &= 0xffffffffu >> (31 - (hi & 31));
+                                cnt += __popc(v);
+                            }
+                        }
+                        uint32_t outw[COV_CH / 4];
+#pragma unroll
+                        for (int q = 0; q < COV_CH / 4; q++) outw[q] = 0u;
+#pragma unroll
+                        for (int ii = 0; ii < COV_CH; ii++) {
+                            outw[ii >> 2] |= (uint32_t)cnt << ((ii & 3) * 8);
+                            const int ja = j0 + ii + 1, jb = j0 + ii + w + 1;     // leaving / entering bit
+                            cnt += (int)((cv[jb >> 5] >> (jb & 31)) & 1u) - (int)((cv[ja >> 5] >> (ja & 31)) & 1u);
+                        }
+                        uint8_t *dst = P.cnt[s] + rbase + i0;
+#pragma unroll
+                        for (int q = 0; q < COV_CH / 16; q++) {
+                            const int ig = i0 + q * 16;
+                            if (ig >= 0 && ig < padded)
+                                *reinterpret_cast<uint4 *>(dst + q * 16) = make_uint4(outw[q * 4], outw[q * 4 + 1], outw[q * 4 + 2], outw[q * 4 + 3]);
+                        }
+                    }
+                }
+                __syncthreads();
+                // keep the last LAG positions of the coverage for the next tile
+                uint32_t keep[2] = {0u, 0u};
+                if (tid < COV_LAG / 32) { keep[0] = s_cov[0][COV_TILE / 32 + tid]; keep[1] = s_cov[1][COV_TILE / 32 + tid]; }
+                __syncthreads();
+                if (tid < COV_LAG / 32) { s_cov[0][tid] = keep[0]; s_cov[1][tid] = keep[1]; }
+            }
+        }
+
+        if (MODE == MODE_COUNT) {
+            for (int s = 0; s < 2; s++) {
+                int v = my_count[s];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(TG_FULL_MASK, v, o);
+                if (lane == 0) s_red[s][warp] = v;
+            }
+            __syncthreads();
+            if (tid < 2) {
+                int v = 0;
+                for (int wq = 0; wq < COV_THREADS / 32; wq++) v += s_red[tid][wq];
+                P.counts[2 * r + tid] = v;
+            }
+        }
+    }
+}
+
+// ---- non-overlapping hits -------------------------------------------------------------------------
+constexpr int HIT_THREADS = 128;
+constexpr int HIT_CH = 16;
+constexpr int HIT_TILE = HIT_THREADS * HIT_CH;      // 2048
+constexpr int HIT_HALO = 32;
+constexpr int HIT_SPAN = HIT_TILE + 2 * HIT_HALO;   // hm / C cover [t0 - 32, t0 + TILE + 32)
+constexpr int HIT_STAGE = HIT_TILE + 2 * HIT_HALO;  // staged bases [t0, t0 + TILE + 64)
+
+struct HitParams {
+    const uint32_t *pack2, *nmask;
+    const int64_t *base_off;
+    const int32_t *slice_read, *slice_lo, *slice_hi;
+    int n_slices;
+    const int64_t *work_off;
+    const KmerTable *tab;
+    uint64_t *S;                 // survivors per work position
+    uint32_t *B;                 // block-start bitmap per work position
+    int64_t total_work;
+    int32_t *span_slice, *span_k, *span_start, *span_end;
+    long long span_cap;
+    unsigned long long *span_count;
+    unsigned int *next_slice;
+};
+
+// H1: selected raw matches -> superstring deletion -> survivors S[x] (tg_kmer.py:175-202)
+__global__ void __launch_bounds__(HIT_THREADS) hits_survivors_kernel(const HitParams P)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t *sp = smem;
+    SmemTable T = load_table(P.tab, sp, true);
+    uint32_t *s_pack = reinterpret_cast<uint32_t *>(carve(sp, HIT_STAGE / 16 * 4));
+    uint32_t *s_mask = reinterpret_cast<uint32_t *>(carve(sp, HIT_STAGE / 32 * 4));
+    unsigned long long *s_hm = reinterpret_cast<unsigned long long *>(carve(sp, (size_t)HIT_SPAN * 8));   // index = x - t0 + HALO
+    unsigned long long *s_C = reinterpret_cast<unsigned long long *>(carve(sp, (size_t)HIT_SPAN * 8));
+    uint32_t *s_bm = reinterpret_cast<uint32_t *>(carve(sp, (size_t)max(T.n_bord, 1) * ((HIT_TILE + HIT_HALO) / 32) * 4));
+    __shared__ int s_blocked[SC_MAXBORD];
+    __shared__ int s_any[SC_MAXBORD];
+    __shared__ unsigned long long s_super[SC_MAXK], s_lengt[SC_MAXLEN];
+    __shared__ int s_len[SC_MAXK];
+    __shared__ unsigned int s_slice;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int BMW = (HIT_TILE + HIT_HALO) / 32;     // bitmap words per bordered slot: positions [t0, t0 + TILE + 32)
+    if (tid < SC_MAXK) { s_super[tid] = P.tab->super[tid]; s_len[tid] = P.tab->len[tid]; }
+    if (tid < SC_MAXLEN) s_lengt[tid] = P.tab->lengt[tid];
+    const unsigned long long has_super = P.tab->has_super_mask;
+    const unsigned long long bord_mask = P.tab->bord_mask;
+    const int max_len = T.max_len;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_slice = atomicAdd(P.next_slice, 1u);
+        __syncthreads();
+        const int q = (int)s_slice;
+        if (q >= P.n_slices) break;
+        const int r = P.slice_read[q];
+        const int lo = P.slice_lo[q], hi = P.slice_hi[q];
+        const int len = hi - lo;
+        const int64_t rbase = P.base_off[r];
+        const int64_t padded = P.base_off[r + 1] - rbase;
+        const int64_t woff = P.work_off[q];
+        const int wlen = (int)(P.work_off[q + 1] - woff);        // padded to 64
+        const int n_tiles = (wlen + HIT_TILE - 1) / HIT_TILE;
+        if (tid < SC_MAXBORD) s_blocked[tid] = 0;
+        for (int i = tid; i < HIT_HALO; i += HIT_THREADS) s_hm[i] = 0ull;      // left halo of the first tile
+
+        for (int tile = 0; tile < n_tiles; tile++) {
+            const int t0 = tile * HIT_TILE;                     // slice-relative
+            __syncthreads();
+            // stage slice positions [t0, t0 + STAGE): read positions lo + t0 ...; lo may be unaligned -> stage per base
+            // (slices are short; simplicity over speed): build aligned words from the read's packed planes
+            for (int wq = tid; wq < HIT_STAGE / 32; wq += HIT_THREADS) {
+                uint32_t m = 0u, a = 0u, b = 0u;
+                for (int i = 0; i < 32; i++) {
+                    const int x = t0 + wq * 32 + i;             // slice-relative
+                    const int64_t rp = (int64_t)lo + x;         // read-relative
+                    uint32_t isn = 1u, code = 0u;
+                    if (x < len && rp < padded) {
+                        isn = base_isn(P.nmask, rbase + rp);
+                        code = isn ? 0u : base_code(P.pack2, rbase + rp);
+                    }
+                    m |= isn << i;
+                    if (i < 16) a |= code << (i * 2); else b |= code << ((i - 16) * 2);
+                }
+                s_mask[wq] = m; s_pack[wq * 2] = a; s_pack[wq * 2 + 1] = b;
+            }
+            for (int i = tid; i < T.n_bord * BMW; i += HIT_THREADS) s_bm[i] = 0u;
+            if (tid < SC_MAXBORD) s_any[tid] = 0;
+            __syncthreads();
+
+            // ---- automaton over [t0, t0 + TILE + HALO): hm = all k-mers starting at x ----
+            {
+                // TILE + HALO positions over 128 threads: 16 each + the first 2 warps... keep it simple:
+                // thread t handles [c0, c0 + HIT_CH); threads < HALO / HIT_CH additionally handle the halo chunk
+                for (int pass = 0; pass < 2; pass++) {
+                    int c0;
+                    if (pass == 0) c0 = tid * HIT_CH;
+                    else { if (tid >= HIT_HALO / HIT_CH) break; c0 = HIT_TILE + tid * HIT_CH; }
+                    uint32_t state = 0;
+                    for (int x = c0 + HIT_CH + max_len - 2; x >= c0; x--) {
+                        uint32_t e = 0u;
+                        if (x < HIT_STAGE) {
+                            const uint32_t isn = (s_mask[x >> 5] >> (x & 31)) & 1u;
+                            const uint32_t code = (s_pack[x >> 4] >> ((x & 15) * 2)) & 3u;
+                            e = isn ? 0u : (uint32_t)T.trans[state * 4 + code];
+                        }
+                        state = e & 0xfffu;
+                        if (x < c0 + HIT_CH) {
+                            unsigned long long hm = 0ull;
+                            if (e & SC_OUT_FLAG) {
+                                hm = T.out_mask[state];
+                                uint32_t ob = T.out_bord[state];
+                                while (ob) {
+                                    const int b = __ffs(ob) - 1;
+                                    ob &= ob - 1;
+                                    atomicOr(&s_bm[b * BMW + (x >> 5)], 1u << (x & 31));
+                                    s_any[b] = 1;
+                                }
+                            }
+                            s_hm[HIT_HALO + x] = hm;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+
+            // ---- greedy resolution of bordered k-mers; unselected candidates are cleared from hm ----
+            if (warp == 0) {
+                for (int b = lane; b < T.n_bord; b += 32) {
+                    if (!s_any[b]) continue;
+                    const int blen = P.tab->bord_len[b];
+                    const unsigned long long kbit = 1ull << P.tab->bord_kmer[b];
+                    int blocked = s_blocked[b];
+                    int carry = -1;
+                    for (int wd = 0; wd < BMW; wd++) {
+                        uint32_t word = s_bm[b * BMW + wd];
+                        if (wd == HIT_TILE / 32 && carry < 0) carry = blocked;      // state at the tile boundary
+                        while (word) {
+                            const int bit = __ffs(word) - 1;
+                            word &= word - 1;
+                            const int x = wd * 32 + bit;
+                            const int p = t0 + x;
+                            if (p >= blocked) blocked = p + blen;
+                            else atomicAnd(&s_hm[HIT_HALO + x], ~kbit);
+                        }
+                    }
+                    s_blocked[b] = carry < 0 ? blocked : carry;
+                }
+            }
+            __syncthreads();
+
+            // ---- C[y] = k-mers whose selected matches cover y, y in [t0, t0 + TILE + HALO) ----
+            for (int y = tid; y < HIT_TILE + HIT_HALO; y += HIT_THREADS) {
+                unsigned long long c = 0ull;
+                for (int d = 0; d < max_len; d++) c |= s_hm[HIT_HALO + y - d] & s_lengt[d];
+                s_C[HIT_HALO + y] = c;
+            }
+            __syncthreads();
+
+            // ---- survivors: drop (k, x) if a superstring k-mer covers any of [x, x + len_k) ----
+            for (int x = tid; x < HIT_TILE; x += HIT_THREADS) {
+                unsigned long long hm = s_hm[HIT_HALO + x];
+                unsigned long long cand = hm & has_super;
+                while (cand) {
+                    const int k = __ffsll((long long)cand) - 1;
+                    cand &= cand - 1;
+                    unsigned long long cover = 0ull;
+                    const int lk = s_len[k];
+                    for (int y = x; y < x + lk; y++) cover |= s_C[HIT_HALO + y];
+                    if (cover & s_super[k]) hm &= ~(1ull << k);
+                }
+                if (t0 + x < wlen) P.S[woff + t0 + x] = hm;
+            }
+            __syncthreads();
+            // carry the last HALO positions of hm as the next tile's left halo
+            unsigned long long keep = 0ull;
+            if (tid < HIT_HALO) keep = s_hm[HIT_TILE + tid];
+            __syncthreads();
+            if (tid < HIT_HALO) s_hm[tid] = keep;
+        }
+    }
+    (void)bord_mask;
+}
+
+// H2: block starts after collapsing abutting same-k-mer survivors (tg_kmer.py:206-212)
+__global__ void __launch_bounds__(256) hits_blockstart_kernel(const HitParams P)
+{
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < P.total_work; g += (int64_t)gridDim.x * blockDim.x) {
+        const int q = find_read(P.work_off, P.n_slices, g);
+        const int x = (int)(g - P.work_off[q]);
+        unsigned long long s = P.S[g];
+        bool start = false;
+        while (s) {
+            const int k = __ffsll((long long)s) - 1;
+            s &= s - 1;
+            const int lk = P.tab->len[k];
+            if (x - lk < 0 || !((P.S[g - lk] >> k) & 1ull)) start = true;
+        }
+        const uint32_t bal = __ballot_sync(TG_FULL_MASK, start);
+        if ((threadIdx.x & 31) == 0) P.B[g >> 5] = bal;
+    }
+}
+
+// H3: walk each block to its end, truncate at the next block start of any k-mer (tg_kmer.py:216-228), emit
+__global__ void __launch_bounds__(256) hits_emit_kernel(const HitParams P)
+{
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < P.total_work; g += (int64_t)gridDim.x * blockDim.x) {
+        unsigned long long s = P.S[g];
+        if (!s) continue;
+        const int q = find_read(P.work_off, P.n_slices, g);
+        const int64_t woff = P.work_off[q];
+        const int x = (int)(g - woff);
+        const int wlen = (int)(P.work_off[q + 1] - woff);
+        int next_start = -2;                                        // lazily computed
+        while (s) {
+            const int k = __ffsll((long long)s) - 1;
+            s &= s - 1;
+            const int lk = P.tab->len[k];
+            if (x - lk >= 0 && ((P.S[g - lk] >> k) & 1ull)) continue;      // not a block start
+            int e = x + lk;
+            while (e < wlen && ((P.S[woff + e] >> k) & 1ull)) e += lk;
+            if (next_start == -2) {
+                next_start = -1;
+                // first set bit of B strictly after x (within this slice)
+                int wd = (x + 1) >> 5;
+                const int wend = wlen >> 5;
+                uint32_t v = (wd < wend) ? (P.B[(woff >> 5) + wd] & (0xffffffffu << ((x + 1) & 31))) : 0u;
+                while (wd < wend) {
+                    if (v) { next_start = wd * 32 + __ffs(v) - 1; break; }
+                    wd++;
+                    if (wd < wend) v = P.B[(woff >> 5) + wd];
+                }
+            }
+            if (next_start >= 0 && next_start < e) e = next_start;
+            const unsigned long long slot = atomicAdd(P.span_count, 1ULL);
+            if ((long long)slot < P.span_cap) {
+                P.span_slice[slot] = q; P.span_k[slot] = k; P.span_start[slot] = x; P.span_end[slot] = e;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+// ================================================================================================
+// host: table construction
+// ================================================================================================
+TG_EXPORT size_t tg_kmer_table_bytes(void) { return sizeof(KmerTable); }
+
+static int code_of(char c)
+{
+    switch (c) { case 'A': return 0; case 'C': return 1; case 'T': return 2; case 'G': return 3; default: return -1; }
+}
+
+TG_EXPORT int tg_kmer_table_build(const char *kmers_concat, const int32_t *kmer_off, int K,
+                                  const int32_t *issub_edges, const int32_t *issub_off, void *h_table)
+{
+    if (!kmers_concat || !kmer_off || !h_table) return tg_set_err(TG_EINVAL, "NULL argument");
+    if (K < 1 || K > SC_MAXK) return tg_set_err(TG_EINVAL, "K=%d outside 1..%d", K, SC_MAXK);
+    KmerTable *T = reinterpret_cast<KmerTable *>(h_table);
+    memset(T, 0, sizeof(KmerTable));
+    T->K = K;
+    std::vector<std::string> km(K);
+    int max_len = 0;
+    for (int k = 0; k < K; k++) {
+        const int l = kmer_off[k + 1] - kmer_off[k];
+        if (l < 1 || l > SC_MAXLEN) return tg_set_err(TG_EINVAL, "k-mer %d has length %d outside 1..%d", k, l, SC_MAXLEN);
+        km[k].assign(kmers_concat + kmer_off[k], l);
+        for (char c : km[k]) if (code_of(c) < 0) return tg_set_err(TG_EINVAL, "k-mer %d contains a non-ACGT character", k);
+        T->len[k] = l;
+        if (l > max_len) max_len = l;
+        for (int d = 0; d < l; d++) T->lengt[d] |= 1ull << k;
+    }
+    T->max_len = max_len;
+    // bordered k-mers: some shift 0 < d < len maps the k-mer onto itself
+    for (int k = 0; k < K; k++) {
+        const std::string &s = km[k];
+        bool bordered = false;
+        for (size_t d = 1; d < s.size() && !bordered; d++) bordered = (s.compare(d, std::string::npos, s, 0, s.size() - d) == 0);
+        if (bordered) {
+            if (T->n_bord >= SC_MAXBORD) return tg_set_err(TG_EINVAL, "more than %d self-overlapping k-mers", SC_MAXBORD);
+            T->bord_kmer[T->n_bord] = k;
+            T->bord_len[T->n_bord] = (int)s.size();
+            T->bord_mask |= 1ull << k;
+            T->n_bord++;
+        }
+    }
+    if (issub_edges && issub_off)
+        for (int k = 0; k < K; k++) {
+            for (int e = issub_off[k]; e < issub_off[k + 1]; e++) {
+                if (issub_edges[e] < 0 || issub_edges[e] >= K) return tg_set_err(TG_EINVAL, "bad KMER_ISSUBSTRING edge");
+                T->super[k] |= 1ull << issub_edges[e];
+            }
+            if (T->super[k]) T->has_super_mask |= 1ull << k;
+        }
+    // Aho-Corasick over the reversed k-mers
+    struct Node { int next[4]; int fail; uint64_t out; };
+    std::vector<Node> nodes(1);
+    nodes[0] = Node{{-1, -1, -1, -1}, 0, 0ull};
+    for (int k = 0; k < K; k++) {
+        int cur = 0;
+        for (int i = (int)km[k].size() - 1; i >= 0; i--) {
+            const int c = code_of(km[k][i]);
+            if (nodes[cur].next[c] < 0) {
+                nodes[cur].next[c] = (int)nodes.size();
+                nodes.push_back(Node{{-1, -1, -1, -1}, 0, 0ull});
+            }
+            cur = nodes[cur].next[c];
+        }
+        nodes[cur].out |= 1ull << k;
+    }
+    if ((int)nodes.size() > SC_MAXSTATES) return tg_set_err(TG_EINVAL, "automaton has %d states (max %d)", (int)nodes.size(), SC_MAXSTATES);
+    std::queue<int> bfs;
+    for (int c = 0; c < 4; c++) {
+        int v = nodes[0].next[c];
+        if (v < 0) nodes[0].next[c] = 0;
+        else { nodes[v].fail = 0; bfs.push(v); }
+    }
+    while (!bfs.empty()) {
+        const int u = bfs.front(); bfs.pop();
+        nodes[u].out |= nodes[nodes[u].fail].out;
+        for (int c = 0; c < 4; c++) {
+            const int v = nodes[u].next[c];
+            if (v < 0) nodes[u].next[c] = nodes[nodes[u].fail].next[c];
+            else { nodes[v].fail = nodes[nodes[u].fail].next[c]; bfs.push(v); }
+        }
+    }
+    // BFS order guarantees fail(u) was finalised before u, but out of children was merged when popped: recompute in order
+    T->n_states = (int)nodes.size();
+    for (int s = 0; s < T->n_states; s++) {
+        T->out_mask[s] = nodes[s].out;
+        int best = 0; uint32_t ob = 0;
+        for (int k = 0; k < K; k++)
+            if ((nodes[s].out >> k) & 1ull) {
+                if ((T->bord_mask >> k) & 1ull) { for (int b = 0; b < T->n_bord; b++) if (T->bord_kmer[b] == k) ob |= 1u << b; }
+                else if (T->len[k] > best) best = T->len[k];
+            }
+        T->out_len[s] = (uint8_t)best;
+        T->out_bord[s] = ob;
+    }
+    for (int s = 0; s < T->n_states; s++)
+        for (int c = 0; c < 4; c++) {
+            const int v = nodes[s].next[c];
+            T->trans[s * 4 + c] = (uint16_t)(v | (nodes[v].out ? SC_OUT_FLAG : 0));
+        }
+    return TG_OK;
+}
+
+// ================================================================================================
+// launches
+// ================================================================================================
+static int grid_for(int64_t items, int block, int sms, int per_sm)
+{
+    int64_t g = (items + block - 1) / block;
+    const int64_t cap = (int64_t)sms * per_sm;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+// host copies of the per-list sizes are needed to size shared memory: read them back once per call
+static int table_dims(const void *d_table, int *n_states, int *n_bord, cudaStream_t st)
+{
+    int32_t hdr[4];
+    TG_CUDA_CHECK(cudaMemcpyAsync(hdr, d_table, sizeof(hdr), cudaMemcpyDeviceToHost, st));
+    TG_CUDA_CHECK(cudaStreamSynchronize(st));
+    *n_states = hdr[1];
+    *n_bord = hdr[3];
+    if (hdr[1] < 1 || hdr[1] > SC_MAXSTATES || hdr[3] < 0 || hdr[3] > SC_MAXBORD) return tg_set_err(TG_EINVAL, "corrupt k-mer table");
+    return TG_OK;
+}
+
+static size_t table_smem(int n_states, bool want_mask)
+{
+    auto up = [](size_t b) { return (b + 15) & ~(size_t)15; };
+    return up((size_t)n_states * 8) + up(n_states) + up((size_t)n_states * 4) + (want_mask ? up((size_t)n_states * 8) : 0);
+}
+
+TG_EXPORT int tg_scan_pack(const uint8_t *d_ascii, const int64_t *d_base_off, const int32_t *d_len, int n_reads,
+                           uint32_t *d_pack2, uint32_t *d_nmask, void *stream)
+{
+    if (n_reads <= 0) return TG_OK;
+    const int sms = tg_sm_count();
+    if (sms <= 0) return tg_set_err(TG_ECUDA, "no CUDA device");
+    pack_kernel<<<sms * 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_ascii, d_base_off, d_len, n_reads, d_pack2, d_nmask);
+    TG_CUDA_CHECK(cudaGetLastError());
+    return TG_OK;
+}
+
+TG_EXPORT int tg_scan_orient(const uint32_t *d_pack2, const uint32_t *d_nmask, const int64_t *d_base_off,
+                             const int32_t *d_len, const uint8_t *d_flip, int n_reads,
+                             uint32_t *d_pack2_out, uint32_t *d_nmask_out, void *stream)
+{
+    if (n_reads <= 0) return TG_OK;
+    const int sms = tg_sm_count();
+    if (sms <= 0) return tg_set_err(TG_ECUDA, "no CUDA device");
+    orient_kernel<<<sms * 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_pack2, d_nmask, d_base_off, d_len, d_flip, n_reads,
+                                                                                d_pack2_out, d_nmask_out);
+    TG_CUDA_CHECK(cudaGetLastError());
+    return TG_OK;
+}
+
+static thread_local unsigned int *g_counter = nullptr;     // device work counter (per host thread / device)
+static thread_local int g_counter_dev = -1;
+
+static int get_counter(unsigned int **out, cudaStream_t st)
+{
+    int dev = 0;
+    TG_CUDA_CHECK(cudaGetDevice(&dev));
+    if (!g_counter || g_counter_dev != dev) {
+        TG_CUDA_CHECK(cudaMalloc(&g_counter, 16));
+        g_counter_dev = dev;
+    }
+    TG_CUDA_CHECK(cudaMemsetAsync(g_counter, 0, 16, st));
+    *out = g_counter;
+    return TG_OK;
+}
+
+template <int MODE>
+static int launch_cov(const uint32_t *d_pack2, const uint32_t *d_nmask, const int64_t *d_base_off, const int32_t *d_len,
+                      int n_reads, const void *ta, const void *tb, int window, uint8_t *ca, uint8_t *cb, int32_t *counts, void *stream)
+{
+    if (n_reads <= 0) return TG_OK;
+    if (!d_pack2 || !d_nmask || !d_base_off || !d_len || !ta || !tb) return tg_set_err(TG_EINVAL, "NULL device pointer");
+    const int sms = tg_sm_count();
+    if (sms <= 0) return tg_set_err(TG_ECUDA, "no CUDA device");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int ns[2], nb[2];
+    int rc = table_dims(ta, &ns[0], &nb[0], st);
+    if (rc != TG_OK) return rc;
+    rc = table_dims(tb, &ns[1], &nb[1], st);
+    if (rc != TG_OK) return rc;
+    auto up = [](size_t b) { return (b + 15) & ~(size_t)15; };
+    size_t smem = table_smem(ns[0], false) + table_smem(ns[1], false) + up(COV_STAGE / 16 * 4) + up(COV_STAGE / 32 * 4);
+    for (int s = 0; s < 2; s++)
+        smem += up(COV_TILE) + up((COV_LAG + COV_TILE) / 32 * 4) + up((size_t)(nb[s] > 1 ? nb[s] : 1) * (COV_TILE / 32) * 4);
+    if (smem > 200 * 1024) return tg_set_err(TG_ERANGE, "k-mer tables too large for shared memory (%zu bytes)", smem);
+    CovParams P;
+    P.pack2 = d_pack2; P.nmask = d_nmask; P.base_off = d_base_off; P.len = d_len; P.n_reads = n_reads;
+    P.tab[0] = reinterpret_cast<const KmerTable *>(ta); P.tab[1] = reinterpret_cast<const KmerTable *>(tb);
+    P.window = window; P.cnt[0] = ca; P.cnt[1] = cb; P.counts = counts;
+    rc = get_counter(&P.next_read, st);
+    if (rc != TG_OK) return rc;
+    TG_CUDA_CHECK(cudaFuncSetAttribute(scan_cov_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = (int)((220 * 1024) / (smem + 2048));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    int grid = sms * per_sm;
+    if (grid > n_reads) grid = n_reads;
+    scan_cov_kernel<MODE><<<grid, COV_THREADS, smem, st>>>(P);
+    TG_CUDA_CHECK(cudaGetLastError());
+    return TG_OK;
+}
+
+TG_EXPORT int tg_scan_basecount(const uint32_t *d_pack2, const uint32_t *d_nmask, const int64_t *d_base_off,
+                                const int32_t *d_len, int n_reads, const void *d_table_a, const void *d_table_b,
+                                int32_t *d_counts, void *stream)
+{
+    if (!d_counts) return tg_set_err(TG_EINVAL, "d_counts is NULL");
+    return launch_cov<MODE_COUNT>(d_pack2, d_nmask, d_base_off, d_len, n_reads, d_table_a, d_table_b, 0, nullptr, nullptr, d_counts, stream);
+}
+
+TG_EXPORT int tg_scan_density(const uint32_t *d_pack2, const uint32_t *d_nmask, const int64_t *d_base_off,
+                              const int32_t *d_len, int n_reads, const void *d_table_a, const void *d_table_b,
+                              int window, uint8_t *d_cnt_a, uint8_t *d_cnt_b, void *stream)
+{
+    if (window < 1 || window > 255) return tg_set_err(TG_ERANGE, "window %d outside 1..255 (uint8 counts)", window);
+    if (!d_cnt_a || !d_cnt_b) return tg_set_err(TG_EINVAL, "output pointer is NULL");
+    return launch_cov<MODE_DENSITY>(d_pack2, d_nmask, d_base_off, d_len, n_reads, d_table_a, d_table_b, window, d_cnt_a, d_cnt_b, nullptr, stream);
+}
+
+TG_EXPORT size_t tg_scan_hits_work_bytes(int64_t total_work_bases, int n_slices)
+{
+    (void)n_slices;
+    const size_t t = (size_t)((total_work_bases + 63) / 64 * 64);
+    return t * 8 + t / 8 + 256;
+}
+
+TG_EXPORT int tg_scan_hits(const uint32_t *d_pack2, const uint32_t *d_nmask, const int64_t *d_base_off,
+                           const int32_t *d_slice_read, const int32_t *d_slice_lo, const int32_t *d_slice_hi, int n_slices,
+                           const int64_t *d_slice_work_off, int64_t total_work_bases, const void *d_table, void *d_work,
+                           int32_t *d_span_slice, int32_t *d_span_k, int32_t *d_span_start, int32_t *d_span_end,
+                           int64_t span_cap, unsigned long long *d_span_count, void *stream)
+{
+    if (n_slices <= 0) return TG_OK;
+    if (!d_pack2 || !d_nmask || !d_base_off || !d_slice_read || !d_slice_lo || !d_slice_hi || !d_slice_work_off || !d_table ||
+        !d_work || !d_span_slice || !d_span_k || !d_span_start || !d_span_end || !d_span_count)
+        return tg_set_err(TG_EINVAL, "NULL device pointer");
+    if (total_work_bases % 64) return tg_set_err(TG_EINVAL, "total_work_bases must be a multiple of 64");
+    const int sms = tg_sm_count();
+    if (sms <= 0) return tg_set_err(TG_ECUDA, "no CUDA device");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int ns, nb;
+    int rc = table_dims(d_table, &ns, &nb, st);
+    if (rc != TG_OK) return rc;
+    auto up = [](size_t b) { return (b + 15) & ~(size_t)15; };
+    const size_t smem = table_smem(ns, true) + up(HIT_STAGE / 16 * 4) + up(HIT_STAGE / 32 * 4) + 2 * up((size_t)HIT_SPAN * 8) +
+                        up((size_t)(nb > 1 ? nb : 1) * ((HIT_TILE + HIT_HALO) / 32) * 4);
+    if (smem > 200 * 1024) return tg_set_err(TG_ERANGE, "k-mer table too large for shared memory (%zu bytes)", smem);
+    HitParams P;
+    P.pack2 = d_pack2; P.nmask = d_nmask; P.base_off = d_base_off;
+    P.slice_read = d_slice_read; P.slice_lo = d_slice_lo; P.slice_hi = d_slice_hi; P.n_slices = n_slices;
+    P.work_off = d_slice_work_off; P.tab = reinterpret_cast<const KmerTable *>(d_table);
+    P.S = reinterpret_cast<uint64_t *>(d_work);
+    P.B = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(d_work) + (size_t)total_work_bases * 8);
+    P.total_work = total_work_bases;
+    P.span_slice = d_span_slice; P.span_k = d_span_k; P.span_start = d_span_start; P.span_end = d_span_end;
+    P.span_cap = span_cap; P.span_count = d_span_count;
+    rc = get_counter(&P.next_slice, st);
+    if (rc != TG_OK) return rc;
+    TG_CUDA_CHECK(cudaMemsetAsync(d_span_count, 0, sizeof(unsigned long long), st));
+    TG_CUDA_CHECK(cudaFuncSetAttribute(hits_survivors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = (int)((220 * 1024) / (smem + 4096));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    int grid = sms * per_sm;
+    if (grid > n_slices) grid = n_slices;
+    hits_survivors_kernel<<<grid, HIT_THREADS, smem, st>>>(P);
+    TG_CUDA_CHECK(cudaGetLastError());
+    const int g2 = grid_for(total_work_bases, 256, sms, 16);
+    hits_blockstart_kernel<<<g2, 256, 0, st>>>(P);
+    TG_CUDA_CHECK(cudaGetLastError());
+    hits_emit_kernel<<<g2, 256, 0, st>>>(P);
+    TG_CUDA_CHECK(cudaGetLastError());
+    return TG_OK;
+}

@@ -1,0 +1,375 @@
+"""All-vs-all TVR distance on the GPU: host orchestration (numpy/torch) over the C-ABI kernels.
+
+Mirrors tvr_distance / get_dist_matrix_parallel of the reference (tg_align.py:109-189):
+  device : NW scores (tg_nw_scores_wave / tg_nw_scores_generic), MT19937 shuffles (tg_mt_shuffle)
+  host   : the float64 epilogue in the reference's expression order (identity score, early-out
+           test, mean, -log ratio, clamps, float32 store) -- integers in, floats out.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+MIN_VIABLE_SEQ_LEN = 1000           # tg_align.py:20
+MAX_SEQ_DIST = 10.0                 # tg_align.py:22
+MIN_SEQ_DIST = 0.0001               # tg_align.py:24
+IDEN_SCORE_SCALAR_CHEAT = 0.900     # tg_align.py:26
+NOT_COMPUTED = np.iinfo(np.int32).min
+
+
+def _as_int(x, what):
+    xi = int(round(float(x)))
+    if float(x) != float(xi):
+        raise NotImplementedError(f'{what}={x!r}: the GPU path needs integer-valued scores (all reference call sites are)')
+    return xi
+
+
+def _gap_attr(aligner, side, kind):
+    """Biopython >= 1.86 names (open_left_gap_score) with the 1.82-1.85 fallback (left_open_gap_score),
+    the same two spellings get_aligner_object tries (tg_align.py:91-97)."""
+    if side == 'internal':
+        names = [f'{kind}_internal_gap_score', f'internal_{kind}_gap_score']
+    else:
+        names = [f'{kind}_{side}_gap_score', f'{side}_{kind}_gap_score']
+    for nm in names:
+        try:
+            return getattr(aligner, nm)
+        except (AttributeError, ValueError):
+            continue
+    raise AttributeError(f'aligner has no {side} {kind} gap score')
+
+
+class Scoring:
+    """Integer view of a configured aligner: what Bio.Align.PairwiseAligner.score() depends on."""
+
+    def __init__(self, sub, alphabet, match, mismatch, gap, gap_left, gap_right):
+        self.sub = None if sub is None else np.asarray(sub)
+        self.alphabet = alphabet            # str (matrix mode) or None (match/mismatch mode)
+        self.match, self.mismatch = match, mismatch
+        self.gap, self.gap_left, self.gap_right = gap, gap_left, gap_right
+
+    @classmethod
+    def from_aligner(cls, aligner):
+        if getattr(aligner, 'mode', 'global') != 'global':
+            raise NotImplementedError('only global alignment is on the hot path')
+        g = {}
+        for side in ('internal', 'left', 'right'):
+            o, e = _gap_attr(aligner, side, 'open'), _gap_attr(aligner, side, 'extend')
+            if o != e:
+                raise NotImplementedError('affine gaps (open != extend) never reach aligner.score() in the reference; '
+                                          'the GPU path implements the linear-gap Needleman-Wunsch score')
+            g[side] = _as_int(o, f'{side} gap score')
+        sm = aligner.substitution_matrix
+        if sm is None:
+            return cls(None, None, _as_int(aligner.match_score, 'match_score'),
+                       _as_int(aligner.mismatch_score, 'mismatch_score'), g['internal'], g['left'], g['right'])
+        arr = np.asarray(sm, dtype=np.float64)
+        if not np.array_equal(arr, np.rint(arr)):
+            raise NotImplementedError('non-integer substitution matrix')
+        return cls(arr.astype(np.int64), str(sm.alphabet), None, None, g['internal'], g['left'], g['right'])
+
+    # ---- encoding -------------------------------------------------------------------------
+    def encode_all(self, sequences):
+        """-> (codes uint8 concatenated, off int64[n+1], sub int64[A, A])."""
+        for s in sequences:
+            if len(s) == 0:
+                raise ValueError('sequence has zero length')       # Biopython raises the same from score()
+        raw = np.frombuffer(''.join(sequences).encode('latin-1'), dtype=np.uint8)
+        off = np.zeros(len(sequences) + 1, dtype=np.int64)
+        off[1:] = np.cumsum([len(s) for s in sequences])
+        lut = np.full(256, 255, dtype=np.uint8)
+        if self.alphabet is not None:
+            for i, ch in enumerate(self.alphabet):
+                lut[ord(ch)] = i
+            A = len(self.alphabet)
+            sub = self.sub
+        else:
+            present = np.unique(raw)
+            A = len(present)
+            lut[present] = np.arange(A, dtype=np.uint8)
+            sub = np.full((A, A), self.mismatch, dtype=np.int64)
+            np.fill_diagonal(sub, self.match)
+        if A > _lib.MAXA:
+            raise NotImplementedError(f'alphabet of {A} symbols exceeds the {_lib.MAXA} the kernels support')
+        codes = lut[raw]
+        if (codes == 255).any():
+            raise ValueError('sequence contains letters not in the alphabet')
+        return np.ascontiguousarray(codes), off, sub
+
+    def c_struct(self, sub):
+        sc = _lib.NwScoring()
+        A = sub.shape[0]
+        sc.alphabet, sc.gap, sc.gap_left, sc.gap_right = A, self.gap, self.gap_left, self.gap_right
+        full = np.zeros((_lib.MAXA, _lib.MAXA), dtype=np.int16)
+        full[:A, :A] = sub
+        C.memmove(sc.sub, full.ctypes.data, full.nbytes)
+        return sc
+
+
+def pair_index_rows(n, i0, i1):
+    """(I, J, P) for rows i0 <= i < i1 of itertools.combinations(range(n), 2) (tg_align.py:156)."""
+    i = np.arange(i0, i1, dtype=np.int64)
+    cnt = n - 1 - i
+    I = np.repeat(i, cnt)
+    start = i * (2 * n - i - 1) // 2
+    P = np.arange(int(cnt.sum()), dtype=np.int64) + (start[0] if len(start) else 0)
+    J = P - np.repeat(start, cnt) + I + 1
+    return I, J, P
+
+
+def pack_jobs(row_off, col_off, n, m, out, allow_mixed):
+    """Group alignments two by two into tg_nw_job records, largest first.  Equal shapes are paired
+    first; left-overs are paired with each other when allow_mixed, else run with a duplicated half."""
+    cnt = len(n)
+    if cnt == 0:
+        return np.zeros(0, dtype=_lib.NW_JOB)
+    order = np.lexsort((m, n))[::-1]
+    ns, ms = n[order], m[order]
+    new_run = np.ones(cnt, dtype=bool)
+    new_run[1:] = (ns[1:] != ns[:-1]) | (ms[1:] != ms[:-1])
+    run_start = np.maximum.accumulate(np.where(new_run, np.arange(cnt), 0))
+    pos = np.arange(cnt) - run_start
+    has_next = np.zeros(cnt, dtype=bool)
+    has_next[:-1] = ~new_run[1:]
+    first = np.nonzero((pos % 2 == 0) & has_next)[0]            # pairs (k, k+1) inside a run
+    single = np.nonzero((pos % 2 == 0) & ~has_next)[0]          # last of an odd run
+    a_idx, b_idx = [first], [first + 1]
+    if allow_mixed and len(single) > 1:
+        k = len(single) // 2 * 2
+        a_idx.append(single[0:k:2]); b_idx.append(single[1:k:2])
+        single = single[k:]
+    a = np.concatenate(a_idx); b = np.concatenate(b_idx)
+    jobs = np.zeros(len(a) + len(single), dtype=_lib.NW_JOB)
+    ia, ib = order[a], order[b]
+    k = len(a)
+    jobs['row_off'][:k, 0], jobs['row_off'][:k, 1] = row_off[ia], row_off[ib]
+    jobs['col_off'][:k, 0], jobs['col_off'][:k, 1] = col_off[ia], col_off[ib]
+    jobs['n'][:k, 0], jobs['n'][:k, 1] = n[ia], n[ib]
+    jobs['m'][:k, 0], jobs['m'][:k, 1] = m[ia], m[ib]
+    jobs['out'][:k, 0], jobs['out'][:k, 1] = out[ia], out[ib]
+    if len(single):
+        s = order[single]
+        for h in (0, 1):
+            jobs['row_off'][k:, h], jobs['col_off'][k:, h] = row_off[s], col_off[s]
+            jobs['n'][k:, h], jobs['m'][k:, h] = n[s], m[s]
+        jobs['out'][k:, 0], jobs['out'][k:, 1] = out[s], -1
+    # largest first (dynamic scheduling on the device)
+    cost = np.maximum(jobs['n'][:, 0], jobs['n'][:, 1]).astype(np.int64) * np.maximum(jobs['m'][:, 0], jobs['m'][:, 1])
+    return jobs[np.argsort(-cost, kind='stable')]
+
+
+class DistEngine:
+    """Device state for one get_dist_matrix_parallel call."""
+
+    def __init__(self, scoring, device=None, force_generic=False, pairs_per_batch=1 << 21,
+                 shuffle_bytes_per_batch=3 << 30):
+        self.torch = _lib.require_cuda()
+        self.L = _lib.load()
+        self.sc = scoring
+        self.device = self.torch.device('cuda', self.torch.cuda.current_device()) if device is None else device
+        self.force_generic = force_generic
+        self.pairs_per_batch = pairs_per_batch
+        self.shuffle_bytes_per_batch = shuffle_bytes_per_batch
+        self.stats = {'cells': 0, 'wave_jobs': 0, 'generic_jobs': 0, 'launches': 0, 'pairs': 0, 'early_out': 0,
+                      'h2d_bytes': 0, 'd2h_bytes': 0}
+        self._scratch = None
+        self._counter = None
+
+    # ---- device helpers --------------------------------------------------------------------
+    def _to_dev(self, arr):
+        t = self.torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1))
+        self.stats['h2d_bytes'] += t.numel()
+        return t.to(self.device, non_blocking=False)
+
+    def _wave_ok_mask(self, jobs, sub):
+        sc = self.sc
+        if self.force_generic or sc.gap_left != sc.gap or sc.gap_right < sc.gap:
+            return np.zeros(len(jobs), dtype=bool)
+        sp = sub - 2 * sc.gap
+        if sp.min() < 0 or sp.max() > 127:
+            return np.zeros(len(jobs), dtype=bool)
+        N = np.maximum(jobs['n'][:, 0], jobs['n'][:, 1]).astype(np.int64)
+        M = np.maximum(jobs['m'][:, 0], jobs['m'][:, 1]).astype(np.int64)
+        ok = int(sp.max()) * np.minimum(N, M) <= 65535
+        if sc.gap_right != sc.gap:
+            ok &= (jobs['n'][:, 0] == jobs['n'][:, 1]) & (jobs['m'][:, 0] == jobs['m'][:, 1])
+        return ok
+
+    def run_jobs(self, d_pool, jobs, sub, n_out):
+        """Launch the NW kernels for `jobs` (host record array); returns int32 scores on the host."""
+        torch = self.torch
+        d_scores = torch.full((max(n_out, 1),), NOT_COMPUTED, dtype=torch.int32, device=self.device)
+        if len(jobs) == 0:
+            return d_scores[:n_out].cpu().numpy()
+        cstruct = self.sc.c_struct(sub)
+        ok = self._wave_ok_mask(jobs, sub)
+        wave, gen = jobs[ok], jobs[~ok]
+        st = _lib.stream_ptr(torch)
+        if len(wave):
+            max_n = int(max(wave['n'].max(), 1))
+            need = self.L.tg_nw_wave_scratch_bytes(max_n)
+            if self._scratch is None or self._scratch.numel() < need:
+                self._scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
+                self._counter = torch.zeros(2, dtype=torch.int32, device=self.device)
+            d_jobs = self._to_dev(wave)
+            _lib.check(self.L.tg_nw_scores_wave(_lib.dptr(d_pool), _lib.dptr(d_jobs), len(wave), max_n, C.byref(cstruct),
+                                                _lib.dptr(d_scores), _lib.dptr(self._scratch), _lib.dptr(self._counter), st))
+            self.stats['wave_jobs'] += len(wave)
+            self.stats['launches'] += 1
+        if len(gen):
+            max_m = int(gen['m'].max())
+            d_jobs_g = self._to_dev(gen)
+            _lib.check(self.L.tg_nw_scores_generic(_lib.dptr(d_pool), _lib.dptr(d_jobs_g), len(gen), max_m, C.byref(cstruct),
+                                                   _lib.dptr(d_scores), st))
+            self.stats['generic_jobs'] += len(gen)
+            self.stats['launches'] += 1
+        out = d_scores[:n_out].cpu().numpy()
+        self.stats['d2h_bytes'] += out.nbytes
+        return out
+
+    # ---- the batch path ----------------------------------------------------------------------
+    def pair_scores(self, sequences, adjust_lens, min_viable, R, rng_seed, pair_idx=None):
+        """Integer results for every pair (combinations order): dict(aln, rnd[n_pairs, R], iden, n, m).
+        rnd == NOT_COMPUTED where the reference returns early (tg_align.py:137-138).
+        pair_idx: optional sorted int64 array of global pair indices to compute (multi-GPU sharding);
+        everything else stays NOT_COMPUTED / 0."""
+        n_seq = len(sequences)
+        n_pairs = n_seq * (n_seq - 1) // 2
+        codes, off, sub = self.sc.encode_all(sequences)
+        lens = np.diff(off)
+        aln = np.full(n_pairs, NOT_COMPUTED, dtype=np.int32)
+        rnd = np.full((n_pairs, max(R, 0)), NOT_COMPUTED, dtype=np.int32)
+        n_eff_all = np.zeros(n_pairs, dtype=np.int32)
+        m_eff_all = np.zeros(n_pairs, dtype=np.int32)
+        iden_all = np.zeros(n_pairs, dtype=np.float64)
+        if n_pairs == 0:
+            return dict(aln=aln, rnd=rnd, iden=iden_all, n=n_eff_all, m=m_eff_all)
+        # prefix sums of the diagonal for the identity score (tg_align.py:127-134)
+        diag_cs = np.zeros(len(codes) + 1, dtype=np.int64)
+        np.cumsum(np.diag(sub)[codes], out=diag_cs[1:])
+        d_codes = self._to_dev(codes)
+        seed0 = int(rng_seed)
+        if pair_idx is None:
+            pair_idx = np.arange(n_pairs, dtype=np.int64)
+        # row starts in combinations order, to turn pair indices into (I, J)
+        ar = np.arange(n_seq, dtype=np.int64)
+        row_start = ar * (2 * n_seq - ar - 1) // 2
+        p = 0
+        while p < len(pair_idx):
+            q = min(len(pair_idx), p + self.pairs_per_batch)
+            P = pair_idx[p:q]
+            I = np.searchsorted(row_start, P, side='right') - 1
+            I = np.minimum(I, n_seq - 2)
+            J = P - row_start[I] + I + 1
+            li, lj = lens[I], lens[J]
+            if adjust_lens:                                   # tg_align.py:115-120
+                ml = np.minimum(li, lj)
+                if min_viable:
+                    ml = np.maximum(ml, MIN_VIABLE_SEQ_LEN)
+                li, lj = np.minimum(li, ml), np.minimum(lj, ml)
+            li = li.astype(np.int32); lj = lj.astype(np.int32)
+            # shuffle area budget: shrink the batch if needed
+            per_pair = (li.astype(np.int64) + lj) * max(R, 0)
+            if R > 0 and per_pair.sum() > self.shuffle_bytes_per_batch and len(P) > 1:
+                keep = max(1, int(np.searchsorted(np.cumsum(per_pair), self.shuffle_bytes_per_batch)))
+                q = p + keep
+                P, I, J, li, lj = P[:keep], I[:keep], J[:keep], li[:keep], lj[:keep]
+            self._batch(d_codes, len(codes), off, sub, diag_cs, I, J, P, li, lj, R, seed0, aln, rnd, iden_all)
+            n_eff_all[P], m_eff_all[P] = li, lj
+            p = q
+        return dict(aln=aln, rnd=rnd, iden=iden_all, n=n_eff_all, m=m_eff_all)
+
+    def _batch(self, d_codes, n_codes, off, sub, diag_cs, I, J, P, li, lj, R, seed0, aln, rnd, iden_all):
+        torch = self.torch
+        sc = self.sc
+        npair = len(P)
+        mixed_ok = (sc.gap_right == sc.gap)
+        row_off, col_off = off[I], off[J]
+        # ---- phase A: the real alignment of every pair (tg_align.py:125) ----
+        jobs = pack_jobs(row_off, col_off, li, lj, np.arange(npair, dtype=np.int32), mixed_ok)
+        a = self.run_jobs(d_codes, jobs, sub, npair)
+        aln[P] = a
+        # ---- identity score and the early-out test (tg_align.py:127-138), float64 like the reference ----
+        if sc.alphabet is None:
+            iden = sc.match * ((li.astype(np.int64) + lj) / 2.)
+        else:
+            is1 = diag_cs[row_off + li] - diag_cs[row_off]
+            is2 = diag_cs[col_off + lj] - diag_cs[col_off]
+            iden = (is1 + is2) / 2.
+        iden_all[P] = iden
+        early = a.astype(np.float64) < -(IDEN_SCORE_SCALAR_CHEAT * iden)
+        cells = li.astype(np.int64) * lj
+        self.stats['pairs'] += npair
+        self.stats['early_out'] += int(early.sum())
+        self.stats['cells'] += int(cells.sum())
+        if R <= 0:
+            return
+        sel = np.nonzero(~early)[0]
+        if len(sel) == 0:
+            return
+        self.stats['cells'] += int(cells[sel].sum()) * R
+        # ---- phase B: null model.  seed = rng_seed + pair index (tg_align.py:157,170-172) ----
+        ns, ms = li[sel], lj[sel]
+        per_pair = (ns.astype(np.int64) + ms) * R
+        dst = np.zeros(len(sel), dtype=np.int64)
+        dst[1:] = np.cumsum(per_pair)[:-1]
+        total_shuf = int(per_pair.sum())
+        d_pool = torch.empty(n_codes + total_shuf, dtype=torch.uint8, device=self.device)
+        d_pool[:n_codes] = d_codes
+        dst += n_codes
+        sj = np.zeros(len(sel), dtype=_lib.SHUFFLE_JOB)
+        seeds = [abs(seed0 + int(pp)) for pp in (P[sel[0]], P[sel[-1]])]
+        if max(seeds) >= 1 << 64:
+            raise NotImplementedError('rng_seed + pair index beyond 64 bits')
+        if seed0 >= 0:
+            sj['seed'] = (P[sel] + seed0).astype(np.uint64)
+        else:
+            sj['seed'] = np.abs(P[sel].astype(np.int64) + seed0).astype(np.uint64)
+        sj['src_i'], sj['src_j'], sj['dst_off'], sj['n'], sj['m'] = row_off[sel], col_off[sel], dst, ns, ms
+        d_sj = self._to_dev(sj)
+        _lib.check(self.L.tg_mt_shuffle(_lib.dptr(d_pool), _lib.dptr(d_sj), len(sel), R, int(max(ns.max(), ms.max())),
+                                        _lib.stream_ptr(torch)))
+        self.stats['launches'] += 1
+        # R alignments per selected pair: rows at dst + k*(n+m), columns right behind
+        k = np.arange(R, dtype=np.int64)
+        r_off = (dst[:, None] + k[None, :] * (ns.astype(np.int64) + ms)[:, None]).reshape(-1)
+        c_off = r_off + np.repeat(ns.astype(np.int64), R)
+        jobs_b = pack_jobs(r_off, c_off, np.repeat(ns, R), np.repeat(ms, R),
+                           np.arange(len(sel) * R, dtype=np.int32), mixed_ok)
+        rs = self.run_jobs(d_pool, jobs_b, sub, len(sel) * R).reshape(len(sel), R)
+        rnd[P[sel]] = rs
+
+    # ---- float epilogue (host, float64, the reference's expression order) --------------------------
+    @staticmethod
+    def distances(res, R):
+        """tg_align.py:137-149 for every pair at once."""
+        aln = res['aln'].astype(np.float64)
+        iden = res['iden']
+        d = np.full(len(aln), MAX_SEQ_DIST, dtype=np.float64)
+        early = aln < -(IDEN_SCORE_SCALAR_CHEAT * iden)
+        live = np.nonzero(~early)[0]
+        if len(live):
+            if R > 0:
+                rmean = np.add.reduce(res['rnd'][live].astype(np.float64), axis=1) / R      # np.mean(rand_scores)
+            else:
+                rmean = np.full(len(live), np.nan)                                         # np.mean([]) -> nan
+            a, idn = aln[live], iden[live]
+            with np.errstate(divide='ignore', invalid='ignore'):
+                dd = np.minimum(-np.log((a - rmean) / (idn - rmean)), MAX_SEQ_DIST)
+            dd = np.where(rmean >= a, MAX_SEQ_DIST, dd)
+            d[live] = np.maximum(dd, MIN_SEQ_DIST)
+        return d
+
+    def dist_matrix(self, sequences, adjust_lens, min_viable, R, rng_seed, res=None):
+        n = len(sequences)
+        D = np.zeros((n, n), dtype='<f4')
+        if n < 2:
+            return D
+        if res is None:
+            res = self.pair_scores(sequences, adjust_lens, min_viable, R, rng_seed)
+        d = self.distances(res, R)
+        iu = np.triu_indices(n, k=1)                 # row-major upper triangle == combinations order
+        D[iu] = d
+        D[(iu[1], iu[0])] = d
+        return D

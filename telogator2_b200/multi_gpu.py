@@ -1,0 +1,62 @@
+"""Sharding of the pair space over the ranks of one box (torch.distributed, one process per GPU).
+
+Pairs are independent and a pair's RNG seed is a pure function of its global index
+(rng_seed + p, tg_align.py:157,170-172), so sharding cannot change any result.  Blocks of
+consecutive pair indices are dealt round-robin to the ranks (statistical cost balance); the only
+exchange step is the gather of the per-pair integer results, done as element-wise all-reduces over
+NCCL/NVLink (MAX for scores whose not-computed sentinel is INT32_MIN, SUM for the zero-filled rest)."""
+import numpy as np
+
+SHARD_BLOCK = 4096
+
+
+def shard_pair_indices(n_pairs, rank, world, block=SHARD_BLOCK):
+    """Sorted global pair indices owned by `rank`."""
+    if world <= 1:
+        return np.arange(n_pairs, dtype=np.int64)
+    starts = np.arange(rank * block, n_pairs, world * block, dtype=np.int64)
+    if len(starts) == 0:
+        return np.zeros(0, dtype=np.int64)
+    idx = (starts[:, None] + np.arange(block, dtype=np.int64)[None, :]).reshape(-1)
+    return idx[idx < n_pairs]
+
+
+def _dist_state():
+    try:
+        import torch.distributed as dist
+    except Exception:                                   # noqa: BLE001
+        return None, 0, 1
+    if not (dist.is_available() and dist.is_initialized()):
+        return None, 0, 1
+    return dist, dist.get_rank(), dist.get_world_size()
+
+
+def gather_results(res, dist, device):
+    """In-place element-wise merge of every rank's partial result dict."""
+    import torch
+    for key, op in (('aln', dist.ReduceOp.MAX), ('rnd', dist.ReduceOp.MAX), ('n', dist.ReduceOp.MAX),
+                    ('m', dist.ReduceOp.MAX), ('iden', dist.ReduceOp.SUM)):
+        arr = res[key]
+        if arr.size == 0:
+            continue
+        t = torch.from_numpy(np.ascontiguousarray(arr)).to(device)
+        dist.all_reduce(t, op=op)
+        res[key] = t.cpu().numpy().reshape(arr.shape)
+    return res
+
+
+def sharded_pair_scores(engine, sequences, adjust_lens, min_viable, R, rng_seed, compute=None, device=None):
+    """engine.pair_scores over this rank's shard + gather.  `compute(pair_idx)` replaces the device
+    call in the CPU (gloo) tests of the sharding logic."""
+    dist, rank, world = _dist_state()
+    n = len(sequences)
+    n_pairs = n * (n - 1) // 2
+    if compute is None:
+        def compute(pair_idx):
+            return engine.pair_scores(sequences, adjust_lens, min_viable, R, rng_seed, pair_idx=pair_idx)
+    if world <= 1 or n_pairs == 0:
+        return compute(None)
+    res = compute(shard_pair_indices(n_pairs, rank, world))
+    if device is None:
+        device = engine.device if dist.get_backend() == 'nccl' else 'cpu'
+    return gather_results(res, dist, device)

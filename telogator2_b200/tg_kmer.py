@@ -1,0 +1,277 @@
+"""Drop-in for the scan functions of the reference's source/tg_kmer.py (lines 11-102, 173-230).
+
+Per-read functions keep the reference's names, signatures and return types and run as a batch of
+one on the GPU; the *_batch / ScanSession entry points are what tg_tel.get_tel_repeat_comp_parallel
+uses (one launch per phase for all reads).  get_telomere_regions / wavelet_smooth / mad
+(tg_kmer.py:105-170, pywt float code) are outside the hot path and stay the reference's own.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+from .tg_util import RC  # noqa: F401  (re-exported like the reference module's namespace)
+
+INCLUDE_SUBTEL_BUFF = 500      # tg_kmer.py:8
+MAX_KMERS = 64
+MAX_KMER_LEN = 32
+
+
+def exists_and_is_nonzero(fn):
+    return os.path.isfile(fn) and os.path.getsize(fn) > 0
+
+
+def _tsv_rows(fn, READ_TYPE):
+    """Rows of a k-mer TSV surviving the read-type filter (tg_kmer.py:22-30, 52-60)."""
+    with open(fn, 'r') as f:
+        for line in f:
+            if line[0] != '#' and len(line.strip()):
+                splt = line.strip().split('\t')
+                flags = splt[3].split(',')
+                if 'pacbio_only' in flags and READ_TYPE not in ['hifi']:
+                    continue
+                if 'nanopore_only' in flags and READ_TYPE not in ['ont']:
+                    continue
+                yield splt[0], splt[1], splt[2], tuple(flags)
+
+
+def read_kmer_tsv(fn, READ_TYPE):
+    """tg_kmer.py:11-48: ([KMER_LIST, COLORS, LETTERS, FLAGS], KMER_ISSUBSTRING, CANONICAL_STRINGS);
+    k-mers de-duplicated and sorted descending by (len, kmer, colour, letter, flags)."""
+    if exists_and_is_nonzero(fn) is False:
+        print('Error: ' + fn + ' not found.')
+        exit(1)
+    rows = list(_tsv_rows(fn, READ_TYPE))
+    canonical = [r[0] for r in rows if 'canonical' in r[3]]
+    dat = sorted(set((len(r[0]), r[0], r[1], r[2], r[3]) for r in rows), reverse=True)
+    kmers = [d[1] for d in dat]
+    meta = [kmers, [d[2] for d in dat], [d[3] for d in dat], [d[4] for d in dat]]
+    issub = [[j for j in range(len(kmers)) if (j != i and kmers[i] in kmers[j])] for i in range(len(kmers))]
+    return (meta, issub, canonical)
+
+
+def get_canonical_letter(fn, READ_TYPE):
+    """tg_kmer.py:51-63: letter of the first canonical row."""
+    for (_kmer, _color, letter, flags) in _tsv_rows(fn, READ_TYPE):
+        if 'canonical' in flags:
+            return letter
+    return None
+
+
+# ------------------------------------------------------------------------------------------------
+# device tables
+# ------------------------------------------------------------------------------------------------
+_table_cache = {}
+
+
+def kmer_table(kmer_list, issub=None):
+    """Device blob of the reversed-k-mer automaton for `kmer_list` (cached per device)."""
+    torch = _lib.require_cuda()
+    L = _lib.load()
+    dev = torch.cuda.current_device()
+    key = (tuple(kmer_list), None if issub is None else tuple(tuple(x) for x in issub), dev)
+    t = _table_cache.get(key)
+    if t is not None:
+        return t
+    if len(kmer_list) < 1 or len(kmer_list) > MAX_KMERS:
+        raise NotImplementedError(f'{len(kmer_list)} k-mers: the GPU scan supports 1..{MAX_KMERS} per list')
+    blob = ''.join(kmer_list).encode('ascii')
+    off = np.zeros(len(kmer_list) + 1, dtype=np.int32)
+    off[1:] = np.cumsum([len(k) for k in kmer_list])
+    if issub is not None:
+        edges = np.array([j for lst in issub for j in lst], dtype=np.int32)
+        eoff = np.zeros(len(issub) + 1, dtype=np.int32)
+        eoff[1:] = np.cumsum([len(lst) for lst in issub])
+        pe, po = edges.ctypes.data_as(C.c_void_p), eoff.ctypes.data_as(C.c_void_p)
+    else:
+        pe = po = None
+    host = np.zeros(L.tg_kmer_table_bytes(), dtype=np.uint8)
+    _lib.check(L.tg_kmer_table_build(blob, off.ctypes.data_as(C.c_void_p), len(kmer_list), pe, po,
+                                     host.ctypes.data_as(C.c_void_p)))
+    t = torch.from_numpy(host).cuda()
+    _table_cache[key] = t
+    return t
+
+
+# ------------------------------------------------------------------------------------------------
+# reads in HBM
+# ------------------------------------------------------------------------------------------------
+_ACGTN = np.zeros(256, dtype=bool)
+_ACGTN[[ord(c) for c in 'ACGTN']] = True
+ALIGN = 128
+
+
+class PackedReads:
+    """A batch of reads packed 2 bits/base + N-mask plane on the device (see tg_scan_pack)."""
+
+    def __init__(self, reads):
+        torch = _lib.require_cuda()
+        L = _lib.load()
+        self.torch, self.L = torch, L
+        self.n = len(reads)
+        self.lens = np.array([len(r) for r in reads], dtype=np.int32)
+        padded = (self.lens.astype(np.int64) + ALIGN - 1) // ALIGN * ALIGN
+        self.base_off = np.zeros(self.n + 1, dtype=np.int64)
+        self.base_off[1:] = np.cumsum(padded)
+        total = int(self.base_off[-1])
+        self.total = total
+        ascii_h = torch.empty(max(total, 16), dtype=torch.uint8, pin_memory=True)
+        buf = ascii_h.numpy()
+        buf[:] = ord('N')
+        for i, r in enumerate(reads):
+            if self.lens[i]:
+                o = int(self.base_off[i])
+                buf[o:o + self.lens[i]] = np.frombuffer(r.encode('latin-1', 'replace'), dtype=np.uint8)
+        self._ascii_host = buf
+        self.h2d_bytes = total + self.base_off.nbytes + self.lens.nbytes
+        self.d_ascii = ascii_h.cuda(non_blocking=True)
+        self.d_base_off = torch.from_numpy(self.base_off).cuda()
+        self.d_len = torch.from_numpy(self.lens).cuda()
+        self.d_pack2 = torch.empty(max(total // 16, 4), dtype=torch.int32, device='cuda')
+        self.d_nmask = torch.empty(max(total // 32, 4), dtype=torch.int32, device='cuda')
+        if self.n and total:
+            _lib.check(L.tg_scan_pack(_lib.dptr(self.d_ascii), _lib.dptr(self.d_base_off), _lib.dptr(self.d_len), self.n,
+                                      _lib.dptr(self.d_pack2), _lib.dptr(self.d_nmask), _lib.stream_ptr(torch)))
+
+    def check_rc_alphabet(self, flip):
+        """RC() raises KeyError outside ACGTN (tg_util.py:433-434); mirror that for reads to be flipped."""
+        for i in np.nonzero(flip)[0]:
+            o = int(self.base_off[i])
+            seg = self._ascii_host[o:o + self.lens[i]]
+            bad = ~_ACGTN[seg]
+            if bad.any():
+                raise KeyError(chr(int(seg[np.argmax(bad)])))
+
+    def basecount(self, list_a, list_b):
+        """int32 [n, 2]: get_telomere_base_count for two k-mer lists (tg_kmer.py:93-102)."""
+        torch = self.torch
+        out = torch.zeros((max(self.n, 1), 2), dtype=torch.int32, device='cuda')
+        if self.n:
+            _lib.check(self.L.tg_scan_basecount(_lib.dptr(self.d_pack2), _lib.dptr(self.d_nmask), _lib.dptr(self.d_base_off),
+                                                _lib.dptr(self.d_len), self.n, _lib.dptr(kmer_table(list_a)),
+                                                _lib.dptr(kmer_table(list_b)), _lib.dptr(out), _lib.stream_ptr(torch)))
+        return out[:self.n]
+
+    def orient(self, flip):
+        """Reverse-complement the reads with flip[i] != 0 in place of tg_tel.py:265-266 (device, packed domain)."""
+        torch = self.torch
+        flip = np.ascontiguousarray(flip, dtype=np.uint8)
+        self.check_rc_alphabet(flip)
+        if not flip.any() or not self.total:
+            return
+        d_flip = torch.from_numpy(flip).cuda()
+        p2, nm = torch.empty_like(self.d_pack2), torch.empty_like(self.d_nmask)
+        _lib.check(self.L.tg_scan_orient(_lib.dptr(self.d_pack2), _lib.dptr(self.d_nmask), _lib.dptr(self.d_base_off),
+                                         _lib.dptr(self.d_len), _lib.dptr(d_flip), self.n, _lib.dptr(p2), _lib.dptr(nm),
+                                         _lib.stream_ptr(torch)))
+        self.d_pack2, self.d_nmask = p2, nm
+
+    def density_counts(self, list_a, list_b, window):
+        """uint8 window counts for two k-mer lists, device tensors over the padded base space."""
+        torch = self.torch
+        ca = torch.zeros(max(self.total, 16), dtype=torch.uint8, device='cuda')
+        cb = torch.zeros(max(self.total, 16), dtype=torch.uint8, device='cuda')
+        if self.n and self.total:
+            _lib.check(self.L.tg_scan_density(_lib.dptr(self.d_pack2), _lib.dptr(self.d_nmask), _lib.dptr(self.d_base_off),
+                                              _lib.dptr(self.d_len), self.n, _lib.dptr(kmer_table(list_a)),
+                                              _lib.dptr(kmer_table(list_b)), int(window), _lib.dptr(ca), _lib.dptr(cb),
+                                              _lib.stream_ptr(torch)))
+        return ca, cb
+
+    def split_counts(self, flat, window):
+        """host: per-read views cnt[0 : len - window) of a flat count array (numpy uint8)."""
+        out = []
+        for i in range(self.n):
+            o = int(self.base_off[i])
+            out.append(flat[o:o + max(int(self.lens[i]) - window, 0)])
+        return out
+
+    def hits(self, slice_read, slice_lo, slice_hi, kmer_list, issub):
+        """get_nonoverlapping_kmer_hits for a batch of slices; returns one out_dat (list[K] of [[s, e], ...]) per slice."""
+        torch = self.torch
+        K = len(kmer_list)
+        ns = len(slice_read)
+        if ns == 0:
+            return []
+        sr = np.ascontiguousarray(slice_read, dtype=np.int32)
+        lo = np.ascontiguousarray(slice_lo, dtype=np.int32)
+        hi = np.ascontiguousarray(slice_hi, dtype=np.int32)
+        ln = (hi - lo).astype(np.int64)
+        woff = np.zeros(ns + 1, dtype=np.int64)
+        woff[1:] = np.cumsum((ln + 63) // 64 * 64)
+        total = int(woff[-1])
+        if total == 0:
+            return [[[] for _ in range(K)] for _ in range(ns)]
+        tab = kmer_table(kmer_list, issub)
+        d_sr, d_lo, d_hi, d_woff = (torch.from_numpy(a).cuda() for a in (sr, lo, hi, woff))
+        work = torch.empty(self.L.tg_scan_hits_work_bytes(total, ns), dtype=torch.uint8, device='cuda')
+        cap = max(total // 2, 1024)
+        while True:
+            spans = torch.empty((4, cap), dtype=torch.int32, device='cuda')
+            cnt = torch.zeros(1, dtype=torch.int64, device='cuda')
+            _lib.check(self.L.tg_scan_hits(_lib.dptr(self.d_pack2), _lib.dptr(self.d_nmask), _lib.dptr(self.d_base_off),
+                                           _lib.dptr(d_sr), _lib.dptr(d_lo), _lib.dptr(d_hi), ns, _lib.dptr(d_woff), total,
+                                           _lib.dptr(tab), _lib.dptr(work), _lib.dptr(spans[0]), _lib.dptr(spans[1]),
+                                           _lib.dptr(spans[2]), _lib.dptr(spans[3]), cap, _lib.dptr(cnt),
+                                           _lib.stream_ptr(torch)))
+            n_sp = int(cnt.item())
+            if n_sp <= cap:
+                break
+            cap = n_sp
+        sp = spans[:, :n_sp].cpu().numpy()
+        self.last_hits_d2h = sp.nbytes
+        order = np.lexsort((sp[2], sp[1], sp[0]))          # by slice, k, start
+        sp = sp[:, order]
+        out = [[[] for _ in range(K)] for _ in range(ns)]
+        sl, kk, ss, ee = sp[0].tolist(), sp[1].tolist(), sp[2].tolist(), sp[3].tolist()
+        for q, k, s, e in zip(sl, kk, ss, ee):
+            out[q][k].append([s, e])
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's per-read functions (batch of one)
+# ------------------------------------------------------------------------------------------------
+_density_cache = {}
+
+
+def prime_density_cache(read, kmer_list, tel_window, result):
+    """Lets a batch caller (tg_tel) hand pre-computed densities to code that still calls the per-read function."""
+    _density_cache[(read, tuple(kmer_list), tel_window)] = result
+
+
+def clear_density_cache():
+    _density_cache.clear()
+
+
+def get_telomere_kmer_density(read_dat, kmer_list, tel_window, mode='hifi', smoothing=False):
+    """tg_kmer.py:66-90 -> (density list, all-zero list), both of length max(len(read) - tel_window, 0)."""
+    if smoothing:
+        raise NotImplementedError('smoothing=True (pywt) is not on the hot path; no reference caller uses it')
+    if _density_cache:
+        hit = _density_cache.get((read_dat, tuple(kmer_list), tel_window))
+        if hit is not None:
+            return hit
+    pr = PackedReads([read_dat])
+    ca, _cb = pr.density_counts(kmer_list, kmer_list, tel_window)
+    n_out = max(len(read_dat) - tel_window, 0)
+    cnt = ca[:n_out].cpu().numpy()
+    dens = (cnt.astype(np.float64) / tel_window).tolist()
+    return (dens, [0.0] * n_out)
+
+
+def get_telomere_base_count(read_dat, kmer_list, mode='hifi'):
+    """tg_kmer.py:93-102."""
+    if len(read_dat) == 0:
+        return 0
+    pr = PackedReads([read_dat])
+    return int(pr.basecount(kmer_list, kmer_list)[0, 0].item())
+
+
+def get_nonoverlapping_kmer_hits(my_telseq, KMER_LIST, KMER_ISSUBSTRING, mode='hifi'):
+    """tg_kmer.py:173-230 -> out_dat[k] = start-sorted list of [start, end] lists."""
+    if len(my_telseq) == 0:
+        return [[] for _ in KMER_LIST]
+    pr = PackedReads([my_telseq])
+    return pr.hits([0], [0], [len(my_telseq)], KMER_LIST, KMER_ISSUBSTRING)[0]

@@ -1,0 +1,213 @@
+"""GPU parity: distance path (tg_align) through the C ABI vs the CPU oracle / golden fixtures."""
+import random
+from itertools import combinations
+
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def tga():
+    import torch
+    assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
+    from telogator2_b200 import tg_align
+    return tg_align
+
+
+def _P(S, gap_bool):
+    return oracle.AlignerParams(S, gap_bool)
+
+
+def _cases(colorvecs):
+    ont = colorvecs['colorvecs']['human_ont']
+    hifi = colorvecs['colorvecs']['human_hifi']
+    return ont, hifi
+
+
+def _check_matrix(tga, seqs, which, gap_bool, adjust, minv, R, seed, force_generic=False):
+    from telogator2_b200.dist_engine import DistEngine, Scoring
+    if which is None:
+        aligner = tga.get_aligner_object(None, gap_bool, 'tvr')
+        P = _P(None, gap_bool)
+    else:
+        aligner = tga.get_aligner_object(tga.get_scoring_matrix('C', which), gap_bool, 'tvr')
+        P = _P(oracle.scoring_matrix('C', which), gap_bool)
+    eng = DistEngine(Scoring.from_aligner(aligner), force_generic=force_generic)
+    res = eng.pair_scores(seqs, adjust, minv, R, seed)
+    D = eng.dist_matrix(seqs, adjust, minv, R, seed, res=res)
+    Do, aln, rnd, cells = oracle.dist_matrix_c(seqs, P, adjust, minv, R, seed, want_scores=True)
+    bad = np.nonzero(res['aln'] != aln)[0]
+    assert len(bad) == 0, f'aln mismatch at pairs {bad[:10]}: gpu {res["aln"][bad[:10]]} oracle {aln[bad[:10]]}'
+    if R:
+        badr = np.argwhere(res['rnd'] != rnd)
+        assert len(badr) == 0, f'rand mismatch at {badr[:10]}: gpu {res["rnd"][tuple(badr[:10].T)]} oracle {rnd[tuple(badr[:10].T)]}'
+    assert np.array_equal(D, Do), 'distance matrix differs'
+    assert eng.stats['cells'] == int(cells)
+    return eng
+
+
+def test_wave_iter0_ont_golden(tga, colorvecs, dp_golden):
+    ont, _ = _cases(colorvecs)
+    seqs = [c[:1000] for c in ont][:24]
+    eng = _check_matrix(tga, seqs, 'tvr', (True, True), True, True, 2, 12345)
+    assert eng.stats['wave_jobs'] > 0 and eng.stats['generic_jobs'] == 0
+    aligner = tga.get_aligner_object(tga.get_scoring_matrix('C', 'tvr'), (True, True), 'tvr')
+    D = tga.get_dist_matrix_parallel(seqs, aligner, True, True, 2, max_workers=3, rng_seed=12345)
+    assert D.dtype == np.dtype('<f4') and np.array_equal(D, dp_golden['ont24_tvr_R2|D'])
+
+
+def test_wave_iter0_hifi_golden(tga, colorvecs, dp_golden):
+    _, hifi = _cases(colorvecs)
+    seqs = [c[:1000] for c in hifi][:24]
+    _check_matrix(tga, seqs, 'tvr', (True, True), True, True, 2, 12345)
+
+
+def test_wave_iter2_shape_and_ragged(tga, colorvecs):
+    ont, hifi = _cases(colorvecs)
+    seqs = [c[:3000] for c in ont][:10]
+    _check_matrix(tga, seqs, 'tvr', (True, True), True, True, 3, 999)
+    # ragged lengths, no min_viable, odd R, mixed shapes in one packed job
+    rag = [c[:137 + 211 * i] for i, c in enumerate(hifi[:9])] + ['C', 'CA', 'DDC']
+    _check_matrix(tga, rag, 'tvr', (True, True), True, False, 1, 7)
+    _check_matrix(tga, rag, 'consensus', (True, True), False, False, 3, 2 ** 32 + 5)
+
+
+def test_wave_right_free_match_mismatch(tga, colorvecs, dp_golden):
+    ont, _ = _cases(colorvecs)
+    seqs = [c[:700 + 97 * i] for i, c in enumerate(ont[:12])]
+    eng = _check_matrix(tga, seqs, None, (True, False), False, False, 3, 12345)
+    assert eng.stats['wave_jobs'] > 0
+    aligner = tga.get_aligner_object(None, (True, False), 'tvr')
+    D = tga.get_dist_matrix_parallel(seqs, aligner, False, False, 3, rng_seed=12345)
+    assert np.array_equal(D, dp_golden['ont12_ms_rightfree_R3|D'])
+    # nucleotide alphabet (stage [4] subtel shape)
+    rng = np.random.default_rng(3)
+    base = ''.join(rng.choice(list('ACGT'), 900))
+    nts = []
+    for i in range(8):
+        s = list(base)
+        for p in rng.choice(len(s), 40 * i, replace=False):
+            s[p] = rng.choice(list('ACGT'))
+        nts.append(''.join(s)[:900 - 31 * i])
+    _check_matrix(tga, nts, None, (True, False), False, False, 3, 5)
+
+
+def test_generic_kernel_all_gap_modes(tga, colorvecs):
+    ont, _ = _cases(colorvecs)
+    seqs = [c[:300 + 41 * i] for i, c in enumerate(ont[:8])] + ['C', 'DC']
+    for gap_bool in ((True, True), (True, False), (False, True), (False, False)):
+        _check_matrix(tga, seqs, 'tvr', gap_bool, False, False, 2, 11, force_generic=(gap_bool[0] is True))
+        _check_matrix(tga, seqs, None, gap_bool, True, False, 1, 12, force_generic=(gap_bool[0] is True))
+
+
+def test_long_sequences_fall_back_to_int32(tga):
+    rng = np.random.default_rng(9)
+    seqs = [''.join(rng.choice(list('CCCCDEFA'), n)) for n in (6000, 5500, 7001)]
+    eng = _check_matrix(tga, seqs, None, (True, False), False, False, 1, 3)
+    assert eng.stats['generic_jobs'] > 0
+
+
+def test_tvr_distance_and_quick_compare_follow_host_random(tga, colorvecs):
+    ont, _ = _cases(colorvecs)
+    a, b = ont[0][:1500], ont[1][:1400]
+    aligner = tga.get_aligner_object(tga.get_scoring_matrix('C', 'tvr'), (True, True), 'tvr')
+    P = _P(oracle.scoring_matrix('C', 'tvr'), (True, True))
+    d = tga.tvr_distance(a, b, aligner, True, True, 3, rng_seed=4242)
+    assert d == oracle.tvr_distance_py(a, b, P, True, True, 3, rng_seed=4242)
+    # no reseed: consumes the process-wide stream exactly like the reference (stage [7])
+    random.seed(77)
+    got = tga.quick_compare_tvrs(a, b)
+    random.seed(77)
+    want = oracle.tvr_distance_py(a, b, _P(None, (True, False)), False, False, 3, rng_seed=None) / 10.0
+    assert got == want
+
+
+def test_edge_cases(tga):
+    aligner = tga.get_aligner_object(tga.get_scoring_matrix('C', 'tvr'), (True, True), 'tvr')
+    assert tga.get_dist_matrix_parallel([], aligner, True, True, 2).shape == (0, 0)
+    assert np.array_equal(tga.get_dist_matrix_parallel(['CCD'], aligner, True, True, 2), np.zeros((1, 1), '<f4'))
+    with pytest.raises(ValueError):
+        tga.get_dist_matrix_parallel(['CCD', ''], aligner, True, True, 2)
+    with pytest.raises(ValueError):
+        tga.get_dist_matrix_parallel(['CCD', 'CBZ'], aligner, True, True, 2)      # letters not in the alphabet
+    D = tga.get_dist_matrix_parallel(['CCDCC' * 50, 'CCDCC' * 50], aligner, True, True, 2)
+    assert D[0, 1] == np.float32(1e-4) and D[0, 0] == 0            # identical sequences hit MIN_SEQ_DIST
+
+
+def test_clustering_assignments_match(tga, colorvecs):
+    from scipy.cluster.hierarchy import fcluster, linkage
+    from scipy.spatial.distance import squareform
+    _, hifi = _cases(colorvecs)
+    seqs = [c[:1000] for c in hifi][:40]
+    aligner = tga.get_aligner_object(tga.get_scoring_matrix('C', 'tvr'), (True, True), 'tvr')
+    D = tga.get_dist_matrix_parallel(seqs, aligner, True, True, 2, rng_seed=31337) / 10.0
+    Do = oracle.dist_matrix_c(seqs, _P(oracle.scoring_matrix('C', 'tvr'), (True, True)), True, True, 2, 31337) / 10.0
+    a1 = fcluster(linkage(squareform(D), method='ward'), 0.2, 'distance')
+    a2 = fcluster(linkage(squareform(Do), method='ward'), 0.2, 'distance')
+    assert np.array_equal(a1, a2)
+
+
+def test_mt_shuffle_kernel_direct(rng_golden):
+    """tg_mt_shuffle against CPython golden permutations, seeds up to 2**63."""
+    import torch
+    from telogator2_b200 import _lib
+    L = _lib.load()
+    keys = sorted(rng_golden.keys())
+    jobs = np.zeros(len(keys), dtype=_lib.SHUFFLE_JOB)
+    srcs, off = [], 0
+    meta = []
+    for q, key in enumerate(keys):
+        seed, n = (int(x) for x in key.split('|'))
+        m = max(n - 1, 1)
+        a = (np.arange(n) % 251).astype(np.uint8)
+        b = (np.arange(m) % 241).astype(np.uint8)
+        jobs[q]['seed'], jobs[q]['src_i'], jobs[q]['src_j'], jobs[q]['n'], jobs[q]['m'] = seed, off, off + n, n, m
+        srcs += [a, b]
+        off += n + m
+        meta.append((n, m, a, b))
+    src_total = off
+    for q, (n, m, a, b) in enumerate(meta):
+        jobs[q]['dst_off'] = off
+        off += 2 * (n + m)            # R = 2 -> i, j, i, j
+    pool = torch.zeros(off, dtype=torch.uint8, device='cuda')
+    pool[:src_total] = torch.from_numpy(np.concatenate(srcs)).cuda()
+    d_jobs = torch.from_numpy(jobs.view(np.uint8).reshape(-1)).cuda()
+    _lib.check(L.tg_mt_shuffle(_lib.dptr(pool), _lib.dptr(d_jobs), len(keys), 2, 3000, _lib.stream_ptr(torch)))
+    out = pool.cpu().numpy()
+    for q, key in enumerate(keys):
+        n, m, a, b = meta[q]
+        perms = rng_golden[key]
+        p1, p2, p3 = perms[:n], perms[n:n + m], perms[n + m:]
+        d = int(jobs[q]['dst_off'])
+        assert np.array_equal(out[d:d + n], a[p1]), key
+        assert np.array_equal(out[d + n:d + n + m], b[p2]), key
+        assert np.array_equal(out[d + n + m:d + 2 * n + m], a[p3]), key
+
+
+def test_full_size_properties(tga, colorvecs):
+    """BASELINE-sized iter-0 shape (N = 512 replicated colour vectors): properties that need no oracle."""
+    ont, hifi = _cases(colorvecs)
+    rng = np.random.default_rng(1)
+    base = [c[:1000] for c in (ont + hifi) if len(c) >= 1000]
+    seqs = []
+    for i in range(512):
+        s = list(base[i % len(base)])
+        for p in rng.choice(len(s), 20, replace=False):
+            s[p] = 'CVHTFDA'[rng.integers(7)]
+        seqs.append(''.join(s))
+    aligner = tga.get_aligner_object(tga.get_scoring_matrix('C', 'tvr'), (True, True), 'tvr')
+    D = tga.get_dist_matrix_parallel(seqs, aligner, True, True, 2, rng_seed=5)
+    assert np.array_equal(D, D.T) and (np.diag(D) == 0).all()
+    assert D[np.triu_indices(512, 1)].min() >= np.float32(1e-4) and D.max() <= 10
+    # permutation consistency on a sub-block: sub-matrix recomputed alone with the matching seeds
+    sub = [0, 5, 17, 300]
+    P = _P(oracle.scoring_matrix('C', 'tvr'), (True, True))
+    pairs = list(combinations(range(512), 2))
+    index = {ij: p for p, ij in enumerate(pairs)}
+    for i, j in combinations(sub, 2):
+        want = oracle.tvr_distance_py(seqs[i], seqs[j], P, True, True, 2, rng_seed=5 + index[(i, j)])
+        assert D[i, j] == np.float32(want)

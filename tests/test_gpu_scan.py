@@ -1,0 +1,138 @@
+"""GPU parity: k-mer scan (tg_kmer) through the C ABI vs golden vectors from the reference and the oracle."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import hits_to_array, rc_py, scan_cases
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def tgk():
+    import torch
+    assert torch.cuda.is_available()
+    from telogator2_b200 import tg_kmer
+    return tg_kmer
+
+
+def test_batch_scan_matches_reference_golden(tgk, kmer_tables, golden_reads, scan_golden):
+    """Phase 1 of the batch boundary: base counts, orientation, densities for every golden read."""
+    by_table = {}
+    for tag, T, rdat in scan_cases(kmer_tables, golden_reads):
+        by_table.setdefault(tag.split('|')[1], []).append((tag, rdat))
+    n_checked = 0
+    for tkey, items in by_table.items():
+        T = kmer_tables[tkey]
+        KL, CANON = T['KMER_LIST'], T['CANONICAL_STRINGS']
+        KL_REV, CANON_REV = [rc_py(k) for k in KL], [rc_py(k) for k in CANON]
+        reads = [r for _, r in items]
+        pr = tgk.PackedReads(reads)
+        bc = pr.basecount(CANON, CANON_REV).cpu().numpy()
+        for q, (tag, _r) in enumerate(items):
+            assert bc[q].tolist() == scan_golden[tag + '|bc'].tolist(), tag
+        flip = bc[:, 0] > bc[:, 1]
+        pr.orient(flip)
+        ca, cb = pr.density_counts(KL, KL_REV, 100)
+        ca, cb = pr.split_counts(ca.cpu().numpy(), 100), pr.split_counts(cb.cpu().numpy(), 100)
+        for q, (tag, _r) in enumerate(items):
+            assert int(flip[q]) == int(scan_golden[tag + '|flip'][0]), tag
+            gp, gq = scan_golden[tag + '|dens_p'], scan_golden[tag + '|dens_q']
+            assert ca[q].shape == gp.shape, tag
+            bad = np.nonzero(ca[q] != gp)[0]
+            assert len(bad) == 0, f'{tag} dens_p differs at {bad[:8]}: gpu {ca[q][bad[:8]]} ref {gp[bad[:8]]}'
+            bad = np.nonzero(cb[q] != gq)[0]
+            assert len(bad) == 0, f'{tag} dens_q differs at {bad[:8]}: gpu {cb[q][bad[:8]]} ref {gq[bad[:8]]}'
+            n_checked += 1
+        # hits on the oriented reads: suffix and prefix slices in one batch
+        ISSUB = T['KMER_ISSUBSTRING']
+        lens = [len(r) for r in reads]
+        idx = np.arange(len(reads))
+        out_sfx = pr.hits(idx, [max(l - 6000, 0) for l in lens], lens, KL_REV, ISSUB)
+        out_fp = pr.hits(idx, [0] * len(reads), [min(l, 20000) for l in lens], KL, ISSUB)
+        out_fq = pr.hits(idx, [0] * len(reads), [min(l, 20000) for l in lens], KL_REV, ISSUB)
+        for q, (tag, _r) in enumerate(items):
+            for nm, got in (('suffix_q', out_sfx[q]), ('full_p', out_fp[q]), ('full_q', out_fq[q])):
+                g = hits_to_array(got)
+                want = scan_golden[tag + '|hits_' + nm]
+                assert g.shape == want.shape and np.array_equal(g, want), f'{tag} hits_{nm}: gpu {g.shape} ref {want.shape}'
+    assert n_checked > 60
+
+
+def test_per_read_functions_keep_reference_types(tgk, kmer_tables, golden_reads, scan_golden):
+    T = kmer_tables['human_hifi']
+    KL, ISSUB, CANON = T['KMER_LIST'], T['KMER_ISSUBSTRING'], T['CANONICAL_STRINGS']
+    rdat = golden_reads['human_hifi'][0][1]
+    tag = 'human_hifi|human_hifi|0'
+    bc = tgk.get_telomere_base_count(rdat, CANON)
+    assert isinstance(bc, int) and bc == int(scan_golden[tag + '|bc'][0])
+    ori = rc_py(rdat) if int(scan_golden[tag + '|flip'][0]) else rdat
+    e0, e1 = tgk.get_telomere_kmer_density(ori, KL, 100)
+    assert isinstance(e0, list) and isinstance(e1, list) and len(e0) == len(e1) == len(ori) - 100
+    assert e0 == (scan_golden[tag + '|dens_p'].astype(np.float64) / 100).tolist() and all(v == 0.0 for v in e1)
+    assert tgk.get_telomere_kmer_density('ACGT' * 10, KL, 100) == ([], [])
+    hits = tgk.get_nonoverlapping_kmer_hits(ori[-6000:], [rc_py(k) for k in KL], ISSUB)
+    assert isinstance(hits, list) and len(hits) == len(KL) and all(isinstance(s, list) and len(s) == 2 for h in hits for s in h)
+    assert np.array_equal(hits_to_array(hits), scan_golden[tag + '|hits_suffix_q'])
+    assert tgk.get_nonoverlapping_kmer_hits('', KL, ISSUB) == [[] for _ in KL]
+    assert tgk.get_telomere_base_count('', CANON) == 0
+
+
+def test_random_and_adversarial_vs_oracle(tgk, kmer_tables):
+    rng = np.random.default_rng(11)
+    T = kmer_tables['human_ont']
+    KL, ISSUB = T['KMER_LIST'], T['KMER_ISSUBSTRING']
+    reads = []
+    for n in (1, 2, 99, 100, 101, 127, 128, 129, 8191, 8192, 8193, 8292, 16500, 40000):
+        reads.append(''.join(rng.choice(list('ACGT'), n, p=[.25, .45, .1, .2])))
+    reads.append('C' * 20000)                                    # longest possible greedy chain across tiles
+    reads.append(('CCCTCC' * 3 + 'CCCTAA' * 2) * 1500)
+    reads.append('CCCTAA' * 1365 + 'CCCCCC' * 10 + 'CCCTAA' * 1400)   # tile boundary inside repeats
+    reads.append(''.join(rng.choice(list('ACGTN'), 9000, p=[.2, .5, .1, .15, .05])))
+    reads.append('acgtCCCTAACCCTAAxyzCCCTAA' * 40)              # lower case / junk never matches
+    pr = tgk.PackedReads(reads)
+    for lists in ((KL, [rc_py(k) for k in KL]), (['CCCCCC', 'CCC'], ['GGGTTA'])):
+        bc = pr.basecount(*lists).cpu().numpy()
+        for w in (100, 7, 255):
+            ca, cb = pr.density_counts(lists[0], lists[1], w)
+            ca, cb = pr.split_counts(ca.cpu().numpy(), w), pr.split_counts(cb.cpu().numpy(), w)
+            for q, r in enumerate(reads):
+                assert np.array_equal(ca[q].astype(np.int32), oracle.density_counts(r, lists[0], w)), (q, w)
+                assert np.array_equal(cb[q].astype(np.int32), oracle.density_counts(r, lists[1], w)), (q, w)
+        for q, r in enumerate(reads):
+            assert bc[q].tolist() == [oracle.base_count(r, lists[0]), oracle.base_count(r, lists[1])], q
+    short = [r for r in reads if len(r) <= 20000]
+    pr = tgk.PackedReads(short)
+    lens = [len(r) for r in short]
+    got = pr.hits(np.arange(len(short)), [0] * len(short), lens, KL, ISSUB)
+    for q, r in enumerate(short):
+        assert np.array_equal(hits_to_array(got[q]), hits_to_array(oracle.nonoverlapping_hits(r, KL, ISSUB))), q
+    # unaligned slices of one read
+    r = reads[15]
+    sl = [(3, 4100), (2047, 2049), (100, 100), (5, 37), (4090, 8200)]
+    pr = tgk.PackedReads([r])
+    got = pr.hits([0] * len(sl), [a for a, _ in sl], [b for _, b in sl], KL, ISSUB)
+    for q, (a, b) in enumerate(sl):
+        assert np.array_equal(hits_to_array(got[q]), hits_to_array(oracle.nonoverlapping_hits(r[a:b], KL, ISSUB))), (a, b)
+
+
+def test_orientation_rejects_non_acgtn_like_reference(tgk):
+    pr = tgk.PackedReads(['CCCTAACCCTAAxCCCTAA'])
+    with pytest.raises(KeyError):
+        pr.orient(np.array([1]))
+
+
+def test_scale_properties(tgk, kmer_tables, golden_reads):
+    """~100 Mbases replicated set: density of a replicated read equals the density of the original."""
+    T = kmer_tables['human_hifi']
+    KL = T['KMER_LIST']
+    KL_REV = [rc_py(k) for k in KL]
+    base = [r for _, r in golden_reads['human_hifi']]
+    reads = base * 400
+    pr = tgk.PackedReads(reads)
+    ca, cb = pr.density_counts(KL, KL_REV, 100)
+    ca = pr.split_counts(ca.cpu().numpy(), 100)
+    for q in range(len(base), len(reads), 37):
+        assert np.array_equal(ca[q], ca[q % len(base)])
+    bc = pr.basecount(KL, KL_REV).cpu().numpy()
+    assert np.array_equal(bc[:len(base)], bc[-len(base):])

@@ -1,0 +1,163 @@
+"""CPU: host-side logic of the product (no CUDA calls) + C-ABI surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import ROOT
+
+
+def test_scoring_matrix_matches_oracle_closed_form_and_literal_replay():
+    from telogator2_b200 import tg_align
+    for which in ('tvr', 'consensus'):
+        for canon in 'CDV':
+            assert np.array_equal(np.asarray(tg_align.get_scoring_matrix(canon, which)), oracle.scoring_matrix(canon, which))
+    # literal replay of tg_align.py:32-68 for all four types
+    A, G, U = tg_align.AMINO, tg_align.GAP_CHR, tg_align.UNKNOWN
+    for which in ('tvr', 'consensus', 'msa', 'msa_refinement'):
+        m = {}
+        for c1 in A:
+            m[c1, c1] = 5.
+            for c2 in A:
+                if c1 != c2:
+                    m[c1, c2] = -4.
+        m[U, U] = 2.
+        m[G, G] = 0.
+        for c1 in A:
+            m[c1, 'C'] = m['C', c1] = -4.
+            m[c1, U] = m[U, c1] = -2.
+            m[c1, G] = m[G, c1] = -4.
+        if which == 'tvr':
+            m['C', 'C'] = 0.; m['C', U] = m[U, 'C'] = -2.; m[U, G] = m[G, U] = -2.
+        elif which == 'consensus':
+            m['C', 'C'] = 1.; m['C', U] = m[U, 'C'] = -2.; m[U, G] = m[G, U] = -2.
+        elif which == 'msa':
+            m['C', 'C'] = 0.; m['C', U] = m[U, 'C'] = 1.; m[U, G] = m[G, U] = -2.
+        else:
+            for c1 in A:
+                m[c1, G] = m[G, c1] = 0.
+            m['C', 'C'] = 2.; m['C', U] = m[U, 'C'] = 1.; m[U, G] = m[G, U] = 1.
+        got = tg_align.get_scoring_matrix('C', which)
+        for (a, b), v in m.items():
+            assert got[a, b] == v, (which, a, b)
+
+
+def test_aligner_object_attributes():
+    from telogator2_b200 import tg_align
+    from telogator2_b200.dist_engine import Scoring
+    al = tg_align.get_aligner_object(None, (True, False), 'tvr')
+    sc = Scoring.from_aligner(al)
+    assert (sc.gap, sc.gap_left, sc.gap_right, sc.match, sc.mismatch, sc.alphabet) == (-4, -4, 0, 5, -4, None)
+    al = tg_align.get_aligner_object(tg_align.get_scoring_matrix('C', 'tvr'), (False, True), 'tvr')
+    sc = Scoring.from_aligner(al)
+    assert (sc.gap, sc.gap_left, sc.gap_right) == (-4, 0, -4) and sc.alphabet == 'ACDEFGHIKLMNPQRSTVWY-'
+    with pytest.raises(NotImplementedError):
+        Scoring.from_aligner(tg_align.get_aligner_object(None, (True, True), 'msa'))     # affine: MSA half, not score()
+    assert tg_align.MAX_SEQ_DIST == 10.0 and tg_align.MIN_VIABLE_SEQ_LEN == 1000 and tg_align.UNKNOWN == 'A'
+
+
+def test_pack_jobs_covers_every_alignment_once():
+    from telogator2_b200.dist_engine import pack_jobs
+    rng = np.random.default_rng(0)
+    for allow_mixed in (True, False):
+        n = rng.integers(1, 6, 101).astype(np.int32) * 100
+        m = rng.integers(1, 4, 101).astype(np.int32) * 100
+        ro = np.arange(101, dtype=np.int64) * 7
+        co = ro + 3
+        jobs = pack_jobs(ro, co, n, m, np.arange(101, dtype=np.int32), allow_mixed)
+        outs = jobs['out'].reshape(-1)
+        assert sorted(outs[outs >= 0].tolist()) == list(range(101))
+        for h in (0, 1):
+            ok = jobs['out'][:, h] >= 0
+            o = jobs['out'][ok, h]
+            assert np.array_equal(jobs['n'][ok, h], n[o]) and np.array_equal(jobs['m'][ok, h], m[o])
+            assert np.array_equal(jobs['row_off'][ok, h], ro[o]) and np.array_equal(jobs['col_off'][ok, h], co[o])
+        if not allow_mixed:
+            assert (jobs['n'][:, 0] == jobs['n'][:, 1]).all() and (jobs['m'][:, 0] == jobs['m'][:, 1]).all()
+        cost = np.maximum(jobs['n'][:, 0], jobs['n'][:, 1]) * np.maximum(jobs['m'][:, 0], jobs['m'][:, 1])
+        assert (np.diff(cost) <= 0).all()
+
+
+def test_pair_sharding_partitions_the_pair_space():
+    from telogator2_b200.multi_gpu import shard_pair_indices
+    for n_pairs in (0, 1, 4095, 4096, 100000):
+        for world in (1, 2, 3, 8):
+            parts = [shard_pair_indices(n_pairs, r, world) for r in range(world)]
+            allp = np.sort(np.concatenate(parts))
+            assert np.array_equal(allp, np.arange(n_pairs))
+            assert all((np.diff(p) > 0).all() for p in parts if len(p) > 1)
+
+
+def test_distance_epilogue_matches_python_scalar_path():
+    from telogator2_b200.dist_engine import DistEngine, NOT_COMPUTED
+    rng = np.random.default_rng(2)
+    n = 500
+    aln = rng.integers(-4000, 5000, n).astype(np.int32)
+    iden = rng.integers(1000, 5000, n) / 2.
+    rnd = rng.integers(-4000, 0, (n, 3)).astype(np.int32)
+    aln[:5] = rnd[:5].mean(axis=1).astype(np.int32) - 1          # rand >= aln branch
+    res = dict(aln=aln, rnd=rnd, iden=iden)
+    early = aln < -(0.9 * iden)
+    rnd[early] = NOT_COMPUTED
+    d = DistEngine.distances(res, 3)
+    for q in range(n):
+        a, i = float(aln[q]), float(iden[q])
+        if a < -(0.900 * i):
+            want = 10.0
+        else:
+            r = np.mean([float(v) for v in rnd[q]])
+            with np.errstate(all='ignore'):
+                want = 10.0 if r >= a else min(-np.log((a - r) / (i - r)), 10.0)
+            want = max(want, 0.0001)
+        assert (np.isnan(want) and np.isnan(d[q])) or d[q] == want, q
+
+
+def test_read_kmer_tsv_matches_reference(tmp_path, kmer_tables):
+    from telogator2_b200 import tg_kmer
+    for key, T in kmer_tables.items():
+        fn = tmp_path / (key + '.tsv')
+        fn.write_text(T['tsv_text'])
+        meta, issub, canon = tg_kmer.read_kmer_tsv(str(fn), T['read_type'])
+        assert meta[0] == T['KMER_LIST'] and meta[1] == T['KMER_COLORS'] and meta[2] == T['KMER_LETTER']
+        assert [list(f) for f in meta[3]] == T['KMER_FLAGS'] and all(isinstance(f, tuple) for f in meta[3])
+        assert issub == T['KMER_ISSUBSTRING'] and canon == T['CANONICAL_STRINGS']
+        assert tg_kmer.get_canonical_letter(str(fn), T['read_type']) == T['canonical_letter']
+    with pytest.raises(SystemExit):
+        tg_kmer.read_kmer_tsv(str(tmp_path / 'missing.tsv'), 'ont')
+
+
+def test_c_abi_exports_every_declared_symbol_and_table_builder(kmer_tables):
+    from telogator2_b200 import _lib
+    from telogator2_b200.build import build
+    build()
+    L = _lib.load()
+    header = open(os.path.join(ROOT, 'include', 'telogator2_b200.h')).read()
+    declared = set(re.findall(r'\b(tg_[a-z0-9_]+)\s*\(', header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.tg_version() == 1
+    # host-side table build (no GPU needed): limits are enforced, errors are reported, nothing throws
+    T = kmer_tables['human_ont']
+    blob = ''.join(T['KMER_LIST']).encode()
+    off = np.zeros(len(T['KMER_LIST']) + 1, dtype=np.int32)
+    off[1:] = np.cumsum([len(k) for k in T['KMER_LIST']])
+    host = np.zeros(L.tg_kmer_table_bytes(), dtype=np.uint8)
+    assert L.tg_kmer_table_build(blob, off.ctypes.data_as(ctypes.c_void_p), len(T['KMER_LIST']), None, None,
+                                 host.ctypes.data_as(ctypes.c_void_p)) == 0
+    hdr = host[:16].view(np.int32)
+    assert hdr[0] == len(T['KMER_LIST']) and hdr[2] == 20 and hdr[3] == 4      # CCCCCC, CCCTCC and the two HOR k-mers
+    bad = b'CCNTAA'
+    off2 = np.array([0, 6], dtype=np.int32)
+    assert L.tg_kmer_table_build(bad, off2.ctypes.data_as(ctypes.c_void_p), 1, None, None, host.ctypes.data_as(ctypes.c_void_p)) == _lib.TG_EINVAL
+    assert b'non-ACGT' in L.tg_last_error()
+    # compute entry points fail loudly without a device instead of falling back
+    import torch
+    if not torch.cuda.is_available():
+        n = ctypes.c_int(0)
+        assert L.tg_device_sm_count(ctypes.byref(n)) == _lib.TG_ECUDA
+        with pytest.raises(RuntimeError):
+            _lib.require_cuda()
