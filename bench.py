@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the Telogator2 hot path on B200.
+
+One "step" = one pass of the hot path over one batch of synthetic input derived from the bundled
+fixtures (tests/golden):
+  * DP   : the iter-0 all-vs-all TVR distance matrix (tvr matrix, gaps -4, adjust_lens + min_viable,
+           R = 2, seed 12345) over N colour vectors of length 1000 (SURVEY 8d "D1"),
+  * scan : base counts + orientation + density x2 + non-overlapping hits on the last 6000 bases
+           (SURVEY 8d "S x r") over replicated reads with seeded edits.
+`value` is DP GCUPS (cells as defined in SURVEY 8d / BASELINE.md 3) with inputs resident in HBM;
+`e2e` is the same metric through the public API (host strings in, float32 matrix out).  The scan
+numbers ride along in the `scan` object.  `--impl reference` times the CPU oracle port
+(oracle/tg_oracle.c, OpenMP over all host cores) on a bounded sample of the same workload.
+"""
+import argparse
+import gzip
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+METRIC = 'tvr_all_vs_all_gcups'
+LETTER_MIX = 'CCCCCCCCCCCCVVVHTFDA'
+
+
+def load_fixtures():
+    with gzip.open(os.path.join(GOLDEN, 'colorvecs.json.gz'), 'rt') as f:
+        cv = json.load(f)['colorvecs']
+    with gzip.open(os.path.join(GOLDEN, 'reads.json.gz'), 'rt') as f:
+        reads = json.load(f)
+    tables = json.load(open(os.path.join(GOLDEN, 'kmer_tables.json')))
+    return cv, reads, tables
+
+
+def make_dp_workload(cv, n_seq, seed=12345):
+    """D1: bundled colour vectors (truncate 1000) replicated with seeded 2 % letter edits."""
+    rng = np.random.default_rng(seed)
+    base = [c[:1000] for c in (cv['human_hifi'] + cv['human_ont']) if len(c) >= 1000]
+    mix = np.frombuffer(LETTER_MIX.encode(), dtype=np.uint8)
+    out = []
+    for i in range(n_seq):
+        s = np.frombuffer(base[i % len(base)].encode(), dtype=np.uint8).copy()
+        pos = rng.choice(len(s), 20, replace=False)
+        s[pos] = mix[rng.integers(len(mix), size=20)]
+        out.append(s.tobytes().decode())
+    return out
+
+
+def make_scan_workload(reads, n_bases, seed=12345):
+    """S x r: bundled HiFi + ONT reads replicated with seeded 0.5 % substitutions."""
+    rng = np.random.default_rng(seed)
+    base = [r for _, r in reads['human_hifi']] + [r for _, r in reads['human_ont']]
+    acgt = np.frombuffer(b'ACGT', dtype=np.uint8)
+    out, tot, i = [], 0, 0
+    while tot < n_bases:
+        s = np.frombuffer(base[i % len(base)].encode(), dtype=np.uint8).copy()
+        k = max(len(s) // 200, 1)
+        s[rng.integers(len(s), size=k)] = acgt[rng.integers(4, size=k)]
+        out.append(s.tobytes().decode())
+        tot += len(s)
+        i += 1
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 6 for k in range(4) if r[2 + k].lower().startswith('active')})
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                'samples': len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        return json.load(open(p)), 'measured (MEASURED_PEAKS.json)'
+    return {'hbm_gbs': 6650.0}, 'fallback (B200_PROFILING.md)'
+
+
+# ----------------------------------------------------------------------------------------------------
+# reference arm: the CPU oracle port, all host threads, bounded sample
+# ----------------------------------------------------------------------------------------------------
+def cpu_dp_sample(seqs, n_pairs_sample, threads):
+    import oracle
+    P = oracle.AlignerParams(oracle.scoring_matrix('C', 'tvr'), (True, True))
+    t0 = time.perf_counter()
+    _D, _a, _r, cells = oracle.dist_matrix_c(seqs, P, True, True, 2, 12345, pair_range=(0, n_pairs_sample),
+                                             n_threads=threads, want_scores=True)
+    dt = time.perf_counter() - t0
+    return cells / dt / 1e9, dt, cells
+
+
+def cpu_scan_sample(reads, tables, threads, budget_bases):
+    import oracle
+    from concurrent.futures import ThreadPoolExecutor
+    T = tables['human_hifi']
+    rc = oracle.rc
+    KL, CANON = T['KMER_LIST'], T['CANONICAL_STRINGS']
+    KLR, CR = [rc(k) for k in KL], [rc(k) for k in CANON]
+    ISSUB = T['KMER_ISSUBSTRING']
+    sample, tot = [], 0
+    for r in reads:
+        if tot >= budget_bases:
+            break
+        sample.append(r)
+        tot += len(r)
+
+    def one(r):                                  # ctypes releases the GIL inside the C calls
+        _f, ori, _c0, _c1, _bc = oracle.scan_read(r, KL, KLR, CANON, CR, 100)
+        oracle.nonoverlapping_hits(ori[-6000:], KLR, ISSUB)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(one, sample))
+    dt = time.perf_counter() - t0
+    return tot / dt / 1e6, dt, tot
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cv, reads, tables = load_fixtures()
+    threads = os.cpu_count() or 1
+    seqs = make_dp_workload(cv, args.n_seq)
+    sample_pairs = max(64, int(args.cpu_pairs))
+    vals, times = [], []
+    for it in range(args.warmup + args.steps):
+        g, dt, cells = cpu_dp_sample(seqs, sample_pairs, threads)
+        if it >= args.warmup:
+            vals.append(g)
+            times.append(dt)
+    scan_reads = make_scan_workload(reads, 2_000_000)
+    mb, sdt, sb = cpu_scan_sample(scan_reads, tables, threads, 2_000_000)
+    v = float(np.mean(vals))
+    line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'GCUPS', 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': float(np.mean(times) * 1e3), 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': f'D1 iter-0 TVR distance matrix N={args.n_seq} L=1000 R=2 (first {sample_pairs} pairs per step)',
+                       'n_seq': args.n_seq},
+            'cpu_baseline': {'value': v, 'unit': 'GCUPS', 'cores': threads, 'kind': 'port',
+                             'sample': f'oracle/tg_oracle.c (Biopython-style double-precision NW + MT19937 shuffles), OpenMP, first '
+                                       f'{sample_pairs} pairs of the same matrix per step; Biopython itself is not installable here'},
+            'e2e': {'value': v, 'unit': 'GCUPS', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'scan': {'value': mb, 'unit': 'Mbases/s', 'sample': f'{sb} bases, oracle C scan (base count x2, density x2, hits on last 6000)',
+                     'cores': threads},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--n-seq', type=int, default=2048, help='sequences per GPU in the DP workload (weak scaling)')
+    ap.add_argument('--scan-mbases', type=float, default=400.0, help='scan workload per GPU, Mbases')
+    ap.add_argument('--cpu-pairs', type=int, default=1500, help='pairs per step of the CPU sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    from telogator2_b200 import tg_align, tg_kmer
+    from telogator2_b200.dist_engine import DistEngine, Scoring
+    from telogator2_b200.multi_gpu import shard_pair_indices, gather_results
+
+    cv, reads, tables = load_fixtures()
+    # weak scaling: the pair space grows with the number of GPUs (n_seq * sqrt(world)), each rank owns 1/world of it
+    n_seq = int(round(args.n_seq * np.sqrt(world)))
+    seqs = make_dp_workload(cv, n_seq)
+    n_pairs = n_seq * (n_seq - 1) // 2
+    aligner = tg_align.get_aligner_object(tg_align.get_scoring_matrix('C', 'tvr'), (True, True), 'tvr')
+    R, SEED = 2, 12345
+    my_pairs = shard_pair_indices(n_pairs, rank, world)
+
+    T = tables['human_hifi']
+    KL, CANON, ISSUB = T['KMER_LIST'], T['CANONICAL_STRINGS'], T['KMER_ISSUBSTRING']
+    KLR, CR = [tg_kmer.RC(k) for k in KL], [tg_kmer.RC(k) for k in CANON]
+    scan_reads = make_scan_workload(reads, int(args.scan_mbases * 1e6), seed=12345 + rank)
+    scan_bases = sum(len(r) for r in scan_reads)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- DP: device-resident timing ----------------
+    eng = DistEngine(Scoring.from_aligner(aligner))
+
+    def dp_step():
+        eng.stats['cells'] = 0
+        eng.stats['launches'] = 0
+        res = eng.pair_scores(seqs, True, True, R, SEED, pair_idx=my_pairs)
+        return res
+
+    # ---------------- scan: device-resident timing ----------------
+    pr = tg_kmer.PackedReads(scan_reads)
+    lens = pr.lens
+    sl_idx = np.arange(pr.n)
+    sl_lo = np.maximum(lens - 6000, 0)
+
+    orig_planes = (pr.d_pack2, pr.d_nmask)
+    sl_hi = lens.copy()
+
+    def scan_step():
+        pr.d_pack2, pr.d_nmask = orig_planes
+        bc = pr.basecount(CANON, CR)                               # tg_tel.py:262-263
+        flip = (bc[:, 0] > bc[:, 1]).cpu().numpy()
+        pr.orient(flip)                                            # tg_tel.py:265-266
+        ca, cb = pr.density_counts(KL, KLR, 100)                   # tg_tel.py:160-161
+        spans = pr.hits_device(sl_idx, sl_lo, sl_hi, KLR, ISSUB)   # tg_tel.py:310 on the last 6000 bases
+        return flip, ca, cb, spans
+
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    sampler = ClockSampler(local_rank)
+    dp_ms, scan_ms, dens_ms = [], [], []
+    cells_step = 0
+    for it in range(args.warmup + args.steps):
+        timed = it >= args.warmup
+        if it == args.warmup:
+            barrier()
+            sampler.start()
+            t_wall0 = time.perf_counter()
+        barrier()
+        ev[0].record()
+        dp_step()
+        ev[1].record()
+        torch.cuda.synchronize()
+        cells_step = eng.stats['cells']
+        launches_dp = eng.stats['launches']
+        ev[2].record()
+        scan_step()
+        ev[3].record()
+        barrier()
+        if timed:
+            dp_ms.append(ev[0].elapsed_time(ev[1]))
+            scan_ms.append(ev[2].elapsed_time(ev[3]))
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+
+    def allmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        t = torch.tensor([x], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    dp_t = allmax(float(np.mean(dp_ms)) * 1e-3)
+    scan_t = allmax(float(np.mean(scan_ms)) * 1e-3)
+    cells_all = allsum(float(cells_step))
+    bases_all = allsum(float(scan_bases))
+    gcups = cells_all / dp_t / 1e9
+    scan_mbs = bases_all / scan_t / 1e6
+
+    # ---------------- kernel-level roofline numbers (rank 0, CUDA events around single launches) -----
+    roof, roof_scan = None, None
+    if rank == 0:
+        import ctypes as C
+        from telogator2_b200 import _lib
+        L = _lib.load()
+        dpx, mixed = C.c_double(0), C.c_double(0)
+        _lib.check(L.tg_int_alu_peak(2000, C.byref(dpx), C.byref(mixed)))
+        # dominant kernel: nw_wave_kernel.  Launch it alone on the phase-A jobs of a sub-matrix.
+        sub = seqs[:min(n_seq, 1024)]
+        e2 = DistEngine(Scoring.from_aligner(aligner))
+        codes, off, subm = e2.sc.encode_all(sub)
+        from telogator2_b200.dist_engine import pack_jobs
+        npz = len(sub) * (len(sub) - 1) // 2
+        iu = np.triu_indices(len(sub), 1)
+        ln = np.diff(off).astype(np.int32)
+        jobs = pack_jobs(off[iu[0]], off[iu[1]], ln[iu[0]], ln[iu[1]], np.arange(npz, dtype=np.int32), True)
+        d_codes = e2._to_dev(codes)
+        e2.run_jobs(d_codes, jobs, subm, npz)
+        torch.cuda.synchronize()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ks = []
+        for _ in range(3):
+            k0.record()
+            e2.run_jobs(d_codes, jobs, subm, npz)
+            k1.record()
+            torch.cuda.synchronize()
+            ks.append(k0.elapsed_time(k1) * 1e-3)
+        kcells = float((ln[iu[0]].astype(np.int64) * ln[iu[1]]).sum())
+        k_gcups = kcells / min(ks) / 1e9
+        instr_per_cell = 1.5                       # minimal s16x2 cost of the linear-gap cell
+        peak_gcups = dpx.value / instr_per_cell / 1e9
+        roof = {'bound': 'int_alu', 'kernel': 'nw_wave_kernel', 'achieved': k_gcups, 'peak': peak_gcups, 'unit': 'GCUPS',
+                'frac': k_gcups / peak_gcups, 'traffic': None,
+                'peak_source': f'measured in this run: {dpx.value / 1e12:.2f} T VIMNMX3.U16x2 lane-ops/s (tg_int_alu_peak) / 1.5 instr per cell '
+                               f'(SURVEY 8d); add+max3 pair rate {mixed.value / 1e12:.2f} T pairs/s',
+                'launch_ms': min(ks) * 1e3, 'cells_per_launch': kcells}
+        # scan: density kernel alone, algorithmic bytes 2.375 B/base
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ds = []
+        for _ in range(3):
+            d0.record()
+            pr.density_counts(KL, KLR, 100)
+            d1.record()
+            torch.cuda.synchronize()
+            ds.append(d0.elapsed_time(d1) * 1e-3)
+        pk, src = peaks()
+        ach = scan_bases * 2.375 / min(ds) / 1e9
+        roof_scan = {'bound': 'hbm', 'kernel': 'scan_cov_kernel<density>', 'achieved': ach, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
+                     'frac': ach / pk['hbm_gbs'], 'traffic': None, 'peak_source': src, 'launch_ms': min(ds) * 1e3,
+                     'bytes_per_base': 2.375, 'mbases_per_s': scan_bases / min(ds) / 1e6}
+
+    # ---------------- e2e through the public API: host strings -> float32 matrix on the host --------
+    e2e_ms = []
+    h2d = d2h = 0
+    for it in range(2):
+        barrier()
+        t0 = time.perf_counter()
+        eng2 = DistEngine(Scoring.from_aligner(aligner))
+        res = eng2.pair_scores(seqs, True, True, R, SEED, pair_idx=my_pairs)
+        if world > 1:
+            res = gather_results(res, dist, eng2.device)
+        D = eng2.dist_matrix(seqs, True, True, R, SEED, res=res)
+        barrier()
+        e2e_ms.append((time.perf_counter() - t0) * 1e3)
+        h2d, d2h = eng2.stats['h2d_bytes'], eng2.stats['d2h_bytes']
+    e2e_t = allmax(min(e2e_ms) * 1e-3)
+    e2e_gcups = cells_all / e2e_t / 1e9
+    assert D.shape == (n_seq, n_seq)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        g, dt, cells = cpu_dp_sample(seqs, args.cpu_pairs, threads)
+        smb, sdt, sb = cpu_scan_sample(scan_reads, tables, threads, 2_000_000)
+        cpu = {'value': g, 'unit': 'GCUPS', 'cores': threads, 'kind': 'port',
+               'sample': f'oracle C port (Biopython-style f64 NW + MT19937), OpenMP {threads} threads, first {args.cpu_pairs} pairs of the same '
+                         f'matrix ({dt:.1f} s); scan: {smb:.2f} Mbases/s on {sb} bases ({sdt:.1f} s)',
+               'scan_mbases_per_s': smb}
+
+    if rank == 0:
+        line = {'metric': METRIC, 'value': gcups, 'unit': 'GCUPS', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+                'ms_per_step': dp_t * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u16',
+                'data': 'synthetic',
+                'config': {'workload': f'D1 iter-0 TVR distance matrix, N={n_seq} colour vectors (bundled reads replicated with 2% edits), '
+                                       f'L=1000, tvr matrix, gaps -4, R=2, seed 12345; pairs sharded over {world} GPU(s)',
+                           'n_seq': n_seq, 'pairs': n_pairs, 'l2_policy': 'inputs larger than L2 are not needed: DP is ALU bound; '
+                                                                            'each step re-uploads jobs and regenerates all shuffles',
+                           'scan_workload': f'{bases_all / 1e6:.0f} Mbases of bundled HiFi+ONT reads replicated with 0.5% edits, K=57, window 100'},
+                'e2e': {'value': e2e_gcups, 'unit': 'GCUPS', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+                        'ms_per_step': e2e_t * 1e3},
+                'gpu_launches': int(launches_dp + 4),
+                'scan': {'value': scan_mbs, 'unit': 'Mbases/s', 'ms_per_step': scan_t * 1e3,
+                         'what': 'basecount x2 + orient + density x2 + hits on the last 6000 bases of every read (device resident)'},
+                'roofline': roof, 'roofline_scan': roof_scan, 'cpu_baseline': cpu, 'clocks': clocks,
+                'wall_s_timed_region': t_wall}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

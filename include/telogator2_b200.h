@@ -66,8 +66,9 @@ typedef struct tg_nw_scoring {
  * Needleman-Wunsch score with linear gaps and left/right end-gap classes.
  *
  * tg_nw_scores_wave: warp-wavefront u16x2 DPX kernel (two alignments per register lane).
- *   Envelope (else TG_ERANGE): gap_left == gap, gap_right in {gap, >= gap with equal shapes in
- *   both halves}, 0 <= sub - 2*gap <= 127, max(sub - 2*gap) * min(n, m) <= 65535 per half.
+ *   Envelope (else TG_ERANGE): alphabet <= 31, gap_left == gap, gap_right >= gap,
+ *   0 <= sub - 2*gap <= 127, max(sub - 2*gap) * min(max n, max m) <= 65535 over the two halves.
+ *   The two halves of a job may have different shapes.
  *   d_scratch: tg_nw_wave_scratch_bytes(max_n) bytes; d_counter: one zeroed int32.
  * tg_nw_scores_generic: int32 row-scan kernel, any gap scores, half 0 and half 1 processed
  *   as separate alignments; max(m) bounded by shared memory (tg_nw_generic_max_m()). */

@@ -17,13 +17,11 @@
 // recovered afterwards as max over the last row / last column of H (see the epilogue).
 #include "tg_common.cuh"
 #include <limits.h>
+#include <stdlib.h>
 
 namespace {
 
-constexpr int WAVE_C = 16;                 // packed columns held in registers by each lane
-constexpr int WAVE_W = 32 * WAVE_C;        // columns per column block (one warp)
-constexpr int WAVE_WARPS = 4;              // warps (= concurrent jobs) per CTA
-constexpr int WAVE_CTAS_PER_SM = 2;
+constexpr int WAVE_MAX_WARPS = 12;         // warps (= concurrent jobs) per CTA, one CTA per SM
 constexpr int MAXA = 32;
 
 struct WaveParams {
@@ -34,7 +32,8 @@ struct WaveParams {
     uint32_t *scratch;          // per-warp border column, scratch_stride u32 each
     unsigned long long *counter;
     int scratch_stride;
-    int A;                      // alphabet size
+    int row_cap;                // rows of the shared-memory row-letter buffer per warp
+    int A;                      // alphabet size; code A is the all-zero padding letter
     int g, gr;                  // internal gap, right end gap
     int right_free;             // gr != g
     uint8_t sp[MAXA * MAXA];    // S' = S - 2g, row-major [a][b] with stride MAXA
@@ -60,19 +59,77 @@ __device__ __forceinline__ uint32_t cell(uint32_t diag, uint32_t sc, uint32_t up
     return __vimax3_u16x2(diag + sc, up, left);
 }
 
-__global__ void __launch_bounds__(WAVE_WARPS * 32, WAVE_CTAS_PER_SM)
-nw_wave_kernel(const __grid_constant__ WaveParams P)
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
 {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// One step of one lane: C packed cells of row r against the lane's C columns.
+template <int C>
+struct Strip;
+
+template <>
+struct Strip<16> {
+    static __device__ __forceinline__ void run(uint32_t (&H)[16], uint32_t d, uint32_t l, uint32_t pa0, uint32_t pa1)
+    {
+        const uint4 q0 = lds128(pa0), q1 = lds128(pa1);
+        uint32_t up;
+#define TG_CELL(c, qa, qb, k) up = H[c]; l = cell(d, merge_scores<k>(qa, qb), up, l); d = up; H[c] = l;
+        TG_CELL(0, q0.x, q1.x, 0) TG_CELL(1, q0.x, q1.x, 1) TG_CELL(2, q0.x, q1.x, 2) TG_CELL(3, q0.x, q1.x, 3)
+        TG_CELL(4, q0.y, q1.y, 0) TG_CELL(5, q0.y, q1.y, 1) TG_CELL(6, q0.y, q1.y, 2) TG_CELL(7, q0.y, q1.y, 3)
+        TG_CELL(8, q0.z, q1.z, 0) TG_CELL(9, q0.z, q1.z, 1) TG_CELL(10, q0.z, q1.z, 2) TG_CELL(11, q0.z, q1.z, 3)
+        TG_CELL(12, q0.w, q1.w, 0) TG_CELL(13, q0.w, q1.w, 1) TG_CELL(14, q0.w, q1.w, 2) TG_CELL(15, q0.w, q1.w, 3)
+    }
+};
+
+template <>
+struct Strip<8> {
+    static __device__ __forceinline__ void run(uint32_t (&H)[8], uint32_t d, uint32_t l, uint32_t pa0, uint32_t pa1)
+    {
+        const uint2 q0 = lds64(pa0), q1 = lds64(pa1);
+        uint32_t up;
+        TG_CELL(0, q0.x, q1.x, 0) TG_CELL(1, q0.x, q1.x, 1) TG_CELL(2, q0.x, q1.x, 2) TG_CELL(3, q0.x, q1.x, 3)
+        TG_CELL(4, q0.y, q1.y, 0) TG_CELL(5, q0.y, q1.y, 1) TG_CELL(6, q0.y, q1.y, 2) TG_CELL(7, q0.y, q1.y, 3)
+#undef TG_CELL
+    }
+};
+
+// Shared memory per warp: query profile [2][A+1][W] bytes, then row letters [row_cap] u16 (a0 | a1 << 8).
+template <int C>
+__global__ void __launch_bounds__(WAVE_MAX_WARPS * 32, 1) nw_wave_kernel(const __grid_constant__ WaveParams P)
+{
+    constexpr int W = 32 * C;
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int A = P.A;
-    uint8_t *s_sp = smem;                                              // MAXA*MAXA bytes
-    uint8_t *prof = smem + MAXA * MAXA + (size_t)warp * (2 * A * WAVE_W);   // [2][A][WAVE_W]
+    const int A = P.A, A1 = P.A + 1;
+    uint8_t *s_sp = smem;                                                    // MAXA*MAXA bytes
+    const size_t per_warp = (size_t)2 * A1 * W + (size_t)P.row_cap * 2;
+    uint8_t *prof = smem + MAXA * MAXA + (size_t)warp * per_warp;            // [2][A+1][W]
+    uint16_t *rows = reinterpret_cast<uint16_t *>(prof + (size_t)2 * A1 * W);
     for (int i = threadIdx.x; i < MAXA * MAXA; i += blockDim.x) s_sp[i] = P.sp[i];
     __syncthreads();
 
-    uint32_t *bord = P.scratch + (size_t)(blockIdx.x * WAVE_WARPS + warp) * P.scratch_stride;
+    const int nwarps = blockDim.x >> 5;
+    uint32_t *bord = P.scratch + (size_t)(blockIdx.x * nwarps + warp) * P.scratch_stride;
     const int g = P.g, gr = P.gr;
+    const uint32_t prof_s = (uint32_t)__cvta_generic_to_shared(prof);
+    const uint32_t rows_s = (uint32_t)__cvta_generic_to_shared(rows);
+    const uint32_t pb0 = prof_s + lane * C;
+    const uint32_t pb1 = prof_s + (uint32_t)A1 * W + lane * C;
 
     for (;;) {
         unsigned long long jid = 0;
@@ -85,83 +142,84 @@ nw_wave_kernel(const __grid_constant__ WaveParams P)
         const int n0 = J->n[0], n1 = J->n[1], m0 = J->m[0], m1 = J->m[1];
         const int out0 = J->out[0], out1 = J->out[1];
         const int N = max(n0, n1), M = max(m0, m1);
-        const int nblk = (M + WAVE_W - 1) / WAVE_W;
-        const int pad0 = nblk * WAVE_W - m0, pad1 = nblk * WAVE_W - m1;   // left padding (right-aligned columns)
-        uint32_t res0 = 0, res1 = 0;
+        const int nblk = (M + W - 1) / W;
+        const int pad0 = nblk * W - m0, pad1 = nblk * W - m1;     // left padding (right-aligned columns)
         int rf0 = INT_MIN, rf1 = INT_MIN;
+        uint32_t H[C];
+
+        // row letters of both alignments; rows past the end of a sequence get the padding letter A, whose
+        // all-zero profile row makes H' copy the previous row (H' is non-decreasing along a row)
+        __syncwarp();
+        for (int r = lane; r < N + 1; r += 32) {
+            const uint32_t a0 = (r < n0) ? (uint32_t)__ldg(P.pool + row0 + r) : (uint32_t)A;
+            const uint32_t a1 = (r < n1) ? (uint32_t)__ldg(P.pool + row1 + r) : (uint32_t)A;
+            rows[r] = (uint16_t)(a0 | (a1 << 8));
+        }
 
         for (int blk = 0; blk < nblk; blk++) {
             // ---- query profile of this column block: prof[h][a][x] = S'(a, colseq_h[x]) (0 on padding) ----
             __syncwarp();
-            for (int x = lane; x < WAVE_W; x += 32) {
-                const int X = blk * WAVE_W + x;
+            for (int x = lane; x < W; x += 32) {
+                const int X = blk * W + x;
                 const int j0 = X - pad0, j1 = X - pad1;
                 const int b0 = (j0 >= 0) ? (int)__ldg(P.pool + col0 + j0) : -1;
                 const int b1 = (j1 >= 0) ? (int)__ldg(P.pool + col1 + j1) : -1;
                 for (int a = 0; a < A; a++) {
-                    prof[(size_t)a * WAVE_W + x] = (b0 >= 0) ? s_sp[a * MAXA + b0] : (uint8_t)0;
-                    prof[(size_t)(A + a) * WAVE_W + x] = (b1 >= 0) ? s_sp[a * MAXA + b1] : (uint8_t)0;
+                    prof[(size_t)a * W + x] = (b0 >= 0) ? s_sp[a * MAXA + b0] : (uint8_t)0;
+                    prof[(size_t)(A1 + a) * W + x] = (b1 >= 0) ? s_sp[a * MAXA + b1] : (uint8_t)0;
                 }
+                prof[(size_t)A * W + x] = 0;
+                prof[(size_t)(A1 + A) * W + x] = 0;
             }
             __syncwarp();
 
-            uint32_t H[WAVE_C];
 #pragma unroll
-            for (int c = 0; c < WAVE_C; c++) H[c] = 0u;
+            for (int c = 0; c < C; c++) H[c] = 0u;
             uint32_t prev_left = 0u;
-            // border column of the previous block, 32 rows at a time
-            uint32_t bcur = (blk > 0 && lane < N) ? __ldcg(bord + lane) : 0u;
-            uint32_t bnext = (blk > 0 && 32 + lane < N) ? __ldcg(bord + 32 + lane) : 0u;
-            const uint8_t *pb0 = prof + lane * WAVE_C;
-            const uint8_t *pb1 = prof + (size_t)A * WAVE_W + lane * WAVE_C;
-            int r = -lane;
-            uint32_t a0 = (r == 0) ? (uint32_t)__ldg(P.pool + row0) : 0u;
-            uint32_t a1 = (r == 0) ? (uint32_t)__ldg(P.pool + row1) : 0u;
-            const bool last_blk = (blk == nblk - 1);
             const int steps = N + 31;
+            int r = -lane;
+            uint32_t ap = (r == 0) ? lds_u16(rows_s) : 0u;        // letters of this lane's next row
+            uint32_t *bw = bord + r;                              // lane 31 stores its last column here
 
-            for (int s = 0; s < steps; s++, r++) {
-                if ((s & 31) == 0 && s > 0) {
-                    bcur = bnext;
-                    const int idx = s + 32 + lane;
-                    bnext = (blk > 0 && idx < N) ? __ldcg(bord + idx) : 0u;
+            if (blk == 0) {
+                for (int s = 0; s < steps; s++, r++, bw++) {
+                    uint32_t left_in = __shfl_up_sync(TG_FULL_MASK, H[C - 1], 1);
+                    if (lane == 0) left_in = 0u;
+                    if ((unsigned)r < (unsigned)N) {
+                        Strip<C>::run(H, prev_left, left_in, pb0 + (ap & 0xffu) * W, pb1 + (ap >> 8) * W);
+                        if (lane == 31) *bw = H[C - 1];
+                        ap = lds_u16(rows_s + 2 * (r + 1));
+                    } else if (r == -1) ap = lds_u16(rows_s);
+                    prev_left = left_in;
                 }
-                uint32_t left_in = __shfl_up_sync(TG_FULL_MASK, H[WAVE_C - 1], 1);
-                const uint32_t bl = __shfl_sync(TG_FULL_MASK, bcur, s & 31);
-                if (lane == 0) left_in = bl;
-                if (r >= 0 && r < N) {
-                    const uint4 q0 = *reinterpret_cast<const uint4 *>(pb0 + a0 * WAVE_W);
-                    const uint4 q1 = *reinterpret_cast<const uint4 *>(pb1 + a1 * WAVE_W);
-                    uint32_t d = prev_left, l = left_in, up;
-#define TG_CELL(c, qa, qb, k)                        \
-    up = H[c];                                       \
-    l = cell(d, merge_scores<k>(qa, qb), up, l);     \
-    d = up;                                          \
-    H[c] = l;
-                    TG_CELL(0, q0.x, q1.x, 0) TG_CELL(1, q0.x, q1.x, 1) TG_CELL(2, q0.x, q1.x, 2) TG_CELL(3, q0.x, q1.x, 3)
-                    TG_CELL(4, q0.y, q1.y, 0) TG_CELL(5, q0.y, q1.y, 1) TG_CELL(6, q0.y, q1.y, 2) TG_CELL(7, q0.y, q1.y, 3)
-                    TG_CELL(8, q0.z, q1.z, 0) TG_CELL(9, q0.z, q1.z, 1) TG_CELL(10, q0.z, q1.z, 2) TG_CELL(11, q0.z, q1.z, 3)
-                    TG_CELL(12, q0.w, q1.w, 0) TG_CELL(13, q0.w, q1.w, 1) TG_CELL(14, q0.w, q1.w, 2) TG_CELL(15, q0.w, q1.w, 3)
-#undef TG_CELL
-                    if (lane == 31) bord[r] = H[WAVE_C - 1];
-                    if (last_blk) {
-                        if (r == n0 - 1) res0 = H[WAVE_C - 1] & 0xffffu;
-                        if (r == n1 - 1) res1 = H[WAVE_C - 1] >> 16;
+            } else {
+                // border column of the previous block, 32 rows at a time
+                uint32_t bcur = (lane < N) ? __ldcg(bord + lane) : 0u;
+                uint32_t bnext = (32 + lane < N) ? __ldcg(bord + 32 + lane) : 0u;
+                for (int s = 0; s < steps; s++, r++, bw++) {
+                    if ((s & 31) == 0 && s > 0) {
+                        bcur = bnext;
+                        const int idx = s + 32 + lane;
+                        bnext = (idx < N) ? __ldcg(bord + idx) : 0u;
                     }
+                    uint32_t left_in = __shfl_up_sync(TG_FULL_MASK, H[C - 1], 1);
+                    const uint32_t bl = __shfl_sync(TG_FULL_MASK, bcur, s & 31);
+                    if (lane == 0) left_in = bl;
+                    if ((unsigned)r < (unsigned)N) {
+                        Strip<C>::run(H, prev_left, left_in, pb0 + (ap & 0xffu) * W, pb1 + (ap >> 8) * W);
+                        if (lane == 31) *bw = H[C - 1];
+                        ap = lds_u16(rows_s + 2 * (r + 1));
+                    } else if (r == -1) ap = lds_u16(rows_s);
+                    prev_left = left_in;
                 }
-                prev_left = left_in;
-                const int rn = r + 1;
-                a0 = (rn >= 0 && rn < n0) ? (uint32_t)__ldg(P.pool + row0 + rn) : 0u;
-                a1 = (rn >= 0 && rn < n1) ? (uint32_t)__ldg(P.pool + row1 + rn) : 0u;
             }
             __syncwarp();
 
             if (P.right_free) {
-                // last row of H for this block (both halves have the same shape in this mode):
-                // H[n][j] + gr*(m-j) = H'[n][j] + g*(n+j) + gr*(m-j)
+                // last row of H for this block: H[n][j] + gr*(m-j) = H'[n][j] + g*(n+j) + gr*(m-j)
 #pragma unroll
-                for (int c = 0; c < WAVE_C; c++) {
-                    const int X = blk * WAVE_W + lane * WAVE_C + c;
+                for (int c = 0; c < C; c++) {
+                    const int X = blk * W + lane * C + c;
                     const int j0 = X - pad0 + 1, j1 = X - pad1 + 1;     // 1-based column
                     if (j0 >= 1) rf0 = max(rf0, (int)(H[c] & 0xffffu) + g * (n0 + j0) + gr * (m0 - j0));
                     if (j1 >= 1) rf1 = max(rf1, (int)(H[c] >> 16) + g * (n1 + j1) + gr * (m1 - j1));
@@ -170,9 +228,10 @@ nw_wave_kernel(const __grid_constant__ WaveParams P)
         }
 
         if (!P.right_free) {
+            // the padding rows carried row n of each alignment down to row N: lane 31's last column is H'[n][m]
             if (lane == 31) {
-                if (out0 >= 0) P.scores[out0] = (int)res0 + g * (n0 + m0);
-                if (out1 >= 0) P.scores[out1] = (int)res1 + g * (n1 + m1);
+                if (out0 >= 0) P.scores[out0] = (int)(H[C - 1] & 0xffffu) + g * (n0 + m0);
+                if (out1 >= 0) P.scores[out1] = (int)(H[C - 1] >> 16) + g * (n1 + m1);
             }
         } else {
             // last column: bord[r] = H'[r+1][m]; H[i][m] + gr*(n-i) = H'[i][m] + g*(i+m) + gr*(n-i)
@@ -322,7 +381,11 @@ __global__ void __launch_bounds__(MT_THREADS) mt_shuffle_kernel(uint8_t *pool, c
         for (int rep = 0; rep < 2 * R; rep++) {
             const int len = (rep & 1) ? J.m : J.n;
             const uint8_t *src = pool + ((rep & 1) ? J.src_j : J.src_i);
-            for (int x = 0; x < len; x++) sp[x] = src[x];         // pool = list(population)
+            // Working array: pool = list(population) shrinks from the back while the selected items fill the
+            // vacated back slots, i.e. result[i] ends up at arr[len-1-i].  Shared memory when it fits
+            // (pool_stride > 0), else in place in the destination region.
+            uint8_t *arr = pool_stride > 0 ? sp : pool + dst;
+            for (int x = 0; x < len; x++) arr[x] = src[x];
             int i = 0;
             while (i < len) {
                 // genrand_uint32, lazy twist of word kk
@@ -340,9 +403,18 @@ __global__ void __launch_bounds__(MT_THREADS) mt_shuffle_kernel(uint8_t *pool, c
                 const uint32_t nn = (uint32_t)(len - i);
                 const uint32_t r = y >> __clz(nn);                 // 32 - bit_length(nn) == clz(nn)
                 if (r < nn) {
-                    pool[dst + i] = sp[r];                         // result[i] = pool[j]
-                    sp[r] = sp[nn - 1];                            // pool[j] = pool[n-i-1]
+                    const uint8_t v = arr[r];                      // result[i] = pool[j]
+                    arr[r] = arr[nn - 1];                          // pool[j] = pool[n-i-1]
+                    arr[nn - 1] = v;
                     i++;
+                }
+            }
+            if (pool_stride > 0) {
+                for (int x = 0; x < len; x++) pool[dst + x] = sp[len - 1 - x];
+            } else {
+                for (int x = 0; x < len / 2; x++) {
+                    const uint8_t a = arr[x], b = arr[len - 1 - x];
+                    arr[x] = b; arr[len - 1 - x] = a;
                 }
             }
             dst += len;
@@ -384,17 +456,29 @@ __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t *out, int iters,
 // ================================================================================================
 // C ABI
 // ================================================================================================
+static int g_wave_c = 16;          // packed columns per lane (8 or 16); TG_WAVE_C overrides
+static int g_wave_warps = 0;       // 0 = as many as shared memory allows
+
+static void wave_env()
+{
+    static bool done = false;
+    if (done) return;
+    done = true;
+    if (const char *e = getenv("TG_WAVE_C")) { const int v = atoi(e); if (v == 8 || v == 16) g_wave_c = v; }
+    if (const char *e = getenv("TG_WAVE_WARPS")) { const int v = atoi(e); if (v >= 1 && v <= WAVE_MAX_WARPS) g_wave_warps = v; }
+}
+
 TG_EXPORT size_t tg_nw_wave_scratch_bytes(int max_n)
 {
     const int sms = tg_sm_count();
     const size_t stride = ((size_t)max_n + 63) / 32 * 32;
-    return (size_t)(sms > 0 ? sms : 148) * WAVE_CTAS_PER_SM * WAVE_WARPS * stride * sizeof(uint32_t);
+    return (size_t)(sms > 0 ? sms : 148) * WAVE_MAX_WARPS * stride * sizeof(uint32_t);
 }
 
 static int wave_envelope(const tg_nw_scoring *sc, int *max_sp_out)
 {
     if (!sc) return tg_set_err(TG_EINVAL, "scoring is NULL");
-    if (sc->alphabet < 1 || sc->alphabet > MAXA) return tg_set_err(TG_EINVAL, "alphabet %d outside 1..%d", sc->alphabet, MAXA);
+    if (sc->alphabet < 1 || sc->alphabet >= MAXA) return tg_set_err(TG_EINVAL, "alphabet %d outside 1..%d", sc->alphabet, MAXA - 1);
     if (sc->gap_left != sc->gap) return tg_set_err(TG_ERANGE, "wave kernel needs gap_left == gap");
     if (sc->gap_right < sc->gap) return tg_set_err(TG_ERANGE, "wave kernel needs gap_right >= gap");
     int max_sp = 0;
@@ -413,7 +497,6 @@ TG_EXPORT int tg_nw_wave_check(const tg_nw_scoring *sc, const tg_nw_job *h_jobs,
     int max_sp = 0;
     int rc = wave_envelope(sc, &max_sp);
     if (rc != TG_OK) return rc;
-    const bool rf = sc->gap_right != sc->gap;
     for (int64_t q = 0; q < n_jobs; q++) {
         const tg_nw_job &J = h_jobs[q];
         for (int h = 0; h < 2; h++)
@@ -421,8 +504,6 @@ TG_EXPORT int tg_nw_wave_check(const tg_nw_scoring *sc, const tg_nw_job *h_jobs,
         const long long N = J.n[0] > J.n[1] ? J.n[0] : J.n[1], M = J.m[0] > J.m[1] ? J.m[0] : J.m[1];
         if ((long long)max_sp * (N < M ? N : M) > 65535)
             return tg_set_err(TG_ERANGE, "job %lld (%lld x %lld) overflows 16-bit scores", (long long)q, N, M);
-        if (rf && (J.n[0] != J.n[1] || J.m[0] != J.m[1]))
-            return tg_set_err(TG_ERANGE, "job %lld: free right end gaps need equal shapes in both halves", (long long)q);
     }
     return TG_OK;
 }
@@ -432,10 +513,12 @@ TG_EXPORT int tg_nw_scores_wave(const uint8_t *d_pool, const tg_nw_job *d_jobs, 
                                 void *stream)
 {
     if (n_jobs <= 0) return TG_OK;
+    wave_env();
     int max_sp = 0;
     int rc = wave_envelope(sc, &max_sp);
     if (rc != TG_OK) return rc;
     if (!d_pool || !d_jobs || !d_scores || !d_scratch || !d_counter) return tg_set_err(TG_EINVAL, "NULL device pointer");
+    if (max_n < 1) return tg_set_err(TG_EINVAL, "max_n < 1");
     const int sms = tg_sm_count();
     if (sms <= 0) return tg_set_err(TG_ECUDA, "no CUDA device");
     WaveParams P;
@@ -443,19 +526,30 @@ TG_EXPORT int tg_nw_scores_wave(const uint8_t *d_pool, const tg_nw_job *d_jobs, 
     P.scratch = reinterpret_cast<uint32_t *>(d_scratch);
     P.counter = reinterpret_cast<unsigned long long *>(d_counter);
     P.scratch_stride = (int)(((size_t)max_n + 63) / 32 * 32);
+    P.row_cap = (max_n + 1 + 7) / 8 * 8;
     P.A = sc->alphabet; P.g = sc->gap; P.gr = sc->gap_right; P.right_free = (sc->gap_right != sc->gap);
     for (int a = 0; a < MAXA; a++)
         for (int b = 0; b < MAXA; b++)
             P.sp[a * MAXA + b] = (a < sc->alphabet && b < sc->alphabet) ? (uint8_t)(sc->sub[a * MAXA + b] - 2 * sc->gap) : 0;
-    const size_t smem = MAXA * MAXA + (size_t)WAVE_WARPS * 2 * sc->alphabet * WAVE_W;
-    TG_CUDA_CHECK(cudaFuncSetAttribute(nw_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int C = g_wave_c;
+    const size_t per_warp = (size_t)2 * (sc->alphabet + 1) * 32 * C + (size_t)P.row_cap * 2;
+    int warps = (int)((226 * 1024 - MAXA * MAXA) / per_warp);
+    if (warps > WAVE_MAX_WARPS) warps = WAVE_MAX_WARPS;
+    if (g_wave_warps && warps > g_wave_warps) warps = g_wave_warps;
+    if (warps < 1) return tg_set_err(TG_ERANGE, "sequences of %d rows do not fit the wave kernel's shared memory", max_n);
+    const size_t smem = MAXA * MAXA + (size_t)warps * per_warp;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     TG_CUDA_CHECK(cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), st));
-    long long warps_needed = n_jobs;
-    int grid = sms * WAVE_CTAS_PER_SM;
-    const long long ctas_needed = (warps_needed + WAVE_WARPS - 1) / WAVE_WARPS;
-    if (ctas_needed < grid) grid = (int)ctas_needed;
-    nw_wave_kernel<<<grid, WAVE_WARPS * 32, smem, st>>>(P);
+    long long grid = sms;
+    const long long ctas_needed = (n_jobs + warps - 1) / warps;
+    if (ctas_needed < grid) grid = ctas_needed;
+    if (C == 16) {
+        TG_CUDA_CHECK(cudaFuncSetAttribute(nw_wave_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        nw_wave_kernel<16><<<(int)grid, warps * 32, smem, st>>>(P);
+    } else {
+        TG_CUDA_CHECK(cudaFuncSetAttribute(nw_wave_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        nw_wave_kernel<8><<<(int)grid, warps * 32, smem, st>>>(P);
+    }
     TG_CUDA_CHECK(cudaGetLastError());
     return TG_OK;
 }
@@ -504,8 +598,11 @@ TG_EXPORT int tg_mt_shuffle(uint8_t *d_pool, const tg_shuffle_job *d_jobs, int64
     int stride = (max_len + 3) / 4;
     if ((stride & 1) == 0) stride++;
     stride *= 4;
-    const size_t smem = 624 * MT_THREADS * sizeof(uint32_t) + (size_t)MT_THREADS * stride;
-    if (smem > 227 * 1024) return tg_set_err(TG_ERANGE, "max_len %d too long for the shuffle kernel", max_len);
+    size_t smem = 624 * MT_THREADS * sizeof(uint32_t) + (size_t)MT_THREADS * stride;
+    if (smem > 200 * 1024) {          // long sequences: shuffle in place in global memory
+        stride = 0;
+        smem = 624 * MT_THREADS * sizeof(uint32_t);
+    }
     static thread_local int base_uploaded_dev = -1;
     int dev = 0;
     TG_CUDA_CHECK(cudaGetDevice(&dev));

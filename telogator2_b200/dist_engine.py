@@ -187,14 +187,11 @@ class DistEngine:
         if self.force_generic or sc.gap_left != sc.gap or sc.gap_right < sc.gap:
             return np.zeros(len(jobs), dtype=bool)
         sp = sub - 2 * sc.gap
-        if sp.min() < 0 or sp.max() > 127:
+        if sp.min() < 0 or sp.max() > 127 or sub.shape[0] >= _lib.MAXA:
             return np.zeros(len(jobs), dtype=bool)
         N = np.maximum(jobs['n'][:, 0], jobs['n'][:, 1]).astype(np.int64)
         M = np.maximum(jobs['m'][:, 0], jobs['m'][:, 1]).astype(np.int64)
-        ok = int(sp.max()) * np.minimum(N, M) <= 65535
-        if sc.gap_right != sc.gap:
-            ok &= (jobs['n'][:, 0] == jobs['n'][:, 1]) & (jobs['m'][:, 0] == jobs['m'][:, 1])
-        return ok
+        return int(sp.max()) * np.minimum(N, M) <= 65535
 
     def run_jobs(self, d_pool, jobs, sub, n_out):
         """Launch the NW kernels for `jobs` (host record array); returns int32 scores on the host."""
@@ -284,7 +281,7 @@ class DistEngine:
         torch = self.torch
         sc = self.sc
         npair = len(P)
-        mixed_ok = (sc.gap_right == sc.gap)
+        mixed_ok = True          # both kernels accept different shapes in the two halves of a job
         row_off, col_off = off[I], off[J]
         # ---- phase A: the real alignment of every pair (tg_align.py:125) ----
         jobs = pack_jobs(row_off, col_off, li, lj, np.arange(npair, dtype=np.int32), mixed_ok)

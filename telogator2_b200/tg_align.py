@@ -140,8 +140,7 @@ def _single_scores(engine, seq_pairs):
     codes, off, sub = engine.sc.encode_all(seqs)
     n = np.diff(off).astype(np.int32)
     k = len(seq_pairs)
-    jobs = pack_jobs(off[0:2 * k:2], off[1:2 * k:2], n[0::2], n[1::2], np.arange(k, dtype=np.int32),
-                     engine.sc.gap_right == engine.sc.gap)
+    jobs = pack_jobs(off[0:2 * k:2], off[1:2 * k:2], n[0::2], n[1::2], np.arange(k, dtype=np.int32), True)
     return engine.run_jobs(engine._to_dev(codes), jobs, sub, k)
 
 

@@ -124,6 +124,7 @@ class PackedReads:
                 o = int(self.base_off[i])
                 buf[o:o + self.lens[i]] = np.frombuffer(r.encode('latin-1', 'replace'), dtype=np.uint8)
         self._ascii_host = buf
+        self._bad_reads = None
         self.h2d_bytes = total + self.base_off.nbytes + self.lens.nbytes
         self.d_ascii = ascii_h.cuda(non_blocking=True)
         self.d_base_off = torch.from_numpy(self.base_off).cuda()
@@ -136,12 +137,15 @@ class PackedReads:
 
     def check_rc_alphabet(self, flip):
         """RC() raises KeyError outside ACGTN (tg_util.py:433-434); mirror that for reads to be flipped."""
-        for i in np.nonzero(flip)[0]:
+        if self._bad_reads is None:
+            bad = ~_ACGTN[self._ascii_host[:self.total]]
+            self._bad_reads = np.zeros(self.n, dtype=bool)
+            if bad.any():
+                self._bad_reads[np.unique(np.searchsorted(self.base_off, np.nonzero(bad)[0], side='right') - 1)] = True
+        for i in np.nonzero(np.asarray(flip, dtype=bool) & self._bad_reads)[0]:
             o = int(self.base_off[i])
             seg = self._ascii_host[o:o + self.lens[i]]
-            bad = ~_ACGTN[seg]
-            if bad.any():
-                raise KeyError(chr(int(seg[np.argmax(bad)])))
+            raise KeyError(chr(int(seg[np.argmax(~_ACGTN[seg])])))
 
     def basecount(self, list_a, list_b):
         """int32 [n, 2]: get_telomere_base_count for two k-mer lists (tg_kmer.py:93-102)."""
@@ -187,13 +191,10 @@ class PackedReads:
             out.append(flat[o:o + max(int(self.lens[i]) - window, 0)])
         return out
 
-    def hits(self, slice_read, slice_lo, slice_hi, kmer_list, issub):
-        """get_nonoverlapping_kmer_hits for a batch of slices; returns one out_dat (list[K] of [[s, e], ...]) per slice."""
+    def hits_device(self, slice_read, slice_lo, slice_hi, kmer_list, issub):
+        """Device part of hits(): returns (spans int32 [4, n_spans] device tensor: slice, k, start, end; unordered)."""
         torch = self.torch
-        K = len(kmer_list)
         ns = len(slice_read)
-        if ns == 0:
-            return []
         sr = np.ascontiguousarray(slice_read, dtype=np.int32)
         lo = np.ascontiguousarray(slice_lo, dtype=np.int32)
         hi = np.ascontiguousarray(slice_hi, dtype=np.int32)
@@ -201,12 +202,12 @@ class PackedReads:
         woff = np.zeros(ns + 1, dtype=np.int64)
         woff[1:] = np.cumsum((ln + 63) // 64 * 64)
         total = int(woff[-1])
-        if total == 0:
-            return [[[] for _ in range(K)] for _ in range(ns)]
+        if ns == 0 or total == 0:
+            return torch.zeros((4, 0), dtype=torch.int32, device='cuda')
         tab = kmer_table(kmer_list, issub)
         d_sr, d_lo, d_hi, d_woff = (torch.from_numpy(a).cuda() for a in (sr, lo, hi, woff))
         work = torch.empty(self.L.tg_scan_hits_work_bytes(total, ns), dtype=torch.uint8, device='cuda')
-        cap = max(total // 2, 1024)
+        cap = max(total // 4, 1024)
         while True:
             spans = torch.empty((4, cap), dtype=torch.int32, device='cuda')
             cnt = torch.zeros(1, dtype=torch.int64, device='cuda')
@@ -219,7 +220,13 @@ class PackedReads:
             if n_sp <= cap:
                 break
             cap = n_sp
-        sp = spans[:, :n_sp].cpu().numpy()
+        return spans[:, :n_sp]
+
+    def hits(self, slice_read, slice_lo, slice_hi, kmer_list, issub):
+        """get_nonoverlapping_kmer_hits for a batch of slices; returns one out_dat (list[K] of [[s, e], ...]) per slice."""
+        K = len(kmer_list)
+        ns = len(slice_read)
+        sp = self.hits_device(slice_read, slice_lo, slice_hi, kmer_list, issub).cpu().numpy()
         self.last_hits_d2h = sp.nbytes
         order = np.lexsort((sp[2], sp[1], sp[0]))          # by slice, k, start
         sp = sp[:, order]
