@@ -240,7 +240,7 @@ def main():
     def dp_step():
         eng.stats['cells'] = 0
         eng.stats['launches'] = 0
-        res = eng.pair_scores(seqs, True, True, R, SEED, pair_idx=my_pairs)
+        res = eng.pair_scores(seqs, True, True, R, SEED, shard=(rank, world))
         return res
 
     # ---------------- scan: device-resident timing ----------------
@@ -366,7 +366,7 @@ def main():
         barrier()
         t0 = time.perf_counter()
         eng2 = DistEngine(Scoring.from_aligner(aligner))
-        res = eng2.pair_scores(seqs, True, True, R, SEED, pair_idx=my_pairs)
+        res = eng2.pair_scores(seqs, True, True, R, SEED, shard=(rank, world))
         if world > 1:
             res = gather_results(res, dist, eng2.device)
         D = eng2.dist_matrix(seqs, True, True, R, SEED, res=res)

@@ -95,6 +95,36 @@ typedef struct tg_shuffle_job {
 int tg_mt_shuffle(uint8_t *d_pool, const tg_shuffle_job *d_jobs, int64_t n_jobs, int R, int max_len,
                   void *stream);
 
+/* The whole device side of get_dist_matrix_parallel (tg_align.py:154-189) for a range of pairs,
+ * enqueued without any host round trip:
+ *   phase A (aligner.score of every pair, :125) -> identity score + early-out flags (:127-138)
+ *   -> MT19937 null model of the surviving pairs (:110-111,141-142) -> phase B (R scores per pair).
+ * Pairs are addressed in "sorted pair space": q indexes itertools.combinations over the sequences
+ * sorted by length (d_order[rank] = sequence index, longest first) so neighbouring pairs have
+ * similar shapes; each pair is mapped back to its original (i < j), its length-adjusted shapes
+ * (:115-120) and its combinations index p (seed = abs(seed0 + p), :157,170-172) on the device.
+ * Outputs are indexed by q - q0: d_aln, d_flags (1 = early-out), d_iden (float64 identity score),
+ * d_shape (n, m), d_rnd[(q - q0) * R + k] (pre-filled by the caller; untouched for early-out pairs).
+ * The shuffled strings live in d_pool at shuf_base + (q - q0) * slot, slot >= 2 * R * max_len.
+ * Requires the wave kernel's envelope for a max_len x max_len alignment (else TG_ERANGE: use the
+ * explicit-job entry points). */
+typedef struct tg_dist_batch_args {
+    uint8_t *d_pool;
+    const int64_t *d_seq_off;       /* [n_seq + 1] */
+    const int32_t *d_order;         /* [n_seq] */
+    const int32_t *d_diag_cs;       /* [codes + 1] prefix sums of sub[c][c] over d_pool codes, NULL in match/mismatch mode */
+    int32_t *d_aln, *d_rnd, *d_shape;
+    uint8_t *d_flags;
+    double *d_iden;
+    void *d_scratch;                /* tg_nw_wave_scratch_bytes(max_len) */
+    int32_t *d_counter;             /* 16 bytes */
+    int64_t q0, q1, seed0, shuf_base, slot;
+    double match;                   /* match score, used when d_diag_cs == NULL */
+    int32_t n_seq, adjust_lens, min_viable, R, max_len, pad_;
+} tg_dist_batch_args;
+
+int tg_dist_batch(const tg_dist_batch_args *args, const tg_nw_scoring *sc, void *stream);
+
 /* Integer-ALU issue-rate microbenchmark used as the DP roofline denominator:
  * runs `iters` dependent-chain-free VIMNMX3.U16x2/IADD pairs per thread on the whole device and
  * returns lane-operations per second for the DPX op and for a plain integer add. */

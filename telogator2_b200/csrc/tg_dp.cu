@@ -18,6 +18,7 @@
 #include "tg_common.cuh"
 #include <limits.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace {
 
@@ -37,7 +38,54 @@ struct WaveParams {
     int g, gr;                  // internal gap, right end gap
     int right_free;             // gr != g
     uint8_t sp[MAXA * MAXA];    // S' = S - 2g, row-major [a][b] with stride MAXA
+    // implicit job modes (tg_dist_batch): jobs are derived from the pair index instead of read from memory
+    const long long *seq_off;   // [n_seq + 1] offsets of the sequences in pool
+    const int *order;           // [n_seq] sequence indices sorted by length, longest first
+    int n_seq, adjust_lens, min_viable, R;
+    long long q0, q1;           // pair range in sorted pair space
+    const uint8_t *flags;       // [q1 - q0] 1 = early-out (phase B skips the pair)
+    long long shuf_base, slot;  // shuffle area: pool offset and bytes per pair
 };
+
+enum { JOBS_EXPLICIT = 0, JOBS_PHASE_A = 1, JOBS_PHASE_B = 2 };
+
+// pair q of itertools.combinations(range(n), 2) -> (a, b), a < b
+__device__ __forceinline__ void unrank_pair(long long q, int n, int &a, int &b)
+{
+    const double t = 2.0 * n - 1.0;
+    long long r = (long long)floor((t - sqrt(t * t - 8.0 * (double)q)) * 0.5);
+    if (r < 0) r = 0;
+    if (r > n - 2) r = n - 2;
+    while (r > 0 && r * (2LL * n - r - 1) / 2 > q) r--;
+    while ((r + 1) * (2LL * n - (r + 1) - 1) / 2 <= q) r++;
+    a = (int)r;
+    b = (int)(q - r * (2LL * n - r - 1) / 2 + r + 1);
+}
+
+struct PairDesc { long long off_i, off_j; int n, m; long long p; };
+
+// sorted-space pair q -> original (i < j), length-adjusted shapes (tg_align.py:115-120) and combinations index p
+template <typename PT>
+__device__ __forceinline__ PairDesc describe_pair(const PT &P, long long q)
+{
+    int a, b;
+    unrank_pair(q, P.n_seq, a, b);
+    const int oa = P.order[a], ob = P.order[b];
+    const int i = min(oa, ob), j = max(oa, ob);
+    PairDesc d;
+    d.off_i = P.seq_off[i];
+    d.off_j = P.seq_off[j];
+    int li = (int)(P.seq_off[i + 1] - d.off_i), lj = (int)(P.seq_off[j + 1] - d.off_j);
+    if (P.adjust_lens) {
+        int ml = min(li, lj);
+        if (P.min_viable) ml = max(ml, 1000);
+        li = min(li, ml);
+        lj = min(lj, ml);
+    }
+    d.n = li; d.m = lj;
+    d.p = (long long)i * (2LL * P.n_seq - i - 1) / 2 + (j - i - 1);
+    return d;
+}
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
 {
@@ -109,7 +157,7 @@ struct Strip<8> {
 };
 
 // Shared memory per warp: query profile [2][A+1][W] bytes, then row letters [row_cap] u16 (a0 | a1 << 8).
-template <int C>
+template <int C, int MODE>
 __global__ void __launch_bounds__(WAVE_MAX_WARPS * 32, 1) nw_wave_kernel(const __grid_constant__ WaveParams P)
 {
     constexpr int W = 32 * C;
@@ -136,11 +184,47 @@ __global__ void __launch_bounds__(WAVE_MAX_WARPS * 32, 1) nw_wave_kernel(const _
         if (lane == 0) jid = atomicAdd(P.counter, 1ULL);
         jid = __shfl_sync(TG_FULL_MASK, jid, 0);
         if (jid >= (unsigned long long)P.n_jobs) break;
-        const tg_nw_job *J = P.jobs + jid;
-        const long long row0 = J->row_off[0], row1 = J->row_off[1];
-        const long long col0 = J->col_off[0], col1 = J->col_off[1];
-        const int n0 = J->n[0], n1 = J->n[1], m0 = J->m[0], m1 = J->m[1];
-        const int out0 = J->out[0], out1 = J->out[1];
+        long long row0, row1, col0, col1;
+        int n0, n1, m0, m1, out0, out1;
+        if (MODE == JOBS_EXPLICIT) {
+            const tg_nw_job *J = P.jobs + jid;
+            row0 = J->row_off[0]; row1 = J->row_off[1];
+            col0 = J->col_off[0]; col1 = J->col_off[1];
+            n0 = J->n[0]; n1 = J->n[1]; m0 = J->m[0]; m1 = J->m[1];
+            out0 = J->out[0]; out1 = J->out[1];
+        } else if (MODE == JOBS_PHASE_A) {
+            // job = sorted-space pairs q0 + 2*jid and q0 + 2*jid + 1 (tg_align.py:125)
+            const long long qa = P.q0 + 2 * (long long)jid, qb = qa + 1;
+            const PairDesc da = describe_pair(P, qa);
+            row0 = da.off_i; col0 = da.off_j; n0 = da.n; m0 = da.m; out0 = (int)(qa - P.q0);
+            if (qb < P.q1) {
+                const PairDesc db = describe_pair(P, qb);
+                row1 = db.off_i; col1 = db.off_j; n1 = db.n; m1 = db.m; out1 = (int)(qb - P.q0);
+            } else { row1 = row0; col1 = col0; n1 = n0; m1 = m0; out1 = -1; }
+        } else {
+            // phase B (tg_align.py:141-142): R even -> shuffles (2t, 2t+1) of one pair share a job;
+            // R odd -> shuffle t of two neighbouring pairs share a job.  Early-out pairs are skipped.
+            const int R = P.R;
+            long long qa, qb;
+            int ta, tb;
+            if ((R & 1) == 0) { qa = qb = P.q0 + (long long)(jid / (R / 2)); ta = 2 * (int)(jid % (R / 2)); tb = ta + 1; }
+            else { qa = P.q0 + 2 * (long long)(jid / R); qb = qa + 1; ta = tb = (int)(jid % R); }
+            const bool ha = !P.flags[qa - P.q0];
+            const bool hb = (qb < P.q1) && !P.flags[qb - P.q0];
+            if (!ha && !hb) continue;
+            PairDesc da, db;
+            if (ha) da = describe_pair(P, qa);
+            if (hb) db = (qb == qa) ? da : describe_pair(P, qb);
+            if (!ha) { da = db; qa = qb; ta = tb; }
+            if (!hb) { db = da; qb = qa; tb = ta; }
+            row0 = P.shuf_base + (qa - P.q0) * P.slot + (long long)ta * (da.n + da.m); col0 = row0 + da.n;
+            row1 = P.shuf_base + (qb - P.q0) * P.slot + (long long)tb * (db.n + db.m); col1 = row1 + db.n;
+            n0 = da.n; m0 = da.m; n1 = db.n; m1 = db.m;
+            out0 = ha ? (int)((qa - P.q0) * R + ta) : -1;
+            out1 = hb ? (int)((qb - P.q0) * R + tb) : -1;
+            if (ha && !hb) out1 = -1;
+            if (!ha && hb) { out0 = out1; out1 = -1; }
+        }
         const int N = max(n0, n1), M = max(m0, m1);
         const int nblk = (M + W - 1) / W;
         const int pad0 = nblk * W - m0, pad1 = nblk * W - m1;     // left padding (right-aligned columns)
@@ -343,84 +427,161 @@ __global__ void __launch_bounds__(GEN_THREADS) nw_generic_kernel(const __grid_co
 constexpr int MT_THREADS = 32;
 __constant__ uint32_t c_mt_base[624];      // init_genrand(19650218)
 
+// one thread: random.seed(seed); R x (shuffle(seq_i), shuffle(seq_j)) written back to back at dst
+__device__ __forceinline__ void mt_shuffle_pair(uint8_t *pool, uint32_t *mt, uint8_t *sp, int pool_stride, int tid,
+                                                uint64_t seed, long long src_i, long long src_j, int n, int m,
+                                                long long dst, int R)
+{
+#define MT(i) mt[(i) * MT_THREADS + tid]
+    // ---- random.seed(int): init_by_array(32-bit words of abs(seed)) ----
+    uint32_t key[2] = {(uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32)};
+    const int klen = key[1] ? 2 : 1;
+    for (int i = 0; i < 624; i++) MT(i) = c_mt_base[i];
+    {
+        int i = 1, j = 0;
+        uint32_t prev = MT(0);
+        for (int k = 624; k; k--) {
+            uint32_t v = (MT(i) ^ ((prev ^ (prev >> 30)) * 1664525u)) + key[j] + (uint32_t)j;
+            MT(i) = v; prev = v;
+            i++; j++;
+            if (i >= 624) { MT(0) = prev; i = 1; }
+            if (j >= klen) j = 0;
+        }
+        for (int k = 623; k; k--) {
+            uint32_t v = (MT(i) ^ ((prev ^ (prev >> 30)) * 1566083941u)) - (uint32_t)i;
+            MT(i) = v; prev = v;
+            i++;
+            if (i >= 624) { MT(0) = prev; i = 1; }
+        }
+        MT(0) = 0x80000000u;
+    }
+    int kk = 0;                                   // next state word to regenerate
+    for (int rep = 0; rep < 2 * R; rep++) {
+        const int len = (rep & 1) ? m : n;
+        const uint8_t *src = pool + ((rep & 1) ? src_j : src_i);
+        // Working array: pool = list(population) shrinks from the back while the selected items fill the
+        // vacated back slots, i.e. result[i] ends up at arr[len-1-i].  Shared memory when it fits
+        // (pool_stride > 0), else in place in the destination region.
+        uint8_t *arr = pool_stride > 0 ? sp : pool + dst;
+        for (int x = 0; x < len; x++) arr[x] = src[x];
+        int i = 0;
+        while (i < len) {
+            // genrand_uint32, lazy twist of word kk
+            const int k1 = (kk == 623) ? 0 : kk + 1;
+            const int k397 = (kk >= 227) ? kk - 227 : kk + 397;
+            const uint32_t y0 = (MT(kk) & 0x80000000u) | (MT(k1) & 0x7fffffffu);
+            uint32_t y = MT(k397) ^ (y0 >> 1) ^ ((y0 & 1u) ? 0x9908b0dfu : 0u);
+            MT(kk) = y;
+            kk = k1;
+            y ^= (y >> 11);
+            y ^= (y << 7) & 0x9d2c5680u;
+            y ^= (y << 15) & 0xefc60000u;
+            y ^= (y >> 18);
+            // _randbelow(nn): k = nn.bit_length(); r = getrandbits(k); redraw while r >= nn
+            const uint32_t nn = (uint32_t)(len - i);
+            const uint32_t r = y >> __clz(nn);                 // 32 - bit_length(nn) == clz(nn)
+            if (r < nn) {
+                const uint8_t v = arr[r];                      // result[i] = pool[j]
+                arr[r] = arr[nn - 1];                          // pool[j] = pool[n-i-1]
+                arr[nn - 1] = v;
+                i++;
+            }
+        }
+        if (pool_stride > 0) {
+            for (int x = 0; x < len; x++) pool[dst + x] = sp[len - 1 - x];
+        } else {
+            for (int x = 0; x < len / 2; x++) {
+                const uint8_t a = arr[x], b = arr[len - 1 - x];
+                arr[x] = b; arr[len - 1 - x] = a;
+            }
+        }
+        dst += len;
+    }
+#undef MT
+}
+
 __global__ void __launch_bounds__(MT_THREADS) mt_shuffle_kernel(uint8_t *pool, const tg_shuffle_job *jobs,
                                                                long long n_jobs, int R, int pool_stride)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     uint32_t *mt = reinterpret_cast<uint32_t *>(smem);                 // [624][MT_THREADS]
     uint8_t *sp = smem + 624 * MT_THREADS * sizeof(uint32_t) + (size_t)threadIdx.x * pool_stride;
-    const int tid = threadIdx.x;
-#define MT(i) mt[(i) * MT_THREADS + tid]
-    for (long long job = (long long)blockIdx.x * MT_THREADS + tid; job < n_jobs;
+    for (long long job = (long long)blockIdx.x * MT_THREADS + threadIdx.x; job < n_jobs;
          job += (long long)gridDim.x * MT_THREADS) {
         const tg_shuffle_job J = jobs[job];
-        // ---- random.seed(int): init_by_array(32-bit words of abs(seed)) ----
-        uint32_t key[2] = {(uint32_t)(J.seed & 0xffffffffu), (uint32_t)(J.seed >> 32)};
-        const int klen = key[1] ? 2 : 1;
-        for (int i = 0; i < 624; i++) MT(i) = c_mt_base[i];
-        {
-            int i = 1, j = 0;
-            uint32_t prev = MT(0);
-            for (int k = 624; k; k--) {
-                uint32_t v = (MT(i) ^ ((prev ^ (prev >> 30)) * 1664525u)) + key[j] + (uint32_t)j;
-                MT(i) = v; prev = v;
-                i++; j++;
-                if (i >= 624) { MT(0) = prev; i = 1; }
-                if (j >= klen) j = 0;
-            }
-            for (int k = 623; k; k--) {
-                uint32_t v = (MT(i) ^ ((prev ^ (prev >> 30)) * 1566083941u)) - (uint32_t)i;
-                MT(i) = v; prev = v;
-                i++;
-                if (i >= 624) { MT(0) = prev; i = 1; }
-            }
-            MT(0) = 0x80000000u;
-        }
-        int kk = 0;                                   // next state word to regenerate
-        long long dst = J.dst_off;
-        for (int rep = 0; rep < 2 * R; rep++) {
-            const int len = (rep & 1) ? J.m : J.n;
-            const uint8_t *src = pool + ((rep & 1) ? J.src_j : J.src_i);
-            // Working array: pool = list(population) shrinks from the back while the selected items fill the
-            // vacated back slots, i.e. result[i] ends up at arr[len-1-i].  Shared memory when it fits
-            // (pool_stride > 0), else in place in the destination region.
-            uint8_t *arr = pool_stride > 0 ? sp : pool + dst;
-            for (int x = 0; x < len; x++) arr[x] = src[x];
-            int i = 0;
-            while (i < len) {
-                // genrand_uint32, lazy twist of word kk
-                const int k1 = (kk == 623) ? 0 : kk + 1;
-                const int k397 = (kk >= 227) ? kk - 227 : kk + 397;
-                const uint32_t y0 = (MT(kk) & 0x80000000u) | (MT(k1) & 0x7fffffffu);
-                uint32_t y = MT(k397) ^ (y0 >> 1) ^ ((y0 & 1u) ? 0x9908b0dfu : 0u);
-                MT(kk) = y;
-                kk = k1;
-                y ^= (y >> 11);
-                y ^= (y << 7) & 0x9d2c5680u;
-                y ^= (y << 15) & 0xefc60000u;
-                y ^= (y >> 18);
-                // _randbelow(nn): k = nn.bit_length(); r = getrandbits(k); redraw while r >= nn
-                const uint32_t nn = (uint32_t)(len - i);
-                const uint32_t r = y >> __clz(nn);                 // 32 - bit_length(nn) == clz(nn)
-                if (r < nn) {
-                    const uint8_t v = arr[r];                      // result[i] = pool[j]
-                    arr[r] = arr[nn - 1];                          // pool[j] = pool[n-i-1]
-                    arr[nn - 1] = v;
-                    i++;
-                }
-            }
-            if (pool_stride > 0) {
-                for (int x = 0; x < len; x++) pool[dst + x] = sp[len - 1 - x];
-            } else {
-                for (int x = 0; x < len / 2; x++) {
-                    const uint8_t a = arr[x], b = arr[len - 1 - x];
-                    arr[x] = b; arr[len - 1 - x] = a;
-                }
-            }
-            dst += len;
-        }
+        mt_shuffle_pair(pool, mt, sp, pool_stride, threadIdx.x, J.seed, J.src_i, J.src_j, J.n, J.m, J.dst_off, R);
     }
-#undef MT
+}
+
+struct BatchShuffleParams {
+    uint8_t *pool;
+    const long long *seq_off;
+    const int *order;
+    int n_seq, adjust_lens, min_viable, R;
+    long long q0, q1;
+    const uint8_t *flags;
+    long long shuf_base, slot;
+    long long seed0;
+    int pool_stride;
+    unsigned long long *counter;
+};
+
+// null model of every non-early pair of a batch; seed = abs(rng_seed + p) (tg_align.py:110-111,157,170-172)
+__global__ void __launch_bounds__(MT_THREADS) mt_shuffle_batch_kernel(const BatchShuffleParams P)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint32_t *mt = reinterpret_cast<uint32_t *>(smem);
+    uint8_t *sp = smem + 624 * MT_THREADS * sizeof(uint32_t) + (size_t)threadIdx.x * P.pool_stride;
+    // dynamic scheduling, one warp fetches 32 pairs at a time (early-out pairs cost nothing but a lane)
+    for (;;) {
+        unsigned long long base = 0;
+        if (threadIdx.x == 0) base = atomicAdd(P.counter, (unsigned long long)MT_THREADS);
+        base = __shfl_sync(TG_FULL_MASK, base, 0);
+        if ((long long)base >= P.q1 - P.q0) break;
+        const long long ql = (long long)base + threadIdx.x;
+        if (ql < P.q1 - P.q0 && !P.flags[ql]) {
+            const PairDesc d = describe_pair(P, P.q0 + ql);
+            const long long sv = P.seed0 + d.p;
+            const uint64_t seed = (uint64_t)(sv < 0 ? -sv : sv);
+            mt_shuffle_pair(P.pool, mt, sp, P.pool_stride, threadIdx.x, seed, d.off_i, d.off_j, d.n, d.m,
+                            P.shuf_base + ql * P.slot, P.R);
+        }
+        __syncwarp();
+    }
+}
+
+struct FlagParams {
+    const long long *seq_off;
+    const int *order;
+    int n_seq, adjust_lens, min_viable, R;
+    long long q0, q1;
+    const int32_t *aln;
+    const int32_t *diag_cs;       // prefix sums of the substitution-matrix diagonal over pool codes, or NULL
+    double match;                 // match score (match/mismatch mode)
+    uint8_t *flags;
+    double *iden;
+    int32_t *shape;               // [2 * pairs] length-adjusted n, m
+};
+
+// identity score and the early-out test of tvr_distance (tg_align.py:127-138), in float64 like the reference
+__global__ void __launch_bounds__(256) dist_flags_kernel(const FlagParams P)
+{
+    for (long long ql = (long long)blockIdx.x * blockDim.x + threadIdx.x; ql < P.q1 - P.q0; ql += (long long)gridDim.x * blockDim.x) {
+        const PairDesc d = describe_pair(P, P.q0 + ql);
+        double iden;
+        if (P.diag_cs) {
+            const double is1 = (double)(P.diag_cs[d.off_i + d.n] - P.diag_cs[d.off_i]);
+            const double is2 = (double)(P.diag_cs[d.off_j + d.m] - P.diag_cs[d.off_j]);
+            iden = (is1 + is2) / 2.0;
+        } else {
+            iden = P.match * ((double)(d.n + d.m) / 2.0);
+        }
+        const double aln = (double)P.aln[ql];
+        P.flags[ql] = (aln < -(0.900 * iden)) ? 1 : 0;
+        P.iden[ql] = iden;
+        P.shape[2 * ql] = d.n;
+        P.shape[2 * ql + 1] = d.m;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -508,23 +669,35 @@ TG_EXPORT int tg_nw_wave_check(const tg_nw_scoring *sc, const tg_nw_job *h_jobs,
     return TG_OK;
 }
 
-TG_EXPORT int tg_nw_scores_wave(const uint8_t *d_pool, const tg_nw_job *d_jobs, int64_t n_jobs, int max_n,
-                                const tg_nw_scoring *sc, int32_t *d_scores, void *d_scratch, int32_t *d_counter,
-                                void *stream)
+template <int C, int MODE>
+static int wave_launch_t(const WaveParams &P, int grid, int warps, size_t smem, cudaStream_t st)
 {
-    if (n_jobs <= 0) return TG_OK;
+    TG_CUDA_CHECK(cudaFuncSetAttribute(nw_wave_kernel<C, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nw_wave_kernel<C, MODE><<<grid, warps * 32, smem, st>>>(P);
+    TG_CUDA_CHECK(cudaGetLastError());
+    return TG_OK;
+}
+
+static int wave_launch(const WaveParams &P, int mode, int C, int grid, int warps, size_t smem, cudaStream_t st)
+{
+    if (C == 16) {
+        if (mode == JOBS_EXPLICIT) return wave_launch_t<16, JOBS_EXPLICIT>(P, grid, warps, smem, st);
+        if (mode == JOBS_PHASE_A) return wave_launch_t<16, JOBS_PHASE_A>(P, grid, warps, smem, st);
+        return wave_launch_t<16, JOBS_PHASE_B>(P, grid, warps, smem, st);
+    }
+    if (mode == JOBS_EXPLICIT) return wave_launch_t<8, JOBS_EXPLICIT>(P, grid, warps, smem, st);
+    if (mode == JOBS_PHASE_A) return wave_launch_t<8, JOBS_PHASE_A>(P, grid, warps, smem, st);
+    return wave_launch_t<8, JOBS_PHASE_B>(P, grid, warps, smem, st);
+}
+
+// shared set-up of the three job modes
+static int wave_setup(WaveParams &P, const tg_nw_scoring *sc, int max_n, int *C_out, int *warps_out, size_t *smem_out)
+{
     wave_env();
     int max_sp = 0;
     int rc = wave_envelope(sc, &max_sp);
     if (rc != TG_OK) return rc;
-    if (!d_pool || !d_jobs || !d_scores || !d_scratch || !d_counter) return tg_set_err(TG_EINVAL, "NULL device pointer");
     if (max_n < 1) return tg_set_err(TG_EINVAL, "max_n < 1");
-    const int sms = tg_sm_count();
-    if (sms <= 0) return tg_set_err(TG_ECUDA, "no CUDA device");
-    WaveParams P;
-    P.pool = d_pool; P.jobs = d_jobs; P.n_jobs = n_jobs; P.scores = d_scores;
-    P.scratch = reinterpret_cast<uint32_t *>(d_scratch);
-    P.counter = reinterpret_cast<unsigned long long *>(d_counter);
     P.scratch_stride = (int)(((size_t)max_n + 63) / 32 * 32);
     P.row_cap = (max_n + 1 + 7) / 8 * 8;
     P.A = sc->alphabet; P.g = sc->gap; P.gr = sc->gap_right; P.right_free = (sc->gap_right != sc->gap);
@@ -537,21 +710,115 @@ TG_EXPORT int tg_nw_scores_wave(const uint8_t *d_pool, const tg_nw_job *d_jobs, 
     if (warps > WAVE_MAX_WARPS) warps = WAVE_MAX_WARPS;
     if (g_wave_warps && warps > g_wave_warps) warps = g_wave_warps;
     if (warps < 1) return tg_set_err(TG_ERANGE, "sequences of %d rows do not fit the wave kernel's shared memory", max_n);
-    const size_t smem = MAXA * MAXA + (size_t)warps * per_warp;
+    *C_out = C; *warps_out = warps;
+    *smem_out = MAXA * MAXA + (size_t)warps * per_warp;
+    return TG_OK;
+}
+
+TG_EXPORT int tg_nw_scores_wave(const uint8_t *d_pool, const tg_nw_job *d_jobs, int64_t n_jobs, int max_n,
+                                const tg_nw_scoring *sc, int32_t *d_scores, void *d_scratch, int32_t *d_counter,
+                                void *stream)
+{
+    if (n_jobs <= 0) return TG_OK;
+    if (!d_pool || !d_jobs || !d_scores || !d_scratch || !d_counter) return tg_set_err(TG_EINVAL, "NULL device pointer");
+    const int sms = tg_sm_count();
+    if (sms <= 0) return tg_set_err(TG_ECUDA, "no CUDA device");
+    WaveParams P;
+    memset(&P, 0, sizeof(P));
+    int C, warps;
+    size_t smem;
+    int rc = wave_setup(P, sc, max_n, &C, &warps, &smem);
+    if (rc != TG_OK) return rc;
+    P.pool = d_pool; P.jobs = d_jobs; P.n_jobs = n_jobs; P.scores = d_scores;
+    P.scratch = reinterpret_cast<uint32_t *>(d_scratch);
+    P.counter = reinterpret_cast<unsigned long long *>(d_counter);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     TG_CUDA_CHECK(cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), st));
     long long grid = sms;
     const long long ctas_needed = (n_jobs + warps - 1) / warps;
     if (ctas_needed < grid) grid = ctas_needed;
-    if (C == 16) {
-        TG_CUDA_CHECK(cudaFuncSetAttribute(nw_wave_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        nw_wave_kernel<16><<<(int)grid, warps * 32, smem, st>>>(P);
-    } else {
-        TG_CUDA_CHECK(cudaFuncSetAttribute(nw_wave_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        nw_wave_kernel<8><<<(int)grid, warps * 32, smem, st>>>(P);
+    return wave_launch(P, JOBS_EXPLICIT, C, (int)grid, warps, smem, st);
+}
+
+static int mt_upload_base();
+
+TG_EXPORT int tg_dist_batch(const tg_dist_batch_args *a, const tg_nw_scoring *sc, void *stream)
+{
+    if (!a || !sc) return tg_set_err(TG_EINVAL, "NULL argument");
+    const long long npairs = a->q1 - a->q0;
+    if (npairs <= 0) return TG_OK;
+    if (!a->d_pool || !a->d_seq_off || !a->d_order || !a->d_aln || !a->d_flags || !a->d_iden || !a->d_shape ||
+        !a->d_scratch || !a->d_counter || (a->R > 0 && !a->d_rnd))
+        return tg_set_err(TG_EINVAL, "NULL device pointer");
+    if (npairs > 0x3fffffff / (a->R > 0 ? a->R : 1)) return tg_set_err(TG_ERANGE, "batch of %lld pairs is too large", npairs);
+    const int sms = tg_sm_count();
+    if (sms <= 0) return tg_set_err(TG_ECUDA, "no CUDA device");
+    WaveParams P;
+    memset(&P, 0, sizeof(P));
+    int C, warps;
+    size_t smem;
+    int rc = wave_setup(P, sc, a->max_len, &C, &warps, &smem);
+    if (rc != TG_OK) return rc;
+    {
+        int max_sp = 0;
+        wave_envelope(sc, &max_sp);
+        if ((long long)max_sp * a->max_len > 65535) return tg_set_err(TG_ERANGE, "max_len %d overflows 16-bit scores", a->max_len);
     }
-    TG_CUDA_CHECK(cudaGetLastError());
-    return TG_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    P.pool = a->d_pool; P.jobs = nullptr; P.scores = a->d_aln;
+    P.scratch = reinterpret_cast<uint32_t *>(a->d_scratch);
+    P.counter = reinterpret_cast<unsigned long long *>(a->d_counter);
+    P.seq_off = reinterpret_cast<const long long *>(a->d_seq_off); P.order = a->d_order; P.n_seq = a->n_seq;
+    P.adjust_lens = a->adjust_lens; P.min_viable = a->min_viable; P.R = a->R;
+    P.q0 = a->q0; P.q1 = a->q1; P.flags = a->d_flags; P.shuf_base = a->shuf_base; P.slot = a->slot;
+    auto grid_for_jobs = [&](long long jobs) { long long g = (jobs + warps - 1) / warps; return (int)(g < sms ? g : sms); };
+    // ---- phase A: the real alignment of every pair ----
+    P.n_jobs = (npairs + 1) / 2;
+    TG_CUDA_CHECK(cudaMemsetAsync(a->d_counter, 0, sizeof(unsigned long long), st));
+    rc = wave_launch(P, JOBS_PHASE_A, C, grid_for_jobs(P.n_jobs), warps, smem, st);
+    if (rc != TG_OK) return rc;
+    // ---- identity score + early-out flags ----
+    FlagParams F;
+    F.seq_off = P.seq_off; F.order = P.order; F.n_seq = P.n_seq; F.adjust_lens = P.adjust_lens; F.min_viable = P.min_viable;
+    F.R = a->R; F.q0 = a->q0; F.q1 = a->q1; F.aln = a->d_aln; F.diag_cs = a->d_diag_cs; F.match = a->match;
+    F.flags = a->d_flags; F.iden = a->d_iden; F.shape = a->d_shape;
+    {
+        long long g = (npairs + 255) / 256;
+        if (g > (long long)sms * 8) g = (long long)sms * 8;
+        dist_flags_kernel<<<(int)g, 256, 0, st>>>(F);
+        TG_CUDA_CHECK(cudaGetLastError());
+    }
+    if (a->R <= 0) return TG_OK;
+    // ---- null model: MT19937 shuffles of every non-early pair ----
+    BatchShuffleParams S;
+    S.pool = a->d_pool; S.seq_off = P.seq_off; S.order = P.order; S.n_seq = P.n_seq; S.adjust_lens = P.adjust_lens;
+    S.min_viable = P.min_viable; S.R = a->R; S.q0 = a->q0; S.q1 = a->q1; S.flags = a->d_flags;
+    S.shuf_base = a->shuf_base; S.slot = a->slot; S.seed0 = a->seed0; S.counter = P.counter;
+    int stride = (a->max_len + 3) / 4;
+    if ((stride & 1) == 0) stride++;
+    stride *= 4;
+    size_t msmem = 624 * MT_THREADS * sizeof(uint32_t) + (size_t)MT_THREADS * stride;
+    if (msmem > 200 * 1024) { stride = 0; msmem = 624 * MT_THREADS * sizeof(uint32_t); }
+    S.pool_stride = stride;
+    rc = mt_upload_base();
+    if (rc != TG_OK) return rc;
+    TG_CUDA_CHECK(cudaFuncSetAttribute(mt_shuffle_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+    {
+        int per_sm = (int)((227 * 1024) / (msmem + 1024));
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 8) per_sm = 8;
+        long long g = (long long)sms * per_sm;
+        const long long need = (npairs + MT_THREADS - 1) / MT_THREADS;
+        if (g > need) g = need;
+        TG_CUDA_CHECK(cudaMemsetAsync(a->d_counter, 0, sizeof(unsigned long long), st));
+        mt_shuffle_batch_kernel<<<(int)g, MT_THREADS, msmem, st>>>(S);
+        TG_CUDA_CHECK(cudaGetLastError());
+    }
+    // ---- phase B: alignments of the shuffled pairs ----
+    P.scores = a->d_rnd;
+    P.n_jobs = (a->R % 2 == 0) ? npairs * (a->R / 2) : ((npairs + 1) / 2) * a->R;
+    TG_CUDA_CHECK(cudaMemsetAsync(a->d_counter, 0, sizeof(unsigned long long), st));
+    return wave_launch(P, JOBS_PHASE_B, C, grid_for_jobs(P.n_jobs), warps, smem, st);
 }
 
 TG_EXPORT int tg_nw_generic_max_m(void) { return 24000; }
@@ -587,6 +854,20 @@ static void mt_base_table_host(uint32_t *mt)
     for (int i = 1; i < 624; i++) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
 }
 
+static int mt_upload_base()
+{
+    static thread_local int base_uploaded_dev = -1;
+    int dev = 0;
+    TG_CUDA_CHECK(cudaGetDevice(&dev));
+    if (base_uploaded_dev != dev) {
+        uint32_t base[624];
+        mt_base_table_host(base);
+        TG_CUDA_CHECK(cudaMemcpyToSymbol(c_mt_base, base, sizeof(base)));
+        base_uploaded_dev = dev;
+    }
+    return TG_OK;
+}
+
 TG_EXPORT int tg_mt_shuffle(uint8_t *d_pool, const tg_shuffle_job *d_jobs, int64_t n_jobs, int R, int max_len, void *stream)
 {
     if (n_jobs <= 0 || R <= 0) return TG_OK;
@@ -603,15 +884,10 @@ TG_EXPORT int tg_mt_shuffle(uint8_t *d_pool, const tg_shuffle_job *d_jobs, int64
         stride = 0;
         smem = 624 * MT_THREADS * sizeof(uint32_t);
     }
-    static thread_local int base_uploaded_dev = -1;
-    int dev = 0;
-    TG_CUDA_CHECK(cudaGetDevice(&dev));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (base_uploaded_dev != dev) {
-        uint32_t base[624];
-        mt_base_table_host(base);
-        TG_CUDA_CHECK(cudaMemcpyToSymbol(c_mt_base, base, sizeof(base)));
-        base_uploaded_dev = dev;
+    {
+        const int rcb = mt_upload_base();
+        if (rcb != TG_OK) return rcb;
     }
     TG_CUDA_CHECK(cudaFuncSetAttribute(mt_shuffle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = (int)((227 * 1024) / (smem + 1024));

@@ -226,11 +226,119 @@ class DistEngine:
         return out
 
     # ---- the batch path ----------------------------------------------------------------------
-    def pair_scores(self, sequences, adjust_lens, min_viable, R, rng_seed, pair_idx=None):
-        """Integer results for every pair (combinations order): dict(aln, rnd[n_pairs, R], iden, n, m).
+    # ---- device-driven path: one tg_dist_batch call per pair range, no host round trips ----------
+    def _fast_ok(self, sub, max_len):
+        sc = self.sc
+        if self.force_generic or sc.gap_left != sc.gap or sc.gap_right < sc.gap or sub.shape[0] >= _lib.MAXA:
+            return False
+        sp = sub - 2 * sc.gap
+        return sp.min() >= 0 and sp.max() <= 127 and int(sp.max()) * max_len <= 65535
+
+    def _pair_scores_fast(self, codes, off, sub, adjust_lens, min_viable, R, rng_seed, shard):
+        torch = self.torch
+        n_seq = len(off) - 1
+        n_pairs = n_seq * (n_seq - 1) // 2
+        lens = np.diff(off)
+        max_len = int(lens.max())
+        order = np.argsort(-lens, kind='stable').astype(np.int32)
+        R = max(int(R), 0)
+        slot = 2 * R * max_len
+        cap = self.pairs_per_batch
+        if slot:
+            cap = max(2, min(cap, self.shuffle_bytes_per_batch // slot))
+        cap -= cap % 2
+        # pair ranges owned by this rank: blocks of sorted pair space dealt round-robin
+        rank, world = shard if shard is not None else (0, 1)
+        if world > 1:
+            blk = max(4096, -(-n_pairs // (world * 16)))
+            blk += blk % 2
+            ranges = [(b, min(b + blk, n_pairs)) for b in range(rank * blk, n_pairs, world * blk)]
+        else:
+            ranges = [(0, n_pairs)]
+        aln = np.full(n_pairs, NOT_COMPUTED, dtype=np.int32)
+        rnd = np.full((n_pairs, R), NOT_COMPUTED, dtype=np.int32)
+        iden = np.zeros(n_pairs, dtype=np.float64)
+        shape = np.zeros((n_pairs, 2), dtype=np.int32)
+        flags = np.zeros(n_pairs, dtype=np.uint8)
+        # device state
+        n_codes = len(codes)
+        pool = torch.empty(n_codes + cap * slot + 64, dtype=torch.uint8, device=self.device)
+        pool[:n_codes] = torch.from_numpy(codes).to(self.device)
+        d_off = torch.from_numpy(off).to(self.device)
+        d_order = torch.from_numpy(order).to(self.device)
+        self.stats['h2d_bytes'] += n_codes + off.nbytes + order.nbytes
+        d_cs = None
+        if self.sc.alphabet is not None:
+            cs = np.zeros(n_codes + 1, dtype=np.int32)
+            np.cumsum(np.diag(sub)[codes], out=cs[1:])
+            d_cs = torch.from_numpy(cs).to(self.device)
+            self.stats['h2d_bytes'] += cs.nbytes
+        need = self.L.tg_nw_wave_scratch_bytes(max_len)
+        if self._scratch is None or self._scratch.numel() < need:
+            self._scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._counter = torch.zeros(4, dtype=torch.int32, device=self.device)
+        cstruct = self.sc.c_struct(sub)
+        outs = []
+        for (rb, re_) in ranges:
+            q = rb
+            while q < re_:
+                q1 = min(re_, q + cap)
+                npb = q1 - q
+                d_aln = torch.empty(npb, dtype=torch.int32, device=self.device)
+                d_rnd = torch.full((npb, max(R, 1)), NOT_COMPUTED, dtype=torch.int32, device=self.device)
+                d_flags = torch.empty(npb, dtype=torch.uint8, device=self.device)
+                d_iden = torch.empty(npb, dtype=torch.float64, device=self.device)
+                d_shape = torch.empty((npb, 2), dtype=torch.int32, device=self.device)
+                a = _lib.DistBatchArgs()
+                a.d_pool, a.d_seq_off, a.d_order = pool.data_ptr(), d_off.data_ptr(), d_order.data_ptr()
+                a.d_diag_cs = d_cs.data_ptr() if d_cs is not None else None
+                a.d_aln, a.d_rnd, a.d_shape = d_aln.data_ptr(), d_rnd.data_ptr(), d_shape.data_ptr()
+                a.d_flags, a.d_iden = d_flags.data_ptr(), d_iden.data_ptr()
+                a.d_scratch, a.d_counter = self._scratch.data_ptr(), self._counter.data_ptr()
+                a.q0, a.q1, a.seed0, a.shuf_base, a.slot = q, q1, int(rng_seed), n_codes, slot
+                a.match = float(self.sc.match) if self.sc.alphabet is None else 0.0
+                a.n_seq, a.adjust_lens, a.min_viable, a.R, a.max_len = n_seq, int(bool(adjust_lens)), int(bool(min_viable)), R, max_len
+                _lib.check(self.L.tg_dist_batch(C.byref(a), C.byref(cstruct), _lib.stream_ptr(torch)))
+                self.stats['launches'] += 4 if R else 2
+                outs.append((q, q1, d_aln, d_rnd, d_flags, d_iden, d_shape))
+                if len(outs) >= 2:                     # keep one batch in flight while the previous one is copied back
+                    self._collect(outs.pop(0), aln, rnd, flags, iden, shape, R)
+                q = q1
+        for o in outs:
+            self._collect(o, aln, rnd, flags, iden, shape, R)
+        live = aln != NOT_COMPUTED
+        cells = shape[:, 0].astype(np.int64) * shape[:, 1]
+        self.stats['pairs'] += int(live.sum())
+        self.stats['early_out'] += int(flags[live].sum())
+        self.stats['cells'] += int(cells[live].sum()) + R * int(cells[live & (flags == 0)].sum())
+        self.stats['wave_jobs'] += int(live.sum())
+        return dict(aln=aln, rnd=rnd, iden=iden, n=shape[:, 0].copy(), m=shape[:, 1].copy(), order=order)
+
+    def _collect(self, o, aln, rnd, flags, iden, shape, R):
+        (q, q1, d_aln, d_rnd, d_flags, d_iden, d_shape) = o
+        aln[q:q1] = d_aln.cpu().numpy()
+        if R:
+            rnd[q:q1] = d_rnd.cpu().numpy()
+        flags[q:q1] = d_flags.cpu().numpy()
+        iden[q:q1] = d_iden.cpu().numpy()
+        shape[q:q1] = d_shape.cpu().numpy()
+        self.stats['d2h_bytes'] += (q1 - q) * (4 + 4 * R + 1 + 8 + 8)
+
+    def pair_scores(self, sequences, adjust_lens, min_viable, R, rng_seed, pair_idx=None, shard=None):
+        """Integer results for every pair: dict(aln, rnd[n_pairs, R], iden, n, m, order).
         rnd == NOT_COMPUTED where the reference returns early (tg_align.py:137-138).
-        pair_idx: optional sorted int64 array of global pair indices to compute (multi-GPU sharding);
-        everything else stays NOT_COMPUTED / 0."""
+        order is None  -> arrays follow itertools.combinations order (tg_align.py:156);
+        order is given -> arrays follow combinations order over the sequences sorted by length
+                          (order[rank] = sequence index); see canonical_order() / dist_matrix().
+        shard=(rank, world) restricts the work to this rank's share of the pair space (multi-GPU);
+        everything else stays NOT_COMPUTED / 0 and is merged by multi_gpu.gather_results."""
+        if len(sequences) >= 2 and pair_idx is None:
+            codes, off, sub = self.sc.encode_all(sequences)
+            if self._fast_ok(sub, int(np.diff(off).max())):
+                return self._pair_scores_fast(codes, off, sub, adjust_lens, min_viable, R, rng_seed, shard)
+        if shard is not None and pair_idx is None and shard[1] > 1:
+            from .multi_gpu import shard_pair_indices
+            pair_idx = shard_pair_indices(len(sequences) * (len(sequences) - 1) // 2, shard[0], shard[1])
         n_seq = len(sequences)
         n_pairs = n_seq * (n_seq - 1) // 2
         codes, off, sub = self.sc.encode_all(sequences)
@@ -241,7 +349,7 @@ class DistEngine:
         m_eff_all = np.zeros(n_pairs, dtype=np.int32)
         iden_all = np.zeros(n_pairs, dtype=np.float64)
         if n_pairs == 0:
-            return dict(aln=aln, rnd=rnd, iden=iden_all, n=n_eff_all, m=m_eff_all)
+            return dict(aln=aln, rnd=rnd, iden=iden_all, n=n_eff_all, m=m_eff_all, order=None)
         # prefix sums of the diagonal for the identity score (tg_align.py:127-134)
         diag_cs = np.zeros(len(codes) + 1, dtype=np.int64)
         np.cumsum(np.diag(sub)[codes], out=diag_cs[1:])
@@ -275,7 +383,7 @@ class DistEngine:
             self._batch(d_codes, len(codes), off, sub, diag_cs, I, J, P, li, lj, R, seed0, aln, rnd, iden_all)
             n_eff_all[P], m_eff_all[P] = li, lj
             p = q
-        return dict(aln=aln, rnd=rnd, iden=iden_all, n=n_eff_all, m=m_eff_all)
+        return dict(aln=aln, rnd=rnd, iden=iden_all, n=n_eff_all, m=m_eff_all, order=None)
 
     def _batch(self, d_codes, n_codes, off, sub, diag_cs, I, J, P, li, lj, R, seed0, aln, rnd, iden_all):
         torch = self.torch
@@ -367,6 +475,25 @@ class DistEngine:
             res = self.pair_scores(sequences, adjust_lens, min_viable, R, rng_seed)
         d = self.distances(res, R)
         iu = np.triu_indices(n, k=1)                 # row-major upper triangle == combinations order
+        if res.get('order') is not None:
+            o = res['order']
+            iu = (o[iu[0]], o[iu[1]])
         D[iu] = d
         D[(iu[1], iu[0])] = d
         return D
+
+
+def canonical_order(res, n_seq):
+    """Re-index a result dict to itertools.combinations order over the ORIGINAL sequence indices."""
+    if res.get('order') is None:
+        return res
+    o = res['order'].astype(np.int64)
+    a, b = np.triu_indices(n_seq, k=1)
+    i, j = np.minimum(o[a], o[b]), np.maximum(o[a], o[b])
+    p = i * (2 * n_seq - i - 1) // 2 + (j - i - 1)
+    out = dict(order=None)
+    for key in ('aln', 'rnd', 'iden', 'n', 'm'):
+        arr = np.empty_like(res[key])
+        arr[p] = res[key]
+        out[key] = arr
+    return out

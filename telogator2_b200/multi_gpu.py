@@ -46,17 +46,17 @@ def gather_results(res, dist, device):
 
 
 def sharded_pair_scores(engine, sequences, adjust_lens, min_viable, R, rng_seed, compute=None, device=None):
-    """engine.pair_scores over this rank's shard + gather.  `compute(pair_idx)` replaces the device
+    """engine.pair_scores over this rank's shard + gather.  `compute(shard)` with shard = (rank, world) replaces the device
     call in the CPU (gloo) tests of the sharding logic."""
     dist, rank, world = _dist_state()
     n = len(sequences)
     n_pairs = n * (n - 1) // 2
     if compute is None:
-        def compute(pair_idx):
-            return engine.pair_scores(sequences, adjust_lens, min_viable, R, rng_seed, pair_idx=pair_idx)
+        def compute(shard):
+            return engine.pair_scores(sequences, adjust_lens, min_viable, R, rng_seed, shard=shard)
     if world <= 1 or n_pairs == 0:
         return compute(None)
-    res = compute(shard_pair_indices(n_pairs, rank, world))
+    res = compute((rank, world))
     if device is None:
         device = engine.device if dist.get_backend() == 'nccl' else 'cpu'
     return gather_results(res, dist, device)

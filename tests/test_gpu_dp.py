@@ -37,8 +37,10 @@ def _check_matrix(tga, seqs, which, gap_bool, adjust, minv, R, seed, force_gener
         aligner = tga.get_aligner_object(tga.get_scoring_matrix('C', which), gap_bool, 'tvr')
         P = _P(oracle.scoring_matrix('C', which), gap_bool)
     eng = DistEngine(Scoring.from_aligner(aligner), force_generic=force_generic)
+    from telogator2_b200.dist_engine import canonical_order
     res = eng.pair_scores(seqs, adjust, minv, R, seed)
     D = eng.dist_matrix(seqs, adjust, minv, R, seed, res=res)
+    res = canonical_order(res, len(seqs))
     Do, aln, rnd, cells = oracle.dist_matrix_c(seqs, P, adjust, minv, R, seed, want_scores=True)
     bad = np.nonzero(res['aln'] != aln)[0]
     assert len(bad) == 0, f'aln mismatch at pairs {bad[:10]}: gpu {res["aln"][bad[:10]]} oracle {aln[bad[:10]]}'
