@@ -1,0 +1,67 @@
+"""Worker of tests/test_multi_gpu_gloo.py: one rank of a world_size-2 gloo job exercising the sharding +
+gather logic of telogator2_b200.multi_gpu with the CPU oracle standing in for the device call."""
+import gzip
+import json
+import os
+import sys
+
+import numpy as np
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import oracle  # noqa: E402
+from telogator2_b200.dist_engine import DistEngine, NOT_COMPUTED  # noqa: E402
+from telogator2_b200.multi_gpu import shard_pair_indices, sharded_pair_scores  # noqa: E402
+
+
+def main():
+    out_path = sys.argv[1]
+    dist.init_process_group('gloo')
+    rank, world = dist.get_rank(), dist.get_world_size()
+    with gzip.open(os.path.join(ROOT, 'tests', 'golden', 'colorvecs.json.gz'), 'rt') as f:
+        cv = json.load(f)['colorvecs']['human_ont']
+    seqs = [c[:400 + 13 * i] for i, c in enumerate(cv[:14])]
+    P = oracle.AlignerParams(oracle.scoring_matrix('C', 'tvr'), (True, True))
+    R, seed = 2, 4321
+    n = len(seqs)
+    n_pairs = n * (n - 1) // 2
+    _D, aln_full, rnd_full, _cells = oracle.dist_matrix_c(seqs, P, True, True, R, seed, want_scores=True)
+
+    def compute(shard):
+        idx = shard_pair_indices(n_pairs, shard[0], shard[1], block=8)
+        aln = np.full(n_pairs, NOT_COMPUTED, dtype=np.int32)
+        rnd = np.full((n_pairs, R), NOT_COMPUTED, dtype=np.int32)
+        iden = np.zeros(n_pairs)
+        nn = np.zeros(n_pairs, dtype=np.int32)
+        mm = np.zeros(n_pairs, dtype=np.int32)
+        pairs = [(i, j) for i in range(n) for j in range(i + 1, n)]
+        for p in idx:
+            i, j = pairs[p]
+            det = {}
+            oracle.tvr_distance_py(seqs[i], seqs[j], P, True, True, R, seed + int(p), detail=det)
+            aln[p] = int(det['aln'])
+            iden[p] = det['iden']
+            nn[p], mm[p] = det['n'], det['m']
+            for k, v in enumerate(det['rand']):
+                rnd[p, k] = int(v)
+        return dict(aln=aln, rnd=rnd, iden=iden, n=nn, m=mm, order=None)
+
+    res = sharded_pair_scores(None, seqs, True, True, R, seed, compute=compute, device='cpu')
+    assert np.array_equal(res['aln'], aln_full), 'gathered aln differs'
+    assert np.array_equal(res['rnd'], rnd_full), 'gathered rnd differs'
+    d = DistEngine.distances(res, R)
+    D = np.zeros((n, n), dtype='<f4')
+    iu = np.triu_indices(n, 1)
+    D[iu] = d
+    D[(iu[1], iu[0])] = d
+    assert np.array_equal(D, _D), 'distance matrix differs'
+    own = shard_pair_indices(n_pairs, rank, world, block=8)
+    np.save(out_path + f'.rank{rank}.npy', own)
+    dist.barrier()
+    dist.destroy_process_group()
+    print('rank', rank, 'ok', len(own), 'pairs')
+
+
+if __name__ == '__main__':
+    main()
