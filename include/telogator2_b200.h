@@ -144,20 +144,30 @@ size_t tg_kmer_table_bytes(void);
 int tg_kmer_table_build(const char *kmers_concat, const int32_t *kmer_off, int K,
                         const int32_t *issub_edges, const int32_t *issub_off, /* KMER_ISSUBSTRING CSR or NULL */
                         void *h_table);
+/* One automaton for TWO k-mer lists (KMER_LIST + KMER_LIST_REV, tg_tel.py:160-161; CANONICAL_STRINGS +
+ * CANONICAL_STRINGS_REV, tg_tel.py:262-263): the coverage kernels then need one table lookup per base for both. */
+int tg_kmer_table_build_pair(const char *kmers_a, const int32_t *off_a, int KA,
+                             const char *kmers_b, const int32_t *off_b, int KB, void *h_table);
 
 /* Read layout: read r occupies bases [base_off[r], base_off[r] + len[r]) of a padded base
  * space; base_off[r] is a multiple of 128.  ASCII input uses one byte per padded base
  * (pad bytes arbitrary).  Packed form: d_pack2[w] holds bases 16w..16w+15, 2 bits each
  * (A=0 C=1 T=2 G=3, little end first); d_nmask[w] holds 32 bases, bit set = not ACGT.
+ * d_base_off has n_reads + 1 entries (the last one = total padded bases).
  * Replaces nothing in the reference (it scans Python str) -- this is the HBM layout. */
 int tg_scan_pack(const uint8_t *d_ascii, const int64_t *d_base_off, const int32_t *d_len, int n_reads,
                  uint32_t *d_pack2, uint32_t *d_nmask, void *stream);
 
+/* The coverage kernels work on independent tiles of tg_scan_tile_bases() output positions.
+ * d_tile_off[n_reads + 1] is the exclusive prefix sum of the tiles per read:
+ *   base count: ceil(len / tile_bases) tiles,  density: ceil(max(len - window, 0) / tile_bases) tiles. */
+int tg_scan_tile_bases(void);
+
 /* get_telomere_base_count(read, kmer_list) (tg_kmer.py:93-102) for two k-mer lists at once
- * (CANONICAL_STRINGS and CANONICAL_STRINGS_REV, tg_tel.py:262-263): d_counts[2r + s]. */
+ * (CANONICAL_STRINGS and CANONICAL_STRINGS_REV, tg_tel.py:262-263): d_counts[2r + s] (zeroed here). */
 int tg_scan_basecount(const uint32_t *d_pack2, const uint32_t *d_nmask, const int64_t *d_base_off,
-                      const int32_t *d_len, int n_reads, const void *d_table_a, const void *d_table_b,
-                      int32_t *d_counts, void *stream);
+                      const int32_t *d_len, int n_reads, const int64_t *d_tile_off, int64_t n_tiles,
+                      const void *d_table_pair, int32_t *d_counts, void *stream);
 
 /* RC(read) (tg_util.py:433-434) applied in place of tg_tel.py:265-266: reads with
  * d_flip[r] != 0 are reverse-complemented into d_pack2_out / d_nmask_out, others copied. */
@@ -170,8 +180,8 @@ int tg_scan_orient(const uint32_t *d_pack2, const uint32_t *d_nmask, const int64
  * counts cnt[i] = #covered positions in (i, i + window], i in [0, len - window), as uint8 at
  * d_cnt_x[base_off[r] + i]; density = cnt / window in float64 on the host.  window <= 255. */
 int tg_scan_density(const uint32_t *d_pack2, const uint32_t *d_nmask, const int64_t *d_base_off,
-                    const int32_t *d_len, int n_reads, const void *d_table_a, const void *d_table_b,
-                    int window, uint8_t *d_cnt_a, uint8_t *d_cnt_b, void *stream);
+                    const int32_t *d_len, int n_reads, const int64_t *d_tile_off, int64_t n_tiles,
+                    const void *d_table_pair, int window, uint8_t *d_cnt_a, uint8_t *d_cnt_b, void *stream);
 
 /* get_nonoverlapping_kmer_hits(seq[lo:hi], KMER_LIST, KMER_ISSUBSTRING) (tg_kmer.py:173-230)
  * for a batch of slices: slice q = read d_slice_read[q], positions [d_slice_lo[q], d_slice_hi[q]).

@@ -19,10 +19,11 @@
 #include <limits.h>
 #include <stdlib.h>
 #include <string.h>
+#include <type_traits>
 
 namespace {
 
-constexpr int WAVE_MAX_WARPS = 12;         // warps (= concurrent jobs) per CTA, one CTA per SM
+constexpr int WAVE_MAX_WARPS = 16;         // warps (= concurrent jobs) per CTA, one CTA per SM
 constexpr int MAXA = 32;
 
 struct WaveParams {
@@ -119,6 +120,12 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr)
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ uint32_t lds_u16(uint32_t addr)
 {
     uint32_t v;
@@ -156,10 +163,57 @@ struct Strip<8> {
     }
 };
 
+// Two rows x 8 columns per step: row r0 (values a_c) and row r0 + 1 (values b_c) advance as two dependency chains
+// offset by one cell, which doubles the instruction-level parallelism of the 3-input-max chain.
+//   a_c = max(up_{c-1} + s0_c, up_c, a_{c-1})      b_c = max(a_{c-1} + s1_c, a_c, b_{c-1})
+struct Strip2x8 {
+    static __device__ __forceinline__ uint32_t run(uint32_t (&H)[8], uint32_t dg, uint32_t L0, uint32_t L1,
+                                                   uint32_t p00, uint32_t p01, uint32_t p10, uint32_t p11)
+    {
+        const uint2 q00 = lds64(p00), q01 = lds64(p01), q10 = lds64(p10), q11 = lds64(p11);
+        uint32_t d0 = dg, la = L0, pa = L0, lb = L1, up, a;
+#define TG_CELL2(c, x0, y0, x1, y1, k)                    \
+    up = H[c];                                             \
+    a = cell(d0, merge_scores<k>(x0, y0), up, la);         \
+    lb = cell(pa, merge_scores<k>(x1, y1), a, lb);         \
+    d0 = up; la = a; pa = a; H[c] = lb;
+        TG_CELL2(0, q00.x, q01.x, q10.x, q11.x, 0) TG_CELL2(1, q00.x, q01.x, q10.x, q11.x, 1)
+        TG_CELL2(2, q00.x, q01.x, q10.x, q11.x, 2) TG_CELL2(3, q00.x, q01.x, q10.x, q11.x, 3)
+        TG_CELL2(4, q00.y, q01.y, q10.y, q11.y, 0) TG_CELL2(5, q00.y, q01.y, q10.y, q11.y, 1)
+        TG_CELL2(6, q00.y, q01.y, q10.y, q11.y, 2) TG_CELL2(7, q00.y, q01.y, q10.y, q11.y, 3)
+#undef TG_CELL2
+        return la;      // a_7: last column of row r0
+    }
+};
+
+struct Strip2x16 {
+    static __device__ __forceinline__ uint32_t run(uint32_t (&H)[16], uint32_t dg, uint32_t L0, uint32_t L1,
+                                                   uint32_t p00, uint32_t p01, uint32_t p10, uint32_t p11)
+    {
+        const uint4 q00 = lds128(p00), q01 = lds128(p01), q10 = lds128(p10), q11 = lds128(p11);
+        uint32_t d0 = dg, la = L0, pa = L0, lb = L1, up, a;
+#define TG_CELL2(c, x0, y0, x1, y1, k)                    \
+    up = H[c];                                             \
+    a = cell(d0, merge_scores<k>(x0, y0), up, la);         \
+    lb = cell(pa, merge_scores<k>(x1, y1), a, lb);         \
+    d0 = up; la = a; pa = a; H[c] = lb;
+#define TG_QUAD2(c, f)                                                                                  \
+    TG_CELL2(c, q00.f, q01.f, q10.f, q11.f, 0) TG_CELL2(c + 1, q00.f, q01.f, q10.f, q11.f, 1)          \
+    TG_CELL2(c + 2, q00.f, q01.f, q10.f, q11.f, 2) TG_CELL2(c + 3, q00.f, q01.f, q10.f, q11.f, 3)
+        TG_QUAD2(0, x) TG_QUAD2(4, y) TG_QUAD2(8, z) TG_QUAD2(12, w)
+#undef TG_QUAD2
+#undef TG_CELL2
+        return la;      // a_15: last column of row r0
+    }
+};
+
 // Shared memory per warp: query profile [2][A+1][W] bytes, then row letters [row_cap] u16 (a0 | a1 << 8).
-template <int C, int MODE>
+// V = 0: 16 columns x 1 row per step, V = 1: 8 x 1, V = 2: 8 columns x 2 rows, V = 3: 16 columns x 2 rows per step
+template <int V, int MODE>
 __global__ void __launch_bounds__(WAVE_MAX_WARPS * 32, 1) nw_wave_kernel(const __grid_constant__ WaveParams P)
 {
+    constexpr int C = (V == 0 || V == 3) ? 16 : 8;
+    constexpr int RR = (V >= 2) ? 2 : 1;
     constexpr int W = 32 * C;
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -234,7 +288,7 @@ __global__ void __launch_bounds__(WAVE_MAX_WARPS * 32, 1) nw_wave_kernel(const _
         // row letters of both alignments; rows past the end of a sequence get the padding letter A, whose
         // all-zero profile row makes H' copy the previous row (H' is non-decreasing along a row)
         __syncwarp();
-        for (int r = lane; r < N + 1; r += 32) {
+        for (int r = lane; r < N + 4; r += 32) {
             const uint32_t a0 = (r < n0) ? (uint32_t)__ldg(P.pool + row0 + r) : (uint32_t)A;
             const uint32_t a1 = (r < n1) ? (uint32_t)__ldg(P.pool + row1 + r) : (uint32_t)A;
             rows[r] = (uint16_t)(a0 | (a1 << 8));
@@ -259,6 +313,7 @@ __global__ void __launch_bounds__(WAVE_MAX_WARPS * 32, 1) nw_wave_kernel(const _
 
 #pragma unroll
             for (int c = 0; c < C; c++) H[c] = 0u;
+            if constexpr (RR == 1) {
             uint32_t prev_left = 0u;
             const int steps = N + 31;
             int r = -lane;
@@ -296,6 +351,44 @@ __global__ void __launch_bounds__(WAVE_MAX_WARPS * 32, 1) nw_wave_kernel(const _
                     } else if (r == -1) ap = lds_u16(rows_s);
                     prev_left = left_in;
                 }
+            }
+            } else {
+            // ---- two rows per step: this lane handles row pair k = s - lane (rows 2k, 2k + 1) ----
+            const int NP = (N + 1) >> 1;
+            const int steps = NP + 31;
+            int k = -lane;
+            uint32_t prevL1 = 0u, A7 = 0u;
+            uint32_t ap2 = (k == 0) ? lds_u32(rows_s) : 0u;       // letters of rows 2k (low half) and 2k + 1
+            uint2 *bord2 = reinterpret_cast<uint2 *>(bord);
+            uint2 *bw = bord2 + k;
+            uint2 bcur = make_uint2(0u, 0u), bnext = make_uint2(0u, 0u);
+            if (blk > 0) {
+                if (lane < NP) bcur = __ldcg(bord2 + lane);
+                if (32 + lane < NP) bnext = __ldcg(bord2 + 32 + lane);
+            }
+            for (int s = 0; s < steps; s++, k++, bw++) {
+                uint32_t L0 = __shfl_up_sync(TG_FULL_MASK, A7, 1);
+                uint32_t L1 = __shfl_up_sync(TG_FULL_MASK, H[C - 1], 1);
+                if (blk > 0) {
+                    if ((s & 31) == 0 && s > 0) {
+                        bcur = bnext;
+                        const int idx = s + 32 + lane;
+                        bnext = (idx < NP) ? __ldcg(bord2 + idx) : make_uint2(0u, 0u);
+                    }
+                    const uint32_t b0 = __shfl_sync(TG_FULL_MASK, bcur.x, s & 31);
+                    const uint32_t b1 = __shfl_sync(TG_FULL_MASK, bcur.y, s & 31);
+                    if (lane == 0) { L0 = b0; L1 = b1; }
+                } else if (lane == 0) { L0 = 0u; L1 = 0u; }
+                if ((unsigned)k < (unsigned)NP) {
+                    using S2 = typename std::conditional<C == 16, Strip2x16, Strip2x8>::type;
+                    A7 = S2::run(H, prevL1, L0, L1,
+                                       pb0 + (ap2 & 0xffu) * W, pb1 + ((ap2 >> 8) & 0xffu) * W,
+                                       pb0 + ((ap2 >> 16) & 0xffu) * W, pb1 + (ap2 >> 24) * W);
+                    if (lane == 31) *bw = make_uint2(A7, H[C - 1]);
+                    ap2 = lds_u32(rows_s + 4 * (k + 1));
+                } else if (k == -1) ap2 = lds_u32(rows_s);
+                prevL1 = L1;
+            }
             }
             __syncwarp();
 
@@ -617,7 +710,7 @@ __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t *out, int iters,
 // ================================================================================================
 // C ABI
 // ================================================================================================
-static int g_wave_c = 16;          // packed columns per lane (8 or 16); TG_WAVE_C overrides
+static int g_wave_variant = 3;     // 0: 16 cols x 1 row, 1: 8 x 1, 2: 8 cols x 2 rows per step; TG_WAVE_VARIANT overrides
 static int g_wave_warps = 0;       // 0 = as many as shared memory allows
 
 static void wave_env()
@@ -625,7 +718,7 @@ static void wave_env()
     static bool done = false;
     if (done) return;
     done = true;
-    if (const char *e = getenv("TG_WAVE_C")) { const int v = atoi(e); if (v == 8 || v == 16) g_wave_c = v; }
+    if (const char *e = getenv("TG_WAVE_VARIANT")) { const int v = atoi(e); if (v >= 0 && v <= 3) g_wave_variant = v; }
     if (const char *e = getenv("TG_WAVE_WARPS")) { const int v = atoi(e); if (v >= 1 && v <= WAVE_MAX_WARPS) g_wave_warps = v; }
 }
 
@@ -669,25 +762,29 @@ TG_EXPORT int tg_nw_wave_check(const tg_nw_scoring *sc, const tg_nw_job *h_jobs,
     return TG_OK;
 }
 
-template <int C, int MODE>
+template <int V, int MODE>
 static int wave_launch_t(const WaveParams &P, int grid, int warps, size_t smem, cudaStream_t st)
 {
-    TG_CUDA_CHECK(cudaFuncSetAttribute(nw_wave_kernel<C, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nw_wave_kernel<C, MODE><<<grid, warps * 32, smem, st>>>(P);
+    TG_CUDA_CHECK(cudaFuncSetAttribute(nw_wave_kernel<V, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nw_wave_kernel<V, MODE><<<grid, warps * 32, smem, st>>>(P);
     TG_CUDA_CHECK(cudaGetLastError());
     return TG_OK;
 }
 
-static int wave_launch(const WaveParams &P, int mode, int C, int grid, int warps, size_t smem, cudaStream_t st)
+template <int V>
+static int wave_launch_v(const WaveParams &P, int mode, int grid, int warps, size_t smem, cudaStream_t st)
 {
-    if (C == 16) {
-        if (mode == JOBS_EXPLICIT) return wave_launch_t<16, JOBS_EXPLICIT>(P, grid, warps, smem, st);
-        if (mode == JOBS_PHASE_A) return wave_launch_t<16, JOBS_PHASE_A>(P, grid, warps, smem, st);
-        return wave_launch_t<16, JOBS_PHASE_B>(P, grid, warps, smem, st);
-    }
-    if (mode == JOBS_EXPLICIT) return wave_launch_t<8, JOBS_EXPLICIT>(P, grid, warps, smem, st);
-    if (mode == JOBS_PHASE_A) return wave_launch_t<8, JOBS_PHASE_A>(P, grid, warps, smem, st);
-    return wave_launch_t<8, JOBS_PHASE_B>(P, grid, warps, smem, st);
+    if (mode == JOBS_EXPLICIT) return wave_launch_t<V, JOBS_EXPLICIT>(P, grid, warps, smem, st);
+    if (mode == JOBS_PHASE_A) return wave_launch_t<V, JOBS_PHASE_A>(P, grid, warps, smem, st);
+    return wave_launch_t<V, JOBS_PHASE_B>(P, grid, warps, smem, st);
+}
+
+static int wave_launch(const WaveParams &P, int mode, int variant, int grid, int warps, size_t smem, cudaStream_t st)
+{
+    if (variant == 0) return wave_launch_v<0>(P, mode, grid, warps, smem, st);
+    if (variant == 1) return wave_launch_v<1>(P, mode, grid, warps, smem, st);
+    if (variant == 3) return wave_launch_v<3>(P, mode, grid, warps, smem, st);
+    return wave_launch_v<2>(P, mode, grid, warps, smem, st);
 }
 
 // shared set-up of the three job modes
@@ -699,18 +796,18 @@ static int wave_setup(WaveParams &P, const tg_nw_scoring *sc, int max_n, int *C_
     if (rc != TG_OK) return rc;
     if (max_n < 1) return tg_set_err(TG_EINVAL, "max_n < 1");
     P.scratch_stride = (int)(((size_t)max_n + 63) / 32 * 32);
-    P.row_cap = (max_n + 1 + 7) / 8 * 8;
+    P.row_cap = (max_n + 4 + 7) / 8 * 8;
     P.A = sc->alphabet; P.g = sc->gap; P.gr = sc->gap_right; P.right_free = (sc->gap_right != sc->gap);
     for (int a = 0; a < MAXA; a++)
         for (int b = 0; b < MAXA; b++)
             P.sp[a * MAXA + b] = (a < sc->alphabet && b < sc->alphabet) ? (uint8_t)(sc->sub[a * MAXA + b] - 2 * sc->gap) : 0;
-    const int C = g_wave_c;
+    const int C = (g_wave_variant == 0 || g_wave_variant == 3) ? 16 : 8;
     const size_t per_warp = (size_t)2 * (sc->alphabet + 1) * 32 * C + (size_t)P.row_cap * 2;
     int warps = (int)((226 * 1024 - MAXA * MAXA) / per_warp);
     if (warps > WAVE_MAX_WARPS) warps = WAVE_MAX_WARPS;
     if (g_wave_warps && warps > g_wave_warps) warps = g_wave_warps;
     if (warps < 1) return tg_set_err(TG_ERANGE, "sequences of %d rows do not fit the wave kernel's shared memory", max_n);
-    *C_out = C; *warps_out = warps;
+    *C_out = g_wave_variant; *warps_out = warps;
     *smem_out = MAXA * MAXA + (size_t)warps * per_warp;
     return TG_OK;
 }

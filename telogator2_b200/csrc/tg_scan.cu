@@ -11,8 +11,9 @@
 // its chunk of positions right to left (after max_len-1 warm-up symbols), so the automaton reports at
 // position p exactly the k-mers that START at p.  re.finditer's leftmost-non-overlapping rule only
 // differs from "all occurrences" for k-mers that can overlap themselves ("bordered"); their candidate
-// starts go to a bitmap that one lane per k-mer resolves greedily, left to right, with the blocking
-// position carried from tile to tile (a CTA walks the tiles of a read in order).
+// starts go to a bitmap that one lane per k-mer resolves greedily, left to right.  Coverage tiles are
+// independent (a chain of overlapping candidates that crosses a tile start is walked back through global
+// memory, exactly); the hits kernel walks the tiles of a slice in order and carries the blocking position.
 #include "tg_common.cuh"
 #include <string.h>
 #include <vector>
@@ -21,25 +22,31 @@
 
 namespace {
 
-constexpr int SC_MAXK = 64;
+constexpr int SC_MAXK = 128;               // two lists of up to 64 k-mers in one automaton
+constexpr int SC_MAXLIST = 64;
 constexpr int SC_MAXLEN = 32;
-constexpr int SC_MAXSTATES = 2112;
+constexpr int SC_MAXSTATES = 4095;
 constexpr int SC_MAXBORD = 32;
 constexpr uint16_t SC_OUT_FLAG = 0x8000;
 
+// One automaton for one k-mer list (hits) or for two lists at once ("groups" 0 and 1: KMER_LIST and
+// KMER_LIST_REV, or CANONICAL_STRINGS and their reverse complements).
 struct KmerTable {
-    int32_t K, n_states, max_len, n_bord;
+    int32_t K, n_states, max_len, n_bord;   // K = k-mers of all groups
+    int32_t n_groups, KA, pad_[2];          // KA = k-mers of group 0 (they come first)
     int32_t len[SC_MAXK];
     int32_t bord_kmer[SC_MAXBORD];          // k-mer index of bordered slot b
     int32_t bord_len[SC_MAXBORD];
-    uint64_t super[SC_MAXK];                // KMER_ISSUBSTRING[k] as a bit mask (k-mers containing k)
-    uint64_t lengt[SC_MAXLEN];              // lengt[d] = k-mers with len > d
-    uint64_t bord_mask;                     // bordered k-mers
-    uint64_t has_super_mask;                // k-mers with a non-empty super[]
-    uint16_t trans[SC_MAXSTATES * 4];       // next state (low 12 bits) | SC_OUT_FLAG
-    uint8_t out_len[SC_MAXSTATES];          // longest NON-bordered k-mer starting here (0 = none)
-    uint32_t out_bord[SC_MAXSTATES];        // bordered slots starting here
-    uint64_t out_mask[SC_MAXSTATES];        // all k-mers starting here
+    int32_t bord_group[SC_MAXBORD];
+    uint64_t bord_pat[SC_MAXBORD];          // the k-mer, 2 bits per base, first base in the low bits
+    uint64_t super[SC_MAXLIST];             // KMER_ISSUBSTRING[k] as a bit mask (group 0 only)
+    uint64_t lengt[SC_MAXLEN];              // lengt[d] = group-0 k-mers with len > d
+    uint64_t bord_mask;                     // bordered group-0 k-mers
+    uint64_t has_super_mask;                // group-0 k-mers with a non-empty super[]
+    uint16_t trans[(SC_MAXSTATES + 1) * 4]; // next state (low 12 bits) | SC_OUT_FLAG
+    uint16_t out_len[SC_MAXSTATES + 1];     // longest NON-bordered k-mer starting here: group 0 low byte, group 1 high byte
+    uint32_t out_bord[SC_MAXSTATES + 1];    // bordered slots starting here
+    uint64_t out_mask[SC_MAXSTATES + 1];    // group-0 k-mers starting here
 };
 
 // ---- packed read access ---------------------------------------------------------------------------
@@ -122,30 +129,6 @@ __global__ void __launch_bounds__(256) orient_kernel(const uint32_t *__restrict_
 }
 
 // ---- shared pieces of the tile kernels -----------------------------------------------------------
-// Stage bases [t0, t0 + n_bases) of a read (absolute base index = rbase + position) into shared memory;
-// positions outside [lo, hi) are forced to N.  n_bases is a multiple of 32, t0 a multiple of 32.
-__device__ __forceinline__ void stage_tile(const uint32_t *__restrict__ pack2, const uint32_t *__restrict__ nmask, int64_t rbase,
-                                           int64_t padded_len, int t0, int n_bases, int lo, int hi,
-                                           uint32_t *s_pack, uint32_t *s_mask)
-{
-    for (int w = threadIdx.x; w < n_bases / 32; w += blockDim.x) {
-        const int p0 = t0 + w * 32;                               // first position of this mask word
-        uint32_t m = 0xffffffffu, a = 0u, b = 0u;
-        if (p0 >= 0 && p0 < padded_len) {
-            const int64_t g = (rbase + p0) >> 5;
-            m = nmask[g];
-            a = pack2[g * 2];
-            b = pack2[g * 2 + 1];
-        }
-        // clip to [lo, hi)
-        if (p0 < lo) m |= (lo - p0 >= 32) ? 0xffffffffu : ((1u << (lo - p0)) - 1u);
-        if (p0 + 32 > hi) m |= (hi <= p0) ? 0xffffffffu : ~((1u << (hi - p0)) - 1u);
-        s_mask[w] = m;
-        s_pack[w * 2] = a;
-        s_pack[w * 2 + 1] = b;
-    }
-}
-
 __device__ __forceinline__ void smem_byte_max(uint8_t *arr, int idx, uint32_t val)
 {
     uint32_t *word = reinterpret_cast<uint32_t *>(arr + (idx & ~3));
@@ -162,7 +145,7 @@ __device__ __forceinline__ void smem_byte_max(uint8_t *arr, int idx, uint32_t va
 // Device-side view of one automaton held in shared memory.
 struct SmemTable {
     const uint16_t *trans;
-    const uint8_t *out_len;
+    const uint16_t *out_len;
     const uint32_t *out_bord;
     const uint64_t *out_mask;     // only in hits mode
     int max_len, n_bord;
@@ -179,7 +162,7 @@ __device__ SmemTable load_table(const KmerTable *__restrict__ T, uint8_t *&sp, b
 {
     const int ns = T->n_states;
     uint16_t *tr = reinterpret_cast<uint16_t *>(carve(sp, (size_t)ns * 4 * sizeof(uint16_t)));
-    uint8_t *ol = carve(sp, ns);
+    uint16_t *ol = reinterpret_cast<uint16_t *>(carve(sp, (size_t)ns * sizeof(uint16_t)));
     uint32_t *ob = reinterpret_cast<uint32_t *>(carve(sp, (size_t)ns * sizeof(uint32_t)));
     uint64_t *om = want_mask ? reinterpret_cast<uint64_t *>(carve(sp, (size_t)ns * sizeof(uint64_t))) : nullptr;
     for (int i = threadIdx.x; i < ns * 4; i += blockDim.x) tr[i] = T->trans[i];
@@ -195,244 +178,321 @@ __device__ SmemTable load_table(const KmerTable *__restrict__ T, uint8_t *&sp, b
 }
 
 // ---- coverage kernel (base count / density) -------------------------------------------------------
+// Tiles are independent: a CTA handles a REGION of 8192 read positions [t0 - HL, t0 + TILE_OUT + HR) and emits the
+// TILE_OUT outputs of [t0, t0 + TILE_OUT).  The halos cover everything an output can depend on: matches start at most
+// max_len - 1 <= 31 positions before a covered position, a density window looks window <= 255 positions ahead.
+// The only long-range dependency -- re.finditer's greedy rule for a self-overlapping k-mer whose chain of overlapping
+// candidates crosses the region start -- is resolved exactly by walking the chain back through global memory.
 constexpr int COV_THREADS = 128;
 constexpr int COV_CH = 64;                          // positions per thread
-constexpr int COV_TILE = COV_THREADS * COV_CH;      // 8192
-constexpr int COV_LAG = 256;                        // density output lags the tile by this many positions (>= window)
-constexpr int COV_STAGE = COV_TILE + 64;            // staged bases per tile (tile + right halo)
+constexpr int COV_REGION = COV_THREADS * COV_CH;    // 8192
+constexpr int COV_HL = 64;
+constexpr int COV_OUT_THREADS = 121;
+constexpr int COV_TILE_OUT = COV_OUT_THREADS * COV_CH;   // 7744
+constexpr int COV_STAGE = COV_REGION + 32;          // staged bases (region + automaton warm-up)
 enum { MODE_COUNT = 0, MODE_DENSITY = 1 };
+
+// shared-memory index maps that make "lane t touches element 64 t + j" conflict free
+__device__ __forceinline__ int pidx(int w) { return w + (w >> 5); }            // 2-bit words (4 per chunk)
+__device__ __forceinline__ int midx(int w) { return w + (w >> 5); }            // mask words (2 per chunk)
+__device__ __forceinline__ int lidx(int x) { return x + ((x >> 6) << 2); }     // L bytes (64 per chunk)
 
 struct CovParams {
     const uint32_t *pack2, *nmask;
     const int64_t *base_off;
     const int32_t *len;
     int n_reads;
-    const KmerTable *tab[2];
+    const int64_t *tile_off;       // [n_reads + 1] exclusive prefix sum of tiles per read
+    long long n_tiles;
+    const KmerTable *tab;
     int window;
     uint8_t *cnt[2];
     int32_t *counts;
-    unsigned int *next_read;
 };
+
+// does bordered k-mer (pat, blen) start at absolute read position p?  (direct test on the packed planes)
+__device__ bool kmer_at(const uint32_t *__restrict__ pack2, const uint32_t *__restrict__ nmask, int64_t rbase, int L, int64_t p,
+                        uint64_t pat, int blen)
+{
+    if (p < 0 || p + blen > L) return false;
+    const int64_t g = rbase + p;
+    // N-mask bits [g, g + blen): only words that hold positions of this read are touched
+    const int64_t mw = g >> 5;
+    const int msh = (int)(g & 31);
+    uint64_t mbits = (uint64_t)nmask[mw];
+    if (msh + blen > 32) mbits |= (uint64_t)nmask[mw + 1] << 32;
+    mbits >>= msh;
+    if (mbits & ((1ull << blen) - 1ull)) return false;           // blen <= 32
+    const int64_t pw = g >> 4;
+    const int sh = (int)(g & 15) * 2;
+    uint64_t lo = (uint64_t)pack2[pw];
+    if (sh + 2 * blen > 32) lo |= (uint64_t)pack2[pw + 1] << 32;
+    uint64_t bits = lo >> sh;
+    if (sh + 2 * blen > 64) bits |= (uint64_t)pack2[pw + 2] << (64 - sh);
+    const uint64_t m = (blen >= 32) ? ~0ull : ((1ull << (2 * blen)) - 1ull);
+    return ((bits ^ pat) & m) == 0;
+}
+
+// Exact greedy state in front of candidate c0 (absolute): walk the chain of overlapping candidates back to its
+// head (a candidate with no other candidate within blen - 1 positions before it, or the first of the read), then
+// replay re.finditer forward.  Returns the position before which the k-mer is blocked.
+__device__ int chain_state_before(const uint32_t *pack2, const uint32_t *nmask, int64_t rbase, int L, int c0,
+                                  uint64_t pat, int blen)
+{
+    int head = c0, p = c0 - 1;
+    while (p >= 0 && head - p < blen) {
+        if (kmer_at(pack2, nmask, rbase, L, p, pat, blen)) head = p;
+        p--;
+    }
+    if (head == c0) return 0;
+    int blocked = head + blen;
+    for (int q = head + 1; q < c0; q++)
+        if (q >= blocked && kmer_at(pack2, nmask, rbase, L, q, pat, blen)) blocked = q + blen;
+    return blocked;
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(COV_THREADS) scan_cov_kernel(const CovParams P)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *sp = smem;
-    SmemTable tab[2];
-    tab[0] = load_table(P.tab[0], sp, false);
-    tab[1] = load_table(P.tab[1], sp, false);
-    uint32_t *s_pack = reinterpret_cast<uint32_t *>(carve(sp, COV_STAGE / 16 * 4));
-    uint32_t *s_mask = reinterpret_cast<uint32_t *>(carve(sp, COV_STAGE / 32 * 4));
+    const SmemTable T = load_table(P.tab, sp, false);
+    uint32_t *s_pack = reinterpret_cast<uint32_t *>(carve(sp, (size_t)pidx(COV_STAGE / 16 + 1) * 4 + 16));
+    uint32_t *s_mask = reinterpret_cast<uint32_t *>(carve(sp, (size_t)midx(COV_STAGE / 32 + 1) * 4 + 16));
     uint8_t *s_L[2];
-    uint32_t *s_cov[2], *s_bm[2];
+    uint32_t *s_cov[2];
     for (int s = 0; s < 2; s++) {
-        s_L[s] = carve(sp, COV_TILE);
-        s_cov[s] = reinterpret_cast<uint32_t *>(carve(sp, (COV_LAG + COV_TILE) / 32 * 4));
-        s_bm[s] = reinterpret_cast<uint32_t *>(carve(sp, (size_t)max(tab[s].n_bord, 1) * (COV_TILE / 32) * 4));
+        s_L[s] = carve(sp, lidx(COV_REGION));
+        s_cov[s] = reinterpret_cast<uint32_t *>(carve(sp, (COV_REGION / 32 + 1) * 4));
     }
-    __shared__ int s_blocked[2][SC_MAXBORD];
-    __shared__ int s_any[2][SC_MAXBORD];
-    __shared__ int s_carry[2];
+    uint32_t *s_bm = reinterpret_cast<uint32_t *>(carve(sp, (size_t)max(T.n_bord, 1) * (COV_REGION / 32) * 4));
+    __shared__ int s_any[SC_MAXBORD];
     __shared__ int s_wmax[2][COV_THREADS / 32];
     __shared__ int s_red[2][COV_THREADS / 32];
-    __shared__ unsigned int s_read;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nb = T.n_bord;
+    const int w = P.window;
 
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) s_read = atomicAdd(P.next_read, 1u);
-        __syncthreads();
-        const int r = (int)s_read;
-        if (r >= P.n_reads) break;
+    for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+        // tile -> (read, tile index in read)
+        int lo = 0, hi = P.n_reads;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (P.tile_off[mid] <= tile) lo = mid; else hi = mid;
+        }
+        const int r = lo;
+        const int t0 = (int)(tile - P.tile_off[r]) * COV_TILE_OUT;
+        const int a0 = t0 - COV_HL;                                   // read position of region index 0
         const int64_t rbase = P.base_off[r];
         const int L = P.len[r];
         const int64_t padded = P.base_off[r + 1] - rbase;
-        const int w = P.window;
-        const int n_out = (MODE == MODE_DENSITY) ? max(L - w, 0) : 0;
-        const int span = (MODE == MODE_DENSITY) ? (n_out > 0 ? n_out + COV_LAG : 0) : L;
-        const int n_tiles = (span + COV_TILE - 1) / COV_TILE;
-        if (tid < SC_MAXBORD) { s_blocked[0][tid] = 0; s_blocked[1][tid] = 0; }
-        if (tid < 2) s_carry[tid] = 0;
-        for (int s = 0; s < 2; s++)
-            for (int i = tid; i < COV_LAG / 32; i += COV_THREADS) s_cov[s][i] = 0u;
-        int my_count[2] = {0, 0};
-
-        for (int tile = 0; tile < n_tiles; tile++) {
-            const int t0 = tile * COV_TILE;
-            __syncthreads();
-            stage_tile(P.pack2, P.nmask, rbase, padded, t0, COV_STAGE, 0, L, s_pack, s_mask);
-            for (int s = 0; s < 2; s++) {
-                for (int i = tid; i < tab[s].n_bord * (COV_TILE / 32); i += COV_THREADS) s_bm[s][i] = 0u;
-                if (tid < SC_MAXBORD) s_any[s][tid] = 0;
+        __syncthreads();
+        // ---- stage the packed planes of [a0, a0 + STAGE) ----
+        for (int wq = tid; wq < COV_STAGE / 32; wq += COV_THREADS) {
+            const int p0 = a0 + wq * 32;
+            uint32_t m = 0xffffffffu, a = 0u, b = 0u;
+            if (p0 >= 0 && p0 < padded) {
+                const int64_t g = (rbase + p0) >> 5;
+                m = P.nmask[g];
+                a = P.pack2[g * 2];
+                b = P.pack2[g * 2 + 1];
             }
-            __syncthreads();
+            s_mask[midx(wq)] = m;
+            s_pack[pidx(wq * 2)] = a;
+            s_pack[pidx(wq * 2 + 1)] = b;
+        }
+        for (int i = tid; i < nb * (COV_REGION / 32); i += COV_THREADS) s_bm[i] = 0u;
+        if (tid < SC_MAXBORD) s_any[tid] = 0;
+        __syncthreads();
 
-            // ---- phase B: automata, right to left over [c0, c0 + CH + max_len - 1) ----
-            {
-                const int c0 = tid * COV_CH;                          // tile-relative
-                for (int s = 0; s < 2; s++) {
-                    const SmemTable &T = tab[s];
-                    uint32_t state = 0;
-                    uint32_t lbuf = 0;                                // 4 L bytes being assembled
-                    for (int x = c0 + COV_CH + T.max_len - 2; x >= c0; x--) {
-                        const uint32_t isn = (s_mask[x >> 5] >> (x & 31)) & 1u;
-                        const uint32_t code = (s_pack[x >> 4] >> ((x & 15) * 2)) & 3u;
-                        uint32_t e = isn ? 0u : (uint32_t)T.trans[state * 4 + code];
-                        state = e & 0xfffu;
-                        if (x < c0 + COV_CH) {
-                            uint32_t Lh = 0;
-                            if (e & SC_OUT_FLAG) {
-                                Lh = T.out_len[state];
-                                uint32_t ob = T.out_bord[state];
-                                while (ob) {
-                                    const int b = __ffs(ob) - 1;
-                                    ob &= ob - 1;
-                                    atomicOr(&s_bm[s][b * (COV_TILE / 32) + (x >> 5)], 1u << (x & 31));
-                                    s_any[s][b] = 1;
-                                }
-                            }
-                            lbuf = (lbuf << 8) | Lh;                  // x descending: byte 0 ends up = lowest x
-                            if ((x & 3) == 0) { *reinterpret_cast<uint32_t *>(s_L[s] + x) = lbuf; lbuf = 0; }
-                        }
-                    }
-                }
+        // ---- phase B: one automaton for both lists, right to left over [c0, c0 + CH + max_len - 1) ----
+        {
+            const int c0 = tid * COV_CH;
+            uint32_t state = 0;
+            int x = c0 + COV_CH + T.max_len - 2;
+            for (; x >= c0 + COV_CH; x--) {                           // warm-up, no output
+                const uint32_t isn = (s_mask[midx(x >> 5)] >> (x & 31)) & 1u;
+                const uint32_t code = (s_pack[pidx(x >> 4)] >> ((x & 15) * 2)) & 3u;
+                state = isn ? 0u : ((uint32_t)T.trans[state * 4 + code] & 0xfffu);
             }
-            __syncthreads();
-
-            // ---- phase C: greedy resolution of bordered k-mers (one lane per (list, slot)) ----
-            if (warp == 0) {
-                for (int slot = lane; slot < tab[0].n_bord + tab[1].n_bord; slot += 32) {
-                    const int s = slot < tab[0].n_bord ? 0 : 1;
-                    const int b = s == 0 ? slot : slot - tab[0].n_bord;
-                    if (!s_any[s][b]) continue;
-                    const int blen = P.tab[s]->bord_len[b];
-                    int blocked = s_blocked[s][b];
-                    const uint32_t *bm = s_bm[s] + b * (COV_TILE / 32);
-                    for (int wd = 0; wd < COV_TILE / 32; wd++) {
-                        uint32_t word = bm[wd];
-                        while (word) {
-                            const int bit = __ffs(word) - 1;
-                            word &= word - 1;
-                            const int p = t0 + wd * 32 + bit;
-                            if (p >= blocked) {
-                                blocked = p + blen;
-                                smem_byte_max(s_L[s], wd * 32 + bit, (uint32_t)blen);
-                            }
-                        }
-                    }
-                    s_blocked[s][b] = blocked;
-                }
-            }
-            __syncthreads();
-
-            // ---- phase D: coverage = prefix max of (p + L[p]) ----
-            {
-                const int c0 = tid * COV_CH;
-                int lm[2];
-                for (int s = 0; s < 2; s++) {
-                    int m = 0;
-                    for (int i = 0; i < COV_CH; i++) {
-                        const int Lh = s_L[s][c0 + i];
-                        if (Lh) m = max(m, t0 + c0 + i + Lh);
-                    }
-                    lm[s] = m;
-                }
-                int inc[2] = {lm[0], lm[1]};
+#pragma unroll 1
+            for (int wd = 3; wd >= 0; wd--) {                         // 4 words of 16 positions
+                const uint32_t pw = s_pack[pidx((c0 >> 4) + wd)];
+                const uint32_t mw = s_mask[midx((c0 >> 5) + (wd >> 1))] >> ((wd & 1) * 16);
+                uint32_t l0 = 0, l1 = 0;                              // 4 L bytes per list being assembled
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int v0 = __shfl_up_sync(TG_FULL_MASK, inc[0], o);
-                    const int v1 = __shfl_up_sync(TG_FULL_MASK, inc[1], o);
-                    if (lane >= o) { inc[0] = max(inc[0], v0); inc[1] = max(inc[1], v1); }
-                }
-                if (lane == 31) { s_wmax[0][warp] = inc[0]; s_wmax[1][warp] = inc[1]; }
-                int ex[2];
-                ex[0] = __shfl_up_sync(TG_FULL_MASK, inc[0], 1);
-                ex[1] = __shfl_up_sync(TG_FULL_MASK, inc[1], 1);
-                if (lane == 0) { ex[0] = 0; ex[1] = 0; }
-                __syncthreads();
-                for (int s = 0; s < 2; s++) {
-                    int e = max(ex[s], s_carry[s]);
-                    for (int wq = 0; wq < warp; wq++) e = max(e, s_wmax[s][wq]);
-                    uint32_t cw[2] = {0u, 0u};
-                    for (int i = 0; i < COV_CH; i++) {
-                        const int p = t0 + c0 + i;
-                        const int Lh = s_L[s][c0 + i];
-                        if (Lh) e = max(e, p + Lh);
-                        if (e > p) cw[i >> 5] |= 1u << (i & 31);
+                for (int k = 15; k >= 0; k--) {
+                    const uint32_t code = (pw >> (2 * k)) & 3u;
+                    const uint32_t e = ((mw >> k) & 1u) ? 0u : (uint32_t)T.trans[state * 4 + code];
+                    state = e & 0xfffu;
+                    uint32_t ol = 0;
+                    if (e & SC_OUT_FLAG) {
+                        ol = T.out_len[state];
+                        uint32_t ob = T.out_bord[state];
+                        while (ob) {
+                            const int b = __ffs(ob) - 1;
+                            ob &= ob - 1;
+                            const int xr = c0 + wd * 16 + k;
+                            atomicOr(&s_bm[b * (COV_REGION / 32) + (xr >> 5)], 1u << (xr & 31));
+                            s_any[b] = 1;
+                        }
                     }
-                    s_cov[s][(COV_LAG + c0) / 32] = cw[0];
-                    s_cov[s][(COV_LAG + c0) / 32 + 1] = cw[1];
-                    if (MODE == MODE_COUNT) my_count[s] += __popc(cw[0]) + __popc(cw[1]);
-                }
-                __syncthreads();
-                if (tid == 0) {
-                    for (int s = 0; s < 2; s++) {
-                        int e = s_carry[s];
-                        for (int wq = 0; wq < COV_THREADS / 32; wq++) e = max(e, s_wmax[s][wq]);
-                        s_carry[s] = e;
+                    l0 = (l0 << 8) | (ol & 0xffu);                    // k descending: byte 0 ends up = lowest position
+                    l1 = (l1 << 8) | (ol >> 8);
+                    if ((k & 3) == 0) {
+                        const int xb = c0 + wd * 16 + k;
+                        *reinterpret_cast<uint32_t *>(s_L[0] + lidx(xb)) = l0;
+                        *reinterpret_cast<uint32_t *>(s_L[1] + lidx(xb)) = l1;
+                        l0 = l1 = 0;
                     }
                 }
             }
+        }
+        __syncthreads();
 
-            // ---- phase E: window counts for outputs i in [t0 - LAG, t0 + TILE - LAG) ----
-            if (MODE == MODE_DENSITY) {
-                // bit j of s_cov <-> position t0 - LAG + j
-                const int j0 = tid * COV_CH;                         // first output of this thread (bit index)
-                const int i0 = t0 - COV_LAG + j0;                    // its read position
-                if (i0 + COV_CH > 0 && i0 < n_out) {
+        // ---- phase C: greedy resolution of self-overlapping k-mers (one lane per k-mer) ----
+        if (warp == 0) {
+            for (int b = lane; b < nb; b += 32) {
+                if (!s_any[b]) continue;
+                const int blen = P.tab->bord_len[b];
+                const int grp = P.tab->bord_group[b];
+                const uint32_t *bm = s_bm + b * (COV_REGION / 32);
+                int blocked = -0x40000000;
+                bool first = true;
+                for (int wd = 0; wd < COV_REGION / 32; wd++) {
+                    uint32_t word = bm[wd];
+                    while (word) {
+                        const int bit = __ffs(word) - 1;
+                        word &= word - 1;
+                        const int xr = wd * 32 + bit;
+                        const int p = a0 + xr;
+                        if (first) {
+                            first = false;
+                            // a chain of overlapping candidates may reach back beyond the region start
+                            if (xr < blen - 1 && a0 > 0)
+                                blocked = chain_state_before(P.pack2, P.nmask, rbase, L, p, P.tab->bord_pat[b], blen);
+                        }
+                        if (p >= blocked) {
+                            blocked = p + blen;
+                            smem_byte_max(s_L[grp], lidx(xr), (uint32_t)blen);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- phase D: coverage bits = prefix max of (x + L[x]) over the region ----
+        {
+            const int c0 = tid * COV_CH;
+            uint32_t cw[2][2];
+            int lm[2];
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                int e = 0;
+                uint32_t c_lo = 0, c_hi = 0;
+#pragma unroll
+                for (int q = 0; q < COV_CH / 4; q++) {
+                    const uint32_t l4 = *reinterpret_cast<const uint32_t *>(s_L[s] + lidx(c0 + q * 4));
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int i = q * 4 + k;
+                        const int Lh = (l4 >> (8 * k)) & 0xff;
+                        e = max(e, Lh ? c0 + i + Lh : 0);
+                        const uint32_t bit = (e > c0 + i) ? 1u : 0u;
+                        if (i < 32) c_lo |= bit << i; else c_hi |= bit << (i - 32);
+                    }
+                }
+                cw[s][0] = c_lo; cw[s][1] = c_hi;
+                lm[s] = e;
+            }
+            int inc[2] = {lm[0], lm[1]};
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v0 = __shfl_up_sync(TG_FULL_MASK, inc[0], o);
+                const int v1 = __shfl_up_sync(TG_FULL_MASK, inc[1], o);
+                if (lane >= o) { inc[0] = max(inc[0], v0); inc[1] = max(inc[1], v1); }
+            }
+            if (lane == 31) { s_wmax[0][warp] = inc[0]; s_wmax[1][warp] = inc[1]; }
+            int ex[2];
+            ex[0] = __shfl_up_sync(TG_FULL_MASK, inc[0], 1);
+            ex[1] = __shfl_up_sync(TG_FULL_MASK, inc[1], 1);
+            if (lane == 0) { ex[0] = 0; ex[1] = 0; }
+            __syncthreads();
+            int cnt_here[2] = {0, 0};
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                int e = ex[s];
+                for (int wq = 0; wq < warp; wq++) e = max(e, s_wmax[s][wq]);
+                // coverage reaching in from earlier chunks: positions c0 .. e - 1
+                const int reach = min(max(e - c0, 0), COV_CH);
+                const uint64_t in = (reach >= 64) ? ~0ull : ((1ull << reach) - 1ull);
+                cw[s][0] |= (uint32_t)in;
+                cw[s][1] |= (uint32_t)(in >> 32);
+                s_cov[s][c0 / 32] = cw[s][0];
+                s_cov[s][c0 / 32 + 1] = cw[s][1];
+                if (MODE == MODE_COUNT && tid >= COV_HL / COV_CH && tid < COV_HL / COV_CH + COV_OUT_THREADS)
+                    cnt_here[s] = __popc(cw[s][0]) + __popc(cw[s][1]);
+            }
+            if (tid == 0) { s_cov[0][COV_REGION / 32] = 0u; s_cov[1][COV_REGION / 32] = 0u; }
+            if (MODE == MODE_COUNT) {
+#pragma unroll
+                for (int s = 0; s < 2; s++) {
+                    int v = cnt_here[s];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(TG_FULL_MASK, v, o);
+                    if (lane == 0) s_red[s][warp] = v;
+                }
+                __syncthreads();
+                if (tid < 2) {
+                    int v = 0;
+                    for (int wq = 0; wq < COV_THREADS / 32; wq++) v += s_red[tid][wq];
+                    if (v) atomicAdd(&P.counts[2 * r + tid], v);
+                }
+            }
+        }
+
+        // ---- phase E: window counts of the TILE_OUT outputs ----
+        if (MODE == MODE_DENSITY) {
+            __syncthreads();
+            if (tid < COV_OUT_THREADS) {
+                const int j0 = COV_HL + tid * COV_CH;                // region index of this thread's first output
+                const int i0 = t0 + tid * COV_CH;                    // its read position
+                if (i0 < padded) {
+#pragma unroll
                     for (int s = 0; s < 2; s++) {
                         const uint32_t *cv = s_cov[s];
-                        // cnt(i0) = popcount of bits [j0 + 1, j0 + w]
-                        int cnt = 0;
+                        int cnt = 0;                                 // popcount of bits [j0 + 1, j0 + w]
                         {
-                            const int lo = j0 + 1, hi = j0 + w;       // inclusive
-                            for (int wd = lo >> 5; wd <= (hi >> 5); wd++) {
+                            const int lo2 = j0 + 1, hi2 = j0 + w;
+                            for (int wd = lo2 >> 5; wd <= (hi2 >> 5); wd++) {
                                 uint32_t v = cv[wd];
-                                if (wd == (lo >> 5)) v &= 0xffffffffu << (lo & 31);
-                                if (wd == (hi >> 5)) v &= 0xffffffffu >> (31 - (hi & 31));
+                                if (wd == (lo2 >> 5)) v &= 0xffffffffu << (lo2 & 31);
+                                if (wd == (hi2 >> 5)) v &= 0xffffffffu >> (31 - (hi2 & 31));
                                 cnt += __popc(v);
                             }
                         }
+                        // leaving bits j0+1 .. j0+64 and entering bits j0+w+1 .. j0+w+64 as two 64-bit streams
+                        const int ja = j0 + 1, jb = j0 + w + 1;
+                        uint64_t sa = ((uint64_t)cv[ja >> 5] | ((uint64_t)cv[(ja >> 5) + 1] << 32)) >> (ja & 31);
+                        if (ja & 31) sa |= (uint64_t)cv[(ja >> 5) + 2] << (64 - (ja & 31));
+                        uint64_t sb = ((uint64_t)cv[jb >> 5] | ((uint64_t)cv[(jb >> 5) + 1] << 32)) >> (jb & 31);
+                        if (jb & 31) sb |= (uint64_t)cv[min((jb >> 5) + 2, COV_REGION / 32)] << (64 - (jb & 31));
                         uint32_t outw[COV_CH / 4];
 #pragma unroll
                         for (int q = 0; q < COV_CH / 4; q++) outw[q] = 0u;
 #pragma unroll
                         for (int ii = 0; ii < COV_CH; ii++) {
                             outw[ii >> 2] |= (uint32_t)cnt << ((ii & 3) * 8);
-                            const int ja = j0 + ii + 1, jb = j0 + ii + w + 1;     // leaving / entering bit
-                            cnt += (int)((cv[jb >> 5] >> (jb & 31)) & 1u) - (int)((cv[ja >> 5] >> (ja & 31)) & 1u);
+                            cnt += (int)((sb >> ii) & 1ull) - (int)((sa >> ii) & 1ull);
                         }
                         uint8_t *dst = P.cnt[s] + rbase + i0;
 #pragma unroll
-                        for (int q = 0; q < COV_CH / 16; q++) {
-                            const int ig = i0 + q * 16;
-                            if (ig >= 0 && ig < padded)
+                        for (int q = 0; q < COV_CH / 16; q++)
+                            if (i0 + q * 16 < padded)
                                 *reinterpret_cast<uint4 *>(dst + q * 16) = make_uint4(outw[q * 4], outw[q * 4 + 1], outw[q * 4 + 2], outw[q * 4 + 3]);
-                        }
                     }
                 }
-                __syncthreads();
-                // keep the last LAG positions of the coverage for the next tile
-                uint32_t keep[2] = {0u, 0u};
-                if (tid < COV_LAG / 32) { keep[0] = s_cov[0][COV_TILE / 32 + tid]; keep[1] = s_cov[1][COV_TILE / 32 + tid]; }
-                __syncthreads();
-                if (tid < COV_LAG / 32) { s_cov[0][tid] = keep[0]; s_cov[1][tid] = keep[1]; }
-            }
-        }
-
-        if (MODE == MODE_COUNT) {
-            for (int s = 0; s < 2; s++) {
-                int v = my_count[s];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(TG_FULL_MASK, v, o);
-                if (lane == 0) s_red[s][warp] = v;
-            }
-            __syncthreads();
-            if (tid < 2) {
-                int v = 0;
-                for (int wq = 0; wq < COV_THREADS / 32; wq++) v += s_red[tid][wq];
-                P.counts[2 * r + tid] = v;
             }
         }
     }
@@ -475,12 +535,12 @@ __global__ void __launch_bounds__(HIT_THREADS) hits_survivors_kernel(const HitPa
     uint32_t *s_bm = reinterpret_cast<uint32_t *>(carve(sp, (size_t)max(T.n_bord, 1) * ((HIT_TILE + HIT_HALO) / 32) * 4));
     __shared__ int s_blocked[SC_MAXBORD];
     __shared__ int s_any[SC_MAXBORD];
-    __shared__ unsigned long long s_super[SC_MAXK], s_lengt[SC_MAXLEN];
-    __shared__ int s_len[SC_MAXK];
+    __shared__ unsigned long long s_super[SC_MAXLIST], s_lengt[SC_MAXLEN];
+    __shared__ int s_len[SC_MAXLIST];
     __shared__ unsigned int s_slice;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int BMW = (HIT_TILE + HIT_HALO) / 32;     // bitmap words per bordered slot: positions [t0, t0 + TILE + 32)
-    if (tid < SC_MAXK) { s_super[tid] = P.tab->super[tid]; s_len[tid] = P.tab->len[tid]; }
+    if (tid < SC_MAXLIST) { s_super[tid] = P.tab->super[tid]; s_len[tid] = P.tab->len[tid]; }
     if (tid < SC_MAXLEN) s_lengt[tid] = P.tab->lengt[tid];
     const unsigned long long has_super = P.tab->has_super_mask;
     const unsigned long long bord_mask = P.tab->bord_mask;
@@ -691,24 +751,20 @@ static int code_of(char c)
     switch (c) { case 'A': return 0; case 'C': return 1; case 'T': return 2; case 'G': return 3; default: return -1; }
 }
 
-TG_EXPORT int tg_kmer_table_build(const char *kmers_concat, const int32_t *kmer_off, int K,
-                                  const int32_t *issub_edges, const int32_t *issub_off, void *h_table)
+// km[0 .. KA) = group 0, km[KA .. K) = group 1
+static int build_table(const std::vector<std::string> &km, int KA, const int32_t *issub_edges, const int32_t *issub_off, KmerTable *T)
 {
-    if (!kmers_concat || !kmer_off || !h_table) return tg_set_err(TG_EINVAL, "NULL argument");
-    if (K < 1 || K > SC_MAXK) return tg_set_err(TG_EINVAL, "K=%d outside 1..%d", K, SC_MAXK);
-    KmerTable *T = reinterpret_cast<KmerTable *>(h_table);
+    const int K = (int)km.size();
     memset(T, 0, sizeof(KmerTable));
-    T->K = K;
-    std::vector<std::string> km(K);
+    T->K = K; T->KA = KA; T->n_groups = (KA < K) ? 2 : 1;
     int max_len = 0;
     for (int k = 0; k < K; k++) {
-        const int l = kmer_off[k + 1] - kmer_off[k];
+        const int l = (int)km[k].size();
         if (l < 1 || l > SC_MAXLEN) return tg_set_err(TG_EINVAL, "k-mer %d has length %d outside 1..%d", k, l, SC_MAXLEN);
-        km[k].assign(kmers_concat + kmer_off[k], l);
         for (char c : km[k]) if (code_of(c) < 0) return tg_set_err(TG_EINVAL, "k-mer %d contains a non-ACGT character", k);
         T->len[k] = l;
         if (l > max_len) max_len = l;
-        for (int d = 0; d < l; d++) T->lengt[d] |= 1ull << k;
+        if (k < KA) for (int d = 0; d < l; d++) T->lengt[d] |= 1ull << k;
     }
     T->max_len = max_len;
     // bordered k-mers: some shift 0 < d < len maps the k-mer onto itself
@@ -718,35 +774,39 @@ TG_EXPORT int tg_kmer_table_build(const char *kmers_concat, const int32_t *kmer_
         for (size_t d = 1; d < s.size() && !bordered; d++) bordered = (s.compare(d, std::string::npos, s, 0, s.size() - d) == 0);
         if (bordered) {
             if (T->n_bord >= SC_MAXBORD) return tg_set_err(TG_EINVAL, "more than %d self-overlapping k-mers", SC_MAXBORD);
-            T->bord_kmer[T->n_bord] = k;
-            T->bord_len[T->n_bord] = (int)s.size();
-            T->bord_mask |= 1ull << k;
-            T->n_bord++;
+            const int b = T->n_bord++;
+            T->bord_kmer[b] = k;
+            T->bord_len[b] = (int)s.size();
+            T->bord_group[b] = (k < KA) ? 0 : 1;
+            uint64_t pat = 0;
+            for (size_t i = 0; i < s.size(); i++) pat |= (uint64_t)code_of(s[i]) << (2 * i);
+            T->bord_pat[b] = pat;
+            if (k < KA) T->bord_mask |= 1ull << k;
         }
     }
     if (issub_edges && issub_off)
-        for (int k = 0; k < K; k++) {
+        for (int k = 0; k < KA; k++) {
             for (int e = issub_off[k]; e < issub_off[k + 1]; e++) {
-                if (issub_edges[e] < 0 || issub_edges[e] >= K) return tg_set_err(TG_EINVAL, "bad KMER_ISSUBSTRING edge");
+                if (issub_edges[e] < 0 || issub_edges[e] >= KA) return tg_set_err(TG_EINVAL, "bad KMER_ISSUBSTRING edge");
                 T->super[k] |= 1ull << issub_edges[e];
             }
             if (T->super[k]) T->has_super_mask |= 1ull << k;
         }
-    // Aho-Corasick over the reversed k-mers
-    struct Node { int next[4]; int fail; uint64_t out; };
+    // Aho-Corasick over the reversed k-mers; out = set of k-mers (two 64-bit halves, one per group)
+    struct Node { int next[4]; int fail; uint64_t out[2]; };
     std::vector<Node> nodes(1);
-    nodes[0] = Node{{-1, -1, -1, -1}, 0, 0ull};
+    nodes[0] = Node{{-1, -1, -1, -1}, 0, {0ull, 0ull}};
     for (int k = 0; k < K; k++) {
         int cur = 0;
         for (int i = (int)km[k].size() - 1; i >= 0; i--) {
             const int c = code_of(km[k][i]);
             if (nodes[cur].next[c] < 0) {
                 nodes[cur].next[c] = (int)nodes.size();
-                nodes.push_back(Node{{-1, -1, -1, -1}, 0, 0ull});
+                nodes.push_back(Node{{-1, -1, -1, -1}, 0, {0ull, 0ull}});
             }
             cur = nodes[cur].next[c];
         }
-        nodes[cur].out |= 1ull << k;
+        if (k < KA) nodes[cur].out[0] |= 1ull << k; else nodes[cur].out[1] |= 1ull << (k - KA);
     }
     if ((int)nodes.size() > SC_MAXSTATES) return tg_set_err(TG_EINVAL, "automaton has %d states (max %d)", (int)nodes.size(), SC_MAXSTATES);
     std::queue<int> bfs;
@@ -757,32 +817,69 @@ TG_EXPORT int tg_kmer_table_build(const char *kmers_concat, const int32_t *kmer_
     }
     while (!bfs.empty()) {
         const int u = bfs.front(); bfs.pop();
-        nodes[u].out |= nodes[nodes[u].fail].out;
+        nodes[u].out[0] |= nodes[nodes[u].fail].out[0];
+        nodes[u].out[1] |= nodes[nodes[u].fail].out[1];
         for (int c = 0; c < 4; c++) {
             const int v = nodes[u].next[c];
             if (v < 0) nodes[u].next[c] = nodes[nodes[u].fail].next[c];
             else { nodes[v].fail = nodes[nodes[u].fail].next[c]; bfs.push(v); }
         }
     }
-    // BFS order guarantees fail(u) was finalised before u, but out of children was merged when popped: recompute in order
     T->n_states = (int)nodes.size();
     for (int s = 0; s < T->n_states; s++) {
-        T->out_mask[s] = nodes[s].out;
-        int best = 0; uint32_t ob = 0;
-        for (int k = 0; k < K; k++)
-            if ((nodes[s].out >> k) & 1ull) {
-                if ((T->bord_mask >> k) & 1ull) { for (int b = 0; b < T->n_bord; b++) if (T->bord_kmer[b] == k) ob |= 1u << b; }
-                else if (T->len[k] > best) best = T->len[k];
-            }
-        T->out_len[s] = (uint8_t)best;
+        T->out_mask[s] = nodes[s].out[0];
+        int best[2] = {0, 0};
+        uint32_t ob = 0;
+        for (int k = 0; k < K; k++) {
+            const int grp = (k < KA) ? 0 : 1;
+            if (!((nodes[s].out[grp] >> (grp ? k - KA : k)) & 1ull)) continue;
+            bool is_bord = false;
+            for (int b = 0; b < T->n_bord; b++) if (T->bord_kmer[b] == k) { ob |= 1u << b; is_bord = true; }
+            if (!is_bord && T->len[k] > best[grp]) best[grp] = T->len[k];
+        }
+        T->out_len[s] = (uint16_t)(best[0] | (best[1] << 8));
         T->out_bord[s] = ob;
     }
     for (int s = 0; s < T->n_states; s++)
         for (int c = 0; c < 4; c++) {
             const int v = nodes[s].next[c];
-            T->trans[s * 4 + c] = (uint16_t)(v | (nodes[v].out ? SC_OUT_FLAG : 0));
+            T->trans[s * 4 + c] = (uint16_t)(v | ((nodes[v].out[0] | nodes[v].out[1]) ? SC_OUT_FLAG : 0));
         }
     return TG_OK;
+}
+
+static int collect_kmers(const char *concat, const int32_t *off, int K, std::vector<std::string> &km)
+{
+    if (!concat || !off) return tg_set_err(TG_EINVAL, "NULL argument");
+    if (K < 1 || K > SC_MAXLIST) return tg_set_err(TG_EINVAL, "K=%d outside 1..%d", K, SC_MAXLIST);
+    for (int k = 0; k < K; k++) {
+        const int l = off[k + 1] - off[k];
+        if (l < 1 || l > SC_MAXLEN) return tg_set_err(TG_EINVAL, "k-mer %d has length %d outside 1..%d", k, l, SC_MAXLEN);
+        km.emplace_back(concat + off[k], (size_t)l);
+    }
+    return TG_OK;
+}
+
+TG_EXPORT int tg_kmer_table_build(const char *kmers_concat, const int32_t *kmer_off, int K,
+                                  const int32_t *issub_edges, const int32_t *issub_off, void *h_table)
+{
+    if (!h_table) return tg_set_err(TG_EINVAL, "NULL argument");
+    std::vector<std::string> km;
+    int rc = collect_kmers(kmers_concat, kmer_off, K, km);
+    if (rc != TG_OK) return rc;
+    return build_table(km, K, issub_edges, issub_off, reinterpret_cast<KmerTable *>(h_table));
+}
+
+TG_EXPORT int tg_kmer_table_build_pair(const char *kmers_a, const int32_t *off_a, int KA,
+                                       const char *kmers_b, const int32_t *off_b, int KB, void *h_table)
+{
+    if (!h_table) return tg_set_err(TG_EINVAL, "NULL argument");
+    std::vector<std::string> km;
+    int rc = collect_kmers(kmers_a, off_a, KA, km);
+    if (rc != TG_OK) return rc;
+    rc = collect_kmers(kmers_b, off_b, KB, km);
+    if (rc != TG_OK) return rc;
+    return build_table(km, KA, nullptr, nullptr, reinterpret_cast<KmerTable *>(h_table));
 }
 
 // ================================================================================================
@@ -812,7 +909,7 @@ static int table_dims(const void *d_table, int *n_states, int *n_bord, cudaStrea
 static size_t table_smem(int n_states, bool want_mask)
 {
     auto up = [](size_t b) { return (b + 15) & ~(size_t)15; };
-    return up((size_t)n_states * 8) + up(n_states) + up((size_t)n_states * 4) + (want_mask ? up((size_t)n_states * 8) : 0);
+    return up((size_t)n_states * 8) + up((size_t)n_states * 2) + up((size_t)n_states * 4) + (want_mask ? up((size_t)n_states * 8) : 0);
 }
 
 TG_EXPORT int tg_scan_pack(const uint8_t *d_ascii, const int64_t *d_base_off, const int32_t *d_len, int n_reads,
@@ -855,57 +952,61 @@ static int get_counter(unsigned int **out, cudaStream_t st)
     return TG_OK;
 }
 
+TG_EXPORT int tg_scan_tile_bases(void) { return COV_TILE_OUT; }
+
 template <int MODE>
 static int launch_cov(const uint32_t *d_pack2, const uint32_t *d_nmask, const int64_t *d_base_off, const int32_t *d_len,
-                      int n_reads, const void *ta, const void *tb, int window, uint8_t *ca, uint8_t *cb, int32_t *counts, void *stream)
+                      int n_reads, const int64_t *d_tile_off, int64_t n_tiles, const void *table, int window,
+                      uint8_t *ca, uint8_t *cb, int32_t *counts, void *stream)
 {
-    if (n_reads <= 0) return TG_OK;
-    if (!d_pack2 || !d_nmask || !d_base_off || !d_len || !ta || !tb) return tg_set_err(TG_EINVAL, "NULL device pointer");
+    if (n_reads <= 0 || n_tiles <= 0) return TG_OK;
+    if (!d_pack2 || !d_nmask || !d_base_off || !d_len || !d_tile_off || !table) return tg_set_err(TG_EINVAL, "NULL device pointer");
     const int sms = tg_sm_count();
     if (sms <= 0) return tg_set_err(TG_ECUDA, "no CUDA device");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    int ns[2], nb[2];
-    int rc = table_dims(ta, &ns[0], &nb[0], st);
-    if (rc != TG_OK) return rc;
-    rc = table_dims(tb, &ns[1], &nb[1], st);
+    int ns, nb;
+    int rc = table_dims(table, &ns, &nb, st);
     if (rc != TG_OK) return rc;
     auto up = [](size_t b) { return (b + 15) & ~(size_t)15; };
-    size_t smem = table_smem(ns[0], false) + table_smem(ns[1], false) + up(COV_STAGE / 16 * 4) + up(COV_STAGE / 32 * 4);
-    for (int s = 0; s < 2; s++)
-        smem += up(COV_TILE) + up((COV_LAG + COV_TILE) / 32 * 4) + up((size_t)(nb[s] > 1 ? nb[s] : 1) * (COV_TILE / 32) * 4);
+    size_t smem = table_smem(ns, false) + up((size_t)(COV_STAGE / 16 + 1 + (COV_STAGE / 16 + 1) / 32) * 4 + 16) +
+                  up((size_t)(COV_STAGE / 32 + 1 + (COV_STAGE / 32 + 1) / 32) * 4 + 16) +
+                  2 * (up(COV_REGION + COV_REGION / 16) + up((COV_REGION / 32 + 1) * 4)) +
+                  up((size_t)(nb > 1 ? nb : 1) * (COV_REGION / 32) * 4);
     if (smem > 200 * 1024) return tg_set_err(TG_ERANGE, "k-mer tables too large for shared memory (%zu bytes)", smem);
     CovParams P;
     P.pack2 = d_pack2; P.nmask = d_nmask; P.base_off = d_base_off; P.len = d_len; P.n_reads = n_reads;
-    P.tab[0] = reinterpret_cast<const KmerTable *>(ta); P.tab[1] = reinterpret_cast<const KmerTable *>(tb);
+    P.tile_off = d_tile_off; P.n_tiles = n_tiles;
+    P.tab = reinterpret_cast<const KmerTable *>(table);
     P.window = window; P.cnt[0] = ca; P.cnt[1] = cb; P.counts = counts;
-    rc = get_counter(&P.next_read, st);
-    if (rc != TG_OK) return rc;
     TG_CUDA_CHECK(cudaFuncSetAttribute(scan_cov_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = (int)((220 * 1024) / (smem + 2048));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;
-    int grid = sms * per_sm;
-    if (grid > n_reads) grid = n_reads;
-    scan_cov_kernel<MODE><<<grid, COV_THREADS, smem, st>>>(P);
+    long long grid = (long long)sms * per_sm;
+    if (grid > n_tiles) grid = n_tiles;
+    scan_cov_kernel<MODE><<<(int)grid, COV_THREADS, smem, st>>>(P);
     TG_CUDA_CHECK(cudaGetLastError());
     return TG_OK;
 }
 
 TG_EXPORT int tg_scan_basecount(const uint32_t *d_pack2, const uint32_t *d_nmask, const int64_t *d_base_off,
-                                const int32_t *d_len, int n_reads, const void *d_table_a, const void *d_table_b,
-                                int32_t *d_counts, void *stream)
+                                const int32_t *d_len, int n_reads, const int64_t *d_tile_off, int64_t n_tiles,
+                                const void *d_table_pair, int32_t *d_counts, void *stream)
 {
     if (!d_counts) return tg_set_err(TG_EINVAL, "d_counts is NULL");
-    return launch_cov<MODE_COUNT>(d_pack2, d_nmask, d_base_off, d_len, n_reads, d_table_a, d_table_b, 0, nullptr, nullptr, d_counts, stream);
+    if (n_reads > 0) TG_CUDA_CHECK(cudaMemsetAsync(d_counts, 0, sizeof(int32_t) * 2 * (size_t)n_reads, reinterpret_cast<cudaStream_t>(stream)));
+    return launch_cov<MODE_COUNT>(d_pack2, d_nmask, d_base_off, d_len, n_reads, d_tile_off, n_tiles, d_table_pair, 0, nullptr, nullptr,
+                                  d_counts, stream);
 }
 
 TG_EXPORT int tg_scan_density(const uint32_t *d_pack2, const uint32_t *d_nmask, const int64_t *d_base_off,
-                              const int32_t *d_len, int n_reads, const void *d_table_a, const void *d_table_b,
-                              int window, uint8_t *d_cnt_a, uint8_t *d_cnt_b, void *stream)
+                              const int32_t *d_len, int n_reads, const int64_t *d_tile_off, int64_t n_tiles,
+                              const void *d_table_pair, int window, uint8_t *d_cnt_a, uint8_t *d_cnt_b, void *stream)
 {
     if (window < 1 || window > 255) return tg_set_err(TG_ERANGE, "window %d outside 1..255 (uint8 counts)", window);
     if (!d_cnt_a || !d_cnt_b) return tg_set_err(TG_EINVAL, "output pointer is NULL");
-    return launch_cov<MODE_DENSITY>(d_pack2, d_nmask, d_base_off, d_len, n_reads, d_table_a, d_table_b, window, d_cnt_a, d_cnt_b, nullptr, stream);
+    return launch_cov<MODE_DENSITY>(d_pack2, d_nmask, d_base_off, d_len, n_reads, d_tile_off, n_tiles, d_table_pair, window,
+                                    d_cnt_a, d_cnt_b, nullptr, stream);
 }
 
 TG_EXPORT size_t tg_scan_hits_work_bytes(int64_t total_work_bases, int n_slices)

@@ -95,6 +95,14 @@ class Scoring:
         codes = lut[raw]
         if (codes == 255).any():
             raise ValueError('sequence contains letters not in the alphabet')
+        # keep only the letters that occur: the wave kernel's shared-memory profile has one row per letter, so a
+        # smaller alphabet means more resident warps
+        present = np.unique(codes)
+        if len(present) < A:
+            remap = np.zeros(256, dtype=np.uint8)
+            remap[present] = np.arange(len(present), dtype=np.uint8)
+            codes = remap[codes]
+            sub = np.ascontiguousarray(sub[np.ix_(present, present)])
         return np.ascontiguousarray(codes), off, sub
 
     def c_struct(self, sub):

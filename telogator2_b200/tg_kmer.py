@@ -94,6 +94,31 @@ def kmer_table(kmer_list, issub=None):
     return t
 
 
+def kmer_table_pair(list_a, list_b):
+    """Device blob of ONE automaton for two k-mer lists (coverage kernels: one lookup per base for both)."""
+    torch = _lib.require_cuda()
+    L = _lib.load()
+    key = ('pair', tuple(list_a), tuple(list_b), torch.cuda.current_device())
+    t = _table_cache.get(key)
+    if t is not None:
+        return t
+    blobs, offs = [], []
+    for lst in (list_a, list_b):
+        if len(lst) < 1 or len(lst) > MAX_KMERS:
+            raise NotImplementedError(f'{len(lst)} k-mers: the GPU scan supports 1..{MAX_KMERS} per list')
+        blobs.append(''.join(lst).encode('ascii'))
+        off = np.zeros(len(lst) + 1, dtype=np.int32)
+        off[1:] = np.cumsum([len(k) for k in lst])
+        offs.append(off)
+    host = np.zeros(L.tg_kmer_table_bytes(), dtype=np.uint8)
+    _lib.check(L.tg_kmer_table_build_pair(blobs[0], offs[0].ctypes.data_as(C.c_void_p), len(list_a),
+                                          blobs[1], offs[1].ctypes.data_as(C.c_void_p), len(list_b),
+                                          host.ctypes.data_as(C.c_void_p)))
+    t = torch.from_numpy(host).cuda()
+    _table_cache[key] = t
+    return t
+
+
 # ------------------------------------------------------------------------------------------------
 # reads in HBM
 # ------------------------------------------------------------------------------------------------
@@ -129,8 +154,9 @@ class PackedReads:
         self.d_ascii = ascii_h.cuda(non_blocking=True)
         self.d_base_off = torch.from_numpy(self.base_off).cuda()
         self.d_len = torch.from_numpy(self.lens).cuda()
-        self.d_pack2 = torch.empty(max(total // 16, 4), dtype=torch.int32, device='cuda')
-        self.d_nmask = torch.empty(max(total // 32, 4), dtype=torch.int32, device='cuda')
+        self.d_pack2 = torch.zeros(total // 16 + 8, dtype=torch.int32, device='cuda')
+        self.d_nmask = torch.zeros(total // 32 + 8, dtype=torch.int32, device='cuda')
+        self._tile_cache = {}
         if self.n and total:
             _lib.check(L.tg_scan_pack(_lib.dptr(self.d_ascii), _lib.dptr(self.d_base_off), _lib.dptr(self.d_len), self.n,
                                       _lib.dptr(self.d_pack2), _lib.dptr(self.d_nmask), _lib.stream_ptr(torch)))
@@ -147,14 +173,27 @@ class PackedReads:
             seg = self._ascii_host[o:o + self.lens[i]]
             raise KeyError(chr(int(seg[np.argmax(~_ACGTN[seg])])))
 
+    def _tiles(self, window):
+        """device prefix sum of coverage tiles per read (window = 0: base count, else density outputs)."""
+        t = self._tile_cache.get(window)
+        if t is None:
+            tb = self.L.tg_scan_tile_bases()
+            items = np.maximum(self.lens.astype(np.int64) - window, 0)
+            off = np.zeros(self.n + 1, dtype=np.int64)
+            off[1:] = np.cumsum((items + tb - 1) // tb)
+            t = (self.torch.from_numpy(off).cuda(), int(off[-1]))
+            self._tile_cache[window] = t
+        return t
+
     def basecount(self, list_a, list_b):
         """int32 [n, 2]: get_telomere_base_count for two k-mer lists (tg_kmer.py:93-102)."""
         torch = self.torch
         out = torch.zeros((max(self.n, 1), 2), dtype=torch.int32, device='cuda')
-        if self.n:
+        d_toff, n_tiles = self._tiles(0)
+        if self.n and n_tiles:
             _lib.check(self.L.tg_scan_basecount(_lib.dptr(self.d_pack2), _lib.dptr(self.d_nmask), _lib.dptr(self.d_base_off),
-                                                _lib.dptr(self.d_len), self.n, _lib.dptr(kmer_table(list_a)),
-                                                _lib.dptr(kmer_table(list_b)), _lib.dptr(out), _lib.stream_ptr(torch)))
+                                                _lib.dptr(self.d_len), self.n, _lib.dptr(d_toff), n_tiles,
+                                                _lib.dptr(kmer_table_pair(list_a, list_b)), _lib.dptr(out), _lib.stream_ptr(torch)))
         return out[:self.n]
 
     def orient(self, flip):
@@ -176,10 +215,11 @@ class PackedReads:
         torch = self.torch
         ca = torch.zeros(max(self.total, 16), dtype=torch.uint8, device='cuda')
         cb = torch.zeros(max(self.total, 16), dtype=torch.uint8, device='cuda')
-        if self.n and self.total:
+        d_toff, n_tiles = self._tiles(int(window))
+        if self.n and self.total and n_tiles:
             _lib.check(self.L.tg_scan_density(_lib.dptr(self.d_pack2), _lib.dptr(self.d_nmask), _lib.dptr(self.d_base_off),
-                                              _lib.dptr(self.d_len), self.n, _lib.dptr(kmer_table(list_a)),
-                                              _lib.dptr(kmer_table(list_b)), int(window), _lib.dptr(ca), _lib.dptr(cb),
+                                              _lib.dptr(self.d_len), self.n, _lib.dptr(d_toff), n_tiles,
+                                              _lib.dptr(kmer_table_pair(list_a, list_b)), int(window), _lib.dptr(ca), _lib.dptr(cb),
                                               _lib.stream_ptr(torch)))
         return ca, cb
 
