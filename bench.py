@@ -252,13 +252,26 @@ def main():
     orig_planes = (pr.d_pack2, pr.d_nmask)
     sl_hi = lens.copy()
 
-    def scan_step():
+    scan_ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+    scan_parts = {'basecount': [], 'orient': [], 'density': [], 'hits': []}
+
+    def scan_step(record=False):
         pr.d_pack2, pr.d_nmask = orig_planes
+        scan_ev[0].record()
         bc = pr.basecount(CANON, CR)                               # tg_tel.py:262-263
+        scan_ev[1].record()
         flip = (bc[:, 0] > bc[:, 1]).cpu().numpy()
+        scan_ev[2].record()
         pr.orient(flip)                                            # tg_tel.py:265-266
+        scan_ev[3].record()
         ca, cb = pr.density_counts(KL, KLR, 100)                   # tg_tel.py:160-161
+        scan_ev[4].record()
         spans = pr.hits_device(sl_idx, sl_lo, sl_hi, KLR, ISSUB)   # tg_tel.py:310 on the last 6000 bases
+        scan_ev[5].record()
+        if record:
+            torch.cuda.synchronize()
+            for name, a, b in (('basecount', 0, 1), ('orient', 2, 3), ('density', 3, 4), ('hits', 4, 5)):
+                scan_parts[name].append(scan_ev[a].elapsed_time(scan_ev[b]))
         return flip, ca, cb, spans
 
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -279,7 +292,7 @@ def main():
         cells_step = eng.stats['cells']
         launches_dp = eng.stats['launches']
         ev[2].record()
-        scan_step()
+        scan_step(record=timed)
         ev[3].record()
         barrier()
         if timed:
@@ -400,7 +413,8 @@ def main():
                         'ms_per_step': e2e_t * 1e3},
                 'gpu_launches': int(launches_dp + 4),
                 'scan': {'value': scan_mbs, 'unit': 'Mbases/s', 'ms_per_step': scan_t * 1e3,
-                         'what': 'basecount x2 + orient + density x2 + hits on the last 6000 bases of every read (device resident)'},
+                         'what': 'basecount x2 + orient + density x2 + hits on the last 6000 bases of every read (device resident)',
+                         'parts_ms': {k: float(np.mean(v)) for k, v in scan_parts.items() if v}},
                 'roofline': roof, 'roofline_scan': roof_scan, 'cpu_baseline': cpu, 'clocks': clocks,
                 'wall_s_timed_region': t_wall}
         print(json.dumps(line))

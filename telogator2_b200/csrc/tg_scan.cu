@@ -252,7 +252,7 @@ __device__ int chain_state_before(const uint32_t *pack2, const uint32_t *nmask, 
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(COV_THREADS) scan_cov_kernel(const CovParams P)
+__global__ void __launch_bounds__(COV_THREADS, 5) scan_cov_kernel(const CovParams P)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *sp = smem;
@@ -350,21 +350,26 @@ __global__ void __launch_bounds__(COV_THREADS) scan_cov_kernel(const CovParams P
         }
         __syncthreads();
 
-        // ---- phase C: greedy resolution of self-overlapping k-mers (one lane per k-mer) ----
-        if (warp == 0) {
-            for (int b = lane; b < nb; b += 32) {
-                if (!s_any[b]) continue;
-                const int blen = P.tab->bord_len[b];
-                const int grp = P.tab->bord_group[b];
-                const uint32_t *bm = s_bm + b * (COV_REGION / 32);
-                int blocked = -0x40000000;
-                bool first = true;
-                for (int wd = 0; wd < COV_REGION / 32; wd++) {
-                    uint32_t word = bm[wd];
+        // ---- phase C: greedy resolution of self-overlapping k-mers: one warp per k-mer, the warp finds the
+        //      non-empty bitmap words together and walks their bits in order (all lanes redundantly) ----
+        for (int b = warp; b < nb; b += COV_THREADS / 32) {
+            if (!s_any[b]) continue;
+            const int blen = P.tab->bord_len[b];
+            const int grp = P.tab->bord_group[b];
+            const uint32_t *bm = s_bm + b * (COV_REGION / 32);
+            int blocked = -0x40000000;
+            bool first = true;
+            for (int ch = 0; ch < COV_REGION / 32; ch += 32) {
+                const uint32_t mine = bm[ch + lane];
+                uint32_t nz = __ballot_sync(TG_FULL_MASK, mine != 0u);
+                while (nz) {
+                    const int l = __ffs(nz) - 1;
+                    nz &= nz - 1;
+                    uint32_t word = __shfl_sync(TG_FULL_MASK, mine, l);
                     while (word) {
                         const int bit = __ffs(word) - 1;
                         word &= word - 1;
-                        const int xr = wd * 32 + bit;
+                        const int xr = (ch + l) * 32 + bit;
                         const int p = a0 + xr;
                         if (first) {
                             first = false;
@@ -374,7 +379,7 @@ __global__ void __launch_bounds__(COV_THREADS) scan_cov_kernel(const CovParams P
                         }
                         if (p >= blocked) {
                             blocked = p + blen;
-                            smem_byte_max(s_L[grp], lidx(xr), (uint32_t)blen);
+                            if (lane == 0) smem_byte_max(s_L[grp], lidx(xr), (uint32_t)blen);
                         }
                     }
                 }
@@ -531,7 +536,7 @@ __global__ void __launch_bounds__(HIT_THREADS) hits_survivors_kernel(const HitPa
     uint32_t *s_pack = reinterpret_cast<uint32_t *>(carve(sp, HIT_STAGE / 16 * 4));
     uint32_t *s_mask = reinterpret_cast<uint32_t *>(carve(sp, HIT_STAGE / 32 * 4));
     unsigned long long *s_hm = reinterpret_cast<unsigned long long *>(carve(sp, (size_t)HIT_SPAN * 8));   // index = x - t0 + HALO
-    unsigned long long *s_C = reinterpret_cast<unsigned long long *>(carve(sp, (size_t)HIT_SPAN * 8));
+    uint32_t *s_sup = reinterpret_cast<uint32_t *>(carve(sp, (size_t)(HIT_SPAN / 32 + 1) * 4));             // hm has a superstring k-mer
     uint32_t *s_bm = reinterpret_cast<uint32_t *>(carve(sp, (size_t)max(T.n_bord, 1) * ((HIT_TILE + HIT_HALO) / 32) * 4));
     __shared__ int s_blocked[SC_MAXBORD];
     __shared__ int s_any[SC_MAXBORD];
@@ -543,8 +548,10 @@ __global__ void __launch_bounds__(HIT_THREADS) hits_survivors_kernel(const HitPa
     if (tid < SC_MAXLIST) { s_super[tid] = P.tab->super[tid]; s_len[tid] = P.tab->len[tid]; }
     if (tid < SC_MAXLEN) s_lengt[tid] = P.tab->lengt[tid];
     const unsigned long long has_super = P.tab->has_super_mask;
-    const unsigned long long bord_mask = P.tab->bord_mask;
     const int max_len = T.max_len;
+    __syncthreads();
+    unsigned long long m_sup = 0ull;                     // k-mers that are a superstring of some other k-mer
+    for (int k = 0; k < SC_MAXLIST; k++) m_sup |= s_super[k];
 
     for (;;) {
         __syncthreads();
@@ -556,7 +563,7 @@ __global__ void __launch_bounds__(HIT_THREADS) hits_survivors_kernel(const HitPa
         const int lo = P.slice_lo[q], hi = P.slice_hi[q];
         const int len = hi - lo;
         const int64_t rbase = P.base_off[r];
-        const int64_t padded = P.base_off[r + 1] - rbase;
+        const int64_t gbase = rbase + lo;                        // absolute base index of slice position 0
         const int64_t woff = P.work_off[q];
         const int wlen = (int)(P.work_off[q + 1] - woff);        // padded to 64
         const int n_tiles = (wlen + HIT_TILE - 1) / HIT_TILE;
@@ -566,20 +573,22 @@ __global__ void __launch_bounds__(HIT_THREADS) hits_survivors_kernel(const HitPa
         for (int tile = 0; tile < n_tiles; tile++) {
             const int t0 = tile * HIT_TILE;                     // slice-relative
             __syncthreads();
-            // stage slice positions [t0, t0 + STAGE): read positions lo + t0 ...; lo may be unaligned -> stage per base
-            // (slices are short; simplicity over speed): build aligned words from the read's packed planes
+            // stage slice positions [t0, t0 + STAGE): unaligned window of the read's packed planes, clipped to the slice
             for (int wq = tid; wq < HIT_STAGE / 32; wq += HIT_THREADS) {
-                uint32_t m = 0u, a = 0u, b = 0u;
-                for (int i = 0; i < 32; i++) {
-                    const int x = t0 + wq * 32 + i;             // slice-relative
-                    const int64_t rp = (int64_t)lo + x;         // read-relative
-                    uint32_t isn = 1u, code = 0u;
-                    if (x < len && rp < padded) {
-                        isn = base_isn(P.nmask, rbase + rp);
-                        code = isn ? 0u : base_code(P.pack2, rbase + rp);
-                    }
-                    m |= isn << i;
-                    if (i < 16) a |= code << (i * 2); else b |= code << ((i - 16) * 2);
+                const int x0 = t0 + wq * 32;
+                uint32_t m = 0xffffffffu, a = 0u, b = 0u;
+                if (x0 < len) {
+                    const int64_t g = gbase + x0;
+                    const int64_t mw = g >> 5;
+                    const int msh = (int)(g & 31);
+                    const uint64_t mm = (uint64_t)P.nmask[mw] | ((uint64_t)P.nmask[mw + 1] << 32);
+                    m = (uint32_t)(mm >> msh);
+                    const int64_t pw = g >> 4;
+                    const int sh = (int)(g & 15) * 2;
+                    const uint32_t w0 = P.pack2[pw], w1 = P.pack2[pw + 1], w2 = P.pack2[pw + 2];
+                    a = sh ? ((w0 >> sh) | (w1 << (32 - sh))) : w0;
+                    b = sh ? ((w1 >> sh) | (w2 << (32 - sh))) : w1;
+                    if (x0 + 32 > len) m |= ~((1u << (len - x0)) - 1u);
                 }
                 s_mask[wq] = m; s_pack[wq * 2] = a; s_pack[wq * 2 + 1] = b;
             }
@@ -588,84 +597,100 @@ __global__ void __launch_bounds__(HIT_THREADS) hits_survivors_kernel(const HitPa
             __syncthreads();
 
             // ---- automaton over [t0, t0 + TILE + HALO): hm = all k-mers starting at x ----
-            {
-                // TILE + HALO positions over 128 threads: 16 each + the first 2 warps... keep it simple:
-                // thread t handles [c0, c0 + HIT_CH); threads < HALO / HIT_CH additionally handle the halo chunk
-                for (int pass = 0; pass < 2; pass++) {
-                    int c0;
-                    if (pass == 0) c0 = tid * HIT_CH;
-                    else { if (tid >= HIT_HALO / HIT_CH) break; c0 = HIT_TILE + tid * HIT_CH; }
-                    uint32_t state = 0;
-                    for (int x = c0 + HIT_CH + max_len - 2; x >= c0; x--) {
-                        uint32_t e = 0u;
-                        if (x < HIT_STAGE) {
-                            const uint32_t isn = (s_mask[x >> 5] >> (x & 31)) & 1u;
-                            const uint32_t code = (s_pack[x >> 4] >> ((x & 15) * 2)) & 3u;
-                            e = isn ? 0u : (uint32_t)T.trans[state * 4 + code];
-                        }
-                        state = e & 0xfffu;
-                        if (x < c0 + HIT_CH) {
-                            unsigned long long hm = 0ull;
-                            if (e & SC_OUT_FLAG) {
-                                hm = T.out_mask[state];
-                                uint32_t ob = T.out_bord[state];
-                                while (ob) {
-                                    const int b = __ffs(ob) - 1;
-                                    ob &= ob - 1;
-                                    atomicOr(&s_bm[b * BMW + (x >> 5)], 1u << (x & 31));
-                                    s_any[b] = 1;
-                                }
+            for (int pass = 0; pass < 2; pass++) {
+                int c0;
+                if (pass == 0) c0 = tid * HIT_CH;
+                else { if (tid >= HIT_HALO / HIT_CH) break; c0 = HIT_TILE + tid * HIT_CH; }
+                uint32_t state = 0;
+                for (int x = c0 + HIT_CH + max_len - 2; x >= c0; x--) {
+                    uint32_t e = 0u;
+                    if (x < HIT_STAGE) {
+                        const uint32_t isn = (s_mask[x >> 5] >> (x & 31)) & 1u;
+                        const uint32_t code = (s_pack[x >> 4] >> ((x & 15) * 2)) & 3u;
+                        e = isn ? 0u : (uint32_t)T.trans[state * 4 + code];
+                    }
+                    state = e & 0xfffu;
+                    if (x < c0 + HIT_CH) {
+                        unsigned long long hm = 0ull;
+                        if (e & SC_OUT_FLAG) {
+                            hm = T.out_mask[state];
+                            uint32_t ob = T.out_bord[state];
+                            while (ob) {
+                                const int b = __ffs(ob) - 1;
+                                ob &= ob - 1;
+                                atomicOr(&s_bm[b * BMW + (x >> 5)], 1u << (x & 31));
+                                s_any[b] = 1;
                             }
-                            s_hm[HIT_HALO + x] = hm;
                         }
+                        s_hm[HIT_HALO + x] = hm;
                     }
                 }
             }
             __syncthreads();
 
-            // ---- greedy resolution of bordered k-mers; unselected candidates are cleared from hm ----
-            if (warp == 0) {
-                for (int b = lane; b < T.n_bord; b += 32) {
-                    if (!s_any[b]) continue;
-                    const int blen = P.tab->bord_len[b];
-                    const unsigned long long kbit = 1ull << P.tab->bord_kmer[b];
-                    int blocked = s_blocked[b];
-                    int carry = -1;
-                    for (int wd = 0; wd < BMW; wd++) {
-                        uint32_t word = s_bm[b * BMW + wd];
-                        if (wd == HIT_TILE / 32 && carry < 0) carry = blocked;      // state at the tile boundary
+            // ---- greedy resolution of bordered k-mers (one warp per k-mer); unselected candidates leave hm ----
+            for (int b = warp; b < T.n_bord; b += HIT_THREADS / 32) {
+                if (!s_any[b]) continue;
+                const int blen = P.tab->bord_len[b];
+                const unsigned long long kbit = 1ull << P.tab->bord_kmer[b];
+                int blocked = s_blocked[b];
+                int carry = -1;
+                for (int ch = 0; ch < BMW; ch += 32) {
+                    const uint32_t mine = (ch + lane < BMW) ? s_bm[b * BMW + ch + lane] : 0u;
+                    uint32_t nz = __ballot_sync(TG_FULL_MASK, mine != 0u);
+                    while (nz) {
+                        const int l = __ffs(nz) - 1;
+                        nz &= nz - 1;
+                        const int wd = ch + l;
+                        if (wd >= HIT_TILE / 32 && carry < 0) carry = blocked;       // state at the tile boundary
+                        uint32_t word = __shfl_sync(TG_FULL_MASK, mine, l);
                         while (word) {
                             const int bit = __ffs(word) - 1;
                             word &= word - 1;
                             const int x = wd * 32 + bit;
                             const int p = t0 + x;
                             if (p >= blocked) blocked = p + blen;
-                            else atomicAnd(&s_hm[HIT_HALO + x], ~kbit);
+                            else if (lane == 0) atomicAnd(&s_hm[HIT_HALO + x], ~kbit);
                         }
                     }
-                    s_blocked[b] = carry < 0 ? blocked : carry;
                 }
+                __syncwarp();
+                if (lane == 0) s_blocked[b] = carry < 0 ? blocked : carry;
             }
             __syncthreads();
 
-            // ---- C[y] = k-mers whose selected matches cover y, y in [t0, t0 + TILE + HALO) ----
-            for (int y = tid; y < HIT_TILE + HIT_HALO; y += HIT_THREADS) {
-                unsigned long long c = 0ull;
-                for (int d = 0; d < max_len; d++) c |= s_hm[HIT_HALO + y - d] & s_lengt[d];
-                s_C[HIT_HALO + y] = c;
+            // ---- bitmap of positions whose selected matches include a superstring k-mer ----
+            for (int i = tid; i < HIT_SPAN; i += HIT_THREADS) {
+                const uint32_t bal = __ballot_sync(TG_FULL_MASK, (s_hm[i] & m_sup) != 0ull);
+                if (lane == 0) s_sup[i >> 5] = bal;
             }
+            if (tid == 0) s_sup[HIT_SPAN / 32] = 0u;
             __syncthreads();
 
-            // ---- survivors: drop (k, x) if a superstring k-mer covers any of [x, x + len_k) ----
+            // ---- survivors: drop (k, x) if a selected match of a superstring k-mer overlaps [x, x + len_k) ----
             for (int x = tid; x < HIT_TILE; x += HIT_THREADS) {
                 unsigned long long hm = s_hm[HIT_HALO + x];
                 unsigned long long cand = hm & has_super;
                 while (cand) {
                     const int k = __ffsll((long long)cand) - 1;
                     cand &= cand - 1;
-                    unsigned long long cover = 0ull;
                     const int lk = s_len[k];
-                    for (int y = x; y < x + lk; y++) cover |= s_C[HIT_HALO + y];
+                    // candidates s' in [x - max_len + 1, x + lk - 1] (indices shifted by HALO)
+                    const int ib = HIT_HALO + x - max_len + 1, ie = HIT_HALO + x + lk - 1;     // inclusive
+                    unsigned long long cover = 0ull;
+                    for (int wd = ib >> 5; wd <= (ie >> 5); wd++) {
+                        uint32_t v = s_sup[wd];
+                        if (wd == (ib >> 5)) v &= 0xffffffffu << (ib & 31);
+                        if (wd == (ie >> 5)) v &= 0xffffffffu >> (31 - (ie & 31));
+                        while (v) {
+                            const int i = wd * 32 + __ffs(v) - 1;
+                            v &= v - 1;
+                            const int d = HIT_HALO + x - i;                                    // x - s'
+                            unsigned long long m = s_hm[i];
+                            if (d > 0) m &= s_lengt[d];                                        // must reach position x
+                            cover |= m;
+                        }
+                    }
                     if (cover & s_super[k]) hm &= ~(1ull << k);
                 }
                 if (t0 + x < wlen) P.S[woff + t0 + x] = hm;
@@ -678,7 +703,6 @@ __global__ void __launch_bounds__(HIT_THREADS) hits_survivors_kernel(const HitPa
             if (tid < HIT_HALO) s_hm[tid] = keep;
         }
     }
-    (void)bord_mask;
 }
 
 // H2: block starts after collapsing abutting same-k-mer survivors (tg_kmer.py:206-212)
@@ -1034,8 +1058,8 @@ TG_EXPORT int tg_scan_hits(const uint32_t *d_pack2, const uint32_t *d_nmask, con
     int rc = table_dims(d_table, &ns, &nb, st);
     if (rc != TG_OK) return rc;
     auto up = [](size_t b) { return (b + 15) & ~(size_t)15; };
-    const size_t smem = table_smem(ns, true) + up(HIT_STAGE / 16 * 4) + up(HIT_STAGE / 32 * 4) + 2 * up((size_t)HIT_SPAN * 8) +
-                        up((size_t)(nb > 1 ? nb : 1) * ((HIT_TILE + HIT_HALO) / 32) * 4);
+    const size_t smem = table_smem(ns, true) + up(HIT_STAGE / 16 * 4) + up(HIT_STAGE / 32 * 4) + up((size_t)HIT_SPAN * 8) +
+                        up((size_t)(HIT_SPAN / 32 + 1) * 4) + up((size_t)(nb > 1 ? nb : 1) * ((HIT_TILE + HIT_HALO) / 32) * 4);
     if (smem > 200 * 1024) return tg_set_err(TG_ERANGE, "k-mer table too large for shared memory (%zu bytes)", smem);
     HitParams P;
     P.pack2 = d_pack2; P.nmask = d_nmask; P.base_off = d_base_off;

@@ -213,8 +213,8 @@ class PackedReads:
     def density_counts(self, list_a, list_b, window):
         """uint8 window counts for two k-mer lists, device tensors over the padded base space."""
         torch = self.torch
-        ca = torch.zeros(max(self.total, 16), dtype=torch.uint8, device='cuda')
-        cb = torch.zeros(max(self.total, 16), dtype=torch.uint8, device='cuda')
+        ca = torch.empty(max(self.total, 16), dtype=torch.uint8, device='cuda')     # only [0, len - window) of each read is defined
+        cb = torch.empty(max(self.total, 16), dtype=torch.uint8, device='cuda')
         d_toff, n_tiles = self._tiles(int(window))
         if self.n and self.total and n_tiles:
             _lib.check(self.L.tg_scan_density(_lib.dptr(self.d_pack2), _lib.dptr(self.d_nmask), _lib.dptr(self.d_base_off),
