@@ -386,6 +386,18 @@ def main():
         barrier()
         e2e_ms.append((time.perf_counter() - t0) * 1e3)
         h2d, d2h = eng2.stats['h2d_bytes'], eng2.stats['d2h_bytes']
+    verified = None
+    if world > 1 and rank == 0:
+        # cross-check the gathered multi-GPU result on a sample of pairs recomputed locally through the
+        # explicit-job path (same global pair indices -> same seeds)
+        from telogator2_b200.dist_engine import canonical_order
+        rs = np.random.default_rng(7)
+        sample = np.sort(rs.choice(n_pairs, size=min(256, n_pairs), replace=False)).astype(np.int64)
+        chk = DistEngine(Scoring.from_aligner(aligner)).pair_scores(seqs, True, True, R, SEED, pair_idx=sample)
+        full = canonical_order(res, n_seq)
+        assert np.array_equal(full['aln'][sample], chk['aln'][sample]), 'multi-GPU aln mismatch'
+        assert np.array_equal(full['rnd'][sample], chk['rnd'][sample]), 'multi-GPU rnd mismatch'
+        verified = int(len(sample))
     e2e_t = allmax(min(e2e_ms) * 1e-3)
     e2e_gcups = cells_all / e2e_t / 1e9
     assert D.shape == (n_seq, n_seq)
@@ -416,6 +428,7 @@ def main():
                          'what': 'basecount x2 + orient + density x2 + hits on the last 6000 bases of every read (device resident)',
                          'parts_ms': {k: float(np.mean(v)) for k, v in scan_parts.items() if v}},
                 'roofline': roof, 'roofline_scan': roof_scan, 'cpu_baseline': cpu, 'clocks': clocks,
+                'multi_gpu_verified_pairs': verified,
                 'wall_s_timed_region': t_wall}
         print(json.dumps(line))
     if world > 1:

@@ -27,7 +27,7 @@ class NwScoring(C.Structure):
 class DistBatchArgs(C.Structure):
     _fields_ = [('d_pool', C.c_void_p), ('d_seq_off', C.c_void_p), ('d_order', C.c_void_p), ('d_diag_cs', C.c_void_p),
                 ('d_aln', C.c_void_p), ('d_rnd', C.c_void_p), ('d_shape', C.c_void_p), ('d_flags', C.c_void_p),
-                ('d_iden', C.c_void_p), ('d_scratch', C.c_void_p), ('d_counter', C.c_void_p),
+                ('d_iden', C.c_void_p), ('d_scratch', C.c_void_p), ('d_counter', C.c_void_p), ('d_mt_work', C.c_void_p),
                 ('q0', C.c_int64), ('q1', C.c_int64), ('seed0', C.c_int64), ('shuf_base', C.c_int64), ('slot', C.c_int64),
                 ('match', C.c_double),
                 ('n_seq', C.c_int32), ('adjust_lens', C.c_int32), ('min_viable', C.c_int32), ('R', C.c_int32),
@@ -44,7 +44,7 @@ _lib = None
 
 EXPORTS = ['tg_last_error', 'tg_version', 'tg_device_sm_count',
            'tg_nw_wave_scratch_bytes', 'tg_nw_wave_check', 'tg_nw_scores_wave', 'tg_nw_generic_max_m',
-           'tg_nw_scores_generic', 'tg_mt_shuffle', 'tg_dist_batch', 'tg_int_alu_peak',
+           'tg_nw_scores_generic', 'tg_mt_shuffle', 'tg_dist_batch', 'tg_dist_batch_mt_work_bytes', 'tg_int_alu_peak',
            'tg_kmer_table_bytes', 'tg_kmer_table_build', 'tg_kmer_table_build_pair', 'tg_scan_tile_bases', 'tg_scan_pack', 'tg_scan_basecount', 'tg_scan_orient',
            'tg_scan_density', 'tg_scan_hits_work_bytes', 'tg_scan_hits']
 
@@ -67,6 +67,8 @@ def load():
     L.tg_nw_scores_generic.argtypes = [vp, vp, i64, i32, C.POINTER(NwScoring), vp, vp]
     L.tg_mt_shuffle.argtypes = [vp, vp, i64, i32, i32, vp]
     L.tg_dist_batch.argtypes = [C.POINTER(DistBatchArgs), C.POINTER(NwScoring), vp]
+    L.tg_dist_batch_mt_work_bytes.restype = sz
+    L.tg_dist_batch_mt_work_bytes.argtypes = [i64, i32, i32]
     L.tg_int_alu_peak.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.tg_device_sm_count.argtypes = [C.POINTER(C.c_int)]
     L.tg_kmer_table_bytes.restype = sz

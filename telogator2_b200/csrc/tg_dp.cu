@@ -643,6 +643,231 @@ __global__ void __launch_bounds__(MT_THREADS) mt_shuffle_batch_kernel(const Batc
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Streamed null model (tg_dist_batch): the same bits as mt_shuffle_pair, split so that the expensive
+// part -- regenerating and tempering the MT19937 state -- runs warp-parallel:
+//   mt_seed_batch_kernel    thread per pair: init_by_array, state -> global (coalesced write-out)
+//   mt_stream_batch_kernel  warp per pair: block twists (3 data-parallel phases) + tempering, the top
+//                           16 bits of every output word go to a per-pair stream (getrandbits(k) only
+//                           ever looks at the top k <= 16 bits)
+//   mt_sample_batch_kernel  thread per pair: random.sample's swap-remove loop consuming the stream
+// ------------------------------------------------------------------------------------------------
+constexpr int MTS_PAD = 33;          // row stride of the transposing state buffer: conflict free both ways
+
+struct StreamParams {
+    uint8_t *pool;
+    const long long *seq_off;
+    const int *order;
+    int n_seq, adjust_lens, min_viable, R;
+    long long q0, q1;
+    const uint8_t *flags;
+    long long shuf_base, slot;
+    long long seed0;
+    int pool_stride;
+    int cap;                         // stream capacity per pair in 16-bit draws (multiple of 624)
+    uint32_t *state;                 // [pairs][624]
+    uint16_t *stream;                // [pairs][cap]
+    unsigned long long *counter;
+    int *overflow;
+};
+
+__host__ __device__ __forceinline__ int mt_blocks_needed(int total_len)
+{
+    // expected draws <= 1.47 per element (worst just above a power of two), sd ~ sqrt(0.6 * elements)
+    return (int)(((long long)total_len * 8 / 5 + 256 + 623) / 624);
+}
+
+__global__ void __launch_bounds__(MT_THREADS) mt_seed_batch_kernel(const StreamParams P)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint32_t *mt = reinterpret_cast<uint32_t *>(smem);                 // [624][MTS_PAD]
+    const int tid = threadIdx.x;
+    const long long npairs = P.q1 - P.q0;
+#define MTP(i) mt[(i) * MTS_PAD + tid]
+    for (;;) {
+        unsigned long long base = 0;
+        if (tid == 0) base = atomicAdd(P.counter, (unsigned long long)MT_THREADS);
+        base = __shfl_sync(TG_FULL_MASK, base, 0);
+        if ((long long)base >= npairs) break;
+        const long long ql = (long long)base + tid;
+        const bool active = ql < npairs && !P.flags[ql];
+        if (active) {
+            const PairDesc d = describe_pair(P, P.q0 + ql);
+            const long long sv = P.seed0 + d.p;
+            const uint64_t seed = (uint64_t)(sv < 0 ? -sv : sv);
+            uint32_t key[2] = {(uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32)};
+            const int klen = key[1] ? 2 : 1;
+            for (int i = 0; i < 624; i++) MTP(i) = c_mt_base[i];
+            int i = 1, j = 0;
+            uint32_t prev = MTP(0);
+            for (int k = 624; k; k--) {
+                uint32_t v = (MTP(i) ^ ((prev ^ (prev >> 30)) * 1664525u)) + key[j] + (uint32_t)j;
+                MTP(i) = v; prev = v;
+                i++; j++;
+                if (i >= 624) { MTP(0) = prev; i = 1; }
+                if (j >= klen) j = 0;
+            }
+            for (int k = 623; k; k--) {
+                uint32_t v = (MTP(i) ^ ((prev ^ (prev >> 30)) * 1566083941u)) - (uint32_t)i;
+                MTP(i) = v; prev = v;
+                i++;
+                if (i >= 624) { MTP(0) = prev; i = 1; }
+            }
+            MTP(0) = 0x80000000u;
+        }
+        __syncwarp();
+        const uint32_t act = __ballot_sync(TG_FULL_MASK, active);
+        for (int l = 0; l < MT_THREADS; l++) {
+            if (!((act >> l) & 1u)) continue;
+            uint32_t *dst = P.state + ((long long)base + l) * 624;
+            for (int i = tid; i < 624; i += MT_THREADS) dst[i] = mt[i * MTS_PAD + l];
+        }
+        __syncwarp();
+    }
+#undef MTP
+}
+
+constexpr int MTG_WARPS = 8;
+
+__global__ void __launch_bounds__(MTG_WARPS * 32) mt_stream_batch_kernel(const StreamParams P)
+{
+    __shared__ uint32_t s_mt[MTG_WARPS][624];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *m = s_mt[warp];
+    const long long npairs = P.q1 - P.q0;
+    for (;;) {
+        unsigned long long ql = 0;
+        if (lane == 0) ql = atomicAdd(P.counter, 1ULL);
+        ql = __shfl_sync(TG_FULL_MASK, ql, 0);
+        if ((long long)ql >= npairs) break;
+        if (P.flags[ql]) continue;
+        const PairDesc d = describe_pair(P, P.q0 + (long long)ql);
+        int nblk = mt_blocks_needed(P.R * (d.n + d.m));
+        if (nblk * 624 > P.cap) nblk = P.cap / 624;
+        const uint32_t *src = P.state + (long long)ql * 624;
+        __syncwarp();
+        for (int i = lane; i < 624; i += 32) m[i] = src[i];
+        __syncwarp();
+        uint32_t *out = reinterpret_cast<uint32_t *>(P.stream + (long long)ql * P.cap);
+        for (int blk = 0; blk < nblk; blk++) {
+            // mt[kk] = mt[kk + 397 (mod 624)] ^ twist(mt[kk], mt[kk + 1]) for kk = 0 .. 623, in place and in order:
+            // three ranges whose inputs are complete when the range starts, then the last word
+#define TG_TWIST_RANGE(lo, hi, far)                                                                    \
+    for (int i0 = (lo); i0 < (hi); i0 += 32) {                                                         \
+        const int i = i0 + lane;                                                                       \
+        uint32_t v = 0;                                                                                \
+        if (i < (hi)) {                                                                                \
+            const uint32_t y = (m[i] & 0x80000000u) | (m[i + 1] & 0x7fffffffu);                        \
+            v = m[i + (far)] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);                               \
+        }                                                                                              \
+        __syncwarp();                                                                                  \
+        if (i < (hi)) m[i] = v;                                                                        \
+        __syncwarp();                                                                                  \
+    }
+            TG_TWIST_RANGE(0, 227, 397)
+            TG_TWIST_RANGE(227, 454, -227)
+            TG_TWIST_RANGE(454, 623, -227)
+#undef TG_TWIST_RANGE
+            if (lane == 0) {
+                const uint32_t y = (m[623] & 0x80000000u) | (m[0] & 0x7fffffffu);
+                m[623] = m[396] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            __syncwarp();
+            // tempering; two consecutive 16-bit draws per 32-bit store
+            for (int i = 2 * lane; i < 624; i += 64) {
+                uint32_t y0 = m[i], y1 = m[i + 1];
+                y0 ^= (y0 >> 11); y0 ^= (y0 << 7) & 0x9d2c5680u; y0 ^= (y0 << 15) & 0xefc60000u; y0 ^= (y0 >> 18);
+                y1 ^= (y1 >> 11); y1 ^= (y1 << 7) & 0x9d2c5680u; y1 ^= (y1 << 15) & 0xefc60000u; y1 ^= (y1 >> 18);
+                out[(blk * 624 + i) >> 1] = (y0 >> 16) | (y1 & 0xffff0000u);
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// SMEM_POOL: the working array lives in shared memory (else in place in the destination region: long sequences)
+template <bool SMEM_POOL>
+__global__ void __launch_bounds__(MT_THREADS) mt_sample_batch_kernel(const StreamParams P)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t *sp = smem + (size_t)threadIdx.x * P.pool_stride;
+    const int tid = threadIdx.x;
+    const long long npairs = P.q1 - P.q0;
+    for (;;) {
+        unsigned long long base = 0;
+        if (tid == 0) base = atomicAdd(P.counter, (unsigned long long)MT_THREADS);
+        base = __shfl_sync(TG_FULL_MASK, base, 0);
+        if ((long long)base >= npairs) break;
+        const long long ql = (long long)base + tid;
+        const bool live = ql < npairs && !P.flags[ql];
+        const unsigned act = __ballot_sync(TG_FULL_MASK, live);
+        if (live) {
+            const PairDesc d = describe_pair(P, P.q0 + ql);
+            int cap = mt_blocks_needed(P.R * (d.n + d.m)) * 624;
+            if (cap > P.cap) cap = P.cap;
+            // The stream is consumed in groups of 16 draws: a group is parked in this lane's 32-byte shared-memory slot
+            // and read back one 16-bit draw at a time, while the NEXT group is already on its way from L2/HBM into
+            // registers (requested ~16 loop iterations before it is needed).
+            const uint4 *st = reinterpret_cast<const uint4 *>(P.stream + ql * P.cap);
+            const int ngroups = cap / 16;
+            int grp = 0, kdraw = 0;
+            uint4 *slot4 = reinterpret_cast<uint4 *>(smem + (size_t)MT_THREADS * P.pool_stride) + 2 * tid;
+            const uint16_t *slot = reinterpret_cast<const uint16_t *>(slot4);
+            slot4[0] = __ldcg(st);
+            slot4[1] = __ldcg(st + 1);
+            uint4 n0 = __ldcg(st + 2), n1 = __ldcg(st + 3);
+            long long dst = P.shuf_base + ql * P.slot;
+            bool ok = true;
+            for (int rep = 0; rep < 2 * P.R; rep++) {
+                // Independent thread scheduling does not re-join lanes that left the sampling loop at different
+                // times; without these barriers the rest of the kernel would run one lane at a time.
+                __syncwarp(act);
+                const int len = (rep & 1) ? d.m : d.n;
+                const uint8_t *src = P.pool + ((rep & 1) ? d.off_j : d.off_i);
+                uint8_t *garr = P.pool + dst;
+#define ARR(ix) (SMEM_POOL ? sp[ix] : garr[ix])
+                for (int x = 0; x < len; x++) { const uint8_t c = src[x]; if (SMEM_POOL) sp[x] = c; else garr[x] = c; }   // pool = list(population)
+                int i = 0;
+                while (i < len) {
+                    const uint32_t v = slot[kdraw];
+                    kdraw++;
+                    if (kdraw == 16) {
+                        kdraw = 0;
+                        grp++;
+                        if (grp >= ngroups) ok = false;                        // stream exhausted: flag it (results are discarded)
+                        slot4[0] = n0;
+                        slot4[1] = n1;
+                        const int gi = min(grp + 1, ngroups - 1);
+                        n0 = __ldcg(st + 2 * gi);
+                        n1 = __ldcg(st + 2 * gi + 1);
+                    }
+                    // _randbelow(nn): k = nn.bit_length(); r = getrandbits(k) = top k bits of the 32-bit output.
+                    // result[i] = pool[j] goes to the vacated tail slot; a rejected draw swaps the tail with itself
+                    const uint32_t nn = (uint32_t)(len - i);
+                    const uint32_t r = v >> (__clz(nn) - 16);                  // 16 - bit_length(nn)
+                    const uint32_t j = min(r, nn - 1u);
+                    const uint8_t t = ARR(j), u = ARR(nn - 1u);
+                    if (SMEM_POOL) { sp[j] = u; sp[nn - 1u] = t; } else { garr[j] = u; garr[nn - 1u] = t; }
+                    i += (r < nn) ? 1 : 0;
+                }
+                __syncwarp(act);
+                if (SMEM_POOL) {
+                    for (int x = 0; x < len; x++) P.pool[dst + x] = sp[len - 1 - x];      // result[i] sits at arr[len-1-i]
+                } else {
+                    for (int x = 0; x < len / 2; x++) {
+                        const uint8_t a = garr[x], b = garr[len - 1 - x];
+                        garr[x] = b; garr[len - 1 - x] = a;
+                    }
+                }
+#undef ARR
+                dst += len;
+            }
+            if (!ok) atomicExch(P.overflow, 1);
+        }
+        __syncwarp();
+    }
+}
+
 struct FlagParams {
     const long long *seq_off;
     const int *order;
@@ -839,6 +1064,13 @@ TG_EXPORT int tg_nw_scores_wave(const uint8_t *d_pool, const tg_nw_job *d_jobs, 
 
 static int mt_upload_base();
 
+TG_EXPORT size_t tg_dist_batch_mt_work_bytes(int64_t n_pairs, int R, int max_len)
+{
+    if (n_pairs <= 0 || R <= 0 || max_len <= 0) return 0;
+    const size_t cap = (size_t)mt_blocks_needed(2 * R * max_len) * 624;
+    return (size_t)n_pairs * (624 * sizeof(uint32_t) + cap * sizeof(uint16_t)) + 256;
+}
+
 TG_EXPORT int tg_dist_batch(const tg_dist_batch_args *a, const tg_nw_scoring *sc, void *stream)
 {
     if (!a || !sc) return tg_set_err(TG_EINVAL, "NULL argument");
@@ -887,18 +1119,64 @@ TG_EXPORT int tg_dist_batch(const tg_dist_batch_args *a, const tg_nw_scoring *sc
     }
     if (a->R <= 0) return TG_OK;
     // ---- null model: MT19937 shuffles of every non-early pair ----
+    int stride = (a->max_len + 3) / 4;
+    if ((stride & 1) == 0) stride++;
+    stride *= 4;
+    rc = mt_upload_base();
+    if (rc != TG_OK) return rc;
+    if (a->d_mt_work && a->max_len < 65536) {
+        StreamParams S;
+        S.pool = a->d_pool; S.seq_off = P.seq_off; S.order = P.order; S.n_seq = P.n_seq; S.adjust_lens = P.adjust_lens;
+        S.min_viable = P.min_viable; S.R = a->R; S.q0 = a->q0; S.q1 = a->q1; S.flags = a->d_flags;
+        S.shuf_base = a->shuf_base; S.slot = a->slot; S.seed0 = a->seed0; S.counter = P.counter;
+        S.cap = mt_blocks_needed(2 * a->R * a->max_len) * 624;
+        S.state = reinterpret_cast<uint32_t *>(a->d_mt_work);
+        S.stream = reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(a->d_mt_work) + (size_t)npairs * 624 * sizeof(uint32_t));
+        S.overflow = reinterpret_cast<int *>(a->d_counter) + 4;      // sticky; the caller zeroes and checks it
+        size_t psmem = (size_t)MT_THREADS * stride + MT_THREADS * 32;
+        if (psmem > 200 * 1024) { stride = 0; psmem = MT_THREADS * 32; }
+        S.pool_stride = stride;
+        const long long need32 = (npairs + MT_THREADS - 1) / MT_THREADS;
+        // seeding
+        const size_t ssmem = (size_t)624 * MTS_PAD * sizeof(uint32_t);
+        TG_CUDA_CHECK(cudaFuncSetAttribute(mt_seed_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
+        TG_CUDA_CHECK(cudaMemsetAsync(a->d_counter, 0, sizeof(unsigned long long), st));
+        {
+            long long g = (long long)sms * 2;
+            if (g > need32) g = need32;
+            mt_seed_batch_kernel<<<(int)g, MT_THREADS, ssmem, st>>>(S);
+            TG_CUDA_CHECK(cudaGetLastError());
+        }
+        // stream generation
+        TG_CUDA_CHECK(cudaMemsetAsync(a->d_counter, 0, sizeof(unsigned long long), st));
+        {
+            long long g = (long long)sms * 8;
+            const long long need = (npairs + MTG_WARPS - 1) / MTG_WARPS;
+            if (g > need) g = need;
+            mt_stream_batch_kernel<<<(int)g, MTG_WARPS * 32, 0, st>>>(S);
+            TG_CUDA_CHECK(cudaGetLastError());
+        }
+        // sampling
+        TG_CUDA_CHECK(cudaMemsetAsync(a->d_counter, 0, sizeof(unsigned long long), st));
+        {
+            if (stride) TG_CUDA_CHECK(cudaFuncSetAttribute(mt_sample_batch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+            int per_sm = (int)((200 * 1024) / (psmem + 512));
+            if (per_sm < 1) per_sm = 1;
+            if (per_sm > 16) per_sm = 16;
+            long long g = (long long)sms * per_sm;
+            if (g > need32) g = need32;
+            if (stride) mt_sample_batch_kernel<true><<<(int)g, MT_THREADS, psmem, st>>>(S);
+            else mt_sample_batch_kernel<false><<<(int)g, MT_THREADS, psmem, st>>>(S);
+            TG_CUDA_CHECK(cudaGetLastError());
+        }
+    } else {
     BatchShuffleParams S;
     S.pool = a->d_pool; S.seq_off = P.seq_off; S.order = P.order; S.n_seq = P.n_seq; S.adjust_lens = P.adjust_lens;
     S.min_viable = P.min_viable; S.R = a->R; S.q0 = a->q0; S.q1 = a->q1; S.flags = a->d_flags;
     S.shuf_base = a->shuf_base; S.slot = a->slot; S.seed0 = a->seed0; S.counter = P.counter;
-    int stride = (a->max_len + 3) / 4;
-    if ((stride & 1) == 0) stride++;
-    stride *= 4;
     size_t msmem = 624 * MT_THREADS * sizeof(uint32_t) + (size_t)MT_THREADS * stride;
     if (msmem > 200 * 1024) { stride = 0; msmem = 624 * MT_THREADS * sizeof(uint32_t); }
     S.pool_stride = stride;
-    rc = mt_upload_base();
-    if (rc != TG_OK) return rc;
     TG_CUDA_CHECK(cudaFuncSetAttribute(mt_shuffle_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
     {
         int per_sm = (int)((227 * 1024) / (msmem + 1024));
@@ -910,6 +1188,7 @@ TG_EXPORT int tg_dist_batch(const tg_dist_batch_args *a, const tg_nw_scoring *sc
         TG_CUDA_CHECK(cudaMemsetAsync(a->d_counter, 0, sizeof(unsigned long long), st));
         mt_shuffle_batch_kernel<<<(int)g, MT_THREADS, msmem, st>>>(S);
         TG_CUDA_CHECK(cudaGetLastError());
+    }
     }
     // ---- phase B: alignments of the shuffled pairs ----
     P.scores = a->d_rnd;
