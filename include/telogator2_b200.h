@@ -117,7 +117,7 @@ typedef struct tg_dist_batch_args {
     uint8_t *d_flags;
     double *d_iden;
     void *d_scratch;                /* tg_nw_wave_scratch_bytes(max_len) */
-    int32_t *d_counter;             /* 32 bytes; d_counter[4] is set to 1 if a random stream overflowed (results invalid: rerun with d_mt_work = NULL) */
+    int32_t *d_counter;             /* 32 bytes, zeroed once by the caller; d_counter[4] is set to 1 if a random stream overflowed (results invalid: rerun with d_mt_work = NULL) */
     void *d_mt_work;                /* tg_dist_batch_mt_work_bytes(q1 - q0, R, max_len) bytes, or NULL for the single-kernel null model */
     int64_t q0, q1, seed0, shuf_base, slot;
     double match;                   /* match score, used when d_diag_cs == NULL */

@@ -669,6 +669,8 @@ struct StreamParams {
     uint16_t *stream;                // [pairs][cap]
     unsigned long long *counter;
     int *overflow;
+    const int *live;                 // pair indices (q - q0) that survived the early-out test, in no particular order
+    const int *n_live;
 };
 
 __host__ __device__ __forceinline__ int mt_blocks_needed(int total_len)
@@ -682,15 +684,15 @@ __global__ void __launch_bounds__(MT_THREADS) mt_seed_batch_kernel(const StreamP
     extern __shared__ __align__(16) uint8_t smem[];
     uint32_t *mt = reinterpret_cast<uint32_t *>(smem);                 // [624][MTS_PAD]
     const int tid = threadIdx.x;
-    const long long npairs = P.q1 - P.q0;
+    const long long npairs = *P.n_live;
 #define MTP(i) mt[(i) * MTS_PAD + tid]
     for (;;) {
         unsigned long long base = 0;
         if (tid == 0) base = atomicAdd(P.counter, (unsigned long long)MT_THREADS);
         base = __shfl_sync(TG_FULL_MASK, base, 0);
         if ((long long)base >= npairs) break;
-        const long long ql = (long long)base + tid;
-        const bool active = ql < npairs && !P.flags[ql];
+        const bool active = (long long)base + tid < npairs;
+        const long long ql = active ? P.live[base + tid] : 0;
         if (active) {
             const PairDesc d = describe_pair(P, P.q0 + ql);
             const long long sv = P.seed0 + d.p;
@@ -719,7 +721,8 @@ __global__ void __launch_bounds__(MT_THREADS) mt_seed_batch_kernel(const StreamP
         const uint32_t act = __ballot_sync(TG_FULL_MASK, active);
         for (int l = 0; l < MT_THREADS; l++) {
             if (!((act >> l) & 1u)) continue;
-            uint32_t *dst = P.state + ((long long)base + l) * 624;
+            const long long qd = __shfl_sync(TG_FULL_MASK, ql, l);
+            uint32_t *dst = P.state + qd * 624;
             for (int i = tid; i < 624; i += MT_THREADS) dst[i] = mt[i * MTS_PAD + l];
         }
         __syncwarp();
@@ -734,13 +737,13 @@ __global__ void __launch_bounds__(MTG_WARPS * 32) mt_stream_batch_kernel(const S
     __shared__ uint32_t s_mt[MTG_WARPS][624];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *m = s_mt[warp];
-    const long long npairs = P.q1 - P.q0;
+    const long long npairs = *P.n_live;
     for (;;) {
-        unsigned long long ql = 0;
-        if (lane == 0) ql = atomicAdd(P.counter, 1ULL);
-        ql = __shfl_sync(TG_FULL_MASK, ql, 0);
-        if ((long long)ql >= npairs) break;
-        if (P.flags[ql]) continue;
+        unsigned long long li = 0;
+        if (lane == 0) li = atomicAdd(P.counter, 1ULL);
+        li = __shfl_sync(TG_FULL_MASK, li, 0);
+        if ((long long)li >= npairs) break;
+        const long long ql = P.live[li];
         const PairDesc d = describe_pair(P, P.q0 + (long long)ql);
         int nblk = mt_blocks_needed(P.R * (d.n + d.m));
         if (nblk * 624 > P.cap) nblk = P.cap / 624;
@@ -792,14 +795,14 @@ __global__ void __launch_bounds__(MT_THREADS) mt_sample_batch_kernel(const Strea
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *sp = smem + (size_t)threadIdx.x * P.pool_stride;
     const int tid = threadIdx.x;
-    const long long npairs = P.q1 - P.q0;
+    const long long npairs = *P.n_live;
     for (;;) {
         unsigned long long base = 0;
         if (tid == 0) base = atomicAdd(P.counter, (unsigned long long)MT_THREADS);
         base = __shfl_sync(TG_FULL_MASK, base, 0);
         if ((long long)base >= npairs) break;
-        const long long ql = (long long)base + tid;
-        const bool live = ql < npairs && !P.flags[ql];
+        const bool live = (long long)base + tid < npairs;
+        const long long ql = live ? P.live[base + tid] : 0;
         const unsigned act = __ballot_sync(TG_FULL_MASK, live);
         if (live) {
             const PairDesc d = describe_pair(P, P.q0 + ql);
@@ -879,6 +882,8 @@ struct FlagParams {
     uint8_t *flags;
     double *iden;
     int32_t *shape;               // [2 * pairs] length-adjusted n, m
+    int *live;                    // optional: compacted list of non-early pairs (unordered) ...
+    int *n_live;                  // ... and its length
 };
 
 // identity score and the early-out test of tvr_distance (tg_align.py:127-138), in float64 like the reference
@@ -895,7 +900,9 @@ __global__ void __launch_bounds__(256) dist_flags_kernel(const FlagParams P)
             iden = P.match * ((double)(d.n + d.m) / 2.0);
         }
         const double aln = (double)P.aln[ql];
-        P.flags[ql] = (aln < -(0.900 * iden)) ? 1 : 0;
+        const bool early = aln < -(0.900 * iden);
+        P.flags[ql] = early ? 1 : 0;
+        if (P.live && !early) P.live[atomicAdd(P.n_live, 1)] = (int)ql;
         P.iden[ql] = iden;
         P.shape[2 * ql] = d.n;
         P.shape[2 * ql + 1] = d.m;
@@ -1068,7 +1075,7 @@ TG_EXPORT size_t tg_dist_batch_mt_work_bytes(int64_t n_pairs, int R, int max_len
 {
     if (n_pairs <= 0 || R <= 0 || max_len <= 0) return 0;
     const size_t cap = (size_t)mt_blocks_needed(2 * R * max_len) * 624;
-    return (size_t)n_pairs * (624 * sizeof(uint32_t) + cap * sizeof(uint16_t)) + 256;
+    return (size_t)n_pairs * (624 * sizeof(uint32_t) + cap * sizeof(uint16_t) + sizeof(int)) + 512;
 }
 
 TG_EXPORT int tg_dist_batch(const tg_dist_batch_args *a, const tg_nw_scoring *sc, void *stream)
@@ -1111,6 +1118,10 @@ TG_EXPORT int tg_dist_batch(const tg_dist_batch_args *a, const tg_nw_scoring *sc
     F.seq_off = P.seq_off; F.order = P.order; F.n_seq = P.n_seq; F.adjust_lens = P.adjust_lens; F.min_viable = P.min_viable;
     F.R = a->R; F.q0 = a->q0; F.q1 = a->q1; F.aln = a->d_aln; F.diag_cs = a->d_diag_cs; F.match = a->match;
     F.flags = a->d_flags; F.iden = a->d_iden; F.shape = a->d_shape;
+    const bool streamed = a->R > 0 && a->d_mt_work && a->max_len < 65536;
+    F.live = streamed ? reinterpret_cast<int *>(a->d_mt_work) : nullptr;
+    F.n_live = reinterpret_cast<int *>(a->d_counter) + 6;
+    if (streamed) TG_CUDA_CHECK(cudaMemsetAsync(F.n_live, 0, sizeof(int), st));
     {
         long long g = (npairs + 255) / 256;
         if (g > (long long)sms * 8) g = (long long)sms * 8;
@@ -1124,14 +1135,16 @@ TG_EXPORT int tg_dist_batch(const tg_dist_batch_args *a, const tg_nw_scoring *sc
     stride *= 4;
     rc = mt_upload_base();
     if (rc != TG_OK) return rc;
-    if (a->d_mt_work && a->max_len < 65536) {
+    if (streamed) {
         StreamParams S;
         S.pool = a->d_pool; S.seq_off = P.seq_off; S.order = P.order; S.n_seq = P.n_seq; S.adjust_lens = P.adjust_lens;
         S.min_viable = P.min_viable; S.R = a->R; S.q0 = a->q0; S.q1 = a->q1; S.flags = a->d_flags;
         S.shuf_base = a->shuf_base; S.slot = a->slot; S.seed0 = a->seed0; S.counter = P.counter;
         S.cap = mt_blocks_needed(2 * a->R * a->max_len) * 624;
-        S.state = reinterpret_cast<uint32_t *>(a->d_mt_work);
-        S.stream = reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(a->d_mt_work) + (size_t)npairs * 624 * sizeof(uint32_t));
+        const size_t live_bytes = ((size_t)npairs * sizeof(int) + 255) / 256 * 256;
+        S.live = F.live; S.n_live = F.n_live;
+        S.state = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(a->d_mt_work) + live_bytes);
+        S.stream = reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(a->d_mt_work) + live_bytes + (size_t)npairs * 624 * sizeof(uint32_t));
         S.overflow = reinterpret_cast<int *>(a->d_counter) + 4;      // sticky; the caller zeroes and checks it
         size_t psmem = (size_t)MT_THREADS * stride + MT_THREADS * 32;
         if (psmem > 200 * 1024) { stride = 0; psmem = MT_THREADS * 32; }
