@@ -30,6 +30,18 @@ METRIC = 'tvr_all_vs_all_gcups'
 LETTER_MIX = 'CCCCCCCCCCCCVVVHTFDA'
 
 
+def workload_config(n_seq, world, scan_mbases_total):
+    n_pairs = n_seq * (n_seq - 1) // 2
+    return {'workload': f'D1 iter-0 TVR distance matrix (SURVEY 8d): N={n_seq} colour vectors (bundled HiFi+ONT reads, truncate 1000, replicated '
+                        f'with 2% seeded letter edits), tvr matrix, gaps -4, adjust_lens+min_viable, R=2, rng_seed 12345; pair space sharded '
+                        f'over {world} GPU(s) (weak scaling: N = n_seq*sqrt(GPUs))',
+            'n_seq': n_seq, 'pairs': n_pairs,
+            'l2_policy': 'DP inputs are register/shared-memory resident (integer-ALU bound, DRAM < 2 MB per launch); every step regenerates '
+                         'all shuffles and rewrites all per-pair outputs; the scan inputs (>= 150 MB packed + 800 MB outputs) exceed the 126 MB L2',
+            'scan_workload': f'{scan_mbases_total:.0f} Mbases of bundled HiFi+ONT reads replicated with 0.5% seeded edits, K=57 (+57 reverse '
+                             f'complements), window 100, hits on the last 6000 bases of every read'}
+
+
 def load_fixtures():
     with gzip.open(os.path.join(GOLDEN, 'colorvecs.json.gz'), 'rt') as f:
         cv = json.load(f)['colorvecs']
@@ -106,6 +118,14 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
+def ncu_traffic(kernel):
+    """dram read+write bytes per launch from the committed `ncu --set full` capture (profiles/), or None."""
+    p = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+    if os.path.exists(p):
+        return json.load(open(p)).get(kernel)
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -156,7 +176,8 @@ def run_reference(args, rank, world):
         return
     cv, reads, tables = load_fixtures()
     threads = os.cpu_count() or 1
-    seqs = make_dp_workload(cv, args.n_seq)
+    n_seq = int(round(args.n_seq * np.sqrt(world)))
+    seqs = make_dp_workload(cv, n_seq)
     sample_pairs = max(64, int(args.cpu_pairs))
     vals, times = [], []
     for it in range(args.warmup + args.steps):
@@ -164,14 +185,13 @@ def run_reference(args, rank, world):
         if it >= args.warmup:
             vals.append(g)
             times.append(dt)
-    scan_reads = make_scan_workload(reads, 2_000_000)
-    mb, sdt, sb = cpu_scan_sample(scan_reads, tables, threads, 2_000_000)
+    scan_reads = make_scan_workload(reads, int(args.cpu_scan_mbases * 1e6))
+    mb, sdt, sb = cpu_scan_sample(scan_reads, tables, threads, int(args.cpu_scan_mbases * 1e6))
     v = float(np.mean(vals))
     line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'GCUPS', 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': float(np.mean(times) * 1e3), 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': f'D1 iter-0 TVR distance matrix N={args.n_seq} L=1000 R=2 (first {sample_pairs} pairs per step)',
-                       'n_seq': args.n_seq},
+            'config': workload_config(n_seq, world, args.scan_mbases * world),
             'cpu_baseline': {'value': v, 'unit': 'GCUPS', 'cores': threads, 'kind': 'port',
                              'sample': f'oracle/tg_oracle.c (Biopython-style double-precision NW + MT19937 shuffles), OpenMP, first '
                                        f'{sample_pairs} pairs of the same matrix per step; Biopython itself is not installable here'},
@@ -193,7 +213,8 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--n-seq', type=int, default=2048, help='sequences per GPU in the DP workload (weak scaling)')
     ap.add_argument('--scan-mbases', type=float, default=400.0, help='scan workload per GPU, Mbases')
-    ap.add_argument('--cpu-pairs', type=int, default=1500, help='pairs per step of the CPU sample')
+    ap.add_argument('--cpu-pairs', type=int, default=30000, help='pairs per step of the CPU sample (~10 s of 16 cores)')
+    ap.add_argument('--cpu-scan-mbases', type=float, default=200.0, help='bases of the CPU scan sample, Mbases')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
@@ -353,7 +374,7 @@ def main():
         instr_per_cell = 1.5                       # minimal s16x2 cost of the linear-gap cell
         peak_gcups = dpx.value / instr_per_cell / 1e9
         roof = {'bound': 'int_alu', 'kernel': 'nw_wave_kernel', 'achieved': k_gcups, 'peak': peak_gcups, 'unit': 'GCUPS',
-                'frac': k_gcups / peak_gcups, 'traffic': None,
+                'frac': k_gcups / peak_gcups, 'traffic': ncu_traffic('nw_wave_kernel'),
                 'peak_source': f'measured in this run: {dpx.value / 1e12:.2f} T VIMNMX3.U16x2 lane-ops/s (tg_int_alu_peak) / 1.5 instr per cell '
                                f'(SURVEY 8d); add+max3 pair rate {mixed.value / 1e12:.2f} T pairs/s',
                 'launch_ms': min(ks) * 1e3, 'cells_per_launch': kcells}
@@ -369,7 +390,7 @@ def main():
         pk, src = peaks()
         ach = scan_bases * 2.375 / min(ds) / 1e9
         roof_scan = {'bound': 'hbm', 'kernel': 'scan_cov_kernel<density>', 'achieved': ach, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
-                     'frac': ach / pk['hbm_gbs'], 'traffic': None, 'peak_source': src, 'launch_ms': min(ds) * 1e3,
+                     'frac': ach / pk['hbm_gbs'], 'traffic': ncu_traffic('scan_cov_kernel<density>'), 'peak_source': src, 'launch_ms': min(ds) * 1e3,
                      'bytes_per_base': 2.375, 'mbases_per_s': scan_bases / min(ds) / 1e6}
 
     # ---------------- e2e through the public API: host strings -> float32 matrix on the host --------
@@ -406,7 +427,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         g, dt, cells = cpu_dp_sample(seqs, args.cpu_pairs, threads)
-        smb, sdt, sb = cpu_scan_sample(scan_reads, tables, threads, 2_000_000)
+        smb, sdt, sb = cpu_scan_sample(scan_reads, tables, threads, int(args.cpu_scan_mbases * 1e6))
         cpu = {'value': g, 'unit': 'GCUPS', 'cores': threads, 'kind': 'port',
                'sample': f'oracle C port (Biopython-style f64 NW + MT19937), OpenMP {threads} threads, first {args.cpu_pairs} pairs of the same '
                          f'matrix ({dt:.1f} s); scan: {smb:.2f} Mbases/s on {sb} bases ({sdt:.1f} s)',
@@ -416,11 +437,7 @@ def main():
         line = {'metric': METRIC, 'value': gcups, 'unit': 'GCUPS', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                 'ms_per_step': dp_t * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u16',
                 'data': 'synthetic',
-                'config': {'workload': f'D1 iter-0 TVR distance matrix, N={n_seq} colour vectors (bundled reads replicated with 2% edits), '
-                                       f'L=1000, tvr matrix, gaps -4, R=2, seed 12345; pairs sharded over {world} GPU(s)',
-                           'n_seq': n_seq, 'pairs': n_pairs, 'l2_policy': 'inputs larger than L2 are not needed: DP is ALU bound; '
-                                                                            'each step re-uploads jobs and regenerates all shuffles',
-                           'scan_workload': f'{bases_all / 1e6:.0f} Mbases of bundled HiFi+ONT reads replicated with 0.5% edits, K=57, window 100'},
+                'config': workload_config(n_seq, world, bases_all / 1e6),
                 'e2e': {'value': e2e_gcups, 'unit': 'GCUPS', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                         'ms_per_step': e2e_t * 1e3},
                 'gpu_launches': int(launches_dp + 4),

@@ -120,6 +120,10 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr)
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ void sts64(uint32_t addr, uint2 v)
+{
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
 {
     uint32_t v;
@@ -219,9 +223,11 @@ __global__ void __launch_bounds__(WAVE_MAX_WARPS * 32, 1) nw_wave_kernel(const _
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int A = P.A, A1 = P.A + 1;
     uint8_t *s_sp = smem;                                                    // MAXA*MAXA bytes
-    const size_t per_warp = (size_t)2 * A1 * W + (size_t)P.row_cap * 2;
+    constexpr int ROFF = (RR == 2) ? 64 : 0;                                 // rows[ROFF + r] = letters of row r
+    const size_t per_warp = (size_t)2 * A1 * W + (size_t)P.row_cap * 2 + 512;
     uint8_t *prof = smem + MAXA * MAXA + (size_t)warp * per_warp;            // [2][A+1][W]
     uint16_t *rows = reinterpret_cast<uint16_t *>(prof + (size_t)2 * A1 * W);
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(prof + (size_t)2 * A1 * W + (size_t)P.row_cap * 2);   // 64 x uint2
     for (int i = threadIdx.x; i < MAXA * MAXA; i += blockDim.x) s_sp[i] = P.sp[i];
     __syncthreads();
 
@@ -288,10 +294,11 @@ __global__ void __launch_bounds__(WAVE_MAX_WARPS * 32, 1) nw_wave_kernel(const _
         // row letters of both alignments; rows past the end of a sequence get the padding letter A, whose
         // all-zero profile row makes H' copy the previous row (H' is non-decreasing along a row)
         __syncwarp();
-        for (int r = lane; r < N + 4; r += 32) {
-            const uint32_t a0 = (r < n0) ? (uint32_t)__ldg(P.pool + row0 + r) : (uint32_t)A;
-            const uint32_t a1 = (r < n1) ? (uint32_t)__ldg(P.pool + row1 + r) : (uint32_t)A;
-            rows[r] = (uint16_t)(a0 | (a1 << 8));
+        for (int e = lane; e < N + 4 + 2 * ROFF + (ROFF ? 4 : 0); e += 32) {
+            const int r = e - ROFF;
+            const uint32_t a0 = (r >= 0 && r < n0) ? (uint32_t)__ldg(P.pool + row0 + r) : (uint32_t)A;
+            const uint32_t a1 = (r >= 0 && r < n1) ? (uint32_t)__ldg(P.pool + row1 + r) : (uint32_t)A;
+            rows[e] = (uint16_t)(a0 | (a1 << 8));
         }
 
         for (int blk = 0; blk < nblk; blk++) {
@@ -353,40 +360,36 @@ __global__ void __launch_bounds__(WAVE_MAX_WARPS * 32, 1) nw_wave_kernel(const _
                 }
             }
             } else {
-            // ---- two rows per step: this lane handles row pair k = s - lane (rows 2k, 2k + 1) ----
+            // ---- two rows per step: this lane handles row pair k = s - lane (rows 2k, 2k + 1).  The loop body is
+            //      branch free: pairs before the first row (k < 0) run on padding letters with zeroed inputs and
+            //      stay zero, pairs past the last row run on padding letters and copy the last row down. ----
             const int NP = (N + 1) >> 1;
             const int steps = NP + 31;
             int k = -lane;
             uint32_t prevL1 = 0u, A7 = 0u;
-            uint32_t ap2 = (k == 0) ? lds_u32(rows_s) : 0u;       // letters of rows 2k (low half) and 2k + 1
-            uint2 *bord2 = reinterpret_cast<uint2 *>(bord);
+            uint2 *bord2 = reinterpret_cast<uint2 *>(bord) + 32;   // bord2[k], k >= -31
             uint2 *bw = bord2 + k;
-            uint2 bcur = make_uint2(0u, 0u), bnext = make_uint2(0u, 0u);
-            if (blk > 0) {
-                if (lane < NP) bcur = __ldcg(bord2 + lane);
-                if (32 + lane < NP) bnext = __ldcg(bord2 + 32 + lane);
-            }
+            // border column of the previous block: 32 row pairs per refill, parked in a 64-entry shared-memory ring
+            uint2 bnext = (blk > 0 && lane < NP) ? __ldcg(bord2 + lane) : make_uint2(0u, 0u);
+            uint32_t ap2 = lds_u32(rows_s + 2 * ROFF + 4 * k);     // letters of rows 2k (low half) and 2k + 1
             for (int s = 0; s < steps; s++, k++, bw++) {
+                if ((s & 31) == 0) {
+                    sts64(ring_s + 8 * ((s + lane) & 63), bnext);
+                    const int idx = s + 32 + lane;
+                    bnext = (blk > 0 && idx < NP) ? __ldcg(bord2 + idx) : make_uint2(0u, 0u);
+                    __syncwarp();
+                }
                 uint32_t L0 = __shfl_up_sync(TG_FULL_MASK, A7, 1);
                 uint32_t L1 = __shfl_up_sync(TG_FULL_MASK, H[C - 1], 1);
-                if (blk > 0) {
-                    if ((s & 31) == 0 && s > 0) {
-                        bcur = bnext;
-                        const int idx = s + 32 + lane;
-                        bnext = (idx < NP) ? __ldcg(bord2 + idx) : make_uint2(0u, 0u);
-                    }
-                    const uint32_t b0 = __shfl_sync(TG_FULL_MASK, bcur.x, s & 31);
-                    const uint32_t b1 = __shfl_sync(TG_FULL_MASK, bcur.y, s & 31);
-                    if (lane == 0) { L0 = b0; L1 = b1; }
-                } else if (lane == 0) { L0 = 0u; L1 = 0u; }
-                if ((unsigned)k < (unsigned)NP) {
-                    using S2 = typename std::conditional<C == 16, Strip2x16, Strip2x8>::type;
-                    A7 = S2::run(H, prevL1, L0, L1,
-                                       pb0 + (ap2 & 0xffu) * W, pb1 + ((ap2 >> 8) & 0xffu) * W,
-                                       pb0 + ((ap2 >> 16) & 0xffu) * W, pb1 + (ap2 >> 24) * W);
-                    if (lane == 31) *bw = make_uint2(A7, H[C - 1]);
-                    ap2 = lds_u32(rows_s + 4 * (k + 1));
-                } else if (k == -1) ap2 = lds_u32(rows_s);
+                const uint2 rb = lds64(ring_s + 8 * (k & 63));
+                if (lane == 0) { L0 = rb.x; L1 = rb.y; }
+                if (k < 0) { L0 = 0u; L1 = 0u; }
+                using S2 = typename std::conditional<C == 16, Strip2x16, Strip2x8>::type;
+                A7 = S2::run(H, prevL1, L0, L1,
+                             pb0 + (ap2 & 0xffu) * W, pb1 + ((ap2 >> 8) & 0xffu) * W,
+                             pb0 + ((ap2 >> 16) & 0xffu) * W, pb1 + (ap2 >> 24) * W);
+                if (lane == 31) *bw = make_uint2(A7, H[C - 1]);
+                ap2 = lds_u32(rows_s + 2 * ROFF + 4 * (k + 1));
                 prevL1 = L1;
             }
             }
@@ -412,8 +415,9 @@ __global__ void __launch_bounds__(WAVE_MAX_WARPS * 32, 1) nw_wave_kernel(const _
             }
         } else {
             // last column: bord[r] = H'[r+1][m]; H[i][m] + gr*(n-i) = H'[i][m] + g*(i+m) + gr*(n-i)
+            const uint32_t *bcol = (RR == 2) ? bord + 64 : bord;
             for (int rr = lane; rr < N; rr += 32) {
-                const uint32_t v = __ldcg(bord + rr);
+                const uint32_t v = __ldcg(bcol + rr);
                 const int i = rr + 1;
                 if (i <= n0) rf0 = max(rf0, (int)(v & 0xffffu) + g * (i + m0) + gr * (n0 - i));
                 if (i <= n1) rf1 = max(rf1, (int)(v >> 16) + g * (i + m1) + gr * (n1 - i));
@@ -957,7 +961,7 @@ static void wave_env()
 TG_EXPORT size_t tg_nw_wave_scratch_bytes(int max_n)
 {
     const int sms = tg_sm_count();
-    const size_t stride = ((size_t)max_n + 63) / 32 * 32;
+    const size_t stride = ((size_t)max_n + 223) / 32 * 32;
     return (size_t)(sms > 0 ? sms : 148) * WAVE_MAX_WARPS * stride * sizeof(uint32_t);
 }
 
@@ -1027,14 +1031,14 @@ static int wave_setup(WaveParams &P, const tg_nw_scoring *sc, int max_n, int *C_
     int rc = wave_envelope(sc, &max_sp);
     if (rc != TG_OK) return rc;
     if (max_n < 1) return tg_set_err(TG_EINVAL, "max_n < 1");
-    P.scratch_stride = (int)(((size_t)max_n + 63) / 32 * 32);
-    P.row_cap = (max_n + 4 + 7) / 8 * 8;
+    P.scratch_stride = (int)(((size_t)max_n + 223) / 32 * 32);
+    P.row_cap = (max_n + 140 + 7) / 8 * 8;
     P.A = sc->alphabet; P.g = sc->gap; P.gr = sc->gap_right; P.right_free = (sc->gap_right != sc->gap);
     for (int a = 0; a < MAXA; a++)
         for (int b = 0; b < MAXA; b++)
             P.sp[a * MAXA + b] = (a < sc->alphabet && b < sc->alphabet) ? (uint8_t)(sc->sub[a * MAXA + b] - 2 * sc->gap) : 0;
     const int C = (g_wave_variant == 0 || g_wave_variant == 3) ? 16 : 8;
-    const size_t per_warp = (size_t)2 * (sc->alphabet + 1) * 32 * C + (size_t)P.row_cap * 2;
+    const size_t per_warp = (size_t)2 * (sc->alphabet + 1) * 32 * C + (size_t)P.row_cap * 2 + 512;
     int warps = (int)((226 * 1024 - MAXA * MAXA) / per_warp);
     if (warps > WAVE_MAX_WARPS) warps = WAVE_MAX_WARPS;
     if (g_wave_warps && warps > g_wave_warps) warps = g_wave_warps;
