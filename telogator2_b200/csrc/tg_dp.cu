@@ -124,6 +124,16 @@ __device__ __forceinline__ void sts64(uint32_t addr, uint2 v)
 {
     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
 }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
 {
     uint32_t v;
@@ -832,30 +842,58 @@ __global__ void __launch_bounds__(MT_THREADS) mt_sample_batch_kernel(const Strea
                 const int len = (rep & 1) ? d.m : d.n;
                 const uint8_t *src = P.pool + ((rep & 1) ? d.off_j : d.off_i);
                 uint8_t *garr = P.pool + dst;
-#define ARR(ix) (SMEM_POOL ? sp[ix] : garr[ix])
                 for (int x = 0; x < len; x++) { const uint8_t c = src[x]; if (SMEM_POOL) sp[x] = c; else garr[x] = c; }   // pool = list(population)
                 int i = 0;
-                while (i < len) {
-                    const uint32_t v = slot[kdraw];
-                    kdraw++;
-                    if (kdraw == 16) {
-                        kdraw = 0;
-                        grp++;
-                        if (grp >= ngroups) ok = false;                        // stream exhausted: flag it (results are discarded)
-                        slot4[0] = n0;
-                        slot4[1] = n1;
-                        const int gi = min(grp + 1, ngroups - 1);
-                        n0 = __ldcg(st + 2 * gi);
-                        n1 = __ldcg(st + 2 * gi + 1);
+                if (SMEM_POOL) {
+                    // tight loop on 32-bit shared addresses: ~20 instructions per draw
+                    const uint32_t arr_s = (uint32_t)__cvta_generic_to_shared(sp);
+                    const uint32_t slot_s = (uint32_t)__cvta_generic_to_shared(slot4);
+                    while (i < len) {
+                        uint32_t v;
+                        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(slot_s + 2 * kdraw) : "memory");
+                        kdraw++;
+                        if (kdraw == 16) {
+                            kdraw = 0;
+                            grp++;
+                            if (grp >= ngroups) ok = false;                    // stream exhausted: flag it (results are discarded)
+                            slot4[0] = n0;
+                            slot4[1] = n1;
+                            const int gi = min(grp + 1, ngroups - 1);
+                            n0 = __ldcg(st + 2 * gi);
+                            n1 = __ldcg(st + 2 * gi + 1);
+                        }
+                        // _randbelow(nn): k = nn.bit_length(); r = getrandbits(k) = top k bits of the 32-bit output.
+                        // result[i] = pool[j] goes to the vacated tail slot; a rejected draw swaps the tail with itself
+                        const uint32_t nn = (uint32_t)(len - i);
+                        const uint32_t r = v >> (__clz(nn) - 16);              // 16 - bit_length(nn)
+                        const uint32_t aj = arr_s + min(r, nn - 1u), at = arr_s + nn - 1u;
+                        const uint32_t t = lds_u8(aj), u = lds_u8(at);
+                        sts_u8(aj, u);                                         // pool[j] = pool[n-i-1]
+                        sts_u8(at, t);
+                        i += (r < nn) ? 1 : 0;
                     }
-                    // _randbelow(nn): k = nn.bit_length(); r = getrandbits(k) = top k bits of the 32-bit output.
-                    // result[i] = pool[j] goes to the vacated tail slot; a rejected draw swaps the tail with itself
-                    const uint32_t nn = (uint32_t)(len - i);
-                    const uint32_t r = v >> (__clz(nn) - 16);                  // 16 - bit_length(nn)
-                    const uint32_t j = min(r, nn - 1u);
-                    const uint8_t t = ARR(j), u = ARR(nn - 1u);
-                    if (SMEM_POOL) { sp[j] = u; sp[nn - 1u] = t; } else { garr[j] = u; garr[nn - 1u] = t; }
-                    i += (r < nn) ? 1 : 0;
+                } else {
+                    while (i < len) {
+                        const uint32_t v = slot[kdraw];
+                        kdraw++;
+                        if (kdraw == 16) {
+                            kdraw = 0;
+                            grp++;
+                            if (grp >= ngroups) ok = false;
+                            slot4[0] = n0;
+                            slot4[1] = n1;
+                            const int gi = min(grp + 1, ngroups - 1);
+                            n0 = __ldcg(st + 2 * gi);
+                            n1 = __ldcg(st + 2 * gi + 1);
+                        }
+                        const uint32_t nn = (uint32_t)(len - i);
+                        const uint32_t r = v >> (__clz(nn) - 16);
+                        const uint32_t j = min(r, nn - 1u);
+                        const uint8_t t = garr[j], u = garr[nn - 1u];
+                        garr[j] = u;
+                        garr[nn - 1u] = t;
+                        i += (r < nn) ? 1 : 0;
+                    }
                 }
                 __syncwarp(act);
                 if (SMEM_POOL) {
@@ -866,7 +904,6 @@ __global__ void __launch_bounds__(MT_THREADS) mt_sample_batch_kernel(const Strea
                         garr[x] = b; garr[len - 1 - x] = a;
                     }
                 }
-#undef ARR
                 dst += len;
             }
             if (!ok) atomicExch(P.overflow, 1);
