@@ -842,7 +842,22 @@ __global__ void __launch_bounds__(MT_THREADS) mt_sample_batch_kernel(const Strea
                 const int len = (rep & 1) ? d.m : d.n;
                 const uint8_t *src = P.pool + ((rep & 1) ? d.off_j : d.off_i);
                 uint8_t *garr = P.pool + dst;
-                for (int x = 0; x < len; x++) { const uint8_t c = src[x]; if (SMEM_POOL) sp[x] = c; else garr[x] = c; }   // pool = list(population)
+                // pool = list(population)
+                if (SMEM_POOL) {
+                    // aligned 32-bit loads + funnel shift (the source starts at an arbitrary byte; reading up to 3 bytes
+                    // past its end stays inside the pool allocation)
+                    const uint32_t *w = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)3);
+                    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3) * 8;
+                    uint32_t *d32 = reinterpret_cast<uint32_t *>(sp);
+                    uint32_t lo = __ldg(w);
+                    for (int q = 0; q * 4 < len; q++) {
+                        const uint32_t hi = __ldg(w + q + 1);
+                        d32[q] = __funnelshift_r(lo, hi, sh);
+                        lo = hi;
+                    }
+                } else {
+                    for (int x = 0; x < len; x++) garr[x] = src[x];
+                }
                 int i = 0;
                 if (SMEM_POOL) {
                     // tight loop on 32-bit shared addresses: ~20 instructions per draw

@@ -161,3 +161,30 @@ def test_c_abi_exports_every_declared_symbol_and_table_builder(kmer_tables):
         assert L.tg_device_sm_count(ctypes.byref(n)) == _lib.TG_ECUDA
         with pytest.raises(RuntimeError):
             _lib.require_cuda()
+
+
+def test_random_stream_capacity_covers_cpython_draw_counts():
+    """tg_dist_batch pre-generates ceil((1.6 * elements + 256) / 624) blocks of MT19937 output per pair
+    (mt_blocks_needed in tg_dp.cu).  Count the getrandbits() calls CPython's random.sample really makes."""
+    import random
+
+    class Counting(random.Random):
+        calls = 0
+
+        def getrandbits(self, k):
+            Counting.calls += 1
+            return super().getrandbits(k)
+
+    worst = 0.0
+    for n in (1, 2, 3, 17, 100, 511, 512, 513, 600, 724, 725, 1000, 1024, 1025, 1449, 2000, 3000, 4097, 5041):
+        for seed in range(6):
+            for R in (1, 2, 3):
+                rng = Counting(seed * 7919 + n)
+                Counting.calls = 0
+                for _ in range(2 * R):
+                    rng.sample(range(n), n)
+                total = 2 * R * n
+                cap = (total * 8 // 5 + 256 + 623) // 624 * 624
+                assert Counting.calls <= cap, (n, seed, R, Counting.calls, cap)
+                worst = max(worst, Counting.calls / cap)
+    assert worst < 0.97
