@@ -118,12 +118,18 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
-def ncu_traffic(kernel):
-    """dram read+write bytes per launch from the committed `ncu --set full` capture (profiles/), or None."""
+def ncu_traffic(kernel, units=None):
+    """dram read+write bytes per launch from the committed `ncu --set full` capture (profiles/r01_traffic.json).
+    Captures are taken on a smaller launch; for the scan the per-base figure is scaled to this launch."""
     p = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
-    if os.path.exists(p):
-        return json.load(open(p)).get(kernel)
-    return None
+    if not os.path.exists(p):
+        return None
+    e = json.load(open(p)).get(kernel)
+    if e is None:
+        return None
+    if units is not None and 'bytes_per_base' in e:
+        return {'bytes': e['bytes_per_base'] * units, 'how': f"{e['bytes_per_base']:.3f} B/base measured by ncu on {e['launch']}, scaled to this launch"}
+    return {'bytes': e['bytes_per_launch'], 'how': 'ncu capture of ' + e['launch']}
 
 
 def peaks():
@@ -390,7 +396,7 @@ def main():
         pk, src = peaks()
         ach = scan_bases * 2.375 / min(ds) / 1e9
         roof_scan = {'bound': 'hbm', 'kernel': 'scan_cov_kernel<density>', 'achieved': ach, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
-                     'frac': ach / pk['hbm_gbs'], 'traffic': ncu_traffic('scan_cov_kernel<density>'), 'peak_source': src, 'launch_ms': min(ds) * 1e3,
+                     'frac': ach / pk['hbm_gbs'], 'traffic': ncu_traffic('scan_cov_kernel<density>', scan_bases), 'peak_source': src, 'launch_ms': min(ds) * 1e3,
                      'bytes_per_base': 2.375, 'mbases_per_s': scan_bases / min(ds) / 1e6}
 
     # ---------------- e2e through the public API: host strings -> float32 matrix on the host --------
