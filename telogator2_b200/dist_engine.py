@@ -260,18 +260,17 @@ class DistEngine:
         cap -= cap % 2
         # pair ranges owned by this rank: blocks of sorted pair space dealt round-robin
         rank, world = shard if shard is not None else (0, 1)
-        if world > 1:
-            blk = max(4096, -(-n_pairs // (world * 8)))
-            blk += blk % 2
-            ranges = [(b, min(b + blk, n_pairs)) for b in range(rank * blk, n_pairs, world * blk)]
-        else:
-            ranges = [(0, n_pairs)]
+        ranges = fast_ranges(n_pairs, rank, world)
         cap = min(cap, max(2, max((e - b for b, e in ranges), default=2) + 1))
-        aln = np.full(n_pairs, NOT_COMPUTED, dtype=np.int32)
-        rnd = np.full((n_pairs, R), NOT_COMPUTED, dtype=np.int32)
-        iden = np.zeros(n_pairs, dtype=np.float64)
-        shape = np.zeros((n_pairs, 2), dtype=np.int32)
-        flags = np.zeros(n_pairs, dtype=np.uint8)
+        # results of this rank's ranges only, stored back to back ("compact"); expand_ranges() / gather_results()
+        # turn them into full-length arrays
+        n_own = sum(e - b for b, e in ranges)
+        range_pos = np.cumsum([0] + [e - b for b, e in ranges])
+        aln = np.full(n_own, NOT_COMPUTED, dtype=np.int32)
+        rnd = np.full((n_own, R), NOT_COMPUTED, dtype=np.int32)
+        iden = np.zeros(n_own, dtype=np.float64)
+        shape = np.zeros((n_own, 2), dtype=np.int32)
+        flags = np.zeros(n_own, dtype=np.uint8)
         # device state
         n_codes = len(codes)
         pool = torch.empty(n_codes + cap * slot + 64, dtype=torch.uint8, device=self.device)
@@ -293,7 +292,7 @@ class DistEngine:
                    for _ in range(1)] if streamed else [None]
         cstruct = self.sc.c_struct(sub)
         outs = []
-        for (rb, re_) in ranges:
+        for ri, (rb, re_) in enumerate(ranges):
             q = rb
             while q < re_:
                 q1 = min(re_, q + cap)
@@ -315,7 +314,8 @@ class DistEngine:
                 a.n_seq, a.adjust_lens, a.min_viable, a.R, a.max_len = n_seq, int(bool(adjust_lens)), int(bool(min_viable)), R, max_len
                 _lib.check(self.L.tg_dist_batch(C.byref(a), C.byref(cstruct), _lib.stream_ptr(torch)))
                 self.stats['launches'] += (6 if streamed else 4) if R else 2
-                outs.append((q, q1, d_aln, d_rnd, d_flags, d_iden, d_shape))
+                cpos = int(range_pos[ri]) + (q - rb)
+                outs.append((cpos, cpos + npb, d_aln, d_rnd, d_flags, d_iden, d_shape))
                 if len(outs) >= 2:                     # keep one batch in flight while the previous one is copied back
                     self._collect(outs.pop(0), aln, rnd, flags, iden, shape, R)
                 q = q1
@@ -331,7 +331,11 @@ class DistEngine:
         self.stats['early_out'] += int(flags[live].sum())
         self.stats['cells'] += int(cells[live].sum()) + R * int(cells[live & (flags == 0)].sum())
         self.stats['wave_jobs'] += int(live.sum())
-        return dict(aln=aln, rnd=rnd, iden=iden, n=shape[:, 0].copy(), m=shape[:, 1].copy(), order=order)
+        res = dict(aln=aln, rnd=rnd, iden=iden, n=shape[:, 0].copy(), m=shape[:, 1].copy(), order=order)
+        if world > 1:
+            res['ranges'] = ranges
+            res['n_pairs'] = n_pairs
+        return res
 
     def _collect(self, o, aln, rnd, flags, iden, shape, R):
         (q, q1, d_aln, d_rnd, d_flags, d_iden, d_shape) = o
@@ -492,6 +496,7 @@ class DistEngine:
             return D
         if res is None:
             res = self.pair_scores(sequences, adjust_lens, min_viable, R, rng_seed)
+        res = expand_ranges(res)
         d = self.distances(res, R)
         iu = np.triu_indices(n, k=1)                 # row-major upper triangle == combinations order
         if res.get('order') is not None:
@@ -502,8 +507,35 @@ class DistEngine:
         return D
 
 
+def fast_ranges(n_pairs, rank, world):
+    """Pair ranges (sorted pair space) owned by `rank`: the blocks DistEngine._pair_scores_fast deals round-robin."""
+    if world <= 1:
+        return [(0, n_pairs)]
+    blk = max(4096, -(-n_pairs // (world * 8)))
+    blk += blk % 2
+    return [(b, min(b + blk, n_pairs)) for b in range(rank * blk, n_pairs, world * blk)]
+
+
+def expand_ranges(res):
+    """Compact per-rank results (see _pair_scores_fast) -> full-length arrays, NOT_COMPUTED / 0 elsewhere."""
+    if 'ranges' not in res:
+        return res
+    n_pairs, ranges = res['n_pairs'], res['ranges']
+    out = {k: v for k, v in res.items() if k not in ('ranges', 'n_pairs')}
+    for key, fill in (('aln', NOT_COMPUTED), ('rnd', NOT_COMPUTED), ('iden', 0), ('n', 0), ('m', 0)):
+        src = res[key]
+        full = np.full((n_pairs,) + src.shape[1:], fill, dtype=src.dtype)
+        pos = 0
+        for (b, e) in ranges:
+            full[b:e] = src[pos:pos + (e - b)]
+            pos += e - b
+        out[key] = full
+    return out
+
+
 def canonical_order(res, n_seq):
     """Re-index a result dict to itertools.combinations order over the ORIGINAL sequence indices."""
+    res = expand_ranges(res)
     if res.get('order') is None:
         return res
     o = res['order'].astype(np.int64)

@@ -3,8 +3,8 @@
 Pairs are independent and a pair's RNG seed is a pure function of its global index
 (rng_seed + p, tg_align.py:157,170-172), so sharding cannot change any result.  Blocks of
 consecutive pair indices are dealt round-robin to the ranks (statistical cost balance); the only
-exchange step is the gather of the per-pair integer results, done as element-wise all-reduces over
-NCCL/NVLink (MAX for scores whose not-computed sentinel is INT32_MIN, SUM for the zero-filled rest)."""
+exchange step is the gather of the per-pair integer results over NCCL/NVLink: an all_gather of each rank's compact
+share (device-driven path) or element-wise all-reduces of full-length partial arrays (explicit-job path)."""
 import numpy as np
 
 SHARD_BLOCK = 4096
@@ -32,8 +32,36 @@ def _dist_state():
 
 
 def gather_results(res, dist, device):
-    """In-place element-wise merge of every rank's partial result dict."""
+    """Merge every rank's partial result dict into full-length arrays on every rank.
+    Compact results of the device-driven path (res['ranges']) are exchanged with all_gather (each rank's share,
+    padded to the longest); full-length partial results are merged with element-wise all-reduces."""
     import torch
+    if 'ranges' in res:
+        from .dist_engine import NOT_COMPUTED, fast_ranges
+        n_pairs = res['n_pairs']
+        world = dist.get_world_size()
+        all_ranges = [fast_ranges(n_pairs, r, world) for r in range(world)]
+        n_max = max(sum(e - b for b, e in rr) for rr in all_ranges)
+        out = {k: v for k, v in res.items() if k not in ('ranges', 'n_pairs')}
+        for key, fill in (('aln', NOT_COMPUTED), ('rnd', NOT_COMPUTED), ('iden', 0), ('n', 0), ('m', 0)):
+            src = np.ascontiguousarray(res[key])
+            if src.size == 0 and src.ndim > 1:
+                out[key] = np.full((n_pairs,) + src.shape[1:], fill, dtype=src.dtype)
+                continue
+            pad = np.full((n_max,) + src.shape[1:], fill, dtype=src.dtype)
+            pad[:len(src)] = src
+            mine = torch.from_numpy(pad).to(device)
+            parts = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(parts, mine)
+            full = np.full((n_pairs,) + src.shape[1:], fill, dtype=src.dtype)
+            for r in range(world):
+                part = parts[r].cpu().numpy()
+                pos = 0
+                for (b, e) in all_ranges[r]:
+                    full[b:e] = part[pos:pos + (e - b)]
+                    pos += e - b
+            out[key] = full
+        return out
     for key, op in (('aln', dist.ReduceOp.MAX), ('rnd', dist.ReduceOp.MAX), ('n', dist.ReduceOp.MAX),
                     ('m', dist.ReduceOp.MAX), ('iden', dist.ReduceOp.SUM)):
         arr = res[key]
