@@ -43,7 +43,7 @@ def lib():
         L.tgo_nw_score.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_double] * 5
         L.tgo_dist_matrix.restype = C.c_int
         L.tgo_dist_matrix.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_double] * 5 + \
-            [C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+            [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.tgo_shuffle_stream.restype = None
         L.tgo_shuffle_stream.argtypes = [C.c_uint64, C.c_int, C.POINTER(C.c_char_p), i32p, C.POINTER(C.c_void_p)]
         L.tgo_mt_base_table.argtypes = [C.c_void_p]
@@ -233,7 +233,7 @@ def dist_matrix_c(sequences, P, adjust_lens, min_viable, rand_shuffle_count, rng
     pb, pe = pair_range if pair_range is not None else (0, n_pairs)
     rc = lib().tgo_dist_matrix(_ptr(flat), _ptr(off), n, _ptr(P.S), 0 if P.S is None else P.S.shape[0],
                                P.match, P.mismatch, P.g, P.gl, P.gr, int(adjust_lens), int(min_viable),
-                               int(rand_shuffle_count), C.c_uint64(rng_seed), pb, pe,
+                               int(rand_shuffle_count), C.c_int64(rng_seed), pb, pe,
                                _ptr(D), _ptr(aln), _ptr(rnd), C.byref(cells), n_threads)
     if rc != 0:
         raise ValueError('sequence has zero length')

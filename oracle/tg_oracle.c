@@ -202,7 +202,7 @@ TGO_API double tgo_nw_score(const uint8_t *a, int n, const uint8_t *b, int m, co
 TGO_API int tgo_dist_matrix(const uint8_t *codes, const int64_t *off, int n_seq,
                             const double *S, int A, double match, double mismatch,
                             double g, double gl, double gr,
-                            int adjust_lens, int min_viable, int R, uint64_t rng_seed,
+                            int adjust_lens, int min_viable, int R, int64_t rng_seed,
                             int64_t pair_begin, int64_t pair_end,
                             float *dist, int32_t *aln_out, int32_t *rnd_out, double *cells_out,
                             int n_threads)
@@ -254,7 +254,8 @@ TGO_API int tgo_dist_matrix(const uint8_t *codes, const int64_t *off, int n_seq,
             if (aln < -(0.900 * iden)) {                                                      /* :137-138 */
                 d = 10.0;
             } else {
-                tgo_mt st; mt_seed_u64(&st, rng_seed + (uint64_t)p);                          /* :110-111, :157 */
+                const int64_t sv = rng_seed + p;                  /* random.seed(int) uses abs(seed) */
+                tgo_mt st; mt_seed_u64(&st, (uint64_t)(sv < 0 ? -sv : sv));                   /* :110-111, :157 */
                 double sum = 0.0;
                 for (int k = 0; k < R; k++) {                                                 /* :141-142 */
                     mt_shuffle_bytes(&st, a, li, si, pool);

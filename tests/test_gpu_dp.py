@@ -213,3 +213,40 @@ def test_full_size_properties(tga, colorvecs):
     for i, j in combinations(sub, 2):
         want = oracle.tvr_distance_py(seqs[i], seqs[j], P, True, True, 2, rng_seed=5 + index[(i, j)])
         assert D[i, j] == np.float32(want)
+
+
+def test_single_kernel_null_model_matches_streamed(tga, colorvecs):
+    """The all-in-one shuffle kernel (fallback of the streamed seed/stream/sample pipeline) gives the same bits."""
+    from telogator2_b200.dist_engine import DistEngine, Scoring, canonical_order
+    ont, hifi = _cases(colorvecs)
+    seqs = [c[:600 + 37 * i] for i, c in enumerate((ont + hifi)[:20])]
+    aligner = tga.get_aligner_object(tga.get_scoring_matrix('C', 'tvr'), (True, True), 'tvr')
+    a = DistEngine(Scoring.from_aligner(aligner), single_kernel_shuffle=True).pair_scores(seqs, True, False, 3, 99)
+    b = DistEngine(Scoring.from_aligner(aligner)).pair_scores(seqs, True, False, 3, 99)
+    for key in ('aln', 'rnd', 'n', 'm'):
+        assert np.array_equal(a[key], b[key]), key
+    _, aln, rnd, _ = oracle.dist_matrix_c(seqs, _P(oracle.scoring_matrix('C', 'tvr'), (True, True)), True, False, 3, 99, want_scores=True)
+    c = canonical_order(a, len(seqs))
+    assert np.array_equal(c['aln'], aln) and np.array_equal(c['rnd'], rnd)
+
+
+def test_unsupported_configurations_fail_loudly(tga):
+    from telogator2_b200.dist_engine import Scoring
+    al = tga.get_aligner_object(None, (True, True), 'msa')                  # affine gaps: MSA half only
+    with pytest.raises(NotImplementedError):
+        tga.get_dist_matrix_parallel(['CCD', 'CDD'], al, True, True, 1)
+    m = tga.get_scoring_matrix('C', 'tvr')
+    m['D', 'D'] = 4.5
+    with pytest.raises(NotImplementedError):
+        Scoring.from_aligner(tga.get_aligner_object(m, (True, True), 'tvr'))
+    with pytest.raises(SystemExit):
+        tga.get_scoring_matrix('C', 'nope')
+    with pytest.raises(SystemExit):
+        tga.get_aligner_object(None, (True, True), 'nope')
+
+
+def test_negative_and_large_seeds(tga, colorvecs):
+    ont, _ = _cases(colorvecs)
+    seqs = [c[:500] for c in ont[:6]]
+    for seed in (-12345, 0, 2 ** 40 + 7):
+        _check_matrix(tga, seqs, 'tvr', (True, True), True, False, 2, seed)

@@ -136,3 +136,31 @@ def test_scale_properties(tgk, kmer_tables, golden_reads):
         assert np.array_equal(ca[q], ca[q % len(base)])
     bc = pr.basecount(KL, KL_REV).cpu().numpy()
     assert np.array_equal(bc[:len(base)], bc[-len(base):])
+
+
+def test_limits_fail_loudly(tgk, kmer_tables):
+    T = kmer_tables['human_hifi']
+    KL = T['KMER_LIST']
+    pr = tgk.PackedReads(['CCCTAA' * 100])
+    with pytest.raises(Exception):
+        pr.density_counts(KL, KL, 256)                         # uint8 counts: window <= 255
+    with pytest.raises(NotImplementedError):
+        tgk.get_telomere_kmer_density('CCCTAA' * 100, KL, 100, smoothing=True)
+    with pytest.raises(NotImplementedError):
+        tgk.kmer_table(['ACGT' + format(i, '06b').replace('0', 'A').replace('1', 'C') for i in range(65)])
+    with pytest.raises(Exception):
+        tgk.kmer_table(['ACGT' * 9])                           # 36 > 32 bases
+    with pytest.raises(Exception):
+        tgk.kmer_table(['ACNT'])
+
+
+def test_window_and_short_reads(tgk, kmer_tables):
+    T = kmer_tables['maize_hifi']
+    KL = T['KMER_LIST']
+    reads = ['', 'C', 'CCCTAAA', 'CCCTAAA' * 14 + 'CC', 'CCCTAAA' * 15, 'CCCTAAA' * 40]
+    pr = tgk.PackedReads(reads)
+    for w in (1, 3, 100, 255):
+        ca, cb = pr.density_counts(KL, [tgk.RC(k) for k in KL], w)
+        ca = pr.split_counts(ca.cpu().numpy(), w)
+        for q, r in enumerate(reads):
+            assert np.array_equal(ca[q].astype(np.int32), oracle.density_counts(r, KL, w)), (q, w)

@@ -118,3 +118,10 @@ def test_dist_matrix_c_matches_python_and_golden(colorvecs, dp_golden):
     pairs = list(combinations(range(5), 2))
     for p, (i, j) in enumerate(pairs):
         assert Dpart[i, j] == (Dc[i, j] if 2 <= p < 5 else 0)
+
+
+def test_dist_matrix_c_negative_seed_uses_abs_like_cpython(colorvecs):
+    seqs = [c[:300] for c in colorvecs['colorvecs']['human_ont']][:5]
+    P = oracle.AlignerParams(oracle.scoring_matrix('C', 'tvr'), (True, True))
+    for seed in (-12345, -3, 2 ** 40 + 7):
+        assert np.array_equal(oracle.dist_matrix_py(seqs, P, True, False, 2, seed), oracle.dist_matrix_c(seqs, P, True, False, 2, seed))
