@@ -27,7 +27,8 @@ constexpr int SC_MAXLIST = 64;
 constexpr int SC_MAXLEN = 32;
 constexpr int SC_MAXSTATES = 4095;
 constexpr int SC_MAXBORD = 32;
-constexpr uint16_t SC_OUT_FLAG = 0x8000;
+constexpr uint32_t SC_BORD_FLAG = 0x1000;   // transition entry: next state has self-overlapping k-mer outputs
+constexpr uint32_t SC_OUT_FLAG = 0x2000;    // transition entry: next state has any output
 
 // One automaton for one k-mer list (hits) or for two lists at once ("groups" 0 and 1: KMER_LIST and
 // KMER_LIST_REV, or CANONICAL_STRINGS and their reverse complements).
@@ -43,8 +44,9 @@ struct KmerTable {
     uint64_t lengt[SC_MAXLEN];              // lengt[d] = group-0 k-mers with len > d
     uint64_t bord_mask;                     // bordered group-0 k-mers
     uint64_t has_super_mask;                // group-0 k-mers with a non-empty super[]
-    uint16_t trans[(SC_MAXSTATES + 1) * 4]; // next state (low 12 bits) | SC_OUT_FLAG
-    uint16_t out_len[SC_MAXSTATES + 1];     // longest NON-bordered k-mer starting here: group 0 low byte, group 1 high byte
+    // transition entry: bits 0-11 next state | SC_BORD_FLAG | SC_OUT_FLAG | byte 2 = longest NON-bordered group-0 k-mer
+    // starting at the next state | byte 3 = same for group 1 (so the common case needs no second table lookup)
+    uint32_t trans[(SC_MAXSTATES + 1) * 4];
     uint32_t out_bord[SC_MAXSTATES + 1];    // bordered slots starting here
     uint64_t out_mask[SC_MAXSTATES + 1];    // group-0 k-mers starting here
 };
@@ -144,8 +146,7 @@ __device__ __forceinline__ void smem_byte_max(uint8_t *arr, int idx, uint32_t va
 
 // Device-side view of one automaton held in shared memory.
 struct SmemTable {
-    const uint16_t *trans;
-    const uint16_t *out_len;
+    const uint32_t *trans;
     const uint32_t *out_bord;
     const uint64_t *out_mask;     // only in hits mode
     int max_len, n_bord;
@@ -161,20 +162,25 @@ __device__ __forceinline__ uint8_t *carve(uint8_t *&p, size_t bytes)
 __device__ SmemTable load_table(const KmerTable *__restrict__ T, uint8_t *&sp, bool want_mask)
 {
     const int ns = T->n_states;
-    uint16_t *tr = reinterpret_cast<uint16_t *>(carve(sp, (size_t)ns * 4 * sizeof(uint16_t)));
-    uint16_t *ol = reinterpret_cast<uint16_t *>(carve(sp, (size_t)ns * sizeof(uint16_t)));
+    uint32_t *tr = reinterpret_cast<uint32_t *>(carve(sp, (size_t)ns * 4 * sizeof(uint32_t)));
     uint32_t *ob = reinterpret_cast<uint32_t *>(carve(sp, (size_t)ns * sizeof(uint32_t)));
     uint64_t *om = want_mask ? reinterpret_cast<uint64_t *>(carve(sp, (size_t)ns * sizeof(uint64_t))) : nullptr;
     for (int i = threadIdx.x; i < ns * 4; i += blockDim.x) tr[i] = T->trans[i];
     for (int i = threadIdx.x; i < ns; i += blockDim.x) {
-        ol[i] = T->out_len[i];
         ob[i] = T->out_bord[i];
         if (want_mask) om[i] = T->out_mask[i];
     }
     SmemTable S;
-    S.trans = tr; S.out_len = ol; S.out_bord = ob; S.out_mask = om;
+    S.trans = tr; S.out_bord = ob; S.out_mask = om;
     S.max_len = T->max_len; S.n_bord = T->n_bord;
     return S;
+}
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
 }
 
 // ---- coverage kernel (base count / density) -------------------------------------------------------
@@ -305,46 +311,51 @@ __global__ void __launch_bounds__(COV_THREADS, 5) scan_cov_kernel(const CovParam
         if (tid < SC_MAXBORD) s_any[tid] = 0;
         __syncthreads();
 
-        // ---- phase B: one automaton for both lists, right to left over [c0, c0 + CH + max_len - 1) ----
+        // ---- phase B: one automaton for both lists, right to left: 32 warm-up positions, then the 64 of this chunk.
+        //      The transition entry carries the two lists' match lengths in its upper bytes; PRMT packs four
+        //      positions' worth of them into the L words (byte = longest k-mer starting at that position). ----
         {
             const int c0 = tid * COV_CH;
             uint32_t state = 0;
-            int x = c0 + COV_CH + T.max_len - 2;
-            for (; x >= c0 + COV_CH; x--) {                           // warm-up, no output
-                const uint32_t isn = (s_mask[midx(x >> 5)] >> (x & 31)) & 1u;
-                const uint32_t code = (s_pack[pidx(x >> 4)] >> ((x & 15) * 2)) & 3u;
-                state = isn ? 0u : ((uint32_t)T.trans[state * 4 + code] & 0xfffu);
+#pragma unroll 1
+            for (int wd = 5; wd >= 4; wd--) {                         // warm-up, no output
+                const uint32_t pw = s_pack[pidx((c0 >> 4) + wd)];
+                const uint32_t mw = s_mask[midx((c0 >> 5) + (wd >> 1))] >> ((wd & 1) * 16);
+#pragma unroll
+                for (int k = 15; k >= 0; k--) {
+                    const uint32_t e = T.trans[state * 4 + ((pw >> (2 * k)) & 3u)];
+                    state = ((mw >> k) & 1u) ? 0u : (e & 0xfffu);
+                }
             }
 #pragma unroll 1
             for (int wd = 3; wd >= 0; wd--) {                         // 4 words of 16 positions
                 const uint32_t pw = s_pack[pidx((c0 >> 4) + wd)];
                 const uint32_t mw = s_mask[midx((c0 >> 5) + (wd >> 1))] >> ((wd & 1) * 16);
-                uint32_t l0 = 0, l1 = 0;                              // 4 L bytes per list being assembled
 #pragma unroll
-                for (int k = 15; k >= 0; k--) {
-                    const uint32_t code = (pw >> (2 * k)) & 3u;
-                    const uint32_t e = ((mw >> k) & 1u) ? 0u : (uint32_t)T.trans[state * 4 + code];
-                    state = e & 0xfffu;
-                    uint32_t ol = 0;
-                    if (e & SC_OUT_FLAG) {
-                        ol = T.out_len[state];
-                        uint32_t ob = T.out_bord[state];
-                        while (ob) {
-                            const int b = __ffs(ob) - 1;
-                            ob &= ob - 1;
+                for (int q = 3; q >= 0; q--) {
+                    uint32_t ev[4];
+#pragma unroll
+                    for (int t = 3; t >= 0; t--) {
+                        const int k = 4 * q + t;
+                        uint32_t e = T.trans[state * 4 + ((pw >> (2 * k)) & 3u)];
+                        if ((mw >> k) & 1u) e = 0u;
+                        state = e & 0xfffu;
+                        ev[t] = e;
+                        if (e & SC_BORD_FLAG) {
+                            uint32_t ob = T.out_bord[state];
                             const int xr = c0 + wd * 16 + k;
-                            atomicOr(&s_bm[b * (COV_REGION / 32) + (xr >> 5)], 1u << (xr & 31));
-                            s_any[b] = 1;
+                            while (ob) {
+                                const int b = __ffs(ob) - 1;
+                                ob &= ob - 1;
+                                atomicOr(&s_bm[b * (COV_REGION / 32) + (xr >> 5)], 1u << (xr & 31));
+                                s_any[b] = 1;
+                            }
                         }
                     }
-                    l0 = (l0 << 8) | (ol & 0xffu);                    // k descending: byte 0 ends up = lowest position
-                    l1 = (l1 << 8) | (ol >> 8);
-                    if ((k & 3) == 0) {
-                        const int xb = c0 + wd * 16 + k;
-                        *reinterpret_cast<uint32_t *>(s_L[0] + lidx(xb)) = l0;
-                        *reinterpret_cast<uint32_t *>(s_L[1] + lidx(xb)) = l1;
-                        l0 = l1 = 0;
-                    }
+                    const uint32_t t01 = prmt(ev[0], ev[1], 0x7362u), t23 = prmt(ev[2], ev[3], 0x7362u);
+                    const int xb = c0 + wd * 16 + 4 * q;
+                    *reinterpret_cast<uint32_t *>(s_L[0] + lidx(xb)) = prmt(t01, t23, 0x5410u);
+                    *reinterpret_cast<uint32_t *>(s_L[1] + lidx(xb)) = prmt(t01, t23, 0x7632u);
                 }
             }
         }
@@ -387,29 +398,39 @@ __global__ void __launch_bounds__(COV_THREADS, 5) scan_cov_kernel(const CovParam
         }
         __syncthreads();
 
-        // ---- phase D: coverage bits = prefix max of (x + L[x]) over the region ----
+        // ---- phase D: coverage bits = prefix max of (x + L[x]) over the region, both lists at once in u16x2:
+        //      e = max(e, x + L[x]); covered(x) = e > x  (a position without a match contributes x, which never covers) ----
         {
             const int c0 = tid * COV_CH;
-            uint32_t cw[2][2];
+            uint32_t cw[2][2] = {{0u, 0u}, {0u, 0u}};
             int lm[2];
-#pragma unroll
-            for (int s = 0; s < 2; s++) {
-                int e = 0;
-                uint32_t c_lo = 0, c_hi = 0;
+            {
+                uint32_t e2 = 0u, acc = 0u;
+                uint32_t pp = (uint32_t)c0 * 0x00010001u;
 #pragma unroll
                 for (int q = 0; q < COV_CH / 4; q++) {
-                    const uint32_t l4 = *reinterpret_cast<const uint32_t *>(s_L[s] + lidx(c0 + q * 4));
+                    const uint32_t l0 = *reinterpret_cast<const uint32_t *>(s_L[0] + lidx(c0 + q * 4));
+                    const uint32_t l1 = *reinterpret_cast<const uint32_t *>(s_L[1] + lidx(c0 + q * 4));
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
-                        const int i = q * 4 + k;
-                        const int Lh = (l4 >> (8 * k)) & 0xff;
-                        e = max(e, Lh ? c0 + i + Lh : 0);
-                        const uint32_t bit = (e > c0 + i) ? 1u : 0u;
-                        if (i < 32) c_lo |= bit << i; else c_hi |= bit << (i - 32);
+                        // byte k of l0 -> low half, byte k of l1 -> high half (upper bytes = replicated sign bit = 0)
+                        const uint32_t sel = k | ((k | 8) << 4) | ((4 + k) << 8) | (((4 + k) | 8) << 12);
+                        const uint32_t pair = prmt(l0, l1, sel);
+                        e2 = __vmaxu2(e2, pair + pp);
+                        acc = acc * 2u + __vminu2(e2 - pp, 0x00010001u);      // 1 per half where e > x
+                        pp += 0x00010001u;
+                    }
+                    if ((q & 3) == 3) {
+                        // 16 positions accumulated MSB first
+                        const uint32_t b0 = __brev(acc << 16), b1 = __brev(acc & 0xffff0000u);
+                        const int j = q >> 2;                                    // 16-bit group 0..3
+                        cw[0][j >> 1] |= b0 << ((j & 1) * 16);
+                        cw[1][j >> 1] |= b1 << ((j & 1) * 16);
+                        acc = 0u;
                     }
                 }
-                cw[s][0] = c_lo; cw[s][1] = c_hi;
-                lm[s] = e;
+                lm[0] = (int)(e2 & 0xffffu);
+                lm[1] = (int)(e2 >> 16);
             }
             int inc[2] = {lm[0], lm[1]};
 #pragma unroll
@@ -484,12 +505,26 @@ __global__ void __launch_bounds__(COV_THREADS, 5) scan_cov_kernel(const CovParam
                         uint64_t sb = ((uint64_t)cv[jb >> 5] | ((uint64_t)cv[(jb >> 5) + 1] << 32)) >> (jb & 31);
                         if (jb & 31) sb |= (uint64_t)cv[min((jb >> 5) + 2, COV_REGION / 32)] << (64 - (jb & 31));
                         uint32_t outw[COV_CH / 4];
+                        if (w >= 4) {
+                            // four outputs per step, one byte each: cnt(i + t) = cnt(i) + sum_{u < t} (in_u - out_u).
+                            // nibble -> 4 bytes of 0/1 (multiply spreads the bits), * 0x01010101 = inclusive byte prefix sums;
+                            // subtracting first never borrows (the leaving bits are inside the current window)
 #pragma unroll
-                        for (int q = 0; q < COV_CH / 4; q++) outw[q] = 0u;
+                            for (int gq = 0; gq < COV_CH / 4; gq++) {
+                                const uint32_t nin = (uint32_t)(sb >> (4 * gq)) & 0xfu, nout = (uint32_t)(sa >> (4 * gq)) & 0xfu;
+                                const uint32_t A = ((nin * 0x00204081u) & 0x01010101u) * 0x01010101u;
+                                const uint32_t B = ((nout * 0x00204081u) & 0x01010101u) * 0x01010101u;
+                                outw[gq] = (uint32_t)cnt * 0x01010101u - (B << 8) + (A << 8);
+                                cnt += (int)(A >> 24) - (int)(B >> 24);
+                            }
+                        } else {
 #pragma unroll
-                        for (int ii = 0; ii < COV_CH; ii++) {
-                            outw[ii >> 2] |= (uint32_t)cnt << ((ii & 3) * 8);
-                            cnt += (int)((sb >> ii) & 1ull) - (int)((sa >> ii) & 1ull);
+                            for (int q = 0; q < COV_CH / 4; q++) outw[q] = 0u;
+#pragma unroll
+                            for (int ii = 0; ii < COV_CH; ii++) {
+                                outw[ii >> 2] |= (uint32_t)cnt << ((ii & 3) * 8);
+                                cnt += (int)((sb >> ii) & 1ull) - (int)((sa >> ii) & 1ull);
+                            }
                         }
                         uint8_t *dst = P.cnt[s] + rbase + i0;
 #pragma unroll
@@ -607,14 +642,14 @@ __global__ void __launch_bounds__(HIT_THREADS) hits_survivors_kernel(const HitPa
                     if (x < HIT_STAGE) {
                         const uint32_t isn = (s_mask[x >> 5] >> (x & 31)) & 1u;
                         const uint32_t code = (s_pack[x >> 4] >> ((x & 15) * 2)) & 3u;
-                        e = isn ? 0u : (uint32_t)T.trans[state * 4 + code];
+                        e = isn ? 0u : T.trans[state * 4 + code];
                     }
                     state = e & 0xfffu;
                     if (x < c0 + HIT_CH) {
                         unsigned long long hm = 0ull;
                         if (e & SC_OUT_FLAG) {
                             hm = T.out_mask[state];
-                            uint32_t ob = T.out_bord[state];
+                            uint32_t ob = (e & SC_BORD_FLAG) ? T.out_bord[state] : 0u;
                             while (ob) {
                                 const int b = __ffs(ob) - 1;
                                 ob &= ob - 1;
@@ -850,6 +885,7 @@ static int build_table(const std::vector<std::string> &km, int KA, const int32_t
         }
     }
     T->n_states = (int)nodes.size();
+    std::vector<uint32_t> out_len(nodes.size(), 0u);     // byte 0: group 0, byte 1: group 1
     for (int s = 0; s < T->n_states; s++) {
         T->out_mask[s] = nodes[s].out[0];
         int best[2] = {0, 0};
@@ -861,13 +897,14 @@ static int build_table(const std::vector<std::string> &km, int KA, const int32_t
             for (int b = 0; b < T->n_bord; b++) if (T->bord_kmer[b] == k) { ob |= 1u << b; is_bord = true; }
             if (!is_bord && T->len[k] > best[grp]) best[grp] = T->len[k];
         }
-        T->out_len[s] = (uint16_t)(best[0] | (best[1] << 8));
+        out_len[s] = (uint32_t)best[0] | ((uint32_t)best[1] << 8);
         T->out_bord[s] = ob;
     }
     for (int s = 0; s < T->n_states; s++)
         for (int c = 0; c < 4; c++) {
             const int v = nodes[s].next[c];
-            T->trans[s * 4 + c] = (uint16_t)(v | ((nodes[v].out[0] | nodes[v].out[1]) ? SC_OUT_FLAG : 0));
+            T->trans[s * 4 + c] = (uint32_t)v | (T->out_bord[v] ? SC_BORD_FLAG : 0u) |
+                                  ((nodes[v].out[0] | nodes[v].out[1]) ? SC_OUT_FLAG : 0u) | (out_len[v] << 16);
         }
     return TG_OK;
 }
@@ -933,7 +970,7 @@ static int table_dims(const void *d_table, int *n_states, int *n_bord, cudaStrea
 static size_t table_smem(int n_states, bool want_mask)
 {
     auto up = [](size_t b) { return (b + 15) & ~(size_t)15; };
-    return up((size_t)n_states * 8) + up((size_t)n_states * 2) + up((size_t)n_states * 4) + (want_mask ? up((size_t)n_states * 8) : 0);
+    return up((size_t)n_states * 16) + up((size_t)n_states * 4) + (want_mask ? up((size_t)n_states * 8) : 0);
 }
 
 TG_EXPORT int tg_scan_pack(const uint8_t *d_ascii, const int64_t *d_base_off, const int32_t *d_len, int n_reads,
