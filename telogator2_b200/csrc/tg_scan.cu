@@ -575,6 +575,7 @@ __global__ void __launch_bounds__(HIT_THREADS) hits_survivors_kernel(const HitPa
     uint32_t *s_bm = reinterpret_cast<uint32_t *>(carve(sp, (size_t)max(T.n_bord, 1) * ((HIT_TILE + HIT_HALO) / 32) * 4));
     __shared__ int s_blocked[SC_MAXBORD];
     __shared__ int s_any[SC_MAXBORD];
+    __shared__ unsigned long long s_shalo[HIT_HALO];
     __shared__ unsigned long long s_super[SC_MAXLIST], s_lengt[SC_MAXLEN];
     __shared__ int s_len[SC_MAXLIST];
     __shared__ unsigned int s_slice;
@@ -603,7 +604,7 @@ __global__ void __launch_bounds__(HIT_THREADS) hits_survivors_kernel(const HitPa
         const int wlen = (int)(P.work_off[q + 1] - woff);        // padded to 64
         const int n_tiles = (wlen + HIT_TILE - 1) / HIT_TILE;
         if (tid < SC_MAXBORD) s_blocked[tid] = 0;
-        for (int i = tid; i < HIT_HALO; i += HIT_THREADS) s_hm[i] = 0ull;      // left halo of the first tile
+        for (int i = tid; i < HIT_HALO; i += HIT_THREADS) { s_hm[i] = 0ull; s_shalo[i] = 0ull; }   // left halos of the first tile
 
         for (int tile = 0; tile < n_tiles; tile++) {
             const int t0 = tile * HIT_TILE;                     // slice-relative
@@ -703,7 +704,9 @@ __global__ void __launch_bounds__(HIT_THREADS) hits_survivors_kernel(const HitPa
             __syncthreads();
 
             // ---- survivors: drop (k, x) if a selected match of a superstring k-mer overlaps [x, x + len_k) ----
-            for (int x = tid; x < HIT_TILE; x += HIT_THREADS) {
+#pragma unroll 1
+            for (int it = 0; it < HIT_CH; it++) {
+                const int x = tid + it * HIT_THREADS;
                 unsigned long long hm = s_hm[HIT_HALO + x];
                 unsigned long long cand = hm & has_super;
                 while (cand) {
@@ -731,57 +734,63 @@ __global__ void __launch_bounds__(HIT_THREADS) hits_survivors_kernel(const HitPa
                 if (t0 + x < wlen) P.S[woff + t0 + x] = hm;
             }
             __syncthreads();
-            // carry the last HALO positions of hm as the next tile's left halo
+            // the raw matches are no longer needed (except the halo of the next tile): overwrite them with the
+            // survivors so that block starts can be decided here (tg_kmer.py:206-212): k starts a block at x unless
+            // it also survived at x - len_k
             unsigned long long keep = 0ull;
             if (tid < HIT_HALO) keep = s_hm[HIT_TILE + tid];
             __syncthreads();
-            if (tid < HIT_HALO) s_hm[tid] = keep;
+            // (each thread re-reads the survivors it just wrote; they are still in L2)
+#pragma unroll 4
+            for (int it = 0; it < HIT_CH; it++) {
+                const int x = tid + it * HIT_THREADS;
+                s_hm[HIT_HALO + x] = (t0 + x < wlen) ? P.S[woff + t0 + x] : 0ull;
+            }
+            if (tid < HIT_HALO) s_hm[tid] = s_shalo[tid];          // survivors of the previous tile's last positions
+            __syncthreads();
+#pragma unroll 1
+            for (int it = 0; it < HIT_CH; it++) {
+                const int x = tid + it * HIT_THREADS;
+                unsigned long long sv = s_hm[HIT_HALO + x];
+                bool start = false;
+                while (sv) {
+                    const int k = __ffsll((long long)sv) - 1;
+                    sv &= sv - 1;
+                    if (!((s_hm[HIT_HALO + x - s_len[k]] >> k) & 1ull)) start = true;
+                }
+                const uint32_t bal = __ballot_sync(TG_FULL_MASK, start);
+                if (lane == 0 && t0 + x < wlen) P.B[(woff + t0 + x) >> 5] = bal;
+            }
+            __syncthreads();
+            if (tid < HIT_HALO) {
+                s_shalo[tid] = s_hm[HIT_TILE + tid];               // survivors at tile positions TILE-32 .. TILE-1
+                s_hm[tid] = keep;                                  // raw left halo of the next tile
+            }
         }
     }
 }
 
-// H2: block starts after collapsing abutting same-k-mer survivors (tg_kmer.py:206-212)
-__global__ void __launch_bounds__(256) hits_blockstart_kernel(const HitParams P)
-{
-    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < P.total_work; g += (int64_t)gridDim.x * blockDim.x) {
-        const int q = find_read(P.work_off, P.n_slices, g);
-        const int x = (int)(g - P.work_off[q]);
-        unsigned long long s = P.S[g];
-        bool start = false;
-        while (s) {
-            const int k = __ffsll((long long)s) - 1;
-            s &= s - 1;
-            const int lk = P.tab->len[k];
-            if (x - lk < 0 || !((P.S[g - lk] >> k) & 1ull)) start = true;
-        }
-        const uint32_t bal = __ballot_sync(TG_FULL_MASK, start);
-        if ((threadIdx.x & 31) == 0) P.B[g >> 5] = bal;
-    }
-}
-
-// H3: walk each block to its end, truncate at the next block start of any k-mer (tg_kmer.py:216-228), emit
+// H2: one thread per word of the block-start plane: walk each block to its end, truncate at the next block start
+// of any k-mer (tg_kmer.py:216-228), emit.  Only positions with a block start touch the survivor masks.
 __global__ void __launch_bounds__(256) hits_emit_kernel(const HitParams P)
 {
-    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < P.total_work; g += (int64_t)gridDim.x * blockDim.x) {
-        unsigned long long s = P.S[g];
-        if (!s) continue;
-        const int q = find_read(P.work_off, P.n_slices, g);
+    const int64_t n_words = P.total_work >> 5;
+    for (int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; wi < n_words; wi += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t bw = P.B[wi];
+        if (!bw) continue;
+        const int q = find_read(P.work_off, P.n_slices, wi << 5);
         const int64_t woff = P.work_off[q];
-        const int x = (int)(g - woff);
         const int wlen = (int)(P.work_off[q + 1] - woff);
-        int next_start = -2;                                        // lazily computed
-        while (s) {
-            const int k = __ffsll((long long)s) - 1;
-            s &= s - 1;
-            const int lk = P.tab->len[k];
-            if (x - lk >= 0 && ((P.S[g - lk] >> k) & 1ull)) continue;      // not a block start
-            int e = x + lk;
-            while (e < wlen && ((P.S[woff + e] >> k) & 1ull)) e += lk;
-            if (next_start == -2) {
-                next_start = -1;
-                // first set bit of B strictly after x (within this slice)
+        const int wend = wlen >> 5;
+        while (bw) {
+            const int bit = __ffs(bw) - 1;
+            bw &= bw - 1;
+            const int64_t g = (wi << 5) + bit;
+            const int x = (int)(g - woff);
+            // first set bit of B strictly after x (within this slice)
+            int next_start = -1;
+            {
                 int wd = (x + 1) >> 5;
-                const int wend = wlen >> 5;
                 uint32_t v = (wd < wend) ? (P.B[(woff >> 5) + wd] & (0xffffffffu << ((x + 1) & 31))) : 0u;
                 while (wd < wend) {
                     if (v) { next_start = wd * 32 + __ffs(v) - 1; break; }
@@ -789,10 +798,19 @@ __global__ void __launch_bounds__(256) hits_emit_kernel(const HitParams P)
                     if (wd < wend) v = P.B[(woff >> 5) + wd];
                 }
             }
-            if (next_start >= 0 && next_start < e) e = next_start;
-            const unsigned long long slot = atomicAdd(P.span_count, 1ULL);
-            if ((long long)slot < P.span_cap) {
-                P.span_slice[slot] = q; P.span_k[slot] = k; P.span_start[slot] = x; P.span_end[slot] = e;
+            unsigned long long s = P.S[g];
+            while (s) {
+                const int k = __ffsll((long long)s) - 1;
+                s &= s - 1;
+                const int lk = P.tab->len[k];
+                if (x - lk >= 0 && ((P.S[g - lk] >> k) & 1ull)) continue;      // not a block start
+                int e = x + lk;
+                while (e < wlen && (next_start < 0 || e < next_start) && ((P.S[woff + e] >> k) & 1ull)) e += lk;
+                if (next_start >= 0 && next_start < e) e = next_start;
+                const unsigned long long slot = atomicAdd(P.span_count, 1ULL);
+                if ((long long)slot < P.span_cap) {
+                    P.span_slice[slot] = q; P.span_k[slot] = k; P.span_start[slot] = x; P.span_end[slot] = e;
+                }
             }
         }
     }
@@ -1118,9 +1136,7 @@ TG_EXPORT int tg_scan_hits(const uint32_t *d_pack2, const uint32_t *d_nmask, con
     if (grid > n_slices) grid = n_slices;
     hits_survivors_kernel<<<grid, HIT_THREADS, smem, st>>>(P);
     TG_CUDA_CHECK(cudaGetLastError());
-    const int g2 = grid_for(total_work_bases, 256, sms, 16);
-    hits_blockstart_kernel<<<g2, 256, 0, st>>>(P);
-    TG_CUDA_CHECK(cudaGetLastError());
+    const int g2 = grid_for(total_work_bases / 32, 256, sms, 16);
     hits_emit_kernel<<<g2, 256, 0, st>>>(P);
     TG_CUDA_CHECK(cudaGetLastError());
     return TG_OK;
