@@ -238,7 +238,7 @@ def main():
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     from telogator2_b200 import tg_align, tg_kmer
     from telogator2_b200.dist_engine import DistEngine, Scoring
-    from telogator2_b200.multi_gpu import shard_pair_indices, gather_results
+    from telogator2_b200.multi_gpu import shard_pair_indices, reduce_matrix, sharded_dist_matrix
 
     cv, reads, tables = load_fixtures()
     # weak scaling: the pair space grows with the number of GPUs (n_seq * sqrt(world)), each rank owns 1/world of it
@@ -262,13 +262,19 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- DP: device-resident timing ----------------
+    # the encoded sequences are resident in HBM before the timed region; a step = every kernel of every batch of this
+    # rank's pair ranges + the float epilogue into the device matrix (+ the matrix all_reduce over NVLink when world > 1)
     eng = DistEngine(Scoring.from_aligner(aligner))
+    dp_state = eng.prepare(seqs)
+    assert dp_state is not None
 
     def dp_step():
         eng.stats['cells'] = 0
         eng.stats['launches'] = 0
-        res = eng.pair_scores(seqs, True, True, R, SEED, shard=(rank, world))
-        return res
+        D = eng.matrix_device(dp_state, True, True, R, SEED, shard=(rank, world) if world > 1 else None)
+        if world > 1:
+            reduce_matrix(D, dist)
+        return D
 
     # ---------------- scan: device-resident timing ----------------
     pr = tg_kmer.PackedReads(scan_reads)
@@ -400,30 +406,31 @@ def main():
                      'bytes_per_base': 2.375, 'mbases_per_s': scan_bases / min(ds) / 1e6}
 
     # ---------------- e2e through the public API: host strings -> float32 matrix on the host --------
+    # (the body of tg_align.get_dist_matrix_parallel, with the engine kept to read its byte counters)
     e2e_ms = []
     h2d = d2h = 0
     for it in range(2):
         barrier()
         t0 = time.perf_counter()
         eng2 = DistEngine(Scoring.from_aligner(aligner))
-        res = eng2.pair_scores(seqs, True, True, R, SEED, shard=(rank, world))
-        if world > 1:
-            res = gather_results(res, dist, eng2.device)
-        D = eng2.dist_matrix(seqs, True, True, R, SEED, res=res)
+        D = sharded_dist_matrix(eng2, seqs, True, True, R, SEED)
         barrier()
         e2e_ms.append((time.perf_counter() - t0) * 1e3)
         h2d, d2h = eng2.stats['h2d_bytes'], eng2.stats['d2h_bytes']
     verified = None
     if world > 1 and rank == 0:
-        # cross-check the gathered multi-GPU result on a sample of pairs recomputed locally through the
-        # explicit-job path (same global pair indices -> same seeds)
-        from telogator2_b200.dist_engine import canonical_order
+        # cross-check the reduced multi-GPU matrix on a sample of pairs recomputed locally through the
+        # explicit-job path + host epilogue (same global pair indices -> same seeds)
         rs = np.random.default_rng(7)
         sample = np.sort(rs.choice(n_pairs, size=min(256, n_pairs), replace=False)).astype(np.int64)
         chk = DistEngine(Scoring.from_aligner(aligner)).pair_scores(seqs, True, True, R, SEED, pair_idx=sample)
-        full = canonical_order(res, n_seq)
-        assert np.array_equal(full['aln'][sample], chk['aln'][sample]), 'multi-GPU aln mismatch'
-        assert np.array_equal(full['rnd'][sample], chk['rnd'][sample]), 'multi-GPU rnd mismatch'
+        want = DistEngine.distances({k: chk[k][sample] for k in ('aln', 'rnd', 'iden')}, R).astype('<f4')
+        ar = np.arange(n_seq, dtype=np.int64)
+        row_start = ar * (2 * n_seq - ar - 1) // 2
+        si = np.minimum(np.searchsorted(row_start, sample, side='right') - 1, n_seq - 2)
+        got = D[si, sample - row_start[si] + si + 1]
+        assert np.array_equal(got, want), 'multi-GPU matrix mismatch'
+        assert np.array_equal(D, D.T)
         verified = int(len(sample))
     e2e_t = allmax(min(e2e_ms) * 1e-3)
     e2e_gcups = cells_all / e2e_t / 1e9

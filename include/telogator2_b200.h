@@ -127,6 +127,33 @@ typedef struct tg_dist_batch_args {
 size_t tg_dist_batch_mt_work_bytes(int64_t n_pairs, int R, int max_len);
 int tg_dist_batch(const tg_dist_batch_args *args, const tg_nw_scoring *sc, void *stream);
 
+/* The float epilogue of tvr_distance (tg_align.py:137-149) and the matrix fill of
+ * get_dist_matrix_parallel (tg_align.py:180-186) for the pairs [q0, q1) of a tg_dist_batch call:
+ *   early-out -> 10;  rand = mean(rnd[0..R));  rand >= aln -> 10;
+ *   else min(-log((aln - rand) / (iden - rand)), 10);  then max(., 1e-4);  float64 -> float32;
+ *   D[i][j] = D[j][i] = dist (original sequence indices; the caller zeroes D once).
+ * All float64 operations are IEEE and in the reference's order; only log() can differ from the host's
+ * libm in the last bit(s).  A pair whose float32 result (clamps included) would change if log() moved by
+ * 2^-margin_log2 relative is NOT trusted: its local index q - q0 is appended to d_ambig (up to ambig_cap
+ * entries; d_stats[3] counts all of them) and the host recomputes that distance from the integer results
+ * with its own libm, so the matrix is bit-identical to the host epilogue.
+ * d_stats (4 x uint64, accumulated, zeroed by the caller): [0] cells of the real alignments,
+ * [1] cells of the null-model alignments, [2] early-out pairs, [3] ambiguous pairs. */
+typedef struct tg_dist_epilogue_args {
+    const int64_t *d_seq_off;
+    const int32_t *d_order;
+    const int32_t *d_aln, *d_rnd;   /* [q1 - q0], [(q1 - q0) * R] as written by tg_dist_batch */
+    const uint8_t *d_flags;
+    const double *d_iden;
+    float *d_matrix;                /* [n_seq * n_seq] row-major */
+    int64_t *d_ambig;               /* [ambig_cap] */
+    unsigned long long *d_stats;    /* [4] */
+    int64_t q0, q1, ambig_base;     /* ambig entries are ambig_base + (q - q0) */
+    int32_t n_seq, adjust_lens, min_viable, R, ambig_cap, margin_log2;
+} tg_dist_epilogue_args;
+
+int tg_dist_epilogue(const tg_dist_epilogue_args *args, void *stream);
+
 /* Integer-ALU issue-rate microbenchmark used as the DP roofline denominator:
  * runs `iters` dependent-chain-free VIMNMX3.U16x2/IADD pairs per thread on the whole device and
  * returns lane-operations per second for the DPX op and for a plain integer add. */

@@ -34,6 +34,14 @@ class DistBatchArgs(C.Structure):
                 ('max_len', C.c_int32), ('pad_', C.c_int32)]
 
 
+class DistEpilogueArgs(C.Structure):
+    _fields_ = [('d_seq_off', C.c_void_p), ('d_order', C.c_void_p), ('d_aln', C.c_void_p), ('d_rnd', C.c_void_p),
+                ('d_flags', C.c_void_p), ('d_iden', C.c_void_p), ('d_matrix', C.c_void_p), ('d_ambig', C.c_void_p),
+                ('d_stats', C.c_void_p), ('q0', C.c_int64), ('q1', C.c_int64), ('ambig_base', C.c_int64),
+                ('n_seq', C.c_int32), ('adjust_lens', C.c_int32), ('min_viable', C.c_int32), ('R', C.c_int32),
+                ('ambig_cap', C.c_int32), ('margin_log2', C.c_int32)]
+
+
 class TgError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f'telogator2_b200 error {code}: {msg}')
@@ -44,7 +52,7 @@ _lib = None
 
 EXPORTS = ['tg_last_error', 'tg_version', 'tg_device_sm_count',
            'tg_nw_wave_scratch_bytes', 'tg_nw_wave_check', 'tg_nw_scores_wave', 'tg_nw_generic_max_m',
-           'tg_nw_scores_generic', 'tg_mt_shuffle', 'tg_dist_batch', 'tg_dist_batch_mt_work_bytes', 'tg_int_alu_peak',
+           'tg_nw_scores_generic', 'tg_mt_shuffle', 'tg_dist_batch', 'tg_dist_batch_mt_work_bytes', 'tg_dist_epilogue', 'tg_int_alu_peak',
            'tg_kmer_table_bytes', 'tg_kmer_table_build', 'tg_kmer_table_build_pair', 'tg_scan_tile_bases', 'tg_scan_pack', 'tg_scan_basecount', 'tg_scan_orient',
            'tg_scan_density', 'tg_scan_hits_work_bytes', 'tg_scan_hits']
 
@@ -67,6 +75,7 @@ def load():
     L.tg_nw_scores_generic.argtypes = [vp, vp, i64, i32, C.POINTER(NwScoring), vp, vp]
     L.tg_mt_shuffle.argtypes = [vp, vp, i64, i32, i32, vp]
     L.tg_dist_batch.argtypes = [C.POINTER(DistBatchArgs), C.POINTER(NwScoring), vp]
+    L.tg_dist_epilogue.argtypes = [C.POINTER(DistEpilogueArgs), vp]
     L.tg_dist_batch_mt_work_bytes.restype = sz
     L.tg_dist_batch_mt_work_bytes.argtypes = [i64, i32, i32]
     L.tg_int_alu_peak.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]

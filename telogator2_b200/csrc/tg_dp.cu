@@ -63,7 +63,7 @@ __device__ __forceinline__ void unrank_pair(long long q, int n, int &a, int &b)
     b = (int)(q - r * (2LL * n - r - 1) / 2 + r + 1);
 }
 
-struct PairDesc { long long off_i, off_j; int n, m; long long p; };
+struct PairDesc { long long off_i, off_j; int n, m; long long p; int i, j; };
 
 // sorted-space pair q -> original (i < j), length-adjusted shapes (tg_align.py:115-120) and combinations index p
 template <typename PT>
@@ -83,7 +83,7 @@ __device__ __forceinline__ PairDesc describe_pair(const PT &P, long long q)
         li = min(li, ml);
         lj = min(lj, ml);
     }
-    d.n = li; d.m = lj;
+    d.n = li; d.m = lj; d.i = i; d.j = j;
     d.p = (long long)i * (2LL * P.n_seq - i - 1) / 2 + (j - i - 1);
     return d;
 }
@@ -966,6 +966,84 @@ __global__ void __launch_bounds__(256) dist_flags_kernel(const FlagParams P)
 }
 
 // ------------------------------------------------------------------------------------------------
+// Float epilogue (tg_align.py:137-149) + matrix fill (tg_align.py:180-186), one thread per pair.
+// ------------------------------------------------------------------------------------------------
+struct EpiParams {
+    const long long *seq_off;
+    const int *order;
+    int n_seq, adjust_lens, min_viable, R;
+    long long q0, q1, ambig_base;
+    const int32_t *aln, *rnd;
+    const uint8_t *flags;
+    const double *iden;
+    float *matrix;
+    long long *ambig;
+    unsigned long long *stats;
+    int ambig_cap;
+    double eps;
+};
+
+// Python's min(x, MAX_SEQ_DIST) / max(x, MIN_SEQ_DIST): a NaN first argument is kept
+__device__ __forceinline__ float clamp_dist(double x)
+{
+    x = (10.0 < x) ? 10.0 : x;
+    x = (1e-4 > x) ? 1e-4 : x;
+    return __double2float_rn(x);
+}
+
+__global__ void __launch_bounds__(256) dist_epilogue_kernel(const EpiParams P)
+{
+    unsigned long long cells_a = 0, cells_b = 0, n_early = 0;
+    for (long long ql = (long long)blockIdx.x * blockDim.x + threadIdx.x; ql < P.q1 - P.q0; ql += (long long)gridDim.x * blockDim.x) {
+        const PairDesc d = describe_pair(P, P.q0 + ql);
+        const unsigned long long cells = (unsigned long long)d.n * (unsigned long long)d.m;
+        cells_a += cells;
+        float f;
+        if (P.flags[ql]) {
+            f = 10.0f;
+            n_early++;
+        } else {
+            cells_b += cells * (unsigned long long)P.R;
+            const double aln = (double)P.aln[ql], iden = P.iden[ql];
+            double rsum = 0.0;
+            for (int k = 0; k < P.R; k++) rsum = __dadd_rn(rsum, (double)P.rnd[ql * P.R + k]);
+            const double rmean = __ddiv_rn(rsum, (double)P.R);                    // np.mean; R == 0 -> nan
+            if (rmean >= aln) {
+                f = 10.0f;
+            } else {
+                const double l = log(__ddiv_rn(__dsub_rn(aln, rmean), __dsub_rn(iden, rmean)));
+                f = clamp_dist(-l);
+                if (l != 0.0 && isfinite(l)) {
+                    const float f0 = clamp_dist(-__dmul_rn(l, 1.0 - P.eps)), f1 = clamp_dist(-__dmul_rn(l, 1.0 + P.eps));
+                    if (f0 != f || f1 != f) {
+                        const unsigned long long k = atomicAdd(&P.stats[3], 1ULL);
+                        if (k < (unsigned long long)P.ambig_cap) P.ambig[k] = P.ambig_base + ql;
+                    }
+                }
+            }
+        }
+        P.matrix[(size_t)d.i * P.n_seq + d.j] = f;
+        P.matrix[(size_t)d.j * P.n_seq + d.i] = f;
+    }
+    // block totals -> three atomics per block
+    for (int o = 16; o > 0; o >>= 1) {
+        cells_a += __shfl_down_sync(0xffffffffu, cells_a, o);
+        cells_b += __shfl_down_sync(0xffffffffu, cells_b, o);
+        n_early += __shfl_down_sync(0xffffffffu, n_early, o);
+    }
+    __shared__ unsigned long long s_tot[3];
+    if (threadIdx.x < 3) s_tot[threadIdx.x] = 0;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&s_tot[0], cells_a);
+        atomicAdd(&s_tot[1], cells_b);
+        atomicAdd(&s_tot[2], n_early);
+    }
+    __syncthreads();
+    if (threadIdx.x < 3 && s_tot[threadIdx.x]) atomicAdd(&P.stats[threadIdx.x], s_tot[threadIdx.x]);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Integer-ALU peak: 8 independent accumulator chains of (add, VIMNMX3.U16x2) per thread.
 // ------------------------------------------------------------------------------------------------
 template <int MODE>
@@ -1342,6 +1420,31 @@ TG_EXPORT int tg_mt_shuffle(uint8_t *d_pool, const tg_shuffle_job *d_jobs, int64
     const long long need = (n_jobs + MT_THREADS - 1) / MT_THREADS;
     if (grid > need) grid = need;
     mt_shuffle_kernel<<<(int)grid, MT_THREADS, smem, st>>>(d_pool, d_jobs, n_jobs, R, stride);
+    TG_CUDA_CHECK(cudaGetLastError());
+    return TG_OK;
+}
+
+TG_EXPORT int tg_dist_epilogue(const tg_dist_epilogue_args *a, void *stream)
+{
+    if (!a) return tg_set_err(TG_EINVAL, "NULL argument");
+    const long long npairs = a->q1 - a->q0;
+    if (npairs <= 0) return TG_OK;
+    if (!a->d_seq_off || !a->d_order || !a->d_aln || !a->d_flags || !a->d_iden || !a->d_matrix || !a->d_stats ||
+        (a->R > 0 && !a->d_rnd) || (a->ambig_cap > 0 && !a->d_ambig))
+        return tg_set_err(TG_EINVAL, "NULL device pointer");
+    if (a->margin_log2 < 8 || a->margin_log2 > 52) return tg_set_err(TG_EINVAL, "margin_log2 %d outside [8, 52]", a->margin_log2);
+    const int sms = tg_sm_count();
+    if (sms <= 0) return tg_set_err(TG_ECUDA, "no CUDA device");
+    EpiParams E;
+    E.seq_off = reinterpret_cast<const long long *>(a->d_seq_off); E.order = a->d_order; E.n_seq = a->n_seq;
+    E.adjust_lens = a->adjust_lens; E.min_viable = a->min_viable; E.R = a->R > 0 ? a->R : 0;
+    E.q0 = a->q0; E.q1 = a->q1; E.ambig_base = a->ambig_base;
+    E.aln = a->d_aln; E.rnd = a->d_rnd; E.flags = a->d_flags; E.iden = a->d_iden; E.matrix = a->d_matrix;
+    E.ambig = reinterpret_cast<long long *>(a->d_ambig); E.stats = a->d_stats; E.ambig_cap = a->ambig_cap;
+    E.eps = ldexp(1.0, -a->margin_log2);
+    long long g = (npairs + 255) / 256;
+    if (g > (long long)sms * 8) g = (long long)sms * 8;
+    dist_epilogue_kernel<<<(int)g, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(E);
     TG_CUDA_CHECK(cudaGetLastError());
     return TG_OK;
 }

@@ -171,7 +171,7 @@ class DistEngine:
     """Device state for one get_dist_matrix_parallel call."""
 
     def __init__(self, scoring, device=None, force_generic=False, pairs_per_batch=1 << 21,
-                 shuffle_bytes_per_batch=8 << 30, single_kernel_shuffle=False):
+                 shuffle_bytes_per_batch=8 << 30, single_kernel_shuffle=False, margin_log2=46, ambig_cap=1 << 16):
         self.torch = _lib.require_cuda()
         self.L = _lib.load()
         self.sc = scoring
@@ -182,6 +182,10 @@ class DistEngine:
         self.single_kernel_shuffle = single_kernel_shuffle or bool(int(__import__('os').environ.get('TG_SINGLE_KERNEL_SHUFFLE', '0')))
         self.stats = {'cells': 0, 'wave_jobs': 0, 'generic_jobs': 0, 'launches': 0, 'pairs': 0, 'early_out': 0,
                       'h2d_bytes': 0, 'd2h_bytes': 0}
+        # device epilogue: a distance is recomputed on the host when moving log() by 2^-margin_log2 (relative; 64 ulp by
+        # default, far beyond any libm's error) could change its float32 value -- about 1 pair in 10^6
+        self.margin_log2 = margin_log2
+        self.ambig_cap = ambig_cap
         self._scratch = None
         self._counter = None
 
@@ -243,13 +247,36 @@ class DistEngine:
         sp = sub - 2 * sc.gap
         return sp.min() >= 0 and sp.max() <= 127 and int(sp.max()) * max_len <= 65535
 
-    def _pair_scores_fast(self, codes, off, sub, adjust_lens, min_viable, R, rng_seed, shard, streamed=True):
-        torch = self.torch
-        n_seq = len(off) - 1
-        n_pairs = n_seq * (n_seq - 1) // 2
+    def prepare(self, sequences):
+        """Encode the sequences and make them resident on the device.  Returns the state consumed by matrix_device() /
+        _pair_scores_fast(), or None if this scoring/length needs the explicit-job path (pair_scores)."""
+        if len(sequences) < 2:
+            return None
+        codes, off, sub = self.sc.encode_all(sequences)
         lens = np.diff(off)
         max_len = int(lens.max())
+        if not self._fast_ok(sub, max_len):
+            return None
+        torch = self.torch
         order = np.argsort(-lens, kind='stable').astype(np.int32)
+        st = dict(n_seq=len(off) - 1, n_codes=len(codes), max_len=max_len, order=order, sub=sub, off=off,
+                  d_codes=torch.from_numpy(codes).to(self.device), d_off=torch.from_numpy(off).to(self.device),
+                  d_order=torch.from_numpy(order).to(self.device), d_cs=None, cstruct=self.sc.c_struct(sub), pool=None)
+        self.stats['h2d_bytes'] += len(codes) + off.nbytes + order.nbytes
+        if self.sc.alphabet is not None:
+            cs = np.zeros(len(codes) + 1, dtype=np.int32)
+            np.cumsum(np.diag(sub)[codes], out=cs[1:])
+            st['d_cs'] = torch.from_numpy(cs).to(self.device)
+            self.stats['h2d_bytes'] += cs.nbytes
+        return st
+
+    def _launch_fast(self, st, adjust_lens, min_viable, R, rng_seed, shard, streamed, d_matrix=None):
+        """Queue every batch of this rank's pair ranges on the current stream (no host synchronisation).
+        Results land in whole-call device arrays, stored range after range ("compact"); with d_matrix the float
+        epilogue runs right behind each batch and fills the matrix."""
+        torch = self.torch
+        n_seq, n_codes, max_len = st['n_seq'], st['n_codes'], st['max_len']
+        n_pairs = n_seq * (n_seq - 1) // 2
         R = max(int(R), 0)
         slot = 2 * R * max_len
         streamed = bool(streamed and R > 0 and not self.single_kernel_shuffle)
@@ -262,90 +289,134 @@ class DistEngine:
         rank, world = shard if shard is not None else (0, 1)
         ranges = fast_ranges(n_pairs, rank, world)
         cap = min(cap, max(2, max((e - b for b, e in ranges), default=2) + 1))
-        # results of this rank's ranges only, stored back to back ("compact"); expand_ranges() / gather_results()
-        # turn them into full-length arrays
         n_own = sum(e - b for b, e in ranges)
         range_pos = np.cumsum([0] + [e - b for b, e in ranges])
-        aln = np.full(n_own, NOT_COMPUTED, dtype=np.int32)
-        rnd = np.full((n_own, R), NOT_COMPUTED, dtype=np.int32)
-        iden = np.zeros(n_own, dtype=np.float64)
-        shape = np.zeros((n_own, 2), dtype=np.int32)
-        flags = np.zeros(n_own, dtype=np.uint8)
-        # device state
-        n_codes = len(codes)
-        pool = torch.empty(n_codes + cap * slot + 64, dtype=torch.uint8, device=self.device)
-        pool[:n_codes] = torch.from_numpy(codes).to(self.device)
-        d_off = torch.from_numpy(off).to(self.device)
-        d_order = torch.from_numpy(order).to(self.device)
-        self.stats['h2d_bytes'] += n_codes + off.nbytes + order.nbytes
-        d_cs = None
-        if self.sc.alphabet is not None:
-            cs = np.zeros(n_codes + 1, dtype=np.int32)
-            np.cumsum(np.diag(sub)[codes], out=cs[1:])
-            d_cs = torch.from_numpy(cs).to(self.device)
-            self.stats['h2d_bytes'] += cs.nbytes
+        if st['pool'] is None or st['pool'].numel() < n_codes + cap * slot + 64:
+            st['pool'] = None
+            st['pool'] = torch.empty(n_codes + cap * slot + 64, dtype=torch.uint8, device=self.device)
+            st['pool'][:n_codes] = st['d_codes']
+        pool = st['pool']
         need = self.L.tg_nw_wave_scratch_bytes(max_len)
         if self._scratch is None or self._scratch.numel() < need:
             self._scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
-        counter = torch.zeros(8, dtype=torch.int32, device=self.device)      # [0:2] work counter, [4] sticky stream overflow
-        mt_work = [torch.empty(self.L.tg_dist_batch_mt_work_bytes(cap, R, max_len), dtype=torch.uint8, device=self.device)
-                   for _ in range(1)] if streamed else [None]
-        cstruct = self.sc.c_struct(sub)
-        outs = []
+        dev = dict(n_own=n_own, ranges=ranges, n_pairs=n_pairs, world=world, R=R, streamed=streamed,
+                   aln=torch.empty(max(n_own, 1), dtype=torch.int32, device=self.device),
+                   rnd=torch.full((max(n_own, 1), max(R, 1)), NOT_COMPUTED, dtype=torch.int32, device=self.device),
+                   flags=torch.empty(max(n_own, 1), dtype=torch.uint8, device=self.device),
+                   iden=torch.empty(max(n_own, 1), dtype=torch.float64, device=self.device),
+                   shape=torch.empty((max(n_own, 1), 2), dtype=torch.int32, device=self.device),
+                   counter=torch.zeros(8, dtype=torch.int32, device=self.device),   # [0:2] work counter, [4] sticky stream overflow
+                   stats=torch.zeros(4, dtype=torch.int64, device=self.device),
+                   ambig=torch.empty(self.ambig_cap, dtype=torch.int64, device=self.device) if d_matrix is not None else None)
+        mt_work = torch.empty(self.L.tg_dist_batch_mt_work_bytes(cap, R, max_len), dtype=torch.uint8, device=self.device) if streamed else None
+        d_cs = st['d_cs']
+        stream = _lib.stream_ptr(torch)
         for ri, (rb, re_) in enumerate(ranges):
             q = rb
             while q < re_:
                 q1 = min(re_, q + cap)
-                npb = q1 - q
-                d_aln = torch.empty(npb, dtype=torch.int32, device=self.device)
-                d_rnd = torch.full((npb, max(R, 1)), NOT_COMPUTED, dtype=torch.int32, device=self.device)
-                d_flags = torch.empty(npb, dtype=torch.uint8, device=self.device)
-                d_iden = torch.empty(npb, dtype=torch.float64, device=self.device)
-                d_shape = torch.empty((npb, 2), dtype=torch.int32, device=self.device)
+                cpos = int(range_pos[ri]) + (q - rb)
                 a = _lib.DistBatchArgs()
-                a.d_pool, a.d_seq_off, a.d_order = pool.data_ptr(), d_off.data_ptr(), d_order.data_ptr()
+                a.d_pool, a.d_seq_off, a.d_order = pool.data_ptr(), st['d_off'].data_ptr(), st['d_order'].data_ptr()
                 a.d_diag_cs = d_cs.data_ptr() if d_cs is not None else None
-                a.d_aln, a.d_rnd, a.d_shape = d_aln.data_ptr(), d_rnd.data_ptr(), d_shape.data_ptr()
-                a.d_flags, a.d_iden = d_flags.data_ptr(), d_iden.data_ptr()
-                a.d_scratch, a.d_counter = self._scratch.data_ptr(), counter.data_ptr()
-                a.d_mt_work = mt_work[0].data_ptr() if streamed else None
+                a.d_aln, a.d_rnd = dev['aln'].data_ptr() + 4 * cpos, dev['rnd'].data_ptr() + 4 * max(R, 1) * cpos
+                a.d_shape, a.d_flags, a.d_iden = dev['shape'].data_ptr() + 8 * cpos, dev['flags'].data_ptr() + cpos, dev['iden'].data_ptr() + 8 * cpos
+                a.d_scratch, a.d_counter = self._scratch.data_ptr(), dev['counter'].data_ptr()
+                a.d_mt_work = mt_work.data_ptr() if streamed else None
                 a.q0, a.q1, a.seed0, a.shuf_base, a.slot = q, q1, int(rng_seed), n_codes, slot
                 a.match = float(self.sc.match) if self.sc.alphabet is None else 0.0
-                a.n_seq, a.adjust_lens, a.min_viable, a.R, a.max_len = n_seq, int(bool(adjust_lens)), int(bool(min_viable)), R, max_len
-                _lib.check(self.L.tg_dist_batch(C.byref(a), C.byref(cstruct), _lib.stream_ptr(torch)))
+                a.n_seq, a.adjust_lens, a.min_viable, a.R, a.max_len = n_seq, int(bool(adjust_lens)), int(bool(min_viable)), R, st['max_len']
+                _lib.check(self.L.tg_dist_batch(C.byref(a), C.byref(st['cstruct']), stream))
                 self.stats['launches'] += (6 if streamed else 4) if R else 2
-                cpos = int(range_pos[ri]) + (q - rb)
-                outs.append((cpos, cpos + npb, d_aln, d_rnd, d_flags, d_iden, d_shape))
-                if len(outs) >= 2:                     # keep one batch in flight while the previous one is copied back
-                    self._collect(outs.pop(0), aln, rnd, flags, iden, shape, R)
+                if d_matrix is not None:
+                    e = _lib.DistEpilogueArgs()
+                    e.d_seq_off, e.d_order = a.d_seq_off, a.d_order
+                    e.d_aln, e.d_rnd, e.d_flags, e.d_iden = a.d_aln, a.d_rnd, a.d_flags, a.d_iden
+                    e.d_matrix, e.d_ambig, e.d_stats = d_matrix.data_ptr(), dev['ambig'].data_ptr(), dev['stats'].data_ptr()
+                    e.q0, e.q1, e.ambig_base = q, q1, cpos
+                    e.n_seq, e.adjust_lens, e.min_viable, e.R = n_seq, a.adjust_lens, a.min_viable, R
+                    e.ambig_cap, e.margin_log2 = self.ambig_cap, self.margin_log2
+                    _lib.check(self.L.tg_dist_epilogue(C.byref(e), stream))
+                    self.stats['launches'] += 1
                 q = q1
-        for o in outs:
-            self._collect(o, aln, rnd, flags, iden, shape, R)
-        if streamed and int(counter[4].item()) != 0:
-            # a pair drew more random numbers than its pre-generated stream holds (never observed; the stream is
-            # sized > 10 sigma above the expectation): redo the range with the single-kernel null model
-            return self._pair_scores_fast(codes, off, sub, adjust_lens, min_viable, R, rng_seed, shard, streamed=False)
-        live = aln != NOT_COMPUTED
-        cells = shape[:, 0].astype(np.int64) * shape[:, 1]
-        self.stats['pairs'] += int(live.sum())
-        self.stats['early_out'] += int(flags[live].sum())
-        self.stats['cells'] += int(cells[live].sum()) + R * int(cells[live & (flags == 0)].sum())
-        self.stats['wave_jobs'] += int(live.sum())
-        res = dict(aln=aln, rnd=rnd, iden=iden, n=shape[:, 0].copy(), m=shape[:, 1].copy(), order=order)
-        if world > 1:
-            res['ranges'] = ranges
-            res['n_pairs'] = n_pairs
-        return res
+        return dev
 
-    def _collect(self, o, aln, rnd, flags, iden, shape, R):
-        (q, q1, d_aln, d_rnd, d_flags, d_iden, d_shape) = o
-        aln[q:q1] = d_aln.cpu().numpy()
-        if R:
-            rnd[q:q1] = d_rnd.cpu().numpy()
-        flags[q:q1] = d_flags.cpu().numpy()
-        iden[q:q1] = d_iden.cpu().numpy()
-        shape[q:q1] = d_shape.cpu().numpy()
-        self.stats['d2h_bytes'] += (q1 - q) * (4 + 4 * R + 1 + 8 + 8)
+    def _compact_to_pairs(self, st, dev, pos):
+        """compact result positions -> (i, j) original sequence indices."""
+        starts = np.array([b for b, _ in dev['ranges']], dtype=np.int64)
+        rpos = np.cumsum([0] + [e - b for b, e in dev['ranges']])
+        ri = np.searchsorted(rpos, pos, side='right') - 1
+        q = starts[ri] + (pos - rpos[ri])
+        n = st['n_seq']
+        t = 2.0 * n - 1.0
+        r = np.floor((t - np.sqrt(t * t - 8.0 * q)) * 0.5).astype(np.int64).clip(0, n - 2)
+        first = lambda rr: rr * (2 * n - rr - 1) // 2
+        r = np.where(first(r) > q, r - 1, r)
+        r = np.where(first(r + 1) <= q, r + 1, r)
+        bcol = q - first(r) + r + 1
+        o = st['order'].astype(np.int64)
+        return o[r], o[bcol]
+
+    def matrix_device(self, st, adjust_lens, min_viable, R, rng_seed, shard=None, streamed=True):
+        """float32 (n, n) distance matrix ON THE DEVICE for this rank's share of the pair space (all of it without
+        shard); other entries stay 0.  tg_align.py:154-189 without the host round trips: the kernels of every batch and
+        the float epilogue are queued back to back, one synchronisation at the end."""
+        torch = self.torch
+        n = st['n_seq']
+        D = torch.zeros((n, n), dtype=torch.float32, device=self.device)
+        dev = self._launch_fast(st, adjust_lens, min_viable, R, rng_seed, shard, streamed, d_matrix=D)
+        tail = torch.cat([dev['stats'], dev['counter'].to(torch.int64)]).cpu().numpy()      # the one synchronisation
+        self.stats['d2h_bytes'] += tail.nbytes
+        if dev['streamed'] and tail[4 + 4] != 0:
+            # a pair drew more random numbers than its pre-generated stream holds (never observed; the stream is
+            # sized > 10 sigma above the expectation): redo with the single-kernel null model
+            return self.matrix_device(st, adjust_lens, min_viable, R, rng_seed, shard, streamed=False)
+        n_amb = int(tail[3])
+        if n_amb:
+            # pairs whose float32 value could depend on the last bits of log(): recompute with the host's libm
+            if n_amb <= self.ambig_cap:
+                pos = np.sort(dev['ambig'][:n_amb].cpu().numpy())
+            else:
+                pos = np.arange(dev['n_own'], dtype=np.int64)
+            for c0 in range(0, len(pos), 1 << 22):
+                pc = pos[c0:c0 + (1 << 22)]
+                d_pc = torch.from_numpy(pc).to(self.device)
+                sub = dict(aln=dev['aln'][d_pc].cpu().numpy(), rnd=dev['rnd'][d_pc][:, :dev['R']].cpu().numpy(),
+                           iden=dev['iden'][d_pc].cpu().numpy())
+                d = torch.from_numpy(self.distances(sub, dev['R']).astype('<f4')).to(self.device)
+                i, j = self._compact_to_pairs(st, dev, pc)
+                d_i, d_j = torch.from_numpy(i).to(self.device), torch.from_numpy(j).to(self.device)
+                D[d_i, d_j] = d
+                D[d_j, d_i] = d
+            self.stats['host_fixed_pairs'] = self.stats.get('host_fixed_pairs', 0) + len(pos)
+        self.stats['pairs'] += dev['n_own']
+        self.stats['early_out'] += int(tail[2])
+        self.stats['cells'] += int(tail[0]) + int(tail[1])
+        self.stats['wave_jobs'] += dev['n_own']
+        return D
+
+    def _pair_scores_fast(self, st, adjust_lens, min_viable, R, rng_seed, shard, streamed=True):
+        """Integer results of the device-driven path, copied to the host (parity tests, explicit gathers)."""
+        dev = self._launch_fast(st, adjust_lens, min_viable, R, rng_seed, shard, streamed)
+        n_own, R = dev['n_own'], dev['R']
+        if dev['streamed'] and int(dev['counter'][4].item()) != 0:
+            return self._pair_scores_fast(st, adjust_lens, min_viable, R, rng_seed, shard, streamed=False)
+        aln = dev['aln'][:n_own].cpu().numpy()
+        rnd = dev['rnd'][:n_own, :R].cpu().numpy() if R else np.zeros((n_own, 0), dtype=np.int32)
+        flags = dev['flags'][:n_own].cpu().numpy()
+        iden = dev['iden'][:n_own].cpu().numpy()
+        shape = dev['shape'][:n_own].cpu().numpy()
+        self.stats['d2h_bytes'] += n_own * (4 + 4 * R + 1 + 8 + 8)
+        cells = shape[:, 0].astype(np.int64) * shape[:, 1]
+        self.stats['pairs'] += n_own
+        self.stats['early_out'] += int(flags.sum())
+        self.stats['cells'] += int(cells.sum()) + R * int(cells[flags == 0].sum())
+        self.stats['wave_jobs'] += n_own
+        res = dict(aln=aln, rnd=np.ascontiguousarray(rnd), iden=iden, n=shape[:, 0].copy(), m=shape[:, 1].copy(), order=st['order'])
+        if dev['world'] > 1:
+            res['ranges'] = dev['ranges']
+            res['n_pairs'] = dev['n_pairs']
+        return res
 
     def pair_scores(self, sequences, adjust_lens, min_viable, R, rng_seed, pair_idx=None, shard=None):
         """Integer results for every pair: dict(aln, rnd[n_pairs, R], iden, n, m, order).
@@ -356,9 +427,9 @@ class DistEngine:
         shard=(rank, world) restricts the work to this rank's share of the pair space (multi-GPU);
         everything else stays NOT_COMPUTED / 0 and is merged by multi_gpu.gather_results."""
         if len(sequences) >= 2 and pair_idx is None:
-            codes, off, sub = self.sc.encode_all(sequences)
-            if self._fast_ok(sub, int(np.diff(off).max())):
-                return self._pair_scores_fast(codes, off, sub, adjust_lens, min_viable, R, rng_seed, shard)
+            st = self.prepare(sequences)
+            if st is not None:
+                return self._pair_scores_fast(st, adjust_lens, min_viable, R, rng_seed, shard)
         if shard is not None and pair_idx is None and shard[1] > 1:
             from .multi_gpu import shard_pair_indices
             pair_idx = shard_pair_indices(len(sequences) * (len(sequences) - 1) // 2, shard[0], shard[1])
@@ -507,11 +578,11 @@ class DistEngine:
         return D
 
 
-def fast_ranges(n_pairs, rank, world):
-    """Pair ranges (sorted pair space) owned by `rank`: the blocks DistEngine._pair_scores_fast deals round-robin."""
+def fast_ranges(n_pairs, rank, world, min_block=4096):
+    """Pair ranges (sorted pair space) owned by `rank`: the blocks DistEngine._launch_fast deals round-robin."""
     if world <= 1:
         return [(0, n_pairs)]
-    blk = max(4096, -(-n_pairs // (world * 8)))
+    blk = max(min_block, -(-n_pairs // (world * 8)))
     blk += blk % 2
     return [(b, min(b + blk, n_pairs)) for b in range(rank * blk, n_pairs, world * blk)]
 

@@ -88,3 +88,35 @@ def sharded_pair_scores(engine, sequences, adjust_lens, min_viable, R, rng_seed,
     if device is None:
         device = engine.device if dist.get_backend() == 'nccl' else 'cpu'
     return gather_results(res, dist, device)
+
+
+def reduce_matrix(D, dist):
+    """Sum the ranks' partial matrices (disjoint non-zero entries) in place: the one exchange step of the matrix path."""
+    dist.all_reduce(D, op=dist.ReduceOp.SUM)
+    return D
+
+
+def sharded_dist_matrix(engine, sequences, adjust_lens, min_viable, R, rng_seed, compute=None):
+    """get_dist_matrix_parallel (tg_align.py:154-189) over every rank of the process group: each rank fills the entries of
+    its share of the pair space in a zeroed float32 matrix on its device, the matrices are summed over NCCL/NVLink
+    (x + 0 = x exactly, NaN stays NaN), and every rank returns the full host matrix.
+    `compute(shard)` -> partial matrix (torch tensor) replaces the device call in the CPU (gloo) tests."""
+    dist, rank, world = _dist_state()
+    n = len(sequences)
+    if n < 2:
+        return np.zeros((n, n), dtype='<f4')
+    if compute is None:
+        st = engine.prepare(sequences)
+        if st is None:                       # scoring/length outside the device-driven path: integer gather + host epilogue
+            res = sharded_pair_scores(engine, sequences, adjust_lens, min_viable, R, rng_seed)
+            return engine.dist_matrix(sequences, adjust_lens, min_viable, R, rng_seed, res=res)
+
+        def compute(shard):
+            return engine.matrix_device(st, adjust_lens, min_viable, R, rng_seed, shard=shard)
+    D = compute((rank, world) if world > 1 else None)
+    if world > 1:
+        D = reduce_matrix(D, dist)
+    out = D.cpu().numpy()
+    if engine is not None:
+        engine.stats['d2h_bytes'] += out.nbytes
+    return out

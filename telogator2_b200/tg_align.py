@@ -186,9 +186,8 @@ def get_dist_matrix_parallel(sequences, aligner, adjust_lens, min_viable, rand_s
     (process-pool knobs); the result never depended on them.  float32 (n, n), symmetric, zero diagonal,
     raw distances in [1e-4, 10] (the caller divides by MAX_SEQ_DIST, tg_tvr.py:154)."""
     eng = DistEngine(Scoring.from_aligner(aligner))
-    from .multi_gpu import sharded_pair_scores
-    res = sharded_pair_scores(eng, sequences, adjust_lens, min_viable, rand_shuffle_count, rng_seed)
-    return eng.dist_matrix(sequences, adjust_lens, min_viable, rand_shuffle_count, rng_seed, res=res)
+    from .multi_gpu import sharded_dist_matrix
+    return sharded_dist_matrix(eng, sequences, adjust_lens, min_viable, rand_shuffle_count, rng_seed)
 
 
 def quick_compare_tvrs(tvr_1, tvr_2):

@@ -12,7 +12,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import oracle  # noqa: E402
 from telogator2_b200.dist_engine import DistEngine, NOT_COMPUTED  # noqa: E402
-from telogator2_b200.multi_gpu import shard_pair_indices, sharded_pair_scores  # noqa: E402
+from telogator2_b200.dist_engine import fast_ranges  # noqa: E402
+from telogator2_b200.multi_gpu import shard_pair_indices, sharded_dist_matrix, sharded_pair_scores  # noqa: E402
 
 
 def main():
@@ -56,6 +57,23 @@ def main():
     D[iu] = d
     D[(iu[1], iu[0])] = d
     assert np.array_equal(D, _D), 'distance matrix differs'
+    # matrix path: every rank fills its ranges of the SORTED pair space in a zeroed matrix, one all_reduce merges them
+    import torch
+    order = np.argsort(-np.array([len(x) for x in seqs]), kind='stable')
+    sorted_pairs = [(a, b) for a in range(n) for b in range(a + 1, n)]
+
+    def compute_matrix(shard):
+        Dp = torch.zeros((n, n), dtype=torch.float32)
+        for (b, e) in (fast_ranges(n_pairs, shard[0], shard[1], min_block=8) if shard else [(0, n_pairs)]):
+            for q in range(b, e):
+                i, j = order[sorted_pairs[q][0]], order[sorted_pairs[q][1]]
+                Dp[i, j] = Dp[j, i] = float(_D[i, j])
+        return Dp
+
+    Dm = sharded_dist_matrix(None, seqs, True, True, R, seed, compute=compute_matrix)
+    assert Dm.dtype == np.dtype('<f4') and np.array_equal(Dm, _D), 'reduced matrix differs'
+    mine = fast_ranges(n_pairs, rank, world, min_block=8)
+    assert 0 < sum(e - b for b, e in mine) < n_pairs
     own = shard_pair_indices(n_pairs, rank, world, block=8)
     np.save(out_path + f'.rank{rank}.npy', own)
     dist.barrier()

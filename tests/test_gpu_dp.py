@@ -49,6 +49,13 @@ def _check_matrix(tga, seqs, which, gap_bool, adjust, minv, R, seed, force_gener
         assert len(badr) == 0, f'rand mismatch at {badr[:10]}: gpu {res["rnd"][tuple(badr[:10].T)]} oracle {rnd[tuple(badr[:10].T)]}'
     assert np.array_equal(D, Do), 'distance matrix differs'
     assert eng.stats['cells'] == int(cells)
+    # device epilogue + matrix fill (the path get_dist_matrix_parallel takes)
+    eng2 = DistEngine(Scoring.from_aligner(aligner), force_generic=force_generic)
+    st = eng2.prepare(seqs)
+    if st is not None:
+        Dd = eng2.matrix_device(st, adjust, minv, R, seed).cpu().numpy()
+        assert np.array_equal(Dd, Do), 'device-epilogue matrix differs'
+        assert eng2.stats['cells'] == int(cells) and eng2.stats['early_out'] == eng.stats['early_out']
     return eng
 
 
@@ -213,6 +220,23 @@ def test_full_size_properties(tga, colorvecs):
     for i, j in combinations(sub, 2):
         want = oracle.tvr_distance_py(seqs[i], seqs[j], P, True, True, 2, rng_seed=5 + index[(i, j)])
         assert D[i, j] == np.float32(want)
+
+
+def test_device_epilogue_untrusted_pairs_go_to_the_host(tga, colorvecs):
+    """A distance whose float32 value could depend on the last bits of log() is recomputed with the host's libm.
+    A huge margin makes many pairs 'untrusted'; a tiny list capacity exercises the overflow path as well."""
+    from telogator2_b200.dist_engine import DistEngine, Scoring
+    ont, hifi = _cases(colorvecs)
+    seqs = [c[:1000] for c in (ont + hifi)[:40]]
+    aligner = tga.get_aligner_object(tga.get_scoring_matrix('C', 'tvr'), (True, True), 'tvr')
+    Do = oracle.dist_matrix_c(seqs, _P(oracle.scoring_matrix('C', 'tvr'), (True, True)), True, True, 2, 777)
+    fixed = []
+    for margin, cap in ((46, 1 << 16), (12, 1 << 16), (12, 4)):
+        eng = DistEngine(Scoring.from_aligner(aligner), margin_log2=margin, ambig_cap=cap)
+        D = eng.matrix_device(eng.prepare(seqs), True, True, 2, 777).cpu().numpy()
+        assert np.array_equal(D, Do), (margin, cap)
+        fixed.append(eng.stats.get('host_fixed_pairs', 0))
+    assert fixed[0] <= 2 and 4 < fixed[1] < len(seqs) * (len(seqs) - 1) // 2 and fixed[2] == len(seqs) * (len(seqs) - 1) // 2, fixed
 
 
 def test_single_kernel_null_model_matches_streamed(tga, colorvecs):
