@@ -124,16 +124,6 @@ __device__ __forceinline__ void sts64(uint32_t addr, uint2 v)
 {
     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
 }
-__device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
-{
-    uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v)
-{
-    asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
 {
     uint32_t v;
@@ -664,7 +654,7 @@ __global__ void __launch_bounds__(MT_THREADS) mt_shuffle_batch_kernel(const Batc
 //   mt_stream_batch_kernel  warp per pair: block twists (3 data-parallel phases) + tempering, the top
 //                           16 bits of every output word go to a per-pair stream (getrandbits(k) only
 //                           ever looks at the top k <= 16 bits)
-//   mt_sample_batch_kernel  thread per pair: random.sample's swap-remove loop consuming the stream
+//   mt_sample_warp_kernel   warp per pair: random.sample's swap-remove loop consuming the stream, 32 draws per step
 // ------------------------------------------------------------------------------------------------
 constexpr int MTS_PAD = 33;          // row stride of the transposing state buffer: conflict free both ways
 
@@ -802,129 +792,110 @@ __global__ void __launch_bounds__(MTG_WARPS * 32) mt_stream_batch_kernel(const S
     }
 }
 
-// SMEM_POOL: the working array lives in shared memory (else in place in the destination region: long sequences)
-template <bool SMEM_POOL>
-__global__ void __launch_bounds__(MT_THREADS) mt_sample_batch_kernel(const StreamParams P)
+// Warp per pair.  random.sample's loop "j = _randbelow(n - i); result[i] = pool[j]; pool[j] = pool[n - i - 1]" is
+// sequential, but 32 consecutive draws can be resolved together:
+//  1. acceptance: draw l is accepted iff r_l < n_l where n_l = remaining - (#accepted draws before l) -- a fixed point
+//     over the ballot mask that is reached after one or two rounds (a lane's decision rarely depends on its prefix);
+//  2. the accepted draws (in order s = 0 .. S-1) read pool[j_s] and the tail pool[t_s], t_s = remaining - 1 - s.  All reads
+//     are issued against the pool as it was before the group; the effect of the group's earlier writes is patched in:
+//       tail value of step s  = tail value of the LAST earlier step that wrote position t_s (j_s' == t_s), else pool[t_s]
+//       result of step s      = tail value of the LAST earlier step with the same j, else pool[j_s]
+//     (first relation via a 32-entry shared-memory atomicMax + pointer jumping, second via match.any);
+//  3. per distinct j the last step writes its tail value back.
+constexpr int MTW_WARPS = 8;
+constexpr int MTW_EXTRA = 256;           // per-warp scratch behind the pool: 32 x u16 compaction + 32 x int hits
+
+__global__ void __launch_bounds__(MTW_WARPS * 32) mt_sample_warp_kernel(const StreamParams P)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    uint8_t *sp = smem + (size_t)threadIdx.x * P.pool_stride;
-    const int tid = threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t *arr = smem + (size_t)warp * P.pool_stride;
+    uint16_t *scr = reinterpret_cast<uint16_t *>(arr + P.pool_stride - MTW_EXTRA);
+    int *hitarr = reinterpret_cast<int *>(arr + P.pool_stride - MTW_EXTRA + 64);
     const long long npairs = *P.n_live;
+    const unsigned lt = (1u << lane) - 1u;
+    bool ok = true;
     for (;;) {
-        unsigned long long base = 0;
-        if (tid == 0) base = atomicAdd(P.counter, (unsigned long long)MT_THREADS);
-        base = __shfl_sync(TG_FULL_MASK, base, 0);
-        if ((long long)base >= npairs) break;
-        const bool live = (long long)base + tid < npairs;
-        const long long ql = live ? P.live[base + tid] : 0;
-        const unsigned act = __ballot_sync(TG_FULL_MASK, live);
-        if (live) {
-            const PairDesc d = describe_pair(P, P.q0 + ql);
-            int cap = mt_blocks_needed(P.R * (d.n + d.m)) * 624;
-            if (cap > P.cap) cap = P.cap;
-            // The stream is consumed in groups of 16 draws: a group is parked in this lane's 32-byte shared-memory slot
-            // and read back one 16-bit draw at a time, while the NEXT group is already on its way from L2/HBM into
-            // registers (requested ~16 loop iterations before it is needed).
-            const uint4 *st = reinterpret_cast<const uint4 *>(P.stream + ql * P.cap);
-            const int ngroups = cap / 16;
-            int grp = 0, kdraw = 0;
-            uint4 *slot4 = reinterpret_cast<uint4 *>(smem + (size_t)MT_THREADS * P.pool_stride) + 2 * tid;
-            const uint16_t *slot = reinterpret_cast<const uint16_t *>(slot4);
-            slot4[0] = __ldcg(st);
-            slot4[1] = __ldcg(st + 1);
-            uint4 n0 = __ldcg(st + 2), n1 = __ldcg(st + 3);
-            long long dst = P.shuf_base + ql * P.slot;
-            bool ok = true;
-            for (int rep = 0; rep < 2 * P.R; rep++) {
-                // Independent thread scheduling does not re-join lanes that left the sampling loop at different
-                // times; without these barriers the rest of the kernel would run one lane at a time.
-                __syncwarp(act);
-                const int len = (rep & 1) ? d.m : d.n;
-                const uint8_t *src = P.pool + ((rep & 1) ? d.off_j : d.off_i);
-                uint8_t *garr = P.pool + dst;
-                // pool = list(population)
-                if (SMEM_POOL) {
-                    // aligned 32-bit loads + funnel shift (the source starts at an arbitrary byte; reading up to 3 bytes
-                    // past its end stays inside the pool allocation)
-                    const uint32_t *w = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)3);
-                    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3) * 8;
-                    uint32_t *d32 = reinterpret_cast<uint32_t *>(sp);
-                    uint32_t lo = __ldg(w);
-                    for (int q = 0; q * 4 < len; q++) {
-                        const uint32_t hi = __ldg(w + q + 1);
-                        d32[q] = __funnelshift_r(lo, hi, sh);
-                        lo = hi;
-                    }
-                } else {
-                    for (int x = 0; x < len; x++) garr[x] = src[x];
-                }
-                int i = 0;
-                if (SMEM_POOL) {
-                    // tight loop on 32-bit shared addresses: ~20 instructions per draw
-                    const uint32_t arr_s = (uint32_t)__cvta_generic_to_shared(sp);
-                    const uint32_t slot_s = (uint32_t)__cvta_generic_to_shared(slot4);
-                    while (i < len) {
-                        uint32_t v;
-                        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(slot_s + 2 * kdraw) : "memory");
-                        kdraw++;
-                        if (kdraw == 16) {
-                            kdraw = 0;
-                            grp++;
-                            if (grp >= ngroups) ok = false;                    // stream exhausted: flag it (results are discarded)
-                            slot4[0] = n0;
-                            slot4[1] = n1;
-                            const int gi = min(grp + 1, ngroups - 1);
-                            n0 = __ldcg(st + 2 * gi);
-                            n1 = __ldcg(st + 2 * gi + 1);
-                        }
-                        // _randbelow(nn): k = nn.bit_length(); r = getrandbits(k) = top k bits of the 32-bit output.
-                        // result[i] = pool[j] goes to the vacated tail slot; a rejected draw swaps the tail with itself
-                        const uint32_t nn = (uint32_t)(len - i);
-                        const uint32_t r = v >> (__clz(nn) - 16);              // 16 - bit_length(nn)
-                        const uint32_t aj = arr_s + min(r, nn - 1u), at = arr_s + nn - 1u;
-                        const uint32_t t = lds_u8(aj), u = lds_u8(at);
-                        sts_u8(aj, u);                                         // pool[j] = pool[n-i-1]
-                        sts_u8(at, t);
-                        i += (r < nn) ? 1 : 0;
-                    }
-                } else {
-                    while (i < len) {
-                        const uint32_t v = slot[kdraw];
-                        kdraw++;
-                        if (kdraw == 16) {
-                            kdraw = 0;
-                            grp++;
-                            if (grp >= ngroups) ok = false;
-                            slot4[0] = n0;
-                            slot4[1] = n1;
-                            const int gi = min(grp + 1, ngroups - 1);
-                            n0 = __ldcg(st + 2 * gi);
-                            n1 = __ldcg(st + 2 * gi + 1);
-                        }
-                        const uint32_t nn = (uint32_t)(len - i);
-                        const uint32_t r = v >> (__clz(nn) - 16);
-                        const uint32_t j = min(r, nn - 1u);
-                        const uint8_t t = garr[j], u = garr[nn - 1u];
-                        garr[j] = u;
-                        garr[nn - 1u] = t;
-                        i += (r < nn) ? 1 : 0;
-                    }
-                }
-                __syncwarp(act);
-                if (SMEM_POOL) {
-                    for (int x = 0; x < len; x++) P.pool[dst + x] = sp[len - 1 - x];      // result[i] sits at arr[len-1-i]
-                } else {
-                    for (int x = 0; x < len / 2; x++) {
-                        const uint8_t a = garr[x], b = garr[len - 1 - x];
-                        garr[x] = b; garr[len - 1 - x] = a;
-                    }
-                }
-                dst += len;
+        unsigned long long li = 0;
+        if (lane == 0) li = atomicAdd(P.counter, 1ULL);
+        li = __shfl_sync(TG_FULL_MASK, li, 0);
+        if ((long long)li >= npairs) break;
+        const long long ql = P.live[li];
+        const PairDesc d = describe_pair(P, P.q0 + ql);
+        int cap = mt_blocks_needed(P.R * (d.n + d.m)) * 624;
+        if (cap > P.cap) cap = P.cap;
+        const uint16_t *st = P.stream + ql * P.cap;
+        int c = 0;                                               // draws consumed so far
+        long long dst = P.shuf_base + ql * P.slot;
+        for (int rep = 0; rep < 2 * P.R; rep++) {
+            const int len = (rep & 1) ? d.m : d.n;
+            const uint8_t *src = P.pool + ((rep & 1) ? d.off_j : d.off_i);
+            uint8_t *out = P.pool + dst;
+            // pool = list(population): aligned 32-bit loads + funnel shift (reads up to 7 bytes past the end of the
+            // source stay inside the pool allocation)
+            {
+                const uint32_t *w = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)3);
+                const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3) * 8;
+                uint32_t *d32 = reinterpret_cast<uint32_t *>(arr);
+                __syncwarp();
+                for (int q = lane; q * 4 < len; q += 32) d32[q] = __funnelshift_r(__ldg(w + q), __ldg(w + q + 1), sh);
+                __syncwarp();
             }
-            if (!ok) atomicExch(P.overflow, 1);
+            int nn = len;                                        // remaining pool size
+            while (nn > 0) {
+                const int ci = min(c + lane, cap - 1);
+                const uint32_t v = __ldcg(st + ci);
+                // ---- 1. acceptance fixed point ----
+                unsigned A = 0, Aprev;
+                int a;
+                uint32_t r = 0;
+                do {
+                    Aprev = A;
+                    a = __popc(Aprev & lt);
+                    const int nl = nn - a;
+                    bool acc = false;
+                    if (nl > 0) {
+                        r = v >> (__clz(nl) - 16);               // getrandbits(nl.bit_length()): top bits of the output word
+                        acc = r < (uint32_t)nl;
+                    }
+                    A = __ballot_sync(TG_FULL_MASK, acc);
+                } while (A != Aprev);
+                const int S = __popc(A);
+                c += (S == nn) ? (32 - __clz(A)) : 32;           // the draws behind the last element belong to the next shuffle
+                if (c > cap) ok = false;                         // stream exhausted: flag it (results are discarded)
+                if ((A >> lane) & 1u) scr[a] = (uint16_t)r;
+                hitarr[lane] = -1;
+                __syncwarp();
+                // ---- 2. the S swap-removes ----
+                const bool act = lane < S;
+                const int j = act ? (int)scr[lane] : 0;
+                const int t = nn - 1 - lane;
+                uint32_t vj = 0, vt = 0;
+                if (act) { vj = arr[j]; vt = arr[t]; }
+                const int tg = nn - 1 - j;                       // the step whose tail read sees this step's write
+                if (act && tg > lane && tg < S) atomicMax(&hitarr[tg], lane);
+                const unsigned same = __match_any_sync(TG_FULL_MASK, act ? j : -1 - lane);
+                __syncwarp();
+                const int hit = hitarr[lane];
+                int root = hit < 0 ? lane : hit;
+                for (;;) {
+                    const int h = __shfl_sync(TG_FULL_MASK, hit, root);
+                    if (!__any_sync(TG_FULL_MASK, h >= 0)) break;
+                    if (h >= 0) root = h;
+                }
+                const uint32_t tailval = __shfl_sync(TG_FULL_MASK, vt, root);
+                const unsigned before = same & lt;
+                const uint32_t tw = __shfl_sync(TG_FULL_MASK, tailval, before ? 31 - __clz(before) : lane);
+                if (act) out[len - nn + lane] = (uint8_t)(before ? tw : vj);        // result[i]
+                // ---- 3. write-back (every read of the group has completed: the shuffles above are warp-wide) ----
+                if (act && (same >> lane) == 1u) arr[j] = (uint8_t)tailval;
+                __syncwarp();
+                nn -= S;
+            }
+            dst += len;
         }
-        __syncwarp();
     }
+    if (!ok) atomicExch(P.overflow, 1);
 }
 
 struct FlagParams {
@@ -1280,9 +1251,10 @@ TG_EXPORT int tg_dist_batch(const tg_dist_batch_args *a, const tg_nw_scoring *sc
         S.state = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(a->d_mt_work) + live_bytes);
         S.stream = reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(a->d_mt_work) + live_bytes + (size_t)npairs * 624 * sizeof(uint32_t));
         S.overflow = reinterpret_cast<int *>(a->d_counter) + 4;      // sticky; the caller zeroes and checks it
-        size_t psmem = (size_t)MT_THREADS * stride + MT_THREADS * 32;
-        if (psmem > 200 * 1024) { stride = 0; psmem = MT_THREADS * 32; }
-        S.pool_stride = stride;
+        const int wstride = (a->max_len + 15) / 16 * 16 + MTW_EXTRA;      // sampling: per-warp pool + scratch
+        const size_t psmem = (size_t)MTW_WARPS * wstride;
+        if (psmem > 200 * 1024) return tg_set_err(TG_ERANGE, "max_len %d: the sampling pool does not fit shared memory", a->max_len);
+        S.pool_stride = wstride;
         const long long need32 = (npairs + MT_THREADS - 1) / MT_THREADS;
         // seeding
         const size_t ssmem = (size_t)624 * MTS_PAD * sizeof(uint32_t);
@@ -1306,14 +1278,14 @@ TG_EXPORT int tg_dist_batch(const tg_dist_batch_args *a, const tg_nw_scoring *sc
         // sampling
         TG_CUDA_CHECK(cudaMemsetAsync(a->d_counter, 0, sizeof(unsigned long long), st));
         {
-            if (stride) TG_CUDA_CHECK(cudaFuncSetAttribute(mt_sample_batch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-            int per_sm = (int)((200 * 1024) / (psmem + 512));
+            TG_CUDA_CHECK(cudaFuncSetAttribute(mt_sample_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+            int per_sm = (int)((200 * 1024) / (psmem + 1024));
             if (per_sm < 1) per_sm = 1;
-            if (per_sm > 16) per_sm = 16;
+            if (per_sm > 8) per_sm = 8;
             long long g = (long long)sms * per_sm;
-            if (g > need32) g = need32;
-            if (stride) mt_sample_batch_kernel<true><<<(int)g, MT_THREADS, psmem, st>>>(S);
-            else mt_sample_batch_kernel<false><<<(int)g, MT_THREADS, psmem, st>>>(S);
+            const long long need = (npairs + MTW_WARPS - 1) / MTW_WARPS;
+            if (g > need) g = need;
+            mt_sample_warp_kernel<<<(int)g, MTW_WARPS * 32, psmem, st>>>(S);
             TG_CUDA_CHECK(cudaGetLastError());
         }
     } else {
