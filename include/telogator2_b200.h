@@ -77,6 +77,13 @@ int tg_nw_wave_check(const tg_nw_scoring *sc, const tg_nw_job *h_jobs, int64_t n
 int tg_nw_scores_wave(const uint8_t *d_pool, const tg_nw_job *d_jobs, int64_t n_jobs, int max_n,
                       const tg_nw_scoring *sc, int32_t *d_scores, void *d_scratch, int32_t *d_counter,
                       void *stream);
+
+/* Same jobs, 32-bit cells, one alignment at a time (each half of a job is an item): for alignments whose
+ * scores leave the 16-bit envelope of tg_nw_scores_wave (tg_nw_wave_check -> TG_ERANGE), e.g. the
+ * untruncated consensus sequences of the collapse stage (tg_tvr.py:375-390).  Half the throughput. */
+int tg_nw_scores_wave32(const uint8_t *d_pool, const tg_nw_job *d_jobs, int64_t n_jobs, int max_n,
+                      const tg_nw_scoring *sc, int32_t *d_scores, void *d_scratch, int32_t *d_counter,
+                      void *stream);
 int tg_nw_generic_max_m(void);
 int tg_nw_scores_generic(const uint8_t *d_pool, const tg_nw_job *d_jobs, int64_t n_jobs, int max_m,
                          const tg_nw_scoring *sc, int32_t *d_scores, void *stream);

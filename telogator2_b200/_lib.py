@@ -51,7 +51,7 @@ class TgError(RuntimeError):
 _lib = None
 
 EXPORTS = ['tg_last_error', 'tg_version', 'tg_device_sm_count',
-           'tg_nw_wave_scratch_bytes', 'tg_nw_wave_check', 'tg_nw_scores_wave', 'tg_nw_generic_max_m',
+           'tg_nw_wave_scratch_bytes', 'tg_nw_wave_check', 'tg_nw_scores_wave', 'tg_nw_scores_wave32', 'tg_nw_generic_max_m',
            'tg_nw_scores_generic', 'tg_mt_shuffle', 'tg_dist_batch', 'tg_dist_batch_mt_work_bytes', 'tg_dist_epilogue', 'tg_int_alu_peak',
            'tg_kmer_table_bytes', 'tg_kmer_table_build', 'tg_kmer_table_build_pair', 'tg_scan_tile_bases', 'tg_scan_pack', 'tg_scan_basecount', 'tg_scan_orient',
            'tg_scan_density', 'tg_scan_hits_work_bytes', 'tg_scan_hits']
@@ -72,6 +72,7 @@ def load():
     L.tg_nw_wave_scratch_bytes.argtypes = [i32]
     L.tg_nw_wave_check.argtypes = [C.POINTER(NwScoring), vp, i64]
     L.tg_nw_scores_wave.argtypes = [vp, vp, i64, i32, C.POINTER(NwScoring), vp, vp, vp, vp]
+    L.tg_nw_scores_wave32.argtypes = [vp, vp, i64, i32, C.POINTER(NwScoring), vp, vp, vp, vp]
     L.tg_nw_scores_generic.argtypes = [vp, vp, i64, i32, C.POINTER(NwScoring), vp, vp]
     L.tg_mt_shuffle.argtypes = [vp, vp, i64, i32, i32, vp]
     L.tg_dist_batch.argtypes = [C.POINTER(DistBatchArgs), C.POINTER(NwScoring), vp]

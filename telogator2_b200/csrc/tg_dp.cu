@@ -96,16 +96,19 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
 }
 
 // byte k of p0 -> low half, byte k of p1 -> high half, upper bytes = replicated sign bit (= 0, S' < 128)
-template <int K>
+// WIDE (one alignment per job, 32-bit cells: sequences whose scores overflow 16 bits): byte k of p0, zero extended
+template <int K, bool WIDE>
 __device__ __forceinline__ uint32_t merge_scores(uint32_t p0, uint32_t p1)
 {
+    if (WIDE) return prmt(p0, 0u, K | 0x4440u);
     constexpr uint32_t sel = K | ((K | 8) << 4) | ((4 + K) << 8) | (((4 + K) | 8) << 12);
     return prmt(p0, p1, sel);
 }
 
+template <bool WIDE>
 __device__ __forceinline__ uint32_t cell(uint32_t diag, uint32_t sc, uint32_t up, uint32_t left)
 {
-    return __vimax3_u16x2(diag + sc, up, left);
+    return WIDE ? __vimax3_u32(diag + sc, up, left) : __vimax3_u16x2(diag + sc, up, left);
 }
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr)
@@ -138,16 +141,16 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr)
 }
 
 // One step of one lane: C packed cells of row r against the lane's C columns.
-template <int C>
+template <int C, bool WIDE>
 struct Strip;
 
-template <>
-struct Strip<16> {
+template <bool WIDE>
+struct Strip<16, WIDE> {
     static __device__ __forceinline__ void run(uint32_t (&H)[16], uint32_t d, uint32_t l, uint32_t pa0, uint32_t pa1)
     {
-        const uint4 q0 = lds128(pa0), q1 = lds128(pa1);
+        const uint4 q0 = lds128(pa0), q1 = WIDE ? q0 : lds128(pa1);
         uint32_t up;
-#define TG_CELL(c, qa, qb, k) up = H[c]; l = cell(d, merge_scores<k>(qa, qb), up, l); d = up; H[c] = l;
+#define TG_CELL(c, qa, qb, k) up = H[c]; l = cell<WIDE>(d, merge_scores<k, WIDE>(qa, qb), up, l); d = up; H[c] = l;
         TG_CELL(0, q0.x, q1.x, 0) TG_CELL(1, q0.x, q1.x, 1) TG_CELL(2, q0.x, q1.x, 2) TG_CELL(3, q0.x, q1.x, 3)
         TG_CELL(4, q0.y, q1.y, 0) TG_CELL(5, q0.y, q1.y, 1) TG_CELL(6, q0.y, q1.y, 2) TG_CELL(7, q0.y, q1.y, 3)
         TG_CELL(8, q0.z, q1.z, 0) TG_CELL(9, q0.z, q1.z, 1) TG_CELL(10, q0.z, q1.z, 2) TG_CELL(11, q0.z, q1.z, 3)
@@ -155,11 +158,11 @@ struct Strip<16> {
     }
 };
 
-template <>
-struct Strip<8> {
+template <bool WIDE>
+struct Strip<8, WIDE> {
     static __device__ __forceinline__ void run(uint32_t (&H)[8], uint32_t d, uint32_t l, uint32_t pa0, uint32_t pa1)
     {
-        const uint2 q0 = lds64(pa0), q1 = lds64(pa1);
+        const uint2 q0 = lds64(pa0), q1 = WIDE ? q0 : lds64(pa1);
         uint32_t up;
         TG_CELL(0, q0.x, q1.x, 0) TG_CELL(1, q0.x, q1.x, 1) TG_CELL(2, q0.x, q1.x, 2) TG_CELL(3, q0.x, q1.x, 3)
         TG_CELL(4, q0.y, q1.y, 0) TG_CELL(5, q0.y, q1.y, 1) TG_CELL(6, q0.y, q1.y, 2) TG_CELL(7, q0.y, q1.y, 3)
@@ -170,16 +173,17 @@ struct Strip<8> {
 // Two rows x 8 columns per step: row r0 (values a_c) and row r0 + 1 (values b_c) advance as two dependency chains
 // offset by one cell, which doubles the instruction-level parallelism of the 3-input-max chain.
 //   a_c = max(up_{c-1} + s0_c, up_c, a_{c-1})      b_c = max(a_{c-1} + s1_c, a_c, b_{c-1})
+template <bool WIDE>
 struct Strip2x8 {
     static __device__ __forceinline__ uint32_t run(uint32_t (&H)[8], uint32_t dg, uint32_t L0, uint32_t L1,
                                                    uint32_t p00, uint32_t p01, uint32_t p10, uint32_t p11)
     {
-        const uint2 q00 = lds64(p00), q01 = lds64(p01), q10 = lds64(p10), q11 = lds64(p11);
+        const uint2 q00 = lds64(p00), q01 = WIDE ? q00 : lds64(p01), q10 = lds64(p10), q11 = WIDE ? q10 : lds64(p11);
         uint32_t d0 = dg, la = L0, pa = L0, lb = L1, up, a;
 #define TG_CELL2(c, x0, y0, x1, y1, k)                    \
     up = H[c];                                             \
-    a = cell(d0, merge_scores<k>(x0, y0), up, la);         \
-    lb = cell(pa, merge_scores<k>(x1, y1), a, lb);         \
+    a = cell<WIDE>(d0, merge_scores<k, WIDE>(x0, y0), up, la);         \
+    lb = cell<WIDE>(pa, merge_scores<k, WIDE>(x1, y1), a, lb);         \
     d0 = up; la = a; pa = a; H[c] = lb;
         TG_CELL2(0, q00.x, q01.x, q10.x, q11.x, 0) TG_CELL2(1, q00.x, q01.x, q10.x, q11.x, 1)
         TG_CELL2(2, q00.x, q01.x, q10.x, q11.x, 2) TG_CELL2(3, q00.x, q01.x, q10.x, q11.x, 3)
@@ -190,16 +194,17 @@ struct Strip2x8 {
     }
 };
 
+template <bool WIDE>
 struct Strip2x16 {
     static __device__ __forceinline__ uint32_t run(uint32_t (&H)[16], uint32_t dg, uint32_t L0, uint32_t L1,
                                                    uint32_t p00, uint32_t p01, uint32_t p10, uint32_t p11)
     {
-        const uint4 q00 = lds128(p00), q01 = lds128(p01), q10 = lds128(p10), q11 = lds128(p11);
+        const uint4 q00 = lds128(p00), q01 = WIDE ? q00 : lds128(p01), q10 = lds128(p10), q11 = WIDE ? q10 : lds128(p11);
         uint32_t d0 = dg, la = L0, pa = L0, lb = L1, up, a;
 #define TG_CELL2(c, x0, y0, x1, y1, k)                    \
     up = H[c];                                             \
-    a = cell(d0, merge_scores<k>(x0, y0), up, la);         \
-    lb = cell(pa, merge_scores<k>(x1, y1), a, lb);         \
+    a = cell<WIDE>(d0, merge_scores<k, WIDE>(x0, y0), up, la);         \
+    lb = cell<WIDE>(pa, merge_scores<k, WIDE>(x1, y1), a, lb);         \
     d0 = up; la = a; pa = a; H[c] = lb;
 #define TG_QUAD2(c, f)                                                                                  \
     TG_CELL2(c, q00.f, q01.f, q10.f, q11.f, 0) TG_CELL2(c + 1, q00.f, q01.f, q10.f, q11.f, 1)          \
@@ -213,9 +218,11 @@ struct Strip2x16 {
 
 // Shared memory per warp: query profile [2][A+1][W] bytes, then row letters [row_cap] u16 (a0 | a1 << 8).
 // V = 0: 16 columns x 1 row per step, V = 1: 8 x 1, V = 2: 8 columns x 2 rows, V = 3: 16 columns x 2 rows per step
-template <int V, int MODE>
+// WIDE: one alignment per job in 32-bit cells (scores beyond 16 bits: long sequences); profile [1][A+1][W].
+template <int V, int MODE, bool WIDE>
 __global__ void __launch_bounds__(WAVE_MAX_WARPS * 32, 1) nw_wave_kernel(const __grid_constant__ WaveParams P)
 {
+    constexpr int NH = WIDE ? 1 : 2;                                         // alignments per job
     constexpr int C = (V == 0 || V == 3) ? 16 : 8;
     constexpr int RR = (V >= 2) ? 2 : 1;
     constexpr int W = 32 * C;
@@ -224,10 +231,10 @@ __global__ void __launch_bounds__(WAVE_MAX_WARPS * 32, 1) nw_wave_kernel(const _
     const int A = P.A, A1 = P.A + 1;
     uint8_t *s_sp = smem;                                                    // MAXA*MAXA bytes
     constexpr int ROFF = (RR == 2) ? 64 : 0;                                 // rows[ROFF + r] = letters of row r
-    const size_t per_warp = (size_t)2 * A1 * W + (size_t)P.row_cap * 2 + 512;
-    uint8_t *prof = smem + MAXA * MAXA + (size_t)warp * per_warp;            // [2][A+1][W]
-    uint16_t *rows = reinterpret_cast<uint16_t *>(prof + (size_t)2 * A1 * W);
-    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(prof + (size_t)2 * A1 * W + (size_t)P.row_cap * 2);   // 64 x uint2
+    const size_t per_warp = (size_t)NH * A1 * W + (size_t)P.row_cap * 2 + 512;
+    uint8_t *prof = smem + MAXA * MAXA + (size_t)warp * per_warp;            // [NH][A+1][W]
+    uint16_t *rows = reinterpret_cast<uint16_t *>(prof + (size_t)NH * A1 * W);
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(prof + (size_t)NH * A1 * W + (size_t)P.row_cap * 2);   // 64 x uint2
     for (int i = threadIdx.x; i < MAXA * MAXA; i += blockDim.x) s_sp[i] = P.sp[i];
     __syncthreads();
 
@@ -237,7 +244,7 @@ __global__ void __launch_bounds__(WAVE_MAX_WARPS * 32, 1) nw_wave_kernel(const _
     const uint32_t prof_s = (uint32_t)__cvta_generic_to_shared(prof);
     const uint32_t rows_s = (uint32_t)__cvta_generic_to_shared(rows);
     const uint32_t pb0 = prof_s + lane * C;
-    const uint32_t pb1 = prof_s + (uint32_t)A1 * W + lane * C;
+    const uint32_t pb1 = WIDE ? pb0 : prof_s + (uint32_t)A1 * W + lane * C;
 
     for (;;) {
         unsigned long long jid = 0;
@@ -246,12 +253,33 @@ __global__ void __launch_bounds__(WAVE_MAX_WARPS * 32, 1) nw_wave_kernel(const _
         if (jid >= (unsigned long long)P.n_jobs) break;
         long long row0, row1, col0, col1;
         int n0, n1, m0, m1, out0, out1;
-        if (MODE == JOBS_EXPLICIT) {
+        if (MODE == JOBS_EXPLICIT && WIDE) {
+            // item = (job, half)
+            const tg_nw_job *J = P.jobs + (jid >> 1);
+            const int h = (int)(jid & 1);
+            if (J->out[h] < 0) continue;
+            row0 = row1 = J->row_off[h]; col0 = col1 = J->col_off[h];
+            n0 = n1 = J->n[h]; m0 = m1 = J->m[h];
+            out0 = J->out[h]; out1 = -1;
+        } else if (MODE == JOBS_EXPLICIT) {
             const tg_nw_job *J = P.jobs + jid;
             row0 = J->row_off[0]; row1 = J->row_off[1];
             col0 = J->col_off[0]; col1 = J->col_off[1];
             n0 = J->n[0]; n1 = J->n[1]; m0 = J->m[0]; m1 = J->m[1];
             out0 = J->out[0]; out1 = J->out[1];
+        } else if (MODE == JOBS_PHASE_A && WIDE) {
+            const long long qa = P.q0 + (long long)jid;
+            const PairDesc da = describe_pair(P, qa);
+            row0 = row1 = da.off_i; col0 = col1 = da.off_j; n0 = n1 = da.n; m0 = m1 = da.m;
+            out0 = (int)(qa - P.q0); out1 = -1;
+        } else if (MODE == JOBS_PHASE_B && WIDE) {
+            const long long qa = P.q0 + (long long)(jid / P.R);
+            const int ta = (int)(jid % P.R);
+            if (P.flags[qa - P.q0]) continue;
+            const PairDesc da = describe_pair(P, qa);
+            row0 = row1 = P.shuf_base + (qa - P.q0) * P.slot + (long long)ta * (da.n + da.m); col0 = col1 = row0 + da.n;
+            n0 = n1 = da.n; m0 = m1 = da.m;
+            out0 = (int)((qa - P.q0) * P.R + ta); out1 = -1;
         } else if (MODE == JOBS_PHASE_A) {
             // job = sorted-space pairs q0 + 2*jid and q0 + 2*jid + 1 (tg_align.py:125)
             const long long qa = P.q0 + 2 * (long long)jid, qb = qa + 1;
@@ -311,10 +339,10 @@ __global__ void __launch_bounds__(WAVE_MAX_WARPS * 32, 1) nw_wave_kernel(const _
                 const int b1 = (j1 >= 0) ? (int)__ldg(P.pool + col1 + j1) : -1;
                 for (int a = 0; a < A; a++) {
                     prof[(size_t)a * W + x] = (b0 >= 0) ? s_sp[a * MAXA + b0] : (uint8_t)0;
-                    prof[(size_t)(A1 + a) * W + x] = (b1 >= 0) ? s_sp[a * MAXA + b1] : (uint8_t)0;
+                    if (!WIDE) prof[(size_t)(A1 + a) * W + x] = (b1 >= 0) ? s_sp[a * MAXA + b1] : (uint8_t)0;
                 }
                 prof[(size_t)A * W + x] = 0;
-                prof[(size_t)(A1 + A) * W + x] = 0;
+                if (!WIDE) prof[(size_t)(A1 + A) * W + x] = 0;
             }
             __syncwarp();
 
@@ -332,7 +360,7 @@ __global__ void __launch_bounds__(WAVE_MAX_WARPS * 32, 1) nw_wave_kernel(const _
                     uint32_t left_in = __shfl_up_sync(TG_FULL_MASK, H[C - 1], 1);
                     if (lane == 0) left_in = 0u;
                     if ((unsigned)r < (unsigned)N) {
-                        Strip<C>::run(H, prev_left, left_in, pb0 + (ap & 0xffu) * W, pb1 + (ap >> 8) * W);
+                        Strip<C, WIDE>::run(H, prev_left, left_in, pb0 + (ap & 0xffu) * W, pb1 + (ap >> 8) * W);
                         if (lane == 31) *bw = H[C - 1];
                         ap = lds_u16(rows_s + 2 * (r + 1));
                     } else if (r == -1) ap = lds_u16(rows_s);
@@ -352,7 +380,7 @@ __global__ void __launch_bounds__(WAVE_MAX_WARPS * 32, 1) nw_wave_kernel(const _
                     const uint32_t bl = __shfl_sync(TG_FULL_MASK, bcur, s & 31);
                     if (lane == 0) left_in = bl;
                     if ((unsigned)r < (unsigned)N) {
-                        Strip<C>::run(H, prev_left, left_in, pb0 + (ap & 0xffu) * W, pb1 + (ap >> 8) * W);
+                        Strip<C, WIDE>::run(H, prev_left, left_in, pb0 + (ap & 0xffu) * W, pb1 + (ap >> 8) * W);
                         if (lane == 31) *bw = H[C - 1];
                         ap = lds_u16(rows_s + 2 * (r + 1));
                     } else if (r == -1) ap = lds_u16(rows_s);
@@ -384,7 +412,7 @@ __global__ void __launch_bounds__(WAVE_MAX_WARPS * 32, 1) nw_wave_kernel(const _
                 const uint2 rb = lds64(ring_s + 8 * (k & 63));
                 if (lane == 0) { L0 = rb.x; L1 = rb.y; }
                 if (k < 0) { L0 = 0u; L1 = 0u; }
-                using S2 = typename std::conditional<C == 16, Strip2x16, Strip2x8>::type;
+                using S2 = typename std::conditional<C == 16, Strip2x16<WIDE>, Strip2x8<WIDE>>::type;
                 A7 = S2::run(H, prevL1, L0, L1,
                              pb0 + (ap2 & 0xffu) * W, pb1 + ((ap2 >> 8) & 0xffu) * W,
                              pb0 + ((ap2 >> 16) & 0xffu) * W, pb1 + (ap2 >> 24) * W);
@@ -401,8 +429,8 @@ __global__ void __launch_bounds__(WAVE_MAX_WARPS * 32, 1) nw_wave_kernel(const _
                 for (int c = 0; c < C; c++) {
                     const int X = blk * W + lane * C + c;
                     const int j0 = X - pad0 + 1, j1 = X - pad1 + 1;     // 1-based column
-                    if (j0 >= 1) rf0 = max(rf0, (int)(H[c] & 0xffffu) + g * (n0 + j0) + gr * (m0 - j0));
-                    if (j1 >= 1) rf1 = max(rf1, (int)(H[c] >> 16) + g * (n1 + j1) + gr * (m1 - j1));
+                    if (j0 >= 1) rf0 = max(rf0, (int)(WIDE ? H[c] : (H[c] & 0xffffu)) + g * (n0 + j0) + gr * (m0 - j0));
+                    if (!WIDE && j1 >= 1) rf1 = max(rf1, (int)(H[c] >> 16) + g * (n1 + j1) + gr * (m1 - j1));
                 }
             }
         }
@@ -410,8 +438,8 @@ __global__ void __launch_bounds__(WAVE_MAX_WARPS * 32, 1) nw_wave_kernel(const _
         if (!P.right_free) {
             // the padding rows carried row n of each alignment down to row N: lane 31's last column is H'[n][m]
             if (lane == 31) {
-                if (out0 >= 0) P.scores[out0] = (int)(H[C - 1] & 0xffffu) + g * (n0 + m0);
-                if (out1 >= 0) P.scores[out1] = (int)(H[C - 1] >> 16) + g * (n1 + m1);
+                if (out0 >= 0) P.scores[out0] = (int)(WIDE ? H[C - 1] : (H[C - 1] & 0xffffu)) + g * (n0 + m0);
+                if (!WIDE && out1 >= 0) P.scores[out1] = (int)(H[C - 1] >> 16) + g * (n1 + m1);
             }
         } else {
             // last column: bord[r] = H'[r+1][m]; H[i][m] + gr*(n-i) = H'[i][m] + g*(i+m) + gr*(n-i)
@@ -419,8 +447,8 @@ __global__ void __launch_bounds__(WAVE_MAX_WARPS * 32, 1) nw_wave_kernel(const _
             for (int rr = lane; rr < N; rr += 32) {
                 const uint32_t v = __ldcg(bcol + rr);
                 const int i = rr + 1;
-                if (i <= n0) rf0 = max(rf0, (int)(v & 0xffffu) + g * (i + m0) + gr * (n0 - i));
-                if (i <= n1) rf1 = max(rf1, (int)(v >> 16) + g * (i + m1) + gr * (n1 - i));
+                if (i <= n0) rf0 = max(rf0, (int)(WIDE ? v : (v & 0xffffu)) + g * (i + m0) + gr * (n0 - i));
+                if (!WIDE && i <= n1) rf1 = max(rf1, (int)(v >> 16) + g * (i + m1) + gr * (n1 - i));
             }
             // whole sequence against end gaps only: H[n][0] + gr*m and H[0][m] + gr*n (gap_left == g)
             rf0 = max(rf0, max(n0 * g + gr * m0, m0 * g + gr * n0));
@@ -1099,25 +1127,27 @@ TG_EXPORT int tg_nw_wave_check(const tg_nw_scoring *sc, const tg_nw_job *h_jobs,
     return TG_OK;
 }
 
-template <int V, int MODE>
+template <int V, int MODE, bool WIDE>
 static int wave_launch_t(const WaveParams &P, int grid, int warps, size_t smem, cudaStream_t st)
 {
-    TG_CUDA_CHECK(cudaFuncSetAttribute(nw_wave_kernel<V, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nw_wave_kernel<V, MODE><<<grid, warps * 32, smem, st>>>(P);
+    TG_CUDA_CHECK(cudaFuncSetAttribute(nw_wave_kernel<V, MODE, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nw_wave_kernel<V, MODE, WIDE><<<grid, warps * 32, smem, st>>>(P);
     TG_CUDA_CHECK(cudaGetLastError());
     return TG_OK;
 }
 
-template <int V>
+template <int V, bool WIDE = false>
 static int wave_launch_v(const WaveParams &P, int mode, int grid, int warps, size_t smem, cudaStream_t st)
 {
-    if (mode == JOBS_EXPLICIT) return wave_launch_t<V, JOBS_EXPLICIT>(P, grid, warps, smem, st);
-    if (mode == JOBS_PHASE_A) return wave_launch_t<V, JOBS_PHASE_A>(P, grid, warps, smem, st);
-    return wave_launch_t<V, JOBS_PHASE_B>(P, grid, warps, smem, st);
+    if (mode == JOBS_EXPLICIT) return wave_launch_t<V, JOBS_EXPLICIT, WIDE>(P, grid, warps, smem, st);
+    if (mode == JOBS_PHASE_A) return wave_launch_t<V, JOBS_PHASE_A, WIDE>(P, grid, warps, smem, st);
+    return wave_launch_t<V, JOBS_PHASE_B, WIDE>(P, grid, warps, smem, st);
 }
 
-static int wave_launch(const WaveParams &P, int mode, int variant, int grid, int warps, size_t smem, cudaStream_t st)
+// wide (32-bit cells) exists for the default geometry only
+static int wave_launch(const WaveParams &P, int mode, int variant, int grid, int warps, size_t smem, cudaStream_t st, bool wide = false)
 {
+    if (wide) return wave_launch_v<3, true>(P, mode, grid, warps, smem, st);
     if (variant == 0) return wave_launch_v<0>(P, mode, grid, warps, smem, st);
     if (variant == 1) return wave_launch_v<1>(P, mode, grid, warps, smem, st);
     if (variant == 3) return wave_launch_v<3>(P, mode, grid, warps, smem, st);
@@ -1125,7 +1155,7 @@ static int wave_launch(const WaveParams &P, int mode, int variant, int grid, int
 }
 
 // shared set-up of the three job modes
-static int wave_setup(WaveParams &P, const tg_nw_scoring *sc, int max_n, int *C_out, int *warps_out, size_t *smem_out)
+static int wave_setup(WaveParams &P, const tg_nw_scoring *sc, int max_n, int *C_out, int *warps_out, size_t *smem_out, bool wide = false)
 {
     wave_env();
     int max_sp = 0;
@@ -1138,20 +1168,20 @@ static int wave_setup(WaveParams &P, const tg_nw_scoring *sc, int max_n, int *C_
     for (int a = 0; a < MAXA; a++)
         for (int b = 0; b < MAXA; b++)
             P.sp[a * MAXA + b] = (a < sc->alphabet && b < sc->alphabet) ? (uint8_t)(sc->sub[a * MAXA + b] - 2 * sc->gap) : 0;
-    const int C = (g_wave_variant == 0 || g_wave_variant == 3) ? 16 : 8;
-    const size_t per_warp = (size_t)2 * (sc->alphabet + 1) * 32 * C + (size_t)P.row_cap * 2 + 512;
+    const int C = (wide || g_wave_variant == 0 || g_wave_variant == 3) ? 16 : 8;
+    const size_t per_warp = (size_t)(wide ? 1 : 2) * (sc->alphabet + 1) * 32 * C + (size_t)P.row_cap * 2 + 512;
     int warps = (int)((226 * 1024 - MAXA * MAXA) / per_warp);
     if (warps > WAVE_MAX_WARPS) warps = WAVE_MAX_WARPS;
     if (g_wave_warps && warps > g_wave_warps) warps = g_wave_warps;
     if (warps < 1) return tg_set_err(TG_ERANGE, "sequences of %d rows do not fit the wave kernel's shared memory", max_n);
-    *C_out = g_wave_variant; *warps_out = warps;
+    *C_out = wide ? 3 : g_wave_variant; *warps_out = warps;
     *smem_out = MAXA * MAXA + (size_t)warps * per_warp;
     return TG_OK;
 }
 
-TG_EXPORT int tg_nw_scores_wave(const uint8_t *d_pool, const tg_nw_job *d_jobs, int64_t n_jobs, int max_n,
-                                const tg_nw_scoring *sc, int32_t *d_scores, void *d_scratch, int32_t *d_counter,
-                                void *stream)
+static int nw_scores_wave(const uint8_t *d_pool, const tg_nw_job *d_jobs, int64_t n_jobs, int max_n,
+                          const tg_nw_scoring *sc, int32_t *d_scores, void *d_scratch, int32_t *d_counter,
+                          void *stream, bool wide)
 {
     if (n_jobs <= 0) return TG_OK;
     if (!d_pool || !d_jobs || !d_scores || !d_scratch || !d_counter) return tg_set_err(TG_EINVAL, "NULL device pointer");
@@ -1161,17 +1191,31 @@ TG_EXPORT int tg_nw_scores_wave(const uint8_t *d_pool, const tg_nw_job *d_jobs, 
     memset(&P, 0, sizeof(P));
     int C, warps;
     size_t smem;
-    int rc = wave_setup(P, sc, max_n, &C, &warps, &smem);
+    int rc = wave_setup(P, sc, max_n, &C, &warps, &smem, wide);
     if (rc != TG_OK) return rc;
-    P.pool = d_pool; P.jobs = d_jobs; P.n_jobs = n_jobs; P.scores = d_scores;
+    P.pool = d_pool; P.jobs = d_jobs; P.n_jobs = wide ? 2 * n_jobs : n_jobs; P.scores = d_scores;
     P.scratch = reinterpret_cast<uint32_t *>(d_scratch);
     P.counter = reinterpret_cast<unsigned long long *>(d_counter);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     TG_CUDA_CHECK(cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), st));
     long long grid = sms;
-    const long long ctas_needed = (n_jobs + warps - 1) / warps;
+    const long long ctas_needed = (P.n_jobs + warps - 1) / warps;
     if (ctas_needed < grid) grid = ctas_needed;
-    return wave_launch(P, JOBS_EXPLICIT, C, (int)grid, warps, smem, st);
+    return wave_launch(P, JOBS_EXPLICIT, C, (int)grid, warps, smem, st, wide);
+}
+
+TG_EXPORT int tg_nw_scores_wave(const uint8_t *d_pool, const tg_nw_job *d_jobs, int64_t n_jobs, int max_n,
+                                const tg_nw_scoring *sc, int32_t *d_scores, void *d_scratch, int32_t *d_counter,
+                                void *stream)
+{
+    return nw_scores_wave(d_pool, d_jobs, n_jobs, max_n, sc, d_scores, d_scratch, d_counter, stream, false);
+}
+
+TG_EXPORT int tg_nw_scores_wave32(const uint8_t *d_pool, const tg_nw_job *d_jobs, int64_t n_jobs, int max_n,
+                                  const tg_nw_scoring *sc, int32_t *d_scores, void *d_scratch, int32_t *d_counter,
+                                  void *stream)
+{
+    return nw_scores_wave(d_pool, d_jobs, n_jobs, max_n, sc, d_scores, d_scratch, d_counter, stream, true);
 }
 
 static int mt_upload_base();
@@ -1198,13 +1242,15 @@ TG_EXPORT int tg_dist_batch(const tg_dist_batch_args *a, const tg_nw_scoring *sc
     memset(&P, 0, sizeof(P));
     int C, warps;
     size_t smem;
-    int rc = wave_setup(P, sc, a->max_len, &C, &warps, &smem);
-    if (rc != TG_OK) return rc;
+    bool wide = false;
     {
         int max_sp = 0;
-        wave_envelope(sc, &max_sp);
-        if ((long long)max_sp * a->max_len > 65535) return tg_set_err(TG_ERANGE, "max_len %d overflows 16-bit scores", a->max_len);
+        int rc0 = wave_envelope(sc, &max_sp);
+        if (rc0 != TG_OK) return rc0;
+        wide = (long long)max_sp * a->max_len > 65535;          // 16-bit cells would overflow: one alignment per job, 32-bit cells
     }
+    int rc = wave_setup(P, sc, a->max_len, &C, &warps, &smem, wide);
+    if (rc != TG_OK) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     P.pool = a->d_pool; P.jobs = nullptr; P.scores = a->d_aln;
     P.scratch = reinterpret_cast<uint32_t *>(a->d_scratch);
@@ -1214,9 +1260,9 @@ TG_EXPORT int tg_dist_batch(const tg_dist_batch_args *a, const tg_nw_scoring *sc
     P.q0 = a->q0; P.q1 = a->q1; P.flags = a->d_flags; P.shuf_base = a->shuf_base; P.slot = a->slot;
     auto grid_for_jobs = [&](long long jobs) { long long g = (jobs + warps - 1) / warps; return (int)(g < sms ? g : sms); };
     // ---- phase A: the real alignment of every pair ----
-    P.n_jobs = (npairs + 1) / 2;
+    P.n_jobs = wide ? npairs : (npairs + 1) / 2;
     TG_CUDA_CHECK(cudaMemsetAsync(a->d_counter, 0, sizeof(unsigned long long), st));
-    rc = wave_launch(P, JOBS_PHASE_A, C, grid_for_jobs(P.n_jobs), warps, smem, st);
+    rc = wave_launch(P, JOBS_PHASE_A, C, grid_for_jobs(P.n_jobs), warps, smem, st, wide);
     if (rc != TG_OK) return rc;
     // ---- identity score + early-out flags ----
     FlagParams F;
@@ -1311,9 +1357,9 @@ TG_EXPORT int tg_dist_batch(const tg_dist_batch_args *a, const tg_nw_scoring *sc
     }
     // ---- phase B: alignments of the shuffled pairs ----
     P.scores = a->d_rnd;
-    P.n_jobs = (a->R % 2 == 0) ? npairs * (a->R / 2) : ((npairs + 1) / 2) * a->R;
+    P.n_jobs = wide ? npairs * a->R : (a->R % 2 == 0) ? npairs * (a->R / 2) : ((npairs + 1) / 2) * a->R;
     TG_CUDA_CHECK(cudaMemsetAsync(a->d_counter, 0, sizeof(unsigned long long), st));
-    return wave_launch(P, JOBS_PHASE_B, C, grid_for_jobs(P.n_jobs), warps, smem, st);
+    return wave_launch(P, JOBS_PHASE_B, C, grid_for_jobs(P.n_jobs), warps, smem, st, wide);
 }
 
 TG_EXPORT int tg_nw_generic_max_m(void) { return 24000; }

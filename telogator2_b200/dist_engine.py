@@ -16,6 +16,7 @@ MAX_SEQ_DIST = 10.0                 # tg_align.py:22
 MIN_SEQ_DIST = 0.0001               # tg_align.py:24
 IDEN_SCORE_SCALAR_CHEAT = 0.900     # tg_align.py:26
 NOT_COMPUTED = np.iinfo(np.int32).min
+MAX_WAVE32_LEN = 20000             # shared-memory budget of the wave and sampling kernels (rows + pools per warp)
 
 
 def _as_int(x, what):
@@ -180,7 +181,7 @@ class DistEngine:
         self.pairs_per_batch = pairs_per_batch
         self.shuffle_bytes_per_batch = shuffle_bytes_per_batch
         self.single_kernel_shuffle = single_kernel_shuffle or bool(int(__import__('os').environ.get('TG_SINGLE_KERNEL_SHUFFLE', '0')))
-        self.stats = {'cells': 0, 'wave_jobs': 0, 'generic_jobs': 0, 'launches': 0, 'pairs': 0, 'early_out': 0,
+        self.stats = {'cells': 0, 'wave_jobs': 0, 'wave32_jobs': 0, 'generic_jobs': 0, 'launches': 0, 'pairs': 0, 'early_out': 0,
                       'h2d_bytes': 0, 'd2h_bytes': 0}
         # device epilogue: a distance is recomputed on the host when moving log() by 2^-margin_log2 (relative; 64 ulp by
         # default, far beyond any libm's error) could change its float32 value -- about 1 pair in 10^6
@@ -196,15 +197,19 @@ class DistEngine:
         return t.to(self.device, non_blocking=False)
 
     def _wave_ok_mask(self, jobs, sub):
+        """(jobs the 16-bit wave kernel takes, jobs the 32-bit wave kernel takes); the rest goes to the generic kernel."""
         sc = self.sc
+        none = np.zeros(len(jobs), dtype=bool)
         if self.force_generic or sc.gap_left != sc.gap or sc.gap_right < sc.gap:
-            return np.zeros(len(jobs), dtype=bool)
+            return none, none
         sp = sub - 2 * sc.gap
         if sp.min() < 0 or sp.max() > 127 or sub.shape[0] >= _lib.MAXA:
-            return np.zeros(len(jobs), dtype=bool)
+            return none, none
         N = np.maximum(jobs['n'][:, 0], jobs['n'][:, 1]).astype(np.int64)
         M = np.maximum(jobs['m'][:, 0], jobs['m'][:, 1]).astype(np.int64)
-        return int(sp.max()) * np.minimum(N, M) <= 65535
+        ok16 = int(sp.max()) * np.minimum(N, M) <= 65535
+        ok32 = ~ok16 & (N <= MAX_WAVE32_LEN)
+        return ok16, ok32
 
     def run_jobs(self, d_pool, jobs, sub, n_out):
         """Launch the NW kernels for `jobs` (host record array); returns int32 scores on the host."""
@@ -213,19 +218,22 @@ class DistEngine:
         if len(jobs) == 0:
             return d_scores[:n_out].cpu().numpy()
         cstruct = self.sc.c_struct(sub)
-        ok = self._wave_ok_mask(jobs, sub)
-        wave, gen = jobs[ok], jobs[~ok]
+        ok16, ok32 = self._wave_ok_mask(jobs, sub)
+        gen = jobs[~(ok16 | ok32)]
         st = _lib.stream_ptr(torch)
-        if len(wave):
+        for wave, fn, key in ((jobs[ok16], self.L.tg_nw_scores_wave, 'wave_jobs'), (jobs[ok32], self.L.tg_nw_scores_wave32, 'wave32_jobs')):
+            if not len(wave):
+                continue
             max_n = int(max(wave['n'].max(), 1))
             need = self.L.tg_nw_wave_scratch_bytes(max_n)
             if self._scratch is None or self._scratch.numel() < need:
                 self._scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
+            if self._counter is None:
                 self._counter = torch.zeros(2, dtype=torch.int32, device=self.device)
             d_jobs = self._to_dev(wave)
-            _lib.check(self.L.tg_nw_scores_wave(_lib.dptr(d_pool), _lib.dptr(d_jobs), len(wave), max_n, C.byref(cstruct),
-                                                _lib.dptr(d_scores), _lib.dptr(self._scratch), _lib.dptr(self._counter), st))
-            self.stats['wave_jobs'] += len(wave)
+            _lib.check(fn(_lib.dptr(d_pool), _lib.dptr(d_jobs), len(wave), max_n, C.byref(cstruct),
+                          _lib.dptr(d_scores), _lib.dptr(self._scratch), _lib.dptr(self._counter), st))
+            self.stats[key] += len(wave)
             self.stats['launches'] += 1
         if len(gen):
             max_m = int(gen['m'].max())
@@ -245,7 +253,8 @@ class DistEngine:
         if self.force_generic or sc.gap_left != sc.gap or sc.gap_right < sc.gap or sub.shape[0] >= _lib.MAXA:
             return False
         sp = sub - 2 * sc.gap
-        return sp.min() >= 0 and sp.max() <= 127 and int(sp.max()) * max_len <= 65535
+        # beyond 16-bit scores (int(sp.max()) * max_len > 65535) the library switches to 32-bit cells by itself
+        return sp.min() >= 0 and sp.max() <= 127 and max_len <= MAX_WAVE32_LEN
 
     def prepare(self, sequences):
         """Encode the sequences and make them resident on the device.  Returns the state consumed by matrix_device() /
@@ -299,7 +308,8 @@ class DistEngine:
         need = self.L.tg_nw_wave_scratch_bytes(max_len)
         if self._scratch is None or self._scratch.numel() < need:
             self._scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
-        dev = dict(n_own=n_own, ranges=ranges, n_pairs=n_pairs, world=world, R=R, streamed=streamed,
+        wide = int((st['sub'] - 2 * self.sc.gap).max()) * max_len > 65535      # the library's rule (tg_dist_batch): 32-bit cells
+        dev = dict(n_own=n_own, ranges=ranges, n_pairs=n_pairs, world=world, R=R, streamed=streamed, wide=wide,
                    aln=torch.empty(max(n_own, 1), dtype=torch.int32, device=self.device),
                    rnd=torch.full((max(n_own, 1), max(R, 1)), NOT_COMPUTED, dtype=torch.int32, device=self.device),
                    flags=torch.empty(max(n_own, 1), dtype=torch.uint8, device=self.device),
@@ -392,7 +402,7 @@ class DistEngine:
         self.stats['pairs'] += dev['n_own']
         self.stats['early_out'] += int(tail[2])
         self.stats['cells'] += int(tail[0]) + int(tail[1])
-        self.stats['wave_jobs'] += dev['n_own']
+        self.stats['wave32_jobs' if dev['wide'] else 'wave_jobs'] += dev['n_own']
         return D
 
     def _pair_scores_fast(self, st, adjust_lens, min_viable, R, rng_seed, shard, streamed=True):
@@ -411,7 +421,7 @@ class DistEngine:
         self.stats['pairs'] += n_own
         self.stats['early_out'] += int(flags.sum())
         self.stats['cells'] += int(cells.sum()) + R * int(cells[flags == 0].sum())
-        self.stats['wave_jobs'] += n_own
+        self.stats['wave32_jobs' if dev['wide'] else 'wave_jobs'] += n_own
         res = dict(aln=aln, rnd=np.ascontiguousarray(rnd), iden=iden, n=shape[:, 0].copy(), m=shape[:, 1].copy(), order=st['order'])
         if dev['world'] > 1:
             res['ranges'] = dev['ranges']

@@ -113,10 +113,24 @@ def test_generic_kernel_all_gap_modes(tga, colorvecs):
         _check_matrix(tga, seqs, None, gap_bool, True, False, 1, 12, force_generic=(gap_bool[0] is True))
 
 
-def test_long_sequences_fall_back_to_int32(tga):
+def test_long_sequences_use_32bit_cells(tga):
+    """Scores beyond 16 bits (collapse stage, untruncated consensus sequences, tg_tvr.py:375-390): the wave kernel runs
+    one alignment per job in 32-bit cells, on the device-driven path and on the explicit-job path."""
+    from telogator2_b200.dist_engine import DistEngine, Scoring, canonical_order
     rng = np.random.default_rng(9)
-    seqs = [''.join(rng.choice(list('CCCCDEFA'), n)) for n in (6000, 5500, 7001)]
+    seqs = [''.join(rng.choice(list('CCCCDEFA'), n)) for n in (6000, 5500, 7001, 5042, 300)]
     eng = _check_matrix(tga, seqs, None, (True, False), False, False, 1, 3)
+    assert eng.stats['wave32_jobs'] == 10 and eng.stats['generic_jobs'] == 0
+    eng = _check_matrix(tga, seqs, 'tvr', (True, True), True, True, 2, 11)
+    assert eng.stats['wave32_jobs'] == 10 and eng.stats['generic_jobs'] == 0
+    # explicit jobs: only the alignments that need it go to the 32-bit kernel
+    aligner = tga.get_aligner_object(None, (True, False), 'tvr')
+    e2 = DistEngine(Scoring.from_aligner(aligner))
+    res = e2.pair_scores(seqs, False, False, 1, 3, pair_idx=np.arange(10, dtype=np.int64))
+    _, aln, rnd, _ = oracle.dist_matrix_c(seqs, _P(None, (True, False)), False, False, 1, 3, want_scores=True)
+    assert np.array_equal(res['aln'], aln) and np.array_equal(res['rnd'], rnd)
+    assert e2.stats['wave32_jobs'] > 0 and e2.stats['wave_jobs'] > 0 and e2.stats['generic_jobs'] == 0
+    eng = _check_matrix(tga, seqs[:3], None, (True, False), False, False, 1, 3, force_generic=True)
     assert eng.stats['generic_jobs'] > 0
 
 
