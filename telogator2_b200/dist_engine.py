@@ -76,7 +76,8 @@ class Scoring:
         for s in sequences:
             if len(s) == 0:
                 raise ValueError('sequence has zero length')       # Biopython raises the same from score()
-        raw = np.frombuffer(''.join(sequences).encode('latin-1'), dtype=np.uint8)
+        raw_bytes = ''.join(sequences).encode('latin-1')
+        raw = np.frombuffer(raw_bytes, dtype=np.uint8)
         off = np.zeros(len(sequences) + 1, dtype=np.int64)
         off[1:] = np.cumsum([len(s) for s in sequences])
         lut = np.full(256, 255, dtype=np.uint8)
@@ -86,24 +87,25 @@ class Scoring:
             A = len(self.alphabet)
             sub = self.sub
         else:
-            present = np.unique(raw)
+            present = np.flatnonzero(np.bincount(raw, minlength=256))
             A = len(present)
             lut[present] = np.arange(A, dtype=np.uint8)
             sub = np.full((A, A), self.mismatch, dtype=np.int64)
             np.fill_diagonal(sub, self.match)
         if A > _lib.MAXA:
             raise NotImplementedError(f'alphabet of {A} symbols exceeds the {_lib.MAXA} the kernels support')
-        codes = lut[raw]
-        if (codes == 255).any():
+        tb = raw_bytes.translate(lut.tobytes())                  # bytes.translate / `in`: C speed
+        if b'\xff' in tb:
             raise ValueError('sequence contains letters not in the alphabet')
         # keep only the letters that occur: the wave kernel's shared-memory profile has one row per letter, so a
         # smaller alphabet means more resident warps
-        present = np.unique(codes)
+        present = np.array([k for k in range(A) if bytes([k]) in tb], dtype=np.int64)
         if len(present) < A:
             remap = np.zeros(256, dtype=np.uint8)
             remap[present] = np.arange(len(present), dtype=np.uint8)
-            codes = remap[codes]
+            tb = tb.translate(remap.tobytes())
             sub = np.ascontiguousarray(sub[np.ix_(present, present)])
+        codes = np.frombuffer(bytearray(tb), dtype=np.uint8)
         return np.ascontiguousarray(codes), off, sub
 
     def c_struct(self, sub):
@@ -273,10 +275,11 @@ class DistEngine:
                   d_order=torch.from_numpy(order).to(self.device), d_cs=None, cstruct=self.sc.c_struct(sub), pool=None)
         self.stats['h2d_bytes'] += len(codes) + off.nbytes + order.nbytes
         if self.sc.alphabet is not None:
-            cs = np.zeros(len(codes) + 1, dtype=np.int32)
-            np.cumsum(np.diag(sub)[codes], out=cs[1:])
-            st['d_cs'] = torch.from_numpy(cs).to(self.device)
-            self.stats['h2d_bytes'] += cs.nbytes
+            # prefix sums of the substitution-matrix diagonal over the codes (identity score, tg_align.py:127-134)
+            diag = torch.from_numpy(np.ascontiguousarray(np.diag(sub)).astype(np.int32)).to(self.device)
+            cs = torch.zeros(len(codes) + 1, dtype=torch.int32, device=self.device)
+            torch.cumsum(diag[st['d_codes'].long()], 0, dtype=torch.int32, out=cs[1:])
+            st['d_cs'] = cs
         return st
 
     def _launch_fast(self, st, adjust_lens, min_viable, R, rng_seed, shard, streamed, d_matrix=None):

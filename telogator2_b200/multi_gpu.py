@@ -116,7 +116,15 @@ def sharded_dist_matrix(engine, sequences, adjust_lens, min_viable, R, rng_seed,
     D = compute((rank, world) if world > 1 else None)
     if world > 1:
         D = reduce_matrix(D, dist)
-    out = D.cpu().numpy()
+    if D.is_cuda:
+        # page-locked destination (torch caches and reuses these blocks): the copy runs at PCIe speed and the returned
+        # ndarray owns the block until it is garbage collected
+        import torch
+        host = torch.empty(D.shape, dtype=D.dtype, pin_memory=True)
+        host.copy_(D)
+        out = host.numpy()
+    else:
+        out = D.numpy()
     if engine is not None:
         engine.stats['d2h_bytes'] += out.nbytes
     return out
