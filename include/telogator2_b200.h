@@ -233,6 +233,45 @@ int tg_scan_hits(const uint32_t *d_pack2, const uint32_t *d_nmask, const int64_t
                  int32_t *d_span_slice, int32_t *d_span_k, int32_t *d_span_start, int32_t *d_span_end,
                  int64_t span_cap, unsigned long long *d_span_count, void *stream);
 
+/* =========================================================================================
+ * Colour-vector preparation (tg_tvr.py) -- the per-read loops cluster_tvrs / quick_get_tvrtel_lens run
+ * before every distance matrix.  Strings are bytes in device buffers, described by (offset, length).
+ * ======================================================================================= */
+
+/* tg_tvr.py:96-105 / :566-575.  Read r's colour vector occupies d_cv[d_cv_off[r] .. d_cv_off[r+1]): `unknown`
+ * everywhere, then the spans of k-mer 0, 1, .. K-1 painted with d_letters[k] in that order (a later k-mer
+ * overwrites).  Spans are sorted by (read, k): those of (r, k) are d_rk_off[r*K + k] .. d_rk_off[r*K + k + 1]. */
+int tg_cv_paint(const int32_t *d_span_start, const int32_t *d_span_end, const int64_t *d_rk_off,
+                const uint8_t *d_letters, int K, const int64_t *d_cv_off, int n_reads, int unknown,
+                uint8_t *d_cv, void *stream);
+
+/* The position search of find_density_boundary (tg_tvr.py:449-479) for n strings; string s is
+ * d_buf[d_off[s] .. + d_len[s]), read backwards when d_reverse[s] != 0 (d_reverse may be NULL).
+ * dens[j] = #(letters of the set at positions j+1 .. j+win, positions < start never count) / win for
+ * start <= j < len - win.  d_first[s] = first j with dens <= thresh (above == 0) or >= thresh (above != 0);
+ * d_extreme[s] = the reference's pos_with_lowest_dens (first position of the strict running minimum starting
+ * at 1.0, or maximum starting at 0.0).  -1 = None. */
+int tg_cv_density_boundary(const uint8_t *d_buf, const int64_t *d_off, const int32_t *d_len, const uint8_t *d_reverse,
+                           int n, const uint8_t *h_letters, int n_letters, int win, double thresh, int above, int start,
+                           int32_t *d_first, int32_t *d_extreme, void *stream);
+
+/* d_out[s] = min(length of the leading run of `letter`, d_cap[s]) (tg_tvr.py:124-126 with cap = len - 1). */
+int tg_cv_lead_run(const uint8_t *d_buf, const int64_t *d_off, const int32_t *d_len, const uint8_t *d_reverse,
+                   const int32_t *d_cap, int n, int letter, int32_t *d_out, void *stream);
+
+/* d_dst[d_dst_off[g] + x] = d_src[d_src_off[g] + x], x < d_len[g]: the string concatenations between the steps. */
+int tg_cv_gather(const uint8_t *d_src, const int64_t *d_src_off, const int64_t *d_dst_off, const int32_t *d_len,
+                 int64_t n_seg, uint8_t *d_dst, void *stream);
+
+/* denoise_colorvec (tg_tvr.py:524-556) for n non-empty strings; output s has d_len[s] + 1 letters at d_out_off[s].
+ * d_keep[s] = d_len[s] - (trailing run of replace_char), d_tile_off = exclusive prefix sum of
+ * ceil((d_len[s] + 1) / tg_cv_denoise_tile()).  Limits: min_size <= 64, max_gap_fill <= 63 (TG_ERANGE). */
+int tg_cv_denoise_tile(void);
+int tg_cv_denoise(const uint8_t *d_buf, const int64_t *d_off, const int32_t *d_len, const int32_t *d_keep,
+                  const int64_t *d_out_off, const int64_t *d_tile_off, int n, int64_t n_tiles, int replace_char,
+                  int min_size, int max_gap_fill, const uint8_t *h_delete, int n_delete,
+                  const uint8_t *h_merge, int n_merge, uint8_t *d_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

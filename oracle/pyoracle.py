@@ -339,3 +339,128 @@ def scan_read(read, kmers_f, kmers_r, canon_f, canon_r, window):
     fl = lib().tgo_scan_read(b, L, bf, br, _ptr(off), len(kmers_f), cf, cr, _ptr(coff), len(canon_f), window,
                              ori, _ptr(c0), _ptr(c1), _ptr(bc))
     return bool(fl), ori.raw[:L].decode('ascii'), c0, c1, bc
+
+
+# =====================================================================================================
+# Colour-vector preparation: restatement of the per-read preparation inside cluster_tvrs
+# (tg_tvr.py:96-142) and quick_get_tvrtel_lens (tg_tvr.py:558-592).  numpy / pure Python, small inputs only.
+# Pinned against the reference's own outputs: tests/golden/tvr_prep_golden.json.gz (make_golden_tvr.py).
+# =====================================================================================================
+UNKNOWN_WIN_SIZE, UNKNOWN_END_DENS = 100, 0.125              # tg_tvr.py:22-23
+UNKNOWN_WIN_SIZE_FINE, UNKNOWN_END_DENS_FINE = 50, 0.500     # tg_tvr.py:24-25
+CANON_WIN_SIZE, CANON_END_DENS = 100, 0.700                  # tg_tvr.py:27-28
+
+
+def colorvec_py(hits_flat, tlen, kmer_letters):
+    """tg_tvr.py:96-105: UNKNOWN everywhere, then every span painted with its k-mer's letter, k-mers in index order
+    (a later k-mer overwrites an earlier one).  hits_flat: iterable of (k, start, end)."""
+    v = np.full(tlen, ord(UNKNOWN), dtype=np.uint8)
+    for k, s, e in sorted((tuple(int(x) for x in h) for h in hits_flat), key=lambda h: h[0]):
+        v[s:e] = ord(kmer_letters[k])
+    return v.tobytes().decode('latin-1')
+
+
+def density_boundary_pos(seq, letters, win, thresh, direction='below', start=0):
+    """Positions (first crossing or None, extreme-density position or None) of find_density_boundary (tg_tvr.py:449-479):
+    dens[j] = #(seq[j+1 .. j+win] in letters, positions >= start) / win for start <= j < len - win."""
+    if direction not in ('below', 'above'):
+        raise ValueError('thresh_dir must be above or below')
+    L = len(seq)
+    if L - win <= start:
+        return None, None
+    a = np.frombuffer(seq.encode('latin-1'), dtype=np.uint8)
+    u = np.isin(a, np.frombuffer(''.join(letters).encode('latin-1'), dtype=np.uint8)).astype(np.float64)
+    u[:start] = 0
+    cum = np.cumsum(u)
+    j = np.arange(start, L - win)
+    dens = (cum[j + win] - cum[j]) / win                      # float64 division like the reference
+    if direction == 'below':
+        hit = np.nonzero(dens <= thresh)[0]
+        ext = int(np.argmin(dens)) if dens.min() < 1.0 else None       # first position of the strict running minimum
+    else:
+        hit = np.nonzero(dens >= thresh)[0]
+        ext = int(np.argmax(dens)) if dens.max() > 0.0 else None
+    first = int(hit[0]) + start if len(hit) else None
+    ext = ext + start if ext is not None else None
+    return first, ext
+
+
+def find_density_boundary_py(seq, letters, win, thresh, direction='below', start=0, use_lowest=False):
+    """tg_tvr.py:449-498 -> (left, right).  A None split position slices to (whole, whole), as in the reference."""
+    first, ext = density_boundary_pos(seq, letters, win, thresh, direction, start)
+    if first is None:
+        first = ext
+    p = ext if use_lowest else first
+    return seq[:p], seq[p:]
+
+
+def denoise_colorvec_py(v, replace_char=UNKNOWN, min_size=10, max_gap_fill=50, chars_to_delete=(), chars_to_merge=()):
+    """tg_tvr.py:524-556.  Runs of equal letters of v + replace_char; the LAST run is never closed, i.e. dropped; runs
+    shorter than min_size of a deletable letter are dropped; neighbouring surviving runs of the same mergeable letter
+    at most max_gap_fill apart are joined (filling the gap); everything else becomes replace_char.  The output is one
+    letter longer than v."""
+    if len(v) == 0:
+        return ''
+    w = v + replace_char
+    a = np.frombuffer(w.encode('latin-1'), dtype=np.uint8)
+    starts = np.concatenate([[0], np.nonzero(a[1:] != a[:-1])[0] + 1])
+    ends = np.concatenate([starts[1:], [len(a)]])
+    runs = [(int(s), int(e), chr(a[s])) for s, e in zip(starts[:-1], ends[:-1])]          # last run dropped
+    runs = [r for r in runs if not (r[1] - r[0] < min_size and r[2] in chars_to_delete)]
+    out = np.full(len(a), ord(replace_char), dtype=np.uint8)
+    for i, (s, e, c) in enumerate(runs):
+        out[s:e] = ord(c)
+        if i and runs[i - 1][2] == c and c in chars_to_merge and s - runs[i - 1][1] <= max_gap_fill:
+            out[runs[i - 1][1]:s] = ord(c)
+    return out.tobytes().decode('latin-1')
+
+
+def _flag_letters(meta):
+    kmer_list, _colors, letters, flags = meta
+    sets = {f: sorted(set(letters[i] for i in range(len(kmer_list)) if f in flags[i]))
+            for f in ('canonical', 'denoise', 'tvr', 'nofilt', 'dubious', 'subtel-filt')}
+    canon = None
+    for i in range(len(kmer_list)):
+        if 'canonical' in flags[i]:
+            canon = letters[i]                 # the last one wins (tg_tvr.py:67-69)
+    return canon, sets
+
+
+def subtel_tvr_split_py(cv, unknown_letters):
+    """tg_tvr.py:117-128 / :580-591 -> (seq_left, seq_right)."""
+    left, right = find_density_boundary_py(cv, unknown_letters, UNKNOWN_WIN_SIZE, UNKNOWN_END_DENS, 'below')
+    rec, rest = find_density_boundary_py(left[::-1], unknown_letters, UNKNOWN_WIN_SIZE_FINE, UNKNOWN_END_DENS_FINE, 'above')
+    right = rec[::-1] + right
+    left = rest[::-1]
+    adj = 0
+    while right[adj] == UNKNOWN and adj < len(right) - 1:
+        adj += 1
+    return left + right[:adj], right[adj:]
+
+
+def tvr_prep_py(kmer_dat, meta, tvr_truncate):
+    """The lists cluster_tvrs builds before the distance matrix (tg_tvr.py:96-142)."""
+    canon, sets = _flag_letters(meta)
+    unk = [UNKNOWN] + sets['subtel-filt']
+    out = {k: [] for k in ('all_colorvecs', 'subtel_regions', 'tvrtel_regions', 'cleaned_colorvecs', 'colorvecs_for_msa',
+                           'err_end_lens', 'tvrtels_for_clustering')}
+    for kd in kmer_dat:
+        cv = colorvec_py(kd['hits'], kd['tlen'], meta[2])
+        left, right = subtel_tvr_split_py(cv, unk)
+        den = denoise_colorvec_py(right, replace_char=canon, chars_to_delete=sets['denoise'], chars_to_merge=[canon] + sets['tvr'])
+        err_left, err_right = find_density_boundary_py(den[::-1], [canon], CANON_WIN_SIZE, CANON_END_DENS, 'above')
+        out['all_colorvecs'].append(cv)
+        out['cleaned_colorvecs'].append(left + err_right[::-1])
+        out['err_end_lens'].append(len(err_left))
+        out['colorvecs_for_msa'].append(err_right[::-1])
+        out['subtel_regions'].append(left)
+        out['tvrtel_regions'].append(right)
+        out['tvrtels_for_clustering'].append(err_right[::-1][:tvr_truncate])
+    return out
+
+
+def quick_tvrtel_lens_py(kmer_dat, meta):
+    """tg_tvr.py:558-592."""
+    _canon, sets = _flag_letters(meta)
+    unk = [UNKNOWN] + sets['subtel-filt']
+    return [len(subtel_tvr_split_py(colorvec_py(kd['hits'], kd['tlen'], meta[2]), unk)[1]) for kd in kmer_dat]

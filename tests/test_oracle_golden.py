@@ -125,3 +125,25 @@ def test_dist_matrix_c_negative_seed_uses_abs_like_cpython(colorvecs):
     P = oracle.AlignerParams(oracle.scoring_matrix('C', 'tvr'), (True, True))
     for seed in (-12345, -3, 2 ** 40 + 7):
         assert np.array_equal(oracle.dist_matrix_py(seqs, P, True, False, 2, seed), oracle.dist_matrix_c(seqs, P, True, False, 2, seed))
+
+
+def test_tvr_prep_oracle_matches_reference_golden():
+    """Colour-vector preparation (SURVEY 8f #1): the numpy/Python restatement against the reference's own outputs."""
+    import gzip
+    import json
+    import os
+    from conftest import ROOT
+    with gzip.open(os.path.join(ROOT, 'tests', 'golden', 'tvr_prep_golden.json.gz'), 'rt') as f:
+        G = json.load(f)
+    for c in G['fdb']:
+        assert oracle.find_density_boundary_py(c['seq'], c['letters'], c['win'], c['thresh'], c['dir'], c['start'], c['lowest']) == \
+            (c['left'], c['right'])
+    for c in G['denoise']:
+        assert oracle.denoise_colorvec_py(c['v'], c['replace'], c['min_size'], c['max_gap_fill'], c['delete'], c['merge']) == c['out']
+    for key, S in G['sets'].items():
+        meta = [list(range(len(S['meta_letters']))), None, S['meta_letters'], S['meta_flags']]
+        for tr in (1000, 3000):
+            got = oracle.tvr_prep_py(S['kmer_dat'], meta, tr)
+            for k, v in S[f'prep_trunc{tr}'].items():
+                assert got[k] == v, (key, tr, k)
+        assert oracle.quick_tvrtel_lens_py(S['kmer_dat'], meta) == S['quick_tvrtel_lens']
