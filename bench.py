@@ -51,6 +51,26 @@ def load_fixtures():
     return cv, reads, tables
 
 
+def make_prep_workload(n_reads):
+    """Colour-vector preparation: the k-mer hits of the bundled reads (tests/golden/tvr_prep_golden.json.gz,
+    produced by the reference), replicated to n_reads reads in the reference's kmer_dat layout."""
+    with gzip.open(os.path.join(GOLDEN, 'tvr_prep_golden.json.gz'), 'rt') as f:
+        S = json.load(f)['sets']['human_hifi']
+    K = len(S['meta_letters'])
+    base = []
+    for kd in S['kmer_dat']:
+        if kd['tlen'] < 1000:
+            continue
+        hits = [[] for _ in range(K)]
+        for k, a, b in kd['hits']:
+            hits[k].append([a, b])
+        base.append([hits, kd['tlen'], 0, 'FWD', kd['name'], 60, ''])
+    kmer_dat = [base[i % len(base)] for i in range(n_reads)]
+    meta = [[f'k{i}' for i in range(K)], [None] * K, S['meta_letters'], S['meta_flags']]
+    flat = [{'hits': [(k, sp[0], sp[1]) for k, spans in enumerate(kd[0]) for sp in spans], 'tlen': kd[1]} for kd in base]
+    return kmer_dat, meta, flat
+
+
 def make_dp_workload(cv, n_seq, seed=12345):
     """D1: bundled colour vectors (truncate 1000) replicated with seeded 2 % letter edits."""
     rng = np.random.default_rng(seed)
@@ -405,6 +425,31 @@ def main():
                      'frac': ach / pk['hbm_gbs'], 'traffic': ncu_traffic('scan_cov_kernel<density>', scan_bases), 'peak_source': src, 'launch_ms': min(ds) * 1e3,
                      'bytes_per_base': 2.375, 'mbases_per_s': scan_bases / min(ds) / 1e6}
 
+    # ---------------- colour-vector preparation, host lists in -> host lists out ----------------
+    prep = None
+    if rank == 0:
+        from telogator2_b200 import tg_tvr
+        kd_prep, meta_prep, flat_prep = make_prep_workload(2048)
+        tg_tvr.tvr_prep(kd_prep[:64], meta_prep, 1000)
+        pt = []
+        for _ in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            got_prep = tg_tvr.tvr_prep(kd_prep, meta_prep, 1000)
+            pt.append(time.perf_counter() - t0)
+        letters = sum(kd[1] for kd in kd_prep)
+        prep = {'value': len(kd_prep) / min(pt), 'unit': 'reads/s', 'ms_per_step': min(pt) * 1e3, 'reads': len(kd_prep),
+                'letters': int(letters), 'what': 'tvr_prep: spans -> colour vectors, 3 density boundaries, denoise, string assembly '
+                                                 '(kmer_dat lists in, Python strings out)'}
+        if not args.no_cpu_baseline:
+            import oracle
+            t0 = time.perf_counter()
+            want = oracle.tvr_prep_py(flat_prep, meta_prep, 1000)
+            dt = time.perf_counter() - t0
+            assert got_prep['tvrtels_for_clustering'][:len(flat_prep)] == want['tvrtels_for_clustering'], 'tvr_prep differs from the oracle'
+            prep['cpu_port_reads_per_s'] = len(flat_prep) / dt
+            prep['cpu_port'] = f'oracle numpy/Python restatement, 1 core, {len(flat_prep)} reads ({dt:.2f} s)'
+
     # ---------------- e2e through the public API: host strings -> float32 matrix on the host --------
     # (the body of tg_align.get_dist_matrix_parallel, with the engine kept to read its byte counters)
     e2e_ms = []
@@ -460,6 +505,7 @@ def main():
                          'what': 'basecount x2 + orient + density x2 + hits on the last 6000 bases of every read (device resident)',
                          'parts_ms': {k: float(np.mean(v)) for k, v in scan_parts.items() if v}},
                 'roofline': roof, 'roofline_scan': roof_scan, 'cpu_baseline': cpu, 'clocks': clocks,
+                'prep': prep,
                 'multi_gpu_verified_pairs': verified,
                 'wall_s_timed_region': t_wall}
         print(json.dumps(line))
