@@ -327,6 +327,9 @@ def main():
                 scan_parts[name].append(scan_ev[a].elapsed_time(scan_ev[b]))
         return flip, ca, cb, spans
 
+    import ctypes as C
+    from telogator2_b200 import _lib
+    L = _lib.load()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     sampler = ClockSampler(local_rank)
     dp_ms, scan_ms, dens_ms = [], [], []
@@ -337,6 +340,7 @@ def main():
             barrier()
             sampler.start()
             t_wall0 = time.perf_counter()
+            _lib.check(L.tg_wave_timing(1))            # CUDA events around every nw_wave_kernel launch of the timed steps
         barrier()
         ev[0].record()
         dp_step()
@@ -353,6 +357,9 @@ def main():
             scan_ms.append(ev[2].elapsed_time(ev[3]))
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
+    wave_ms, wave_n = C.c_double(0), C.c_int(0)
+    _lib.check(L.tg_wave_timing_read(C.byref(wave_ms), C.byref(wave_n)))
+    _lib.check(L.tg_wave_timing(0))
 
     def allmax(x):
         t = torch.tensor([x], dtype=torch.float64, device='cuda')
@@ -376,40 +383,22 @@ def main():
     # ---------------- kernel-level roofline numbers (rank 0, CUDA events around single launches) -----
     roof, roof_scan = None, None
     if rank == 0:
-        import ctypes as C
-        from telogator2_b200 import _lib
-        L = _lib.load()
         dpx, mixed = C.c_double(0), C.c_double(0)
         _lib.check(L.tg_int_alu_peak(2000, C.byref(dpx), C.byref(mixed)))
-        # dominant kernel: nw_wave_kernel.  Launch it alone on the phase-A jobs of a sub-matrix.
-        sub = seqs[:min(n_seq, 1024)]
-        e2 = DistEngine(Scoring.from_aligner(aligner))
-        codes, off, subm = e2.sc.encode_all(sub)
-        from telogator2_b200.dist_engine import pack_jobs
-        npz = len(sub) * (len(sub) - 1) // 2
-        iu = np.triu_indices(len(sub), 1)
-        ln = np.diff(off).astype(np.int32)
-        jobs = pack_jobs(off[iu[0]], off[iu[1]], ln[iu[0]], ln[iu[1]], np.arange(npz, dtype=np.int32), True)
-        d_codes = e2._to_dev(codes)
-        e2.run_jobs(d_codes, jobs, subm, npz)
-        torch.cuda.synchronize()
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ks = []
-        for _ in range(3):
-            k0.record()
-            e2.run_jobs(d_codes, jobs, subm, npz)
-            k1.record()
-            torch.cuda.synchronize()
-            ks.append(k0.elapsed_time(k1) * 1e-3)
-        kcells = float((ln[iu[0]].astype(np.int64) * ln[iu[1]]).sum())
-        k_gcups = kcells / min(ks) / 1e9
+        # dominant kernel: nw_wave_kernel, timed inside the timed steps (CUDA events on the launching stream around every
+        # launch: phase A + phase B of every batch).  Algorithmic work = the cells of the steps.
+        k_cells = float(cells_step) * args.steps
+        k_gcups = k_cells / (wave_ms.value * 1e-3) / 1e9
         instr_per_cell = 1.5                       # minimal s16x2 cost of the linear-gap cell
         peak_gcups = dpx.value / instr_per_cell / 1e9
         roof = {'bound': 'int_alu', 'kernel': 'nw_wave_kernel', 'achieved': k_gcups, 'peak': peak_gcups, 'unit': 'GCUPS',
                 'frac': k_gcups / peak_gcups, 'traffic': ncu_traffic('nw_wave_kernel'),
                 'peak_source': f'measured in this run: {dpx.value / 1e12:.2f} T VIMNMX3.U16x2 lane-ops/s (tg_int_alu_peak) / 1.5 instr per cell '
                                f'(SURVEY 8d); add+max3 pair rate {mixed.value / 1e12:.2f} T pairs/s',
-                'launch_ms': min(ks) * 1e3, 'cells_per_launch': kcells}
+                'launch_ms': wave_ms.value / max(wave_n.value, 1), 'launches': wave_n.value,
+                'cells_per_launch': k_cells / max(wave_n.value, 1),
+                'share_of_step': wave_ms.value / (float(np.sum(dp_ms)) if dp_ms else 1.0),
+                'how': 'CUDA events around every nw_wave_kernel launch (phase A and phase B of every batch) of the timed steps on rank 0'}
         # scan: density kernel alone, algorithmic bytes 2.375 B/base
         d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ds = []

@@ -161,6 +161,12 @@ typedef struct tg_dist_epilogue_args {
 
 int tg_dist_epilogue(const tg_dist_epilogue_args *args, void *stream);
 
+/* Measurement aid (bench.py's roofline figure): while enabled, CUDA events on the launching stream bracket every
+ * nw_wave_kernel launch of this process; tg_wave_timing_read waits for them, returns the summed kernel
+ * milliseconds and the number of launches since the last read, and forgets them.  Not thread safe. */
+int tg_wave_timing(int enable);
+int tg_wave_timing_read(double *total_ms, int *n_launches);
+
 /* Integer-ALU issue-rate microbenchmark used as the DP roofline denominator:
  * runs `iters` dependent-chain-free VIMNMX3.U16x2/IADD pairs per thread on the whole device and
  * returns lane-operations per second for the DPX op and for a plain integer add. */

@@ -16,6 +16,8 @@
 // the whole boundary row/column of H' is zero.  Free right end gaps (gap_right >= g) are
 // recovered afterwards as max over the last row / last column of H (see the epilogue).
 #include "tg_common.cuh"
+#include <utility>
+#include <vector>
 #include <limits.h>
 #include <stdlib.h>
 #include <string.h>
@@ -892,7 +894,6 @@ __global__ void __launch_bounds__(MTW_WARPS * 32) mt_sample_warp_kernel(const St
                 c += (S == nn) ? (32 - __clz(A)) : 32;           // the draws behind the last element belong to the next shuffle
                 if (c > cap) ok = false;                         // stream exhausted: flag it (results are discarded)
                 if ((A >> lane) & 1u) scr[a] = (uint16_t)r;
-                hitarr[lane] = -1;
                 __syncwarp();
                 // ---- 2. the S swap-removes ----
                 const bool act = lane < S;
@@ -901,17 +902,23 @@ __global__ void __launch_bounds__(MTW_WARPS * 32) mt_sample_warp_kernel(const St
                 uint32_t vj = 0, vt = 0;
                 if (act) { vj = arr[j]; vt = arr[t]; }
                 const int tg = nn - 1 - j;                       // the step whose tail read sees this step's write
-                if (act && tg > lane && tg < S) atomicMax(&hitarr[tg], lane);
+                const bool writes_tail = act && tg > lane && tg < S;
                 const unsigned same = __match_any_sync(TG_FULL_MASK, act ? j : -1 - lane);
-                __syncwarp();
-                const int hit = hitarr[lane];
-                int root = hit < 0 ? lane : hit;
-                for (;;) {
-                    const int h = __shfl_sync(TG_FULL_MASK, hit, root);
-                    if (!__any_sync(TG_FULL_MASK, h >= 0)) break;
-                    if (h >= 0) root = h;
+                uint32_t tailval = vt;
+                if (__any_sync(TG_FULL_MASK, writes_tail)) {     // rare for long pools: some j falls into the group's tail window
+                    hitarr[lane] = -1;
+                    __syncwarp();
+                    if (writes_tail) atomicMax(&hitarr[tg], lane);
+                    __syncwarp();
+                    const int hit = hitarr[lane];
+                    int root = hit < 0 ? lane : hit;
+                    for (;;) {
+                        const int h = __shfl_sync(TG_FULL_MASK, hit, root);
+                        if (!__any_sync(TG_FULL_MASK, h >= 0)) break;
+                        if (h >= 0) root = h;
+                    }
+                    tailval = __shfl_sync(TG_FULL_MASK, vt, root);
                 }
-                const uint32_t tailval = __shfl_sync(TG_FULL_MASK, vt, root);
                 const unsigned before = same & lt;
                 const uint32_t tw = __shfl_sync(TG_FULL_MASK, tailval, before ? 31 - __clz(before) : lane);
                 if (act) out[len - nn + lane] = (uint8_t)(before ? tw : vj);        // result[i]
@@ -1144,8 +1151,27 @@ static int wave_launch_v(const WaveParams &P, int mode, int grid, int warps, siz
     return wave_launch_t<V, JOBS_PHASE_B, WIDE>(P, grid, warps, smem, st);
 }
 
+// Optional timing of the wave launches (bench.py's roofline figure): CUDA events on the launching stream around every launch.
+static bool g_timing_on = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_timing_events;
+
+static int wave_launch_inner(const WaveParams &P, int mode, int variant, int grid, int warps, size_t smem, cudaStream_t st, bool wide);
+
 // wide (32-bit cells) exists for the default geometry only
 static int wave_launch(const WaveParams &P, int mode, int variant, int grid, int warps, size_t smem, cudaStream_t st, bool wide = false)
+{
+    if (!g_timing_on) return wave_launch_inner(P, mode, variant, grid, warps, smem, st, wide);
+    cudaEvent_t e0, e1;
+    TG_CUDA_CHECK(cudaEventCreate(&e0));
+    TG_CUDA_CHECK(cudaEventCreate(&e1));
+    TG_CUDA_CHECK(cudaEventRecord(e0, st));
+    const int rc = wave_launch_inner(P, mode, variant, grid, warps, smem, st, wide);
+    TG_CUDA_CHECK(cudaEventRecord(e1, st));
+    g_timing_events.emplace_back(e0, e1);
+    return rc;
+}
+
+static int wave_launch_inner(const WaveParams &P, int mode, int variant, int grid, int warps, size_t smem, cudaStream_t st, bool wide)
 {
     if (wide) return wave_launch_v<3, true>(P, mode, grid, warps, smem, st);
     if (variant == 0) return wave_launch_v<0>(P, mode, grid, warps, smem, st);
@@ -1360,6 +1386,31 @@ TG_EXPORT int tg_dist_batch(const tg_dist_batch_args *a, const tg_nw_scoring *sc
     P.n_jobs = wide ? npairs * a->R : (a->R % 2 == 0) ? npairs * (a->R / 2) : ((npairs + 1) / 2) * a->R;
     TG_CUDA_CHECK(cudaMemsetAsync(a->d_counter, 0, sizeof(unsigned long long), st));
     return wave_launch(P, JOBS_PHASE_B, C, grid_for_jobs(P.n_jobs), warps, smem, st, wide);
+}
+
+TG_EXPORT int tg_wave_timing(int enable)
+{
+    g_timing_on = enable != 0;
+    return TG_OK;
+}
+
+TG_EXPORT int tg_wave_timing_read(double *total_ms, int *n_launches)
+{
+    double tot = 0.0;
+    int n = 0;
+    for (auto &ev : g_timing_events) {
+        float ms = 0.f;
+        TG_CUDA_CHECK(cudaEventSynchronize(ev.second));
+        TG_CUDA_CHECK(cudaEventElapsedTime(&ms, ev.first, ev.second));
+        tot += ms;
+        n++;
+        cudaEventDestroy(ev.first);
+        cudaEventDestroy(ev.second);
+    }
+    g_timing_events.clear();
+    if (total_ms) *total_ms = tot;
+    if (n_launches) *n_launches = n;
+    return TG_OK;
 }
 
 TG_EXPORT int tg_nw_generic_max_m(void) { return 24000; }

@@ -1,7 +1,10 @@
 #!/bin/bash
-# Run on the GPU box (gpurun): final evidence for profiles/.  One ncu invocation pair, after plain runs exited 0.
+# Run on the GPU box (gpurun): final evidence for profiles/.  Two calls, one ncu invocation each, each after the same
+# command exited 0 without ncu:   tools/capture_profiles.sh a   (tests, both bench arms, launch list)
+#                                 tools/capture_profiles.sh b   (full-set capture of the hot kernels)
 set -x
 mkdir -p gpurun_out/final
+if [ "$1" != "b" ]; then
 python -m pytest tests -m gpu -q --timeout 900 > gpurun_out/final/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/final/pytest_gpu.log
 python bench.py --impl reference > gpurun_out/final/bench_reference.json 2> gpurun_out/final/bench_reference.err
 python bench.py > gpurun_out/final/bench_b200.json 2> gpurun_out/final/bench_b200.err
@@ -10,8 +13,10 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,clocks_event_reas
 python bench.py --steps 1 --warmup 1 --n-seq 1024 --scan-mbases 200 --no-cpu-baseline > gpurun_out/final/plain_short.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/final/launches.csv \
     python bench.py --steps 1 --warmup 1 --n-seq 1024 --scan-mbases 200 --no-cpu-baseline > gpurun_out/final/ncu_launches.log 2>&1
+else
 # full-set capture of every hot kernel on a small fixed workload
 python tools/prof_run.py 256 100 > gpurun_out/final/prof_plain.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:"nw_wave|mt_|scan_cov|hits_|dist_flags" -c 14 -o gpurun_out/final/full \
+ncu --set full --clock-control none --import-source on -k regex:"nw_wave|mt_|scan_cov|hits_|dist_flags|dist_epilogue|cv_" -c 20 -o gpurun_out/final/full \
     python tools/prof_run.py 256 100 > gpurun_out/final/ncu_full.log 2>&1
+fi
 echo done

@@ -18,8 +18,9 @@ cv, reads, tables = bench.load_fixtures()
 seqs = bench.make_dp_workload(cv, n_seq)
 aligner = tg_align.get_aligner_object(tg_align.get_scoring_matrix('C', 'tvr'), (True, True), 'tvr')
 eng = DistEngine(Scoring.from_aligner(aligner))
+st = eng.prepare(seqs)
 for _ in range(2):
-    res = eng.pair_scores(seqs, True, True, 2, 12345)
+    D = eng.matrix_device(st, True, True, 2, 12345)
 torch.cuda.synchronize()
 print('dp cells', eng.stats['cells'], 'early', eng.stats['early_out'], 'pairs', eng.stats['pairs'])
 T = tables['human_hifi']
@@ -33,3 +34,9 @@ for _ in range(2):
     sp = pr.hits_device(np.arange(pr.n), np.maximum(pr.lens - 6000, 0), pr.lens, KLR, ISSUB)
 torch.cuda.synchronize()
 print('scan bases', int(pr.lens.sum()), 'reads', pr.n, 'spans', sp.shape[1])
+from telogator2_b200 import tg_tvr  # noqa: E402
+kd, meta, _flat = bench.make_prep_workload(512)
+for _ in range(2):
+    out = tg_tvr.tvr_prep(kd, meta, 1000)
+torch.cuda.synchronize()
+print('prep reads', len(kd), 'letters', sum(k[1] for k in kd))
