@@ -439,6 +439,52 @@ def main():
             prep['cpu_port_reads_per_s'] = len(flat_prep) / dt
             prep['cpu_port'] = f'oracle numpy/Python restatement, 1 core, {len(flat_prep)} reads ({dt:.2f} s)'
 
+    # ---------------- stage [0a] prefilter: str.count of KMER_INITIAL / RC over every read ----------------
+    prefilter = None
+    if rank == 0:
+        from telogator2_b200 import tg_prefilter
+        g = torch.Generator(device='cuda')
+        g.manual_seed(99)
+        n_wgs, wgs_len = 32768, 16384                                  # 537 Mbases of genome-like reads (uniform ACGT) ...
+        tail = tg_prefilter._lib.load().tg_prefilter_tail_bytes()
+        d_wgs = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device='cuda')[
+            torch.randint(0, 4, (n_wgs * wgs_len + tail,), generator=g, device='cuda')]
+        # ... with the telomeric scan reads spliced over the first of them (every 64th read)
+        tel = [r for r in scan_reads if len(r) <= wgs_len][:n_wgs // 64]
+        for k, r in enumerate(tel):
+            o = 64 * k * wgs_len
+            d_wgs[o:o + len(r)] = torch.frombuffer(bytearray(r.encode('latin-1')), dtype=torch.uint8).cuda()
+        lens_wgs = np.full(n_wgs, wgs_len, dtype=np.int32)
+        for k, r in enumerate(tel):
+            lens_wgs[64 * k] = len(r)
+        ar = tg_prefilter.AsciiReads.from_device(d_wgs, np.arange(n_wgs + 1, dtype=np.int64) * wgs_len, lens_wgs)
+        KI, KIR = CANON[0] + CANON[0], CR[0] + CR[0]                   # telogator2.py:393-394
+        ca, cb = ar.count_pair_device(KI, KIR)
+        torch.cuda.synchronize()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ps = []
+        for _ in range(5):
+            p0.record()
+            ca, cb = ar.count_pair_device(KI, KIR)
+            p1.record()
+            torch.cuda.synchronize()
+            ps.append(p0.elapsed_time(p1) * 1e-3)
+        pf_bases = float(lens_wgs.astype(np.int64).sum())
+        pkp, srcp = peaks()
+        # spot check against str.count (the reference's own code) on the telomeric reads and some random ones
+        h_ca, h_cb = ca.cpu().numpy(), cb.cpu().numpy()
+        for k in list(range(0, min(len(tel), 24))):
+            assert h_ca[64 * k] == tel[k].count(KI) and h_cb[64 * k] == tel[k].count(KIR), 'prefilter count differs from str.count'
+        for i in (1, 2, 3, 1000, n_wgs - 1):
+            s_i = bytes(d_wgs[i * wgs_len:(i + 1) * wgs_len].cpu().numpy()).decode('latin-1')
+            assert h_ca[i] == s_i.count(KI) and h_cb[i] == s_i.count(KIR), 'prefilter count differs from str.count'
+        prefilter = {'kernel': 'prefilter_count_kernel', 'bound': 'hbm', 'achieved': pf_bases / min(ps) / 1e9, 'peak': pkp['hbm_gbs'],
+                     'unit': 'GB/s', 'frac': pf_bases / min(ps) / 1e9 / pkp['hbm_gbs'], 'peak_source': srcp, 'launch_ms': min(ps) * 1e3,
+                     'bytes_per_base': 1.0, 'mbases_per_s': pf_bases / min(ps) / 1e6, 'reads': n_wgs,
+                     'telomeric_reads': len(tel), 'reads_kept': int(((h_ca >= 5) | (h_cb >= 5)).sum()),
+                     'what': 'read.count(KMER_INITIAL), read.count(KMER_INITIAL_RC) for every read (telogator2.py:451-454), ASCII resident in HBM'}
+        del d_wgs, ar
+
     # ---------------- e2e through the public API: host strings -> float32 matrix on the host --------
     # (the body of tg_align.get_dist_matrix_parallel, with the engine kept to read its byte counters)
     e2e_ms = []
@@ -494,7 +540,7 @@ def main():
                          'what': 'basecount x2 + orient + density x2 + hits on the last 6000 bases of every read (device resident)',
                          'parts_ms': {k: float(np.mean(v)) for k, v in scan_parts.items() if v}},
                 'roofline': roof, 'roofline_scan': roof_scan, 'cpu_baseline': cpu, 'clocks': clocks,
-                'prep': prep,
+                'prep': prep, 'prefilter': prefilter,
                 'multi_gpu_verified_pairs': verified,
                 'wall_s_timed_region': t_wall}
         print(json.dumps(line))

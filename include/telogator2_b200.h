@@ -278,6 +278,20 @@ int tg_cv_denoise(const uint8_t *d_buf, const int64_t *d_off, const int32_t *d_l
                   int min_size, int max_gap_fill, const uint8_t *h_delete, int n_delete,
                   const uint8_t *h_merge, int n_merge, uint8_t *d_out, void *stream);
 
+/* =========================================================================================
+ * Stage [0a] telomere-read prefilter (telogator2.py:451-459)
+ * ======================================================================================= */
+
+/* d_count_a[r] = read.count(kmer_a), d_count_b[r] = read.count(kmer_b) (Python str.count: non-overlapping
+ * occurrences, left to right) for every read; kmer_a / kmer_b are two ACGT patterns of the same length klen <= 32
+ * (KMER_INITIAL and KMER_INITIAL_RC, telogator2.py:393-394).  Reads are ASCII in the padded layout of tg_scan_pack
+ * (d_base_off multiples of 16); the buffer must extend tg_prefilter_tail_bytes() beyond the last read.
+ * d_counter: 8 bytes of scratch. */
+int tg_prefilter_tail_bytes(void);
+int tg_prefilter_count(const uint8_t *d_ascii, const int64_t *d_base_off, const int32_t *d_len, int n_reads,
+                       const char *kmer_a, const char *kmer_b, int klen, int32_t *d_count_a, int32_t *d_count_b,
+                       void *d_counter, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,7 +55,8 @@ EXPORTS = ['tg_last_error', 'tg_version', 'tg_device_sm_count',
            'tg_nw_scores_generic', 'tg_mt_shuffle', 'tg_dist_batch', 'tg_dist_batch_mt_work_bytes', 'tg_dist_epilogue', 'tg_wave_timing', 'tg_wave_timing_read', 'tg_int_alu_peak',
            'tg_kmer_table_bytes', 'tg_kmer_table_build', 'tg_kmer_table_build_pair', 'tg_scan_tile_bases', 'tg_scan_pack', 'tg_scan_basecount', 'tg_scan_orient',
            'tg_scan_density', 'tg_scan_hits_work_bytes', 'tg_scan_hits',
-           'tg_cv_paint', 'tg_cv_density_boundary', 'tg_cv_lead_run', 'tg_cv_gather', 'tg_cv_denoise_tile', 'tg_cv_denoise']
+           'tg_cv_paint', 'tg_cv_density_boundary', 'tg_cv_lead_run', 'tg_cv_gather', 'tg_cv_denoise_tile', 'tg_cv_denoise',
+           'tg_prefilter_tail_bytes', 'tg_prefilter_count']
 
 
 def load():
@@ -99,6 +100,7 @@ def load():
     L.tg_cv_lead_run.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp, vp]
     L.tg_cv_gather.argtypes = [vp, vp, vp, vp, i64, vp, vp]
     L.tg_cv_denoise.argtypes = [vp, vp, vp, vp, vp, vp, i32, i64, i32, i32, i32, C.c_char_p, i32, C.c_char_p, i32, vp, vp]
+    L.tg_prefilter_count.argtypes = [vp, vp, vp, i32, C.c_char_p, C.c_char_p, i32, vp, vp, vp, vp]
     _lib = L
     return L
 
