@@ -445,18 +445,19 @@ def main():
         from telogator2_b200 import tg_prefilter
         g = torch.Generator(device='cuda')
         g.manual_seed(99)
-        n_wgs, wgs_len = 32768, 16384                                  # 537 Mbases of genome-like reads (uniform ACGT) ...
+        n_wgs, wgs_len = 131072, 16384                                 # 2.1 Gbases of genome-like reads (uniform ACGT) ...
         tail = tg_prefilter._lib.load().tg_prefilter_tail_bytes()
         d_wgs = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device='cuda')[
             torch.randint(0, 4, (n_wgs * wgs_len + tail,), generator=g, device='cuda')]
-        # ... with the telomeric scan reads spliced over the first of them (every 64th read)
-        tel = [r for r in scan_reads if len(r) <= wgs_len][:n_wgs // 64]
+        # ... with telomeric scan reads spliced in (every 512th read: still ~5x the telomeric fraction of a real 30x genome)
+        TEL_EVERY = 512
+        tel = [r for r in scan_reads if len(r) <= wgs_len][:n_wgs // TEL_EVERY]
         for k, r in enumerate(tel):
-            o = 64 * k * wgs_len
+            o = TEL_EVERY * k * wgs_len
             d_wgs[o:o + len(r)] = torch.frombuffer(bytearray(r.encode('latin-1')), dtype=torch.uint8).cuda()
         lens_wgs = np.full(n_wgs, wgs_len, dtype=np.int32)
         for k, r in enumerate(tel):
-            lens_wgs[64 * k] = len(r)
+            lens_wgs[TEL_EVERY * k] = len(r)
         ar = tg_prefilter.AsciiReads.from_device(d_wgs, np.arange(n_wgs + 1, dtype=np.int64) * wgs_len, lens_wgs)
         KI, KIR = CANON[0] + CANON[0], CR[0] + CR[0]                   # telogator2.py:393-394
         ca, cb = ar.count_pair_device(KI, KIR)
@@ -474,7 +475,7 @@ def main():
         # spot check against str.count (the reference's own code) on the telomeric reads and some random ones
         h_ca, h_cb = ca.cpu().numpy(), cb.cpu().numpy()
         for k in list(range(0, min(len(tel), 24))):
-            assert h_ca[64 * k] == tel[k].count(KI) and h_cb[64 * k] == tel[k].count(KIR), 'prefilter count differs from str.count'
+            assert h_ca[TEL_EVERY * k] == tel[k].count(KI) and h_cb[TEL_EVERY * k] == tel[k].count(KIR), 'prefilter count differs from str.count'
         for i in (1, 2, 3, 1000, n_wgs - 1):
             s_i = bytes(d_wgs[i * wgs_len:(i + 1) * wgs_len].cpu().numpy()).decode('latin-1')
             assert h_ca[i] == s_i.count(KI) and h_cb[i] == s_i.count(KIR), 'prefilter count differs from str.count'

@@ -48,8 +48,10 @@ __device__ __forceinline__ uint32_t plane(const uint32_t (&w)[8])
 }
 
 // KLEN > 0: pattern length known at compile time (the matching loop unrolls and the expected planes become
-// constant-bank operands); KLEN == 0: any length up to PF_MAXK
-template <int KLEN>
+// constant-bank operands); KLEN == 0: any length up to PF_MAXK.
+// DOUBLED: both patterns are a word repeated twice (KMER_INITIAL = canonical + canonical, telogator2.py:393-394): a match at p
+// is a match of the half at p and at p + KLEN/2, which halves the matching chain.
+template <int KLEN, bool DOUBLED>
 __global__ void __launch_bounds__(PF_WARPS * 32) prefilter_count_kernel(const __grid_constant__ PrefParams P)
 {
     const int lane = threadIdx.x & 31;
@@ -78,11 +80,18 @@ __global__ void __launch_bounds__(PF_WARPS * 32) prefilter_count_kernel(const __
                 const uint32_t b1 = plane<1>(w), b2 = plane<2>(w);
                 const uint32_t b1n = __shfl_down_sync(TG_FULL_MASK, b1, 1), b2n = __shfl_down_sync(TG_FULL_MASK, b2, 1);
                 uint32_t acc0 = 0, acc1 = 0;
+                constexpr int CHAIN = DOUBLED ? KLEN / 2 : KLEN;
 #pragma unroll
-                for (int t = 0; t < (KLEN ? KLEN : klen); t++) {
+                for (int t = 0; t < (KLEN ? CHAIN : klen); t++) {
                     const uint32_t s1 = __funnelshift_r(b1, b1n, t), s2 = __funnelshift_r(b2, b2n, t);
                     acc0 |= (s1 ^ P.x1[0][t]) | (s2 ^ P.x2[0][t]);
                     acc1 |= (s1 ^ P.x1[1][t]) | (s2 ^ P.x2[1][t]);
+                }
+                if (DOUBLED) {
+                    // acc = mismatch mask of the half word; the whole pattern also needs the half at + KLEN / 2
+                    const uint32_t a0n = __shfl_down_sync(TG_FULL_MASK, acc0, 1), a1n = __shfl_down_sync(TG_FULL_MASK, acc1, 1);
+                    acc0 |= __funnelshift_r(acc0, a0n, CHAIN);
+                    acc1 |= __funnelshift_r(acc1, a1n, CHAIN);
                 }
                 // positions of this lane: it * 992 + 32 * lane + i; lane 31 is look-ahead only
                 const int p0 = it * PF_STRIDE + 32 * lane;
@@ -109,10 +118,13 @@ __global__ void __launch_bounds__(PF_WARPS * 32) prefilter_count_kernel(const __
                             lanes &= lanes - 1;
                             uint32_t g = __shfl_sync(TG_FULL_MASK, good, l);
                             const int pb = it * PF_STRIDE + 32 * l;
+                            // jump from taken match to taken match: bits below the next free position are dropped at once
+                            if (nf[q] > pb) g = (nf[q] - pb >= 32) ? 0u : (g & (0xffffffffu << (nf[q] - pb)));
                             while (g) {
-                                const int p = pb + __ffs(g) - 1;
-                                g &= g - 1;
-                                if (p >= nf[q]) { cnt[q]++; nf[q] = p + klen; }
+                                const int i = __ffs(g) - 1;
+                                cnt[q]++;
+                                nf[q] = pb + i + klen;
+                                g = (i + klen >= 32) ? 0u : (g & (0xffffffffu << (i + klen)));
                             }
                         }
                     }
@@ -154,9 +166,13 @@ TG_EXPORT int tg_prefilter_count(const uint8_t *d_ascii, const int64_t *d_base_o
     TG_CUDA_CHECK(cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), st));
     long long g = ((long long)n_reads + PF_WARPS - 1) / PF_WARPS;
     if (g > (long long)sms * 8) g = (long long)sms * 8;
-    if (klen == 12) prefilter_count_kernel<12><<<(int)g, PF_WARPS * 32, 0, st>>>(P);        // human, C. elegans: 6-mer twice
-    else if (klen == 14) prefilter_count_kernel<14><<<(int)g, PF_WARPS * 32, 0, st>>>(P);   // maize: 7-mer twice
-    else prefilter_count_kernel<0><<<(int)g, PF_WARPS * 32, 0, st>>>(P);
+    bool doubled = (klen % 2) == 0;
+    for (int q = 0; q < 2 && doubled; q++)
+        for (int t = 0; t < klen / 2; t++) doubled = doubled && pats[q][t] == pats[q][t + klen / 2];
+    if (klen == 12 && doubled) prefilter_count_kernel<12, true><<<(int)g, PF_WARPS * 32, 0, st>>>(P);        // human, C. elegans: 6-mer twice
+    else if (klen == 14 && doubled) prefilter_count_kernel<14, true><<<(int)g, PF_WARPS * 32, 0, st>>>(P);   // maize: 7-mer twice
+    else if (klen == 12) prefilter_count_kernel<12, false><<<(int)g, PF_WARPS * 32, 0, st>>>(P);
+    else prefilter_count_kernel<0, false><<<(int)g, PF_WARPS * 32, 0, st>>>(P);
     TG_CUDA_CHECK(cudaGetLastError());
     return TG_OK;
 }

@@ -34,6 +34,12 @@ def test_counts_match_str_count(golden_reads, kmer_tables):
         want_r = np.array([r.count(kb) for r in reads])
         assert np.array_equal(cf, want_f), (canon, np.nonzero(cf != want_f)[0][:5])
         assert np.array_equal(cr, want_r), (canon, np.nonzero(cr != want_r)[0][:5])
+    # patterns that are not a word twice (generic matching chain), odd lengths, the longest supported pattern
+    for ka, kb in (('CCCTAACCCTAG', 'CTAGGGTTAGGG'), ('CCCTAAC', 'GTTAGGG'), ('C', 'G'), ('CCCTAA' * 5 + 'CC', 'GG' + 'TTAGGG' * 5),
+                   ('TTAGGGTTAGGG', 'CCCTAACCCTAA')):
+        cf, cr = tg_prefilter.count_initial_kmers(reads, ka, kb)
+        assert np.array_equal(cf, np.array([r.count(ka) for r in reads])), ka
+        assert np.array_equal(cr, np.array([r.count(kb) for r in reads])), kb
     keep = tg_prefilter.tel_read_prefilter(reads, 'CCCTAACCCTAA', 'TTAGGGTTAGGG', 5)
     assert keep == [(r.count('CCCTAACCCTAA') >= 5 or r.count('TTAGGGTTAGGG') >= 5) for r in reads]
     assert tg_prefilter.tel_read_prefilter([], 'CCCTAACCCTAA', 'TTAGGGTTAGGG', 5) == []
