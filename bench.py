@@ -447,8 +447,11 @@ def main():
         g.manual_seed(99)
         n_wgs, wgs_len = 131072, 16384                                 # 2.1 Gbases of genome-like reads (uniform ACGT) ...
         tail = tg_prefilter._lib.load().tg_prefilter_tail_bytes()
-        d_wgs = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device='cuda')[
-            torch.randint(0, 4, (n_wgs * wgs_len + tail,), generator=g, device='cuda')]
+        d_wgs = torch.empty(n_wgs * wgs_len + tail, dtype=torch.uint8, device='cuda')
+        acgt = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device='cuda')
+        for c0 in range(0, d_wgs.numel(), 1 << 26):
+            c1 = min(c0 + (1 << 26), d_wgs.numel())
+            d_wgs[c0:c1] = acgt[torch.randint(0, 4, (c1 - c0,), generator=g, device='cuda')]
         # ... with telomeric scan reads spliced in (every 512th read: still ~5x the telomeric fraction of a real 30x genome)
         TEL_EVERY = 512
         tel = [r for r in scan_reads if len(r) <= wgs_len][:n_wgs // TEL_EVERY]

@@ -40,3 +40,10 @@ for _ in range(2):
     out = tg_tvr.tvr_prep(kd, meta, 1000)
 torch.cuda.synchronize()
 print('prep reads', len(kd), 'letters', sum(k[1] for k in kd))
+from telogator2_b200 import tg_prefilter  # noqa: E402
+wg = [''.join(np.random.default_rng(5).choice(list('ACGT'), 16384)) for _ in range(64)] * 256
+ar = tg_prefilter.AsciiReads(wg + sr[:64])
+for _ in range(2):
+    ca, cb = ar.count_pair_device('CCCTAACCCTAA', 'TTAGGGTTAGGG')
+torch.cuda.synchronize()
+print('prefilter reads', ar.n, 'bases', int(ar.lens.astype(np.int64).sum()))
