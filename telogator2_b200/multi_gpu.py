@@ -128,3 +128,65 @@ def sharded_dist_matrix(engine, sequences, adjust_lens, min_viable, R, rng_seed,
     if engine is not None:
         engine.stats['d2h_bytes'] += out.nbytes
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# scan: reads are independent -> contiguous shares of equal base count, no exchange step on the data path; the per-read
+# results are exchanged once at the end
+# ---------------------------------------------------------------------------------------------------------
+def shard_reads_by_bases(lens, world):
+    """world + 1 boundaries: rank r owns reads [b[r], b[r+1]) -- contiguous, cumulative base count as even as possible."""
+    lens = np.asarray(lens, dtype=np.int64)
+    cum = np.concatenate([[0], np.cumsum(lens)])
+    targets = cum[-1] * np.arange(1, world, dtype=np.float64) / world
+    inner = np.searchsorted(cum, targets, side='left')
+    b = np.concatenate([[0], inner, [len(lens)]]).astype(np.int64)
+    return [int(x) for x in np.maximum.accumulate(b)]
+
+
+def strip_tel_results(res, meta):
+    """A rank's result list with every read sequence replaced by (global read index, reverse-complemented?) (from
+    _tel_repeat_comp_local's meta), so that only hits and numbers travel.  Entries are [hits, tlen, 0, 'q', name, mapq, read];
+    the interstitial sub-telomere pairs [(name_left, left), (name_right, right)] keep their names and lengths."""
+    out = list(res)
+    out[0] = [e[:6] + [m] for e, m in zip(res[0], meta['tvr'])]
+    keys = list(res[7].keys())
+    if len(keys) == len(meta['interstitial']) == len(res[6]):
+        out[6] = [[(nm, len(seq)) for (nm, seq) in pair] for pair in res[6]]
+        out[7] = {rn: res[7][rn][:6] + [m] for rn, m in zip(keys, meta['interstitial'])}
+        out[8] = {rn: res[8][rn][:6] + [m] for rn, m in zip(keys, meta['interstitial'])}
+        out.append(True)
+    else:                       # duplicate read names collapsed dictionary entries (as upstream): ship that part as it is
+        out.append(False)
+    return out
+
+
+def attach_tel_results(parts, all_read_dat):
+    """Merge the stripped per-rank results (rank order = read order) and put the sequences back."""
+    from .tg_util import RC
+
+    def attach(e):
+        idx, flipped = e[6]
+        seq = all_read_dat[idx][1]
+        return e[:6] + [RC(seq) if flipped else seq]
+    out = [[], [], [], 0, 0, 0, [], {}, {}]
+    for p in parts:
+        out[0] += [attach(e) for e in p[0]]
+        out[1] += p[1]
+        out[2] += p[2]
+        out[3] += p[3]
+        out[4] += p[4]
+        out[5] += p[5]
+        if not p[9]:
+            out[6] += p[6]
+            out[7].update(p[7])
+            out[8].update(p[8])
+            continue
+        for pair, rn in zip(p[6], p[7].keys()):
+            out[7][rn] = attach(p[7][rn])
+            out[8][rn] = attach(p[8][rn])
+            # interstitial sub-telomeres (tg_tel.py:283-286): left = read[:len_left], right = read[len - len_right:]
+            seq = out[7][rn][6]
+            (nl, ll), (nr, lr) = pair
+            out[6].append([(nl, seq[:ll]), (nr, seq[len(seq) - lr:])])
+    return out

@@ -31,6 +31,26 @@ def _reference_get_terminating_tl():
 
 
 def get_tel_repeat_comp_parallel(all_read_dat, gtrc_params, max_workers=4, max_pending=100, get_terminating_tl=None):
+    """tg_tel.py:331-389.  Under an initialised torch.distributed process group (one process per GPU) the reads are split
+    into contiguous shares of equal base count, every rank scans its share on its GPU, and the per-read results are
+    exchanged (no read sequence travels: each rank re-attaches them from its own copy of all_read_dat), so every rank
+    returns the complete 9-element list."""
+    from .multi_gpu import _dist_state, shard_reads_by_bases, strip_tel_results, attach_tel_results
+    dist, rank, world = _dist_state()
+    if world <= 1 or len(all_read_dat) < world:
+        return _tel_repeat_comp_local(all_read_dat, gtrc_params, get_terminating_tl, 0)
+    bounds = shard_reads_by_bases([len(r[1]) for r in all_read_dat], world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    mine, meta = _tel_repeat_comp_local(all_read_dat[lo:hi], gtrc_params, get_terminating_tl, lo, return_meta=True)
+    parts = [None] * world
+    dist.all_gather_object(parts, strip_tel_results(mine, meta))
+    return attach_tel_results(parts, all_read_dat)
+
+
+def _tel_repeat_comp_local(all_read_dat, gtrc_params, get_terminating_tl=None, index_offset=0, return_meta=False):
+    """The three phases on this process's GPU; index_offset = position of all_read_dat[0] in the caller's read list
+    (the telomere-signal plot file names depend on it, tg_tel.py:269-273).  return_meta: also return, for every entry that
+    carries a read sequence, (global read index, was it reverse-complemented) -- what the multi-GPU exchange ships instead."""
     [READ_TYPE, DUMMY_TEL_MAPQ,
      KMER_LIST, KMER_LIST_REV, KMER_ISSUBSTRING, CANONICAL_STRINGS, CANONICAL_STRINGS_REV,
      TEL_WINDOW_SIZE, P_VS_Q_AMP_THRESH,
@@ -66,7 +86,7 @@ def get_tel_repeat_comp_parallel(all_read_dat, gtrc_params, max_workers=4, max_p
             if my_qdat is not None:
                 my_qdat = my_qdat[::-1]
         if PLOT_TEL_SIGNALS:                                        # tg_tel.py:269-273 (pool passed the read index)
-            tel_signal_plot_dat = (my_rnm, TEL_SIGNAL_DIR + 'signal_' + str(i).zfill(5) + '.png')
+            tel_signal_plot_dat = (my_rnm, TEL_SIGNAL_DIR + 'signal_' + str(i + index_offset).zfill(5) + '.png')
             tel_signal_plot_num += 1
         else:
             tel_signal_plot_dat = None
@@ -117,27 +137,31 @@ def get_tel_repeat_comp_parallel(all_read_dat, gtrc_params, max_workers=4, max_p
     reads_removed_term_tel = reads_removed_term_unk = reads_removed_term_sub = 0
     interstitial_subtels = []
     interstitial_khd_by_readname, interstitial_khd_rev_by_readname = {}, {}
+    meta = {'tvr': [], 'interstitial': []}
     for i, st in enumerate(per_read):                               # tg_tel.py:352-375, read order
         my_rdat, my_rnm = st['rdat'], st['rnm']
         if st['want_tvr']:
             kmer_hit_dat.append([next(it_tvr), st['tvr_len'], 0, 'q', my_rnm.split(' ')[0], DUMMY_TEL_MAPQ, my_rdat])
             all_terminating_tl.append(st['termtel'])
             all_nontel_end.append(st['nontelend'])
+            meta['tvr'].append((i + index_offset, bool(flip[i])))
         if st['want_i']:
             (hf, hr) = next(it_i)
             interstitial_subtels.append(st['isubtels'])             # list of two tuples, as upstream
+            meta['interstitial'].append((i + index_offset, bool(flip[i])))
             rn = all_read_dat[i][0]
             interstitial_khd_by_readname[rn] = [hf, len(my_rdat), 0, 'q', my_rnm.split(' ')[0], DUMMY_TEL_MAPQ, my_rdat]
             interstitial_khd_rev_by_readname[rn] = [hr, len(my_rdat), 0, 'q', my_rnm.split(' ')[0], DUMMY_TEL_MAPQ, my_rdat]
         reads_removed_term_tel += st['skipped_termtel'] * 1
         reads_removed_term_unk += st['skipped_termunk'] * 1
         reads_removed_term_sub += st['skipped_termsub'] * 1
-    return [kmer_hit_dat,
-            all_terminating_tl,
-            all_nontel_end,
-            reads_removed_term_tel,
-            reads_removed_term_unk,
-            reads_removed_term_sub,
-            interstitial_subtels,
-            interstitial_khd_by_readname,
-            interstitial_khd_rev_by_readname]
+    res = [kmer_hit_dat,
+           all_terminating_tl,
+           all_nontel_end,
+           reads_removed_term_tel,
+           reads_removed_term_unk,
+           reads_removed_term_sub,
+           interstitial_subtels,
+           interstitial_khd_by_readname,
+           interstitial_khd_rev_by_readname]
+    return (res, meta) if return_meta else res

@@ -188,3 +188,48 @@ def test_random_stream_capacity_covers_cpython_draw_counts():
                 assert Counting.calls <= cap, (n, seed, R, Counting.calls, cap)
                 worst = max(worst, Counting.calls / cap)
     assert worst < 0.97
+
+
+def _fake_tel_local(all_read_dat, offset):
+    """Stand-in for tg_tel._tel_repeat_comp_local with the same result/meta structure, deterministic per read."""
+    from telogator2_b200.tg_util import RC
+    res = [[], [], [], 0, 0, 0, [], {}, {}]
+    meta = {'tvr': [], 'interstitial': []}
+    for i, (name, rdat, _q) in enumerate(all_read_dat):
+        flip = (len(rdat) % 3) == 0
+        my = RC(rdat) if flip else rdat
+        kind = len(rdat) % 5
+        if kind in (0, 1, 2):
+            res[0].append([[[1, 7]], len(my) // 2, 0, 'q', name.split(' ')[0], 60, my])
+            res[1].append(len(my) // 3)
+            res[2].append(len(my) % 11)
+            meta['tvr'].append((i + offset, flip))
+        elif kind == 3:
+            a, b = len(my) // 4, len(my) // 2
+            res[6].append([(f'interstitial-left_{len(my)}_{name}', my[:a]), (f'interstitial-right_{len(my)}_{name}', my[b:])])
+            res[7][name] = [[[0, 5]], len(my), 0, 'q', name.split(' ')[0], 60, my]
+            res[8][name] = [[[2, 9]], len(my), 0, 'q', name.split(' ')[0], 60, my]
+            meta['interstitial'].append((i + offset, flip))
+        else:
+            res[3] += 1
+            res[4] += len(rdat) % 2
+            res[5] += 1
+    return res, meta
+
+
+def test_scan_read_sharding_and_result_merge():
+    """Multi-GPU scan: contiguous shares by base count; stripped per-rank results merge to the unsharded result."""
+    from telogator2_b200.multi_gpu import shard_reads_by_bases, strip_tel_results, attach_tel_results
+    rng = np.random.default_rng(8)
+    reads = [(f'read{i} extra', ''.join(rng.choice(list('ACGT'), int(rng.integers(30, 400)))), None) for i in range(57)]
+    want, _ = _fake_tel_local(reads, 0)
+    for world in (2, 3, 8):
+        b = shard_reads_by_bases([len(r[1]) for r in reads], world)
+        assert b[0] == 0 and b[-1] == len(reads) and all(x <= y for x, y in zip(b, b[1:]))
+        tot = sum(len(r[1]) for r in reads)
+        assert max(sum(len(r[1]) for r in reads[b[k]:b[k + 1]]) for k in range(world)) <= tot / world + 400
+        parts = [strip_tel_results(*_fake_tel_local(reads[b[k]:b[k + 1]], b[k])) for k in range(world)]
+        import pickle
+        assert len(pickle.dumps(parts)) < len(pickle.dumps(want))          # no read sequence travels
+        assert attach_tel_results(parts, reads) == want
+    assert shard_reads_by_bases([1000, 1, 1, 1], 4) == [0, 1, 1, 1, 4]
