@@ -128,7 +128,14 @@ typedef struct tg_dist_batch_args {
     void *d_mt_work;                /* tg_dist_batch_mt_work_bytes(q1 - q0, R, max_len) bytes, or NULL for the single-kernel null model */
     int64_t q0, q1, seed0, shuf_base, slot;
     double match;                   /* match score, used when d_diag_cs == NULL */
-    int32_t n_seq, adjust_lens, min_viable, R, max_len, pad_;
+    int32_t n_seq, adjust_lens, min_viable, R, max_len;
+    int32_t n_mat;                  /* 0: one matrix over all n_seq sequences.  > 0: the pair space is the concatenation of the pair
+                                     * spaces of n_mat independent matrices (the per-cluster calls of tg_tvr.py:147-159, 375-390 batched):
+                                     * matrix b owns pairs [d_mat_pair_off[b], d_mat_pair_off[b+1]) and sequences
+                                     * [d_mat_seq_off[b], d_mat_seq_off[b+1]); d_order sorts each matrix's sequences by length
+                                     * (global indices); every matrix uses seeds seed0 + its own combinations index. */
+    const int64_t *d_mat_pair_off;  /* [n_mat + 1] */
+    const int32_t *d_mat_seq_off;   /* [n_mat + 1] */
 } tg_dist_batch_args;
 
 size_t tg_dist_batch_mt_work_bytes(int64_t n_pairs, int R, int max_len);
@@ -157,6 +164,10 @@ typedef struct tg_dist_epilogue_args {
     unsigned long long *d_stats;    /* [4] */
     int64_t q0, q1, ambig_base;     /* ambig entries are ambig_base + (q - q0) */
     int32_t n_seq, adjust_lens, min_viable, R, ambig_cap, margin_log2;
+    int32_t n_mat, pad_;            /* as in tg_dist_batch_args; matrix b (n_b x n_b, row-major) starts at d_matrix + d_mat_out_off[b] */
+    const int64_t *d_mat_pair_off;
+    const int32_t *d_mat_seq_off;
+    const int64_t *d_mat_out_off;   /* [n_mat] */
 } tg_dist_epilogue_args;
 
 int tg_dist_epilogue(const tg_dist_epilogue_args *args, void *stream);

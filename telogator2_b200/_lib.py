@@ -31,7 +31,7 @@ class DistBatchArgs(C.Structure):
                 ('q0', C.c_int64), ('q1', C.c_int64), ('seed0', C.c_int64), ('shuf_base', C.c_int64), ('slot', C.c_int64),
                 ('match', C.c_double),
                 ('n_seq', C.c_int32), ('adjust_lens', C.c_int32), ('min_viable', C.c_int32), ('R', C.c_int32),
-                ('max_len', C.c_int32), ('pad_', C.c_int32)]
+                ('max_len', C.c_int32), ('n_mat', C.c_int32), ('d_mat_pair_off', C.c_void_p), ('d_mat_seq_off', C.c_void_p)]
 
 
 class DistEpilogueArgs(C.Structure):
@@ -39,7 +39,8 @@ class DistEpilogueArgs(C.Structure):
                 ('d_flags', C.c_void_p), ('d_iden', C.c_void_p), ('d_matrix', C.c_void_p), ('d_ambig', C.c_void_p),
                 ('d_stats', C.c_void_p), ('q0', C.c_int64), ('q1', C.c_int64), ('ambig_base', C.c_int64),
                 ('n_seq', C.c_int32), ('adjust_lens', C.c_int32), ('min_viable', C.c_int32), ('R', C.c_int32),
-                ('ambig_cap', C.c_int32), ('margin_log2', C.c_int32)]
+                ('ambig_cap', C.c_int32), ('margin_log2', C.c_int32), ('n_mat', C.c_int32), ('pad_', C.c_int32),
+                ('d_mat_pair_off', C.c_void_p), ('d_mat_seq_off', C.c_void_p), ('d_mat_out_off', C.c_void_p)]
 
 
 class TgError(RuntimeError):

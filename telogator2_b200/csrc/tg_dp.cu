@@ -48,6 +48,7 @@ struct WaveParams {
     long long q0, q1;           // pair range in sorted pair space
     const uint8_t *flags;       // [q1 - q0] 1 = early-out (phase B skips the pair)
     long long shuf_base, slot;  // shuffle area: pool offset and bytes per pair
+    const long long *mat_pair_off; const int *mat_seq_off; int n_mat;   // several matrices in one pair space (0 = one matrix)
 };
 
 enum { JOBS_EXPLICIT = 0, JOBS_PHASE_A = 1, JOBS_PHASE_B = 2 };
@@ -65,15 +66,29 @@ __device__ __forceinline__ void unrank_pair(long long q, int n, int &a, int &b)
     b = (int)(q - r * (2LL * n - r - 1) / 2 + r + 1);
 }
 
-struct PairDesc { long long off_i, off_j; int n, m; long long p; int i, j; };
+struct PairDesc { long long off_i, off_j; int n, m; long long p; int i, j, mat, n_local; };
 
-// sorted-space pair q -> original (i < j), length-adjusted shapes (tg_align.py:115-120) and combinations index p
+// sorted-space pair q -> original (i < j), length-adjusted shapes (tg_align.py:115-120) and combinations index p.
+// With n_mat > 0 the pair space is the concatenation of the pair spaces of several independent matrices (the per-cluster
+// calls of iterations 1/2 and of the sub-telomere stage): matrix b owns pairs [mat_pair_off[b], mat_pair_off[b+1])
+// and sequences [mat_seq_off[b], mat_seq_off[b+1]); i, j, p are local to the matrix.
 template <typename PT>
 __device__ __forceinline__ PairDesc describe_pair(const PT &P, long long q)
 {
-    int a, b;
-    unrank_pair(q, P.n_seq, a, b);
-    const int oa = P.order[a], ob = P.order[b];
+    int a, b, nloc = P.n_seq, sbase = 0, mat = 0;
+    if (P.n_mat > 0) {
+        int lo = 0, hi = P.n_mat;                            // last matrix with mat_pair_off[mat] <= q
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (P.mat_pair_off[mid] <= q) lo = mid; else hi = mid;
+        }
+        mat = lo;
+        q -= P.mat_pair_off[mat];
+        sbase = P.mat_seq_off[mat];
+        nloc = P.mat_seq_off[mat + 1] - sbase;
+    }
+    unrank_pair(q, nloc, a, b);
+    const int oa = P.order[sbase + a], ob = P.order[sbase + b];
     const int i = min(oa, ob), j = max(oa, ob);
     PairDesc d;
     d.off_i = P.seq_off[i];
@@ -85,8 +100,8 @@ __device__ __forceinline__ PairDesc describe_pair(const PT &P, long long q)
         li = min(li, ml);
         lj = min(lj, ml);
     }
-    d.n = li; d.m = lj; d.i = i; d.j = j;
-    d.p = (long long)i * (2LL * P.n_seq - i - 1) / 2 + (j - i - 1);
+    d.n = li; d.m = lj; d.i = i - sbase; d.j = j - sbase; d.mat = mat; d.n_local = nloc;
+    d.p = (long long)d.i * (2LL * nloc - d.i - 1) / 2 + (d.j - d.i - 1);
     return d;
 }
 
@@ -651,6 +666,7 @@ struct BatchShuffleParams {
     long long seed0;
     int pool_stride;
     unsigned long long *counter;
+    const long long *mat_pair_off; const int *mat_seq_off; int n_mat;   // several matrices in one pair space (0 = one matrix)
 };
 
 // null model of every non-early pair of a batch; seed = abs(rng_seed + p) (tg_align.py:110-111,157,170-172)
@@ -705,6 +721,7 @@ struct StreamParams {
     int *overflow;
     const int *live;                 // pair indices (q - q0) that survived the early-out test, in no particular order
     const int *n_live;
+    const long long *mat_pair_off; const int *mat_seq_off; int n_mat;   // several matrices in one pair space (0 = one matrix)
 };
 
 __host__ __device__ __forceinline__ int mt_blocks_needed(int total_len)
@@ -946,6 +963,7 @@ struct FlagParams {
     int32_t *shape;               // [2 * pairs] length-adjusted n, m
     int *live;                    // optional: compacted list of non-early pairs (unordered) ...
     int *n_live;                  // ... and its length
+    const long long *mat_pair_off; const int *mat_seq_off; int n_mat;   // several matrices in one pair space (0 = one matrix)
 };
 
 // identity score and the early-out test of tvr_distance (tg_align.py:127-138), in float64 like the reference
@@ -987,6 +1005,8 @@ struct EpiParams {
     unsigned long long *stats;
     int ambig_cap;
     double eps;
+    const long long *mat_pair_off; const int *mat_seq_off; int n_mat;   // several matrices in one pair space (0 = one matrix)
+    const long long *mat_out_off;     // offset of matrix b in `matrix` (n_mat > 0)
 };
 
 // Python's min(x, MAX_SEQ_DIST) / max(x, MIN_SEQ_DIST): a NaN first argument is kept
@@ -1028,8 +1048,9 @@ __global__ void __launch_bounds__(256) dist_epilogue_kernel(const EpiParams P)
                 }
             }
         }
-        P.matrix[(size_t)d.i * P.n_seq + d.j] = f;
-        P.matrix[(size_t)d.j * P.n_seq + d.i] = f;
+        float *M = P.n_mat > 0 ? P.matrix + P.mat_out_off[d.mat] : P.matrix;
+        M[(size_t)d.i * d.n_local + d.j] = f;
+        M[(size_t)d.j * d.n_local + d.i] = f;
     }
     // block totals -> three atomics per block
     for (int o = 16; o > 0; o >>= 1) {
@@ -1284,6 +1305,8 @@ TG_EXPORT int tg_dist_batch(const tg_dist_batch_args *a, const tg_nw_scoring *sc
     P.seq_off = reinterpret_cast<const long long *>(a->d_seq_off); P.order = a->d_order; P.n_seq = a->n_seq;
     P.adjust_lens = a->adjust_lens; P.min_viable = a->min_viable; P.R = a->R;
     P.q0 = a->q0; P.q1 = a->q1; P.flags = a->d_flags; P.shuf_base = a->shuf_base; P.slot = a->slot;
+    if (a->n_mat < 0 || (a->n_mat > 0 && (!a->d_mat_pair_off || !a->d_mat_seq_off))) return tg_set_err(TG_EINVAL, "bad matrix table");
+    P.mat_pair_off = reinterpret_cast<const long long *>(a->d_mat_pair_off); P.mat_seq_off = a->d_mat_seq_off; P.n_mat = a->n_mat;
     auto grid_for_jobs = [&](long long jobs) { long long g = (jobs + warps - 1) / warps; return (int)(g < sms ? g : sms); };
     // ---- phase A: the real alignment of every pair ----
     P.n_jobs = wide ? npairs : (npairs + 1) / 2;
@@ -1295,6 +1318,7 @@ TG_EXPORT int tg_dist_batch(const tg_dist_batch_args *a, const tg_nw_scoring *sc
     F.seq_off = P.seq_off; F.order = P.order; F.n_seq = P.n_seq; F.adjust_lens = P.adjust_lens; F.min_viable = P.min_viable;
     F.R = a->R; F.q0 = a->q0; F.q1 = a->q1; F.aln = a->d_aln; F.diag_cs = a->d_diag_cs; F.match = a->match;
     F.flags = a->d_flags; F.iden = a->d_iden; F.shape = a->d_shape;
+    F.mat_pair_off = P.mat_pair_off; F.mat_seq_off = P.mat_seq_off; F.n_mat = P.n_mat;
     const bool streamed = a->R > 0 && a->d_mt_work && a->max_len < 65536;
     F.live = streamed ? reinterpret_cast<int *>(a->d_mt_work) : nullptr;
     F.n_live = reinterpret_cast<int *>(a->d_counter) + 6;
@@ -1317,6 +1341,7 @@ TG_EXPORT int tg_dist_batch(const tg_dist_batch_args *a, const tg_nw_scoring *sc
         S.pool = a->d_pool; S.seq_off = P.seq_off; S.order = P.order; S.n_seq = P.n_seq; S.adjust_lens = P.adjust_lens;
         S.min_viable = P.min_viable; S.R = a->R; S.q0 = a->q0; S.q1 = a->q1; S.flags = a->d_flags;
         S.shuf_base = a->shuf_base; S.slot = a->slot; S.seed0 = a->seed0; S.counter = P.counter;
+        S.mat_pair_off = P.mat_pair_off; S.mat_seq_off = P.mat_seq_off; S.n_mat = P.n_mat;
         S.cap = mt_blocks_needed(2 * a->R * a->max_len) * 624;
         const size_t live_bytes = ((size_t)npairs * sizeof(int) + 255) / 256 * 256;
         S.live = F.live; S.n_live = F.n_live;
@@ -1365,6 +1390,7 @@ TG_EXPORT int tg_dist_batch(const tg_dist_batch_args *a, const tg_nw_scoring *sc
     S.pool = a->d_pool; S.seq_off = P.seq_off; S.order = P.order; S.n_seq = P.n_seq; S.adjust_lens = P.adjust_lens;
     S.min_viable = P.min_viable; S.R = a->R; S.q0 = a->q0; S.q1 = a->q1; S.flags = a->d_flags;
     S.shuf_base = a->shuf_base; S.slot = a->slot; S.seed0 = a->seed0; S.counter = P.counter;
+    S.mat_pair_off = P.mat_pair_off; S.mat_seq_off = P.mat_seq_off; S.n_mat = P.n_mat;
     size_t msmem = 624 * MT_THREADS * sizeof(uint32_t) + (size_t)MT_THREADS * stride;
     if (msmem > 200 * 1024) { stride = 0; msmem = 624 * MT_THREADS * sizeof(uint32_t); }
     S.pool_stride = stride;
@@ -1511,6 +1537,9 @@ TG_EXPORT int tg_dist_epilogue(const tg_dist_epilogue_args *a, void *stream)
     E.aln = a->d_aln; E.rnd = a->d_rnd; E.flags = a->d_flags; E.iden = a->d_iden; E.matrix = a->d_matrix;
     E.ambig = reinterpret_cast<long long *>(a->d_ambig); E.stats = a->d_stats; E.ambig_cap = a->ambig_cap;
     E.eps = ldexp(1.0, -a->margin_log2);
+    if (a->n_mat < 0 || (a->n_mat > 0 && (!a->d_mat_pair_off || !a->d_mat_seq_off || !a->d_mat_out_off))) return tg_set_err(TG_EINVAL, "bad matrix table");
+    E.mat_pair_off = reinterpret_cast<const long long *>(a->d_mat_pair_off); E.mat_seq_off = a->d_mat_seq_off; E.n_mat = a->n_mat;
+    E.mat_out_off = reinterpret_cast<const long long *>(a->d_mat_out_off);
     long long g = (npairs + 255) / 256;
     if (g > (long long)sms * 8) g = (long long)sms * 8;
     dist_epilogue_kernel<<<(int)g, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(E);

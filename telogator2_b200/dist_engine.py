@@ -258,21 +258,40 @@ class DistEngine:
         # beyond 16-bit scores (int(sp.max()) * max_len > 65535) the library switches to 32-bit cells by itself
         return sp.min() >= 0 and sp.max() <= 127 and max_len <= MAX_WAVE32_LEN
 
-    def prepare(self, sequences):
+    def prepare(self, sequences, many=False):
         """Encode the sequences and make them resident on the device.  Returns the state consumed by matrix_device() /
-        _pair_scores_fast(), or None if this scoring/length needs the explicit-job path (pair_scores)."""
-        if len(sequences) < 2:
+        _pair_scores_fast(), or None if this scoring/length needs the explicit-job path (pair_scores).
+        many=True: `sequences` is a list of sequence lists, one independent matrix each (the per-cluster calls of
+        tg_tvr.py:147-159 / 375-390 batched into one pair space)."""
+        groups = [list(g) for g in sequences] if many else [sequences]
+        flat = [s for g in groups for s in g]
+        sizes = np.array([len(g) for g in groups], dtype=np.int64)
+        if int((sizes * (sizes - 1) // 2).sum()) == 0:
             return None
-        codes, off, sub = self.sc.encode_all(sequences)
+        codes, off, sub = self.sc.encode_all(flat)
         lens = np.diff(off)
         max_len = int(lens.max())
         if not self._fast_ok(sub, max_len):
             return None
         torch = self.torch
-        order = np.argsort(-lens, kind='stable').astype(np.int32)
+        mat_seq_off = np.zeros(len(groups) + 1, dtype=np.int32)
+        np.cumsum(sizes, out=mat_seq_off[1:])
+        # each matrix's sequences sorted by length, longest first (global indices)
+        order = np.concatenate([mat_seq_off[b] + np.argsort(-lens[mat_seq_off[b]:mat_seq_off[b + 1]], kind='stable')
+                                for b in range(len(groups))]).astype(np.int32)
         st = dict(n_seq=len(off) - 1, n_codes=len(codes), max_len=max_len, order=order, sub=sub, off=off,
                   d_codes=torch.from_numpy(codes).to(self.device), d_off=torch.from_numpy(off).to(self.device),
-                  d_order=torch.from_numpy(order).to(self.device), d_cs=None, cstruct=self.sc.c_struct(sub), pool=None)
+                  d_order=torch.from_numpy(order).to(self.device), d_cs=None, cstruct=self.sc.c_struct(sub), pool=None,
+                  n_mat=0, sizes=sizes, n_pairs=int((sizes * (sizes - 1) // 2).sum()), out_elems=int((sizes * sizes).sum()))
+        if many:
+            mat_pair_off = np.zeros(len(groups) + 1, dtype=np.int64)
+            np.cumsum(sizes * (sizes - 1) // 2, out=mat_pair_off[1:])
+            mat_out_off = np.zeros(len(groups) + 1, dtype=np.int64)
+            np.cumsum(sizes * sizes, out=mat_out_off[1:])
+            st.update(n_mat=len(groups), mat_seq_off=mat_seq_off, mat_pair_off=mat_pair_off, mat_out_off=mat_out_off,
+                      d_mat_seq_off=torch.from_numpy(mat_seq_off).to(self.device),
+                      d_mat_pair_off=torch.from_numpy(mat_pair_off).to(self.device),
+                      d_mat_out_off=torch.from_numpy(mat_out_off).to(self.device))
         self.stats['h2d_bytes'] += len(codes) + off.nbytes + order.nbytes
         if self.sc.alphabet is not None:
             # prefix sums of the substitution-matrix diagonal over the codes (identity score, tg_align.py:127-134)
@@ -288,7 +307,7 @@ class DistEngine:
         epilogue runs right behind each batch and fills the matrix."""
         torch = self.torch
         n_seq, n_codes, max_len = st['n_seq'], st['n_codes'], st['max_len']
-        n_pairs = n_seq * (n_seq - 1) // 2
+        n_pairs = st['n_pairs']
         R = max(int(R), 0)
         slot = 2 * R * max_len
         streamed = bool(streamed and R > 0 and not self.single_kernel_shuffle)
@@ -339,6 +358,8 @@ class DistEngine:
                 a.q0, a.q1, a.seed0, a.shuf_base, a.slot = q, q1, int(rng_seed), n_codes, slot
                 a.match = float(self.sc.match) if self.sc.alphabet is None else 0.0
                 a.n_seq, a.adjust_lens, a.min_viable, a.R, a.max_len = n_seq, int(bool(adjust_lens)), int(bool(min_viable)), R, st['max_len']
+                if st['n_mat']:
+                    a.n_mat, a.d_mat_pair_off, a.d_mat_seq_off = st['n_mat'], st['d_mat_pair_off'].data_ptr(), st['d_mat_seq_off'].data_ptr()
                 _lib.check(self.L.tg_dist_batch(C.byref(a), C.byref(st['cstruct']), stream))
                 self.stats['launches'] += (6 if streamed else 4) if R else 2
                 if d_matrix is not None:
@@ -349,34 +370,44 @@ class DistEngine:
                     e.q0, e.q1, e.ambig_base = q, q1, cpos
                     e.n_seq, e.adjust_lens, e.min_viable, e.R = n_seq, a.adjust_lens, a.min_viable, R
                     e.ambig_cap, e.margin_log2 = self.ambig_cap, self.margin_log2
+                    if st['n_mat']:
+                        e.n_mat, e.d_mat_pair_off, e.d_mat_seq_off = a.n_mat, a.d_mat_pair_off, a.d_mat_seq_off
+                        e.d_mat_out_off = st['d_mat_out_off'].data_ptr()
                     _lib.check(self.L.tg_dist_epilogue(C.byref(e), stream))
                     self.stats['launches'] += 1
                 q = q1
         return dev
 
-    def _compact_to_pairs(self, st, dev, pos):
-        """compact result positions -> (i, j) original sequence indices."""
+    def _compact_to_flat(self, st, dev, pos):
+        """compact result positions -> flat indices of D[i][j] and D[j][i] in the output buffer (all matrices back to back)."""
         starts = np.array([b for b, _ in dev['ranges']], dtype=np.int64)
         rpos = np.cumsum([0] + [e - b for b, e in dev['ranges']])
         ri = np.searchsorted(rpos, pos, side='right') - 1
         q = starts[ri] + (pos - rpos[ri])
-        n = st['n_seq']
+        if st['n_mat']:
+            mat = np.searchsorted(st['mat_pair_off'], q, side='right') - 1
+            q = q - st['mat_pair_off'][mat]
+            sbase = st['mat_seq_off'][mat].astype(np.int64)
+            n = st['sizes'][mat]
+            obase = st['mat_out_off'][mat]
+        else:
+            sbase, n, obase = 0, np.int64(st['n_seq']), 0
         t = 2.0 * n - 1.0
-        r = np.floor((t - np.sqrt(t * t - 8.0 * q)) * 0.5).astype(np.int64).clip(0, n - 2)
+        r = np.floor((t - np.sqrt(t * t - 8.0 * q)) * 0.5).astype(np.int64).clip(0, np.maximum(n - 2, 0))
         first = lambda rr: rr * (2 * n - rr - 1) // 2
         r = np.where(first(r) > q, r - 1, r)
         r = np.where(first(r + 1) <= q, r + 1, r)
         bcol = q - first(r) + r + 1
         o = st['order'].astype(np.int64)
-        return o[r], o[bcol]
+        i, j = o[sbase + r] - sbase, o[sbase + bcol] - sbase
+        return obase + i * n + j, obase + j * n + i
 
     def matrix_device(self, st, adjust_lens, min_viable, R, rng_seed, shard=None, streamed=True):
         """float32 (n, n) distance matrix ON THE DEVICE for this rank's share of the pair space (all of it without
         shard); other entries stay 0.  tg_align.py:154-189 without the host round trips: the kernels of every batch and
         the float epilogue are queued back to back, one synchronisation at the end."""
         torch = self.torch
-        n = st['n_seq']
-        D = torch.zeros((n, n), dtype=torch.float32, device=self.device)
+        D = torch.zeros(st['out_elems'], dtype=torch.float32, device=self.device)    # all matrices back to back
         dev = self._launch_fast(st, adjust_lens, min_viable, R, rng_seed, shard, streamed, d_matrix=D)
         tail = torch.cat([dev['stats'], dev['counter'].to(torch.int64)]).cpu().numpy()      # the one synchronisation
         self.stats['d2h_bytes'] += tail.nbytes
@@ -397,16 +428,17 @@ class DistEngine:
                 sub = dict(aln=dev['aln'][d_pc].cpu().numpy(), rnd=dev['rnd'][d_pc][:, :dev['R']].cpu().numpy(),
                            iden=dev['iden'][d_pc].cpu().numpy())
                 d = torch.from_numpy(self.distances(sub, dev['R']).astype('<f4')).to(self.device)
-                i, j = self._compact_to_pairs(st, dev, pc)
-                d_i, d_j = torch.from_numpy(i).to(self.device), torch.from_numpy(j).to(self.device)
-                D[d_i, d_j] = d
-                D[d_j, d_i] = d
+                fij, fji = self._compact_to_flat(st, dev, pc)
+                D[torch.from_numpy(fij).to(self.device)] = d
+                D[torch.from_numpy(fji).to(self.device)] = d
             self.stats['host_fixed_pairs'] = self.stats.get('host_fixed_pairs', 0) + len(pos)
         self.stats['pairs'] += dev['n_own']
         self.stats['early_out'] += int(tail[2])
         self.stats['cells'] += int(tail[0]) + int(tail[1])
         self.stats['wave32_jobs' if dev['wide'] else 'wave_jobs'] += dev['n_own']
-        return D
+        if st['n_mat']:
+            return D                                          # flat: matrix b = D[mat_out_off[b] : mat_out_off[b+1]].view(n_b, n_b)
+        return D.view(st['n_seq'], st['n_seq'])
 
     def _pair_scores_fast(self, st, adjust_lens, min_viable, R, rng_seed, shard, streamed=True):
         """Integer results of the device-driven path, copied to the host (parity tests, explicit gathers)."""

@@ -130,6 +130,30 @@ def sharded_dist_matrix(engine, sequences, adjust_lens, min_viable, R, rng_seed,
     return out
 
 
+def sharded_dist_matrices(engine, seq_lists, adjust_lens, min_viable, R, rng_seed):
+    """Several independent get_dist_matrix_parallel calls (one per entry of seq_lists, all with the same aligner and
+    rng_seed) as ONE device pass: the matrices' pair spaces are concatenated, so small per-cluster matrices (iterations 1/2,
+    sub-telomere stage) fill the GPU together, and under a process group the concatenated space is what gets
+    sharded.  Returns a list of float32 (n_b, n_b) host matrices, identical to the per-call results."""
+    dist, rank, world = _dist_state()
+    seq_lists = [list(g) for g in seq_lists]
+    st = engine.prepare(seq_lists, many=True) if any(len(g) >= 2 for g in seq_lists) else None
+    if st is None:                            # nothing to align, or outside the device-driven path: one call per matrix
+        if any(len(g) >= 2 for g in seq_lists):
+            return [sharded_dist_matrix(engine, g, adjust_lens, min_viable, R, rng_seed) for g in seq_lists]
+        return [np.zeros((len(g), len(g)), dtype='<f4') for g in seq_lists]
+    D = engine.matrix_device(st, adjust_lens, min_viable, R, rng_seed, shard=(rank, world) if world > 1 else None)
+    if world > 1:
+        D = reduce_matrix(D, dist)
+    import torch
+    host = torch.empty(D.shape, dtype=D.dtype, pin_memory=True)
+    host.copy_(D)
+    flat = host.numpy()
+    engine.stats['d2h_bytes'] += flat.nbytes
+    off = st['mat_out_off']
+    return [flat[off[b]:off[b + 1]].reshape(len(g), len(g)) for b, g in enumerate(seq_lists)]
+
+
 # ---------------------------------------------------------------------------------------------------------
 # scan: reads are independent -> contiguous shares of equal base count, no exchange step on the data path; the per-read
 # results are exchanged once at the end (SURVEY 8e)

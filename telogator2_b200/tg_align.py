@@ -190,6 +190,15 @@ def get_dist_matrix_parallel(sequences, aligner, adjust_lens, min_viable, rand_s
     return sharded_dist_matrix(eng, sequences, adjust_lens, min_viable, rand_shuffle_count, rng_seed)
 
 
+def get_dist_matrices_parallel(sequence_lists, aligner, adjust_lens, min_viable, rand_shuffle_count, rng_seed=12345):
+    """[get_dist_matrix_parallel(seqs, aligner, adjust_lens, min_viable, rand_shuffle_count, rng_seed=rng_seed) for seqs in
+    sequence_lists] in one device pass (no upstream counterpart: upstream calls tg_align.py:154-189 once per cluster,
+    tg_tvr.py:147-159 / 375-390).  Small matrices leave most of a GPU idle one at a time; batched they share it."""
+    eng = DistEngine(Scoring.from_aligner(aligner))
+    from .multi_gpu import sharded_dist_matrices
+    return sharded_dist_matrices(eng, sequence_lists, adjust_lens, min_viable, rand_shuffle_count, rng_seed)
+
+
 def quick_compare_tvrs(tvr_1, tvr_2):
     """tg_align.py:379-381 (match/mismatch scoring, free right end gaps, no reseed)."""
     aligner = get_aligner_object(gap_bool=(True, False), which_type='tvr')

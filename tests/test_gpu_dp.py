@@ -288,3 +288,22 @@ def test_negative_and_large_seeds(tga, colorvecs):
     seqs = [c[:500] for c in ont[:6]]
     for seed in (-12345, 0, 2 ** 40 + 7):
         _check_matrix(tga, seqs, 'tvr', (True, True), True, False, 2, seed)
+
+
+def test_many_matrices_in_one_pass_equal_the_per_call_results(tga, colorvecs):
+    """independent per-cluster matrices batched into one pair space give the per-call bits."""
+    ont, hifi = _cases(colorvecs)
+    allv = ont + hifi
+    groups = [[c[:3000] for c in allv[0:9]], [c[:700] for c in allv[9:11]], [allv[11][:50]], [], [c[:3000] for c in allv[12:30]],
+              [c[:1000 + 97 * i] for i, c in enumerate(allv[30:37])]]
+    for (which, gap_bool, adjust, minv, R, seed) in (('tvr', (True, True), True, True, 3, 12345), (None, (True, False), False, False, 3, 7)):
+        aligner = tga.get_aligner_object(tga.get_scoring_matrix('C', which) if which else None, gap_bool, 'tvr')
+        many = tga.get_dist_matrices_parallel(groups, aligner, adjust, minv, R, rng_seed=seed)
+        assert len(many) == len(groups)
+        P = _P(oracle.scoring_matrix('C', which) if which else None, gap_bool)
+        for g, D in zip(groups, many):
+            assert D.shape == (len(g), len(g)) and D.dtype == np.dtype('<f4')
+            one = tga.get_dist_matrix_parallel(g, aligner, adjust, minv, R, rng_seed=seed)
+            assert np.array_equal(D, one)
+            if 2 <= len(g) <= 9:
+                assert np.array_equal(D, oracle.dist_matrix_c(g, P, adjust, minv, R, seed))
