@@ -414,6 +414,38 @@ def main():
                      'frac': ach / pk['hbm_gbs'], 'traffic': ncu_traffic('scan_cov_kernel<density>', scan_bases), 'peak_source': src, 'launch_ms': min(ds) * 1e3,
                      'bytes_per_base': 2.375, 'mbases_per_s': scan_bases / min(ds) / 1e6}
 
+    # ---------------- D2: many small matrices, iteration-2 shape (N=48, L<=3000, R=3) ----------------
+    d2 = None
+    if rank == 0:
+        rs2 = np.random.default_rng(21)
+        long_cv = [c for c in (cv['human_ont'] + cv['human_hifi']) if len(c) >= 3000]
+        groups = []
+        for gi in range(64):
+            grp = []
+            for k in range(48):
+                sq = list(long_cv[(gi * 48 + k) % len(long_cv)][:3000])
+                for ppos in rs2.choice(3000, 60, replace=False):
+                    sq[ppos] = 'CVHTFDA'[rs2.integers(7)]
+                grp.append(''.join(sq))
+            groups.append(grp)
+        tg_align.get_dist_matrices_parallel(groups[:2], aligner, True, True, 3, rng_seed=SEED)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        many = tg_align.get_dist_matrices_parallel(groups, aligner, True, True, 3, rng_seed=SEED)
+        t_many = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        ones = [tg_align.get_dist_matrix_parallel(gq, aligner, True, True, 3, rng_seed=SEED) for gq in groups[:16]]
+        t_one = (time.perf_counter() - t0) * len(groups) / 16
+        assert all(np.array_equal(a, b) for a, b in zip(many[:16], ones)), 'batched matrices differ from the per-call matrices'
+        e3 = DistEngine(Scoring.from_aligner(aligner))
+        e3.matrix_device(e3.prepare(groups, many=True), True, True, 3, SEED)
+        d2 = {'matrices': len(groups), 'n_seq': 48, 'len': 3000, 'R': 3, 'cells': int(e3.stats['cells']),
+              'batched_gcups': e3.stats['cells'] / t_many / 1e9, 'batched_ms': t_many * 1e3,
+              'per_call_gcups': e3.stats['cells'] / t_one / 1e9, 'per_call_ms': t_one * 1e3,
+              'what': 'host strings -> host matrices; batched = get_dist_matrices_parallel (one pass), per_call = one '
+                      'get_dist_matrix_parallel per matrix (16 timed, scaled)'}
+        del many, ones, e3
+
     # ---------------- colour-vector preparation, host lists in -> host lists out ----------------
     prep = None
     if rank == 0:
@@ -544,7 +576,7 @@ def main():
                          'what': 'basecount x2 + orient + density x2 + hits on the last 6000 bases of every read (device resident)',
                          'parts_ms': {k: float(np.mean(v)) for k, v in scan_parts.items() if v}},
                 'roofline': roof, 'roofline_scan': roof_scan, 'cpu_baseline': cpu, 'clocks': clocks,
-                'prep': prep, 'prefilter': prefilter,
+                'prep': prep, 'prefilter': prefilter, 'd2': d2,
                 'multi_gpu_verified_pairs': verified,
                 'wall_s_timed_region': t_wall}
         print(json.dumps(line))

@@ -72,11 +72,13 @@ struct PairDesc { long long off_i, off_j; int n, m; long long p; int i, j, mat, 
 // With n_mat > 0 the pair space is the concatenation of the pair spaces of several independent matrices (the per-cluster
 // calls of iterations 1/2 and of the sub-telomere stage): matrix b owns pairs [mat_pair_off[b], mat_pair_off[b+1])
 // and sequences [mat_seq_off[b], mat_seq_off[b+1]); i, j, p are local to the matrix.
-template <typename PT>
+// MM = false compiles the matrix lookup out: the wave kernel's single-matrix instantiations keep their code generation
+// (an A/B run showed the extra branch costing the dominant kernel 1 %).
+template <bool MM = true, typename PT>
 __device__ __forceinline__ PairDesc describe_pair(const PT &P, long long q)
 {
     int a, b, nloc = P.n_seq, sbase = 0, mat = 0;
-    if (P.n_mat > 0) {
+    if (MM && P.n_mat > 0) {
         int lo = 0, hi = P.n_mat;                            // last matrix with mat_pair_off[mat] <= q
         while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
@@ -236,7 +238,7 @@ struct Strip2x16 {
 // Shared memory per warp: query profile [2][A+1][W] bytes, then row letters [row_cap] u16 (a0 | a1 << 8).
 // V = 0: 16 columns x 1 row per step, V = 1: 8 x 1, V = 2: 8 columns x 2 rows, V = 3: 16 columns x 2 rows per step
 // WIDE: one alignment per job in 32-bit cells (scores beyond 16 bits: long sequences); profile [1][A+1][W].
-template <int V, int MODE, bool WIDE>
+template <int V, int MODE, bool WIDE, bool MM>
 __global__ void __launch_bounds__(WAVE_MAX_WARPS * 32, 1) nw_wave_kernel(const __grid_constant__ WaveParams P)
 {
     constexpr int NH = WIDE ? 1 : 2;                                         // alignments per job
@@ -286,24 +288,24 @@ __global__ void __launch_bounds__(WAVE_MAX_WARPS * 32, 1) nw_wave_kernel(const _
             out0 = J->out[0]; out1 = J->out[1];
         } else if (MODE == JOBS_PHASE_A && WIDE) {
             const long long qa = P.q0 + (long long)jid;
-            const PairDesc da = describe_pair(P, qa);
+            const PairDesc da = describe_pair<MM>(P, qa);
             row0 = row1 = da.off_i; col0 = col1 = da.off_j; n0 = n1 = da.n; m0 = m1 = da.m;
             out0 = (int)(qa - P.q0); out1 = -1;
         } else if (MODE == JOBS_PHASE_B && WIDE) {
             const long long qa = P.q0 + (long long)(jid / P.R);
             const int ta = (int)(jid % P.R);
             if (P.flags[qa - P.q0]) continue;
-            const PairDesc da = describe_pair(P, qa);
+            const PairDesc da = describe_pair<MM>(P, qa);
             row0 = row1 = P.shuf_base + (qa - P.q0) * P.slot + (long long)ta * (da.n + da.m); col0 = col1 = row0 + da.n;
             n0 = n1 = da.n; m0 = m1 = da.m;
             out0 = (int)((qa - P.q0) * P.R + ta); out1 = -1;
         } else if (MODE == JOBS_PHASE_A) {
             // job = sorted-space pairs q0 + 2*jid and q0 + 2*jid + 1 (tg_align.py:125)
             const long long qa = P.q0 + 2 * (long long)jid, qb = qa + 1;
-            const PairDesc da = describe_pair(P, qa);
+            const PairDesc da = describe_pair<MM>(P, qa);
             row0 = da.off_i; col0 = da.off_j; n0 = da.n; m0 = da.m; out0 = (int)(qa - P.q0);
             if (qb < P.q1) {
-                const PairDesc db = describe_pair(P, qb);
+                const PairDesc db = describe_pair<MM>(P, qb);
                 row1 = db.off_i; col1 = db.off_j; n1 = db.n; m1 = db.m; out1 = (int)(qb - P.q0);
             } else { row1 = row0; col1 = col0; n1 = n0; m1 = m0; out1 = -1; }
         } else {
@@ -318,8 +320,8 @@ __global__ void __launch_bounds__(WAVE_MAX_WARPS * 32, 1) nw_wave_kernel(const _
             const bool hb = (qb < P.q1) && !P.flags[qb - P.q0];
             if (!ha && !hb) continue;
             PairDesc da, db;
-            if (ha) da = describe_pair(P, qa);
-            if (hb) db = (qb == qa) ? da : describe_pair(P, qb);
+            if (ha) da = describe_pair<MM>(P, qa);
+            if (hb) db = (qb == qa) ? da : describe_pair<MM>(P, qb);
             if (!ha) { da = db; qa = qb; ta = tb; }
             if (!hb) { db = da; qb = qa; tb = ta; }
             row0 = P.shuf_base + (qa - P.q0) * P.slot + (long long)ta * (da.n + da.m); col0 = row0 + da.n;
@@ -1155,11 +1157,11 @@ TG_EXPORT int tg_nw_wave_check(const tg_nw_scoring *sc, const tg_nw_job *h_jobs,
     return TG_OK;
 }
 
-template <int V, int MODE, bool WIDE>
+template <int V, int MODE, bool WIDE, bool MM = false>
 static int wave_launch_t(const WaveParams &P, int grid, int warps, size_t smem, cudaStream_t st)
 {
-    TG_CUDA_CHECK(cudaFuncSetAttribute(nw_wave_kernel<V, MODE, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nw_wave_kernel<V, MODE, WIDE><<<grid, warps * 32, smem, st>>>(P);
+    TG_CUDA_CHECK(cudaFuncSetAttribute(nw_wave_kernel<V, MODE, WIDE, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nw_wave_kernel<V, MODE, WIDE, MM><<<grid, warps * 32, smem, st>>>(P);
     TG_CUDA_CHECK(cudaGetLastError());
     return TG_OK;
 }
@@ -1168,6 +1170,10 @@ template <int V, bool WIDE = false>
 static int wave_launch_v(const WaveParams &P, int mode, int grid, int warps, size_t smem, cudaStream_t st)
 {
     if (mode == JOBS_EXPLICIT) return wave_launch_t<V, JOBS_EXPLICIT, WIDE>(P, grid, warps, smem, st);
+    if (V == 3 && P.n_mat > 0) {              // several matrices in one pair space: default geometry only
+        if (mode == JOBS_PHASE_A) return wave_launch_t<3, JOBS_PHASE_A, WIDE, true>(P, grid, warps, smem, st);
+        return wave_launch_t<3, JOBS_PHASE_B, WIDE, true>(P, grid, warps, smem, st);
+    }
     if (mode == JOBS_PHASE_A) return wave_launch_t<V, JOBS_PHASE_A, WIDE>(P, grid, warps, smem, st);
     return wave_launch_t<V, JOBS_PHASE_B, WIDE>(P, grid, warps, smem, st);
 }
@@ -1298,6 +1304,7 @@ TG_EXPORT int tg_dist_batch(const tg_dist_batch_args *a, const tg_nw_scoring *sc
     }
     int rc = wave_setup(P, sc, a->max_len, &C, &warps, &smem, wide);
     if (rc != TG_OK) return rc;
+    if (a->n_mat > 0 && C != 3) return tg_set_err(TG_EINVAL, "several matrices per call need the default wave variant (TG_WAVE_VARIANT=3)");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     P.pool = a->d_pool; P.jobs = nullptr; P.scores = a->d_aln;
     P.scratch = reinterpret_cast<uint32_t *>(a->d_scratch);
