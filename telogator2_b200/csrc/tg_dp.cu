@@ -51,7 +51,10 @@ struct WaveParams {
     const long long *mat_pair_off; const int *mat_seq_off; int n_mat;   // several matrices in one pair space (0 = one matrix)
 };
 
-enum { JOBS_EXPLICIT = 0, JOBS_PHASE_A = 1, JOBS_PHASE_B = 2 };
+// JOBS_PHASE_A_SHCOL: phase A with the two alignments of a job sharing their COLUMN sequence (pairs (a, b), (a, b+1) of the
+// sorted pair space share sequence a; NW is symmetric in its two sequences when the substitution matrix is): one query profile
+// per warp instead of two, so almost twice as many warps are resident.
+enum { JOBS_EXPLICIT = 0, JOBS_PHASE_A = 1, JOBS_PHASE_B = 2, JOBS_PHASE_A_SHCOL = 3 };
 
 // pair q of itertools.combinations(range(n), 2) -> (a, b), a < b
 __device__ __forceinline__ void unrank_pair(long long q, int n, int &a, int &b)
@@ -66,7 +69,7 @@ __device__ __forceinline__ void unrank_pair(long long q, int n, int &a, int &b)
     b = (int)(q - r * (2LL * n - r - 1) / 2 + r + 1);
 }
 
-struct PairDesc { long long off_i, off_j; int n, m; long long p; int i, j, mat, n_local; };
+struct PairDesc { long long off_i, off_j; int n, m; long long p; int i, j, mat, n_local, ra; bool a_is_i; };
 
 // sorted-space pair q -> original (i < j), length-adjusted shapes (tg_align.py:115-120) and combinations index p.
 // With n_mat > 0 the pair space is the concatenation of the pair spaces of several independent matrices (the per-cluster
@@ -103,6 +106,7 @@ __device__ __forceinline__ PairDesc describe_pair(const PT &P, long long q)
         lj = min(lj, ml);
     }
     d.n = li; d.m = lj; d.i = i - sbase; d.j = j - sbase; d.mat = mat; d.n_local = nloc;
+    d.ra = a; d.a_is_i = (oa == i);            // sorted rank of the longer sequence, and whether it is the pair's first sequence
     d.p = (long long)d.i * (2LL * nloc - d.i - 1) / 2 + (d.j - d.i - 1);
     return d;
 }
@@ -241,7 +245,8 @@ struct Strip2x16 {
 template <int V, int MODE, bool WIDE, bool MM>
 __global__ void __launch_bounds__(WAVE_MAX_WARPS * 32, 1) nw_wave_kernel(const __grid_constant__ WaveParams P)
 {
-    constexpr int NH = WIDE ? 1 : 2;                                         // alignments per job
+    constexpr bool SHCOL = (MODE == JOBS_PHASE_A_SHCOL);
+    constexpr int NH = (WIDE || SHCOL) ? 1 : 2;                              // query profiles per job
     constexpr int C = (V == 0 || V == 3) ? 16 : 8;
     constexpr int RR = (V >= 2) ? 2 : 1;
     constexpr int W = 32 * C;
@@ -263,16 +268,45 @@ __global__ void __launch_bounds__(WAVE_MAX_WARPS * 32, 1) nw_wave_kernel(const _
     const uint32_t prof_s = (uint32_t)__cvta_generic_to_shared(prof);
     const uint32_t rows_s = (uint32_t)__cvta_generic_to_shared(rows);
     const uint32_t pb0 = prof_s + lane * C;
-    const uint32_t pb1 = WIDE ? pb0 : prof_s + (uint32_t)A1 * W + lane * C;
+    const uint32_t pb1 = (WIDE || SHCOL) ? pb0 : prof_s + (uint32_t)A1 * W + lane * C;
 
+    // SHCOL: a job whose two pairs cannot share their columns runs as two single alignments, the second one parked here
+    bool pend = false;
+    long long pend_row = 0, pend_col = 0;
+    int pend_n = 0, pend_m = 0, pend_out = -1;
     for (;;) {
         unsigned long long jid = 0;
-        if (lane == 0) jid = atomicAdd(P.counter, 1ULL);
-        jid = __shfl_sync(TG_FULL_MASK, jid, 0);
-        if (jid >= (unsigned long long)P.n_jobs) break;
+        if (!(SHCOL && pend)) {
+            if (lane == 0) jid = atomicAdd(P.counter, 1ULL);
+            jid = __shfl_sync(TG_FULL_MASK, jid, 0);
+            if (jid >= (unsigned long long)P.n_jobs) break;
+        }
         long long row0, row1, col0, col1;
         int n0, n1, m0, m1, out0, out1;
-        if (MODE == JOBS_EXPLICIT && WIDE) {
+        if (SHCOL) {
+            if (pend) {
+                row0 = row1 = pend_row; col0 = col1 = pend_col; n0 = n1 = pend_n; m0 = m1 = pend_m; out0 = pend_out; out1 = -1;
+                pend = false;
+            } else {
+                const long long qa = P.q0 + 2 * (long long)jid, qb = qa + 1;
+                const PairDesc da = describe_pair<MM>(P, qa);
+                // columns = the longer sequence (sorted rank ra, shared by neighbouring pairs), rows = its partner
+                row0 = da.a_is_i ? da.off_j : da.off_i; n0 = da.a_is_i ? da.m : da.n;
+                col0 = da.a_is_i ? da.off_i : da.off_j; m0 = da.a_is_i ? da.n : da.m;
+                out0 = (int)(qa - P.q0);
+                row1 = row0; col1 = col0; n1 = n0; m1 = m0; out1 = -1;
+                if (qb < P.q1) {
+                    const PairDesc db = describe_pair<MM>(P, qb);
+                    const long long rowb = db.a_is_i ? db.off_j : db.off_i, colb = db.a_is_i ? db.off_i : db.off_j;
+                    const int nb = db.a_is_i ? db.m : db.n, mb = db.a_is_i ? db.n : db.m;
+                    if (db.ra == da.ra && db.mat == da.mat && colb == col0 && mb == m0) {
+                        row1 = rowb; n1 = nb; out1 = (int)(qb - P.q0);
+                    } else {
+                        pend = true; pend_row = rowb; pend_col = colb; pend_n = nb; pend_m = mb; pend_out = (int)(qb - P.q0);
+                    }
+                }
+            }
+        } else if (MODE == JOBS_EXPLICIT && WIDE) {
             // item = (job, half)
             const tg_nw_job *J = P.jobs + (jid >> 1);
             const int h = (int)(jid & 1);
@@ -358,10 +392,10 @@ __global__ void __launch_bounds__(WAVE_MAX_WARPS * 32, 1) nw_wave_kernel(const _
                 const int b1 = (j1 >= 0) ? (int)__ldg(P.pool + col1 + j1) : -1;
                 for (int a = 0; a < A; a++) {
                     prof[(size_t)a * W + x] = (b0 >= 0) ? s_sp[a * MAXA + b0] : (uint8_t)0;
-                    if (!WIDE) prof[(size_t)(A1 + a) * W + x] = (b1 >= 0) ? s_sp[a * MAXA + b1] : (uint8_t)0;
+                    if (!WIDE && !SHCOL) prof[(size_t)(A1 + a) * W + x] = (b1 >= 0) ? s_sp[a * MAXA + b1] : (uint8_t)0;
                 }
                 prof[(size_t)A * W + x] = 0;
-                if (!WIDE) prof[(size_t)(A1 + A) * W + x] = 0;
+                if (!WIDE && !SHCOL) prof[(size_t)(A1 + A) * W + x] = 0;
             }
             __syncwarp();
 
@@ -1108,6 +1142,7 @@ __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t *out, int iters,
 static int g_wave_variant = 3;     // 0: 16 cols x 1 row, 1: 8 x 1, 2: 8 cols x 2 rows per step; TG_WAVE_VARIANT overrides
 static int g_wave_warps = 0;       // 0 = as many as shared memory allows
 
+static bool g_wave_shcol = true;            // TG_WAVE_SHCOL=0 disables the shared-column phase A (A/B measurements)
 static void wave_env()
 {
     static bool done = false;
@@ -1115,6 +1150,7 @@ static void wave_env()
     done = true;
     if (const char *e = getenv("TG_WAVE_VARIANT")) { const int v = atoi(e); if (v >= 0 && v <= 3) g_wave_variant = v; }
     if (const char *e = getenv("TG_WAVE_WARPS")) { const int v = atoi(e); if (v >= 1 && v <= WAVE_MAX_WARPS) g_wave_warps = v; }
+    if (const char *e = getenv("TG_WAVE_SHCOL")) g_wave_shcol = atoi(e) != 0;
 }
 
 TG_EXPORT size_t tg_nw_wave_scratch_bytes(int max_n)
@@ -1170,6 +1206,7 @@ template <int V, bool WIDE = false>
 static int wave_launch_v(const WaveParams &P, int mode, int grid, int warps, size_t smem, cudaStream_t st)
 {
     if (mode == JOBS_EXPLICIT) return wave_launch_t<V, JOBS_EXPLICIT, WIDE>(P, grid, warps, smem, st);
+    if (mode == JOBS_PHASE_A_SHCOL) return wave_launch_t<3, JOBS_PHASE_A_SHCOL, false, false>(P, grid, warps, smem, st);
     if (V == 3 && P.n_mat > 0) {              // several matrices in one pair space: default geometry only
         if (mode == JOBS_PHASE_A) return wave_launch_t<3, JOBS_PHASE_A, WIDE, true>(P, grid, warps, smem, st);
         return wave_launch_t<3, JOBS_PHASE_B, WIDE, true>(P, grid, warps, smem, st);
@@ -1208,7 +1245,8 @@ static int wave_launch_inner(const WaveParams &P, int mode, int variant, int gri
 }
 
 // shared set-up of the three job modes
-static int wave_setup(WaveParams &P, const tg_nw_scoring *sc, int max_n, int *C_out, int *warps_out, size_t *smem_out, bool wide = false)
+static int wave_setup(WaveParams &P, const tg_nw_scoring *sc, int max_n, int *C_out, int *warps_out, size_t *smem_out, bool wide = false,
+                      bool one_profile = false)
 {
     wave_env();
     int max_sp = 0;
@@ -1222,7 +1260,7 @@ static int wave_setup(WaveParams &P, const tg_nw_scoring *sc, int max_n, int *C_
         for (int b = 0; b < MAXA; b++)
             P.sp[a * MAXA + b] = (a < sc->alphabet && b < sc->alphabet) ? (uint8_t)(sc->sub[a * MAXA + b] - 2 * sc->gap) : 0;
     const int C = (wide || g_wave_variant == 0 || g_wave_variant == 3) ? 16 : 8;
-    const size_t per_warp = (size_t)(wide ? 1 : 2) * (sc->alphabet + 1) * 32 * C + (size_t)P.row_cap * 2 + 512;
+    const size_t per_warp = (size_t)((wide || one_profile) ? 1 : 2) * (sc->alphabet + 1) * 32 * C + (size_t)P.row_cap * 2 + 512;
     int warps = (int)((226 * 1024 - MAXA * MAXA) / per_warp);
     if (warps > WAVE_MAX_WARPS) warps = WAVE_MAX_WARPS;
     if (g_wave_warps && warps > g_wave_warps) warps = g_wave_warps;
@@ -1318,7 +1356,19 @@ TG_EXPORT int tg_dist_batch(const tg_dist_batch_args *a, const tg_nw_scoring *sc
     // ---- phase A: the real alignment of every pair ----
     P.n_jobs = wide ? npairs : (npairs + 1) / 2;
     TG_CUDA_CHECK(cudaMemsetAsync(a->d_counter, 0, sizeof(unsigned long long), st));
-    rc = wave_launch(P, JOBS_PHASE_A, C, grid_for_jobs(P.n_jobs), warps, smem, st, wide);
+    bool shcol = !wide && a->n_mat == 0 && C == 3 && g_wave_shcol;
+    for (int x = 0; x < sc->alphabet && shcol; x++)                    // role swap needs a symmetric substitution matrix
+        for (int y = 0; y < x; y++) shcol = shcol && sc->sub[x * MAXA + y] == sc->sub[y * MAXA + x];
+    if (shcol) {
+        int C2, warps2;
+        size_t smem2;
+        rc = wave_setup(P, sc, a->max_len, &C2, &warps2, &smem2, false, true);
+        if (rc != TG_OK) return rc;
+        long long g2 = (P.n_jobs + warps2 - 1) / warps2;
+        rc = wave_launch(P, JOBS_PHASE_A_SHCOL, 3, (int)(g2 < sms ? g2 : sms), warps2, smem2, st, false);
+    } else {
+        rc = wave_launch(P, JOBS_PHASE_A, C, grid_for_jobs(P.n_jobs), warps, smem, st, wide);
+    }
     if (rc != TG_OK) return rc;
     // ---- identity score + early-out flags ----
     FlagParams F;
