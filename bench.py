@@ -415,8 +415,10 @@ def main():
                      'bytes_per_base': 2.375, 'mbases_per_s': scan_bases / min(ds) / 1e6}
 
     # ---------------- D2: many small matrices, iteration-2 shape (N=48, L<=3000, R=3) ----------------
+    # (single-process runs only: the public API it calls is collective under a process group, and the other ranks are
+    #  not taking part here)
     d2 = None
-    if rank == 0:
+    if world == 1:
         rs2 = np.random.default_rng(21)
         long_cv = [c for c in (cv['human_ont'] + cv['human_hifi']) if len(c) >= 3000]
         groups = []
@@ -448,7 +450,7 @@ def main():
 
     # ---------------- colour-vector preparation, host lists in -> host lists out ----------------
     prep = None
-    if rank == 0:
+    if world == 1:
         from telogator2_b200 import tg_tvr
         kd_prep, meta_prep, flat_prep = make_prep_workload(2048)
         tg_tvr.tvr_prep(kd_prep[:64], meta_prep, 1000)
@@ -473,7 +475,7 @@ def main():
 
     # ---------------- stage [0a] prefilter: str.count of KMER_INITIAL / RC over every read ----------------
     prefilter = None
-    if rank == 0:
+    if world == 1:
         from telogator2_b200 import tg_prefilter
         g = torch.Generator(device='cuda')
         g.manual_seed(99)
