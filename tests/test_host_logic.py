@@ -233,3 +233,200 @@ def test_scan_read_sharding_and_result_merge():
         assert len(pickle.dumps(parts)) < len(pickle.dumps(want))          # no read sequence travels
         assert attach_tel_results(parts, reads) == want
     assert shard_reads_by_bases([1000, 1, 1, 1], 4) == [0, 1, 1, 1, 4]
+
+
+def test_compact_positions_map_to_matrix_cells_single_and_many():
+    """Host fix-up path of the device epilogue: compact result position -> flat cells (i, j), (j, i) of the output buffer,
+    for one matrix and for several matrices in one pair space, over sharded ranges."""
+    from itertools import combinations
+    from telogator2_b200.dist_engine import DistEngine, fast_ranges
+    rng = np.random.default_rng(12)
+    for sizes in ([7], [5, 0, 1, 9, 2, 6]):
+        sizes = np.array(sizes, dtype=np.int64)
+        many = len(sizes) > 1
+        lens = [rng.integers(5, 50, size=int(n)) for n in sizes]
+        seq_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+        order = np.concatenate([seq_off[b] + np.argsort(-lens[b], kind='stable') for b in range(len(sizes))]).astype(np.int32)
+        pair_off = np.concatenate([[0], np.cumsum(sizes * (sizes - 1) // 2)]).astype(np.int64)
+        out_off = np.concatenate([[0], np.cumsum(sizes * sizes)]).astype(np.int64)
+        st = dict(n_seq=int(sizes.sum()), order=order, n_mat=len(sizes) if many else 0, sizes=sizes, mat_pair_off=pair_off,
+                  mat_seq_off=seq_off, mat_out_off=out_off)
+        # brute force: sorted pair space = per matrix, combinations over the ranks; cell indices are local original indices
+        want = []
+        for b, n in enumerate(sizes):
+            for (a, c) in combinations(range(int(n)), 2):
+                i, j = order[seq_off[b] + a] - seq_off[b], order[seq_off[b] + c] - seq_off[b]
+                want.append((out_off[b] + i * n + j, out_off[b] + j * n + i))
+        n_pairs = len(want)
+        for world in (1, 3):
+            for rank in range(world):
+                ranges = fast_ranges(n_pairs, rank, world, min_block=4)
+                q_of_pos = np.concatenate([np.arange(b, e) for b, e in ranges]) if ranges else np.zeros(0, dtype=np.int64)
+                if len(q_of_pos) == 0:
+                    continue
+                fij, fji = DistEngine._compact_to_flat(None, st, dict(ranges=ranges), np.arange(len(q_of_pos), dtype=np.int64))
+                assert [(int(x), int(y)) for x, y in zip(fij, fji)] == [tuple(int(v) for v in want[q]) for q in q_of_pos]
+
+
+def _clz32(x):
+    return 32 - int(x).bit_length()
+
+
+def test_warp_sampler_algorithm_equals_sequential_random_sample():
+    """Python emulation of mt_sample_warp_kernel's group step (acceptance fixed point over the ballot mask, reads against the
+    pre-group pool patched with the group's own earlier writes) against the sequential pool algorithm of random.sample."""
+    import random
+
+    def seq_shuffle(pool, draws):
+        pool = list(pool); n = len(pool); res = []; c = 0
+        for i in range(n):
+            nn = n - i
+            while True:
+                v = draws[c]; c += 1
+                r = v >> (_clz32(nn) - 16)
+                if r < nn:
+                    break
+            res.append(pool[r]); pool[r] = pool[nn - 1]
+        return res, c
+
+    def warp_shuffle(pool, draws):
+        arr = list(pool) + [None] * 8
+        ln = len(pool); nn = ln; c = 0; out = [None] * ln
+        while nn > 0:
+            v = [draws[c + l] for l in range(32)]
+            A = 0
+            while True:
+                Aprev = A; acc = []; rs = []; az = []
+                for l in range(32):
+                    a = bin(Aprev & ((1 << l) - 1)).count('1'); nl = nn - a
+                    ok = False; r = 0
+                    if nl > 0:
+                        r = v[l] >> (_clz32(nl) - 16); ok = r < nl
+                    acc.append(ok); rs.append(r); az.append(a)
+                A = sum(1 << l for l in range(32) if acc[l])
+                if A == Aprev:
+                    break
+            S = bin(A).count('1')
+            c += A.bit_length() if S == nn else 32
+            scr = [0] * 32
+            for l in range(32):
+                if (A >> l) & 1:
+                    scr[az[l]] = rs[l]
+            j = [scr[l] if l < S else 0 for l in range(32)]
+            vj = [arr[j[l]] if l < S else 0 for l in range(32)]
+            vt = [arr[nn - 1 - l] if l < S else 0 for l in range(32)]
+            hit = [-1] * 32
+            for l in range(S):
+                tg = nn - 1 - j[l]
+                if l < tg < S:
+                    hit[tg] = max(hit[tg], l)
+            root = [l if hit[l] < 0 else hit[l] for l in range(32)]
+            while True:
+                h = [hit[root[l]] for l in range(32)]
+                if not any(x >= 0 for x in h):
+                    break
+                root = [h[l] if h[l] >= 0 else root[l] for l in range(32)]
+            tail = [vt[root[l]] for l in range(32)]
+            for l in range(S):
+                before = [w for w in range(l) if j[w] == j[l]]
+                out[ln - nn + l] = tail[before[-1]] if before else vj[l]
+            for l in range(S):
+                if not any(j[w] == j[l] for w in range(l + 1, S)):
+                    arr[j[l]] = tail[l]
+            nn -= S
+        return out, c
+
+    rng = random.Random(5)
+    for trial in range(400):
+        n = rng.choice([1, 2, 3, 5, 17, 31, 32, 33, 63, 64, 65, 100, 127, 128, 129, 500, 1000, 1023, 1025])
+        pool = [rng.randrange(256) for _ in range(n)] if trial % 2 else list(range(n))
+        draws = [rng.randrange(65536) for _ in range(4 * n + 600)]
+        assert seq_shuffle(pool, draws) == warp_shuffle(pool, draws), (trial, n)
+
+
+def test_prefilter_bit_tricks():
+    """The arithmetic of prefilter_count_kernel: the multiply that gathers bit B of four ASCII letters into a nibble, the
+    2-bit code of A/C/G/T, the doubled-pattern shortcut and the jump-ahead greedy count, emulated on integers."""
+    M32 = 0xffffffff
+    for B in (1, 2):
+        M = (1 << (28 - B)) | (1 << (29 - B - 8)) | (1 << (30 - B - 16)) | (1 << (31 - B - 24))
+        for bits in range(16):
+            for noise in (0x00000000, 0x41434754, 0xffffffff, 0x9e3779b9):
+                w = noise & ~(0x01010101 << B) & M32
+                for k in range(4):
+                    if (bits >> k) & 1:
+                        w |= 1 << (8 * k + B)
+                assert ((((w & (0x01010101 << B)) * M) & M32) >> 28) == bits
+    code = {c: ((ord(c) >> 1) & 1) | (((ord(c) >> 2) & 1) << 1) for c in 'ACGT'}
+    assert sorted(code.values()) == [0, 1, 2, 3]
+
+    def count_gpu_style(read, pat):
+        k = len(pat)
+        doubled = k % 2 == 0 and pat[:k // 2] == pat[k // 2:]
+        n = len(read)
+        half_ok = [all(i + t < n and read[i + t] == pat[t] for t in range(k // 2)) for i in range(n)] if doubled else None
+        good = []
+        for i in range(n - k + 1):
+            m = (half_ok[i] and half_ok[i + k // 2]) if doubled else read[i:i + k] == pat
+            good.append(m)
+        cnt, nf = 0, 0
+        for w0 in range(0, len(good), 32):                       # per 32-position word: drop bits below nf, jump by k
+            g = sum(1 << i for i, m in enumerate(good[w0:w0 + 32]) if m)
+            if nf > w0:
+                g = 0 if nf - w0 >= 32 else g & (M32 << (nf - w0)) & M32
+            while g:
+                i = (g & -g).bit_length() - 1
+                cnt += 1
+                nf = w0 + i + k
+                g = 0 if i + k >= 32 else g & (M32 << (i + k)) & M32
+        return cnt
+    rng = np.random.default_rng(2)
+    reads = ['CCCTAA' * 50, 'A' * 40, 'CCCTAACCCTA' + 'CCCTAACCCTAA' * 3, ''.join(rng.choice(list('ACGT'), 3000)), 'AAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAA',
+              'CCCTAA' * 7 + 'G' + 'CCCTAA' * 9]
+    for pat in ('CCCTAACCCTAA', 'AAAAAAAAAAAA', 'ACACACAC', 'CCCTAAC', 'AA', 'CCCTAAACCCTAAA'):
+        for r in reads:
+            assert count_gpu_style(r, pat) == r.count(pat), (pat, r[:30])
+
+
+def test_denoise_stencil_restatement_matches_reference_golden():
+    """cv_denoise_kernel's formulation (survival of a block is local; a dropped position takes the letter of its nearest surviving
+    neighbours when they match, are mergeable and close) emulated in Python against the reference's block-list algorithm."""
+    import gzip
+    import json
+    with gzip.open(os.path.join(ROOT, 'tests', 'golden', 'tvr_prep_golden.json.gz'), 'rt') as f:
+        cases = json.load(f)['denoise']
+
+    def stencil(v, rep, min_size, gap, dele, mrg):
+        if not v:
+            return ''
+        L = len(v)
+        keep = L - (len(v) - len(v.rstrip(rep)))                  # positions >= keep: the run that is never closed
+        c = [v[y] if y < keep else None for y in range(L + 1)]
+        surv = [False] * (L + 1)
+        for y in range(keep):
+            s = True
+            if c[y] in dele:
+                size, k = 1, y - 1
+                while size < min_size and k >= 0 and c[k] == c[y]:
+                    size += 1; k -= 1
+                k = y + 1
+                while size < min_size and k <= L and c[k] == c[y]:
+                    size += 1; k += 1
+                s = size >= min_size
+            surv[y] = s
+        out = []
+        for x in range(L + 1):
+            o = rep
+            if surv[x]:
+                o = c[x]
+            elif x < keep:
+                yl = next((x - k for k in range(1, gap + 1) if x - k >= 0 and surv[x - k]), None)
+                yr = next((x + k for k in range(1, gap + 1) if x + k <= L and surv[x + k]), None)
+                if yl is not None and yr is not None and c[yl] == c[yr] and c[yl] in mrg and yr - yl - 1 <= gap:
+                    o = c[yl]
+            out.append(o)
+        return ''.join(out)
+    for cse in cases[::3]:
+        if len(cse['v']) > 3000:
+            continue
+        assert stencil(cse['v'], cse['replace'], cse['min_size'], cse['max_gap_fill'], cse['delete'], cse['merge']) == cse['out']
