@@ -464,3 +464,37 @@ def quick_tvrtel_lens_py(kmer_dat, meta):
     _canon, sets = _flag_letters(meta)
     unk = [UNKNOWN] + sets['subtel-filt']
     return [len(subtel_tvr_split_py(colorvec_py(kd['hits'], kd['tlen'], meta[2]), unk)[1]) for kd in kmer_dat]
+
+
+# =====================================================================================================
+# Stand-in for Bio.Align.PairwiseAligner that lets the REFERENCE's own tvr_distance / get_dist_matrix_parallel run here
+# (tests/golden/make_golden_dp_ref.py): everything of tg_align.py:109-189 is then the reference's code -- length adjust,
+# Counter-based identity score, early-out, random.seed + shuffle_seq order, np.mean, -log ratio, clamps, seeds per pair,
+# float32 matrix fill -- and only aligner.score() (Biopython's C, absent) is answered by this oracle's NW restatement.
+# =====================================================================================================
+class _LetterMatrix:
+    """aligner.substitution_matrix[n, n] with letter keys (tg_align.py:131-132)."""
+
+    def __init__(self, S):
+        self.S = np.ascontiguousarray(S, dtype=np.float64)
+
+    def __getitem__(self, key):
+        a, b = key
+        return self.S[ALPHABET.index(a), ALPHABET.index(b)]
+
+
+class ScoreStandInAligner:
+    """Picklable (the reference submits it to a ProcessPoolExecutor)."""
+
+    def __init__(self, S=None, gap_bool=(True, True), match=5., mismatch=-4., gap=-4.):
+        self._args = (None if S is None else np.array(S, dtype=np.float64), tuple(gap_bool), match, mismatch, gap)
+        self.substitution_matrix = None if S is None else _LetterMatrix(S)
+        self.match_score = float(match)
+        self.mismatch_score = float(mismatch)
+
+    def params(self):
+        S, gap_bool, match, mismatch, gap = self._args
+        return AlignerParams(S, gap_bool, match, mismatch, gap)
+
+    def score(self, a, b):
+        return float(nw_score(a, b, self.params()))

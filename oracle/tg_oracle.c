@@ -15,6 +15,11 @@
  *     not vendored in the reference and not installable here.  tgo_nw_score restates its
  *     published Needleman-Wunsch score path (linear gaps, left/right end-gap classes) as
  *     used from tg_align.py:71-106,125,142.
+ *   - everything AROUND the score in tvr_distance / get_dist_matrix_parallel (tg_align.py:109-189: length
+ *     adjustment, identity score, early-out, random.seed + shuffle order, mean, -log ratio, clamps, per-pair
+ *     seeds, float32 fill): PINNED against the reference's own code, run in the build container with a stand-in
+ *     aligner whose score() is tgo_nw_score (tests/golden/make_golden_dp_ref.py -> dp_ref_golden.npz).
+ *   - colour-vector preparation (tg_tvr.py): PINNED (tests/golden/make_golden_tvr.py).
  */
 #include <stdint.h>
 #include <stdlib.h>

@@ -147,3 +147,26 @@ def test_tvr_prep_oracle_matches_reference_golden():
             for k, v in S[f'prep_trunc{tr}'].items():
                 assert got[k] == v, (key, tr, k)
         assert oracle.quick_tvrtel_lens_py(S['kmer_dat'], meta) == S['quick_tvrtel_lens']
+
+
+def test_distance_half_pinned_against_reference_code(colorvecs, dp_golden):
+    """tests/golden/dp_ref_golden.npz was produced by the reference's OWN tvr_distance / get_dist_matrix_parallel (process pool,
+    random.seed, shuffle_seq, Counter identity score, clamps, float32 fill) with only aligner.score() answered by the oracle's
+    NW restatement (make_golden_dp_ref.py).  The oracle's matrices -- the ones the GPU tests compare with -- must equal them."""
+    import os
+    from conftest import ROOT
+    ref = np.load(os.path.join(ROOT, 'tests', 'golden', 'dp_ref_golden.npz'))
+    for key in ('ont24_tvr_R2', 'hifi24_tvr_R2', 'ont12_tvr2000_R3', 'ont12_ms_rightfree_R3'):
+        assert np.array_equal(ref[key + '|D'], dp_golden[key + '|D']), key
+    cv = colorvecs['colorvecs']['human_ont']
+    seqs = [c[:1000] for c in cv][:24]
+    P = oracle.AlignerParams(oracle.scoring_matrix('C', 'tvr'), (True, True))
+    assert np.array_equal(oracle.dist_matrix_c(seqs, P, True, True, 2, 12345), ref['ont24_tvr_R2|D'])
+    ont = [c[:1500] for c in cv][:6]
+    got = [oracle.tvr_distance_py(ont[0], ont[k], P, True, True, 3, rng_seed=777 + k) for k in range(1, 6)]
+    assert got == list(ref['single_reseeded'])
+    import random
+    P2 = oracle.AlignerParams(None, (True, False))
+    random.seed(4242)
+    got2 = [oracle.tvr_distance_py(ont[0], ont[k], P2, False, False, 3, rng_seed=None) / 10.0 for k in range(1, 6)]
+    assert got2 == list(ref['quick_compare_style_seed4242'])
