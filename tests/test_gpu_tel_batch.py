@@ -71,7 +71,54 @@ def oracle_flow(all_read_dat, gtrc_params):
     return out
 
 
-@pytest.mark.parametrize('tkey,filters', [('human_hifi', (400, 100, 1000)), ('human_ont', (0, 0, 0)), ('maize_hifi', (400, 100, 1000))])
+def tel_cases():
+    return [('human_hifi', (400, 100, 1000)), ('human_ont', (0, 0, 0)), ('maize_hifi', (400, 100, 1000))]
+
+
+def digest_tel_result(res):
+    """JSON-able form of the 9-element result with read sequences replaced by SHA-1 digests (golden fixture format)."""
+    import hashlib
+
+    def h(s):
+        return hashlib.sha1(s.encode('latin-1')).hexdigest()
+
+    def entry(e):
+        return [[[list(map(int, sp)) for sp in k] for k in e[0]], int(e[1]), int(e[2]), e[3], e[4], int(e[5]), h(e[6])]
+    return [[entry(e) for e in res[0]], [int(x) for x in res[1]], [int(x) for x in res[2]], int(res[3]), int(res[4]), int(res[5]),
+            [[[nm, h(seq)] for (nm, seq) in pair] for pair in res[6]],
+            {rn: entry(e) for rn, e in res[7].items()}, {rn: entry(e) for rn, e in res[8].items()}]
+
+
+def _tel_inputs(kmer_tables, golden_reads, tkey, filters):
+    T = kmer_tables[tkey]
+    KL, ISSUB, CANON = T['KMER_LIST'], T['KMER_ISSUBSTRING'], T['CANONICAL_STRINGS']
+    KLR, CANON_REV = [rc_py(k) for k in KL], [rc_py(k) for k in CANON]
+    reads = [(name + ' extra', seq, None) for name, seq in golden_reads[tkey]]
+    reads += [(n, s, None) for n, s in golden_reads['synthetic'] if len(s) > 0 and set(s) <= set('ACGTN')]
+    params = [T['read_type'], 60, KL, KLR, ISSUB, CANON, CANON_REV, 100, 0.5, 100, filters[0], filters[1], filters[2],
+              False, '', 100, 1000]
+    return reads, params
+
+
+def reference_golden():
+    import gzip
+    import json
+    import os
+    from conftest import ROOT
+    with gzip.open(os.path.join(ROOT, 'tests', 'golden', 'tel_batch_golden.json.gz'), 'rt') as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize('tkey,filters', tel_cases())
+def test_batch_boundary_matches_reference_driver(kmer_tables, golden_reads, tkey, filters):
+    """GPU batch boundary vs the output of the reference's own get_tel_repeat_comp_parallel (tests/golden/make_golden_tel.py)."""
+    from telogator2_b200 import tg_kmer, tg_tel
+    reads, params = _tel_inputs(kmer_tables, golden_reads, tkey, filters)
+    got = tg_tel.get_tel_repeat_comp_parallel(reads, params, max_workers=7, get_terminating_tl=make_gtt(tg_kmer.get_telomere_kmer_density))
+    assert digest_tel_result(got) == reference_golden()[tkey]
+
+
+@pytest.mark.parametrize('tkey,filters', tel_cases())
 def test_batch_boundary_matches_per_read_flow(kmer_tables, golden_reads, tkey, filters):
     from telogator2_b200 import tg_kmer, tg_tel
     T = kmer_tables[tkey]

@@ -170,3 +170,13 @@ def test_distance_half_pinned_against_reference_code(colorvecs, dp_golden):
     random.seed(4242)
     got2 = [oracle.tvr_distance_py(ont[0], ont[k], P2, False, False, 3, rng_seed=None) / 10.0 for k in range(1, 6)]
     assert got2 == list(ref['quick_compare_style_seed4242'])
+
+
+def test_scan_batch_flow_pinned_against_reference_driver(kmer_tables, golden_reads):
+    """tests/golden/tel_batch_golden.json.gz is the output of the reference's own get_tel_repeat_comp_parallel (process pool +
+    gtrc_parallel_job, tg_tel.py:238-389; make_golden_tel.py).  The per-read restatement the GPU test compares with must equal it."""
+    from test_gpu_tel_batch import _tel_inputs, digest_tel_result, oracle_flow, reference_golden, tel_cases
+    gold = reference_golden()
+    for tkey, filters in tel_cases():
+        reads, params = _tel_inputs(kmer_tables, golden_reads, tkey, filters)
+        assert digest_tel_result(oracle_flow(reads, params)) == gold[tkey], tkey
