@@ -430,3 +430,17 @@ def test_denoise_stencil_restatement_matches_reference_golden():
         if len(cse['v']) > 3000:
             continue
         assert stencil(cse['v'], cse['replace'], cse['min_size'], cse['max_gap_fill'], cse['delete'], cse['merge']) == cse['out']
+
+
+def test_header_is_plain_c():
+    """The drop-in boundary is a C ABI: include/telogator2_b200.h must compile as C99 (no C++-isms, no torch types)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which('gcc')
+    if gcc is None:
+        pytest.skip('no gcc')
+    hdr = os.path.join(ROOT, 'include', 'telogator2_b200.h')
+    r = subprocess.run([gcc, '-std=c99', '-Wall', '-Wextra', '-Werror', '-fsyntax-only', '-x', 'c', hdr], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    txt = open(hdr).read()
+    assert 'torch' not in txt.lower() and 'at::' not in txt and 'std::' not in txt
