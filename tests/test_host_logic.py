@@ -443,4 +443,4 @@ def test_header_is_plain_c():
     r = subprocess.run([gcc, '-std=c99', '-Wall', '-Wextra', '-Werror', '-fsyntax-only', '-x', 'c', hdr], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     txt = open(hdr).read()
-    assert 'torch' not in txt.lower() and 'at::' not in txt and 'std::' not in txt
+    assert '#include <torch' not in txt and 'at::' not in txt and 'std::' not in txt and 'Tensor' not in txt
