@@ -258,7 +258,7 @@ def main():
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     from telogator2_b200 import tg_align, tg_kmer
     from telogator2_b200.dist_engine import DistEngine, Scoring
-    from telogator2_b200.multi_gpu import shard_pair_indices, reduce_matrix, sharded_dist_matrix
+    from telogator2_b200.multi_gpu import local_only, shard_pair_indices, reduce_matrix, sharded_dist_matrix
 
     cv, reads, tables = load_fixtures()
     # weak scaling: the pair space grows with the number of GPUs (n_seq * sqrt(world)), each rank owns 1/world of it
@@ -539,19 +539,20 @@ def main():
         h2d, d2h = eng2.stats['h2d_bytes'], eng2.stats['d2h_bytes']
     verified = None
     if world > 1 and rank == 0:
-        # cross-check the reduced multi-GPU matrix on a sample of pairs recomputed locally through the
-        # explicit-job path + host epilogue (same global pair indices -> same seeds)
-        rs = np.random.default_rng(7)
-        sample = np.sort(rs.choice(n_pairs, size=min(256, n_pairs), replace=False)).astype(np.int64)
-        chk = DistEngine(Scoring.from_aligner(aligner)).pair_scores(seqs, True, True, R, SEED, pair_idx=sample)
-        want = DistEngine.distances({k: chk[k][sample] for k in ('aln', 'rnd', 'iden')}, R).astype('<f4')
-        ar = np.arange(n_seq, dtype=np.int64)
-        row_start = ar * (2 * n_seq - ar - 1) // 2
-        si = np.minimum(np.searchsorted(row_start, sample, side='right') - 1, n_seq - 2)
-        got = D[si, sample - row_start[si] + si + 1]
-        assert np.array_equal(got, want), 'multi-GPU matrix mismatch'
-        assert np.array_equal(D, D.T)
-        verified = int(len(sample))
+        with local_only():                   # rank 0 alone: nothing in here may take part in a collective
+            # cross-check the reduced multi-GPU matrix on a sample of pairs recomputed locally through the
+            # explicit-job path + host epilogue (same global pair indices -> same seeds)
+            rs = np.random.default_rng(7)
+            sample = np.sort(rs.choice(n_pairs, size=min(256, n_pairs), replace=False)).astype(np.int64)
+            chk = DistEngine(Scoring.from_aligner(aligner)).pair_scores(seqs, True, True, R, SEED, pair_idx=sample)
+            want = DistEngine.distances({k: chk[k][sample] for k in ('aln', 'rnd', 'iden')}, R).astype('<f4')
+            ar = np.arange(n_seq, dtype=np.int64)
+            row_start = ar * (2 * n_seq - ar - 1) // 2
+            si = np.minimum(np.searchsorted(row_start, sample, side='right') - 1, n_seq - 2)
+            got = D[si, sample - row_start[si] + si + 1]
+            assert np.array_equal(got, want), 'multi-GPU matrix mismatch'
+            assert np.array_equal(D, D.T)
+            verified = int(len(sample))
     e2e_t = allmax(min(e2e_ms) * 1e-3)
     e2e_gcups = cells_all / e2e_t / 1e9
     assert D.shape == (n_seq, n_seq)

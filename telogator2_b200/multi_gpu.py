@@ -21,7 +21,27 @@ def shard_pair_indices(n_pairs, rank, world, block=SHARD_BLOCK):
     return idx[idx < n_pairs]
 
 
+_LOCAL_ONLY = 0
+
+
+class local_only:
+    """Context manager: inside it the sharding entry points behave as in a single-process run even if a process group is
+    initialised -- for code that only SOME ranks execute (a collective there would hang the job)."""
+
+    def __enter__(self):
+        global _LOCAL_ONLY
+        _LOCAL_ONLY += 1
+        return self
+
+    def __exit__(self, *exc):
+        global _LOCAL_ONLY
+        _LOCAL_ONLY -= 1
+        return False
+
+
 def _dist_state():
+    if _LOCAL_ONLY:
+        return None, 0, 1
     try:
         import torch.distributed as dist
     except Exception:                                   # noqa: BLE001

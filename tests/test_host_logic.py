@@ -444,3 +444,18 @@ def test_header_is_plain_c():
     assert r.returncode == 0, r.stderr
     txt = open(hdr).read()
     assert '#include <torch' not in txt and 'at::' not in txt and 'std::' not in txt and 'Tensor' not in txt
+
+
+def test_local_only_hides_the_process_group():
+    """multi_gpu.local_only(): code that only some ranks run must see a single-process world (bench.py's rank-0 sections)."""
+    from telogator2_b200 import multi_gpu
+    calls = []
+    real = multi_gpu._dist_state
+    assert real()[2] == 1                                  # no process group in this test process
+    with multi_gpu.local_only():
+        assert multi_gpu._LOCAL_ONLY == 1 and multi_gpu._dist_state() == (None, 0, 1)
+        with multi_gpu.local_only():
+            assert multi_gpu._LOCAL_ONLY == 2
+        assert multi_gpu._LOCAL_ONLY == 1
+    assert multi_gpu._LOCAL_ONLY == 0
+    del calls
