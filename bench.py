@@ -419,110 +419,119 @@ def main():
     #  not taking part here)
     d2 = None
     if world == 1:
-        rs2 = np.random.default_rng(21)
-        long_cv = [c for c in (cv['human_ont'] + cv['human_hifi']) if len(c) >= 3000]
-        groups = []
-        for gi in range(64):
-            grp = []
-            for k in range(48):
-                sq = list(long_cv[(gi * 48 + k) % len(long_cv)][:3000])
-                for ppos in rs2.choice(3000, 60, replace=False):
-                    sq[ppos] = 'CVHTFDA'[rs2.integers(7)]
-                grp.append(''.join(sq))
-            groups.append(grp)
-        tg_align.get_dist_matrices_parallel(groups[:2], aligner, True, True, 3, rng_seed=SEED)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        many = tg_align.get_dist_matrices_parallel(groups, aligner, True, True, 3, rng_seed=SEED)
-        t_many = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        ones = [tg_align.get_dist_matrix_parallel(gq, aligner, True, True, 3, rng_seed=SEED) for gq in groups[:16]]
-        t_one = (time.perf_counter() - t0) * len(groups) / 16
-        assert all(np.array_equal(a, b) for a, b in zip(many[:16], ones)), 'batched matrices differ from the per-call matrices'
-        e3 = DistEngine(Scoring.from_aligner(aligner))
-        e3.matrix_device(e3.prepare(groups, many=True), True, True, 3, SEED)
-        d2 = {'matrices': len(groups), 'n_seq': 48, 'len': 3000, 'R': 3, 'cells': int(e3.stats['cells']),
-              'batched_gcups': e3.stats['cells'] / t_many / 1e9, 'batched_ms': t_many * 1e3,
-              'per_call_gcups': e3.stats['cells'] / t_one / 1e9, 'per_call_ms': t_one * 1e3,
-              'what': 'host strings -> host matrices; batched = get_dist_matrices_parallel (one pass), per_call = one '
-                      'get_dist_matrix_parallel per matrix (16 timed, scaled)'}
-        del many, ones, e3
+        try:
+            rs2 = np.random.default_rng(21)
+            long_cv = [c for c in (cv['human_ont'] + cv['human_hifi']) if len(c) >= 3000]
+            groups = []
+            for gi in range(64):
+                grp = []
+                for k in range(48):
+                    sq = list(long_cv[(gi * 48 + k) % len(long_cv)][:3000])
+                    for ppos in rs2.choice(3000, 60, replace=False):
+                        sq[ppos] = 'CVHTFDA'[rs2.integers(7)]
+                    grp.append(''.join(sq))
+                groups.append(grp)
+            tg_align.get_dist_matrices_parallel(groups[:2], aligner, True, True, 3, rng_seed=SEED)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            many = tg_align.get_dist_matrices_parallel(groups, aligner, True, True, 3, rng_seed=SEED)
+            t_many = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            ones = [tg_align.get_dist_matrix_parallel(gq, aligner, True, True, 3, rng_seed=SEED) for gq in groups[:16]]
+            t_one = (time.perf_counter() - t0) * len(groups) / 16
+            assert all(np.array_equal(a, b) for a, b in zip(many[:16], ones)), 'batched matrices differ from the per-call matrices'
+            e3 = DistEngine(Scoring.from_aligner(aligner))
+            e3.matrix_device(e3.prepare(groups, many=True), True, True, 3, SEED)
+            d2 = {'matrices': len(groups), 'n_seq': 48, 'len': 3000, 'R': 3, 'cells': int(e3.stats['cells']),
+                  'batched_gcups': e3.stats['cells'] / t_many / 1e9, 'batched_ms': t_many * 1e3,
+                  'per_call_gcups': e3.stats['cells'] / t_one / 1e9, 'per_call_ms': t_one * 1e3,
+                  'what': 'host strings -> host matrices; batched = get_dist_matrices_parallel (one pass), per_call = one '
+                          'get_dist_matrix_parallel per matrix (16 timed, scaled)'}
+            del many, ones, e3
 
+        except Exception as exc:                      # an auxiliary line must not cost the headline metric
+            d2 = {'error': f'{type(exc).__name__}: {exc}'}
     # ---------------- colour-vector preparation, host lists in -> host lists out ----------------
     prep = None
     if world == 1:
-        from telogator2_b200 import tg_tvr
-        kd_prep, meta_prep, flat_prep = make_prep_workload(2048)
-        tg_tvr.tvr_prep(kd_prep[:64], meta_prep, 1000)
-        pt = []
-        for _ in range(3):
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            got_prep = tg_tvr.tvr_prep(kd_prep, meta_prep, 1000)
-            pt.append(time.perf_counter() - t0)
-        letters = sum(kd[1] for kd in kd_prep)
-        prep = {'value': len(kd_prep) / min(pt), 'unit': 'reads/s', 'ms_per_step': min(pt) * 1e3, 'reads': len(kd_prep),
-                'letters': int(letters), 'what': 'tvr_prep: spans -> colour vectors, 3 density boundaries, denoise, string assembly '
-                                                 '(kmer_dat lists in, Python strings out)'}
-        if not args.no_cpu_baseline:
-            import oracle
-            t0 = time.perf_counter()
-            want = oracle.tvr_prep_py(flat_prep, meta_prep, 1000)
-            dt = time.perf_counter() - t0
-            assert got_prep['tvrtels_for_clustering'][:len(flat_prep)] == want['tvrtels_for_clustering'], 'tvr_prep differs from the oracle'
-            prep['cpu_port_reads_per_s'] = len(flat_prep) / dt
-            prep['cpu_port'] = f'oracle numpy/Python restatement, 1 core, {len(flat_prep)} reads ({dt:.2f} s)'
+        try:
+            from telogator2_b200 import tg_tvr
+            kd_prep, meta_prep, flat_prep = make_prep_workload(2048)
+            tg_tvr.tvr_prep(kd_prep[:64], meta_prep, 1000)
+            pt = []
+            for _ in range(3):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                got_prep = tg_tvr.tvr_prep(kd_prep, meta_prep, 1000)
+                pt.append(time.perf_counter() - t0)
+            letters = sum(kd[1] for kd in kd_prep)
+            prep = {'value': len(kd_prep) / min(pt), 'unit': 'reads/s', 'ms_per_step': min(pt) * 1e3, 'reads': len(kd_prep),
+                    'letters': int(letters), 'what': 'tvr_prep: spans -> colour vectors, 3 density boundaries, denoise, string assembly '
+                                                     '(kmer_dat lists in, Python strings out)'}
+            if not args.no_cpu_baseline:
+                import oracle
+                t0 = time.perf_counter()
+                want = oracle.tvr_prep_py(flat_prep, meta_prep, 1000)
+                dt = time.perf_counter() - t0
+                assert got_prep['tvrtels_for_clustering'][:len(flat_prep)] == want['tvrtels_for_clustering'], 'tvr_prep differs from the oracle'
+                prep['cpu_port_reads_per_s'] = len(flat_prep) / dt
+                prep['cpu_port'] = f'oracle numpy/Python restatement, 1 core, {len(flat_prep)} reads ({dt:.2f} s)'
 
+        except Exception as exc:                      # an auxiliary line must not cost the headline metric
+            prep = {'error': f'{type(exc).__name__}: {exc}'}
     # ---------------- stage [0a] prefilter: str.count of KMER_INITIAL / RC over every read ----------------
     prefilter = None
     if world == 1:
-        from telogator2_b200 import tg_prefilter
-        g = torch.Generator(device='cuda')
-        g.manual_seed(99)
-        n_wgs, wgs_len = 131072, 16384                                 # 2.1 Gbases of genome-like reads (uniform ACGT) ...
-        tail = tg_prefilter._lib.load().tg_prefilter_tail_bytes()
-        d_wgs = torch.empty(n_wgs * wgs_len + tail, dtype=torch.uint8, device='cuda')
-        acgt = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device='cuda')
-        for c0 in range(0, d_wgs.numel(), 1 << 26):
-            c1 = min(c0 + (1 << 26), d_wgs.numel())
-            d_wgs[c0:c1] = acgt[torch.randint(0, 4, (c1 - c0,), generator=g, device='cuda')]
-        # ... with telomeric scan reads spliced in (every 512th read: still ~5x the telomeric fraction of a real 30x genome)
-        TEL_EVERY = 512
-        tel = [r for r in scan_reads if len(r) <= wgs_len][:n_wgs // TEL_EVERY]
-        for k, r in enumerate(tel):
-            o = TEL_EVERY * k * wgs_len
-            d_wgs[o:o + len(r)] = torch.frombuffer(bytearray(r.encode('latin-1')), dtype=torch.uint8).cuda()
-        lens_wgs = np.full(n_wgs, wgs_len, dtype=np.int32)
-        for k, r in enumerate(tel):
-            lens_wgs[TEL_EVERY * k] = len(r)
-        ar = tg_prefilter.AsciiReads.from_device(d_wgs, np.arange(n_wgs + 1, dtype=np.int64) * wgs_len, lens_wgs)
-        KI, KIR = CANON[0] + CANON[0], CR[0] + CR[0]                   # telogator2.py:393-394
-        ca, cb = ar.count_pair_device(KI, KIR)
-        torch.cuda.synchronize()
-        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ps = []
-        for _ in range(5):
-            p0.record()
+        try:
+            from telogator2_b200 import tg_prefilter
+            g = torch.Generator(device='cuda')
+            g.manual_seed(99)
+            n_wgs, wgs_len = 131072, 16384                                 # 2.1 Gbases of genome-like reads (uniform ACGT) ...
+            tail = tg_prefilter._lib.load().tg_prefilter_tail_bytes()
+            d_wgs = torch.empty(n_wgs * wgs_len + tail, dtype=torch.uint8, device='cuda')
+            acgt = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device='cuda')
+            for c0 in range(0, d_wgs.numel(), 1 << 26):
+                c1 = min(c0 + (1 << 26), d_wgs.numel())
+                d_wgs[c0:c1] = acgt[torch.randint(0, 4, (c1 - c0,), generator=g, device='cuda')]
+            # ... with telomeric scan reads spliced in (every 512th read: still ~5x the telomeric fraction of a real 30x genome)
+            TEL_EVERY = 512
+            tel = [r for r in scan_reads if len(r) <= wgs_len][:n_wgs // TEL_EVERY]
+            for k, r in enumerate(tel):
+                o = TEL_EVERY * k * wgs_len
+                d_wgs[o:o + len(r)] = torch.frombuffer(bytearray(r.encode('latin-1')), dtype=torch.uint8).cuda()
+            lens_wgs = np.full(n_wgs, wgs_len, dtype=np.int32)
+            for k, r in enumerate(tel):
+                lens_wgs[TEL_EVERY * k] = len(r)
+            ar = tg_prefilter.AsciiReads.from_device(d_wgs, np.arange(n_wgs + 1, dtype=np.int64) * wgs_len, lens_wgs)
+            KI, KIR = CANON[0] + CANON[0], CR[0] + CR[0]                   # telogator2.py:393-394
             ca, cb = ar.count_pair_device(KI, KIR)
-            p1.record()
             torch.cuda.synchronize()
-            ps.append(p0.elapsed_time(p1) * 1e-3)
-        pf_bases = float(lens_wgs.astype(np.int64).sum())
-        pkp, srcp = peaks()
-        # spot check against str.count (the reference's own code) on the telomeric reads and some random ones
-        h_ca, h_cb = ca.cpu().numpy(), cb.cpu().numpy()
-        for k in list(range(0, min(len(tel), 24))):
-            assert h_ca[TEL_EVERY * k] == tel[k].count(KI) and h_cb[TEL_EVERY * k] == tel[k].count(KIR), 'prefilter count differs from str.count'
-        for i in (1, 2, 3, 1000, n_wgs - 1):
-            s_i = bytes(d_wgs[i * wgs_len:(i + 1) * wgs_len].cpu().numpy()).decode('latin-1')
-            assert h_ca[i] == s_i.count(KI) and h_cb[i] == s_i.count(KIR), 'prefilter count differs from str.count'
-        prefilter = {'kernel': 'prefilter_count_kernel', 'bound': 'hbm', 'achieved': pf_bases / min(ps) / 1e9, 'peak': pkp['hbm_gbs'],
-                     'unit': 'GB/s', 'frac': pf_bases / min(ps) / 1e9 / pkp['hbm_gbs'], 'peak_source': srcp, 'launch_ms': min(ps) * 1e3,
-                     'bytes_per_base': 1.0, 'mbases_per_s': pf_bases / min(ps) / 1e6, 'reads': n_wgs,
-                     'telomeric_reads': len(tel), 'reads_kept': int(((h_ca >= 5) | (h_cb >= 5)).sum()),
-                     'what': 'read.count(KMER_INITIAL), read.count(KMER_INITIAL_RC) for every read (telogator2.py:451-454), ASCII resident in HBM'}
-        del d_wgs, ar
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ps = []
+            for _ in range(5):
+                p0.record()
+                ca, cb = ar.count_pair_device(KI, KIR)
+                p1.record()
+                torch.cuda.synchronize()
+                ps.append(p0.elapsed_time(p1) * 1e-3)
+            pf_bases = float(lens_wgs.astype(np.int64).sum())
+            pkp, srcp = peaks()
+            # spot check against str.count (the reference's own code) on the telomeric reads and some random ones
+            h_ca, h_cb = ca.cpu().numpy(), cb.cpu().numpy()
+            for k in list(range(0, min(len(tel), 24))):
+                assert h_ca[TEL_EVERY * k] == tel[k].count(KI) and h_cb[TEL_EVERY * k] == tel[k].count(KIR), 'prefilter count differs from str.count'
+            for i in (1, 2, 3, 1000, n_wgs - 1):
+                s_i = bytes(d_wgs[i * wgs_len:(i + 1) * wgs_len].cpu().numpy()).decode('latin-1')
+                assert h_ca[i] == s_i.count(KI) and h_cb[i] == s_i.count(KIR), 'prefilter count differs from str.count'
+            prefilter = {'kernel': 'prefilter_count_kernel', 'bound': 'hbm', 'achieved': pf_bases / min(ps) / 1e9, 'peak': pkp['hbm_gbs'],
+                         'unit': 'GB/s', 'frac': pf_bases / min(ps) / 1e9 / pkp['hbm_gbs'], 'peak_source': srcp, 'launch_ms': min(ps) * 1e3,
+                         'bytes_per_base': 1.0, 'mbases_per_s': pf_bases / min(ps) / 1e6, 'reads': n_wgs,
+                         'telomeric_reads': len(tel), 'reads_kept': int(((h_ca >= 5) | (h_cb >= 5)).sum()),
+                         'what': 'read.count(KMER_INITIAL), read.count(KMER_INITIAL_RC) for every read (telogator2.py:451-454), ASCII resident in HBM'}
+            del d_wgs, ar
 
+        except Exception as exc:                      # an auxiliary line must not cost the headline metric
+            prefilter = {'error': f'{type(exc).__name__}: {exc}'}
     # ---------------- e2e through the public API: host strings -> float32 matrix on the host --------
     # (the body of tg_align.get_dist_matrix_parallel, with the engine kept to read its byte counters)
     e2e_ms = []
