@@ -459,3 +459,70 @@ def test_local_only_hides_the_process_group():
         assert multi_gpu._LOCAL_ONLY == 1
     assert multi_gpu._LOCAL_ONLY == 0
     del calls
+
+
+def test_shared_column_job_mapping_covers_every_pair_once():
+    """Python transcription of describe_pair + the JOBS_PHASE_A_SHCOL job selection of nw_wave_kernel: over arbitrary (even-start)
+    pair ranges every pair is aligned exactly once, rows/columns are the pair's two (length-adjusted) sequences in one of the
+    two orientations, and a shared job really shares its column sequence and length."""
+    rng = np.random.default_rng(31)
+
+    def unrank(q, n):
+        r = 0
+        while (r + 1) * (2 * n - (r + 1) - 1) // 2 <= q:
+            r += 1
+        return r, q - r * (2 * n - r - 1) // 2 + r + 1
+
+    for trial in range(30):
+        n = int(rng.integers(2, 14))
+        lens = rng.integers(1, 40, size=n) * (50 if trial % 3 else 1)
+        off = np.concatenate([[0], np.cumsum(lens)])
+        order = np.argsort(-lens, kind='stable')
+        adjust, minv = bool(trial % 2), bool((trial // 2) % 2)
+
+        def describe(q):
+            a, b = unrank(q, n)
+            oa, ob = int(order[a]), int(order[b])
+            i, j = min(oa, ob), max(oa, ob)
+            li, lj = int(lens[i]), int(lens[j])
+            if adjust:
+                ml = min(li, lj)
+                if minv:
+                    ml = max(ml, 1000)
+                li, lj = min(li, ml), min(lj, ml)
+            return dict(off_i=int(off[i]), off_j=int(off[j]), n=li, m=lj, ra=a, a_is_i=(oa == i), i=i, j=j)
+
+        def orient(d):
+            return ((d['off_j'], d['m'], d['off_i'], d['n']) if d['a_is_i'] else (d['off_i'], d['n'], d['off_j'], d['m']))
+        n_pairs = n * (n - 1) // 2
+        q0 = 2 * int(rng.integers(0, n_pairs // 2 + 1))
+        q1 = int(rng.integers(q0, n_pairs + 1))
+        done, pend, jid, n_jobs = {}, None, 0, (q1 - q0 + 1) // 2
+        while True:
+            if pend is not None:
+                (row, nr, col, m, out) = pend
+                pend = None
+                jobs = [(row, nr, col, m, out)]
+            else:
+                if jid >= n_jobs:
+                    break
+                qa = q0 + 2 * jid
+                jid += 1
+                da = describe(qa)
+                row0, n0, col0, m0 = orient(da)
+                jobs = [(row0, n0, col0, m0, qa - q0)]
+                if qa + 1 < q1:
+                    db = describe(qa + 1)
+                    rowb, nb, colb, mb = orient(db)
+                    if db['ra'] == da['ra'] and colb == col0 and mb == m0:
+                        jobs.append((rowb, nb, col0, m0, qa + 1 - q0))          # shared columns
+                    else:
+                        pend = (rowb, nb, colb, mb, qa + 1 - q0)
+            assert len({(c, m) for (_r, _n, c, m, _o) in jobs}) == 1
+            for (row, nr, col, m, out) in jobs:
+                assert out not in done
+                done[out] = (row, nr, col, m)
+        assert sorted(done) == list(range(q1 - q0))
+        for out, (row, nr, col, m) in done.items():
+            d = describe(q0 + out)
+            assert {(row, nr), (col, m)} == {(d['off_i'], d['n']), (d['off_j'], d['m'])}
