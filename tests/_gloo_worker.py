@@ -74,6 +74,17 @@ def main():
     assert Dm.dtype == np.dtype('<f4') and np.array_equal(Dm, _D), 'reduced matrix differs'
     mine = fast_ranges(n_pairs, rank, world, min_block=8)
     assert 0 < sum(e - b for b, e in mine) < n_pairs
+    # scan: contiguous read shares by base count, per-read results exchanged with all_gather_object (no sequences travel)
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from test_host_logic import _fake_tel_local
+    from telogator2_b200.multi_gpu import attach_tel_results, shard_reads_by_bases, strip_tel_results
+    rng = np.random.default_rng(8)
+    reads = [(f'read{i} x', ''.join(rng.choice(list('ACGT'), int(rng.integers(30, 400)))), None) for i in range(41)]
+    bnd = shard_reads_by_bases([len(r[1]) for r in reads], world)
+    mine_res, mine_meta = _fake_tel_local(reads[bnd[rank]:bnd[rank + 1]], bnd[rank])
+    parts = [None] * world
+    dist.all_gather_object(parts, strip_tel_results(mine_res, mine_meta))
+    assert attach_tel_results(parts, reads) == _fake_tel_local(reads, 0)[0], 'merged scan result differs'
     own = shard_pair_indices(n_pairs, rank, world, block=8)
     np.save(out_path + f'.rank{rank}.npy', own)
     dist.barrier()
