@@ -85,6 +85,11 @@ def main():
     parts = [None] * world
     dist.all_gather_object(parts, strip_tel_results(mine_res, mine_meta))
     assert attach_tel_results(parts, reads) == _fake_tel_local(reads, 0)[0], 'merged scan result differs'
+    # the product entry point itself, with the per-rank device work replaced by the stand-in
+    from telogator2_b200 import tg_tel
+    tg_tel._tel_repeat_comp_local = lambda rd, params, gtt=None, off=0, return_meta=False: (
+        _fake_tel_local(rd, off) if return_meta else _fake_tel_local(rd, off)[0])
+    assert tg_tel.get_tel_repeat_comp_parallel(reads, None) == _fake_tel_local(reads, 0)[0], 'sharded entry point differs'
     own = shard_pair_indices(n_pairs, rank, world, block=8)
     np.save(out_path + f'.rank{rank}.npy', own)
     dist.barrier()
