@@ -110,6 +110,17 @@ def sharded_pair_scores(engine, sequences, adjust_lens, min_viable, R, rng_seed,
     return gather_results(res, dist, device)
 
 
+def _to_host(D):
+    """Device tensor -> ndarray through a page-locked block (torch caches and reuses these): the copy runs at PCIe speed and
+    the returned ndarray owns the block until it is garbage collected.  CPU tensors (gloo tests) are returned as they are."""
+    if not D.is_cuda:
+        return D.numpy()
+    import torch
+    host = torch.empty(D.shape, dtype=D.dtype, pin_memory=True)
+    host.copy_(D)
+    return host.numpy()
+
+
 def reduce_matrix(D, dist):
     """Sum the ranks' partial matrices (disjoint non-zero entries) in place: the one exchange step of the matrix path."""
     dist.all_reduce(D, op=dist.ReduceOp.SUM)
@@ -136,15 +147,7 @@ def sharded_dist_matrix(engine, sequences, adjust_lens, min_viable, R, rng_seed,
     D = compute((rank, world) if world > 1 else None)
     if world > 1:
         D = reduce_matrix(D, dist)
-    if D.is_cuda:
-        # page-locked destination (torch caches and reuses these blocks): the copy runs at PCIe speed and the returned
-        # ndarray owns the block until it is garbage collected
-        import torch
-        host = torch.empty(D.shape, dtype=D.dtype, pin_memory=True)
-        host.copy_(D)
-        out = host.numpy()
-    else:
-        out = D.numpy()
+    out = _to_host(D)
     if engine is not None:
         engine.stats['d2h_bytes'] += out.nbytes
     return out
@@ -165,10 +168,7 @@ def sharded_dist_matrices(engine, seq_lists, adjust_lens, min_viable, R, rng_see
     D = engine.matrix_device(st, adjust_lens, min_viable, R, rng_seed, shard=(rank, world) if world > 1 else None)
     if world > 1:
         D = reduce_matrix(D, dist)
-    import torch
-    host = torch.empty(D.shape, dtype=D.dtype, pin_memory=True)
-    host.copy_(D)
-    flat = host.numpy()
+    flat = _to_host(D)
     engine.stats['d2h_bytes'] += flat.nbytes
     off = st['mat_out_off']
     return [flat[off[b]:off[b + 1]].reshape(len(g), len(g)) for b, g in enumerate(seq_lists)]

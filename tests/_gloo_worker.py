@@ -74,6 +74,33 @@ def main():
     assert Dm.dtype == np.dtype('<f4') and np.array_equal(Dm, _D), 'reduced matrix differs'
     mine = fast_ranges(n_pairs, rank, world, min_block=8)
     assert 0 < sum(e - b for b, e in mine) < n_pairs
+    # several matrices in one pair space (sharded_dist_matrices) with a stand-in engine that fills its ranges from the oracle
+    from telogator2_b200.multi_gpu import sharded_dist_matrices
+    groups = [seqs[:5], seqs[5:6], [], seqs[6:14]]
+    sizes = np.array([len(g) for g in groups], dtype=np.int64)
+    want_many = [oracle.dist_matrix_c(g, P, True, True, R, seed) if len(g) >= 2 else np.zeros((len(g), len(g)), '<f4') for g in groups]
+
+    class FakeEngine:
+        stats = {'d2h_bytes': 0}
+
+        def prepare(self, seq_lists, many=False):
+            assert many
+            return dict(mat_out_off=np.concatenate([[0], np.cumsum(sizes * sizes)]),
+                        mat_pair_off=np.concatenate([[0], np.cumsum(sizes * (sizes - 1) // 2)]))
+
+        def matrix_device(self, st, adjust_lens, min_viable, R_, seed_, shard=None):
+            flat = torch.zeros(int(st['mat_out_off'][-1]), dtype=torch.float32)
+            tot = int(st['mat_pair_off'][-1])
+            for (b, e) in (fast_ranges(tot, shard[0], shard[1], min_block=6) if shard else [(0, tot)]):
+                for q in range(b, e):
+                    m = int(np.searchsorted(st['mat_pair_off'], q, side='right') - 1)
+                    nloc = int(sizes[m])
+                    pl = [(a, c) for a in range(nloc) for c in range(a + 1, nloc)][q - int(st['mat_pair_off'][m])]
+                    for (x, y) in (pl, pl[::-1]):
+                        flat[int(st['mat_out_off'][m]) + x * nloc + y] = float(want_many[m][x, y])
+            return flat
+    got_many = sharded_dist_matrices(FakeEngine(), groups, True, True, R, seed)
+    assert len(got_many) == len(groups) and all(np.array_equal(a, b) for a, b in zip(got_many, want_many)), 'batched matrices differ'
     # scan: contiguous read shares by base count, per-read results exchanged with all_gather_object (no sequences travel)
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     from test_host_logic import _fake_tel_local
