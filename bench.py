@@ -197,6 +197,25 @@ def cpu_scan_sample(reads, tables, threads, budget_bases):
     return tot / dt / 1e6, dt, tot
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print banners there (e.g. 'NCCL version ...' on the first collective), so
+    everything written to file descriptor 1 from now on goes to stderr and emit() writes the line to the real stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + '\n').encode()
+    sys.stdout.flush()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, data)
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -225,7 +244,7 @@ def run_reference(args, rank, world):
             'scan': {'value': mb, 'unit': 'Mbases/s', 'sample': f'{sb} bases, oracle C scan (base count x2, density x2, hits on last 6000)',
                      'cores': threads},
             'gpu_launches': 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -243,6 +262,7 @@ def main():
     ap.add_argument('--cpu-scan-mbases', type=float, default=200.0, help='bases of the CPU scan sample, Mbases')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
+    claim_stdout()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -591,7 +611,7 @@ def main():
                 'prep': prep, 'prefilter': prefilter, 'd2': d2,
                 'multi_gpu_verified_pairs': verified,
                 'wall_s_timed_region': t_wall}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -526,3 +526,16 @@ def test_shared_column_job_mapping_covers_every_pair_once():
         for out, (row, nr, col, m) in done.items():
             d = describe(q0 + out)
             assert {(row, nr), (col, m)} == {(d['off_i'], d['n']), (d['off_j'], d['m'])}
+
+
+def test_bench_emits_exactly_one_json_line_on_stdout():
+    """bench.py's contract: ONE JSON line on stdout; banners of libraries (NCCL prints its version there) must not join it."""
+    import json
+    import subprocess
+    import sys
+    code = ("import sys, os; sys.path.insert(0, %r); import bench; bench.claim_stdout(); print('banner'); os.system('echo child'); "
+            "bench.emit({'a': 1})" % ROOT)
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, cwd=ROOT)
+    assert r.returncode == 0, r.stderr
+    assert json.loads(r.stdout) == {'a': 1} and r.stdout.count('\n') == 1
+    assert 'banner' in r.stderr and 'child' in r.stderr
