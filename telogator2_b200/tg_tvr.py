@@ -64,6 +64,19 @@ class _Dev:
             buf[:len(raw)] = self.torch.frombuffer(bytearray(raw), dtype=self.torch.uint8).to(self.dev)
         return buf, off[:-1].copy(), lens
 
+    def paint(self, start, end, rk_off, kmer_letters, off0):
+        """Colour vectors of all reads (tg_tvr.py:96-105): spans sorted by (read, k), rk_off their (read, k) index,
+        off0 the n + 1 vector offsets -> byte buffer."""
+        t = self.torch
+        n, K = len(off0) - 1, len(kmer_letters)
+        B0 = t.empty(max(int(off0[-1]), 1), dtype=t.uint8, device=self.dev)
+        if n:
+            _lib.check(self.L.tg_cv_paint(_lib.dptr(self.up(start.astype(np.int32))) if len(start) else None,
+                                          _lib.dptr(self.up(end.astype(np.int32))) if len(end) else None, _lib.dptr(self.up(rk_off)),
+                                          _lib.dptr(self.up(np.frombuffer(_codes(kmer_letters), dtype=np.uint8).copy())) if K else None, K,
+                                          _lib.dptr(self.up(off0)), n, ord(UNKNOWN), _lib.dptr(B0), self.stream()))
+        return B0
+
     def boundary(self, buf, off, lens, reverse, letters, win, thresh, above, start=0):
         """-> (first, extreme) int32 arrays, -1 = None (tg_tvr.py:449-479)."""
         n = len(lens)
@@ -219,13 +232,7 @@ class _Prep:
         np.cumsum(tlen, out=off0[1:])
         self.off0 = off0[:-1].copy()
         self.total0 = int(off0[-1])
-        t = d.torch
-        self.B0 = t.empty(max(self.total0, 1), dtype=t.uint8, device=d.dev)
-        if n:
-            _lib.check(d.L.tg_cv_paint(_lib.dptr(d.up(start.astype(np.int32))) if len(start) else None,
-                                       _lib.dptr(d.up(end.astype(np.int32))) if len(end) else None, _lib.dptr(d.up(rk_off)),
-                                       _lib.dptr(d.up(np.frombuffer(_codes(kmer_letters), dtype=np.uint8).copy())) if K else None, K,
-                                       _lib.dptr(d.up(off0)), n, ord(UNKNOWN), _lib.dptr(self.B0), d.stream()))
+        self.B0 = d.paint(start, end, rk_off, kmer_letters, off0)
         unk = [UNKNOWN] + list(subfilt_letters)
         L = tlen.astype(np.int64)
         # tg_tvr.py:118  (seq_left, seq_right) = find_density_boundary(cv, unknown, 100, 0.125, 'below')

@@ -539,3 +539,90 @@ def test_bench_emits_exactly_one_json_line_on_stdout():
     assert r.returncode == 0, r.stderr
     assert json.loads(r.stdout) == {'a': 1} and r.stdout.count('\n') == 1
     assert 'banner' in r.stderr and 'child' in r.stderr
+
+
+class _NumpyDev:
+    """Stand-in for tg_tvr._Dev: the same five device operations answered by the oracle on numpy buffers, so that the HOST
+    orchestration of tg_tvr (slicing arithmetic on (offset, length) pairs, the None-slice quirk, string assembly) runs on the CPU."""
+
+    def paint(self, start, end, rk_off, kmer_letters, off0):
+        n, K = len(off0) - 1, len(kmer_letters)
+        buf = np.zeros(max(int(off0[-1]), 1), dtype=np.uint8)
+        for r in range(n):
+            hits = [(k, int(start[s]), int(end[s])) for k in range(K) for s in range(int(rk_off[r * K + k]), int(rk_off[r * K + k + 1]))]
+            cv = oracle.colorvec_py(hits, int(off0[r + 1] - off0[r]), kmer_letters)
+            buf[off0[r]:off0[r + 1]] = np.frombuffer(cv.encode('latin-1'), dtype=np.uint8)
+        return buf
+
+    def upload_strings(self, seqs):
+        lens = np.array([len(s) for s in seqs], dtype=np.int32)
+        off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        return np.frombuffer(''.join(seqs).encode('latin-1') or b'\\0', dtype=np.uint8).copy(), off[:-1].copy(), lens
+
+    @staticmethod
+    def _s(buf, o, ln, rev):
+        s = buf[int(o):int(o) + int(ln)].tobytes().decode('latin-1')
+        return s[::-1] if rev else s
+
+    def boundary(self, buf, off, lens, reverse, letters, win, thresh, above, start=0):
+        first, ext = [], []
+        for i in range(len(lens)):
+            f, e = oracle.density_boundary_pos(self._s(buf, off[i], lens[i], reverse is not None and reverse[i]), letters, win, thresh,
+                                               'above' if above else 'below', start)
+            first.append(-1 if f is None else f)
+            ext.append(-1 if e is None else e)
+        return np.array(first, dtype=np.int32), np.array(ext, dtype=np.int32)
+
+    def lead_run(self, buf, off, lens, reverse, cap, letter):
+        out = []
+        for i in range(len(lens)):
+            s = self._s(buf, off[i], lens[i], reverse is not None and reverse[i])
+            out.append(min(len(s) - len(s.lstrip(letter)), int(cap[i])))
+        return np.array(out, dtype=np.int32)
+
+    def gather(self, src, src_off, dst_off, seg_len, total):
+        dst = np.zeros(max(int(total), 1), dtype=np.uint8)
+        for so, do, ln in zip(src_off, dst_off, seg_len):
+            dst[int(do):int(do) + int(ln)] = src[int(so):int(so) + int(ln)]
+        return dst
+
+    def denoise(self, buf, off, lens, replace_char, min_size, max_gap_fill, chars_to_delete, chars_to_merge):
+        outs = [oracle.denoise_colorvec_py(self._s(buf, off[i], lens[i], False), replace_char, min_size, max_gap_fill,
+                                           chars_to_delete, chars_to_merge) for i in range(len(lens))]
+        olen = np.array([len(o) for o in outs], dtype=np.int32)
+        ooff = np.concatenate([[0], np.cumsum(olen)]).astype(np.int64)
+        return np.frombuffer(''.join(outs).encode('latin-1') or b'\\0', dtype=np.uint8).copy(), ooff[:-1].copy(), olen
+
+    def download(self, buf, total):
+        return buf[:int(total)].tobytes()
+
+
+def test_tvr_prep_host_orchestration_on_cpu(monkeypatch):
+    """tg_tvr's host side (everything but the five device operations) against the reference-generated golden vectors."""
+    import gzip
+    import json
+    from telogator2_b200 import tg_tvr
+    monkeypatch.setattr(tg_tvr, '_Dev', _NumpyDev)
+    with gzip.open(os.path.join(ROOT, 'tests', 'golden', 'tvr_prep_golden.json.gz'), 'rt') as f:
+        G = json.load(f)
+    for key, S in G['sets'].items():
+        K = len(S['meta_letters'])
+        kd = []
+        for e in S['kmer_dat']:
+            hits = [[] for _ in range(K)]
+            for k, a, b in e['hits']:
+                hits[k].append([a, b])
+            kd.append([hits, e['tlen'], 0, 'FWD', e['name'], 60, ''])
+        meta = [[f'k{i}' for i in range(K)], [None] * K, S['meta_letters'], S['meta_flags']]
+        for trunc in (1000, 3000):
+            got = tg_tvr.tvr_prep(kd, meta, trunc)
+            for k, v in S[f'prep_trunc{trunc}'].items():
+                assert got[k] == v, (key, trunc, k)
+        assert tg_tvr.quick_get_tvrtel_lens(kd, meta) == S['quick_tvrtel_lens']
+    for c in G['fdb'][::7]:
+        assert tg_tvr.find_density_boundary(c['seq'], c['letters'], c['win'], c['thresh'], thresh_dir=c['dir'], starting_coord=c['start'],
+                                            use_lowest_dens=c['lowest']) == (c['left'], c['right'])
+    for c in G['denoise'][::11]:
+        assert tg_tvr.denoise_colorvec(c['v'], c['replace'], c['min_size'], c['max_gap_fill'], c['delete'], c['merge']) == c['out']
+    with pytest.raises(IndexError):
+        tg_tvr.tvr_prep([[[[[0, 5]]] + [[] for _ in range(K - 1)], 3, 0, 'FWD', 'x', 60, '']], meta, 1000)     # span beyond tlen
