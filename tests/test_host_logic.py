@@ -626,3 +626,67 @@ def test_tvr_prep_host_orchestration_on_cpu(monkeypatch):
         assert tg_tvr.denoise_colorvec(c['v'], c['replace'], c['min_size'], c['max_gap_fill'], c['delete'], c['merge']) == c['out']
     with pytest.raises(IndexError):
         tg_tvr.tvr_prep([[[[[0, 5]]] + [[] for _ in range(K - 1)], 3, 0, 'FWD', 'x', 60, '']], meta, 1000)     # span beyond tlen
+
+
+class _T:
+    """numpy array posing as a device tensor (.cpu().numpy())."""
+
+    def __init__(self, a):
+        self.a = a
+
+    def cpu(self):
+        return self
+
+    def numpy(self):
+        return self.a
+
+
+class _OraclePackedReads:
+    """Stand-in for tg_kmer.PackedReads: the device scans answered by the CPU oracle, so that tg_tel's HOST logic (phase 2,
+    slices, result assembly: tg_tel.py:238-389) runs on the CPU."""
+
+    def __init__(self, reads):
+        self.reads = list(reads)
+        self.n = len(reads)
+        self.lens = np.array([len(r) for r in reads], dtype=np.int32)
+        self.base_off = np.concatenate([[0], np.cumsum((self.lens.astype(np.int64) + 127) // 128 * 128)])
+
+    def basecount(self, la, lb):
+        return _T(np.array([[oracle.base_count(r, la), oracle.base_count(r, lb)] for r in self.reads], dtype=np.int32).reshape(-1, 2))
+
+    def orient(self, flip):
+        from conftest import rc_py
+        self.reads = [rc_py(r) if f else r for r, f in zip(self.reads, flip)]
+
+    def density_counts(self, la, lb, window):
+        outs = []
+        for lst in (la, lb):
+            flat = np.zeros(int(self.base_off[-1]) + 16, dtype=np.uint8)
+            for i, r in enumerate(self.reads):
+                c = oracle.density_counts(r, lst, window)
+                flat[self.base_off[i]:self.base_off[i] + len(c)] = c
+            outs.append(_T(flat))
+        return outs[0], outs[1]
+
+    def split_counts(self, flat, window):
+        return [flat[int(self.base_off[i]):int(self.base_off[i]) + max(int(self.lens[i]) - window, 0)] for i in range(self.n)]
+
+    def hits(self, slice_read, slice_lo, slice_hi, kmer_list, issub):
+        return [oracle.nonoverlapping_hits(self.reads[r][lo:hi], kmer_list, issub) for r, lo, hi in zip(slice_read, slice_lo, slice_hi)]
+
+
+def test_scan_batch_boundary_host_logic_on_cpu(monkeypatch, kmer_tables, golden_reads):
+    """tg_tel.get_tel_repeat_comp_parallel's host side against the output of the reference's own driver (tel_batch_golden)."""
+    from telogator2_b200 import tg_kmer, tg_tel
+    from test_gpu_tel_batch import _tel_inputs, digest_tel_result, make_gtt, reference_golden, tel_cases
+    monkeypatch.setattr(tg_kmer, 'PackedReads', _OraclePackedReads)
+
+    def dens(read, kmer_list, w):                          # the per-read function, served from the primed cache only
+        hit = tg_kmer._density_cache.get((read, tuple(kmer_list), w))
+        assert hit is not None, 'phase 2 asked for a density that phase 1 did not provide'
+        return hit
+    gold = reference_golden()
+    for tkey, filters in tel_cases():
+        reads, params = _tel_inputs(kmer_tables, golden_reads, tkey, filters)
+        got = tg_tel.get_tel_repeat_comp_parallel(reads, params, max_workers=3, get_terminating_tl=make_gtt(dens))
+        assert digest_tel_result(got) == gold[tkey], tkey
