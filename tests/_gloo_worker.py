@@ -74,6 +74,17 @@ def main():
     assert Dm.dtype == np.dtype('<f4') and np.array_equal(Dm, _D), 'reduced matrix differs'
     mine = fast_ranges(n_pairs, rank, world, min_block=8)
     assert 0 < sum(e - b for b, e in mine) < n_pairs
+    # the product path itself: DistEngine (host orchestration) + sharded_dist_matrix / sharded_dist_matrices over this gloo group,
+    # with only the two C entry points answered by the oracle (tests/test_dist_engine_host.py)
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from test_dist_engine_host import OracleLib, _engine
+    from telogator2_b200 import _lib as tglib, tg_align
+    tglib.stream_ptr = lambda t: None
+    aligner = tg_align.get_aligner_object(tg_align.get_scoring_matrix('C', 'tvr'), (True, True), 'tvr')
+    short = [c[:150] for c in seqs[:9]]
+    want_short = oracle.dist_matrix_c(short, P, True, True, R, seed)
+    got_short = sharded_dist_matrix(_engine(aligner, OracleLib()), short, True, True, R, seed)
+    assert got_short.dtype == np.dtype('<f4') and np.array_equal(got_short, want_short), 'sharded_dist_matrix differs from the oracle'
     # several matrices in one pair space (sharded_dist_matrices) with a stand-in engine that fills its ranges from the oracle
     from telogator2_b200.multi_gpu import sharded_dist_matrices
     groups = [seqs[:5], seqs[5:6], [], seqs[6:14]]
@@ -101,6 +112,10 @@ def main():
             return flat
     got_many = sharded_dist_matrices(FakeEngine(), groups, True, True, R, seed)
     assert len(got_many) == len(groups) and all(np.array_equal(a, b) for a, b in zip(got_many, want_many)), 'batched matrices differ'
+    small = [[c[:120] for c in g] for g in groups]
+    want_small = [oracle.dist_matrix_c(g, P, True, True, R, seed) if len(g) >= 2 else np.zeros((len(g), len(g)), '<f4') for g in small]
+    got_small = sharded_dist_matrices(_engine(aligner, OracleLib()), small, True, True, R, seed)
+    assert all(np.array_equal(a, b) for a, b in zip(got_small, want_small)), 'sharded_dist_matrices (real engine) differs'
     # scan: contiguous read shares by base count, per-read results exchanged with all_gather_object (no sequences travel)
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     from test_host_logic import _fake_tel_local
