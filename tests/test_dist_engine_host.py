@@ -146,9 +146,10 @@ class OracleLib:
         return 0
 
 
-def _engine(aligner, lib, **kw):
+def _engine_from_scoring(sc, lib, **kw):
+    """A DistEngine on CPU tensors whose C library is `lib` (DistEngine.__init__ insists on a CUDA device)."""
     eng = DistEngine.__new__(DistEngine)
-    eng.torch, eng.L, eng.sc = torch, lib, Scoring.from_aligner(aligner)
+    eng.torch, eng.L, eng.sc = torch, lib, sc
     eng.device = torch.device('cpu')
     eng.force_generic = False
     eng.pairs_per_batch = kw.get('pairs_per_batch', 1 << 21)
@@ -159,6 +160,10 @@ def _engine(aligner, lib, **kw):
                  'h2d_bytes': 0, 'd2h_bytes': 0}
     eng._scratch = eng._counter = None
     return eng
+
+
+def _engine(aligner, lib, **kw):
+    return _engine_from_scoring(Scoring.from_aligner(aligner), lib, **kw)
 
 
 @pytest.fixture()
@@ -219,3 +224,100 @@ def test_many_matrices_one_pair_space(host_only, colorvecs):
         off = st['mat_out_off']
         for b, g in enumerate(groups):
             assert np.array_equal(flat[off[b]:off[b + 1]].reshape(len(g), len(g)), want[b]), (untrusted, b)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# explicit-job path: tg_nw_scores_wave / _wave32 / _generic and tg_mt_shuffle answered by the oracle
+# ---------------------------------------------------------------------------------------------------------
+def _addr(p):
+    return p.value if isinstance(p, C.c_void_p) else p
+
+
+class OracleJobLib(OracleLib):
+    def __init__(self):
+        super().__init__()
+        self.calls = {'wave': 0, 'wave32': 0, 'generic': 0, 'shuffle': 0}
+
+    def _scores(self, kind, d_pool, d_jobs, n_jobs, sc_ref, d_scores):
+        self.calls[kind] += 1
+        sc = sc_ref._obj
+        A = sc.alphabet
+        S = np.array(sc.sub, dtype=np.float64).reshape(_lib.MAXA, _lib.MAXA)[:A, :A].copy()
+        jobs = _view(_addr(d_jobs), C.c_uint8, n_jobs * _lib.NW_JOB.itemsize).view(_lib.NW_JOB)
+        hi = int(max((jobs['row_off'] + jobs['n']).max(), (jobs['col_off'] + jobs['m']).max()))
+        pool = _view(_addr(d_pool), C.c_uint8, hi)
+        n_out = int(jobs['out'].max()) + 1
+        scores = _view(_addr(d_scores), C.c_int32, n_out)
+        L = oracle.lib()
+        for J in jobs:
+            for h in (0, 1):
+                if J['out'][h] < 0:
+                    continue
+                x = np.ascontiguousarray(pool[J['row_off'][h]:J['row_off'][h] + J['n'][h]])
+                y = np.ascontiguousarray(pool[J['col_off'][h]:J['col_off'][h] + J['m'][h]])
+                scores[J['out'][h]] = int(L.tgo_nw_score(x.ctypes.data, len(x), y.ctypes.data, len(y), S.ctypes.data, A, 0., 0.,
+                                                          float(sc.gap), float(sc.gap_left), float(sc.gap_right)))
+        return 0
+
+    def tg_nw_scores_wave(self, d_pool, d_jobs, n_jobs, max_n, sc_ref, d_scores, d_scratch, d_counter, stream):
+        return self._scores('wave', d_pool, d_jobs, n_jobs, sc_ref, d_scores)
+
+    def tg_nw_scores_wave32(self, d_pool, d_jobs, n_jobs, max_n, sc_ref, d_scores, d_scratch, d_counter, stream):
+        return self._scores('wave32', d_pool, d_jobs, n_jobs, sc_ref, d_scores)
+
+    def tg_nw_scores_generic(self, d_pool, d_jobs, n_jobs, max_m, sc_ref, d_scores, stream):
+        return self._scores('generic', d_pool, d_jobs, n_jobs, sc_ref, d_scores)
+
+    def tg_mt_shuffle(self, d_pool, d_jobs, n_jobs, R, max_len, stream):
+        self.calls['shuffle'] += 1
+        jobs = _view(_addr(d_jobs), C.c_uint8, n_jobs * _lib.SHUFFLE_JOB.itemsize).view(_lib.SHUFFLE_JOB)
+        hi = int((jobs['dst_off'] + R * (jobs['n'].astype(np.int64) + jobs['m'])).max())
+        pool = _view(_addr(d_pool), C.c_uint8, hi)
+        for J in jobs:
+            random.seed(int(J['seed']))
+            dst = int(J['dst_off'])
+            si = pool[J['src_i']:J['src_i'] + J['n']].tolist()
+            sj = pool[J['src_j']:J['src_j'] + J['m']].tolist()
+            for _ in range(R):
+                for s in (si, sj):
+                    pool[dst:dst + len(s)] = random.sample(s, len(s))
+                    dst += len(s)
+        return 0
+
+
+def test_explicit_job_path_routing_and_seeds(host_only, colorvecs):
+    """pair_scores(pair_idx=...): job packing, routing to the 16-bit / 32-bit / generic kernels, shuffle jobs with abs(seed + p),
+    results scattered back in combinations order."""
+    from telogator2_b200 import tg_align
+    rng = np.random.default_rng(6)
+    seqs = [''.join(rng.choice(list('CCCCDEFA'), n)) for n in (5100, 5060, 300, 200, 7)]
+    n_pairs = len(seqs) * (len(seqs) - 1) // 2
+    for gap_bool, seed, expect in (((True, False), -40, ('wave', 'wave32')), ((False, True), 12, ('generic',))):
+        aligner = tg_align.get_aligner_object(None, gap_bool, 'tvr')
+        P = oracle.AlignerParams(None, gap_bool)
+        lib = OracleJobLib()
+        eng = _engine(aligner, lib)
+        res = eng.pair_scores(seqs, False, False, 2, seed, pair_idx=np.arange(n_pairs, dtype=np.int64))
+        _, aln, rnd, _ = oracle.dist_matrix_c(seqs, P, False, False, 2, seed, want_scores=True)
+        assert np.array_equal(res['aln'], aln) and np.array_equal(res['rnd'], rnd), gap_bool
+        used = {k for k, v in lib.calls.items() if v and k != 'shuffle'}
+        assert used == set(expect), (gap_bool, lib.calls)
+        assert np.array_equal(eng.dist_matrix(seqs, False, False, 2, seed, res=res), oracle.dist_matrix_c(seqs, P, False, False, 2, seed))
+
+
+def test_single_pair_api_follows_host_random(host_only, colorvecs):
+    """tvr_distance / quick_compare_tvrs consume the process-wide `random` stream like the reference (tg_align.py:109-151, 379-381)."""
+    from telogator2_b200 import tg_align
+    host_only.setattr(tg_align, 'DistEngine', lambda sc: _engine_from_scoring(sc, OracleJobLib()))
+    cv = colorvecs['colorvecs']['human_ont']
+    a, b = cv[0][:400], cv[1][:350]
+    aligner = tg_align.get_aligner_object(tg_align.get_scoring_matrix('C', 'tvr'), (True, True), 'tvr')
+    P = oracle.AlignerParams(oracle.scoring_matrix('C', 'tvr'), (True, True))
+    assert tg_align.tvr_distance(a, b, aligner, True, False, 3, rng_seed=5) == oracle.tvr_distance_py(a, b, P, True, False, 3, rng_seed=5)
+    random.seed(99)
+    got = [tg_align.quick_compare_tvrs(a, b), tg_align.quick_compare_tvrs(b, a)]
+    P2 = oracle.AlignerParams(None, (True, False))
+    random.seed(99)
+    want = [oracle.tvr_distance_py(a, b, P2, False, False, 3, rng_seed=None) / 10.0, oracle.tvr_distance_py(b, a, P2, False, False, 3, rng_seed=None) / 10.0]
+    assert got == want
+    assert aligner.score(a, b) == oracle.nw_score(a, b, P)
