@@ -197,13 +197,18 @@ size_t tg_kmer_table_bytes(void);
 int tg_kmer_table_build(const char *kmers_concat, const int32_t *kmer_off, int K,
                         const int32_t *issub_edges, const int32_t *issub_off, /* KMER_ISSUBSTRING CSR or NULL */
                         void *h_table);
-/* One automaton for TWO k-mer lists (KMER_LIST + KMER_LIST_REV, tg_tel.py:160-161; CANONICAL_STRINGS +
- * CANONICAL_STRINGS_REV, tg_tel.py:262-263): the coverage kernels then need one table lookup per base for both. */
+/* Coverage table for TWO k-mer lists (KMER_LIST + KMER_LIST_REV, tg_tel.py:160-161; CANONICAL_STRINGS +
+ * CANONICAL_STRINGS_REV, tg_tel.py:262-263): a lookup table over the 4^7 windows of 7 bases whose 32-bit entries answer, for
+ * both lists, "which positions does the longest plain k-mer starting here cover" and "might a special k-mer (longer than 7
+ * bases or self-overlapping) start here"; plus the packed patterns for the exact slow paths.  tg_kmer_table_pair_bytes()
+ * bytes, built on the host, uploaded as is.  Replaces the per-k-mer re.finditer passes of tg_kmer.py:69,96. */
+size_t tg_kmer_table_pair_bytes(void);
 int tg_kmer_table_build_pair(const char *kmers_a, const int32_t *off_a, int KA,
                              const char *kmers_b, const int32_t *off_b, int KB, void *h_table);
 
 /* Read layout: read r occupies bases [base_off[r], base_off[r] + len[r]) of a padded base
- * space; base_off[r] is a multiple of 128.  ASCII input uses one byte per padded base
+ * space; base_off[r] is a multiple of 128 and base_off[r + 1] - base_off[r] > len[r] (at least one
+ * padding base, which carries the N bit, separates two reads).  ASCII input uses one byte per padded base
  * (pad bytes arbitrary).  Packed form: d_pack2[w] holds bases 16w..16w+15, 2 bits each
  * (A=0 C=1 T=2 G=3, little end first); d_nmask[w] holds 32 bases, bit set = not ACGT.
  * d_base_off has n_reads + 1 entries (the last one = total padded bases).
@@ -211,16 +216,12 @@ int tg_kmer_table_build_pair(const char *kmers_a, const int32_t *off_a, int KA,
 int tg_scan_pack(const uint8_t *d_ascii, const int64_t *d_base_off, const int32_t *d_len, int n_reads,
                  uint32_t *d_pack2, uint32_t *d_nmask, void *stream);
 
-/* The coverage kernels work on independent tiles of tg_scan_tile_bases() output positions.
- * d_tile_off[n_reads + 1] is the exclusive prefix sum of the tiles per read:
- *   base count: ceil(len / tile_bases) tiles,  density: ceil(max(len - window, 0) / tile_bases) tiles. */
-int tg_scan_tile_bases(void);
-
 /* get_telomere_base_count(read, kmer_list) (tg_kmer.py:93-102) for two k-mer lists at once
- * (CANONICAL_STRINGS and CANONICAL_STRINGS_REV, tg_tel.py:262-263): d_counts[2r + s] (zeroed here). */
-int tg_scan_basecount(const uint32_t *d_pack2, const uint32_t *d_nmask, const int64_t *d_base_off,
-                      const int32_t *d_len, int n_reads, const int64_t *d_tile_off, int64_t n_tiles,
-                      const void *d_table_pair, int32_t *d_counts, void *stream);
+ * (CANONICAL_STRINGS and CANONICAL_STRINGS_REV, tg_tel.py:262-263): d_counts[2r + s] (zeroed here).
+ * total_bases = base_off[n_reads]; d_blk_read[b] = read index of the 128-base block b of the padded base space.
+ * d_pack2 / d_nmask need 4 readable words of slack behind total_bases. */
+int tg_scan_basecount(const uint32_t *d_pack2, const uint32_t *d_nmask, int64_t total_bases,
+                      const int32_t *d_blk_read, int n_reads, const void *d_table_pair, int32_t *d_counts, void *stream);
 
 /* RC(read) (tg_util.py:433-434) applied in place of tg_tel.py:265-266: reads with
  * d_flip[r] != 0 are reverse-complemented into d_pack2_out / d_nmask_out, others copied. */
@@ -231,9 +232,9 @@ int tg_scan_orient(const uint32_t *d_pack2, const uint32_t *d_nmask, const int64
 /* get_telomere_kmer_density(read, kmer_list, tel_window) (tg_kmer.py:66-90) for two k-mer
  * lists at once (KMER_LIST and KMER_LIST_REV, tg_tel.py:160-161).  Emits the integer window
  * counts cnt[i] = #covered positions in (i, i + window], i in [0, len - window), as uint8 at
- * d_cnt_x[base_off[r] + i]; density = cnt / window in float64 on the host.  window <= 255. */
-int tg_scan_density(const uint32_t *d_pack2, const uint32_t *d_nmask, const int64_t *d_base_off,
-                    const int32_t *d_len, int n_reads, const int64_t *d_tile_off, int64_t n_tiles,
+ * d_cnt_x[base_off[r] + i] (arrays of total_bases bytes; entries outside [0, len - window) of a read are
+ * unspecified); density = cnt / window in float64 on the host.  window <= 255. */
+int tg_scan_density(const uint32_t *d_pack2, const uint32_t *d_nmask, int64_t total_bases,
                     const void *d_table_pair, int window, uint8_t *d_cnt_a, uint8_t *d_cnt_b, void *stream);
 
 /* get_nonoverlapping_kmer_hits(seq[lo:hi], KMER_LIST, KMER_ISSUBSTRING) (tg_kmer.py:173-230)

@@ -183,361 +183,6 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
     return d;
 }
 
-// ---- coverage kernel (base count / density) -------------------------------------------------------
-// Tiles are independent: a CTA handles a REGION of 8192 read positions [t0 - HL, t0 + TILE_OUT + HR) and emits the
-// TILE_OUT outputs of [t0, t0 + TILE_OUT).  The halos cover everything an output can depend on: matches start at most
-// max_len - 1 <= 31 positions before a covered position, a density window looks window <= 255 positions ahead.
-// The only long-range dependency -- re.finditer's greedy rule for a self-overlapping k-mer whose chain of overlapping
-// candidates crosses the region start -- is resolved exactly by walking the chain back through global memory.
-constexpr int COV_THREADS = 128;
-constexpr int COV_CH = 64;                          // positions per thread
-constexpr int COV_REGION = COV_THREADS * COV_CH;    // 8192
-constexpr int COV_HL = 64;
-constexpr int COV_OUT_THREADS = 121;
-constexpr int COV_TILE_OUT = COV_OUT_THREADS * COV_CH;   // 7744
-constexpr int COV_STAGE = COV_REGION + 32;          // staged bases (region + automaton warm-up)
-enum { MODE_COUNT = 0, MODE_DENSITY = 1 };
-
-// shared-memory index maps that make "lane t touches element 64 t + j" conflict free
-__device__ __forceinline__ int pidx(int w) { return w + (w >> 5); }            // 2-bit words (4 per chunk)
-__device__ __forceinline__ int midx(int w) { return w + (w >> 5); }            // mask words (2 per chunk)
-__device__ __forceinline__ int lidx(int x) { return x + ((x >> 6) << 2); }     // L bytes (64 per chunk)
-
-struct CovParams {
-    const uint32_t *pack2, *nmask;
-    const int64_t *base_off;
-    const int32_t *len;
-    int n_reads;
-    const int64_t *tile_off;       // [n_reads + 1] exclusive prefix sum of tiles per read
-    long long n_tiles;
-    const KmerTable *tab;
-    int window;
-    uint8_t *cnt[2];
-    int32_t *counts;
-};
-
-// does bordered k-mer (pat, blen) start at absolute read position p?  (direct test on the packed planes)
-__device__ bool kmer_at(const uint32_t *__restrict__ pack2, const uint32_t *__restrict__ nmask, int64_t rbase, int L, int64_t p,
-                        uint64_t pat, int blen)
-{
-    if (p < 0 || p + blen > L) return false;
-    const int64_t g = rbase + p;
-    // N-mask bits [g, g + blen): only words that hold positions of this read are touched
-    const int64_t mw = g >> 5;
-    const int msh = (int)(g & 31);
-    uint64_t mbits = (uint64_t)nmask[mw];
-    if (msh + blen > 32) mbits |= (uint64_t)nmask[mw + 1] << 32;
-    mbits >>= msh;
-    if (mbits & ((1ull << blen) - 1ull)) return false;           // blen <= 32
-    const int64_t pw = g >> 4;
-    const int sh = (int)(g & 15) * 2;
-    uint64_t lo = (uint64_t)pack2[pw];
-    if (sh + 2 * blen > 32) lo |= (uint64_t)pack2[pw + 1] << 32;
-    uint64_t bits = lo >> sh;
-    if (sh + 2 * blen > 64) bits |= (uint64_t)pack2[pw + 2] << (64 - sh);
-    const uint64_t m = (blen >= 32) ? ~0ull : ((1ull << (2 * blen)) - 1ull);
-    return ((bits ^ pat) & m) == 0;
-}
-
-// Exact greedy state in front of candidate c0 (absolute): walk the chain of overlapping candidates back to its
-// head (a candidate with no other candidate within blen - 1 positions before it, or the first of the read), then
-// replay re.finditer forward.  Returns the position before which the k-mer is blocked.
-__device__ int chain_state_before(const uint32_t *pack2, const uint32_t *nmask, int64_t rbase, int L, int c0,
-                                  uint64_t pat, int blen)
-{
-    int head = c0, p = c0 - 1;
-    while (p >= 0 && head - p < blen) {
-        if (kmer_at(pack2, nmask, rbase, L, p, pat, blen)) head = p;
-        p--;
-    }
-    if (head == c0) return 0;
-    int blocked = head + blen;
-    for (int q = head + 1; q < c0; q++)
-        if (q >= blocked && kmer_at(pack2, nmask, rbase, L, q, pat, blen)) blocked = q + blen;
-    return blocked;
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(COV_THREADS, 5) scan_cov_kernel(const CovParams P)
-{
-    extern __shared__ __align__(16) uint8_t smem[];
-    uint8_t *sp = smem;
-    const SmemTable T = load_table(P.tab, sp, false);
-    uint32_t *s_pack = reinterpret_cast<uint32_t *>(carve(sp, (size_t)pidx(COV_STAGE / 16 + 1) * 4 + 16));
-    uint32_t *s_mask = reinterpret_cast<uint32_t *>(carve(sp, (size_t)midx(COV_STAGE / 32 + 1) * 4 + 16));
-    uint8_t *s_L[2];
-    uint32_t *s_cov[2];
-    for (int s = 0; s < 2; s++) {
-        s_L[s] = carve(sp, lidx(COV_REGION));
-        s_cov[s] = reinterpret_cast<uint32_t *>(carve(sp, (COV_REGION / 32 + 1) * 4));
-    }
-    uint32_t *s_bm = reinterpret_cast<uint32_t *>(carve(sp, (size_t)max(T.n_bord, 1) * (COV_REGION / 32) * 4));
-    __shared__ int s_any[SC_MAXBORD];
-    __shared__ int s_wmax[2][COV_THREADS / 32];
-    __shared__ int s_red[2][COV_THREADS / 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nb = T.n_bord;
-    const int w = P.window;
-
-    for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-        // tile -> (read, tile index in read)
-        int lo = 0, hi = P.n_reads;
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (P.tile_off[mid] <= tile) lo = mid; else hi = mid;
-        }
-        const int r = lo;
-        const int t0 = (int)(tile - P.tile_off[r]) * COV_TILE_OUT;
-        const int a0 = t0 - COV_HL;                                   // read position of region index 0
-        const int64_t rbase = P.base_off[r];
-        const int L = P.len[r];
-        const int64_t padded = P.base_off[r + 1] - rbase;
-        __syncthreads();
-        // ---- stage the packed planes of [a0, a0 + STAGE) ----
-        for (int wq = tid; wq < COV_STAGE / 32; wq += COV_THREADS) {
-            const int p0 = a0 + wq * 32;
-            uint32_t m = 0xffffffffu, a = 0u, b = 0u;
-            if (p0 >= 0 && p0 < padded) {
-                const int64_t g = (rbase + p0) >> 5;
-                m = P.nmask[g];
-                a = P.pack2[g * 2];
-                b = P.pack2[g * 2 + 1];
-            }
-            s_mask[midx(wq)] = m;
-            s_pack[pidx(wq * 2)] = a;
-            s_pack[pidx(wq * 2 + 1)] = b;
-        }
-        for (int i = tid; i < nb * (COV_REGION / 32); i += COV_THREADS) s_bm[i] = 0u;
-        if (tid < SC_MAXBORD) s_any[tid] = 0;
-        __syncthreads();
-
-        // ---- phase B: one automaton for both lists, right to left: 32 warm-up positions, then the 64 of this chunk.
-        //      The transition entry carries the two lists' match lengths in its upper bytes; PRMT packs four
-        //      positions' worth of them into the L words (byte = longest k-mer starting at that position). ----
-        {
-            const int c0 = tid * COV_CH;
-            uint32_t state = 0;
-#pragma unroll 1
-            for (int wd = 5; wd >= 4; wd--) {                         // warm-up, no output
-                const uint32_t pw = s_pack[pidx((c0 >> 4) + wd)];
-                const uint32_t mw = s_mask[midx((c0 >> 5) + (wd >> 1))] >> ((wd & 1) * 16);
-#pragma unroll
-                for (int k = 15; k >= 0; k--) {
-                    const uint32_t e = T.trans[state * 4 + ((pw >> (2 * k)) & 3u)];
-                    state = ((mw >> k) & 1u) ? 0u : (e & 0xfffu);
-                }
-            }
-#pragma unroll 1
-            for (int wd = 3; wd >= 0; wd--) {                         // 4 words of 16 positions
-                const uint32_t pw = s_pack[pidx((c0 >> 4) + wd)];
-                const uint32_t mw = s_mask[midx((c0 >> 5) + (wd >> 1))] >> ((wd & 1) * 16);
-#pragma unroll
-                for (int q = 3; q >= 0; q--) {
-                    uint32_t ev[4];
-#pragma unroll
-                    for (int t = 3; t >= 0; t--) {
-                        const int k = 4 * q + t;
-                        uint32_t e = T.trans[state * 4 + ((pw >> (2 * k)) & 3u)];
-                        if ((mw >> k) & 1u) e = 0u;
-                        state = e & 0xfffu;
-                        ev[t] = e;
-                        if (e & SC_BORD_FLAG) {
-                            uint32_t ob = T.out_bord[state];
-                            const int xr = c0 + wd * 16 + k;
-                            while (ob) {
-                                const int b = __ffs(ob) - 1;
-                                ob &= ob - 1;
-                                atomicOr(&s_bm[b * (COV_REGION / 32) + (xr >> 5)], 1u << (xr & 31));
-                                s_any[b] = 1;
-                            }
-                        }
-                    }
-                    const uint32_t t01 = prmt(ev[0], ev[1], 0x7362u), t23 = prmt(ev[2], ev[3], 0x7362u);
-                    const int xb = c0 + wd * 16 + 4 * q;
-                    *reinterpret_cast<uint32_t *>(s_L[0] + lidx(xb)) = prmt(t01, t23, 0x5410u);
-                    *reinterpret_cast<uint32_t *>(s_L[1] + lidx(xb)) = prmt(t01, t23, 0x7632u);
-                }
-            }
-        }
-        __syncthreads();
-
-        // ---- phase C: greedy resolution of self-overlapping k-mers: one warp per k-mer, the warp finds the
-        //      non-empty bitmap words together and walks their bits in order (all lanes redundantly) ----
-        for (int b = warp; b < nb; b += COV_THREADS / 32) {
-            if (!s_any[b]) continue;
-            const int blen = P.tab->bord_len[b];
-            const int grp = P.tab->bord_group[b];
-            const uint32_t *bm = s_bm + b * (COV_REGION / 32);
-            int blocked = -0x40000000;
-            bool first = true;
-            for (int ch = 0; ch < COV_REGION / 32; ch += 32) {
-                const uint32_t mine = bm[ch + lane];
-                uint32_t nz = __ballot_sync(TG_FULL_MASK, mine != 0u);
-                while (nz) {
-                    const int l = __ffs(nz) - 1;
-                    nz &= nz - 1;
-                    uint32_t word = __shfl_sync(TG_FULL_MASK, mine, l);
-                    while (word) {
-                        const int bit = __ffs(word) - 1;
-                        word &= word - 1;
-                        const int xr = (ch + l) * 32 + bit;
-                        const int p = a0 + xr;
-                        if (first) {
-                            first = false;
-                            // a chain of overlapping candidates may reach back beyond the region start
-                            if (xr < blen - 1 && a0 > 0)
-                                blocked = chain_state_before(P.pack2, P.nmask, rbase, L, p, P.tab->bord_pat[b], blen);
-                        }
-                        if (p >= blocked) {
-                            blocked = p + blen;
-                            if (lane == 0) smem_byte_max(s_L[grp], lidx(xr), (uint32_t)blen);
-                        }
-                    }
-                }
-            }
-        }
-        __syncthreads();
-
-        // ---- phase D: coverage bits = prefix max of (x + L[x]) over the region, both lists at once in u16x2:
-        //      e = max(e, x + L[x]); covered(x) = e > x  (a position without a match contributes x, which never covers) ----
-        {
-            const int c0 = tid * COV_CH;
-            uint32_t cw[2][2] = {{0u, 0u}, {0u, 0u}};
-            int lm[2];
-            {
-                uint32_t e2 = 0u, acc = 0u;
-                uint32_t pp = (uint32_t)c0 * 0x00010001u;
-#pragma unroll
-                for (int q = 0; q < COV_CH / 4; q++) {
-                    const uint32_t l0 = *reinterpret_cast<const uint32_t *>(s_L[0] + lidx(c0 + q * 4));
-                    const uint32_t l1 = *reinterpret_cast<const uint32_t *>(s_L[1] + lidx(c0 + q * 4));
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        // byte k of l0 -> low half, byte k of l1 -> high half (upper bytes = replicated sign bit = 0)
-                        const uint32_t sel = k | ((k | 8) << 4) | ((4 + k) << 8) | (((4 + k) | 8) << 12);
-                        const uint32_t pair = prmt(l0, l1, sel);
-                        e2 = __vmaxu2(e2, pair + pp);
-                        acc = acc * 2u + __vminu2(e2 - pp, 0x00010001u);      // 1 per half where e > x
-                        pp += 0x00010001u;
-                    }
-                    if ((q & 3) == 3) {
-                        // 16 positions accumulated MSB first
-                        const uint32_t b0 = __brev(acc << 16), b1 = __brev(acc & 0xffff0000u);
-                        const int j = q >> 2;                                    // 16-bit group 0..3
-                        cw[0][j >> 1] |= b0 << ((j & 1) * 16);
-                        cw[1][j >> 1] |= b1 << ((j & 1) * 16);
-                        acc = 0u;
-                    }
-                }
-                lm[0] = (int)(e2 & 0xffffu);
-                lm[1] = (int)(e2 >> 16);
-            }
-            int inc[2] = {lm[0], lm[1]};
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v0 = __shfl_up_sync(TG_FULL_MASK, inc[0], o);
-                const int v1 = __shfl_up_sync(TG_FULL_MASK, inc[1], o);
-                if (lane >= o) { inc[0] = max(inc[0], v0); inc[1] = max(inc[1], v1); }
-            }
-            if (lane == 31) { s_wmax[0][warp] = inc[0]; s_wmax[1][warp] = inc[1]; }
-            int ex[2];
-            ex[0] = __shfl_up_sync(TG_FULL_MASK, inc[0], 1);
-            ex[1] = __shfl_up_sync(TG_FULL_MASK, inc[1], 1);
-            if (lane == 0) { ex[0] = 0; ex[1] = 0; }
-            __syncthreads();
-            int cnt_here[2] = {0, 0};
-#pragma unroll
-            for (int s = 0; s < 2; s++) {
-                int e = ex[s];
-                for (int wq = 0; wq < warp; wq++) e = max(e, s_wmax[s][wq]);
-                // coverage reaching in from earlier chunks: positions c0 .. e - 1
-                const int reach = min(max(e - c0, 0), COV_CH);
-                const uint64_t in = (reach >= 64) ? ~0ull : ((1ull << reach) - 1ull);
-                cw[s][0] |= (uint32_t)in;
-                cw[s][1] |= (uint32_t)(in >> 32);
-                s_cov[s][c0 / 32] = cw[s][0];
-                s_cov[s][c0 / 32 + 1] = cw[s][1];
-                if (MODE == MODE_COUNT && tid >= COV_HL / COV_CH && tid < COV_HL / COV_CH + COV_OUT_THREADS)
-                    cnt_here[s] = __popc(cw[s][0]) + __popc(cw[s][1]);
-            }
-            if (tid == 0) { s_cov[0][COV_REGION / 32] = 0u; s_cov[1][COV_REGION / 32] = 0u; }
-            if (MODE == MODE_COUNT) {
-#pragma unroll
-                for (int s = 0; s < 2; s++) {
-                    int v = cnt_here[s];
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(TG_FULL_MASK, v, o);
-                    if (lane == 0) s_red[s][warp] = v;
-                }
-                __syncthreads();
-                if (tid < 2) {
-                    int v = 0;
-                    for (int wq = 0; wq < COV_THREADS / 32; wq++) v += s_red[tid][wq];
-                    if (v) atomicAdd(&P.counts[2 * r + tid], v);
-                }
-            }
-        }
-
-        // ---- phase E: window counts of the TILE_OUT outputs ----
-        if (MODE == MODE_DENSITY) {
-            __syncthreads();
-            if (tid < COV_OUT_THREADS) {
-                const int j0 = COV_HL + tid * COV_CH;                // region index of this thread's first output
-                const int i0 = t0 + tid * COV_CH;                    // its read position
-                if (i0 < padded) {
-#pragma unroll
-                    for (int s = 0; s < 2; s++) {
-                        const uint32_t *cv = s_cov[s];
-                        int cnt = 0;                                 // popcount of bits [j0 + 1, j0 + w]
-                        {
-                            const int lo2 = j0 + 1, hi2 = j0 + w;
-                            for (int wd = lo2 >> 5; wd <= (hi2 >> 5); wd++) {
-                                uint32_t v = cv[wd];
-                                if (wd == (lo2 >> 5)) v &= 0xffffffffu << (lo2 & 31);
-                                if (wd == (hi2 >> 5)) v &= 0xffffffffu >> (31 - (hi2 & 31));
-                                cnt += __popc(v);
-                            }
-                        }
-                        // leaving bits j0+1 .. j0+64 and entering bits j0+w+1 .. j0+w+64 as two 64-bit streams
-                        const int ja = j0 + 1, jb = j0 + w + 1;
-                        uint64_t sa = ((uint64_t)cv[ja >> 5] | ((uint64_t)cv[(ja >> 5) + 1] << 32)) >> (ja & 31);
-                        if (ja & 31) sa |= (uint64_t)cv[(ja >> 5) + 2] << (64 - (ja & 31));
-                        uint64_t sb = ((uint64_t)cv[jb >> 5] | ((uint64_t)cv[(jb >> 5) + 1] << 32)) >> (jb & 31);
-                        if (jb & 31) sb |= (uint64_t)cv[min((jb >> 5) + 2, COV_REGION / 32)] << (64 - (jb & 31));
-                        uint32_t outw[COV_CH / 4];
-                        if (w >= 4) {
-                            // four outputs per step, one byte each: cnt(i + t) = cnt(i) + sum_{u < t} (in_u - out_u).
-                            // nibble -> 4 bytes of 0/1 (multiply spreads the bits), * 0x01010101 = inclusive byte prefix sums;
-                            // subtracting first never borrows (the leaving bits are inside the current window)
-#pragma unroll
-                            for (int gq = 0; gq < COV_CH / 4; gq++) {
-                                const uint32_t nin = (uint32_t)(sb >> (4 * gq)) & 0xfu, nout = (uint32_t)(sa >> (4 * gq)) & 0xfu;
-                                const uint32_t A = ((nin * 0x00204081u) & 0x01010101u) * 0x01010101u;
-                                const uint32_t B = ((nout * 0x00204081u) & 0x01010101u) * 0x01010101u;
-                                outw[gq] = (uint32_t)cnt * 0x01010101u - (B << 8) + (A << 8);
-                                cnt += (int)(A >> 24) - (int)(B >> 24);
-                            }
-                        } else {
-#pragma unroll
-                            for (int q = 0; q < COV_CH / 4; q++) outw[q] = 0u;
-#pragma unroll
-                            for (int ii = 0; ii < COV_CH; ii++) {
-                                outw[ii >> 2] |= (uint32_t)cnt << ((ii & 3) * 8);
-                                cnt += (int)((sb >> ii) & 1ull) - (int)((sa >> ii) & 1ull);
-                            }
-                        }
-                        uint8_t *dst = P.cnt[s] + rbase + i0;
-#pragma unroll
-                        for (int q = 0; q < COV_CH / 16; q++)
-                            if (i0 + q * 16 < padded)
-                                *reinterpret_cast<uint4 *>(dst + q * 16) = make_uint4(outw[q * 4], outw[q * 4 + 1], outw[q * 4 + 2], outw[q * 4 + 3]);
-                    }
-                }
-            }
-        }
-    }
-}
-
 // ---- non-overlapping hits -------------------------------------------------------------------------
 constexpr int HIT_THREADS = 128;
 constexpr int HIT_CH = 16;
@@ -949,18 +594,6 @@ TG_EXPORT int tg_kmer_table_build(const char *kmers_concat, const int32_t *kmer_
     return build_table(km, K, issub_edges, issub_off, reinterpret_cast<KmerTable *>(h_table));
 }
 
-TG_EXPORT int tg_kmer_table_build_pair(const char *kmers_a, const int32_t *off_a, int KA,
-                                       const char *kmers_b, const int32_t *off_b, int KB, void *h_table)
-{
-    if (!h_table) return tg_set_err(TG_EINVAL, "NULL argument");
-    std::vector<std::string> km;
-    int rc = collect_kmers(kmers_a, off_a, KA, km);
-    if (rc != TG_OK) return rc;
-    rc = collect_kmers(kmers_b, off_b, KB, km);
-    if (rc != TG_OK) return rc;
-    return build_table(km, KA, nullptr, nullptr, reinterpret_cast<KmerTable *>(h_table));
-}
-
 // ================================================================================================
 // launches
 // ================================================================================================
@@ -1029,63 +662,6 @@ static int get_counter(unsigned int **out, cudaStream_t st)
     TG_CUDA_CHECK(cudaMemsetAsync(g_counter, 0, 16, st));
     *out = g_counter;
     return TG_OK;
-}
-
-TG_EXPORT int tg_scan_tile_bases(void) { return COV_TILE_OUT; }
-
-template <int MODE>
-static int launch_cov(const uint32_t *d_pack2, const uint32_t *d_nmask, const int64_t *d_base_off, const int32_t *d_len,
-                      int n_reads, const int64_t *d_tile_off, int64_t n_tiles, const void *table, int window,
-                      uint8_t *ca, uint8_t *cb, int32_t *counts, void *stream)
-{
-    if (n_reads <= 0 || n_tiles <= 0) return TG_OK;
-    if (!d_pack2 || !d_nmask || !d_base_off || !d_len || !d_tile_off || !table) return tg_set_err(TG_EINVAL, "NULL device pointer");
-    const int sms = tg_sm_count();
-    if (sms <= 0) return tg_set_err(TG_ECUDA, "no CUDA device");
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    int ns, nb;
-    int rc = table_dims(table, &ns, &nb, st);
-    if (rc != TG_OK) return rc;
-    auto up = [](size_t b) { return (b + 15) & ~(size_t)15; };
-    size_t smem = table_smem(ns, false) + up((size_t)(COV_STAGE / 16 + 1 + (COV_STAGE / 16 + 1) / 32) * 4 + 16) +
-                  up((size_t)(COV_STAGE / 32 + 1 + (COV_STAGE / 32 + 1) / 32) * 4 + 16) +
-                  2 * (up(COV_REGION + COV_REGION / 16) + up((COV_REGION / 32 + 1) * 4)) +
-                  up((size_t)(nb > 1 ? nb : 1) * (COV_REGION / 32) * 4);
-    if (smem > 200 * 1024) return tg_set_err(TG_ERANGE, "k-mer tables too large for shared memory (%zu bytes)", smem);
-    CovParams P;
-    P.pack2 = d_pack2; P.nmask = d_nmask; P.base_off = d_base_off; P.len = d_len; P.n_reads = n_reads;
-    P.tile_off = d_tile_off; P.n_tiles = n_tiles;
-    P.tab = reinterpret_cast<const KmerTable *>(table);
-    P.window = window; P.cnt[0] = ca; P.cnt[1] = cb; P.counts = counts;
-    TG_CUDA_CHECK(cudaFuncSetAttribute(scan_cov_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = (int)((220 * 1024) / (smem + 2048));
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 8) per_sm = 8;
-    long long grid = (long long)sms * per_sm;
-    if (grid > n_tiles) grid = n_tiles;
-    scan_cov_kernel<MODE><<<(int)grid, COV_THREADS, smem, st>>>(P);
-    TG_CUDA_CHECK(cudaGetLastError());
-    return TG_OK;
-}
-
-TG_EXPORT int tg_scan_basecount(const uint32_t *d_pack2, const uint32_t *d_nmask, const int64_t *d_base_off,
-                                const int32_t *d_len, int n_reads, const int64_t *d_tile_off, int64_t n_tiles,
-                                const void *d_table_pair, int32_t *d_counts, void *stream)
-{
-    if (!d_counts) return tg_set_err(TG_EINVAL, "d_counts is NULL");
-    if (n_reads > 0) TG_CUDA_CHECK(cudaMemsetAsync(d_counts, 0, sizeof(int32_t) * 2 * (size_t)n_reads, reinterpret_cast<cudaStream_t>(stream)));
-    return launch_cov<MODE_COUNT>(d_pack2, d_nmask, d_base_off, d_len, n_reads, d_tile_off, n_tiles, d_table_pair, 0, nullptr, nullptr,
-                                  d_counts, stream);
-}
-
-TG_EXPORT int tg_scan_density(const uint32_t *d_pack2, const uint32_t *d_nmask, const int64_t *d_base_off,
-                              const int32_t *d_len, int n_reads, const int64_t *d_tile_off, int64_t n_tiles,
-                              const void *d_table_pair, int window, uint8_t *d_cnt_a, uint8_t *d_cnt_b, void *stream)
-{
-    if (window < 1 || window > 255) return tg_set_err(TG_ERANGE, "window %d outside 1..255 (uint8 counts)", window);
-    if (!d_cnt_a || !d_cnt_b) return tg_set_err(TG_EINVAL, "output pointer is NULL");
-    return launch_cov<MODE_DENSITY>(d_pack2, d_nmask, d_base_off, d_len, n_reads, d_tile_off, n_tiles, d_table_pair, window,
-                                    d_cnt_a, d_cnt_b, nullptr, stream);
 }
 
 TG_EXPORT size_t tg_scan_hits_work_bytes(int64_t total_work_bases, int n_slices)

@@ -95,7 +95,7 @@ def kmer_table(kmer_list, issub=None):
 
 
 def kmer_table_pair(list_a, list_b):
-    """Device blob of ONE automaton for two k-mer lists (coverage kernels: one lookup per base for both)."""
+    """Device blob of the 7-base window table for two k-mer lists (coverage kernels: one lookup per base for both)."""
     torch = _lib.require_cuda()
     L = _lib.load()
     key = ('pair', tuple(list_a), tuple(list_b), torch.cuda.current_device())
@@ -110,7 +110,7 @@ def kmer_table_pair(list_a, list_b):
         off = np.zeros(len(lst) + 1, dtype=np.int32)
         off[1:] = np.cumsum([len(k) for k in lst])
         offs.append(off)
-    host = np.zeros(L.tg_kmer_table_bytes(), dtype=np.uint8)
+    host = np.zeros(L.tg_kmer_table_pair_bytes(), dtype=np.uint8)
     _lib.check(L.tg_kmer_table_build_pair(blobs[0], offs[0].ctypes.data_as(C.c_void_p), len(list_a),
                                           blobs[1], offs[1].ctypes.data_as(C.c_void_p), len(list_b),
                                           host.ctypes.data_as(C.c_void_p)))
@@ -136,18 +136,19 @@ class PackedReads:
         self.torch, self.L = torch, L
         self.n = len(reads)
         self.lens = np.array([len(r) for r in reads], dtype=np.int32)
-        padded = (self.lens.astype(np.int64) + ALIGN - 1) // ALIGN * ALIGN
+        padded = (self.lens.astype(np.int64) + ALIGN) // ALIGN * ALIGN          # at least one padding base per read
         self.base_off = np.zeros(self.n + 1, dtype=np.int64)
         self.base_off[1:] = np.cumsum(padded)
         total = int(self.base_off[-1])
         self.total = total
         ascii_h = torch.empty(max(total, 16), dtype=torch.uint8, pin_memory=True)
         buf = ascii_h.numpy()
-        buf[:] = ord('N')
-        for i, r in enumerate(reads):
-            if self.lens[i]:
-                o = int(self.base_off[i])
-                buf[o:o + self.lens[i]] = np.frombuffer(r.encode('latin-1', 'replace'), dtype=np.uint8)
+        pad = b'N' * ALIGN
+        joined = b''.join(x for i, r in enumerate(reads)
+                          for x in (r.encode('latin-1', 'replace'), pad[:int(padded[i]) - len(r)]))
+        if len(joined) != total:
+            raise ValueError('reads must be str of single-byte characters')
+        buf[:total] = np.frombuffer(joined, dtype=np.uint8)
         self._ascii_host = buf
         self._bad_reads = None
         self.h2d_bytes = total + self.base_off.nbytes + self.lens.nbytes
@@ -156,7 +157,7 @@ class PackedReads:
         self.d_len = torch.from_numpy(self.lens).cuda()
         self.d_pack2 = torch.zeros(total // 16 + 8, dtype=torch.int32, device='cuda')
         self.d_nmask = torch.zeros(total // 32 + 8, dtype=torch.int32, device='cuda')
-        self._tile_cache = {}
+        self._blk_read = None
         if self.n and total:
             _lib.check(L.tg_scan_pack(_lib.dptr(self.d_ascii), _lib.dptr(self.d_base_off), _lib.dptr(self.d_len), self.n,
                                       _lib.dptr(self.d_pack2), _lib.dptr(self.d_nmask), _lib.stream_ptr(torch)))
@@ -173,26 +174,21 @@ class PackedReads:
             seg = self._ascii_host[o:o + self.lens[i]]
             raise KeyError(chr(int(seg[np.argmax(~_ACGTN[seg])])))
 
-    def _tiles(self, window):
-        """device prefix sum of coverage tiles per read (window = 0: base count, else density outputs)."""
-        t = self._tile_cache.get(window)
-        if t is None:
-            tb = self.L.tg_scan_tile_bases()
-            items = np.maximum(self.lens.astype(np.int64) - window, 0)
-            off = np.zeros(self.n + 1, dtype=np.int64)
-            off[1:] = np.cumsum((items + tb - 1) // tb)
-            t = (self.torch.from_numpy(off).cuda(), int(off[-1]))
-            self._tile_cache[window] = t
-        return t
+    def blk_read(self):
+        """device int32: read index of every 128-base block of the padded base space."""
+        if self._blk_read is None:
+            torch = self.torch
+            reps = torch.from_numpy(np.diff(self.base_off) // ALIGN).cuda()
+            self._blk_read = torch.repeat_interleave(torch.arange(self.n, dtype=torch.int32, device='cuda'), reps)
+        return self._blk_read
 
     def basecount(self, list_a, list_b):
         """int32 [n, 2]: get_telomere_base_count for two k-mer lists (tg_kmer.py:93-102)."""
         torch = self.torch
         out = torch.zeros((max(self.n, 1), 2), dtype=torch.int32, device='cuda')
-        d_toff, n_tiles = self._tiles(0)
-        if self.n and n_tiles:
-            _lib.check(self.L.tg_scan_basecount(_lib.dptr(self.d_pack2), _lib.dptr(self.d_nmask), _lib.dptr(self.d_base_off),
-                                                _lib.dptr(self.d_len), self.n, _lib.dptr(d_toff), n_tiles,
+        if self.n and self.total:
+            _lib.check(self.L.tg_scan_basecount(_lib.dptr(self.d_pack2), _lib.dptr(self.d_nmask), self.total,
+                                                _lib.dptr(self.blk_read()), self.n,
                                                 _lib.dptr(kmer_table_pair(list_a, list_b)), _lib.dptr(out), _lib.stream_ptr(torch)))
         return out[:self.n]
 
@@ -215,10 +211,8 @@ class PackedReads:
         torch = self.torch
         ca = torch.empty(max(self.total, 16), dtype=torch.uint8, device='cuda')     # only [0, len - window) of each read is defined
         cb = torch.empty(max(self.total, 16), dtype=torch.uint8, device='cuda')
-        d_toff, n_tiles = self._tiles(int(window))
-        if self.n and self.total and n_tiles:
-            _lib.check(self.L.tg_scan_density(_lib.dptr(self.d_pack2), _lib.dptr(self.d_nmask), _lib.dptr(self.d_base_off),
-                                              _lib.dptr(self.d_len), self.n, _lib.dptr(d_toff), n_tiles,
+        if self.n and self.total:
+            _lib.check(self.L.tg_scan_density(_lib.dptr(self.d_pack2), _lib.dptr(self.d_nmask), self.total,
                                               _lib.dptr(kmer_table_pair(list_a, list_b)), int(window), _lib.dptr(ca), _lib.dptr(cb),
                                               _lib.stream_ptr(torch)))
         return ca, cb

@@ -83,9 +83,12 @@ def test_random_and_adversarial_vs_oracle(tgk, kmer_tables):
     T = kmer_tables['human_ont']
     KL, ISSUB = T['KMER_LIST'], T['KMER_ISSUBSTRING']
     reads = []
-    for n in (1, 2, 99, 100, 101, 127, 128, 129, 8191, 8192, 8193, 8292, 16500, 40000):
+    for n in (1, 2, 99, 100, 101, 127, 128, 129, 256, 8191, 8192, 8193, 8292, 16500, 32576, 32577, 40000, 65153):
         reads.append(''.join(rng.choice(list('ACGT'), n, p=[.25, .45, .1, .2])))
     reads.append('C' * 20000)                                    # longest possible greedy chain across tiles
+    reads.append('C' * 70001)
+    reads.append('CCCTAA' * 5400 + 'CCCCC' + 'CCCCTAACCCTAACCCCTAA' * 30 + 'CCCTCC' * 7 + 'CCCTAA' * 6000)   # 32 k tile borders inside repeats
+    reads.append('ACGTTGCA' * 4060 + 'C' * 200 + 'ACGTTGCA' * 4000)         # a chain of candidates across the 32576 border
     reads.append(('CCCTCC' * 3 + 'CCCTAA' * 2) * 1500)
     reads.append('CCCTAA' * 1365 + 'CCCCCC' * 10 + 'CCCTAA' * 1400)   # tile boundary inside repeats
     reads.append(''.join(rng.choice(list('ACGTN'), 9000, p=[.2, .5, .1, .15, .05])))
@@ -108,7 +111,7 @@ def test_random_and_adversarial_vs_oracle(tgk, kmer_tables):
     for q, r in enumerate(short):
         assert np.array_equal(hits_to_array(got[q]), hits_to_array(oracle.nonoverlapping_hits(r, KL, ISSUB))), q
     # unaligned slices of one read
-    r = reads[15]
+    r = reads[22]
     sl = [(3, 4100), (2047, 2049), (100, 100), (5, 37), (4090, 8200)]
     pr = tgk.PackedReads([r])
     got = pr.hits([0] * len(sl), [a for a, _ in sl], [b for _, b in sl], KL, ISSUB)
