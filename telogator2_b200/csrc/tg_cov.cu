@@ -3,38 +3,55 @@
 //
 // One thread owns 64 consecutive bases: one 128-bit load of the 2-bit plane, one 64-bit load of the N plane, then one
 // shared-memory table lookup per base.  The 32-bit table entry, indexed by the next 7 bases, holds for each of the two
-// lists the coverage mask (1 << L) - 1 of the longest plain k-mer starting here (bits 0-6 / 16-22) and a "special k-mer
-// might start here" flag (bit 7 / 23); the masks of 8 neighbouring bases are OR-ed into a 16-bit field per list with one
-// shift and one LOP3 per base, so the union coverage (cov[p] = some selected match covers p) falls out as bit planes
-// without any per-match loop.  Flagged bases (self-overlapping or long k-mers) and bases with an N within reach are rare;
-// they go through per-chunk bitmaps to an exact slow path (direct comparison against the packed planes; greedy
-// leftmost-non-overlapping selection per self-overlapping k-mer, one warp per k-mer).
-// MODE_DENSITY then turns the coverage plane into the uint8 window counts cnt[i] = |cov (i, i + w]| with a sliding
-// difference of the entering and leaving coverage bits, four outputs per step through a 16-entry prefix-sum table.
+// lists the coverage mask (1 << L) - 1 of the longest plain k-mer starting here and a few flag bits for the k-mers a
+// 7-base window cannot decide (see below).  The entry is shifted by the base's position within its group of 8 and OR-ed
+// into three accumulators (coverage masks, flags) with one LOP3 each, so the union coverage cov[p] = "some selected match
+// covers p" and the flag planes fall out as bit planes without any per-match loop.
+//
+// k-mers a window cannot decide ("special"):
+//   * self-overlapping k-mers that fit the window (CCCCCC, CCCTCC): the entry flags their exact occurrences (S1).
+//     re.finditer's leftmost-non-overlapping rule only matters where two occurrences of one k-mer are closer than its
+//     length; elsewhere "all occurrences" is right and their coverage is the S1 plane smeared over the k-mer length.
+//     Close occurrences inside one thread's chunk are resolved by that thread, across chunks by the warp (rare).
+//   * k-mers longer than the window: the entry flags "its first 7 bases start here" (S2) and "bases 8.. of some long k-mer
+//     start here" (T); S2(p) & T(p + 7) leaves few candidates, which are compared against the staged planes.
+//   * special k-mers whose every base is covered by plain k-mers occurring inside them (the HOR k-mers) never change the
+//     union coverage and are dropped.
+//   * windows cut short by an N (read ends, mostly) use small tables indexed by the d < 7 bases in front of the N.
+// One warp = one group: it works on its own tiles (2048 bases with halos) and only ever synchronises with itself.
+// MODE_DENSITY turns the coverage plane into the uint8 window counts cnt[i] = |cov (i, i + w]| with a sliding difference
+// of the entering and leaving coverage bits, eight outputs per step through a 256-entry prefix-popcount table.
 #include "tg_scan_common.cuh"
 #include <string.h>
 
 namespace {
 
+constexpr int32_t COV_MAGIC = 0x43563037;             // "CV07"
+constexpr int COV_SHORT_N = 5464;                     // sum of 4^d, d = 1 .. 6, rounded up to a multiple of 4
+__host__ __device__ constexpr int COV_SHORT_OFF(int d) { return ((1 << (2 * d)) - 4) / 3; }
+
+// table entry bits (list A; list B = + 16 for the mask and S1)
+constexpr uint32_t E_S1A = 1u << 7, E_T = 1u << 8, E_S2A = 1u << 15, E_S1B = 1u << 23, E_S2B = 1u << 24;
+
 struct CovTable {
-    int32_t magic, n_all, KA, n_sp, n_bord, max_len, pad_[2];
+    int32_t magic, n_all, KA, n_bord, max_len, pad_;
+    int32_t bord_len[2];               // per list: L > 0: its window-sized self-overlapping k-mers all have length L (smear);
+                                       // 0: it has none; -1: several lengths (per-position handling)
     uint64_t pat[SC_MAXK];
     int32_t len[SC_MAXK];
-    int32_t kind[SC_MAXK];             // SC_PLAIN / SC_SPECIAL / SC_BORDERED; k-mers of list A come first
-    int32_t sp_idx[SC_MAXK];           // the n_sp special k-mers that are NOT self-overlapping
-    int32_t bord_idx[SC_MAXBORD];      // the n_bord self-overlapping k-mers
+    int32_t kind[SC_MAXK];             // SC_PLAIN / SC_SPECIAL / SC_BORDERED / SC_REDUNDANT; k-mers of list A come first
+    int32_t bord_idx[SC_MAXBORD];      // the n_bord self-overlapping k-mers that are not redundant
+    // windows cut short by an N: tab_short[COV_SHORT_OFF(d) + window of d bases], d = 1 .. 6 bases in front of the N, same
+    // entry format (only k-mers of length <= d can match there)
+    uint32_t tab_short[COV_SHORT_N];
     uint32_t tab[SC_TAB];
 };
-constexpr int32_t COV_MAGIC = 0x43563033;      // "CV03"
-constexpr int COV_SLOT_MANY = 127;
 
-constexpr int COV_THREADS = 512;                      // threads per CTA: they share one copy of the lookup table
-constexpr int COV_GT = 128;                           // threads per group: a group works on its own tiles, own barrier
-constexpr int COV_GROUPS = COV_THREADS / COV_GT;
+constexpr int COV_THREADS = 448;                      // threads per CTA: they share one copy of the lookup table (2 CTAs / SM)
+constexpr int COV_GROUPS = COV_THREADS / 32;          // one warp = one group
 constexpr int COV_CH = 64;                            // bases per thread
-constexpr int COV_REGION = COV_GT * COV_CH;           // 8192 bases per tile (64 left halo, window right halo)
+constexpr int COV_REGION = 32 * COV_CH;               // 2048 bases per tile (64 left halo, window right halo)
 constexpr int COV_WORDS = COV_REGION / 32;
-constexpr int COV_GW = COV_GT / 32;                   // warps per group
 enum { MODE_COUNT = 0, MODE_DENSITY = 1 };
 
 struct CovParams {
@@ -48,34 +65,26 @@ struct CovParams {
     int32_t *counts;
 };
 
-struct CovGroupSmem {
+struct alignas(16) CovGroupSmem {
     uint32_t cov[2][COV_WORDS + 4];
-    uint32_t spill[2][COV_GT + 4];
+    uint32_t spill[2][32 + 4];
     uint32_t pk[COV_REGION / 16 + 8];          // the staged planes (slow paths read them back)
     uint32_t nm[COV_WORDS + 4];
-    uint32_t flag[2][COV_WORDS + 2];           // per list: a special k-mer may start here (or an N is within the window)
-    uint32_t defer[2][COV_GW];                 // per list: chunks holding candidates that need the greedy walk
+    uint32_t s1[2][COV_WORDS + 4];             // per list: exact occurrences of window-sized self-overlapping k-mers
+    uint32_t s2[2][COV_WORDS + 4];             // per list: the first 7 bases of a long k-mer start here
+    uint32_t tr[COV_WORDS + 4];                // bases 8.. of a long k-mer (either list) start here
+    uint32_t defer[2], pad_[2];                // per list: chunks that need the warp-wide greedy walk, one bit per chunk
 };
 
-struct CovSmem {
+struct alignas(16) CovSmem {
     uint32_t tab[SC_TAB];
     uint64_t pat[SC_MAXK];
     uint8_t len[SC_MAXK], kind[SC_MAXK];
-    uint32_t lut[16];
+    uint8_t bsk[2][SC_MAXLIST], lgk[2][SC_MAXLIST];   // per list: window-sized self-overlapping k-mers / long k-mers
+    int32_t n_bsk[2], n_lgk[2];
+    uint2 lut8[256];                           // inclusive prefix popcounts of the 8 bits of a byte, one byte each
     CovGroupSmem g[COV_GROUPS];
 };
-
-__device__ __forceinline__ void group_sync(int grp)
-{
-    asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(COV_GT) : "memory");
-}
-__device__ __forceinline__ bool group_sync_or(int grp, bool pred)
-{
-    int r;
-    asm volatile("{ .reg .pred p, q; setp.ne.s32 p, %3, 0; bar.red.or.pred q, %1, %2, p; selp.s32 %0, 1, 0, q; }"
-                 : "=r"(r) : "r"(grp + 1), "r"(COV_GT), "r"((int)pred) : "memory");
-    return r != 0;
-}
 
 __device__ __noinline__ void cov_or(uint32_t *cv, int x, int len)
 {
@@ -105,29 +114,80 @@ __device__ __forceinline__ uint32_t tab_at(const uint32_t *s_tab, uint32_t lo, u
     return *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(s_tab) + t4);
 }
 
-// does k-mer (pat, len) start at region position x?  (staged planes; N anywhere in the span = no)
-__device__ __noinline__ bool sm_kmer_at(const uint32_t *pk, const uint32_t *nm, int x, uint64_t pat, int len)
+// the 32 bases that start at region position x, from the staged plane
+__device__ __forceinline__ uint64_t sm_bases64(const uint32_t *pk, int x)
 {
     const int pw = x >> 4, sh = (x & 15) * 2;
     uint64_t bases = ((uint64_t)pk[pw] | ((uint64_t)pk[pw + 1] << 32)) >> sh;
     if (sh) bases |= (uint64_t)pk[pw + 2] << (64 - sh);
+    return bases;
+}
+
+// does k-mer (pat, len) start at region position x?  (staged planes; N anywhere in the span = no)
+__device__ __noinline__ bool sm_kmer_at(const uint32_t *pk, const uint32_t *nm, int x, uint64_t pat, int len)
+{
     const uint32_t nbits = __funnelshift_r(nm[x >> 5], nm[(x >> 5) + 1], x & 31);
     const uint32_t lm = (len >= 32) ? 0xffffffffu : ((1u << len) - 1u);
     const uint64_t m = (len >= 32) ? ~0ull : ((1ull << (2 * len)) - 1ull);
-    return (nbits & lm) == 0u && ((bases ^ pat) & m) == 0ull;
+    return (nbits & lm) == 0u && ((sm_bases64(pk, x) ^ pat) & m) == 0ull;
 }
 
-// flag bits of the positions (x - d, x + d) except x itself, one list
-__device__ __forceinline__ bool flags_near(const uint32_t *fw, int x, int d)
+// any flag bit of the positions (x - d, x + d) except x itself?  (fw: a flag plane with 2 readable words behind it)
+__device__ __noinline__ bool flags_near(const uint32_t *fw, int x, int d)
 {
-    // bits [x - d + 1, x + d - 1] as a 64-bit window starting at x - 31 (d <= 32)
-    const int s = x - 31;                        // may be negative: words before the region do not exist
-    const int w0 = s >> 5, sh = s & 31;          // arithmetic shift: floor
+    const int s = x - 31;                        // 64-bit window starting at x - 31: position x is bit 31
+    const int w0 = s >> 5, sh = s & 31;          // (arithmetic shift: floor)
     const uint32_t a = (w0 >= 0) ? fw[w0] : 0u, b = fw[w0 + 1], c = fw[w0 + 2];
     const uint64_t lo = ((uint64_t)a | ((uint64_t)b << 32)) >> sh;
-    const uint64_t win = sh ? (lo | ((uint64_t)c << (64 - sh))) : lo;         // bit j <-> position s + j, position x is bit 31
+    const uint64_t win = sh ? (lo | ((uint64_t)c << (64 - sh))) : lo;
     const uint64_t m = (((1ull << (2 * d - 1)) - 1ull) << (32 - d)) & ~(1ull << 31);
     return (win & m) != 0ull;
+}
+
+// Flags X of my chunk = exact occurrences of self-overlapping k-mers of length L (prev / next: the flag words of the
+// neighbouring chunks).  Returns 0: no two flags closer than L -- the coverage of my occurrences (every flag smeared over
+// L positions) was OR-ed into cv[0..2];  1: close flags, all inside my chunk (the caller runs the greedy rule over them);
+// 2: close flags across a chunk border (the chunk goes to the warp-wide greedy walk).
+template <int LS>                             // LS = L known at compile time, or 0: use the argument
+__device__ __forceinline__ int smear_flags(uint64_t X, uint32_t prev, uint32_t next, uint32_t *cv, int l_arg)
+{
+    const int L = LS ? LS : l_arg;
+    const uint32_t pv = prev >> (32 - (L - 1)), nx = next & ((1u << (L - 1)) - 1u);
+    uint64_t near_own = 0ull;
+#pragma unroll
+    for (int k = 1; k < L; k++) near_own |= X & (X >> k);
+    if (pv | nx) {
+        // V = [L-1 flags of the previous chunk][my 64][L-1 flags of the next chunk], 64 + 2 (L - 1) <= 76 bits
+        const uint64_t vlo = (X << (L - 1)) | pv;
+        const uint32_t vhi = (uint32_t)(X >> (64 - (L - 1))) | (nx << (L - 1));
+        uint64_t nl = 0ull;
+        uint32_t nh = 0u;
+#pragma unroll
+        for (int k = 1; k < L; k++) {
+            nl |= vlo & ((vlo >> k) | ((uint64_t)vhi << (64 - k)));
+            nh |= vhi & (vhi >> k);
+        }
+        // pairs among my own flags show up here too; a pair that involves a neighbour's flag forces the warp-wide walk
+        // (the largest of my flags close to a flag of the next chunk is never the lower end of a pair of my own)
+        const uint64_t own_lo = near_own << (L - 1);
+        const uint32_t own_hi = (uint32_t)(near_own >> (64 - (L - 1)));
+        if ((nl & ~own_lo) | (uint64_t)(nh & ~own_hi)) return 2;
+    }
+    if (near_own) return 1;
+    uint64_t B = X;
+    uint32_t over = 0u;
+#pragma unroll
+    for (int k = 1; k < L; k++) { B |= X << k; over |= (uint32_t)(X >> (64 - k)); }
+    if ((uint32_t)B) atomicOr(&cv[0], (uint32_t)B);
+    if (B >> 32) atomicOr(&cv[1], (uint32_t)(B >> 32));
+    if (over) atomicOr(&cv[2], over);
+    return 0;
+}
+
+// four bytes (bits sh .. sh+7 of x0..x3) -> one word
+__device__ __forceinline__ uint32_t gather4(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, int sh)
+{
+    return ((x0 >> sh) & 0xffu) | (((x1 >> sh) & 0xffu) << 8) | (((x2 >> sh) & 0xffu) << 16) | ((x3 >> sh) << 24);
 }
 
 template <int MODE>
@@ -135,7 +195,7 @@ __global__ void __launch_bounds__(COV_THREADS, 2) scan_cov_kernel(const CovParam
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     CovSmem &S = *reinterpret_cast<CovSmem *>(smem_raw);
-    const int grp = threadIdx.x / COV_GT, tid = threadIdx.x % COV_GT, lane = tid & 31, warp = tid >> 5;
+    const int grp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     CovGroupSmem &G = S.g[grp];
     const CovTable *__restrict__ T = P.tab;
     {
@@ -146,25 +206,38 @@ __global__ void __launch_bounds__(COV_THREADS, 2) scan_cov_kernel(const CovParam
             const int k = threadIdx.x;
             S.pat[k] = T->pat[k]; S.len[k] = (uint8_t)T->len[k]; S.kind[k] = (uint8_t)T->kind[k];
         }
-        if (threadIdx.x < 16) {                          // inclusive prefix popcounts of a nibble, one byte each
-            uint32_t v = 0;
-            for (int j = 0; j < 4; j++) v |= (uint32_t)__popc(threadIdx.x & ((2 << j) - 1)) << (8 * j);
-            S.lut[threadIdx.x] = v;
+        if (threadIdx.x < 2) {
+            int nb = 0, nl = 0;
+            for (int k = threadIdx.x ? T->KA : 0; k < (threadIdx.x ? T->n_all : T->KA); k++) {
+                if (T->kind[k] != SC_SPECIAL && T->kind[k] != SC_BORDERED) continue;
+                if (T->len[k] > SC_W) S.lgk[threadIdx.x][nl++] = (uint8_t)k;
+                else S.bsk[threadIdx.x][nb++] = (uint8_t)k;
+            }
+            S.n_bsk[threadIdx.x] = nb; S.n_lgk[threadIdx.x] = nl;
+        }
+        if (threadIdx.x < 256) {
+            uint32_t lo = 0, hi = 0;
+            for (int j = 0; j < 4; j++) {
+                lo |= (uint32_t)__popc(threadIdx.x & ((2 << j) - 1)) << (8 * j);
+                hi |= (uint32_t)__popc(threadIdx.x & ((32 << j) - 1)) << (8 * j);
+            }
+            S.lut8[threadIdx.x] = make_uint2(lo, hi);
         }
     }
     __syncthreads();
-    const int n_bord = T->n_bord, n_all = T->n_all, KA = T->KA;
+    const int n_bord = T->n_bord, KA = T->KA;
+    const int bord_len[2] = {T->bord_len[0], T->bord_len[1]};
     const int w = P.window;
     const int64_t total = P.pl.total;
 
     for (long long tile = (long long)blockIdx.x * COV_GROUPS + grp; tile < P.n_tiles; tile += (long long)gridDim.x * COV_GROUPS) {
         const int64_t a0 = tile * (int64_t)P.out_chunks * COV_CH - COV_CH;     // absolute base of region index 0
-        const int64_t a = a0 + (int64_t)tid * COV_CH;
-        uint32_t fl[2][2] = {{0u, 0u}, {0u, 0u}}, nn[2] = {0u, 0u};
-        group_sync(grp);
+        const int64_t a = a0 + (int64_t)lane * COV_CH;
+        __syncwarp();
         // ---- phase 1: table lookups of my 64 bases -> coverage words, spill into the next chunk, flag planes ----
         {
             uint32_t cvw[2][2] = {{0u, 0u}, {0u, 0u}}, sp[2] = {0u, 0u};
+            uint32_t s1w[2][2] = {{0u, 0u}, {0u, 0u}}, s2w[2][2] = {{0u, 0u}, {0u, 0u}}, trw[2] = {0u, 0u};
             uint32_t pk[5] = {0u, 0u, 0u, 0u, 0u}, nmw[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu};
             bool slow = false;
             if (a >= 0 && a < total) {
@@ -174,40 +247,40 @@ __global__ void __launch_bounds__(COV_THREADS, 2) scan_cov_kernel(const CovParam
                 nmw[0] = nv.x; nmw[1] = nv.y;
                 if (a + COV_CH < total) nmw[2] = __ldg(P.pl.nmask + (a >> 5) + 2);
                 if ((nmw[0] | nmw[1] | (nmw[2] & ((1u << (SC_W - 1)) - 1u))) == 0u) {
-                    // fast path: no N within reach of any of my windows.  Per base: entry << r, then the coverage masks
-                    // (bits 0-6 / 16-22) and the special flags (bit 7 / 23) of 8 neighbours share one register each.
-                    uint32_t acc[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}, facc[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+                    // fast path: no N within reach of any of my windows
 #pragma unroll
-                    for (int i = 0; i < COV_CH; i++) {
-                        const uint32_t e = tab_at(S.tab, pk[i >> 4], pk[(i >> 4) + 1], 2 * (i & 15));
-                        const int r = i & 7;
-                        const uint32_t t = e << r;
-                        acc[i >> 3] |= t & (0x007f007fu << r);
-                        facc[i >> 3] |= t & (0x00800080u << r);
-                    }
+                    for (int h = 0; h < 2; h++) {
+                        uint32_t acc[4] = {0u, 0u, 0u, 0u}, f1[4] = {0u, 0u, 0u, 0u}, f2[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-                    for (int g = 0; g < 2; g++) {
-                        uint32_t f[8];
-#pragma unroll
-                        for (int j = 0; j < 8; j++) f[j] = (acc[j] >> (16 * g)) & 0xffffu;
-                        cvw[g][0] = f[0] | (f[1] << 8) | (f[2] << 16) | (f[3] << 24);
-                        cvw[g][1] = (f[3] >> 8) | f[4] | (f[5] << 8) | (f[6] << 16) | (f[7] << 24);
-                        sp[g] = f[7] >> 8;
-                    }
-                    if ((facc[0] | facc[1] | facc[2] | facc[3] | facc[4] | facc[5] | facc[6] | facc[7]) != 0u) {
+                        for (int q = 0; q < 32; q++) {
+                            const int i = 32 * h + q, r = q & 7;
+                            const uint32_t e = tab_at(S.tab, pk[i >> 4], pk[(i >> 4) + 1], 2 * (i & 15));
+                            const uint32_t t = e << r;
+                            acc[q >> 3] |= t & (0x007f007fu << r);                // coverage masks: bits 0-6 / 16-22
+                            f1[q >> 3] |= t & ((E_S1A | E_S2A | E_S1B) << r);     // three flag kinds, 8 bits apart
+                            f2[q >> 3] |= t & ((E_T | E_S2B) << r);
+                        }
 #pragma unroll
                         for (int g = 0; g < 2; g++) {
-                            uint32_t f[8];
-#pragma unroll
-                            for (int j = 0; j < 8; j++) f[j] = (facc[j] >> (16 * g + 7)) & 0xffu;
-                            fl[g][0] = f[0] | (f[1] << 8) | (f[2] << 16) | (f[3] << 24);
-                            fl[g][1] = f[4] | (f[5] << 8) | (f[6] << 16) | (f[7] << 24);
+                            const uint32_t c0 = (acc[0] >> (16 * g)) & 0xffffu, c1 = (acc[1] >> (16 * g)) & 0xffffu,
+                                           c2 = (acc[2] >> (16 * g)) & 0xffffu, c3 = (acc[3] >> (16 * g)) & 0xffffu;
+                            cvw[g][h] |= c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
+                            if (h == 0) cvw[g][1] = c3 >> 8; else sp[g] = c3 >> 8;
+                        }
+                        if ((f1[0] | f1[1] | f1[2] | f1[3]) != 0u) {
+                            s1w[0][h] = gather4(f1[0], f1[1], f1[2], f1[3], 7);
+                            s2w[0][h] = gather4(f1[0], f1[1], f1[2], f1[3], 15);
+                            s1w[1][h] = gather4(f1[0], f1[1], f1[2], f1[3], 23);
+                        }
+                        if ((f2[0] | f2[1] | f2[2] | f2[3]) != 0u) {
+                            trw[h] = gather4(f2[0], f2[1], f2[2], f2[3], 8);
+                            s2w[1][h] = gather4(f2[0], f2[1], f2[2], f2[3], 24);
                         }
                     }
                 } else slow = (nmw[0] & nmw[1]) != 0xffffffffu;           // some N within reach (all N: nothing to do)
             }
             // lanes with an N within reach (read ends, mostly), one at a time, all 32 lanes helping: lane j looks at bases
-            // j and j + 32 of that lane's chunk; windows holding an N are skipped and noted
+            // j and j + 32 of that lane's chunk; a window cut short by an N after d < 7 bases goes to the table of d-base windows
             uint32_t need = __ballot_sync(TG_FULL_MASK, slow);
             while (need) {
                 const int l = __ffs(need) - 1;
@@ -218,182 +291,189 @@ __global__ void __launch_bounds__(COV_THREADS, 2) scan_cov_kernel(const CovParam
                 const uint32_t m0 = __shfl_sync(TG_FULL_MASK, nmw[0], l), m1 = __shfl_sync(TG_FULL_MASK, nmw[1], l),
                                m2 = __shfl_sync(TG_FULL_MASK, nmw[2], l);
                 const bool lowhalf = lane < 16;
-                uint32_t msk[2][2], fbal[2][2], nbal[2];
+                const int over = lane > 32 - SC_W ? 32 - lane : 32;       // bits of my mask that stay in this word
+                uint32_t carry[2] = {0u, 0u};
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     const uint32_t lo = h ? (lowhalf ? b2 : b3) : (lowhalf ? b0 : b1);
                     const uint32_t hi = h ? (lowhalf ? b3 : b4) : (lowhalf ? b1 : b2);
                     const uint32_t nwin = __funnelshift_r(h ? m1 : m0, h ? m2 : m1, lane) & ((1u << SC_W) - 1u);
-                    const uint32_t e = nwin ? 0u : tab_at(S.tab, lo, hi, 2 * (lane & 15));
-                    msk[0][h] = e & 0x7fu;
-                    msk[1][h] = (e >> 16) & 0x7fu;
-                    fbal[0][h] = __ballot_sync(TG_FULL_MASK, (e >> 7) & 1u);
-                    fbal[1][h] = __ballot_sync(TG_FULL_MASK, (e >> 23) & 1u);
-                    nbal[h] = __ballot_sync(TG_FULL_MASK, nwin != 0u && (nwin & 1u) == 0u);
-                }
-                const int over = lane > 32 - SC_W ? 32 - lane : 32;       // bits of my mask that stay in this word
-#pragma unroll
-                for (int g = 0; g < 2; g++) {
-                    const uint32_t w0 = __reduce_or_sync(TG_FULL_MASK, msk[g][0] << lane);
-                    const uint32_t w1 = __reduce_or_sync(TG_FULL_MASK, (over < 32 ? msk[g][0] >> over : 0u) | (msk[g][1] << lane));
-                    const uint32_t w2 = __reduce_or_sync(TG_FULL_MASK, over < 32 ? msk[g][1] >> over : 0u);
-                    if (lane == l) {
-                        cvw[g][0] = w0; cvw[g][1] = w1; sp[g] = w2;
-                        fl[g][0] = fbal[g][0]; fl[g][1] = fbal[g][1];
+                    uint32_t e = 0u;
+                    if (nwin == 0u) e = tab_at(S.tab, lo, hi, 2 * (lane & 15));
+                    else if (!(nwin & 1u)) {
+                        const int d = __ffs(nwin) - 1;                    // bases in front of the N: 1 .. 6
+                        const uint32_t wb = __funnelshift_r(lo, hi, 2 * (lane & 15)) & ((1u << (2 * d)) - 1u);
+                        e = __ldg(T->tab_short + COV_SHORT_OFF(d) + wb);
                     }
+                    const uint32_t fa = __ballot_sync(TG_FULL_MASK, e & E_S1A), fb = __ballot_sync(TG_FULL_MASK, e & E_S1B),
+                                   la = __ballot_sync(TG_FULL_MASK, e & E_S2A), lb = __ballot_sync(TG_FULL_MASK, e & E_S2B),
+                                   tt = __ballot_sync(TG_FULL_MASK, e & E_T);
+#pragma unroll
+                    for (int g = 0; g < 2; g++) {
+                        const uint32_t mk = (e >> (16 * g)) & 0x7fu;
+                        const uint32_t wd = __reduce_or_sync(TG_FULL_MASK, mk << lane) | carry[g];
+                        carry[g] = __reduce_or_sync(TG_FULL_MASK, over < 32 ? mk >> over : 0u);
+                        if (lane == l) { cvw[g][h] = wd; s1w[g][h] = g ? fb : fa; s2w[g][h] = g ? lb : la; }
+                    }
+                    if (lane == l) trw[h] = tt;
                 }
-                if (lane == l) { nn[0] = nbal[0]; nn[1] = nbal[1]; }
+                if (lane == l) { sp[0] = carry[0]; sp[1] = carry[1]; }
             }
-            *reinterpret_cast<uint4 *>(&G.pk[4 * tid]) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            *reinterpret_cast<uint2 *>(&G.nm[2 * tid]) = make_uint2(nmw[0], nmw[1]);
+            *reinterpret_cast<uint4 *>(&G.pk[4 * lane]) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint2 *>(&G.nm[2 * lane]) = make_uint2(nmw[0], nmw[1]);
+            *reinterpret_cast<uint2 *>(&G.tr[2 * lane]) = make_uint2(trw[0], trw[1]);
 #pragma unroll
             for (int g = 0; g < 2; g++) {
-                *reinterpret_cast<uint2 *>(&G.cov[g][2 * tid]) = make_uint2(cvw[g][0], cvw[g][1]);
-                *reinterpret_cast<uint2 *>(&G.flag[g][2 * tid]) = make_uint2(fl[g][0] | nn[0], fl[g][1] | nn[1]);
-                G.spill[g][tid + 1] = sp[g];
+                *reinterpret_cast<uint2 *>(&G.cov[g][2 * lane]) = make_uint2(cvw[g][0], cvw[g][1]);
+                *reinterpret_cast<uint2 *>(&G.s1[g][2 * lane]) = make_uint2(s1w[g][0], s1w[g][1]);
+                *reinterpret_cast<uint2 *>(&G.s2[g][2 * lane]) = make_uint2(s2w[g][0], s2w[g][1]);
+                G.spill[g][lane + 1] = sp[g];
             }
-            if (tid < 4) {
-                G.cov[0][COV_WORDS + tid] = 0u; G.cov[1][COV_WORDS + tid] = 0u;
+            if (lane < 4) {
+                G.cov[0][COV_WORDS + lane] = 0u; G.cov[1][COV_WORDS + lane] = 0u;
+                G.s1[0][COV_WORDS + lane] = 0u; G.s1[1][COV_WORDS + lane] = 0u;
+                G.s2[0][COV_WORDS + lane] = 0u; G.s2[1][COV_WORDS + lane] = 0u;
+                G.tr[COV_WORDS + lane] = 0u;
                 // planes behind the region (a long k-mer that starts in the last chunk is compared against them)
-                const int64_t ax = a0 + COV_REGION + 32 * (int64_t)tid;
+                const int64_t ax = a0 + COV_REGION + 32 * (int64_t)lane;
                 const bool ok = ax >= 0 && ax < total;
-                G.nm[COV_WORDS + tid] = ok ? __ldg(P.pl.nmask + (ax >> 5)) : 0xffffffffu;
-                G.pk[COV_REGION / 16 + 2 * tid] = ok ? __ldg(P.pl.pack2 + (ax >> 4)) : 0u;
-                G.pk[COV_REGION / 16 + 2 * tid + 1] = ok ? __ldg(P.pl.pack2 + (ax >> 4) + 1) : 0u;
+                G.nm[COV_WORDS + lane] = ok ? __ldg(P.pl.nmask + (ax >> 5)) : 0xffffffffu;
+                G.pk[COV_REGION / 16 + 2 * lane] = ok ? __ldg(P.pl.pack2 + (ax >> 4)) : 0u;
+                G.pk[COV_REGION / 16 + 2 * lane + 1] = ok ? __ldg(P.pl.pack2 + (ax >> 4) + 1) : 0u;
             }
-            if (tid < 2) { G.spill[tid][0] = 0u; G.flag[tid][COV_WORDS] = 0u; G.flag[tid][COV_WORDS + 1] = 0u; }
-            if (tid < 2 * COV_GW) G.defer[tid / COV_GW][tid % COV_GW] = 0u;
+            if (lane < 2) { G.spill[lane][0] = 0u; G.defer[lane] = 0u; }
         }
-        group_sync(grp);
-        // ---- phase 2a: spill of the previous chunk; my own flagged positions ----
+        __syncwarp();
+        // ---- phase 2a: spill of the previous chunk; special k-mers that start in my chunk ----
         bool deferred = false;
-#pragma unroll 1
+#pragma unroll
         for (int g = 0; g < 2; g++) {
-            const uint32_t s_in = G.spill[g][tid];
-            if (s_in) atomicOr(&G.cov[g][2 * tid], s_in);
-            const int k0 = g ? KA : 0, k1 = g ? n_all : KA;
-#pragma unroll 1
-            for (int h = 0; h < 2; h++) {
-                uint32_t fw = G.flag[g][2 * tid + h] & ~(h ? nn[1] : nn[0]);     // (N-near positions: below)
-                while (fw) {
-                    // a special k-mer of list g may start at x: compare those whose prefix the window holds.  One that does
-                    // not overlap itself is covered right away; a self-overlapping one too, unless another candidate of
-                    // the list is close enough to overlap it -- then re.finditer's greedy rule decides (phase 2b).
-                    const int x = tid * COV_CH + h * 32 + __ffs(fw) - 1;
-                    fw &= fw - 1;
-                    const uint32_t e = tab_at(S.tab, G.pk[x >> 4], G.pk[(x >> 4) + 1], 2 * (x & 15));
-                    const int slot = (int)((e >> (16 * g + 8)) & 0x7fu);
-                    const int ka = (slot == COV_SLOT_MANY) ? k0 : k0 + slot, kb = (slot == COV_SLOT_MANY) ? k1 : ka + 1;
-                    for (int k = ka; k < kb; k++) {
-                        const int kind = S.kind[k], len = S.len[k];
-                        if (kind != SC_SPECIAL && kind != SC_BORDERED) continue;
-                        // (a k-mer that fits the window is fully decided by the entry)
-                        if ((len > SC_W || slot == COV_SLOT_MANY) && !sm_kmer_at(G.pk, G.nm, x, S.pat[k], len))
-                            continue;
-                        if (kind == SC_BORDERED && flags_near(G.flag[g], x, len)) {
-                            atomicOr(&G.defer[g][warp], 1u << lane);
+            const uint32_t s_in = G.spill[g][lane];
+            if (s_in) atomicOr(&G.cov[g][2 * lane], s_in);
+            const uint64_t X = (uint64_t)G.s1[g][2 * lane] | ((uint64_t)G.s1[g][2 * lane + 1] << 32);
+            if (X != 0ull) {
+                const int L = bord_len[g];
+                if (L > 0) {
+                    // (what lies in front of the region is unknown: a flag at its very start may be overlapped from there, and
+                    // only the warp-wide walk looks back)
+                    const uint32_t prev = lane ? G.s1[g][2 * lane - 1] : ((a0 > 0) ? 0xffffffffu : 0u), next = G.s1[g][2 * lane + 2];
+                    const int conflict = (L == 6) ? smear_flags<6>(X, prev, next, &G.cov[g][2 * lane], 6)
+                                                  : smear_flags<0>(X, prev, next, &G.cov[g][2 * lane], L);
+                    if (conflict == 2) {
+                        atomicOr(&G.defer[g], 1u << lane);
+                        deferred = true;
+                    } else if (conflict == 1) {
+                        // close flags, all mine: the greedy rule per k-mer, left to right
+                        uint64_t B = 0ull;
+                        uint32_t over = 0u;
+                        const uint64_t lm = (1ull << L) - 1ull, bm = (1ull << (2 * L)) - 1ull;
+                        for (int q = 0; q < S.n_bsk[g]; q++) {
+                            const uint64_t pat = S.pat[S.bsk[g][q]];
+                            int blocked = -1;
+                            uint64_t rest = X;
+                            while (rest) {
+                                const int bit = __ffsll((long long)rest) - 1;
+                                rest &= rest - 1;
+                                if (bit < blocked || ((sm_bases64(G.pk, lane * COV_CH + bit) ^ pat) & bm) != 0ull) continue;
+                                blocked = bit + L;
+                                B |= lm << bit;
+                                if (bit + L > 64) over |= (uint32_t)(lm >> (64 - bit));
+                            }
+                        }
+                        if ((uint32_t)B) atomicOr(&G.cov[g][2 * lane], (uint32_t)B);
+                        if (B >> 32) atomicOr(&G.cov[g][2 * lane + 1], (uint32_t)(B >> 32));
+                        if (over) atomicOr(&G.cov[g][2 * lane + 2], over);
+                    }
+                } else {
+                    // window-sized self-overlapping k-mers of several lengths: per occurrence
+                    uint64_t rest = X;
+                    while (rest) {
+                        const int x = lane * COV_CH + __ffsll((long long)rest) - 1;
+                        rest &= rest - 1;
+                        for (int q = 0; q < S.n_bsk[g]; q++) {
+                            const int k = S.bsk[g][q], len = S.len[k];
+                            if (!sm_kmer_at(G.pk, G.nm, x, S.pat[k], len)) continue;
+                            if (flags_near(G.s1[g], x, SC_W) || (x < SC_W - 1 && a0 > 0)) {
+                                atomicOr(&G.defer[g], 1u << lane);
+                                deferred = true;
+                            } else cov_or(G.cov[g], x, len);
+                        }
+                    }
+                }
+            }
+            // long k-mers: their first 7 bases start at p and the continuation of some long k-mer at p + 7
+            const uint64_t S2 = (uint64_t)G.s2[g][2 * lane] | ((uint64_t)G.s2[g][2 * lane + 1] << 32);
+            if (S2 != 0ull) {
+                const uint64_t TR = (uint64_t)G.tr[2 * lane] | ((uint64_t)G.tr[2 * lane + 1] << 32);
+                uint64_t cand = S2 & ((TR >> SC_W) | ((uint64_t)G.tr[2 * lane + 2] << (64 - SC_W)));
+                while (cand) {
+                    const int x = lane * COV_CH + __ffsll((long long)cand) - 1;
+                    cand &= cand - 1;
+                    for (int q = 0; q < S.n_lgk[g]; q++) {
+                        const int k = S.lgk[g][q], len = S.len[k];
+                        if (!sm_kmer_at(G.pk, G.nm, x, S.pat[k], len)) continue;
+                        if (S.kind[k] == SC_BORDERED) {                       // long AND self-overlapping: always the greedy walk
+                            atomicOr(&G.defer[g], 1u << lane);
                             deferred = true;
                         } else cov_or(G.cov[g], x, len);
                     }
                 }
             }
         }
-        {
-            // an N within the window: every k-mer is compared directly, the warp takes the k-mers
-            uint32_t have = __ballot_sync(TG_FULL_MASK, (nn[0] | nn[1]) != 0u);
-            while (have) {
-                const int l = __ffs(have) - 1;
-                have &= have - 1;
-                const uint32_t n0 = __shfl_sync(TG_FULL_MASK, nn[0], l), n1 = __shfl_sync(TG_FULL_MASK, nn[1], l);
-                const int xb = (warp * 32 + l) * COV_CH;
-#pragma unroll 1
-                for (int h = 0; h < 2; h++) {
-                    uint32_t nw = h ? n1 : n0;
-                    while (nw) {
-                        const int x = xb + h * 32 + __ffs(nw) - 1;
-                        nw &= nw - 1;
-                        for (int k = lane; k < n_all; k += 32) {
-                            const int kind = S.kind[k], g = k >= KA ? 1 : 0;
-                            if (kind == SC_REDUNDANT || !sm_kmer_at(G.pk, G.nm, x, S.pat[k], S.len[k])) continue;
-                            if (kind == SC_BORDERED && flags_near(G.flag[g], x, S.len[k])) {
-                                atomicOr(&G.defer[g][warp], 1u << l);
-                                deferred = true;
-                            } else cov_or(G.cov[g], x, S.len[k]);
-                        }
-                    }
-                }
-            }
-        }
-        if (group_sync_or(grp, deferred)) {
-            // ---- phase 2b (rare): self-overlapping k-mer b, one warp each: lanes verify the flagged positions of the
-            //      deferred chunks (32 chunks per round, in position order), then the warp walks the true candidates left
-            //      to right with re.finditer's rule.  Candidates outside the deferred chunks cannot overlap one inside. ----
-            for (int b = warp; b < n_bord; b += COV_GW) {
+        if (__any_sync(TG_FULL_MASK, deferred)) {
+            // ---- phase 2b (rare): the warp walks the candidates of every self-overlapping k-mer in the deferred chunks, left
+            //      to right, with re.finditer's rule.  A candidate outside the deferred chunks cannot overlap one inside. ----
+            __syncwarp();
+            for (int b = 0; b < n_bord; b++) {
                 const int k = T->bord_idx[b];
                 const int g = (k >= KA) ? 1 : 0;
+                const uint32_t dmask = G.defer[g];
+                if (!dmask) continue;
                 const int blen = S.len[k];
                 const uint64_t pat = S.pat[k];
-                int n_def = 0;
-#pragma unroll
-                for (int i = 0; i < COV_GW; i++) n_def += __popc(G.defer[g][i]);
+                // lane c verifies the candidates of chunk c
+                uint64_t mine = 0ull;
+                if ((dmask >> lane) & 1u) {
+                    const uint32_t *fp = (blen > SC_W) ? G.s2[g] : G.s1[g];
+                    uint64_t fw = (uint64_t)fp[2 * lane] | ((uint64_t)fp[2 * lane + 1] << 32);
+                    while (fw) {
+                        const int bit = __ffsll((long long)fw) - 1;
+                        fw &= fw - 1;
+                        if (sm_kmer_at(G.pk, G.nm, lane * COV_CH + bit, pat, blen)) mine |= 1ull << bit;
+                    }
+                }
+                uint32_t nz = __ballot_sync(TG_FULL_MASK, mine != 0ull);
                 int blocked = -0x40000000;
                 bool first = true;
-                for (int r0 = 0; r0 < n_def; r0 += 32) {
-                    int c = -1;                                           // my chunk: the (r0 + lane)-th deferred one
-                    {
-                        int rank = r0 + lane;
-#pragma unroll
-                        for (int i = 0; i < COV_GW; i++) {
-                            const uint32_t wd = G.defer[g][i];
-                            const int pc = __popc(wd);
-                            if (c < 0 && rank >= 0 && rank < pc) c = i * 32 + (int)__fns(wd, 0, rank + 1);
-                            rank -= pc;
-                        }
-                    }
-                    uint64_t mine = 0ull;
-                    if (c >= 0) {
-#pragma unroll 1
-                        for (int h = 0; h < 2; h++) {
-                            uint32_t fw = G.flag[g][2 * c + h];
-                            while (fw) {
-                                const int bit = __ffs(fw) - 1;
-                                fw &= fw - 1;
-                                if (sm_kmer_at(G.pk, G.nm, c * COV_CH + h * 32 + bit, pat, blen)) mine |= 1ull << (h * 32 + bit);
+                while (nz) {
+                    const int l = __ffs(nz) - 1;
+                    nz &= nz - 1;
+                    uint64_t word = __shfl_sync(TG_FULL_MASK, mine, l);
+                    while (word) {
+                        const int x = l * COV_CH + __ffsll((long long)word) - 1;
+                        word &= word - 1;
+                        if (first) {
+                            first = false;
+                            if (x < blen - 1 && a0 + x > 0) {             // the chain may reach back beyond the region
+                                const int64_t bl = sc_chain_state_before(P.pl, a0 + x, pat, blen);
+                                blocked = (bl < a0) ? -0x40000000 : (int)(bl - a0);
                             }
                         }
-                    }
-                    uint32_t nz = __ballot_sync(TG_FULL_MASK, mine != 0ull);
-                    while (nz) {
-                        const int l = __ffs(nz) - 1;
-                        nz &= nz - 1;
-                        uint64_t word = __shfl_sync(TG_FULL_MASK, mine, l);
-                        const int cc = __shfl_sync(TG_FULL_MASK, c, l);
-                        while (word) {
-                            const int x = cc * COV_CH + __ffsll((long long)word) - 1;
-                            word &= word - 1;
-                            if (first) {
-                                first = false;
-                                if (x < blen - 1 && a0 + x > 0) {         // the chain may reach back beyond the region
-                                    const int64_t bl = sc_chain_state_before(P.pl, a0 + x, pat, blen);
-                                    blocked = (bl < a0) ? -0x40000000 : (int)(bl - a0);
-                                }
-                            }
-                            if (x >= blocked) {
-                                blocked = x + blen;
-                                if (lane == 0) cov_or(G.cov[g], x, blen);
-                            }
+                        if (x >= blocked) {
+                            blocked = x + blen;
+                            if (lane == 0) cov_or(G.cov[g], x, blen);
                         }
                     }
                 }
             }
-            group_sync(grp);
         }
+        __syncwarp();
         // ---- phase 3: outputs of chunks 1 .. out_chunks ----
-        const bool act = tid >= 1 && tid <= P.out_chunks && a < total;
+        const bool act = lane >= 1 && lane <= P.out_chunks && a < total;
         if (MODE == MODE_COUNT) {
             // popcount of my two coverage words, one atomic per warp when the warp lies inside one read
-            const int c0 = act ? __popc(G.cov[0][2 * tid]) + __popc(G.cov[0][2 * tid + 1]) : 0;
-            const int c1 = act ? __popc(G.cov[1][2 * tid]) + __popc(G.cov[1][2 * tid + 1]) : 0;
+            const int c0 = act ? __popc(G.cov[0][2 * lane]) + __popc(G.cov[0][2 * lane + 1]) : 0;
+            const int c1 = act ? __popc(G.cov[1][2 * lane]) + __popc(G.cov[1][2 * lane + 1]) : 0;
             const unsigned r1 = act ? (unsigned)P.blk_read[a >> 7] + 1u : 0u;
             const unsigned rmax = __reduce_max_sync(TG_FULL_MASK, r1);
             const unsigned rmin = __reduce_min_sync(TG_FULL_MASK, act ? r1 : 0xffffffffu);
@@ -410,12 +490,13 @@ __global__ void __launch_bounds__(COV_THREADS, 2) scan_cov_kernel(const CovParam
                 }
             }
         } else if (act) {
-            const int j0 = tid * COV_CH;
+            const int j0 = lane * COV_CH;
+            const char *lut = reinterpret_cast<const char *>(S.lut8);
 #pragma unroll 1
             for (int g = 0; g < 2; g++) {
                 const uint32_t *cv = G.cov[g];
                 const int cnt = range_popc(cv, j0 + 1, j0 + w);
-                const uint32_t a0w = cv[2 * tid], a1w = cv[2 * tid + 1], a2w = cv[2 * tid + 2];
+                const uint32_t a0w = cv[2 * lane], a1w = cv[2 * lane + 1], a2w = cv[2 * lane + 2];
                 const uint32_t sa[2] = {__funnelshift_r(a0w, a1w, 1), __funnelshift_r(a1w, a2w, 1)};      // leaving bits
                 const int jb = j0 + w + 1;
                 const uint32_t b0w = cv[jb >> 5], b1w = cv[(jb >> 5) + 1], b2w = cv[(jb >> 5) + 2];
@@ -426,13 +507,16 @@ __global__ void __launch_bounds__(COV_THREADS, 2) scan_cov_kernel(const CovParam
                 for (int q = 0; q < 4; q++) {
                     uint32_t o[4];
 #pragma unroll
-                    for (int h = 0; h < 4; h++) {
-                        const int g4 = 4 * q + h;
-                        const uint32_t A = S.lut[(sb[g4 >> 3] >> (4 * (g4 & 7))) & 15u];
-                        const uint32_t B = S.lut[(sa[g4 >> 3] >> (4 * (g4 & 7))) & 15u];
-                        const uint32_t incl = cnt4 + A - B;            // counts of outputs 4 g4 + 1 .. 4 g4 + 4 (exact mod 2^32)
-                        o[h] = __byte_perm(incl, cnt4, 0x2104);
-                        cnt4 = __byte_perm(incl, 0u, 0x3333);
+                    for (int h = 0; h < 2; h++) {
+                        // 8 outputs per step: prefix popcounts of the entering and of the leaving byte
+                        const int g8 = 2 * q + h;
+                        const uint32_t bi = (sb[g8 >> 2] >> (8 * (g8 & 3))) & 0xffu, bo = (sa[g8 >> 2] >> (8 * (g8 & 3))) & 0xffu;
+                        const uint2 A = *reinterpret_cast<const uint2 *>(lut + bi * 8), B = *reinterpret_cast<const uint2 *>(lut + bo * 8);
+                        const uint32_t lo = cnt4 + A.x - B.x;              // counts of outputs 8 g8 + 1 .. + 4 (exact mod 2^32)
+                        const uint32_t hi = cnt4 + A.y - B.y;              // counts of outputs 8 g8 + 5 .. + 8
+                        o[2 * h] = __byte_perm(lo, cnt4, 0x2104);
+                        o[2 * h + 1] = __byte_perm(hi, lo, 0x2107);
+                        cnt4 = __byte_perm(hi, 0u, 0x3333);
                     }
                     *reinterpret_cast<uint4 *>(dst + 16 * q) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
@@ -460,6 +544,7 @@ TG_EXPORT int tg_kmer_table_build_pair(const char *kmers_a, const int32_t *off_a
     CovTable *T = reinterpret_cast<CovTable *>(h_table);
     memset(T, 0, sizeof(CovTable));
     T->magic = COV_MAGIC; T->n_all = KA + KB; T->KA = KA;
+    int n_bordered = 0;
     for (int k = 0; k < KA + KB; k++) {
         const std::string &s = km[k];
         T->pat[k] = sc_pattern(s);
@@ -467,7 +552,7 @@ TG_EXPORT int tg_kmer_table_build_pair(const char *kmers_a, const int32_t *off_a
         if ((int)s.size() > T->max_len) T->max_len = (int)s.size();
         const bool bord = sc_is_bordered(s);
         T->kind[k] = bord ? SC_BORDERED : ((int)s.size() > SC_W ? SC_SPECIAL : SC_PLAIN);
-        if (bord && ++T->n_bord > SC_MAXBORD) return tg_set_err(TG_EINVAL, "more than %d self-overlapping k-mers", SC_MAXBORD);
+        if (bord && ++n_bordered > SC_MAXBORD) return tg_set_err(TG_EINVAL, "more than %d self-overlapping k-mers", SC_MAXBORD);
     }
     // A special k-mer whose every base is covered by plain k-mers of its own list occurring inside it (the HOR k-mers
     // CCCCTA|CCCTAA|CCCCTA, ...) never changes the UNION coverage: wherever it matches, those plain k-mers match too.
@@ -484,27 +569,36 @@ TG_EXPORT int tg_kmer_table_build_pair(const char *kmers_a, const int32_t *off_a
         for (char c : covd) all = all && c;
         if (all) T->kind[k] = SC_REDUNDANT;
     }
-    T->n_bord = T->n_sp = 0;
     for (int k = 0; k < KA + KB; k++) {
-        if (T->kind[k] == SC_BORDERED) T->bord_idx[T->n_bord++] = k;
-        else if (T->kind[k] == SC_SPECIAL) T->sp_idx[T->n_sp++] = k;
+        if (T->kind[k] != SC_BORDERED) continue;
+        T->bord_idx[T->n_bord++] = k;
+        if (T->len[k] > SC_W) continue;
+        int &bl = T->bord_len[k >= KA ? 1 : 0];
+        if (bl == 0) bl = T->len[k];
+        else if (bl != T->len[k]) bl = -1;
     }
-    for (uint32_t w = 0; w < (uint32_t)SC_TAB; w++) {
+    // entry of a window of n bases (n = SC_W: the main table; n < SC_W: an N follows, only what fits in n bases can match)
+    auto entry = [&](uint32_t w, int n) {
         uint32_t e = 0;
         for (int k = 0; k < KA + KB; k++) {
-            if (T->kind[k] == SC_REDUNDANT || !sc_window_has_prefix(w, km[k])) continue;
-            const int sh = (k >= KA) ? 16 : 0;
-            if (T->kind[k] == SC_PLAIN) e |= ((1u << km[k].size()) - 1u) << sh;      // union of prefixes = the longest
-            else {
-                // flag + which special k-mer (index within its list), COV_SLOT_MANY if several share the prefix
-                const uint32_t slot = (uint32_t)(k >= KA ? k - KA : k);
-                const uint32_t old = (e >> (sh + 8)) & 0x7fu;
-                const uint32_t now = ((e >> (sh + 7)) & 1u) ? (old == slot ? slot : (uint32_t)COV_SLOT_MANY) : slot;
-                e = (e & ~(0x7f00u << sh)) | (0x80u << sh) | (now << (sh + 8));
+            if (T->kind[k] == SC_REDUNDANT) continue;
+            const bool b_list = k >= KA;
+            const int len = (int)km[k].size();
+            if (len > SC_W) {
+                // bases 8.. of a long k-mer: "continues here" (T), whichever list
+                const std::string rem = km[k].substr(SC_W);
+                if (!(n < SC_W && (int)rem.size() > n) && sc_window_has_prefix(w, rem)) e |= E_T;
             }
+            if (!sc_window_has_prefix(w, km[k]) || (n < SC_W && len > n)) continue;
+            if (T->kind[k] == SC_PLAIN) e |= ((1u << len) - 1u) << (b_list ? 16 : 0);        // union of prefixes = the longest
+            else if (len > SC_W) e |= b_list ? E_S2B : E_S2A;
+            else e |= b_list ? E_S1B : E_S1A;
         }
-        T->tab[w] = e;
-    }
+        return e;
+    };
+    for (uint32_t w = 0; w < (uint32_t)SC_TAB; w++) T->tab[w] = entry(w, SC_W);
+    for (int d = 1; d < SC_W; d++)
+        for (uint32_t w = 0; w < (1u << (2 * d)); w++) T->tab_short[COV_SHORT_OFF(d) + w] = entry(w, d);
     return TG_OK;
 }
 
@@ -520,7 +614,9 @@ static int launch_cov(int mode, const uint32_t *d_pack2, const uint32_t *d_nmask
     CovParams P;
     P.pl.pack2 = d_pack2; P.pl.nmask = d_nmask; P.pl.total = total_bases;
     P.blk_read = d_blk_read;
-    P.out_chunks = COV_GT - 1 - (mode == MODE_DENSITY ? ((window + 63) >> 6) : 0);
+    // 1 chunk of left halo; right halo: the window (density), or one chunk so that a long k-mer starting in the last
+    // output chunk still sees its continuation flag (count)
+    P.out_chunks = 32 - 1 - (mode == MODE_DENSITY ? ((window + 63) >> 6) : 1);
     const int64_t out_bases = (int64_t)P.out_chunks * COV_CH;
     P.n_tiles = (total_bases + out_bases - 1) / out_bases;
     P.tab = reinterpret_cast<const CovTable *>(table);

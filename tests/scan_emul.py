@@ -48,21 +48,44 @@ def redundant(kmers):
     return out
 
 
-def build_cov_table(list_a, list_b):
-    """entry = (mask | flag << 7 | slot << 8) per list, list B in the upper half: mask = (1 << L) - 1 for the longest plain
-    k-mer that is a prefix of the window; flag = a special k-mer's first min(len, W) letters are a prefix of the window;
-    slot = index of that k-mer in its list (127 when several qualify)."""
-    tab = [0] * (1 << (2 * W))
+E_S1A, E_T, E_S2A, E_S1B, E_S2B = 1 << 7, 1 << 8, 1 << 15, 1 << 23, 1 << 24      # tg_cov.cu entry bits
+
+
+def cov_entry(s, n, list_a, list_b, meta):
+    """table entry of a window holding the n bases `s` (n = W: main table; n < W: an N follows, only what fits can match):
+    per list the coverage mask of the longest plain k-mer that is a prefix, S1 = exact occurrence of a window-sized
+    self-overlapping k-mer, S2 = the first W bases of a long k-mer, T = bases W+1.. of a long k-mer of either list."""
+    e = 0
     for g, lst in enumerate((list_a, list_b)):
-        sp = [x and not r for x, r in zip(classify(lst), redundant(lst))]
-        plain = [not x for x in classify(lst)]
-        for w in range(1 << (2 * W)):
-            s = window_str(w)
-            L = max([len(k) for k, x in zip(lst, plain) if x and s.startswith(k)], default=0)
-            slots = [i for i, (k, x) in enumerate(zip(lst, sp)) if x and s.startswith(k[:W])]
-            slot = 0 if not slots else (slots[0] if len(slots) == 1 else 127)
-            tab[w] |= (((1 << L) - 1) | (int(bool(slots)) << 7) | (slot << 8)) << (16 * g)
-    return tab
+        spc, red = meta[g]
+        for k, x, r in zip(lst, spc, red):
+            if r:
+                continue
+            if len(k) > W:
+                rem = k[W:]
+                if not (n < W and len(rem) > n) and s.startswith(rem[:W]):
+                    e |= E_T
+            if not s.startswith(k[:W]) or (n < W and len(k) > n):
+                continue
+            if not x:
+                e |= ((1 << len(k)) - 1) << (16 * g)
+            elif len(k) > W:
+                e |= E_S2B if g else E_S2A
+            else:
+                e |= E_S1B if g else E_S1A
+    return e
+
+
+def build_cov_table(list_a, list_b):
+    meta = [(classify(lst), redundant(lst)) for lst in (list_a, list_b)]
+    return [cov_entry(window_str(w), W, list_a, list_b, meta) for w in range(1 << (2 * W))]
+
+
+def build_cov_short_tables(list_a, list_b):
+    """tab_short: the entries of windows cut short by an N after d = 1 .. 6 bases, concatenated at offsets (4^d - 4) / 3
+    (tg_cov.cu: COV_SHORT_OFF)."""
+    meta = [(classify(lst), redundant(lst)) for lst in (list_a, list_b)]
+    return [cov_entry(window_str(w)[:d], d, list_a, list_b, meta) for d in range(1, W) for w in range(1 << (2 * d))]
 
 
 def kmer_at(seq, p, k):
@@ -91,12 +114,16 @@ def coverage_emulate(read, kmers, tab, group):
         if isn[p]:
             continue
         if not any(isn[p:p + W]):                               # clean window: table lookup
-            e = (tab[window_code(read, p)] >> (16 * group)) & 0xff
-            m = e & 0x7f
+            e = tab[window_code(read, p)]
+            m = (e >> (16 * group)) & 0x7f
             for t in range(W):
                 if (m >> t) & 1:
                     cov[p + t] = 1
-            todo = [k for k, x in zip(kmers, sp) if x] if e & 0x80 else []
+            todo = []
+            if e & (E_S1B if group else E_S1A):
+                todo += [k for k, x in zip(kmers, sp) if x and len(k) <= W]
+            if e & (E_S2B if group else E_S2A):
+                todo += [k for k, x in zip(kmers, sp) if x and len(k) > W]
         else:                                                   # an N within reach: every k-mer is tested directly
             todo = kmers
         for k in todo:

@@ -73,10 +73,14 @@ def test_library_pair_table_equals_python_construction(tname):
                                           blobs[1], offs[1].ctypes.data_as(C.c_void_p), len(KR), host.ctypes.data_as(C.c_void_p)))
     tab = host[-4 * (1 << (2 * E.W)):].view(np.uint32)           # the table is the last member of the blob
     assert tab.tolist() == E.build_cov_table(KL, KR)
-    hdr = host[:24].view(np.int32)
+    short = E.build_cov_short_tables(KL, KR)
+    n_short = 5464                                              # COV_SHORT_N
+    got = host[-4 * (1 << (2 * E.W)) - 4 * n_short:-4 * (1 << (2 * E.W))].view(np.uint32)
+    assert got[:len(short)].tolist() == short
+    hdr = host[:32].view(np.int32)
     red = E.redundant(KL) + E.redundant(KR)
     n_bord = sum(E.is_bordered(k) and not r for k, r in zip(KL + KR, red))
-    n_sp = sum((len(k) > E.W) and not E.is_bordered(k) and not r for k, r in zip(KL + KR, red))
     if tname.startswith('human'):
         assert sum(red) == 4                                     # the two HOR k-mers of both strands
-    assert (hdr[1], hdr[2], hdr[3], hdr[4], hdr[5]) == (2 * len(KL), len(KL), n_sp, n_bord, max(map(len, KL)))
+        assert (hdr[6], hdr[7]) == (6, 6)                        # CCCCCC / CCCTCC and their reverse complements
+    assert (hdr[1], hdr[2], hdr[3], hdr[4]) == (2 * len(KL), len(KL), n_bord, max(map(len, KL)))
