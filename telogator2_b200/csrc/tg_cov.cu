@@ -70,9 +70,6 @@ struct alignas(16) CovGroupSmem {
     uint32_t spill[2][32 + 4];
     uint32_t pk[COV_REGION / 16 + 8];          // the staged planes (slow paths read them back)
     uint32_t nm[COV_WORDS + 4];
-    uint32_t s1[2][COV_WORDS + 4];             // per list: exact occurrences of window-sized self-overlapping k-mers
-    uint32_t s2[2][COV_WORDS + 4];             // per list: the first 7 bases of a long k-mer start here
-    uint32_t tr[COV_WORDS + 4];                // bases 8.. of a long k-mer (either list) start here
     uint32_t defer[2], pad_[2];                // per list: chunks that need the warp-wide greedy walk, one bit per chunk
 };
 
@@ -132,16 +129,18 @@ __device__ __noinline__ bool sm_kmer_at(const uint32_t *pk, const uint32_t *nm, 
     return (nbits & lm) == 0u && ((sm_bases64(pk, x) ^ pat) & m) == 0ull;
 }
 
-// any flag bit of the positions (x - d, x + d) except x itself?  (fw: a flag plane with 2 readable words behind it)
-__device__ __noinline__ bool flags_near(const uint32_t *fw, int x, int d)
+// any flag within (bit - d, bit + d) except `bit` itself?  X: the 64 flags of my chunk, prev / next: the neighbouring words
+__device__ __forceinline__ bool flags_near(uint64_t X, uint32_t prev, uint32_t next, int bit, int d)
 {
-    const int s = x - 31;                        // 64-bit window starting at x - 31: position x is bit 31
-    const int w0 = s >> 5, sh = s & 31;          // (arithmetic shift: floor)
-    const uint32_t a = (w0 >= 0) ? fw[w0] : 0u, b = fw[w0 + 1], c = fw[w0 + 2];
-    const uint64_t lo = ((uint64_t)a | ((uint64_t)b << 32)) >> sh;
-    const uint64_t win = sh ? (lo | ((uint64_t)c << (64 - sh))) : lo;
-    const uint64_t m = (((1ull << (2 * d - 1)) - 1ull) << (32 - d)) & ~(1ull << 31);
-    return (win & m) != 0ull;
+    // 128-bit window [prev][X][next], my bit at index 32 + bit; d <= 32
+    const int lo_i = 32 + bit - (d - 1), hi_i = 32 + bit + (d - 1);
+    bool hit = false;
+    for (int i = lo_i; i <= hi_i; i++) {
+        if (i == 32 + bit) continue;
+        const uint32_t v = (i < 32) ? (prev >> i) : (i < 96) ? (uint32_t)(X >> (i - 32)) : (next >> (i - 96));
+        hit = hit || (v & 1u);
+    }
+    return hit;
 }
 
 // Flags X of my chunk = exact occurrences of self-overlapping k-mers of length L (prev / next: the flag words of the
@@ -233,11 +232,11 @@ __global__ void __launch_bounds__(COV_THREADS, 2) scan_cov_kernel(const CovParam
     for (long long tile = (long long)blockIdx.x * COV_GROUPS + grp; tile < P.n_tiles; tile += (long long)gridDim.x * COV_GROUPS) {
         const int64_t a0 = tile * (int64_t)P.out_chunks * COV_CH - COV_CH;     // absolute base of region index 0
         const int64_t a = a0 + (int64_t)lane * COV_CH;
+        uint32_t s1w[2][2] = {{0u, 0u}, {0u, 0u}}, s2w[2][2] = {{0u, 0u}, {0u, 0u}}, trw[2] = {0u, 0u};   // my flag planes
         __syncwarp();
         // ---- phase 1: table lookups of my 64 bases -> coverage words, spill into the next chunk, flag planes ----
         {
             uint32_t cvw[2][2] = {{0u, 0u}, {0u, 0u}}, sp[2] = {0u, 0u};
-            uint32_t s1w[2][2] = {{0u, 0u}, {0u, 0u}}, s2w[2][2] = {{0u, 0u}, {0u, 0u}}, trw[2] = {0u, 0u};
             uint32_t pk[5] = {0u, 0u, 0u, 0u, 0u}, nmw[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu};
             bool slow = false;
             if (a >= 0 && a < total) {
@@ -247,36 +246,47 @@ __global__ void __launch_bounds__(COV_THREADS, 2) scan_cov_kernel(const CovParam
                 nmw[0] = nv.x; nmw[1] = nv.y;
                 if (a + COV_CH < total) nmw[2] = __ldg(P.pl.nmask + (a >> 5) + 2);
                 if ((nmw[0] | nmw[1] | (nmw[2] & ((1u << (SC_W - 1)) - 1u))) == 0u) {
-                    // fast path: no N within reach of any of my windows
+                    // fast path: no N within reach of any of my windows.  16 bases per iteration (kept rolled: the loop body
+                    // must stay in the instruction cache, every warp runs at its own pace)
+                    uint64_t c64[2] = {0ull, 0ull}, s1_64[2] = {0ull, 0ull}, s2_64[2] = {0ull, 0ull}, tr64 = 0ull;
+                    uint32_t w0 = pk[0], w1 = pk[1], w2 = pk[2], w3 = pk[3], w4 = pk[4];
+#pragma unroll 1
+                    for (int it = 0; it < 4; it++) {
+                        uint32_t acc[2] = {0u, 0u}, f1[2] = {0u, 0u}, f2[2] = {0u, 0u};
 #pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        uint32_t acc[4] = {0u, 0u, 0u, 0u}, f1[4] = {0u, 0u, 0u, 0u}, f2[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-                        for (int q = 0; q < 32; q++) {
-                            const int i = 32 * h + q, r = q & 7;
-                            const uint32_t e = tab_at(S.tab, pk[i >> 4], pk[(i >> 4) + 1], 2 * (i & 15));
+                        for (int q = 0; q < 16; q++) {
+                            const int r = q & 7;
+                            const uint32_t e = tab_at(S.tab, w0, w1, 2 * q);
                             const uint32_t t = e << r;
                             acc[q >> 3] |= t & (0x007f007fu << r);                // coverage masks: bits 0-6 / 16-22
                             f1[q >> 3] |= t & ((E_S1A | E_S2A | E_S1B) << r);     // three flag kinds, 8 bits apart
                             f2[q >> 3] |= t & ((E_T | E_S2B) << r);
                         }
-#pragma unroll
-                        for (int g = 0; g < 2; g++) {
-                            const uint32_t c0 = (acc[0] >> (16 * g)) & 0xffffu, c1 = (acc[1] >> (16 * g)) & 0xffffu,
-                                           c2 = (acc[2] >> (16 * g)) & 0xffffu, c3 = (acc[3] >> (16 * g)) & 0xffffu;
-                            cvw[g][h] |= c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
-                            if (h == 0) cvw[g][1] = c3 >> 8; else sp[g] = c3 >> 8;
+                        const int sh = 16 * it;
+                        c64[0] |= (uint64_t)((acc[0] & 0xffffu) | ((acc[1] & 0xffffu) << 8)) << sh;
+                        c64[1] |= (uint64_t)((acc[0] >> 16) | ((acc[1] >> 16) << 8)) << sh;
+                        if (it == 3) {
+                            sp[0] = (acc[1] & 0xffffu) >> 8;
+                            sp[1] = acc[1] >> 24;
                         }
-                        if ((f1[0] | f1[1] | f1[2] | f1[3]) != 0u) {
-                            s1w[0][h] = gather4(f1[0], f1[1], f1[2], f1[3], 7);
-                            s2w[0][h] = gather4(f1[0], f1[1], f1[2], f1[3], 15);
-                            s1w[1][h] = gather4(f1[0], f1[1], f1[2], f1[3], 23);
+                        if ((f1[0] | f1[1]) != 0u) {
+                            s1_64[0] |= (uint64_t)(((f1[0] >> 7) & 0xffu) | (((f1[1] >> 7) & 0xffu) << 8)) << sh;
+                            s2_64[0] |= (uint64_t)(((f1[0] >> 15) & 0xffu) | (((f1[1] >> 15) & 0xffu) << 8)) << sh;
+                            s1_64[1] |= (uint64_t)(((f1[0] >> 23) & 0xffu) | (((f1[1] >> 23) & 0xffu) << 8)) << sh;
                         }
-                        if ((f2[0] | f2[1] | f2[2] | f2[3]) != 0u) {
-                            trw[h] = gather4(f2[0], f2[1], f2[2], f2[3], 8);
-                            s2w[1][h] = gather4(f2[0], f2[1], f2[2], f2[3], 24);
+                        if ((f2[0] | f2[1]) != 0u) {
+                            tr64 |= (uint64_t)(((f2[0] >> 8) & 0xffu) | (((f2[1] >> 8) & 0xffu) << 8)) << sh;
+                            s2_64[1] |= (uint64_t)((f2[0] >> 24) | ((f2[1] >> 24) << 8)) << sh;
                         }
+                        w0 = w1; w1 = w2; w2 = w3; w3 = w4;
                     }
+#pragma unroll
+                    for (int g = 0; g < 2; g++) {
+                        cvw[g][0] = (uint32_t)c64[g]; cvw[g][1] = (uint32_t)(c64[g] >> 32);
+                        s1w[g][0] = (uint32_t)s1_64[g]; s1w[g][1] = (uint32_t)(s1_64[g] >> 32);
+                        s2w[g][0] = (uint32_t)s2_64[g]; s2w[g][1] = (uint32_t)(s2_64[g] >> 32);
+                    }
+                    trw[0] = (uint32_t)tr64; trw[1] = (uint32_t)(tr64 >> 32);
                 } else slow = (nmw[0] & nmw[1]) != 0xffffffffu;           // some N within reach (all N: nothing to do)
             }
             // lanes with an N within reach (read ends, mostly), one at a time, all 32 lanes helping: lane j looks at bases
@@ -321,19 +331,13 @@ __global__ void __launch_bounds__(COV_THREADS, 2) scan_cov_kernel(const CovParam
             }
             *reinterpret_cast<uint4 *>(&G.pk[4 * lane]) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             *reinterpret_cast<uint2 *>(&G.nm[2 * lane]) = make_uint2(nmw[0], nmw[1]);
-            *reinterpret_cast<uint2 *>(&G.tr[2 * lane]) = make_uint2(trw[0], trw[1]);
 #pragma unroll
             for (int g = 0; g < 2; g++) {
                 *reinterpret_cast<uint2 *>(&G.cov[g][2 * lane]) = make_uint2(cvw[g][0], cvw[g][1]);
-                *reinterpret_cast<uint2 *>(&G.s1[g][2 * lane]) = make_uint2(s1w[g][0], s1w[g][1]);
-                *reinterpret_cast<uint2 *>(&G.s2[g][2 * lane]) = make_uint2(s2w[g][0], s2w[g][1]);
                 G.spill[g][lane + 1] = sp[g];
             }
             if (lane < 4) {
                 G.cov[0][COV_WORDS + lane] = 0u; G.cov[1][COV_WORDS + lane] = 0u;
-                G.s1[0][COV_WORDS + lane] = 0u; G.s1[1][COV_WORDS + lane] = 0u;
-                G.s2[0][COV_WORDS + lane] = 0u; G.s2[1][COV_WORDS + lane] = 0u;
-                G.tr[COV_WORDS + lane] = 0u;
                 // planes behind the region (a long k-mer that starts in the last chunk is compared against them)
                 const int64_t ax = a0 + COV_REGION + 32 * (int64_t)lane;
                 const bool ok = ax >= 0 && ax < total;
@@ -346,17 +350,20 @@ __global__ void __launch_bounds__(COV_THREADS, 2) scan_cov_kernel(const CovParam
         __syncwarp();
         // ---- phase 2a: spill of the previous chunk; special k-mers that start in my chunk ----
         bool deferred = false;
+        const uint32_t tr_next = __shfl_down_sync(TG_FULL_MASK, trw[0], 1);
 #pragma unroll
         for (int g = 0; g < 2; g++) {
             const uint32_t s_in = G.spill[g][lane];
             if (s_in) atomicOr(&G.cov[g][2 * lane], s_in);
-            const uint64_t X = (uint64_t)G.s1[g][2 * lane] | ((uint64_t)G.s1[g][2 * lane + 1] << 32);
+            // flag words of the neighbouring chunks.  What lies in front of the region is unknown: a flag at its very start
+            // may be overlapped from there, and only the warp-wide walk looks back -- all ones force it.
+            uint32_t prev = __shfl_up_sync(TG_FULL_MASK, s1w[g][1], 1), next = __shfl_down_sync(TG_FULL_MASK, s1w[g][0], 1);
+            if (lane == 0) prev = (a0 > 0) ? 0xffffffffu : 0u;
+            if (lane == 31) next = 0u;
+            const uint64_t X = (uint64_t)s1w[g][0] | ((uint64_t)s1w[g][1] << 32);
             if (X != 0ull) {
                 const int L = bord_len[g];
                 if (L > 0) {
-                    // (what lies in front of the region is unknown: a flag at its very start may be overlapped from there, and
-                    // only the warp-wide walk looks back)
-                    const uint32_t prev = lane ? G.s1[g][2 * lane - 1] : ((a0 > 0) ? 0xffffffffu : 0u), next = G.s1[g][2 * lane + 2];
                     const int conflict = (L == 6) ? smear_flags<6>(X, prev, next, &G.cov[g][2 * lane], 6)
                                                   : smear_flags<0>(X, prev, next, &G.cov[g][2 * lane], L);
                     if (conflict == 2) {
@@ -388,24 +395,24 @@ __global__ void __launch_bounds__(COV_THREADS, 2) scan_cov_kernel(const CovParam
                     // window-sized self-overlapping k-mers of several lengths: per occurrence
                     uint64_t rest = X;
                     while (rest) {
-                        const int x = lane * COV_CH + __ffsll((long long)rest) - 1;
+                        const int bit = __ffsll((long long)rest) - 1;
                         rest &= rest - 1;
                         for (int q = 0; q < S.n_bsk[g]; q++) {
                             const int k = S.bsk[g][q], len = S.len[k];
-                            if (!sm_kmer_at(G.pk, G.nm, x, S.pat[k], len)) continue;
-                            if (flags_near(G.s1[g], x, SC_W) || (x < SC_W - 1 && a0 > 0)) {
+                            if (!sm_kmer_at(G.pk, G.nm, lane * COV_CH + bit, S.pat[k], len)) continue;
+                            if (flags_near(X, prev, next, bit, SC_W)) {
                                 atomicOr(&G.defer[g], 1u << lane);
                                 deferred = true;
-                            } else cov_or(G.cov[g], x, len);
+                            } else cov_or(G.cov[g], lane * COV_CH + bit, len);
                         }
                     }
                 }
             }
             // long k-mers: their first 7 bases start at p and the continuation of some long k-mer at p + 7
-            const uint64_t S2 = (uint64_t)G.s2[g][2 * lane] | ((uint64_t)G.s2[g][2 * lane + 1] << 32);
+            const uint64_t S2 = (uint64_t)s2w[g][0] | ((uint64_t)s2w[g][1] << 32);
             if (S2 != 0ull) {
-                const uint64_t TR = (uint64_t)G.tr[2 * lane] | ((uint64_t)G.tr[2 * lane + 1] << 32);
-                uint64_t cand = S2 & ((TR >> SC_W) | ((uint64_t)G.tr[2 * lane + 2] << (64 - SC_W)));
+                const uint64_t TR = (uint64_t)trw[0] | ((uint64_t)trw[1] << 32);
+                uint64_t cand = S2 & ((TR >> SC_W) | ((uint64_t)(lane == 31 ? 0u : tr_next) << (64 - SC_W)));
                 while (cand) {
                     const int x = lane * COV_CH + __ffsll((long long)cand) - 1;
                     cand &= cand - 1;
@@ -434,8 +441,8 @@ __global__ void __launch_bounds__(COV_THREADS, 2) scan_cov_kernel(const CovParam
                 // lane c verifies the candidates of chunk c
                 uint64_t mine = 0ull;
                 if ((dmask >> lane) & 1u) {
-                    const uint32_t *fp = (blen > SC_W) ? G.s2[g] : G.s1[g];
-                    uint64_t fw = (uint64_t)fp[2 * lane] | ((uint64_t)fp[2 * lane + 1] << 32);
+                    uint64_t fw = (blen > SC_W) ? ((uint64_t)(g ? s2w[1][0] : s2w[0][0]) | ((uint64_t)(g ? s2w[1][1] : s2w[0][1]) << 32))
+                                                : ((uint64_t)(g ? s1w[1][0] : s1w[0][0]) | ((uint64_t)(g ? s1w[1][1] : s1w[0][1]) << 32));
                     while (fw) {
                         const int bit = __ffsll((long long)fw) - 1;
                         fw &= fw - 1;
@@ -497,28 +504,28 @@ __global__ void __launch_bounds__(COV_THREADS, 2) scan_cov_kernel(const CovParam
                 const uint32_t *cv = G.cov[g];
                 const int cnt = range_popc(cv, j0 + 1, j0 + w);
                 const uint32_t a0w = cv[2 * lane], a1w = cv[2 * lane + 1], a2w = cv[2 * lane + 2];
-                const uint32_t sa[2] = {__funnelshift_r(a0w, a1w, 1), __funnelshift_r(a1w, a2w, 1)};      // leaving bits
+                uint64_t sa = (uint64_t)__funnelshift_r(a0w, a1w, 1) | ((uint64_t)__funnelshift_r(a1w, a2w, 1) << 32);    // leaving bits
                 const int jb = j0 + w + 1;
                 const uint32_t b0w = cv[jb >> 5], b1w = cv[(jb >> 5) + 1], b2w = cv[(jb >> 5) + 2];
-                const uint32_t sb[2] = {__funnelshift_r(b0w, b1w, jb & 31), __funnelshift_r(b1w, b2w, jb & 31)};  // entering
+                uint64_t sb = (uint64_t)__funnelshift_r(b0w, b1w, jb & 31) | ((uint64_t)__funnelshift_r(b1w, b2w, jb & 31) << 32);  // entering
                 uint32_t cnt4 = (uint32_t)cnt * 0x01010101u;
                 uint8_t *dst = P.cnt[g] + a;
-#pragma unroll
+#pragma unroll 1
                 for (int q = 0; q < 4; q++) {
                     uint32_t o[4];
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
                         // 8 outputs per step: prefix popcounts of the entering and of the leaving byte
-                        const int g8 = 2 * q + h;
-                        const uint32_t bi = (sb[g8 >> 2] >> (8 * (g8 & 3))) & 0xffu, bo = (sa[g8 >> 2] >> (8 * (g8 & 3))) & 0xffu;
+                        const uint32_t bi = ((uint32_t)sb >> (8 * h)) & 0xffu, bo = ((uint32_t)sa >> (8 * h)) & 0xffu;
                         const uint2 A = *reinterpret_cast<const uint2 *>(lut + bi * 8), B = *reinterpret_cast<const uint2 *>(lut + bo * 8);
-                        const uint32_t lo = cnt4 + A.x - B.x;              // counts of outputs 8 g8 + 1 .. + 4 (exact mod 2^32)
-                        const uint32_t hi = cnt4 + A.y - B.y;              // counts of outputs 8 g8 + 5 .. + 8
+                        const uint32_t lo = cnt4 + A.x - B.x;              // counts of outputs + 1 .. + 4 (exact mod 2^32)
+                        const uint32_t hi = cnt4 + A.y - B.y;              // counts of outputs + 5 .. + 8
                         o[2 * h] = __byte_perm(lo, cnt4, 0x2104);
                         o[2 * h + 1] = __byte_perm(hi, lo, 0x2107);
                         cnt4 = __byte_perm(hi, 0u, 0x3333);
                     }
                     *reinterpret_cast<uint4 *>(dst + 16 * q) = make_uint4(o[0], o[1], o[2], o[3]);
+                    sa >>= 16; sb >>= 16;
                 }
             }
         }
