@@ -187,15 +187,15 @@ int tg_int_alu_peak(int iters, double *dpx_lane_ops_per_s, double *iadd_lane_ops
  * k-mer scan (tg_kmer.py)
  * ======================================================================================= */
 
-/* Device table for one k-mer list (KMER_LIST / KMER_LIST_REV / CANONICAL_STRINGS ...):
- * an Aho-Corasick automaton over the REVERSED k-mers (the kernels walk each chunk right to
- * left so that a match is reported at its start position), plus per-k-mer metadata.
- * Built on the host; upload the blob as is.  Limits: K <= 64 k-mers, length <= 32,
- * alphabet ACGT, <= 32 self-overlapping ("bordered") k-mers, < 4096 automaton states.
- * Replaces the per-k-mer re.finditer passes of tg_kmer.py:69,96,178. */
+/* Device table for one k-mer list with its KMER_ISSUBSTRING relation (the hits kernel): a lookup table over the 4^7
+ * windows of 7 bases whose 16-bit entries name the SET of plain k-mers starting there (an index into a table of 64-bit
+ * sets) and the special k-mer -- longer than 7 bases or self-overlapping -- that may start there; tables for windows cut
+ * short by an N; per-k-mer patterns, lengths and superstring sets.  tg_kmer_table_bytes() bytes, built on the host,
+ * uploaded as is.  Limits: K <= 64 k-mers, length <= 32, alphabet ACGT, <= 32 self-overlapping k-mers, <= 512 distinct
+ * sets.  Replaces the per-k-mer re.finditer passes of tg_kmer.py:178. */
 size_t tg_kmer_table_bytes(void);
 int tg_kmer_table_build(const char *kmers_concat, const int32_t *kmer_off, int K,
-                        const int32_t *issub_edges, const int32_t *issub_off, /* KMER_ISSUBSTRING CSR or NULL */
+                        const int32_t *issub_edges, const int32_t *issub_off, /* KMER_ISSUBSTRING in CSR form */
                         void *h_table);
 /* Coverage table for TWO k-mer lists (KMER_LIST + KMER_LIST_REV, tg_tel.py:160-161; CANONICAL_STRINGS +
  * CANONICAL_STRINGS_REV, tg_tel.py:262-263): a lookup table over the 4^7 windows of 7 bases whose 32-bit entries answer, for
@@ -239,15 +239,12 @@ int tg_scan_density(const uint32_t *d_pack2, const uint32_t *d_nmask, int64_t to
 
 /* get_nonoverlapping_kmer_hits(seq[lo:hi], KMER_LIST, KMER_ISSUBSTRING) (tg_kmer.py:173-230)
  * for a batch of slices: slice q = read d_slice_read[q], positions [d_slice_lo[q], d_slice_hi[q]).
- * d_work: tg_scan_hits_work_bytes(total slice bases) bytes of scratch.  Spans are appended to
- * d_span_* (slice, k, start, end relative to lo) in no particular order; *d_span_count
- * receives the number of spans (if it exceeds span_cap the extra spans were dropped and the
- * caller must retry with a larger buffer). */
-size_t tg_scan_hits_work_bytes(int64_t total_slice_bases, int n_slices);
+ * One warp per slice, no scratch in HBM.  Spans are appended to d_span_* (slice, k, start, end relative to lo) in no
+ * particular order; *d_span_count receives the number of spans (if it exceeds span_cap the extra spans were dropped and
+ * the caller must retry with a larger buffer). */
 int tg_scan_hits(const uint32_t *d_pack2, const uint32_t *d_nmask, const int64_t *d_base_off,
                  const int32_t *d_slice_read, const int32_t *d_slice_lo, const int32_t *d_slice_hi, int n_slices,
-                 const int64_t *d_slice_work_off, /* exclusive prefix sum of slice lengths padded to 64 */
-                 int64_t total_work_bases, const void *d_table, void *d_work,
+                 const void *d_table,
                  int32_t *d_span_slice, int32_t *d_span_k, int32_t *d_span_start, int32_t *d_span_end,
                  int64_t span_cap, unsigned long long *d_span_count, void *stream);
 

@@ -55,7 +55,7 @@ EXPORTS = ['tg_last_error', 'tg_version', 'tg_device_sm_count',
            'tg_nw_wave_scratch_bytes', 'tg_nw_wave_check', 'tg_nw_scores_wave', 'tg_nw_scores_wave32', 'tg_nw_generic_max_m',
            'tg_nw_scores_generic', 'tg_mt_shuffle', 'tg_dist_batch', 'tg_dist_batch_mt_work_bytes', 'tg_dist_epilogue', 'tg_wave_timing', 'tg_wave_timing_read', 'tg_int_alu_peak',
            'tg_kmer_table_bytes', 'tg_kmer_table_build', 'tg_kmer_table_pair_bytes', 'tg_kmer_table_build_pair', 'tg_scan_pack', 'tg_scan_basecount', 'tg_scan_orient',
-           'tg_scan_density', 'tg_scan_hits_work_bytes', 'tg_scan_hits',
+           'tg_scan_density', 'tg_scan_hits',
            'tg_cv_paint', 'tg_cv_density_boundary', 'tg_cv_lead_run', 'tg_cv_gather', 'tg_cv_denoise_tile', 'tg_cv_denoise',
            'tg_prefilter_tail_bytes', 'tg_prefilter_count']
 
@@ -94,9 +94,7 @@ def load():
     L.tg_kmer_table_pair_bytes.restype = sz
     L.tg_scan_orient.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp]
     L.tg_scan_density.argtypes = [vp, vp, i64, vp, i32, vp, vp, vp]
-    L.tg_scan_hits_work_bytes.restype = sz
-    L.tg_scan_hits_work_bytes.argtypes = [i64, i32]
-    L.tg_scan_hits.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, i64, vp, vp, vp, vp, vp, vp, i64, vp, vp]
+    L.tg_scan_hits.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, i64, vp, vp]
     L.tg_cv_paint.argtypes = [vp, vp, vp, vp, i32, vp, i32, i32, vp, vp]
     L.tg_cv_density_boundary.argtypes = [vp, vp, vp, vp, i32, C.c_char_p, i32, i32, C.c_double, i32, i32, vp, vp, vp]
     L.tg_cv_lead_run.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp, vp]

@@ -1,57 +1,28 @@
-// k-mer scan kernels for sm_100a (reference: source/tg_kmer.py).
+// k-mer scan kernels for sm_100a (reference: source/tg_kmer.py); the coverage kernels live in tg_cov.cu.
 //
-//   pack_kernel        ASCII -> 2-bit codes + N-mask bit plane (the HBM layout of the reads)
-//   orient_kernel      reverse complement of flagged reads in the packed domain (tg_tel.py:265-266)
-//   scan_cov_kernel    union coverage of all k-mers of TWO k-mer lists in one pass:
-//                        MODE_COUNT   -> get_telomere_base_count   (tg_kmer.py:93-102)
-//                        MODE_DENSITY -> get_telomere_kmer_density (tg_kmer.py:66-90), uint8 window counts
-//   hits_*_kernel      get_nonoverlapping_kmer_hits (tg_kmer.py:173-230)
+//   pack_kernel     ASCII -> 2-bit codes + N-mask bit plane (the HBM layout of the reads)
+//   orient_kernel   reverse complement of flagged reads in the packed domain (tg_tel.py:265-266), word parallel
+//   hits_kernel     get_nonoverlapping_kmer_hits (tg_kmer.py:173-230), one warp per slice, fused: nothing but the packed
+//                   bases is read from HBM and nothing but the spans is written
 //
-// Matching: one Aho-Corasick automaton per k-mer list, built over the REVERSED k-mers.  A thread walks
-// its chunk of positions right to left (after max_len-1 warm-up symbols), so the automaton reports at
-// position p exactly the k-mers that START at p.  re.finditer's leftmost-non-overlapping rule only
-// differs from "all occurrences" for k-mers that can overlap themselves ("bordered"); their candidate
-// starts go to a bitmap that one lane per k-mer resolves greedily, left to right.  Coverage tiles are
-// independent (a chain of overlapping candidates that crosses a tile start is walked back through global
-// memory, exactly); the hits kernel walks the tiles of a slice in order and carries the blocking position.
-#include "tg_common.cuh"
+// hits_kernel works on SETS of k-mers (64-bit masks, K <= 64) per position, in the closed form of SURVEY 9-E:
+//   R(p)  k-mers with a selected raw match starting at p: a 7-base window lookup names the set of plain k-mers; special
+//         k-mers (self-overlapping: re.finditer's greedy rule; longer than the window) are flagged by the lookup and verified
+//   C(q)  k-mers whose selected match covers q            = OR_d R(q - d) & {len > d}
+//   S(p)  survivors: k in R(p) unless a superstring k-mer covers some position of [p, p + len_k)   (tg_kmer.py:187-202)
+//   P(x)  k-mers with a surviving match ending at x; block starts Start(x) = S(x) & ~P(x), chain ends End(x) = P(x) & ~S(x)
+//         (abutting matches of one k-mer collapse, tg_kmer.py:206-212)
+//   sweep: the blocks opened at the latest block-start position stay open until their chain ends or the next block start
+//         of any k-mer truncates them (tg_kmer.py:216-228); every closing emits one span.
+// The warp streams over its slice in tiles of 128 positions; R / S, C and P live in shared-memory rings, S and the events
+// lag one maximal k-mer length behind R so that nothing is computed twice.
+#include "tg_scan_common.cuh"
 #include <string.h>
-#include <vector>
-#include <queue>
-#include <string>
+#include <map>
 
 namespace {
 
-constexpr int SC_MAXK = 128;               // two lists of up to 64 k-mers in one automaton
-constexpr int SC_MAXLIST = 64;
-constexpr int SC_MAXLEN = 32;
-constexpr int SC_MAXSTATES = 4095;
-constexpr int SC_MAXBORD = 32;
-constexpr uint32_t SC_BORD_FLAG = 0x1000;   // transition entry: next state has self-overlapping k-mer outputs
-constexpr uint32_t SC_OUT_FLAG = 0x2000;    // transition entry: next state has any output
-
-// One automaton for one k-mer list (hits) or for two lists at once ("groups" 0 and 1: KMER_LIST and
-// KMER_LIST_REV, or CANONICAL_STRINGS and their reverse complements).
-struct KmerTable {
-    int32_t K, n_states, max_len, n_bord;   // K = k-mers of all groups
-    int32_t n_groups, KA, pad_[2];          // KA = k-mers of group 0 (they come first)
-    int32_t len[SC_MAXK];
-    int32_t bord_kmer[SC_MAXBORD];          // k-mer index of bordered slot b
-    int32_t bord_len[SC_MAXBORD];
-    int32_t bord_group[SC_MAXBORD];
-    uint64_t bord_pat[SC_MAXBORD];          // the k-mer, 2 bits per base, first base in the low bits
-    uint64_t super[SC_MAXLIST];             // KMER_ISSUBSTRING[k] as a bit mask (group 0 only)
-    uint64_t lengt[SC_MAXLEN];              // lengt[d] = group-0 k-mers with len > d
-    uint64_t bord_mask;                     // bordered group-0 k-mers
-    uint64_t has_super_mask;                // group-0 k-mers with a non-empty super[]
-    // transition entry: bits 0-11 next state | SC_BORD_FLAG | SC_OUT_FLAG | byte 2 = longest NON-bordered group-0 k-mer
-    // starting at the next state | byte 3 = same for group 1 (so the common case needs no second table lookup)
-    uint32_t trans[(SC_MAXSTATES + 1) * 4];
-    uint32_t out_bord[SC_MAXSTATES + 1];    // bordered slots starting here
-    uint64_t out_mask[SC_MAXSTATES + 1];    // group-0 k-mers starting here
-};
-
-// ---- packed read access ---------------------------------------------------------------------------
+// ---- pack / orient ----------------------------------------------------------------------------------------------
 // codes: A=0 C=1 T=2 G=3 ((ascii >> 1) & 3); complement = code ^ 2.
 __device__ __forceinline__ uint32_t ascii_code(uint32_t c) { return (c >> 1) & 3u; }
 __device__ __forceinline__ bool ascii_is_acgt(uint32_t c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
@@ -93,9 +64,8 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint8_t *__restrict__ a
     }
 }
 
-__device__ __forceinline__ uint32_t base_code(const uint32_t *pack2, int64_t b) { return (pack2[b >> 4] >> ((b & 15) * 2)) & 3u; }
-__device__ __forceinline__ uint32_t base_isn(const uint32_t *nmask, int64_t b) { return (nmask[b >> 5] >> (b & 31)) & 1u; }
-
+// 32 output positions per thread: the 32 source bases [L - 32 - q0, L - q0) as one 64-bit word, reversed pair-wise and
+// complemented (code ^ 2); positions past the read stay N.
 __global__ void __launch_bounds__(256) orient_kernel(const uint32_t *__restrict__ pack2, const uint32_t *__restrict__ nmask,
                                                      const int64_t *__restrict__ base_off, const int32_t *__restrict__ len,
                                                      const uint8_t *__restrict__ flip, int n_reads,
@@ -112,352 +82,324 @@ __global__ void __launch_bounds__(256) orient_kernel(const uint32_t *__restrict_
             continue;
         }
         const int64_t ro = base_off[r];
-        const int64_t rel = b0 - ro;
         const int L = len[r];
-        uint32_t p[2] = {0u, 0u}, m = 0u;
-        for (int i = 0; i < 32; i++) {
-            const int64_t q = rel + i;               // oriented position
-            if (q < L) {
-                const int64_t src = ro + (L - 1 - q);
-                const uint32_t isn = base_isn(nmask, src);
-                p[i >> 4] |= (isn ? 0u : (base_code(pack2, src) ^ 2u)) << ((i & 15) * 2);
-                m |= isn << i;
-            } else m |= 1u << i;
+        const int s0 = L - 32 - (int)(b0 - ro);              // first source position (may be negative: outputs past the read)
+        uint64_t bases = 0ull;
+        uint32_t nb = 0xffffffffu;
+        if (s0 > -32) {
+            const int sh = s0 < 0 ? -s0 : 0;                 // source positions below 0 do not exist
+            bases = sc_bases64(pack2, ro + s0 + sh) << (2 * sh);
+            nb = (sc_nbits32(nmask, ro + s0 + sh) << sh) | ((1u << sh) - 1u);
         }
-        pack2_out[g * 2] = p[0];
-        pack2_out[g * 2 + 1] = p[1];
-        nmask_out[g] = m;
+        // reverse the order of the 2-bit codes: bit reversal, then swap the two bits of every code back
+        uint64_t rv = ((uint64_t)__brev((uint32_t)bases) << 32) | (uint64_t)__brev((uint32_t)(bases >> 32));
+        rv = ((rv >> 1) & 0x5555555555555555ull) | ((rv & 0x5555555555555555ull) << 1);
+        const uint32_t nr = __brev(nb);
+        // spread the N bits to both bits of their code, clear those codes
+        uint64_t x = (uint64_t)(~nr);
+        x = (x | (x << 16)) & 0x0000ffff0000ffffull;
+        x = (x | (x << 8)) & 0x00ff00ff00ff00ffull;
+        x = (x | (x << 4)) & 0x0f0f0f0f0f0f0f0full;
+        x = (x | (x << 2)) & 0x3333333333333333ull;
+        x = (x | (x << 1)) & 0x5555555555555555ull;
+        rv = (rv ^ 0xaaaaaaaaaaaaaaaaull) & (x | (x << 1));
+        pack2_out[g * 2] = (uint32_t)rv;
+        pack2_out[g * 2 + 1] = (uint32_t)(rv >> 32);
+        nmask_out[g] = nr;
     }
 }
 
-// ---- shared pieces of the tile kernels -----------------------------------------------------------
-__device__ __forceinline__ void smem_byte_max(uint8_t *arr, int idx, uint32_t val)
-{
-    uint32_t *word = reinterpret_cast<uint32_t *>(arr + (idx & ~3));
-    const int sh = (idx & 3) * 8;
-    uint32_t old = *word;
-    for (;;) {
-        if (((old >> sh) & 0xffu) >= val) return;
-        const uint32_t assumed = old;
-        old = atomicCAS(word, assumed, (assumed & ~(0xffu << sh)) | (val << sh));
-        if (old == assumed) return;
-    }
-}
+// ---- non-overlapping hits -----------------------------------------------------------------------------------------
+constexpr int32_t HIT_MAGIC = 0x48543032;            // "HT02"
+constexpr int HIT_MAXSETS = 512;                      // distinct sets of plain k-mers a window can name
+constexpr int HIT_SHORT_N = 5464;                     // sum of 4^d, d = 1 .. 6, rounded up
+__host__ __device__ constexpr int HIT_SHORT_OFF(int d) { return ((1 << (2 * d)) - 4) / 3; }
+constexpr int HIT_SLOT_MANY = 63;
+constexpr int HIT_SHORT_LEN = 8;                      // k-mers up to this length are covered by the fixed 8-step gathers
 
-// Device-side view of one automaton held in shared memory.
-struct SmemTable {
-    const uint32_t *trans;
-    const uint32_t *out_bord;
-    const uint64_t *out_mask;     // only in hits mode
-    int max_len, n_bord;
+// table entry (16 bits): bits 0-8 set id, bits 9-14 special slot (HIT_SLOT_MANY: several), bit 15 "a special k-mer may start here"
+struct HitTable {
+    int32_t magic, K, n_sets, n_bord, max_len, n_spec, pad_[2];
+    uint64_t pat[SC_MAXLIST];
+    int32_t len[SC_MAXLIST];
+    int32_t kind[SC_MAXLIST];                 // SC_PLAIN / SC_SPECIAL / SC_BORDERED
+    int32_t bslot[SC_MAXLIST];                // index among the self-overlapping k-mers, -1 otherwise
+    int32_t spec_idx[SC_MAXLIST];             // the n_spec special k-mers (entry slot -> k-mer)
+    uint64_t sup[SC_MAXLIST];                 // KMER_ISSUBSTRING[k] as a bit set
+    uint64_t lengt[SC_MAXLEN];                // lengt[d] = k-mers longer than d
+    uint64_t bylen[SC_MAXLEN + 1];            // bylen[l] = k-mers of length l
+    uint64_t longmask;                        // k-mers longer than HIT_SHORT_LEN
+    uint64_t sets[HIT_MAXSETS];
+    uint16_t tab_short[HIT_SHORT_N];
+    uint16_t tab[SC_TAB];
 };
 
-__device__ __forceinline__ uint8_t *carve(uint8_t *&p, size_t bytes)
-{
-    uint8_t *r = p;
-    p += (bytes + 15) & ~(size_t)15;
-    return r;
-}
-
-__device__ SmemTable load_table(const KmerTable *__restrict__ T, uint8_t *&sp, bool want_mask)
-{
-    const int ns = T->n_states;
-    uint32_t *tr = reinterpret_cast<uint32_t *>(carve(sp, (size_t)ns * 4 * sizeof(uint32_t)));
-    uint32_t *ob = reinterpret_cast<uint32_t *>(carve(sp, (size_t)ns * sizeof(uint32_t)));
-    uint64_t *om = want_mask ? reinterpret_cast<uint64_t *>(carve(sp, (size_t)ns * sizeof(uint64_t))) : nullptr;
-    for (int i = threadIdx.x; i < ns * 4; i += blockDim.x) tr[i] = T->trans[i];
-    for (int i = threadIdx.x; i < ns; i += blockDim.x) {
-        ob[i] = T->out_bord[i];
-        if (want_mask) om[i] = T->out_mask[i];
-    }
-    SmemTable S;
-    S.trans = tr; S.out_bord = ob; S.out_mask = om;
-    S.max_len = T->max_len; S.n_bord = T->n_bord;
-    return S;
-}
-
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
-{
-    uint32_t d;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
-    return d;
-}
-
-// ---- non-overlapping hits -------------------------------------------------------------------------
-constexpr int HIT_THREADS = 128;
-constexpr int HIT_CH = 16;
-constexpr int HIT_TILE = HIT_THREADS * HIT_CH;      // 2048
-constexpr int HIT_HALO = 32;
-constexpr int HIT_SPAN = HIT_TILE + 2 * HIT_HALO;   // hm / C cover [t0 - 32, t0 + TILE + 32)
-constexpr int HIT_STAGE = HIT_TILE + 2 * HIT_HALO;  // staged bases [t0, t0 + TILE + 64)
+constexpr int HIT_WARPS = 24;                         // warps per CTA (one CTA per SM, they share the table)
+constexpr int HIT_T = 128;                            // positions per tile
+constexpr int HIT_CAP = 256;                          // ring capacity >= HIT_T + 2 * SC_MAXLEN (+ slack), power of two
+constexpr int HIT_BUF = 64;                           // spans buffered per warp before they go to global memory
 
 struct HitParams {
     const uint32_t *pack2, *nmask;
     const int64_t *base_off;
     const int32_t *slice_read, *slice_lo, *slice_hi;
     int n_slices;
-    const int64_t *work_off;
-    const KmerTable *tab;
-    uint64_t *S;                 // survivors per work position
-    uint32_t *B;                 // block-start bitmap per work position
-    int64_t total_work;
+    const HitTable *tab;
     int32_t *span_slice, *span_k, *span_start, *span_end;
     long long span_cap;
     unsigned long long *span_count;
     unsigned int *next_slice;
 };
 
-// H1: selected raw matches -> superstring deletion -> survivors S[x] (tg_kmer.py:175-202)
-__global__ void __launch_bounds__(HIT_THREADS) hits_survivors_kernel(const HitParams P)
+struct alignas(16) HitWarpSmem {
+    unsigned long long rs[HIT_CAP];           // R(p), overwritten by S(p) once decided
+    unsigned long long c[HIT_CAP];            // C(q)
+    unsigned long long pe[HIT_CAP];           // P(x)
+    uint32_t pk[HIT_T / 16 + 4];              // staged bases [rA, rA + T + 64)
+    uint32_t nm[HIT_T / 32 + 4];
+    int32_t blocked[SC_MAXBORD];              // greedy state of every self-overlapping k-mer
+    int32_t buf[HIT_BUF][3];                  // (k, start, end)
+};
+
+struct alignas(16) HitSmem {
+    uint16_t tab[SC_TAB];
+    unsigned long long sets[HIT_MAXSETS];
+    unsigned long long sup[SC_MAXLIST], lengt[SC_MAXLEN], bylen[SC_MAXLEN + 1], pat[SC_MAXLIST];
+    uint8_t len[SC_MAXLIST], kind[SC_MAXLIST], spec[SC_MAXLIST];
+    int8_t bslot[SC_MAXLIST];
+    uint8_t bord_k[SC_MAXBORD];
+    HitWarpSmem w[HIT_WARPS];
+};
+
+__device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int l)
 {
-    extern __shared__ __align__(16) uint8_t smem[];
-    uint8_t *sp = smem;
-    SmemTable T = load_table(P.tab, sp, true);
-    uint32_t *s_pack = reinterpret_cast<uint32_t *>(carve(sp, HIT_STAGE / 16 * 4));
-    uint32_t *s_mask = reinterpret_cast<uint32_t *>(carve(sp, HIT_STAGE / 32 * 4));
-    unsigned long long *s_hm = reinterpret_cast<unsigned long long *>(carve(sp, (size_t)HIT_SPAN * 8));   // index = x - t0 + HALO
-    uint32_t *s_sup = reinterpret_cast<uint32_t *>(carve(sp, (size_t)(HIT_SPAN / 32 + 1) * 4));             // hm has a superstring k-mer
-    uint32_t *s_bm = reinterpret_cast<uint32_t *>(carve(sp, (size_t)max(T.n_bord, 1) * ((HIT_TILE + HIT_HALO) / 32) * 4));
-    __shared__ int s_blocked[SC_MAXBORD];
-    __shared__ int s_any[SC_MAXBORD];
-    __shared__ unsigned long long s_shalo[HIT_HALO];
-    __shared__ unsigned long long s_super[SC_MAXLIST], s_lengt[SC_MAXLEN];
-    __shared__ int s_len[SC_MAXLIST];
-    __shared__ unsigned int s_slice;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int BMW = (HIT_TILE + HIT_HALO) / 32;     // bitmap words per bordered slot: positions [t0, t0 + TILE + 32)
-    if (tid < SC_MAXLIST) { s_super[tid] = P.tab->super[tid]; s_len[tid] = P.tab->len[tid]; }
-    if (tid < SC_MAXLEN) s_lengt[tid] = P.tab->lengt[tid];
-    const unsigned long long has_super = P.tab->has_super_mask;
-    const int max_len = T.max_len;
+    return ((unsigned long long)__shfl_sync(TG_FULL_MASK, (uint32_t)(v >> 32), l) << 32) | __shfl_sync(TG_FULL_MASK, (uint32_t)v, l);
+}
+
+// does k-mer (pat, len) start at tile position u?  (staged planes; N anywhere in the span = no)
+__device__ __forceinline__ bool hit_kmer_at(const uint32_t *pk, const uint32_t *nm, int u, unsigned long long pat, int len)
+{
+    const int pw = u >> 4, sh = (u & 15) * 2;
+    unsigned long long bases = ((unsigned long long)pk[pw] | ((unsigned long long)pk[pw + 1] << 32)) >> sh;
+    if (sh) bases |= (unsigned long long)pk[pw + 2] << (64 - sh);
+    const uint32_t nbits = __funnelshift_r(nm[u >> 5], nm[(u >> 5) + 1], u & 31);
+    const uint32_t lm = (len >= 32) ? 0xffffffffu : ((1u << len) - 1u);
+    const unsigned long long m = (len >= 32) ? ~0ull : ((1ull << (2 * len)) - 1ull);
+    return (nbits & lm) == 0u && ((bases ^ pat) & m) == 0ull;
+}
+
+// the span buffer of a warp goes to global memory: one atomic for the warp
+__device__ __forceinline__ void flush_spans(const HitParams &P, HitWarpSmem &W, int q, int n_buf, int lane)
+{
+    unsigned long long base = 0ull;
+    if (lane == 0) base = atomicAdd(P.span_count, (unsigned long long)n_buf);
+    base = shfl64(base, 0);
+    __syncwarp();
+    for (int j = lane; j < n_buf; j += 32)
+        if ((long long)(base + j) < P.span_cap) {
+            P.span_slice[base + j] = q; P.span_k[base + j] = W.buf[j][0];
+            P.span_start[base + j] = W.buf[j][1]; P.span_end[base + j] = W.buf[j][2];
+        }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(HIT_WARPS * 32, 1) hits_kernel(const HitParams P)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    HitSmem &S = *reinterpret_cast<HitSmem *>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    HitWarpSmem &W = S.w[warp];
+    const HitTable *__restrict__ T = P.tab;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(T->tab);
+        uint4 *dst = reinterpret_cast<uint4 *>(S.tab);
+        for (int i = threadIdx.x; i < SC_TAB / 8; i += blockDim.x) dst[i] = src[i];
+        for (int i = threadIdx.x; i < HIT_MAXSETS; i += blockDim.x) S.sets[i] = T->sets[i];
+        if (threadIdx.x < SC_MAXLIST) {
+            const int k = threadIdx.x;
+            S.sup[k] = T->sup[k]; S.pat[k] = T->pat[k]; S.len[k] = (uint8_t)T->len[k]; S.kind[k] = (uint8_t)T->kind[k];
+            S.spec[k] = (uint8_t)T->spec_idx[k]; S.bslot[k] = (int8_t)T->bslot[k];
+            if (k < T->K && T->bslot[k] >= 0) S.bord_k[T->bslot[k]] = (uint8_t)k;
+        }
+        if (threadIdx.x < SC_MAXLEN) S.lengt[threadIdx.x] = T->lengt[threadIdx.x];
+        if (threadIdx.x <= SC_MAXLEN) S.bylen[threadIdx.x] = T->bylen[threadIdx.x];
+    }
     __syncthreads();
-    unsigned long long m_sup = 0ull;                     // k-mers that are a superstring of some other k-mer
-    for (int k = 0; k < SC_MAXLIST; k++) m_sup |= s_super[k];
+    const int n_bord = T->n_bord, n_spec = T->n_spec, M = T->max_len;
+    const unsigned long long longmask = T->longmask;
+    unsigned long long lg8[HIT_SHORT_LEN];
+#pragma unroll
+    for (int d = 0; d < HIT_SHORT_LEN; d++) lg8[d] = S.lengt[d];
 
     for (;;) {
-        __syncthreads();
-        if (tid == 0) s_slice = atomicAdd(P.next_slice, 1u);
-        __syncthreads();
-        const int q = (int)s_slice;
+        int q = 0;
+        if (lane == 0) q = (int)atomicAdd(P.next_slice, 1u);
+        q = __shfl_sync(TG_FULL_MASK, q, 0);
         if (q >= P.n_slices) break;
-        const int r = P.slice_read[q];
-        const int lo = P.slice_lo[q], hi = P.slice_hi[q];
-        const int len = hi - lo;
-        const int64_t rbase = P.base_off[r];
-        const int64_t gbase = rbase + lo;                        // absolute base index of slice position 0
-        const int64_t woff = P.work_off[q];
-        const int wlen = (int)(P.work_off[q + 1] - woff);        // padded to 64
-        const int n_tiles = (wlen + HIT_TILE - 1) / HIT_TILE;
-        if (tid < SC_MAXBORD) s_blocked[tid] = 0;
-        for (int i = tid; i < HIT_HALO; i += HIT_THREADS) { s_hm[i] = 0ull; s_shalo[i] = 0ull; }   // left halos of the first tile
-
+        const int len = P.slice_hi[q] - P.slice_lo[q];
+        const int64_t gbase = P.base_off[P.slice_read[q]] + P.slice_lo[q];      // absolute base of slice position 0
+        __syncwarp();
+        for (int i = lane; i < HIT_CAP; i += 32) { W.rs[i] = 0ull; W.c[i] = 0ull; W.pe[i] = 0ull; }
+        if (lane < SC_MAXBORD) W.blocked[lane] = 0;
+        unsigned long long open = 0ull;                  // blocks opened at s_open that are still running (warp uniform)
+        int s_open = 0, n_buf = 0;
+        const int n_tiles = (len + 1 + M + HIT_T - 1) / HIT_T;
         for (int tile = 0; tile < n_tiles; tile++) {
-            const int t0 = tile * HIT_TILE;                     // slice-relative
-            __syncthreads();
-            // stage slice positions [t0, t0 + STAGE): unaligned window of the read's packed planes, clipped to the slice
-            for (int wq = tid; wq < HIT_STAGE / 32; wq += HIT_THREADS) {
-                const int x0 = t0 + wq * 32;
-                uint32_t m = 0xffffffffu, a = 0u, b = 0u;
+            const int rA = tile * HIT_T;
+            __syncwarp();
+            // ---- stage the planes of slice positions [rA, rA + T + 64): an unaligned window, clipped to the slice ----
+            if (lane < HIT_T / 16 + 4) {
+                const int x0 = rA + 16 * lane;
+                uint32_t v = 0u;
                 if (x0 < len) {
                     const int64_t g = gbase + x0;
-                    const int64_t mw = g >> 5;
-                    const int msh = (int)(g & 31);
-                    const uint64_t mm = (uint64_t)P.nmask[mw] | ((uint64_t)P.nmask[mw + 1] << 32);
-                    m = (uint32_t)(mm >> msh);
-                    const int64_t pw = g >> 4;
-                    const int sh = (int)(g & 15) * 2;
-                    const uint32_t w0 = P.pack2[pw], w1 = P.pack2[pw + 1], w2 = P.pack2[pw + 2];
-                    a = sh ? ((w0 >> sh) | (w1 << (32 - sh))) : w0;
-                    b = sh ? ((w1 >> sh) | (w2 << (32 - sh))) : w1;
+                    v = __funnelshift_r(P.pack2[g >> 4], P.pack2[(g >> 4) + 1], (int)(g & 15) * 2);
+                }
+                W.pk[lane] = v;
+            } else if (lane >= 16 && lane < 16 + HIT_T / 32 + 4) {
+                const int j = lane - 16, x0 = rA + 32 * j;
+                uint32_t m = 0xffffffffu;
+                if (x0 < len) {
+                    const int64_t g = gbase + x0;
+                    m = __funnelshift_r(P.nmask[g >> 5], P.nmask[(g >> 5) + 1], (int)(g & 31));
                     if (x0 + 32 > len) m |= ~((1u << (len - x0)) - 1u);
                 }
-                s_mask[wq] = m; s_pack[wq * 2] = a; s_pack[wq * 2 + 1] = b;
+                W.nm[j] = m;
             }
-            for (int i = tid; i < T.n_bord * BMW; i += HIT_THREADS) s_bm[i] = 0u;
-            if (tid < SC_MAXBORD) s_any[tid] = 0;
-            __syncthreads();
-
-            // ---- automaton over [t0, t0 + TILE + HALO): hm = all k-mers starting at x ----
-            for (int pass = 0; pass < 2; pass++) {
-                int c0;
-                if (pass == 0) c0 = tid * HIT_CH;
-                else { if (tid >= HIT_HALO / HIT_CH) break; c0 = HIT_TILE + tid * HIT_CH; }
-                uint32_t state = 0;
-                for (int x = c0 + HIT_CH + max_len - 2; x >= c0; x--) {
-                    uint32_t e = 0u;
-                    if (x < HIT_STAGE) {
-                        const uint32_t isn = (s_mask[x >> 5] >> (x & 31)) & 1u;
-                        const uint32_t code = (s_pack[x >> 4] >> ((x & 15) * 2)) & 3u;
-                        e = isn ? 0u : T.trans[state * 4 + code];
-                    }
-                    state = e & 0xfffu;
-                    if (x < c0 + HIT_CH) {
-                        unsigned long long hm = 0ull;
-                        if (e & SC_OUT_FLAG) {
-                            hm = T.out_mask[state];
-                            uint32_t ob = (e & SC_BORD_FLAG) ? T.out_bord[state] : 0u;
-                            while (ob) {
-                                const int b = __ffs(ob) - 1;
-                                ob &= ob - 1;
-                                atomicOr(&s_bm[b * BMW + (x >> 5)], 1u << (x & 31));
-                                s_any[b] = 1;
-                            }
-                        }
-                        s_hm[HIT_HALO + x] = hm;
-                    }
+            __syncwarp();
+            // ---- stage A: R(pos) for the T new positions; candidates of self-overlapping k-mers go to ballots ----
+            uint32_t cm[HIT_T / 32];                     // per sub-tile: which self-overlapping k-mers may start at my position
+#pragma unroll
+            for (int i = 0; i < HIT_T / 32; i++) {
+                const int u = 32 * i + lane, pos = rA + u;
+                const uint32_t nwin = __funnelshift_r(W.nm[u >> 5], W.nm[(u >> 5) + 1], u & 31) & ((1u << SC_W) - 1u);
+                const uint32_t win = __funnelshift_r(W.pk[u >> 4], W.pk[(u >> 4) + 1], 2 * (u & 15)) & (uint32_t)(SC_TAB - 1);
+                uint32_t e = 0u;
+                if (nwin == 0u) e = S.tab[win];
+                else if (!(nwin & 1u)) {
+                    const int d = __ffs(nwin) - 1;
+                    e = __ldg(T->tab_short + HIT_SHORT_OFF(d) + (win & ((1u << (2 * d)) - 1u)));
                 }
-            }
-            __syncthreads();
-
-            // ---- greedy resolution of bordered k-mers (one warp per k-mer); unselected candidates leave hm ----
-            for (int b = warp; b < T.n_bord; b += HIT_THREADS / 32) {
-                if (!s_any[b]) continue;
-                const int blen = P.tab->bord_len[b];
-                const unsigned long long kbit = 1ull << P.tab->bord_kmer[b];
-                int blocked = s_blocked[b];
-                int carry = -1;
-                for (int ch = 0; ch < BMW; ch += 32) {
-                    const uint32_t mine = (ch + lane < BMW) ? s_bm[b * BMW + ch + lane] : 0u;
-                    uint32_t nz = __ballot_sync(TG_FULL_MASK, mine != 0u);
-                    while (nz) {
-                        const int l = __ffs(nz) - 1;
-                        nz &= nz - 1;
-                        const int wd = ch + l;
-                        if (wd >= HIT_TILE / 32 && carry < 0) carry = blocked;       // state at the tile boundary
-                        uint32_t word = __shfl_sync(TG_FULL_MASK, mine, l);
-                        while (word) {
-                            const int bit = __ffs(word) - 1;
-                            word &= word - 1;
-                            const int x = wd * 32 + bit;
-                            const int p = t0 + x;
-                            if (p >= blocked) blocked = p + blen;
-                            else if (lane == 0) atomicAnd(&s_hm[HIT_HALO + x], ~kbit);
+                unsigned long long r = S.sets[e & (HIT_MAXSETS - 1)];
+                uint32_t cmask = 0u;
+                if (e & 0x8000u) {
+                    const int slot = (e >> 9) & 63;
+                    const int s_lo = (slot == HIT_SLOT_MANY) ? 0 : slot, s_hi = (slot == HIT_SLOT_MANY) ? n_spec : slot + 1;
+                    for (int s = s_lo; s < s_hi; s++) {
+                        const int k = S.spec[s], kl = S.len[k];
+                        // (a k-mer that fits the window and is named alone is decided by the entry)
+                        if ((kl > SC_W || slot == HIT_SLOT_MANY || nwin != 0u) && !hit_kmer_at(W.pk, W.nm, u, S.pat[k], kl)) continue;
+                        if (S.bslot[k] >= 0) cmask |= 1u << S.bslot[k];
+                        else {
+                            r |= 1ull << k;
+                            for (int d = HIT_SHORT_LEN; d < kl; d++) atomicOr(&W.c[(pos + d) & (HIT_CAP - 1)], 1ull << k);
                         }
                     }
                 }
+                cm[i] = cmask;
+                W.rs[pos & (HIT_CAP - 1)] = r;
+            }
+            // ---- self-overlapping k-mers: re.finditer's rule, left to right, the whole warp in lock step ----
+            if (__any_sync(TG_FULL_MASK, (cm[0] | cm[1] | cm[2] | cm[3]) != 0u)) {
                 __syncwarp();
-                if (lane == 0) s_blocked[b] = carry < 0 ? blocked : carry;
-            }
-            __syncthreads();
-
-            // ---- bitmap of positions whose selected matches include a superstring k-mer ----
-            for (int i = tid; i < HIT_SPAN; i += HIT_THREADS) {
-                const uint32_t bal = __ballot_sync(TG_FULL_MASK, (s_hm[i] & m_sup) != 0ull);
-                if (lane == 0) s_sup[i >> 5] = bal;
-            }
-            if (tid == 0) s_sup[HIT_SPAN / 32] = 0u;
-            __syncthreads();
-
-            // ---- survivors: drop (k, x) if a selected match of a superstring k-mer overlaps [x, x + len_k) ----
-#pragma unroll 1
-            for (int it = 0; it < HIT_CH; it++) {
-                const int x = tid + it * HIT_THREADS;
-                unsigned long long hm = s_hm[HIT_HALO + x];
-                unsigned long long cand = hm & has_super;
-                while (cand) {
-                    const int k = __ffsll((long long)cand) - 1;
-                    cand &= cand - 1;
-                    const int lk = s_len[k];
-                    // candidates s' in [x - max_len + 1, x + lk - 1] (indices shifted by HALO)
-                    const int ib = HIT_HALO + x - max_len + 1, ie = HIT_HALO + x + lk - 1;     // inclusive
-                    unsigned long long cover = 0ull;
-                    for (int wd = ib >> 5; wd <= (ie >> 5); wd++) {
-                        uint32_t v = s_sup[wd];
-                        if (wd == (ib >> 5)) v &= 0xffffffffu << (ib & 31);
-                        if (wd == (ie >> 5)) v &= 0xffffffffu >> (31 - (ie & 31));
-                        while (v) {
-                            const int i = wd * 32 + __ffs(v) - 1;
-                            v &= v - 1;
-                            const int d = HIT_HALO + x - i;                                    // x - s'
-                            unsigned long long m = s_hm[i];
-                            if (d > 0) m &= s_lengt[d];                                        // must reach position x
-                            cover |= m;
+                for (int b = 0; b < n_bord; b++) {
+                    const int k = S.bord_k[b], kl = S.len[k];
+                    int blocked = W.blocked[b];
+#pragma unroll
+                    for (int i = 0; i < HIT_T / 32; i++) {
+                        uint32_t cand = __ballot_sync(TG_FULL_MASK, (cm[i] >> b) & 1u), sel = 0u;
+                        while (cand) {
+                            const int bit = __ffs(cand) - 1;
+                            cand &= cand - 1;
+                            const int pos = rA + 32 * i + bit;
+                            if (pos >= blocked) { blocked = pos + kl; sel |= 1u << bit; }
+                        }
+                        if ((sel >> lane) & 1u) {
+                            const int pos = rA + 32 * i + lane;
+                            W.rs[pos & (HIT_CAP - 1)] |= 1ull << k;
+                            for (int d = HIT_SHORT_LEN; d < kl; d++) atomicOr(&W.c[(pos + d) & (HIT_CAP - 1)], 1ull << k);
                         }
                     }
-                    if (cover & s_super[k]) hm &= ~(1ull << k);
+                    __syncwarp();
+                    if (lane == 0) W.blocked[b] = blocked;
                 }
-                if (t0 + x < wlen) P.S[woff + t0 + x] = hm;
             }
-            __syncthreads();
-            // the raw matches are no longer needed (except the halo of the next tile): overwrite them with the
-            // survivors so that block starts can be decided here (tg_kmer.py:206-212): k starts a block at x unless
-            // it also survived at x - len_k
-            unsigned long long keep = 0ull;
-            if (tid < HIT_HALO) keep = s_hm[HIT_TILE + tid];
-            __syncthreads();
-            // (each thread re-reads the survivors it just wrote; they are still in L2)
-#pragma unroll 4
-            for (int it = 0; it < HIT_CH; it++) {
-                const int x = tid + it * HIT_THREADS;
-                s_hm[HIT_HALO + x] = (t0 + x < wlen) ? P.S[woff + t0 + x] : 0ull;
+            __syncwarp();
+            // ---- stage B: C(q) |= OR_{d < 8} R(q - d) & {len > d}   (longer reaches were pushed above) ----
+#pragma unroll
+            for (int i = 0; i < HIT_T / 32; i++) {
+                const int pos = rA + 32 * i + lane;
+                unsigned long long c = 0ull;
+#pragma unroll
+                for (int d = 0; d < HIT_SHORT_LEN; d++) c |= W.rs[(pos - d) & (HIT_CAP - 1)] & lg8[d];   // (positions < 0: zeroed ring)
+                if (c) W.c[pos & (HIT_CAP - 1)] |= c;
             }
-            if (tid < HIT_HALO) s_hm[tid] = s_shalo[tid];          // survivors of the previous tile's last positions
-            __syncthreads();
+            __syncwarp();
+            // ---- stage C: survivors S(p), p in [rA - M, rA + T - M); each survivor announces its end in P ----
 #pragma unroll 1
-            for (int it = 0; it < HIT_CH; it++) {
-                const int x = tid + it * HIT_THREADS;
-                unsigned long long sv = s_hm[HIT_HALO + x];
-                bool start = false;
+            for (int i = 0; i < HIT_T / 32; i++) {
+                const int p = rA - M + 32 * i + lane;
+                if (p < 0) continue;
+                const unsigned long long r = W.rs[p & (HIT_CAP - 1)];
+                if (r == 0ull) continue;
+                unsigned long long dead = 0ull, acc = 0ull, rem = r;
+                const int dmax = (r & longmask) ? M : HIT_SHORT_LEN;
+                for (int d = 0; d < dmax && rem; d++) {
+                    acc |= W.c[(p + d) & (HIT_CAP - 1)];
+                    unsigned long long cand = rem & S.bylen[d + 1];
+                    rem &= ~cand;
+                    while (cand) {
+                        const int k = __ffsll((long long)cand) - 1;
+                        cand &= cand - 1;
+                        if (S.sup[k] & acc) dead |= 1ull << k;
+                    }
+                }
+                unsigned long long sv = r & ~dead;
+                W.rs[p & (HIT_CAP - 1)] = sv;
                 while (sv) {
                     const int k = __ffsll((long long)sv) - 1;
                     sv &= sv - 1;
-                    if (!((s_hm[HIT_HALO + x - s_len[k]] >> k) & 1ull)) start = true;
+                    atomicOr(&W.pe[(p + S.len[k]) & (HIT_CAP - 1)], 1ull << k);
                 }
-                const uint32_t bal = __ballot_sync(TG_FULL_MASK, start);
-                if (lane == 0 && t0 + x < wlen) P.B[(woff + t0 + x) >> 5] = bal;
             }
-            __syncthreads();
-            if (tid < HIT_HALO) {
-                s_shalo[tid] = s_hm[HIT_TILE + tid];               // survivors at tile positions TILE-32 .. TILE-1
-                s_hm[tid] = keep;                                  // raw left halo of the next tile
+            __syncwarp();
+            // ---- stage D: events at x in [rA - M, rA + T - M), x <= len; one sweep, the warp in lock step ----
+#pragma unroll 1
+            for (int i = 0; i < HIT_T / 32; i++) {
+                const int x0 = rA - M + 32 * i, x = x0 + lane;
+                unsigned long long st = 0ull, en = 0ull;
+                if (x >= 0 && x <= len) {
+                    const unsigned long long sx = W.rs[x & (HIT_CAP - 1)], px = W.pe[x & (HIT_CAP - 1)];
+                    st = sx & ~px;
+                    en = px & ~sx;
+                    W.pe[x & (HIT_CAP - 1)] = 0ull;
+                }
+                uint32_t ev = __ballot_sync(TG_FULL_MASK, (st | en) != 0ull);
+                while (ev) {
+                    const int l = __ffs(ev) - 1;
+                    ev &= ev - 1;
+                    const unsigned long long s_l = shfl64(st, l), e_l = shfl64(en, l);
+                    // a block start closes everything still open; otherwise the chains that end here close
+                    const unsigned long long closing = s_l ? open : (e_l & open);
+                    if (closing) {
+                        const int n = __popcll(closing);
+                        if (n_buf + n > HIT_BUF) { flush_spans(P, W, q, n_buf, lane); n_buf = 0; }
+                        for (int j = lane; j < n; j += 32) {         // lane j takes the j-th closing k-mer
+                            unsigned long long m = closing;
+                            for (int t = 0; t < j; t++) m &= m - 1;
+                            W.buf[n_buf + j][0] = __ffsll((long long)m) - 1;
+                            W.buf[n_buf + j][1] = s_open;
+                            W.buf[n_buf + j][2] = x0 + l;
+                        }
+                        n_buf += n;
+                    }
+                    if (s_l) { open = s_l; s_open = x0 + l; } else open &= ~e_l;
+                }
             }
+            // the C ring slots the next tile will push into / OR into
+            for (int i = lane; i < HIT_T; i += 32) W.c[(rA + HIT_T + M + i) & (HIT_CAP - 1)] = 0ull;
         }
-    }
-}
-
-// H2: one thread per word of the block-start plane: walk each block to its end, truncate at the next block start
-// of any k-mer (tg_kmer.py:216-228), emit.  Only positions with a block start touch the survivor masks.
-__global__ void __launch_bounds__(256) hits_emit_kernel(const HitParams P)
-{
-    const int64_t n_words = P.total_work >> 5;
-    for (int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; wi < n_words; wi += (int64_t)gridDim.x * blockDim.x) {
-        uint32_t bw = P.B[wi];
-        if (!bw) continue;
-        const int q = find_read(P.work_off, P.n_slices, wi << 5);
-        const int64_t woff = P.work_off[q];
-        const int wlen = (int)(P.work_off[q + 1] - woff);
-        const int wend = wlen >> 5;
-        while (bw) {
-            const int bit = __ffs(bw) - 1;
-            bw &= bw - 1;
-            const int64_t g = (wi << 5) + bit;
-            const int x = (int)(g - woff);
-            // first set bit of B strictly after x (within this slice)
-            int next_start = -1;
-            {
-                int wd = (x + 1) >> 5;
-                uint32_t v = (wd < wend) ? (P.B[(woff >> 5) + wd] & (0xffffffffu << ((x + 1) & 31))) : 0u;
-                while (wd < wend) {
-                    if (v) { next_start = wd * 32 + __ffs(v) - 1; break; }
-                    wd++;
-                    if (wd < wend) v = P.B[(woff >> 5) + wd];
-                }
-            }
-            unsigned long long s = P.S[g];
-            while (s) {
-                const int k = __ffsll((long long)s) - 1;
-                s &= s - 1;
-                const int lk = P.tab->len[k];
-                if (x - lk >= 0 && ((P.S[g - lk] >> k) & 1ull)) continue;      // not a block start
-                int e = x + lk;
-                while (e < wlen && (next_start < 0 || e < next_start) && ((P.S[woff + e] >> k) & 1ull)) e += lk;
-                if (next_start >= 0 && next_start < e) e = next_start;
-                const unsigned long long slot = atomicAdd(P.span_count, 1ULL);
-                if ((long long)slot < P.span_cap) {
-                    P.span_slice[slot] = q; P.span_k[slot] = k; P.span_start[slot] = x; P.span_end[slot] = e;
-                }
-            }
-        }
+        if (n_buf) flush_spans(P, W, q, n_buf, lane);
     }
 }
 
@@ -466,164 +408,77 @@ __global__ void __launch_bounds__(256) hits_emit_kernel(const HitParams P)
 // ================================================================================================
 // host: table construction
 // ================================================================================================
-TG_EXPORT size_t tg_kmer_table_bytes(void) { return sizeof(KmerTable); }
-
-static int code_of(char c)
-{
-    switch (c) { case 'A': return 0; case 'C': return 1; case 'T': return 2; case 'G': return 3; default: return -1; }
-}
-
-// km[0 .. KA) = group 0, km[KA .. K) = group 1
-static int build_table(const std::vector<std::string> &km, int KA, const int32_t *issub_edges, const int32_t *issub_off, KmerTable *T)
-{
-    const int K = (int)km.size();
-    memset(T, 0, sizeof(KmerTable));
-    T->K = K; T->KA = KA; T->n_groups = (KA < K) ? 2 : 1;
-    int max_len = 0;
-    for (int k = 0; k < K; k++) {
-        const int l = (int)km[k].size();
-        if (l < 1 || l > SC_MAXLEN) return tg_set_err(TG_EINVAL, "k-mer %d has length %d outside 1..%d", k, l, SC_MAXLEN);
-        for (char c : km[k]) if (code_of(c) < 0) return tg_set_err(TG_EINVAL, "k-mer %d contains a non-ACGT character", k);
-        T->len[k] = l;
-        if (l > max_len) max_len = l;
-        if (k < KA) for (int d = 0; d < l; d++) T->lengt[d] |= 1ull << k;
-    }
-    T->max_len = max_len;
-    // bordered k-mers: some shift 0 < d < len maps the k-mer onto itself
-    for (int k = 0; k < K; k++) {
-        const std::string &s = km[k];
-        bool bordered = false;
-        for (size_t d = 1; d < s.size() && !bordered; d++) bordered = (s.compare(d, std::string::npos, s, 0, s.size() - d) == 0);
-        if (bordered) {
-            if (T->n_bord >= SC_MAXBORD) return tg_set_err(TG_EINVAL, "more than %d self-overlapping k-mers", SC_MAXBORD);
-            const int b = T->n_bord++;
-            T->bord_kmer[b] = k;
-            T->bord_len[b] = (int)s.size();
-            T->bord_group[b] = (k < KA) ? 0 : 1;
-            uint64_t pat = 0;
-            for (size_t i = 0; i < s.size(); i++) pat |= (uint64_t)code_of(s[i]) << (2 * i);
-            T->bord_pat[b] = pat;
-            if (k < KA) T->bord_mask |= 1ull << k;
-        }
-    }
-    if (issub_edges && issub_off)
-        for (int k = 0; k < KA; k++) {
-            for (int e = issub_off[k]; e < issub_off[k + 1]; e++) {
-                if (issub_edges[e] < 0 || issub_edges[e] >= KA) return tg_set_err(TG_EINVAL, "bad KMER_ISSUBSTRING edge");
-                T->super[k] |= 1ull << issub_edges[e];
-            }
-            if (T->super[k]) T->has_super_mask |= 1ull << k;
-        }
-    // Aho-Corasick over the reversed k-mers; out = set of k-mers (two 64-bit halves, one per group)
-    struct Node { int next[4]; int fail; uint64_t out[2]; };
-    std::vector<Node> nodes(1);
-    nodes[0] = Node{{-1, -1, -1, -1}, 0, {0ull, 0ull}};
-    for (int k = 0; k < K; k++) {
-        int cur = 0;
-        for (int i = (int)km[k].size() - 1; i >= 0; i--) {
-            const int c = code_of(km[k][i]);
-            if (nodes[cur].next[c] < 0) {
-                nodes[cur].next[c] = (int)nodes.size();
-                nodes.push_back(Node{{-1, -1, -1, -1}, 0, {0ull, 0ull}});
-            }
-            cur = nodes[cur].next[c];
-        }
-        if (k < KA) nodes[cur].out[0] |= 1ull << k; else nodes[cur].out[1] |= 1ull << (k - KA);
-    }
-    if ((int)nodes.size() > SC_MAXSTATES) return tg_set_err(TG_EINVAL, "automaton has %d states (max %d)", (int)nodes.size(), SC_MAXSTATES);
-    std::queue<int> bfs;
-    for (int c = 0; c < 4; c++) {
-        int v = nodes[0].next[c];
-        if (v < 0) nodes[0].next[c] = 0;
-        else { nodes[v].fail = 0; bfs.push(v); }
-    }
-    while (!bfs.empty()) {
-        const int u = bfs.front(); bfs.pop();
-        nodes[u].out[0] |= nodes[nodes[u].fail].out[0];
-        nodes[u].out[1] |= nodes[nodes[u].fail].out[1];
-        for (int c = 0; c < 4; c++) {
-            const int v = nodes[u].next[c];
-            if (v < 0) nodes[u].next[c] = nodes[nodes[u].fail].next[c];
-            else { nodes[v].fail = nodes[nodes[u].fail].next[c]; bfs.push(v); }
-        }
-    }
-    T->n_states = (int)nodes.size();
-    std::vector<uint32_t> out_len(nodes.size(), 0u);     // byte 0: group 0, byte 1: group 1
-    for (int s = 0; s < T->n_states; s++) {
-        T->out_mask[s] = nodes[s].out[0];
-        int best[2] = {0, 0};
-        uint32_t ob = 0;
-        for (int k = 0; k < K; k++) {
-            const int grp = (k < KA) ? 0 : 1;
-            if (!((nodes[s].out[grp] >> (grp ? k - KA : k)) & 1ull)) continue;
-            bool is_bord = false;
-            for (int b = 0; b < T->n_bord; b++) if (T->bord_kmer[b] == k) { ob |= 1u << b; is_bord = true; }
-            if (!is_bord && T->len[k] > best[grp]) best[grp] = T->len[k];
-        }
-        out_len[s] = (uint32_t)best[0] | ((uint32_t)best[1] << 8);
-        T->out_bord[s] = ob;
-    }
-    for (int s = 0; s < T->n_states; s++)
-        for (int c = 0; c < 4; c++) {
-            const int v = nodes[s].next[c];
-            T->trans[s * 4 + c] = (uint32_t)v | (T->out_bord[v] ? SC_BORD_FLAG : 0u) |
-                                  ((nodes[v].out[0] | nodes[v].out[1]) ? SC_OUT_FLAG : 0u) | (out_len[v] << 16);
-        }
-    return TG_OK;
-}
-
-static int collect_kmers(const char *concat, const int32_t *off, int K, std::vector<std::string> &km)
-{
-    if (!concat || !off) return tg_set_err(TG_EINVAL, "NULL argument");
-    if (K < 1 || K > SC_MAXLIST) return tg_set_err(TG_EINVAL, "K=%d outside 1..%d", K, SC_MAXLIST);
-    for (int k = 0; k < K; k++) {
-        const int l = off[k + 1] - off[k];
-        if (l < 1 || l > SC_MAXLEN) return tg_set_err(TG_EINVAL, "k-mer %d has length %d outside 1..%d", k, l, SC_MAXLEN);
-        km.emplace_back(concat + off[k], (size_t)l);
-    }
-    return TG_OK;
-}
+TG_EXPORT size_t tg_kmer_table_bytes(void) { return sizeof(HitTable); }
 
 TG_EXPORT int tg_kmer_table_build(const char *kmers_concat, const int32_t *kmer_off, int K,
                                   const int32_t *issub_edges, const int32_t *issub_off, void *h_table)
 {
     if (!h_table) return tg_set_err(TG_EINVAL, "NULL argument");
     std::vector<std::string> km;
-    int rc = collect_kmers(kmers_concat, kmer_off, K, km);
+    int rc = sc_collect_kmers(kmers_concat, kmer_off, K, km);
     if (rc != TG_OK) return rc;
-    return build_table(km, K, issub_edges, issub_off, reinterpret_cast<KmerTable *>(h_table));
+    HitTable *T = reinterpret_cast<HitTable *>(h_table);
+    memset(T, 0, sizeof(HitTable));
+    T->magic = HIT_MAGIC; T->K = K;
+    for (int k = 0; k < SC_MAXLIST; k++) T->bslot[k] = -1;
+    for (int k = 0; k < K; k++) {
+        const int l = (int)km[k].size();
+        T->pat[k] = sc_pattern(km[k]);
+        T->len[k] = l;
+        if (l > T->max_len) T->max_len = l;
+        for (int d = 0; d < l; d++) T->lengt[d] |= 1ull << k;
+        T->bylen[l] |= 1ull << k;
+        if (l > HIT_SHORT_LEN) T->longmask |= 1ull << k;
+        const bool bord = sc_is_bordered(km[k]);
+        T->kind[k] = bord ? SC_BORDERED : (l > SC_W ? SC_SPECIAL : SC_PLAIN);
+        T->bslot[k] = -1;
+        if (bord) {
+            if (T->n_bord >= SC_MAXBORD) return tg_set_err(TG_EINVAL, "more than %d self-overlapping k-mers", SC_MAXBORD);
+            T->bslot[k] = T->n_bord++;
+        }
+        if (T->kind[k] != SC_PLAIN) {
+            if (T->n_spec >= HIT_SLOT_MANY) return tg_set_err(TG_EINVAL, "more than %d special k-mers", HIT_SLOT_MANY);
+            T->spec_idx[T->n_spec++] = k;
+        }
+    }
+    if (issub_edges && issub_off)
+        for (int k = 0; k < K; k++)
+            for (int e = issub_off[k]; e < issub_off[k + 1]; e++) {
+                if (issub_edges[e] < 0 || issub_edges[e] >= K) return tg_set_err(TG_EINVAL, "bad KMER_ISSUBSTRING edge");
+                T->sup[k] |= 1ull << issub_edges[e];
+            }
+    std::map<uint64_t, int> ids;
+    ids[0ull] = 0;
+    T->n_sets = 1;
+    bool overflow = false;
+    // entry of a window of n bases (n = SC_W: the main table; n < SC_W: an N follows, only k-mers of length <= n fit)
+    auto entry = [&](uint32_t w, int n) -> uint16_t {
+        uint64_t set = 0;
+        int slot = -1;
+        for (int k = 0; k < K; k++) {
+            if (!sc_window_has_prefix(w, km[k]) || (n < SC_W && (int)km[k].size() > n)) continue;
+            if (T->kind[k] == SC_PLAIN) { set |= 1ull << k; continue; }
+            int s = 0;
+            while (T->spec_idx[s] != k) s++;
+            slot = (slot < 0) ? s : HIT_SLOT_MANY;
+        }
+        auto it = ids.find(set);
+        int id;
+        if (it != ids.end()) id = it->second;
+        else if (T->n_sets >= HIT_MAXSETS) { overflow = true; id = 0; }
+        else { id = T->n_sets; ids[set] = id; T->sets[T->n_sets++] = set; }
+        return (uint16_t)(id | (slot >= 0 ? (0x8000 | (slot << 9)) : 0));
+    };
+    for (uint32_t w = 0; w < (uint32_t)SC_TAB; w++) T->tab[w] = entry(w, SC_W);
+    for (int d = 1; d < SC_W; d++)
+        for (uint32_t w = 0; w < (1u << (2 * d)); w++) T->tab_short[HIT_SHORT_OFF(d) + w] = entry(w, d);
+    if (overflow) return tg_set_err(TG_ERANGE, "more than %d distinct k-mer sets per window", HIT_MAXSETS);
+    return TG_OK;
 }
 
 // ================================================================================================
 // launches
 // ================================================================================================
-static int grid_for(int64_t items, int block, int sms, int per_sm)
-{
-    int64_t g = (items + block - 1) / block;
-    const int64_t cap = (int64_t)sms * per_sm;
-    if (g > cap) g = cap;
-    if (g < 1) g = 1;
-    return (int)g;
-}
-
-// host copies of the per-list sizes are needed to size shared memory: read them back once per call
-static int table_dims(const void *d_table, int *n_states, int *n_bord, cudaStream_t st)
-{
-    int32_t hdr[4];
-    TG_CUDA_CHECK(cudaMemcpyAsync(hdr, d_table, sizeof(hdr), cudaMemcpyDeviceToHost, st));
-    TG_CUDA_CHECK(cudaStreamSynchronize(st));
-    *n_states = hdr[1];
-    *n_bord = hdr[3];
-    if (hdr[1] < 1 || hdr[1] > SC_MAXSTATES || hdr[3] < 0 || hdr[3] > SC_MAXBORD) return tg_set_err(TG_EINVAL, "corrupt k-mer table");
-    return TG_OK;
-}
-
-static size_t table_smem(int n_states, bool want_mask)
-{
-    auto up = [](size_t b) { return (b + 15) & ~(size_t)15; };
-    return up((size_t)n_states * 16) + up((size_t)n_states * 4) + (want_mask ? up((size_t)n_states * 8) : 0);
-}
-
 TG_EXPORT int tg_scan_pack(const uint8_t *d_ascii, const int64_t *d_base_off, const int32_t *d_len, int n_reads,
                            uint32_t *d_pack2, uint32_t *d_nmask, void *stream)
 {
@@ -664,56 +519,33 @@ static int get_counter(unsigned int **out, cudaStream_t st)
     return TG_OK;
 }
 
-TG_EXPORT size_t tg_scan_hits_work_bytes(int64_t total_work_bases, int n_slices)
-{
-    (void)n_slices;
-    const size_t t = (size_t)((total_work_bases + 63) / 64 * 64);
-    return t * 8 + t / 8 + 256;
-}
-
 TG_EXPORT int tg_scan_hits(const uint32_t *d_pack2, const uint32_t *d_nmask, const int64_t *d_base_off,
                            const int32_t *d_slice_read, const int32_t *d_slice_lo, const int32_t *d_slice_hi, int n_slices,
-                           const int64_t *d_slice_work_off, int64_t total_work_bases, const void *d_table, void *d_work,
+                           const void *d_table,
                            int32_t *d_span_slice, int32_t *d_span_k, int32_t *d_span_start, int32_t *d_span_end,
                            int64_t span_cap, unsigned long long *d_span_count, void *stream)
 {
     if (n_slices <= 0) return TG_OK;
-    if (!d_pack2 || !d_nmask || !d_base_off || !d_slice_read || !d_slice_lo || !d_slice_hi || !d_slice_work_off || !d_table ||
-        !d_work || !d_span_slice || !d_span_k || !d_span_start || !d_span_end || !d_span_count)
+    if (!d_pack2 || !d_nmask || !d_base_off || !d_slice_read || !d_slice_lo || !d_slice_hi || !d_table ||
+        !d_span_slice || !d_span_k || !d_span_start || !d_span_end || !d_span_count)
         return tg_set_err(TG_EINVAL, "NULL device pointer");
-    if (total_work_bases % 64) return tg_set_err(TG_EINVAL, "total_work_bases must be a multiple of 64");
     const int sms = tg_sm_count();
     if (sms <= 0) return tg_set_err(TG_ECUDA, "no CUDA device");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    int ns, nb;
-    int rc = table_dims(d_table, &ns, &nb, st);
-    if (rc != TG_OK) return rc;
-    auto up = [](size_t b) { return (b + 15) & ~(size_t)15; };
-    const size_t smem = table_smem(ns, true) + up(HIT_STAGE / 16 * 4) + up(HIT_STAGE / 32 * 4) + up((size_t)HIT_SPAN * 8) +
-                        up((size_t)(HIT_SPAN / 32 + 1) * 4) + up((size_t)(nb > 1 ? nb : 1) * ((HIT_TILE + HIT_HALO) / 32) * 4);
-    if (smem > 200 * 1024) return tg_set_err(TG_ERANGE, "k-mer table too large for shared memory (%zu bytes)", smem);
     HitParams P;
     P.pack2 = d_pack2; P.nmask = d_nmask; P.base_off = d_base_off;
     P.slice_read = d_slice_read; P.slice_lo = d_slice_lo; P.slice_hi = d_slice_hi; P.n_slices = n_slices;
-    P.work_off = d_slice_work_off; P.tab = reinterpret_cast<const KmerTable *>(d_table);
-    P.S = reinterpret_cast<uint64_t *>(d_work);
-    P.B = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(d_work) + (size_t)total_work_bases * 8);
-    P.total_work = total_work_bases;
+    P.tab = reinterpret_cast<const HitTable *>(d_table);
     P.span_slice = d_span_slice; P.span_k = d_span_k; P.span_start = d_span_start; P.span_end = d_span_end;
     P.span_cap = span_cap; P.span_count = d_span_count;
-    rc = get_counter(&P.next_slice, st);
+    int rc = get_counter(&P.next_slice, st);
     if (rc != TG_OK) return rc;
     TG_CUDA_CHECK(cudaMemsetAsync(d_span_count, 0, sizeof(unsigned long long), st));
-    TG_CUDA_CHECK(cudaFuncSetAttribute(hits_survivors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = (int)((220 * 1024) / (smem + 4096));
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 8) per_sm = 8;
-    int grid = sms * per_sm;
-    if (grid > n_slices) grid = n_slices;
-    hits_survivors_kernel<<<grid, HIT_THREADS, smem, st>>>(P);
-    TG_CUDA_CHECK(cudaGetLastError());
-    const int g2 = grid_for(total_work_bases / 32, 256, sms, 16);
-    hits_emit_kernel<<<g2, 256, 0, st>>>(P);
+    const size_t smem = sizeof(HitSmem);
+    TG_CUDA_CHECK(cudaFuncSetAttribute(hits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = sms;
+    if (grid > (n_slices + HIT_WARPS - 1) / HIT_WARPS) grid = (n_slices + HIT_WARPS - 1) / HIT_WARPS;
+    hits_kernel<<<grid, HIT_WARPS * 32, smem, st>>>(P);
     TG_CUDA_CHECK(cudaGetLastError());
     return TG_OK;
 }

@@ -59,7 +59,7 @@ __device__ __forceinline__ bool sc_kmer_at(const ScPlanes &P, int64_t g, uint64_
 // Exact state of re.finditer's greedy rule in front of candidate c0 (absolute) of a self-overlapping k-mer: walk the
 // chain of overlapping candidates back to its head (no other candidate within blen - 1 bases before it), then replay
 // forward.  Returns the absolute position before which the k-mer is blocked (LLONG_MIN-ish if there is no chain).
-__device__ __noinline__ int64_t sc_chain_state_before(const ScPlanes &P, int64_t c0, uint64_t pat, int blen)
+static __device__ __noinline__ int64_t sc_chain_state_before(const ScPlanes &P, int64_t c0, uint64_t pat, int blen)
 {
     int64_t head = c0, p = c0 - 1;
     while (p >= 0 && head - p < blen) {

@@ -66,7 +66,7 @@ _table_cache = {}
 
 
 def kmer_table(kmer_list, issub=None):
-    """Device blob of the reversed-k-mer automaton for `kmer_list` (cached per device)."""
+    """Device blob of the window table + k-mer sets for `kmer_list` (hits kernel; cached per device)."""
     torch = _lib.require_cuda()
     L = _lib.load()
     dev = torch.cuda.current_device()
@@ -79,6 +79,8 @@ def kmer_table(kmer_list, issub=None):
     blob = ''.join(kmer_list).encode('ascii')
     off = np.zeros(len(kmer_list) + 1, dtype=np.int32)
     off[1:] = np.cumsum([len(k) for k in kmer_list])
+    if issub is None:
+        issub = [[j for j in range(len(kmer_list)) if (j != i and kmer_list[i] in kmer_list[j])] for i in range(len(kmer_list))]
     if issub is not None:
         edges = np.array([j for lst in issub for j in lst], dtype=np.int32)
         eoff = np.zeros(len(issub) + 1, dtype=np.int32)
@@ -232,22 +234,18 @@ class PackedReads:
         sr = np.ascontiguousarray(slice_read, dtype=np.int32)
         lo = np.ascontiguousarray(slice_lo, dtype=np.int32)
         hi = np.ascontiguousarray(slice_hi, dtype=np.int32)
-        ln = (hi - lo).astype(np.int64)
-        woff = np.zeros(ns + 1, dtype=np.int64)
-        woff[1:] = np.cumsum((ln + 63) // 64 * 64)
-        total = int(woff[-1])
+        total = int((hi - lo).astype(np.int64).sum())
         if ns == 0 or total == 0:
             return torch.zeros((4, 0), dtype=torch.int32, device='cuda')
         tab = kmer_table(kmer_list, issub)
-        d_sr, d_lo, d_hi, d_woff = (torch.from_numpy(a).cuda() for a in (sr, lo, hi, woff))
-        work = torch.empty(self.L.tg_scan_hits_work_bytes(total, ns), dtype=torch.uint8, device='cuda')
+        d_sr, d_lo, d_hi = (torch.from_numpy(a).cuda() for a in (sr, lo, hi))
         cap = max(total // 4, 1024)
         while True:
             spans = torch.empty((4, cap), dtype=torch.int32, device='cuda')
             cnt = torch.zeros(1, dtype=torch.int64, device='cuda')
             _lib.check(self.L.tg_scan_hits(_lib.dptr(self.d_pack2), _lib.dptr(self.d_nmask), _lib.dptr(self.d_base_off),
-                                           _lib.dptr(d_sr), _lib.dptr(d_lo), _lib.dptr(d_hi), ns, _lib.dptr(d_woff), total,
-                                           _lib.dptr(tab), _lib.dptr(work), _lib.dptr(spans[0]), _lib.dptr(spans[1]),
+                                           _lib.dptr(d_sr), _lib.dptr(d_lo), _lib.dptr(d_hi), ns,
+                                           _lib.dptr(tab), _lib.dptr(spans[0]), _lib.dptr(spans[1]),
                                            _lib.dptr(spans[2]), _lib.dptr(spans[3]), cap, _lib.dptr(cnt),
                                            _lib.stream_ptr(torch)))
             n_sp = int(cnt.item())

@@ -148,8 +148,8 @@ def test_c_abi_exports_every_declared_symbol_and_table_builder(kmer_tables):
     host = np.zeros(L.tg_kmer_table_bytes(), dtype=np.uint8)
     assert L.tg_kmer_table_build(blob, off.ctypes.data_as(ctypes.c_void_p), len(T['KMER_LIST']), None, None,
                                  host.ctypes.data_as(ctypes.c_void_p)) == 0
-    hdr = host[:16].view(np.int32)
-    assert hdr[0] == len(T['KMER_LIST']) and hdr[2] == 20 and hdr[3] == 4      # CCCCCC, CCCTCC and the two HOR k-mers
+    hdr = host[:24].view(np.int32)
+    assert hdr[1] == len(T['KMER_LIST']) and hdr[4] == 20 and hdr[3] == 4      # CCCCCC, CCCTCC and the two HOR k-mers
     bad = b'CCNTAA'
     off2 = np.array([0, 6], dtype=np.int32)
     assert L.tg_kmer_table_build(bad, off2.ctypes.data_as(ctypes.c_void_p), 1, None, None, host.ctypes.data_as(ctypes.c_void_p)) == _lib.TG_EINVAL
