@@ -158,6 +158,7 @@ struct alignas(16) HitWarpSmem {
     uint32_t pk[HIT_T / 16 + 4];              // staged bases [rA, rA + T + 64)
     uint32_t nm[HIT_T / 32 + 4];
     int32_t blocked[SC_MAXBORD];              // greedy state of every self-overlapping k-mer
+    uint8_t list[HIT_T];                      // tile positions with a match (stage C works on these only)
     int32_t buf[HIT_BUF][3];                  // (k, start, end)
 };
 
@@ -226,7 +227,6 @@ __global__ void __launch_bounds__(HIT_WARPS * 32, 1) hits_kernel(const HitParams
     }
     __syncthreads();
     const int n_bord = T->n_bord, n_spec = T->n_spec, M = T->max_len;
-    const unsigned long long longmask = T->longmask;
     unsigned long long lg8[HIT_SHORT_LEN];
 #pragma unroll
     for (int d = 0; d < HIT_SHORT_LEN; d++) lg8[d] = S.lengt[d];
@@ -335,22 +335,45 @@ __global__ void __launch_bounds__(HIT_WARPS * 32, 1) hits_kernel(const HitParams
                 if (c) W.c[pos & (HIT_CAP - 1)] |= c;
             }
             __syncwarp();
-            // ---- stage C: survivors S(p), p in [rA - M, rA + T - M); each survivor announces its end in P ----
-#pragma unroll 1
+            // ---- stage C: survivors S(p), p in [rA - M, rA + T - M); each survivor announces its end in P.
+            //      Positions without a match are skipped: the others are compacted so that all lanes work ----
+            int n_list = 0;
+#pragma unroll
             for (int i = 0; i < HIT_T / 32; i++) {
                 const int p = rA - M + 32 * i + lane;
-                if (p < 0) continue;
+                const bool has = p >= 0 && W.rs[p & (HIT_CAP - 1)] != 0ull;
+                const uint32_t bal = __ballot_sync(TG_FULL_MASK, has);
+                if (has) W.list[n_list + __popc(bal & ((1u << lane) - 1u))] = (uint8_t)(32 * i + lane);
+                n_list += __popc(bal);
+            }
+            __syncwarp();
+#pragma unroll 1
+            for (int i0 = 0; i0 < n_list; i0 += 32) {
+                if (i0 + lane >= n_list) continue;
+                const int p = rA - M + W.list[i0 + lane];
                 const unsigned long long r = W.rs[p & (HIT_CAP - 1)];
-                if (r == 0ull) continue;
-                unsigned long long dead = 0ull, acc = 0ull, rem = r;
-                const int dmax = (r & longmask) ? M : HIT_SHORT_LEN;
-                for (int d = 0; d < dmax && rem; d++) {
-                    acc |= W.c[(p + d) & (HIT_CAP - 1)];
-                    unsigned long long cand = rem & S.bylen[d + 1];
-                    rem &= ~cand;
-                    while (cand) {
-                        const int k = __ffsll((long long)cand) - 1;
-                        cand &= cand - 1;
+                // most deleted matches are covered by a superstring at their very first position
+                const unsigned long long c0 = W.c[p & (HIT_CAP - 1)];
+                unsigned long long dead = 0ull, rem = r, need = 0ull;
+                while (rem) {
+                    const int k = __ffsll((long long)rem) - 1;
+                    rem &= rem - 1;
+                    if (S.sup[k] & c0) dead |= 1ull << k; else if (S.sup[k]) need |= 1ull << k;
+                }
+                if (need) {
+                    // coverage sets of the next positions, OR-ed up: D[t] = C(p) | .. | C(p + t)
+                    unsigned long long D[HIT_SHORT_LEN];
+                    D[0] = c0;
+#pragma unroll
+                    for (int t = 1; t < HIT_SHORT_LEN; t++) D[t] = D[t - 1] | W.c[(p + t) & (HIT_CAP - 1)];
+                    while (need) {
+                        const int k = __ffsll((long long)need) - 1;
+                        need &= need - 1;
+                        const int kl = S.len[k];
+                        unsigned long long acc = D[HIT_SHORT_LEN - 1];
+#pragma unroll
+                        for (int t = HIT_SHORT_LEN - 2; t >= 0; t--) acc = (kl <= t + 1) ? D[t] : acc;
+                        for (int d = HIT_SHORT_LEN; d < kl; d++) acc |= W.c[(p + d) & (HIT_CAP - 1)];      // long k-mers
                         if (S.sup[k] & acc) dead |= 1ull << k;
                     }
                 }
@@ -462,6 +485,10 @@ TG_EXPORT int tg_kmer_table_build(const char *kmers_concat, const int32_t *kmer_
             while (T->spec_idx[s] != k) s++;
             slot = (slot < 0) ? s : HIT_SLOT_MANY;
         }
+        // a plain k-mer with a plain superstring starting at the same position is deleted by it, and whatever it could
+        // delete itself the superstring deletes too (substring containment is transitive): it never needs to be seen
+        for (int k = 0; k < K; k++)
+            if (((set >> k) & 1ull) && (T->sup[k] & set)) set &= ~(1ull << k);
         auto it = ids.find(set);
         int id;
         if (it != ids.end()) id = it->second;
