@@ -214,7 +214,9 @@ int tg_kmer_table_build_pair(const char *kmers_a, const int32_t *off_a, int KA,
  * d_base_off has n_reads + 1 entries (the last one = total padded bases).
  * Replaces nothing in the reference (it scans Python str) -- this is the HBM layout. */
 int tg_scan_pack(const uint8_t *d_ascii, const int64_t *d_base_off, const int32_t *d_len, int n_reads,
-                 uint32_t *d_pack2, uint32_t *d_nmask, void *stream);
+                 uint32_t *d_pack2, uint32_t *d_nmask,
+                 uint8_t *d_not_acgtn, /* [n_reads] zeroed by the caller, or NULL: set to 1 for reads holding a letter RC() rejects */
+                 void *stream);
 
 /* get_telomere_base_count(read, kmer_list) (tg_kmer.py:93-102) for two k-mer lists at once
  * (CANONICAL_STRINGS and CANONICAL_STRINGS_REV, tg_tel.py:262-263): d_counts[2r + s] (zeroed here).

@@ -88,7 +88,7 @@ def load():
     L.tg_device_sm_count.argtypes = [C.POINTER(C.c_int)]
     L.tg_kmer_table_bytes.restype = sz
     L.tg_kmer_table_build.argtypes = [C.c_char_p, vp, i32, vp, vp, vp]
-    L.tg_scan_pack.argtypes = [vp, vp, vp, i32, vp, vp, vp]
+    L.tg_scan_pack.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp]
     L.tg_kmer_table_build_pair.argtypes = [C.c_char_p, vp, i32, C.c_char_p, vp, i32, vp]
     L.tg_scan_basecount.argtypes = [vp, vp, i64, vp, i32, vp, vp, vp]
     L.tg_kmer_table_pair_bytes.restype = sz

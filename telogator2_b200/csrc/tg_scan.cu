@@ -39,7 +39,8 @@ __device__ __forceinline__ int find_read(const int64_t *off, int n, int64_t base
 
 __global__ void __launch_bounds__(256) pack_kernel(const uint8_t *__restrict__ ascii, const int64_t *__restrict__ base_off,
                                                    const int32_t *__restrict__ len, int n_reads,
-                                                   uint32_t *__restrict__ pack2, uint32_t *__restrict__ nmask)
+                                                   uint32_t *__restrict__ pack2, uint32_t *__restrict__ nmask,
+                                                   uint8_t *__restrict__ not_acgtn)
 {
     const int64_t total = base_off[n_reads];
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g * 32 < total; g += (int64_t)gridDim.x * blockDim.x) {
@@ -51,16 +52,19 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint8_t *__restrict__ a
         const uint4 v1 = *reinterpret_cast<const uint4 *>(ascii + b0 + 16);
         const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
         uint32_t p[2] = {0u, 0u}, m = 0u;
+        bool other = false;                          // a letter RC() has no complement for (tg_util.py:41)
 #pragma unroll
         for (int i = 0; i < 32; i++) {
             const uint32_t c = (w[i >> 2] >> ((i & 3) * 8)) & 0xffu;
             const bool ok = ascii_is_acgt(c) && (rel + i < L);
             p[i >> 4] |= (ok ? ascii_code(c) : 0u) << ((i & 15) * 2);
             m |= (ok ? 0u : 1u) << i;
+            other = other || (!ok && c != 'N' && rel + i < L);
         }
         pack2[g * 2] = p[0];
         pack2[g * 2 + 1] = p[1];
         nmask[g] = m;
+        if (other && not_acgtn) not_acgtn[r] = 1;
     }
 }
 
@@ -507,12 +511,13 @@ TG_EXPORT int tg_kmer_table_build(const char *kmers_concat, const int32_t *kmer_
 // launches
 // ================================================================================================
 TG_EXPORT int tg_scan_pack(const uint8_t *d_ascii, const int64_t *d_base_off, const int32_t *d_len, int n_reads,
-                           uint32_t *d_pack2, uint32_t *d_nmask, void *stream)
+                           uint32_t *d_pack2, uint32_t *d_nmask, uint8_t *d_not_acgtn, void *stream)
 {
     if (n_reads <= 0) return TG_OK;
     const int sms = tg_sm_count();
     if (sms <= 0) return tg_set_err(TG_ECUDA, "no CUDA device");
-    pack_kernel<<<sms * 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_ascii, d_base_off, d_len, n_reads, d_pack2, d_nmask);
+    pack_kernel<<<sms * 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_ascii, d_base_off, d_len, n_reads, d_pack2, d_nmask,
+                                                                              d_not_acgtn);
     TG_CUDA_CHECK(cudaGetLastError());
     return TG_OK;
 }

@@ -124,6 +124,20 @@ def kmer_table_pair(list_a, list_b):
 # ------------------------------------------------------------------------------------------------
 # reads in HBM
 # ------------------------------------------------------------------------------------------------
+_pinned_pool = {}
+
+
+def pinned_bytes(slot, nbytes):
+    """A page-locked uint8 host buffer of at least nbytes, kept per slot across calls (allocating page-locked memory costs
+    ~1 ms per MB).  The caller owns it until its next request for the same slot."""
+    import torch
+    buf = _pinned_pool.get(slot)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes * 1.25), 1 << 20), dtype=torch.uint8, pin_memory=True)
+        _pinned_pool[slot] = buf
+    return buf[:nbytes]
+
+
 _ACGTN = np.zeros(256, dtype=bool)
 _ACGTN[[ord(c) for c in 'ACGTN']] = True
 ALIGN = 128
@@ -143,7 +157,7 @@ class PackedReads:
         self.base_off[1:] = np.cumsum(padded)
         total = int(self.base_off[-1])
         self.total = total
-        ascii_h = torch.empty(max(total, 16), dtype=torch.uint8, pin_memory=True)
+        ascii_h = pinned_bytes('ascii', max(total, 16))
         buf = ascii_h.numpy()
         pad = b'N' * ALIGN
         joined = b''.join(x for i, r in enumerate(reads)
@@ -151,30 +165,28 @@ class PackedReads:
         if len(joined) != total:
             raise ValueError('reads must be str of single-byte characters')
         buf[:total] = np.frombuffer(joined, dtype=np.uint8)
-        self._ascii_host = buf
+        self._reads = reads
         self._bad_reads = None
         self.h2d_bytes = total + self.base_off.nbytes + self.lens.nbytes
         self.d_ascii = ascii_h.cuda(non_blocking=True)
+        torch.cuda.current_stream().synchronize()                 # the page-locked staging buffer is reused by the next batch
         self.d_base_off = torch.from_numpy(self.base_off).cuda()
         self.d_len = torch.from_numpy(self.lens).cuda()
         self.d_pack2 = torch.zeros(total // 16 + 8, dtype=torch.int32, device='cuda')
         self.d_nmask = torch.zeros(total // 32 + 8, dtype=torch.int32, device='cuda')
         self._blk_read = None
+        self.d_not_acgtn = torch.zeros(max(self.n, 1), dtype=torch.uint8, device='cuda')
         if self.n and total:
             _lib.check(L.tg_scan_pack(_lib.dptr(self.d_ascii), _lib.dptr(self.d_base_off), _lib.dptr(self.d_len), self.n,
-                                      _lib.dptr(self.d_pack2), _lib.dptr(self.d_nmask), _lib.stream_ptr(torch)))
+                                      _lib.dptr(self.d_pack2), _lib.dptr(self.d_nmask), _lib.dptr(self.d_not_acgtn),
+                                      _lib.stream_ptr(torch)))
 
     def check_rc_alphabet(self, flip):
         """RC() raises KeyError outside ACGTN (tg_util.py:433-434); mirror that for reads to be flipped."""
         if self._bad_reads is None:
-            bad = ~_ACGTN[self._ascii_host[:self.total]]
-            self._bad_reads = np.zeros(self.n, dtype=bool)
-            if bad.any():
-                self._bad_reads[np.unique(np.searchsorted(self.base_off, np.nonzero(bad)[0], side='right') - 1)] = True
+            self._bad_reads = self.d_not_acgtn[:self.n].cpu().numpy().astype(bool)      # found by the pack kernel
         for i in np.nonzero(np.asarray(flip, dtype=bool) & self._bad_reads)[0]:
-            o = int(self.base_off[i])
-            seg = self._ascii_host[o:o + self.lens[i]]
-            raise KeyError(chr(int(seg[np.argmax(~_ACGTN[seg])])))
+            RC(self._reads[i])                                   # raises the reference's KeyError
 
     def blk_read(self):
         """device int32: read index of every 128-base block of the padded base space."""
@@ -219,6 +231,17 @@ class PackedReads:
                                               _lib.stream_ptr(torch)))
         return ca, cb
 
+    def counts_to_host(self, ca, cb):
+        """The two uint8 count planes -> page-locked host memory (numpy views, valid until the next call)."""
+        torch = self.torch
+        out = []
+        for slot, t in (('cnt_a', ca), ('cnt_b', cb)):
+            h = pinned_bytes(slot, t.numel())
+            h.copy_(t, non_blocking=True)
+            out.append(h.numpy())
+        torch.cuda.current_stream().synchronize()
+        return out
+
     def split_counts(self, flat, window):
         """host: per-read views cnt[0 : len - window) of a flat count array (numpy uint8)."""
         out = []
@@ -262,11 +285,10 @@ class PackedReads:
         self.last_hits_d2h = sp.nbytes
         order = np.lexsort((sp[2], sp[1], sp[0]))          # by slice, k, start
         sp = sp[:, order]
-        out = [[[] for _ in range(K)] for _ in range(ns)]
-        sl, kk, ss, ee = sp[0].tolist(), sp[1].tolist(), sp[2].tolist(), sp[3].tolist()
-        for q, k, s, e in zip(sl, kk, ss, ee):
-            out[q][k].append([s, e])
-        return out
+        # one C-level conversion of all spans, then list slices per (slice, k)
+        pairs = np.ascontiguousarray(sp[2:4].T).tolist()
+        cuts = np.searchsorted(sp[0].astype(np.int64) * K + sp[1], np.arange(ns * K + 1, dtype=np.int64)).tolist()
+        return [[pairs[cuts[q * K + k]:cuts[q * K + k + 1]] for k in range(K)] for q in range(ns)]
 
 
 # ------------------------------------------------------------------------------------------------

@@ -17,8 +17,12 @@ computed in phase 1 (tg_kmer.prime_density_cache).
 """
 import numpy as np
 
+import time
+
 from . import tg_kmer
 from .tg_util import RC
+
+LAST_STATS = {}          # byte counts and phase times of the most recent local batch (bench.py reads them)
 
 
 def _reference_get_terminating_tl():
@@ -66,14 +70,17 @@ def _tel_repeat_comp_local(all_read_dat, gtrc_params, get_terminating_tl=None, i
     n_reads = len(all_read_dat)
 
     # ---- phase 1: GPU ----
+    t_ph = [time.perf_counter()]
     reads = [r[1] for r in all_read_dat]
     pr = tg_kmer.PackedReads(reads)
     bc = pr.basecount(CANONICAL_STRINGS, CANONICAL_STRINGS_REV).cpu().numpy()
     flip = bc[:, 0] > bc[:, 1]                                      # tg_tel.py:265
     pr.orient(flip)
     d_p, d_q = pr.density_counts(KMER_LIST, KMER_LIST_REV, TEL_WINDOW_SIZE)
-    cnt_p = pr.split_counts(d_p.cpu().numpy(), TEL_WINDOW_SIZE)
-    cnt_q = pr.split_counts(d_q.cpu().numpy(), TEL_WINDOW_SIZE)
+    h_p, h_q = pr.counts_to_host(d_p, d_q)
+    cnt_p = pr.split_counts(h_p, TEL_WINDOW_SIZE)
+    cnt_q = pr.split_counts(h_q, TEL_WINDOW_SIZE)
+    t_ph.append(time.perf_counter())
 
     # ---- phase 2: CPU, per read, the reference's own boundary calling and filters ----
     per_read = []
@@ -90,12 +97,12 @@ def _tel_repeat_comp_local(all_read_dat, gtrc_params, get_terminating_tl=None, i
             tel_signal_plot_num += 1
         else:
             tel_signal_plot_dat = None
+        # densities as float64 arrays (every consumer only needs len(), indexing and numpy conversion: tg_kmer.py:106-115,
+        # tg_plot.py:84-98); the all-zero second track of the reference (tg_kmer.py:67-76) is one shared read-only view
         n_out = len(cnt_p[i])
-        zeros = [0.0] * n_out
-        tg_kmer.prime_density_cache(my_rdat, KMER_LIST, TEL_WINDOW_SIZE,
-                                    ((cnt_p[i].astype(np.float64) / TEL_WINDOW_SIZE).tolist(), zeros))
-        tg_kmer.prime_density_cache(my_rdat, KMER_LIST_REV, TEL_WINDOW_SIZE,
-                                    ((cnt_q[i].astype(np.float64) / TEL_WINDOW_SIZE).tolist(), zeros))
+        zeros = np.broadcast_to(np.float64(0.0), (n_out,))
+        tg_kmer.prime_density_cache(my_rdat, KMER_LIST, TEL_WINDOW_SIZE, (cnt_p[i].astype(np.float64) / TEL_WINDOW_SIZE, zeros))
+        tg_kmer.prime_density_cache(my_rdat, KMER_LIST_REV, TEL_WINDOW_SIZE, (cnt_q[i].astype(np.float64) / TEL_WINDOW_SIZE, zeros))
         try:
             (my_terminating_tel, my_nontel_end, interstitial_tel) = get_terminating_tl(my_rdat, 'q', gtt_params,
                                                                                        telplot_dat=tel_signal_plot_dat)
@@ -128,9 +135,17 @@ def _tel_repeat_comp_local(all_read_dat, gtrc_params, get_terminating_tl=None, i
         per_read.append(st)
 
     # ---- phase 3: GPU, all hit slices at once (reads are already oriented on the device) ----
+    t_ph.append(time.perf_counter())
+    d2h = bc.nbytes + 2 * int(getattr(pr, 'total', 0))
     hits_tvr = pr.hits(*slices['tvr'], KMER_LIST_REV, KMER_ISSUBSTRING)
+    d2h += getattr(pr, 'last_hits_d2h', 0)
     hits_ifwd = pr.hits(*slices['ifwd'], KMER_LIST, KMER_ISSUBSTRING)
     hits_irev = pr.hits(*slices['irev'], KMER_LIST_REV, KMER_ISSUBSTRING)
+    t_ph.append(time.perf_counter())
+    LAST_STATS.clear()
+    LAST_STATS.update(h2d_bytes=getattr(pr, 'h2d_bytes', 0), d2h_bytes=d2h,
+                      phases={'gpu_pack_count_orient_density_d2h': t_ph[1] - t_ph[0], 'host_per_read_boundary_calling': t_ph[2] - t_ph[1],
+                              'gpu_hits_and_list_assembly': t_ph[3] - t_ph[2]})
     it_tvr, it_i = iter(hits_tvr), iter(zip(hits_ifwd, hits_irev))
 
     kmer_hit_dat, all_terminating_tl, all_nontel_end = [], [], []

@@ -48,6 +48,30 @@ def colorvecs():
         return json.load(f)
 
 
+@pytest.fixture(scope='session')
+def reads_all():
+    """ALL bundled reads (83 ONT + 200 HiFi + 13 maize, BASELINE configs 1-3)."""
+    with gzip.open(os.path.join(GOLDEN, 'reads_all.json.gz'), 'rt') as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope='session')
+def scan_all_golden():
+    """Per read of reads_all: what the REFERENCE's scan functions compute (make_golden_all.py), as digests."""
+    with gzip.open(os.path.join(GOLDEN, 'scan_all_golden.json.gz'), 'rt') as f:
+        return json.load(f)
+
+
+def sha1_of(a):
+    import hashlib
+    return hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def hits_digest(hits):
+    tri = np.array([(k, sp[0], sp[1]) for k, spans in enumerate(hits) for sp in spans], dtype=np.int32).reshape(-1, 3)
+    return sha1_of(tri), int(len(tri))
+
+
 RC_DICT = {'A': 'T', 'C': 'G', 'G': 'C', 'T': 'A', 'N': 'N'}
 
 

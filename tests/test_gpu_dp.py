@@ -307,3 +307,20 @@ def test_many_matrices_in_one_pass_equal_the_per_call_results(tga, colorvecs):
             assert np.array_equal(D, one)
             if 2 <= len(g) <= 9:
                 assert np.array_equal(D, oracle.dist_matrix_c(g, P, adjust, minv, R, seed))
+
+
+@pytest.mark.parametrize('key,n', [('human_ont', 83), ('human_hifi', 101), ('maize_hifi', 13)])
+def test_full_iter0_matrices_of_the_bundled_sets(tga, colorvecs, key, n):
+    """D0: the whole iteration-0 matrix of every bundled set (N = 83 / 101 / 13, truncate 1000, R = 2, seed
+    12345) through the drop-in call, bit-equal to the oracle, and the same ward clusters."""
+    from scipy.cluster.hierarchy import fcluster, linkage
+    from scipy.spatial.distance import squareform
+    seqs = [c[:1000] for c in colorvecs['colorvecs'][key]]
+    assert len(seqs) == n
+    aligner = tga.get_aligner_object(tga.get_scoring_matrix('C', 'tvr'), (True, True), 'tvr')
+    D = tga.get_dist_matrix_parallel(seqs, aligner, True, True, 2, rng_seed=12345)
+    Do = oracle.dist_matrix_c(seqs, _P(oracle.scoring_matrix('C', 'tvr'), (True, True)), True, True, 2, 12345)
+    assert D.dtype == np.dtype('<f4') and np.array_equal(D, Do)
+    a1 = fcluster(linkage(squareform(D / 10.0), method='ward'), 0.2, 'distance')
+    a2 = fcluster(linkage(squareform(Do / 10.0), method='ward'), 0.2, 'distance')
+    assert np.array_equal(a1, a2)

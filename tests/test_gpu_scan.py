@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 import oracle
-from conftest import hits_to_array, rc_py, scan_cases
+from conftest import hits_digest, hits_to_array, rc_py, scan_cases, sha1_of
 
 pytestmark = pytest.mark.gpu
 
@@ -167,3 +167,29 @@ def test_window_and_short_reads(tgk, kmer_tables):
         ca = pr.split_counts(ca.cpu().numpy(), w)
         for q, r in enumerate(reads):
             assert np.array_equal(ca[q].astype(np.int32), oracle.density_counts(r, KL, w)), (q, w)
+
+
+def test_all_bundled_reads_match_reference(tgk, kmer_tables, reads_all, scan_all_golden):
+    """BASELINE configs 1-3 whole (83 ONT + 200 HiFi + 13 maize reads): base counts, orientation, both density tracks and the
+    hit spans of the last 6000 bases, against what the reference's own tg_kmer functions computed (make_golden_all.py)."""
+    n = 0
+    for key, rs in reads_all.items():
+        T = kmer_tables[key]
+        KL, ISSUB, CANON = T['KMER_LIST'], T['KMER_ISSUBSTRING'], T['CANONICAL_STRINGS']
+        KLR, CR = [rc_py(k) for k in KL], [rc_py(k) for k in CANON]
+        reads = [r for _, r in rs]
+        pr = tgk.PackedReads(reads)
+        bc = pr.basecount(CANON, CR).cpu().numpy()
+        flip = bc[:, 0] > bc[:, 1]
+        pr.orient(flip)
+        ca, cb = pr.density_counts(KL, KLR, 100)
+        ca, cb = pr.split_counts(ca.cpu().numpy(), 100), pr.split_counts(cb.cpu().numpy(), 100)
+        lens = np.array([len(r) for r in reads])
+        hits = pr.hits(np.arange(len(reads)), np.maximum(lens - 6000, 0), lens, KLR, ISSUB)
+        for q, ((name, _r), g) in enumerate(zip(rs, scan_all_golden[key])):
+            assert bc[q].tolist() == g['bc'] and bool(flip[q]) == g['flip'], name
+            assert int(ca[q].astype(np.int64).sum()) == g['sum_p'] and int(cb[q].astype(np.int64).sum()) == g['sum_q'], name
+            assert sha1_of(ca[q]) == g['dens_p'] and sha1_of(cb[q]) == g['dens_q'], name
+            assert hits_digest(hits[q]) == (g['hits'], g['n_spans']), name
+            n += 1
+    assert n == 296

@@ -138,3 +138,19 @@ def test_batch_boundary_matches_per_read_flow(kmer_tables, golden_reads, tkey, f
         assert g[0] == w[0]
     assert got[6] == want[6]
     assert got[7] == want[7] and got[8] == want[8]
+
+
+def test_all_bundled_reads_through_the_batch_boundary(kmer_tables, reads_all):
+    """get_tel_repeat_comp_parallel on ALL bundled reads of every set (83 / 200 / 13) against the per-read oracle flow."""
+    from telogator2_b200 import tg_kmer, tg_tel
+    for key, filt in tel_cases():
+        T = kmer_tables[key]
+        KL, CANON = T['KMER_LIST'], T['CANONICAL_STRINGS']
+        params = [T['read_type'], 60, KL, [rc_py(k) for k in KL], T['KMER_ISSUBSTRING'], CANON, [rc_py(k) for k in CANON], 100, 0.5, 100,
+                  filt[0], filt[1], filt[2], False, '', 100, 1000]
+        ard = [(name, r, None) for name, r in reads_all[key]]
+        got = tg_tel.get_tel_repeat_comp_parallel(ard, params, get_terminating_tl=make_gtt(tg_kmer.get_telomere_kmer_density))
+        want = oracle_flow(ard, params)
+        assert got[1:6] == want[1:6], key
+        assert len(got[0]) == len(want[0]) and all(a == b for a, b in zip(got[0], want[0])), key
+        assert got[6] == want[6] and got[7] == want[7] and got[8] == want[8], key

@@ -668,6 +668,9 @@ class _OraclePackedReads:
             outs.append(_T(flat))
         return outs[0], outs[1]
 
+    def counts_to_host(self, ca, cb):
+        return ca.cpu().numpy(), cb.cpu().numpy()
+
     def split_counts(self, flat, window):
         return [flat[int(self.base_off[i]):int(self.base_off[i]) + max(int(self.lens[i]) - window, 0)] for i in range(self.n)]
 

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import oracle
-from conftest import hits_to_array, rc_py, scan_cases
+from conftest import hits_digest, hits_to_array, rc_py, scan_cases, sha1_of
 
 
 def test_scan_oracle_matches_reference_golden(kmer_tables, golden_reads, scan_golden):
@@ -180,3 +180,88 @@ def test_scan_batch_flow_pinned_against_reference_driver(kmer_tables, golden_rea
     for tkey, filters in tel_cases():
         reads, params = _tel_inputs(kmer_tables, golden_reads, tkey, filters)
         assert digest_tel_result(oracle_flow(reads, params)) == gold[tkey], tkey
+
+
+def test_scan_oracle_matches_reference_on_all_bundled_reads(kmer_tables, reads_all, scan_all_golden):
+    """The whole of BASELINE configs 1-3 (83 / 200 / 13 reads): the oracle's scan functions against what the reference's own
+    tg_kmer functions computed (make_golden_all.py; digests of the density counts and of the hit spans)."""
+    n = 0
+    for key, rs in reads_all.items():
+        T = kmer_tables[key]
+        KL, ISSUB, CANON = T['KMER_LIST'], T['KMER_ISSUBSTRING'], T['CANONICAL_STRINGS']
+        KLR, CR = [rc_py(k) for k in KL], [rc_py(k) for k in CANON]
+        assert len(rs) == len(scan_all_golden[key]) == {'human_ont': 83, 'human_hifi': 200, 'maize_hifi': 13}[key]
+        for (name, rdat), g in zip(rs, scan_all_golden[key]):
+            flip, ori, c0, c1, bc = oracle.scan_read(rdat, KL, KLR, CANON, CR, 100)
+            assert bc.tolist() == g['bc'] and bool(flip) == g['flip'], name
+            assert sha1_of(c0.astype(np.uint8)) == g['dens_p'] and sha1_of(c1.astype(np.uint8)) == g['dens_q'], name
+            assert hits_digest(oracle.nonoverlapping_hits(ori[-6000:], KLR, ISSUB)) == (g['hits'], g['n_spans']), name
+            n += 1
+    assert n == 296
+
+
+def _nw_by_enumeration(a, b, P):
+    """Needleman-Wunsch score from the DEFINITION in Biopython's documentation, not from a recurrence: the maximum over ALL
+    global alignments of the sum of the column scores, where a gap column costs the left end-gap score if the gapped
+    sequence has no letter to its left, the right end-gap score if it has none to its right, the internal gap score
+    otherwise (open == extend at every call site that reaches score(), tg_align.py:71-106)."""
+    n, m = len(a), len(b)
+
+    def sub(x, y):
+        if P.S is not None:
+            return P.S[oracle.ALPHABET.index(x), oracle.ALPHABET.index(y)]
+        return P.match if x == y else P.mismatch
+    best = [None]
+
+    def walk(i, j, score):
+        if i == n and j == m:
+            if best[0] is None or score > best[0]:
+                best[0] = score
+            return
+        if i < n and j < m:
+            walk(i + 1, j + 1, score + sub(a[i], b[j]))
+        if i < n:                                   # a[i] against a gap in b: b has consumed j of its m letters
+            walk(i + 1, j, score + (P.gl if j == 0 else P.gr if j == m else P.g))
+        if j < m:                                   # b[j] against a gap in a
+            walk(i, j + 1, score + (P.gl if i == 0 else P.gr if i == n else P.g))
+    walk(0, 0, 0.0)
+    return best[0]
+
+
+def test_nw_restatement_equals_exhaustive_enumeration_of_alignments():
+    """Second, independent restatement of the one unpinned piece (Bio.Align.PairwiseAligner.score): brute force over every
+    alignment of short sequences, all four end-gap configurations, both scoring modes."""
+    rng = np.random.default_rng(11)
+    letters = list('ACDEFY')
+    S = oracle.scoring_matrix('C', 'tvr')
+    n_cases = 0
+    for trial in range(40):
+        n, m = int(rng.integers(1, 7)), int(rng.integers(1, 7))
+        a, b = ''.join(rng.choice(letters, n)), ''.join(rng.choice(letters, m))
+        for gb in ((True, True), (True, False), (False, True), (False, False)):
+            for Sm in (S, None):
+                P = oracle.AlignerParams(Sm, gb)
+                assert oracle.nw_score(a, b, P) == _nw_by_enumeration(a, b, P), (a, b, gb, Sm is None)
+                n_cases += 1
+    assert n_cases == 320
+
+
+def test_nw_properties():
+    """Size-independent properties any global alignment score must have (the score stays unpinned against Biopython itself)."""
+    rng = np.random.default_rng(12)
+    letters = list('ACDEFHTVY')
+    S = oracle.scoring_matrix('C', 'tvr')
+    for trial in range(30):
+        n, m = int(rng.integers(1, 300)), int(rng.integers(1, 300))
+        a, b = ''.join(rng.choice(letters, n)), ''.join(rng.choice(letters, m))
+        for gb in ((True, True), (True, False)):
+            for Sm in (S, None):
+                P = oracle.AlignerParams(Sm, gb)
+                s_ab = oracle.nw_score(a, b, P)
+                assert s_ab == oracle.nw_score(b, a, P)                                   # symmetric scoring -> symmetric score
+                assert s_ab == oracle.nw_score(a[::-1], b[::-1], oracle.AlignerParams(Sm, gb[::-1]))      # mirror image
+                assert s_ab <= oracle.iden_score(a, a, P) / 2 + oracle.iden_score(b, b, P) / 2 or Sm is not None
+                assert s_ab >= P.gl * 0 + (-4.0) * (n + m)                                # all-gap alignment is a lower bound
+                assert oracle.nw_score(a, b, oracle.AlignerParams(Sm, (gb[0], False))) >= s_ab     # freeing end gaps never hurts
+        P = oracle.AlignerParams(None, (True, True))
+        assert oracle.nw_score(a, a, P) == 5.0 * n
