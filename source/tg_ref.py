@@ -1,0 +1,4 @@
+"""The reference's source/tg_ref.py, unchanged (outside the hot path)."""
+from source._overlay import exec_reference
+
+exec_reference(__name__, globals())
