@@ -209,7 +209,8 @@ class DistEngine:
             return none, none
         N = np.maximum(jobs['n'][:, 0], jobs['n'][:, 1]).astype(np.int64)
         M = np.maximum(jobs['m'][:, 0], jobs['m'][:, 1]).astype(np.int64)
-        ok16 = int(sp.max()) * np.minimum(N, M) <= 65535
+        # (the row letters of a job live in shared memory: rows beyond MAX_WAVE32_LEN go to the generic kernel in both widths)
+        ok16 = (int(sp.max()) * np.minimum(N, M) <= 65535) & (N <= MAX_WAVE32_LEN)
         ok32 = ~ok16 & (N <= MAX_WAVE32_LEN)
         return ok16, ok32
 
@@ -264,6 +265,10 @@ class DistEngine:
         many=True: `sequences` is a list of sequence lists, one independent matrix each (the per-cluster calls of
         tg_tvr.py:147-159 / 375-390 batched into one pair space)."""
         groups = [list(g) for g in sequences] if many else [sequences]
+        if many:
+            # a group without a pair is never aligned upstream (zeros((n, n)), tg_align.py:158): its sequences may be
+            # anything, including empty -- keep its size, not its letters
+            groups = [g if len(g) >= 2 else ['A'] * len(g) for g in groups]
         flat = [s for g in groups for s in g]
         sizes = np.array([len(g) for g in groups], dtype=np.int64)
         if int((sizes * (sizes - 1) // 2).sum()) == 0:
@@ -308,13 +313,20 @@ class DistEngine:
         torch = self.torch
         n_seq, n_codes, max_len = st['n_seq'], st['n_codes'], st['max_len']
         n_pairs = st['n_pairs']
+        if abs(int(rng_seed)) + n_pairs >= 2 ** 63:
+            # the device forms |rng_seed + p| in 64 bits (one or two init_by_array key words); CPython takes any int
+            raise NotImplementedError('rng_seed beyond 63 bits is not supported on the device path')
         R = max(int(R), 0)
         slot = 2 * R * max_len
         streamed = bool(streamed and R > 0 and not self.single_kernel_shuffle)
         mt_per_pair = (self.L.tg_dist_batch_mt_work_bytes(1024, R, max_len) - 256) // 1024 if streamed else 0
         cap = self.pairs_per_batch
         if slot:
-            cap = max(2, min(cap, self.shuffle_bytes_per_batch // (slot + mt_per_pair)))
+            budget = self.shuffle_bytes_per_batch
+            if self.device.type == 'cuda':
+                # leave room for the other whole-call arrays and for other processes on the device
+                budget = max(64 << 20, min(budget, torch.cuda.mem_get_info(self.device)[0] // 2))
+            cap = max(2, min(cap, budget // (slot + mt_per_pair)))
         cap -= cap % 2
         # pair ranges owned by this rank: blocks of sorted pair space dealt round-robin
         rank, world = shard if shard is not None else (0, 1)

@@ -324,3 +324,26 @@ def test_full_iter0_matrices_of_the_bundled_sets(tga, colorvecs, key, n):
     a1 = fcluster(linkage(squareform(D / 10.0), method='ward'), 0.2, 'distance')
     a2 = fcluster(linkage(squareform(Do / 10.0), method='ward'), 0.2, 'distance')
     assert np.array_equal(a1, a2)
+
+
+def test_against_real_biopython_when_importable(tga, colorvecs):
+    """The one unpinned piece: Bio.Align.PairwiseAligner.score.  Skipped where Biopython is absent (the build image and the GPU
+    boxes: profiles/r02_pin_biopython_*.log); wherever it is importable this compares the CUDA matrices with the reference's
+    tvr_distance arithmetic around the REAL aligner (tools/pin_biopython.py holds the same code for freezing golden vectors)."""
+    pytest.importorskip('Bio')
+    import os
+    import sys
+    from itertools import combinations
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tools'))
+    import pin_biopython
+    ont, hifi = _cases(colorvecs)
+    for seqs, S_type, gb, adj, R in (([c[:1000] for c in ont[:20]], 'tvr', (True, True), True, 2),
+                                     ([c[:700 + 61 * i] for i, c in enumerate(hifi[:14])], None, (True, False), False, 3)):
+        S = tga.get_scoring_matrix('C', S_type) if S_type else None
+        aligner = tga.get_aligner_object(S, gb, 'tvr')
+        assert type(aligner).__module__.startswith('Bio.')
+        diag = {ch: float(S[ch, ch]) for ch in tga.AMINO} if S is not None else None
+        D = tga.get_dist_matrix_parallel(seqs, aligner, adj, adj, R, rng_seed=4242)
+        for p, (i, j) in enumerate(combinations(range(len(seqs)), 2)):
+            d, _aln, _rs = pin_biopython.tvr_distance(seqs[i], seqs[j], aligner, adj, adj, R, 4242 + p, diag)
+            assert D[i, j] == np.float32(d) == D[j, i], (i, j)
