@@ -639,7 +639,10 @@ def fast_ranges(n_pairs, rank, world, min_block=4096):
     """Pair ranges (sorted pair space) owned by `rank`: the blocks DistEngine._launch_fast deals round-robin."""
     if world <= 1:
         return [(0, n_pairs)]
-    blk = max(min_block, -(-n_pairs // (world * 8)))
+    # several blocks per rank even out the cost gradient of the sorted pair space (longest sequences first); every block is
+    # at least one batch of kernels, so no more of them than needed to keep a block around half a million pairs
+    per_rank = max(2, min(8, (n_pairs // world) >> 19))
+    blk = max(min_block, -(-n_pairs // (world * per_rank)))
     blk += blk % 2
     return [(b, min(b + blk, n_pairs)) for b in range(rank * blk, n_pairs, world * blk)]
 

@@ -281,13 +281,18 @@ class PackedReads:
         """get_nonoverlapping_kmer_hits for a batch of slices; returns one out_dat (list[K] of [[s, e], ...]) per slice."""
         K = len(kmer_list)
         ns = len(slice_read)
-        sp = self.hits_device(slice_read, slice_lo, slice_hi, kmer_list, issub).cpu().numpy()
-        self.last_hits_d2h = sp.nbytes
-        order = np.lexsort((sp[2], sp[1], sp[0]))          # by slice, k, start
-        sp = sp[:, order]
+        d_sp = self.hits_device(slice_read, slice_lo, slice_hi, kmer_list, issub)
+        # order by (slice, k, start) on the device, bring back (key, start, end) only
+        torch = self.torch
+        key = (d_sp[0].to(torch.int64) * K + d_sp[1].to(torch.int64)) * (1 << 32) + d_sp[2].to(torch.int64)
+        key, order = torch.sort(key)
+        pairs_d = torch.stack((d_sp[2][order], d_sp[3][order]), dim=1).contiguous()
+        group = (key >> 32).cpu().numpy()
+        pairs = pairs_d.cpu().numpy()
+        self.last_hits_d2h = group.nbytes + pairs.nbytes
         # one C-level conversion of all spans, then list slices per (slice, k)
-        pairs = np.ascontiguousarray(sp[2:4].T).tolist()
-        cuts = np.searchsorted(sp[0].astype(np.int64) * K + sp[1], np.arange(ns * K + 1, dtype=np.int64)).tolist()
+        pairs = pairs.tolist()
+        cuts = np.searchsorted(group, np.arange(ns * K + 1, dtype=np.int64)).tolist()
         return [[pairs[cuts[q * K + k]:cuts[q * K + k + 1]] for k in range(K)] for q in range(ns)]
 
 
