@@ -402,25 +402,36 @@ __global__ void __launch_bounds__(HIT_WARPS * 32, 1) hits_kernel(const HitParams
                     W.pe[x & (HIT_CAP - 1)] = 0ull;
                 }
                 uint32_t ev = __ballot_sync(TG_FULL_MASK, (st | en) != 0ull);
+                const uint32_t starts = __ballot_sync(TG_FULL_MASK, st != 0ull);
+                const unsigned long long mine = st ? st : en;         // a block start closes everything: its chain ends do not matter
                 while (ev) {
                     const int l = __ffs(ev) - 1;
                     ev &= ev - 1;
-                    const unsigned long long s_l = shfl64(st, l), e_l = shfl64(en, l);
+                    const unsigned long long v = shfl64(mine, l);
+                    const bool is_start = (starts >> l) & 1u;
                     // a block start closes everything still open; otherwise the chains that end here close
-                    const unsigned long long closing = s_l ? open : (e_l & open);
+                    const unsigned long long closing = is_start ? open : (v & open);
                     if (closing) {
                         const int n = __popcll(closing);
                         if (n_buf + n > HIT_BUF) { flush_spans(P, W, q, n_buf, lane); n_buf = 0; }
-                        for (int j = lane; j < n; j += 32) {         // lane j takes the j-th closing k-mer
-                            unsigned long long m = closing;
-                            for (int t = 0; t < j; t++) m &= m - 1;
-                            W.buf[n_buf + j][0] = __ffsll((long long)m) - 1;
-                            W.buf[n_buf + j][1] = s_open;
-                            W.buf[n_buf + j][2] = x0 + l;
+                        if (n == 1) {
+                            if (lane == 0) {
+                                W.buf[n_buf][0] = __ffsll((long long)closing) - 1;
+                                W.buf[n_buf][1] = s_open;
+                                W.buf[n_buf][2] = x0 + l;
+                            }
+                        } else {
+                            for (int j = lane; j < n; j += 32) {         // lane j takes the j-th closing k-mer
+                                unsigned long long m = closing;
+                                for (int t = 0; t < j; t++) m &= m - 1;
+                                W.buf[n_buf + j][0] = __ffsll((long long)m) - 1;
+                                W.buf[n_buf + j][1] = s_open;
+                                W.buf[n_buf + j][2] = x0 + l;
+                            }
                         }
                         n_buf += n;
                     }
-                    if (s_l) { open = s_l; s_open = x0 + l; } else open &= ~e_l;
+                    if (is_start) { open = v; s_open = x0 + l; } else open &= ~v;
                 }
             }
             // the C ring slots the next tile will push into / OR into
