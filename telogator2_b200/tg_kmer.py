@@ -8,6 +8,8 @@ uses (one launch per phase for all reads).  get_telomere_regions / wavelet_smoot
 import ctypes as C
 import os
 
+import gc
+
 import numpy as np
 
 from . import _lib
@@ -290,10 +292,17 @@ class PackedReads:
         group = (key >> 32).cpu().numpy()
         pairs = pairs_d.cpu().numpy()
         self.last_hits_d2h = group.nbytes + pairs.nbytes
-        # one C-level conversion of all spans, then list slices per (slice, k)
-        pairs = pairs.tolist()
-        cuts = np.searchsorted(group, np.arange(ns * K + 1, dtype=np.int64)).tolist()
-        return [[pairs[cuts[q * K + k]:cuts[q * K + k + 1]] for k in range(K)] for q in range(ns)]
+        # one C-level conversion of all spans, then list slices per (slice, k); the cycle collector is paused while the
+        # millions of small lists are made (it finds nothing and costs 4x)
+        gc_was_on = gc.isenabled()
+        gc.disable()
+        try:
+            pairs = pairs.tolist()
+            cuts = np.searchsorted(group, np.arange(ns * K + 1, dtype=np.int64)).tolist()
+            return [[pairs[cuts[q * K + k]:cuts[q * K + k + 1]] for k in range(K)] for q in range(ns)]
+        finally:
+            if gc_was_on:
+                gc.enable()
 
 
 # ------------------------------------------------------------------------------------------------

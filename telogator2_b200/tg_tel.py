@@ -20,7 +20,9 @@ import numpy as np
 import time
 
 from . import tg_kmer
-from .tg_util import RC
+import gc
+
+from .tg_util import rc_clean
 
 LAST_STATS = {}          # byte counts and phase times of the most recent local batch (bench.py reads them)
 
@@ -63,6 +65,23 @@ def _tel_repeat_comp_local(all_read_dat, gtrc_params, get_terminating_tl=None, i
      MIN_INTERSTITIAL_TL, MIN_FUSION_ANCHOR] = gtrc_params
     if get_terminating_tl is None:
         get_terminating_tl = _reference_get_terminating_tl()
+    # millions of small result lists are built below; the cycle collector only slows that down (4x on the list assembly)
+    gc_was_on = gc.isenabled()
+    gc.disable()
+    try:
+        return _tel_repeat_comp_phases(all_read_dat, gtrc_params, get_terminating_tl, index_offset, return_meta)
+    finally:
+        if gc_was_on:
+            gc.enable()
+
+
+def _tel_repeat_comp_phases(all_read_dat, gtrc_params, get_terminating_tl, index_offset, return_meta):
+    [READ_TYPE, DUMMY_TEL_MAPQ,
+     KMER_LIST, KMER_LIST_REV, KMER_ISSUBSTRING, CANONICAL_STRINGS, CANONICAL_STRINGS_REV,
+     TEL_WINDOW_SIZE, P_VS_Q_AMP_THRESH,
+     MIN_TEL_SCORE, FILT_TERM_TEL, FILT_TERM_NONTEL, FILT_TERM_SUBTEL,
+     PLOT_TEL_SIGNALS, TEL_SIGNAL_DIR,
+     MIN_INTERSTITIAL_TL, MIN_FUSION_ANCHOR] = gtrc_params
     gtt_min_tel_score = MIN_TEL_SCORE                               # tg_tel.py:248-251
     if FILT_TERM_TEL > 0:
         gtt_min_tel_score = min(FILT_TERM_TEL, MIN_TEL_SCORE)
@@ -89,7 +108,7 @@ def _tel_repeat_comp_local(all_read_dat, gtrc_params, get_terminating_tl=None, i
     for i in range(n_reads):
         (my_rnm, my_rdat, my_qdat) = all_read_dat[i]
         if flip[i]:
-            my_rdat = RC(my_rdat)
+            my_rdat = rc_clean(my_rdat)                         # (orient() above raised RC()'s KeyError for reads outside ACGTN)
             if my_qdat is not None:
                 my_qdat = my_qdat[::-1]
         if PLOT_TEL_SIGNALS:                                        # tg_tel.py:269-273 (pool passed the read index)
