@@ -303,6 +303,47 @@ int tg_prefilter_count(const uint8_t *d_ascii, const int64_t *d_base_off, const 
                        const char *kmer_a, const char *kmer_b, int klen, int32_t *d_count_a, int32_t *d_count_b,
                        void *d_counter, void *stream);
 
+/* =========================================================================================
+ * Telomere-boundary calling: tg_kmer.get_telomere_regions (tg_kmer.py:105-142), wavelet_smooth / mad
+ * (tg_kmer.py:145-170: pywt.wavedec / threshold / waverec, wavelet 'db4', mode 'per') and tg_tel.get_terminating_tl
+ * (tg_tel.py:156-235), for a batch of reads.
+ *
+ * Per read r: n = d_sig_n[r] power samples (len(read) - window, or 0), float64 slabs at element offsets d_x_off[r]
+ * (even(n) samples), d_a_off[r] (approximations a_1..a_L, each padded to an even length) and d_d_off[r] (details d_1..d_L,
+ * contiguous; d_d_off has n_reads + 1 entries), m_0 = n, m_l = ceil(m_(l-1) / 2), L = floor(log2(n / 7)).  max_n = the
+ * largest n of the batch (grid sizing).
+ * ======================================================================================= */
+
+/* X[r][i] = cnt_p[base_off[r] + i] / window - cnt_q[base_off[r] + i] / window, i < n: the p-vs-q power signal from the two
+ * window-count planes of tg_scan_density (tg_kmer.py:90, 114-115). */
+int tg_bound_power(const uint8_t *d_cnt_p, const uint8_t *d_cnt_q, const int64_t *d_base_off, const int32_t *d_sig_n,
+                   const int64_t *d_x_off, int n_reads, int max_n, int window, double *d_X, void *stream);
+
+/* wavelet_smooth(X[r]) in place for every read with n >= window (tg_kmer.py:116-117, 152-170): d_smoothed[r] = 1 and
+ * d_out_len[r] = even(n) when the signal was replaced by its reconstruction, 0 and n when one of the two early-outs
+ * (fewer than smoothing_level coefficient arrays; sigma < fail_sigma) left it as it was.  d_log_factor[r] = sqrt(2 ln n)
+ * (host); d_sigma / d_uthresh receive mad(coeff[-smoothing_level]) and the threshold.  d_scratch / d_sc_off: sort space for
+ * reads whose coeff[-smoothing_level] has more than 4096 entries (offset per read, -1 = not needed). */
+int tg_bound_smooth(double *d_X, double *d_A, double *d_D, const int64_t *d_x_off, const int64_t *d_a_off,
+                    const int64_t *d_d_off, const int32_t *d_sig_n, int n_reads, int max_n, int window,
+                    int smoothing_level, double fail_sigma, const double *d_log_factor, double *d_scratch,
+                    const int64_t *d_sc_off, double *d_uthresh, double *d_sigma, int32_t *d_out_len,
+                    uint8_t *d_smoothed, void *stream);
+
+/* Region walk over X[r][: out_len - window] (tg_kmer.py:118-140): maximal runs of one class (1 'p' >= pthresh, 2 'q' <=
+ * -pthresh, 0 None).  d_reg_off == NULL: count only (d_reg_count, d_last_end, d_err); else also d_reg_start / d_reg_cls at
+ * d_reg_off[r].  The end of a region is the start of the next one; the last region ends at d_last_end[r].  d_err[r] = 1
+ * where the reference raises IndexError (empty signal); reads with n < window give the single region [0, 0, None]. */
+int tg_bound_regions(const double *d_X, const int64_t *d_x_off, const int32_t *d_sig_n, const int32_t *d_out_len,
+                     int n_reads, int window, double pthresh, const int64_t *d_reg_off, int32_t *d_reg_count,
+                     int32_t *d_reg_start, uint8_t *d_reg_cls, int32_t *d_last_end, uint8_t *d_err, void *stream);
+
+/* get_terminating_tl's scoring on the region lists (tg_tel.py:164-233): d_out[r] = (tel_len, edge_nontel, a, b) with
+ * (a, b) the largest interstitial telomere region or (-1, -1). */
+int tg_bound_terminating(const int64_t *d_reg_off, const int32_t *d_reg_count, const int32_t *d_reg_start,
+                         const uint8_t *d_reg_cls, const int32_t *d_last_end, int n_reads, int pq_is_p, int window,
+                         double min_tel_score, int32_t *d_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,7 +57,8 @@ EXPORTS = ['tg_last_error', 'tg_version', 'tg_device_sm_count',
            'tg_kmer_table_bytes', 'tg_kmer_table_build', 'tg_kmer_table_pair_bytes', 'tg_kmer_table_build_pair', 'tg_scan_pack', 'tg_scan_basecount', 'tg_scan_orient',
            'tg_scan_density', 'tg_scan_hits',
            'tg_cv_paint', 'tg_cv_density_boundary', 'tg_cv_lead_run', 'tg_cv_gather', 'tg_cv_denoise_tile', 'tg_cv_denoise',
-           'tg_prefilter_tail_bytes', 'tg_prefilter_count']
+           'tg_prefilter_tail_bytes', 'tg_prefilter_count',
+           'tg_bound_power', 'tg_bound_smooth', 'tg_bound_regions', 'tg_bound_terminating']
 
 
 def load():
@@ -101,6 +102,11 @@ def load():
     L.tg_cv_gather.argtypes = [vp, vp, vp, vp, i64, vp, vp]
     L.tg_cv_denoise.argtypes = [vp, vp, vp, vp, vp, vp, i32, i64, i32, i32, i32, C.c_char_p, i32, C.c_char_p, i32, vp, vp]
     L.tg_prefilter_count.argtypes = [vp, vp, vp, i32, C.c_char_p, C.c_char_p, i32, vp, vp, vp, vp]
+    f64 = C.c_double
+    L.tg_bound_power.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp]
+    L.tg_bound_smooth.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f64, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.tg_bound_regions.argtypes = [vp, vp, vp, vp, i32, i32, f64, vp, vp, vp, vp, vp, vp, vp]
+    L.tg_bound_terminating.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, f64, vp, vp]
     _lib = L
     return L
 

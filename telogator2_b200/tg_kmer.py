@@ -3,7 +3,7 @@
 Per-read functions keep the reference's names, signatures and return types and run as a batch of
 one on the GPU; the *_batch / ScanSession entry points are what tg_tel.get_tel_repeat_comp_parallel
 uses (one launch per phase for all reads).  get_telomere_regions / wavelet_smooth / mad
-(tg_kmer.py:105-170, pywt float code) are outside the hot path and stay the reference's own.
+(tg_kmer.py:105-170) run on the device as well, through telogator2_b200.tg_boundary.
 """
 import ctypes as C
 import os
@@ -350,3 +350,48 @@ def get_nonoverlapping_kmer_hits(my_telseq, KMER_LIST, KMER_ISSUBSTRING, mode='h
         return [[] for _ in KMER_LIST]
     pr = PackedReads([my_telseq])
     return pr.hits([0], [0], [len(my_telseq)], KMER_LIST, KMER_ISSUBSTRING)[0]
+
+
+# ------------------------------------------------------------------------------------------------
+# boundary calling (tg_kmer.py:105-170), batch of one on the device (tg_boundary.py)
+# ------------------------------------------------------------------------------------------------
+def get_telomere_regions(td_p_e0, td_p_e1, td_q_e0, td_q_e1, tel_window, pthresh, mode='hifi', smoothing=True):
+    """tg_kmer.py:105-142 -> (p_vs_q_power float64 ndarray, [[start, end, None | 'p' | 'q'], ...])."""
+    from .tg_boundary import BoundaryBatch
+    lens = [len(td_p_e0), len(td_p_e1), len(td_q_e0), len(td_q_e1)]
+    min_win_pos, max_win_pos = min(lens), max(lens)
+    if max_win_pos < tel_window:
+        return ([], [[0, 0, None]])
+    power = np.zeros(max_win_pos)
+    power[:min_win_pos] = (np.asarray(td_p_e0[:min_win_pos], dtype=np.float64)
+                           - np.asarray(td_q_e0[:min_win_pos], dtype=np.float64))          # :114-115
+    bb = BoundaryBatch([max_win_pos], tel_window)
+    bb.power_from_host([power])
+    if smoothing:
+        bb.smooth()
+    else:
+        bb.no_smoothing()
+    bb.regions(pthresh)
+    return (bb.signal_host(0), bb.regions_host(0))
+
+
+def mad(x, c=1.4826):
+    """tg_kmer.py:145-149: median absolute deviation (numpy; the batch path computes it on the device)."""
+    return c * np.median(np.abs(x - np.median(x)))
+
+
+def wavelet_smooth(x, wavelet="db4", smoothing_level=5, fail_sigma=1e-3):
+    """tg_kmer.py:152-170 for the only configuration the reference uses (db4, level 5, 1e-3); returns x itself when one
+    of the early-outs applies, else the reconstruction (one sample longer than an odd-length input, as pywt.waverec)."""
+    from . import tg_boundary
+    if wavelet != 'db4' or smoothing_level != tg_boundary.SMOOTHING_LEVEL or fail_sigma != tg_boundary.FAIL_SIGMA:
+        raise NotImplementedError('wavelet_smooth: only db4 / smoothing_level 5 / fail_sigma 1e-3 (the reference never passes others)')
+    sig = np.asarray(x, dtype=np.float64)
+    if len(sig) == 0:
+        return x
+    bb = tg_boundary.BoundaryBatch([len(sig)], 1)
+    bb.power_from_host([sig])
+    bb.smooth()
+    if not int(bb.d_smoothed[0].item()):
+        return x
+    return bb.signal_host(0, trimmed=False)

@@ -19,7 +19,7 @@ import numpy as np
 
 import time
 
-from . import tg_kmer
+from . import tg_boundary, tg_kmer
 import gc
 
 from .tg_util import rc_clean
@@ -63,7 +63,7 @@ def _tel_repeat_comp_local(all_read_dat, gtrc_params, get_terminating_tl=None, i
      MIN_TEL_SCORE, FILT_TERM_TEL, FILT_TERM_NONTEL, FILT_TERM_SUBTEL,
      PLOT_TEL_SIGNALS, TEL_SIGNAL_DIR,
      MIN_INTERSTITIAL_TL, MIN_FUSION_ANCHOR] = gtrc_params
-    if get_terminating_tl is None:
+    if get_terminating_tl is None and gtrc_params[13]:            # PLOT_TEL_SIGNALS: the plots are drawn by the reference's function
         get_terminating_tl = _reference_get_terminating_tl()
     # millions of small result lists are built below; the cycle collector only slows that down (4x on the list assembly)
     gc_was_on = gc.isenabled()
@@ -96,106 +96,128 @@ def _tel_repeat_comp_phases(all_read_dat, gtrc_params, get_terminating_tl, index
     flip = bc[:, 0] > bc[:, 1]                                      # tg_tel.py:265
     pr.orient(flip)
     d_p, d_q = pr.density_counts(KMER_LIST, KMER_LIST_REV, TEL_WINDOW_SIZE)
-    h_p, h_q = pr.counts_to_host(d_p, d_q)
-    cnt_p = pr.split_counts(h_p, TEL_WINDOW_SIZE)
-    cnt_q = pr.split_counts(h_q, TEL_WINDOW_SIZE)
-    t_ph.append(time.perf_counter())
+    lens = pr.lens.astype(np.int64)
+    d2h = bc.nbytes
+    oriented = [None] * n_reads                                     # the read as the reference sees it after :265-266
 
-    # ---- phase 2: CPU, per read, the reference's own boundary calling and filters ----
-    per_read = []
-    slices = {'tvr': ([], [], []), 'ifwd': ([], [], []), 'irev': ([], [], [])}
-    tel_signal_plot_num = 0
-    for i in range(n_reads):
-        (my_rnm, my_rdat, my_qdat) = all_read_dat[i]
-        if flip[i]:
-            my_rdat = rc_clean(my_rdat)                         # (orient() above raised RC()'s KeyError for reads outside ACGTN)
-            if my_qdat is not None:
-                my_qdat = my_qdat[::-1]
-        if PLOT_TEL_SIGNALS:                                        # tg_tel.py:269-273 (pool passed the read index)
-            tel_signal_plot_dat = (my_rnm, TEL_SIGNAL_DIR + 'signal_' + str(i + index_offset).zfill(5) + '.png')
-            tel_signal_plot_num += 1
-        else:
-            tel_signal_plot_dat = None
-        # densities as float64 arrays (every consumer only needs len(), indexing and numpy conversion: tg_kmer.py:106-115,
-        # tg_plot.py:84-98); the all-zero second track of the reference (tg_kmer.py:67-76) is one shared read-only view
-        n_out = len(cnt_p[i])
-        zeros = np.broadcast_to(np.float64(0.0), (n_out,))
-        tg_kmer.prime_density_cache(my_rdat, KMER_LIST, TEL_WINDOW_SIZE, (cnt_p[i].astype(np.float64) / TEL_WINDOW_SIZE, zeros))
-        tg_kmer.prime_density_cache(my_rdat, KMER_LIST_REV, TEL_WINDOW_SIZE, (cnt_q[i].astype(np.float64) / TEL_WINDOW_SIZE, zeros))
-        try:
-            (my_terminating_tel, my_nontel_end, interstitial_tel) = get_terminating_tl(my_rdat, 'q', gtt_params,
-                                                                                       telplot_dat=tel_signal_plot_dat)
-        finally:
-            tg_kmer.clear_density_cache()
-        my_terminating_tel = min(my_terminating_tel, len(my_rdat))  # tg_tel.py:278-279
-        my_nontel_end = min(my_nontel_end, len(my_rdat))
-        st = {'rdat': my_rdat, 'rnm': my_rnm, 'isubtels': None, 'want_i': False, 'want_tvr': False,
-              'termtel': my_terminating_tel, 'nontelend': my_nontel_end}
-        if my_terminating_tel == 0 and interstitial_tel is not None and interstitial_tel[1] - interstitial_tel[0] >= MIN_INTERSTITIAL_TL:
-            isubtel_left = my_rdat[:interstitial_tel[0]]            # tg_tel.py:281-290
-            isubtel_right = my_rdat[interstitial_tel[1]:]
-            if len(isubtel_left) >= MIN_FUSION_ANCHOR and len(isubtel_right) >= MIN_FUSION_ANCHOR:
-                st['isubtels'] = [(f'interstitial-left_{len(my_rdat)}_{my_rnm}', isubtel_left),
-                                  (f'interstitial-right_{len(my_rdat)}_{my_rnm}', isubtel_right)]
-                st['want_i'] = True
-                for key in ('ifwd', 'irev'):
-                    slices[key][0].append(i); slices[key][1].append(0); slices[key][2].append(len(my_rdat))
-        st['skipped_termtel'] = bool(FILT_TERM_TEL > 0 and my_terminating_tel < FILT_TERM_TEL)         # tg_tel.py:292-298
-        st['skipped_termunk'] = bool(FILT_TERM_NONTEL > 0 and my_nontel_end > FILT_TERM_NONTEL)
-        st['skipped_termsub'] = bool(FILT_TERM_SUBTEL > 0 and len(my_rdat) < my_terminating_tel + FILT_TERM_SUBTEL)
-        if not (st['skipped_termtel'] or st['skipped_termunk'] or st['skipped_termsub']):
-            my_subtel_end = max(len(my_rdat) - my_terminating_tel - FILT_TERM_SUBTEL, 0)                # tg_tel.py:301-305
-            lo, hi = my_subtel_end, len(my_rdat)
-            if hi - lo == 0:
-                lo = 0
-            st['want_tvr'] = True
-            st['tvr_len'] = hi - lo
-            slices['tvr'][0].append(i); slices['tvr'][1].append(lo); slices['tvr'][2].append(hi)
-        per_read.append(st)
+    def rdat_of(i):
+        if oriented[i] is None:
+            # (orient() above raised RC()'s KeyError for reads outside ACGTN)
+            oriented[i] = rc_clean(all_read_dat[i][1]) if flip[i] else all_read_dat[i][1]
+        return oriented[i]
+
+    # ---- phase 2: boundary calling per read (tg_tel.py:276-279) ----
+    if get_terminating_tl is None:
+        # on the device, from the window counts where they lie (tg_boundary.py)
+        term = tg_boundary.terminating_tl_from_counts(d_p, d_q, pr.d_base_off, lens, TEL_WINDOW_SIZE, P_VS_Q_AMP_THRESH,
+                                                      gtt_min_tel_score, 'q')
+        d2h += term.nbytes
+        t_ph.append(time.perf_counter())
+    else:
+        # a caller-supplied get_terminating_tl (e.g. the reference's own, for the telomere-signal plots): per read on the
+        # host; its get_telomere_kmer_density calls are served from the densities computed above
+        h_p, h_q = pr.counts_to_host(d_p, d_q)
+        cnt_p = pr.split_counts(h_p, TEL_WINDOW_SIZE)
+        cnt_q = pr.split_counts(h_q, TEL_WINDOW_SIZE)
+        d2h += 2 * int(getattr(pr, 'total', 0))
+        t_ph.append(time.perf_counter())
+        term = np.full((n_reads, 4), -1, dtype=np.int64)
+        for i in range(n_reads):
+            my_rdat = rdat_of(i)
+            if PLOT_TEL_SIGNALS:                                    # tg_tel.py:269-273 (pool passed the read index)
+                tel_signal_plot_dat = (all_read_dat[i][0], TEL_SIGNAL_DIR + 'signal_' + str(i + index_offset).zfill(5) + '.png')
+            else:
+                tel_signal_plot_dat = None
+            # densities as float64 arrays (every consumer only needs len(), indexing and numpy conversion: tg_kmer.py:106-115,
+            # tg_plot.py:84-98); the all-zero second track of the reference (tg_kmer.py:67-76) is one shared read-only view
+            n_out = len(cnt_p[i])
+            zeros = np.broadcast_to(np.float64(0.0), (n_out,))
+            tg_kmer.prime_density_cache(my_rdat, KMER_LIST, TEL_WINDOW_SIZE, (cnt_p[i].astype(np.float64) / TEL_WINDOW_SIZE, zeros))
+            tg_kmer.prime_density_cache(my_rdat, KMER_LIST_REV, TEL_WINDOW_SIZE, (cnt_q[i].astype(np.float64) / TEL_WINDOW_SIZE, zeros))
+            try:
+                (tl, nontel, inter) = get_terminating_tl(my_rdat, 'q', gtt_params, telplot_dat=tel_signal_plot_dat)
+            finally:
+                tg_kmer.clear_density_cache()
+            term[i, 0], term[i, 1] = tl, nontel
+            if inter is not None:
+                term[i, 2], term[i, 3] = inter[0], inter[1]
+    termtel = np.minimum(term[:, 0].astype(np.int64), lens)        # tg_tel.py:278-279
+    nontelend = np.minimum(term[:, 1].astype(np.int64), lens)
+    ia, ib = term[:, 2].astype(np.int64), term[:, 3].astype(np.int64)
+    # interstitial-telomere candidates (tg_tel.py:281-290): both anchors long enough
+    want_i = (termtel == 0) & (ia >= 0) & (ib - ia >= MIN_INTERSTITIAL_TL) \
+        & (np.minimum(ia, lens) >= MIN_FUSION_ANCHOR) & (np.maximum(lens - ib, 0) >= MIN_FUSION_ANCHOR)
+    skipped_termtel = (termtel < FILT_TERM_TEL) if FILT_TERM_TEL > 0 else np.zeros(n_reads, dtype=bool)          # :292-298
+    skipped_termunk = (nontelend > FILT_TERM_NONTEL) if FILT_TERM_NONTEL > 0 else np.zeros(n_reads, dtype=bool)
+    skipped_termsub = (lens < termtel + FILT_TERM_SUBTEL) if FILT_TERM_SUBTEL > 0 else np.zeros(n_reads, dtype=bool)
+    want_tvr = ~(skipped_termtel | skipped_termunk | skipped_termsub)
+    tvr_lo = np.maximum(lens - termtel - FILT_TERM_SUBTEL, 0)       # tg_tel.py:301-305
+    tvr_lo = np.where(lens - tvr_lo == 0, 0, tvr_lo)
+    tvr_idx = np.nonzero(want_tvr)[0]
+    i_idx = np.nonzero(want_i)[0]
 
     # ---- phase 3: GPU, all hit slices at once (reads are already oriented on the device) ----
     t_ph.append(time.perf_counter())
-    d2h = bc.nbytes + 2 * int(getattr(pr, 'total', 0))
-    hits_tvr = pr.hits(*slices['tvr'], KMER_LIST_REV, KMER_ISSUBSTRING)
+    hits_tvr = pr.hits(tvr_idx, tvr_lo[tvr_idx], lens[tvr_idx], KMER_LIST_REV, KMER_ISSUBSTRING)
     d2h += getattr(pr, 'last_hits_d2h', 0)
-    hits_ifwd = pr.hits(*slices['ifwd'], KMER_LIST, KMER_ISSUBSTRING)
-    hits_irev = pr.hits(*slices['irev'], KMER_LIST_REV, KMER_ISSUBSTRING)
+    hits_ifwd = pr.hits(i_idx, np.zeros_like(i_idx), lens[i_idx], KMER_LIST, KMER_ISSUBSTRING)
+    hits_irev = pr.hits(i_idx, np.zeros_like(i_idx), lens[i_idx], KMER_LIST_REV, KMER_ISSUBSTRING)
+    t_ph.append(time.perf_counter())
+
+    # ---- results in read order (tg_tel.py:352-375) ----
+    kmer_hit_dat, interstitial_subtels = [], []
+    interstitial_khd_by_readname, interstitial_khd_rev_by_readname = {}, {}
+    meta = {'tvr': [], 'interstitial': []}
+    tvr_len = (lens - tvr_lo).tolist()
+    flip_l = flip.tolist()
+    for q, i in enumerate(tvr_idx.tolist()):
+        kmer_hit_dat.append([hits_tvr[q], tvr_len[i], 0, 'q', all_read_dat[i][0].split(' ')[0], DUMMY_TEL_MAPQ, rdat_of(i)])
+        meta['tvr'].append((i + index_offset, flip_l[i]))
+    for q, i in enumerate(i_idx.tolist()):
+        my_rnm, my_rdat = all_read_dat[i][0], rdat_of(i)
+        a, b = int(ia[i]), int(ib[i])
+        interstitial_subtels.append([(f'interstitial-left_{len(my_rdat)}_{my_rnm}', my_rdat[:a]),       # list of two tuples, as
+                                     (f'interstitial-right_{len(my_rdat)}_{my_rnm}', my_rdat[b:])])     # upstream
+        meta['interstitial'].append((i + index_offset, flip_l[i]))
+        interstitial_khd_by_readname[my_rnm] = [hits_ifwd[q], len(my_rdat), 0, 'q', my_rnm.split(' ')[0], DUMMY_TEL_MAPQ, my_rdat]
+        interstitial_khd_rev_by_readname[my_rnm] = [hits_irev[q], len(my_rdat), 0, 'q', my_rnm.split(' ')[0], DUMMY_TEL_MAPQ, my_rdat]
     t_ph.append(time.perf_counter())
     LAST_STATS.clear()
     LAST_STATS.update(h2d_bytes=getattr(pr, 'h2d_bytes', 0), d2h_bytes=d2h,
-                      phases={'gpu_pack_count_orient_density_d2h': t_ph[1] - t_ph[0], 'host_per_read_boundary_calling': t_ph[2] - t_ph[1],
-                              'gpu_hits_and_list_assembly': t_ph[3] - t_ph[2]})
-    it_tvr, it_i = iter(hits_tvr), iter(zip(hits_ifwd, hits_irev))
-
-    kmer_hit_dat, all_terminating_tl, all_nontel_end = [], [], []
-    reads_removed_term_tel = reads_removed_term_unk = reads_removed_term_sub = 0
-    interstitial_subtels = []
-    interstitial_khd_by_readname, interstitial_khd_rev_by_readname = {}, {}
-    meta = {'tvr': [], 'interstitial': []}
-    for i, st in enumerate(per_read):                               # tg_tel.py:352-375, read order
-        my_rdat, my_rnm = st['rdat'], st['rnm']
-        if st['want_tvr']:
-            kmer_hit_dat.append([next(it_tvr), st['tvr_len'], 0, 'q', my_rnm.split(' ')[0], DUMMY_TEL_MAPQ, my_rdat])
-            all_terminating_tl.append(st['termtel'])
-            all_nontel_end.append(st['nontelend'])
-            meta['tvr'].append((i + index_offset, bool(flip[i])))
-        if st['want_i']:
-            (hf, hr) = next(it_i)
-            interstitial_subtels.append(st['isubtels'])             # list of two tuples, as upstream
-            meta['interstitial'].append((i + index_offset, bool(flip[i])))
-            rn = all_read_dat[i][0]
-            interstitial_khd_by_readname[rn] = [hf, len(my_rdat), 0, 'q', my_rnm.split(' ')[0], DUMMY_TEL_MAPQ, my_rdat]
-            interstitial_khd_rev_by_readname[rn] = [hr, len(my_rdat), 0, 'q', my_rnm.split(' ')[0], DUMMY_TEL_MAPQ, my_rdat]
-        reads_removed_term_tel += st['skipped_termtel'] * 1
-        reads_removed_term_unk += st['skipped_termunk'] * 1
-        reads_removed_term_sub += st['skipped_termsub'] * 1
+                      phases={'gpu_pack_count_orient_density': t_ph[1] - t_ph[0], 'boundary_calling': t_ph[2] - t_ph[1],
+                              'gpu_hits_and_span_lists': t_ph[3] - t_ph[2], 'result_lists': t_ph[4] - t_ph[3]},
+                      boundary='device' if get_terminating_tl is None else 'callback')
     res = [kmer_hit_dat,
-           all_terminating_tl,
-           all_nontel_end,
-           reads_removed_term_tel,
-           reads_removed_term_unk,
-           reads_removed_term_sub,
+           termtel[tvr_idx].tolist(),
+           nontelend[tvr_idx].tolist(),
+           int(skipped_termtel.sum()),
+           int(skipped_termunk.sum()),
+           int(skipped_termsub.sum()),
            interstitial_subtels,
            interstitial_khd_by_readname,
            interstitial_khd_rev_by_readname]
     return (res, meta) if return_meta else res
+
+
+def get_terminating_tl(rdat, pq, gtt_params, telplot_dat=None):
+    """tg_tel.py:156-235 for one read (batch of one on the device) -> (tel_len, edge_nontel, largest interstitial or None)."""
+    [SIGNAL_KMERS, SIGNAL_KMERS_REV, TEL_WINDOW_SIZE, P_VS_Q_AMP_THRESH, MIN_TEL_SCORE] = gtt_params
+    pr = tg_kmer.PackedReads([rdat])
+    d_p, d_q = pr.density_counts(SIGNAL_KMERS, SIGNAL_KMERS_REV, TEL_WINDOW_SIZE)
+    n = max(len(rdat) - TEL_WINDOW_SIZE, 0)
+    bb = tg_boundary.BoundaryBatch([n], TEL_WINDOW_SIZE)
+    bb.power_from_counts(d_p, d_q, pr.d_base_off)
+    bb.smooth()
+    bb.regions(P_VS_Q_AMP_THRESH)
+    (tl, edge, a, b) = (int(v) for v in bb.terminating(pq, MIN_TEL_SCORE)[0])
+    largest = None if a < 0 else (a, b)
+    if telplot_dat is not None:                                     # tg_tel.py:221-229; plotting is the reference's own code
+        from source.tg_plot import plot_tel_signal
+        (telplot_title, telplot_fn) = telplot_dat
+        dp = (d_p[:n].cpu().numpy().astype(np.float64) / TEL_WINDOW_SIZE).tolist()
+        dq = (d_q[:n].cpu().numpy().astype(np.float64) / TEL_WINDOW_SIZE).tolist()
+        power = bb.signal_host(0) if n >= TEL_WINDOW_SIZE else []
+        density_data = [dp, [0.0] * n, dq, [0.0] * n, power, len(rdat), TEL_WINDOW_SIZE]
+        print(telplot_title, telplot_fn)
+        plot_tel_signal(density_data, telplot_title, telplot_fn, tl_vals=[0, tl] if tl > 0 else None, interstitial_tels=[largest])
+    return (tl, edge, largest)

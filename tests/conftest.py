@@ -94,3 +94,15 @@ def hits_to_array(hits):
         for sp in spans:
             k.append(ki), s.append(sp[0]), e.append(sp[1])
     return np.stack([np.array(k, np.int32), np.array(s, np.int32), np.array(e, np.int32)]) if k else np.zeros((3, 0), np.int32)
+
+
+@pytest.fixture(scope='session')
+def boundary_golden():
+    """Per read of reads_all: the REFERENCE's get_telomere_regions / get_terminating_tl outputs (make_golden_boundary.py)."""
+    with gzip.open(os.path.join(GOLDEN, 'boundary_golden.json.gz'), 'rt') as f:
+        return json.load(f)
+
+
+def regions_digest(regs):
+    cls = {None: 0, 'p': 1, 'q': 2}
+    return sha1_of(np.array([(r[0], r[1], cls[r[2]]) for r in regs], dtype=np.int32).reshape(-1, 3))

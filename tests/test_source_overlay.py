@@ -45,14 +45,18 @@ sys.path.insert(0, %r)
 import source
 from source import tg_align, tg_kmer, tg_plot, tg_reader, tg_ref, tg_tel, tg_tvr, tg_util
 import telogator2_b200.tg_align as A, telogator2_b200.tg_kmer as K, telogator2_b200.tg_tvr as V, telogator2_b200.tg_util as U
+import telogator2_b200.tg_tel as T
 ref = os.path.join(%r, 'source')
 assert tg_align.get_dist_matrix_parallel is A.get_dist_matrix_parallel and tg_align.tvr_distance is A.tvr_distance
 assert tg_align.quick_compare_tvrs is A.quick_compare_tvrs and tg_tvr.get_dist_matrix_parallel is A.get_dist_matrix_parallel
 assert tg_kmer.get_telomere_kmer_density is K.get_telomere_kmer_density and tg_kmer.get_nonoverlapping_kmer_hits is K.get_nonoverlapping_kmer_hits
 assert tg_kmer.get_telomere_base_count is K.get_telomere_base_count and tg_tvr.quick_get_tvrtel_lens is V.quick_get_tvrtel_lens
 assert tg_util.RC is U.RC and tg_tel.get_tel_repeat_comp_parallel.__module__ == 'source.tg_tel'
-for fn in (tg_kmer.get_telomere_regions, tg_kmer.read_kmer_tsv, tg_align.progressive_alignment, tg_align.get_final_tvr_consensus,
-           tg_tel.get_terminating_tl, tg_tel.get_allele_tsv_dat, tg_tvr.cluster_tvrs, tg_tvr.cluster_consensus_tvrs,
+# boundary calling (SURVEY 8f #3) is bound too; the reference's own functions stay reachable
+assert tg_kmer.get_telomere_regions is K.get_telomere_regions and tg_kmer.wavelet_smooth is K.wavelet_smooth and tg_kmer.mad is K.mad
+assert tg_tel.get_terminating_tl is T.get_terminating_tl
+for fn in (tg_kmer._reference_get_telomere_regions, tg_kmer.read_kmer_tsv, tg_align.progressive_alignment, tg_align.get_final_tvr_consensus,
+           tg_tel._reference_get_terminating_tl, tg_tel.get_allele_tsv_dat, tg_tvr.cluster_tvrs, tg_tvr.cluster_consensus_tvrs,
            tg_plot.plot_kmer_hits, tg_util.parse_read, tg_util.shuffle_seq):
     assert fn.__code__.co_filename.startswith(ref), fn
 assert hasattr(tg_reader, 'TG_Reader') and hasattr(tg_ref, 'ReferenceFasta')
