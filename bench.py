@@ -201,24 +201,6 @@ def cpu_scan_sample(reads, tables, threads, budget_bases):
     return tot / dt / 1e6, dt, tot
 
 
-def standin_gtt(density_fn):
-    """A fixed, cheap stand-in for the reference's get_terminating_tl (tg_tel.py:156-235: pywt wavelet smoothing + region
-    walk, outside the hot path), driven by the two density tracks: trailing run of q-type windows = terminal telomere.
-    The SAME function runs on both arms of `scan_e2e`."""
-    def gtt(rdat, pq, gtt_params, telplot_dat=None):
-        [KL, KLR, W, thr, min_score] = gtt_params
-        power = np.asarray(density_fn(rdat, KL, W)[0]) - np.asarray(density_fn(rdat, KLR, W)[0])
-        qt = power <= -thr
-        n = len(qt)
-        last = n - 1 - int(np.argmax(qt[::-1])) if qt.any() else -1           # a short non-telomeric tail is tolerated
-        run = (last + 1 if qt[:last + 1].all() else int(np.argmin(qt[last::-1]))) if last >= 0 else 0
-        tl = (n - (last + 1 - run)) if run >= min_score else 0
-        tl = tl + W // 2 if tl else 0
-        nontel = 0 if tl else (int(np.argmax(qt[::-1])) if qt.any() else n)
-        return (tl, nontel, None)                  # (terminal telomeres only: interstitial ones are rare in real data)
-    return gtt
-
-
 def scan_gtrc_params(T, rc):
     KL, CANON = T['KMER_LIST'], T['CANONICAL_STRINGS']
     return ['hifi', 60, KL, [rc(k) for k in KL], T['KMER_ISSUBSTRING'], CANON, [rc(k) for k in CANON], 100, 0.5, 100, 400, 100, 1000,
@@ -226,9 +208,10 @@ def scan_gtrc_params(T, rc):
 
 
 def cpu_scan_e2e_sample(reads, tables, threads, budget_bases):
-    """CPU arm of `scan_e2e`: gtrc_parallel_job (tg_tel.py:238-328) per read through the oracle's C scan functions, host
-    threads over reads, the same stand-in get_terminating_tl."""
+    """CPU arm of `scan_e2e`: gtrc_parallel_job (tg_tel.py:238-328) per read through the oracle's C scan functions and its
+    numpy boundary calling (oracle/boundary.py), host threads over reads."""
     import oracle
+    from oracle import boundary
     from concurrent.futures import ThreadPoolExecutor
     P = scan_gtrc_params(tables['human_hifi'], oracle.rc)
     [_rt, _mq, KL, KLR, ISSUB, CANON, CR, W, THR, MINS, F_TEL, F_NONTEL, F_SUB, _p, _d, _mi, _ma] = P
@@ -241,9 +224,8 @@ def cpu_scan_e2e_sample(reads, tables, threads, budget_bases):
 
     def one(r):
         _f, ori, c0, c1, _bc = oracle.scan_read(r, KL, KLR, CANON, CR, W)
-        dens = {id(KL): c0, id(KLR): c1}
-        gtt = standin_gtt(lambda rd, kl, w: (dens[id(kl)].astype(np.float64) / w, None))
-        (tl, nontel, _inter) = gtt(ori, 'q', [KL, KLR, W, THR, min(F_TEL, MINS)])
+        (tl, nontel, _inter) = boundary.get_terminating_tl(c0.astype(np.float64) / W, c1.astype(np.float64) / W, 'q', W, THR,
+                                                           min(F_TEL, MINS))
         tl, nontel = min(tl, len(ori)), min(nontel, len(ori))
         if not (tl < F_TEL or nontel > F_NONTEL or len(ori) < tl + F_SUB):
             return oracle.nonoverlapping_hits(ori[max(len(ori) - tl - F_SUB, 0):], KLR, ISSUB)
@@ -304,7 +286,7 @@ def run_reference(args, rank, world):
                      'cores': threads},
             'scan_e2e': {'value': emb, 'unit': 'Mbases/s', 'cores': threads, 'reads_kept': ekept,
                          'sample': f'{eb} bases ({edt:.1f} s): gtrc_parallel_job per read through the oracle C scan, host threads over reads, '
-                                   f'stand-in get_terminating_tl; the reference Python itself runs 0.56-1.0 Mbases/s/core (SURVEY 3)'},
+                                   f'numpy boundary calling; the reference Python itself runs 0.56-1.0 Mbases/s/core (SURVEY 3)'},
             'parity': PARITY_NOTE,
             'gpu_launches': 0}
     emit(line)
@@ -445,6 +427,26 @@ def main():
     wave_ms, wave_n = C.c_double(0), C.c_int(0)
     _lib.check(L.tg_wave_timing_read(C.byref(wave_ms), C.byref(wave_n)))
     _lib.check(L.tg_wave_timing(0))
+
+    # boundary calling on the device-resident window counts of the last step (tg_kmer.py:105-170, tg_tel.py:164-233)
+    boundary = None
+    try:
+        from telogator2_b200 import tg_boundary
+        _f, ca_, cb_, _s = scan_step()
+        del _s
+        bt = []
+        for _ in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            term = tg_boundary.terminating_tl_from_counts(ca_, cb_, pr.d_base_off, pr.lens, 100, 0.5, 100, 'q')
+            torch.cuda.synchronize()
+            bt.append(time.perf_counter() - t0)
+        boundary = {'ms': min(bt) * 1e3, 'mbases_per_s': float(pr.lens.sum()) / min(bt) / 1e6, 'reads_with_telomere': int((term[:, 0] > 0).sum()),
+                    'what': 'power signal + db4 wavelet smoothing + region walk + scoring for every read, host wall clock incl. the '
+                            '16 B/read result copy; ~100 B of float64 traffic per base'}
+        del ca_, cb_
+    except Exception as exc:                          # an auxiliary line must not cost the headline metric
+        boundary = {'error': f'{type(exc).__name__}: {exc}'}
 
     def allmax(x):
         t = torch.tensor([x], dtype=torch.float64, device='cuda')
@@ -624,31 +626,21 @@ def main():
             from telogator2_b200 import tg_tel
             gp = scan_gtrc_params(T, tg_kmer.RC)
             ard = [(f'read{i}', r, None) for i, r in enumerate(scan_reads)]
-            gtt_inner = standin_gtt(tg_kmer.get_telomere_kmer_density)
-            gtt_s = [0.0]
-
-            def gtt(*a, **k):                         # the callback's own time is reported beside the total
-                t_in = time.perf_counter()
-                try:
-                    return gtt_inner(*a, **k)
-                finally:
-                    gtt_s[0] += time.perf_counter() - t_in
-            tg_tel.get_tel_repeat_comp_parallel(ard[:64], gp, get_terminating_tl=gtt)
-            gtt_s[0] = 0.0
+            tg_tel.get_tel_repeat_comp_parallel(ard[:64], gp)
             st = []
             for _ in range(2):
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
-                res = tg_tel.get_tel_repeat_comp_parallel(ard, gp, get_terminating_tl=gtt)
+                res = tg_tel.get_tel_repeat_comp_parallel(ard, gp)
                 st.append(time.perf_counter() - t0)
             n_spans = sum(len(sp) for khd in res[0] for sp in khd[0])
             scan_e2e = {'value': scan_bases / float(np.mean(st)) / 1e6, 'unit': 'Mbases/s', 'ms_per_step': float(np.mean(st)) * 1e3,
                         'reads': len(ard), 'reads_kept': len(res[0]), 'spans': int(n_spans),
                         'h2d_bytes_per_step': int(tg_tel.LAST_STATS.get('h2d_bytes', 0)), 'd2h_bytes_per_step': int(tg_tel.LAST_STATS.get('d2h_bytes', 0)),
                         'phases_ms': {k: float(v) * 1e3 for k, v in tg_tel.LAST_STATS.get('phases', {}).items()},
-                        'callback_ms': gtt_s[0] / len(st) * 1e3,
-                        'what': 'tg_tel.get_tel_repeat_comp_parallel: all_read_dat (Python strings) in -> kmer_hit_dat lists out; a fixed '
-                                'stand-in get_terminating_tl (the reference\'s needs pywt) on both arms'}
+                        'boundary': tg_tel.LAST_STATS.get('boundary'), 'hits_phases_ms': {k: float(v) * 1e3 for k, v in tg_tel.LAST_STATS.get('hits_phases', {}).items()},
+                        'what': 'tg_tel.get_tel_repeat_comp_parallel: all_read_dat (Python strings) in -> the 9-element result (kmer_hit_dat '
+                                'lists etc.) out; boundary calling (get_terminating_tl) on the device'}
         except Exception as exc:                      # an auxiliary line must not cost the headline metric
             scan_e2e = {'error': f'{type(exc).__name__}: {exc}'}
     # ---------------- e2e through the public API: host strings -> float32 matrix on the host --------
@@ -693,7 +685,7 @@ def main():
         emb, edt, eb, _k = cpu_scan_e2e_sample(scan_reads, tables, threads, int(args.cpu_scan_mbases * 1e6) // 2)
         if scan_e2e is not None and 'value' in scan_e2e:
             scan_e2e['cpu_port_mbases_per_s'] = emb
-            scan_e2e['cpu_port'] = f'oracle C scan per read, {threads} host threads, {eb} bases ({edt:.1f} s), same stand-in'
+            scan_e2e['cpu_port'] = f'oracle C scan per read, {threads} host threads, {eb} bases ({edt:.1f} s), numpy boundary calling'
         cpu = {'value': g, 'unit': 'GCUPS', 'cores': threads, 'kind': 'port',
                'sample': f'oracle C port (Biopython-style f64 NW + MT19937), OpenMP {threads} threads, first {args.cpu_pairs} pairs of the same '
                          f'matrix ({dt:.1f} s); scan: {smb:.2f} Mbases/s on {sb} bases ({sdt:.1f} s)',
@@ -709,7 +701,7 @@ def main():
                 'gpu_launches': int(launches_dp + 4),
                 'scan': {'value': scan_mbs, 'unit': 'Mbases/s', 'ms_per_step': scan_t * 1e3,
                          'what': 'basecount x2 + orient + density x2 + hits on the last 6000 bases of every read (device resident)',
-                         'parts_ms': {k: float(np.mean(v)) for k, v in scan_parts.items() if v}},
+                         'parts_ms': {k: float(np.mean(v)) for k, v in scan_parts.items() if v}, 'boundary': boundary},
                 'roofline': roof, 'roofline_scan': roof_scan, 'cpu_baseline': cpu, 'clocks': clocks,
                 'scan_e2e': scan_e2e, 'parity': PARITY_NOTE,
                 'prep': prep, 'prefilter': prefilter, 'd2': d2,

@@ -281,25 +281,38 @@ class PackedReads:
 
     def hits(self, slice_read, slice_lo, slice_hi, kmer_list, issub):
         """get_nonoverlapping_kmer_hits for a batch of slices; returns one out_dat (list[K] of [[s, e], ...]) per slice."""
+        import time
         K = len(kmer_list)
         ns = len(slice_read)
+        t = [time.perf_counter()]
         d_sp = self.hits_device(slice_read, slice_lo, slice_hi, kmer_list, issub)
+        t.append(time.perf_counter())
         # order by (slice, k, start) on the device, bring back (key, start, end) only
         torch = self.torch
         key = (d_sp[0].to(torch.int64) * K + d_sp[1].to(torch.int64)) * (1 << 32) + d_sp[2].to(torch.int64)
         key, order = torch.sort(key)
         pairs_d = torch.stack((d_sp[2][order], d_sp[3][order]), dim=1).contiguous()
-        group = (key >> 32).cpu().numpy()
-        pairs = pairs_d.cpu().numpy()
+        n_sp = int(key.numel())
+        h_group = pinned_bytes('hit_group', max(n_sp, 1) * 8).view(torch.int64)[:n_sp]
+        h_pairs = pinned_bytes('hit_pairs', max(n_sp, 1) * 8).view(torch.int32)[:2 * n_sp].view(n_sp, 2)
+        h_group.copy_(key >> 32)
+        h_pairs.copy_(pairs_d)
+        group, pairs = h_group.numpy(), h_pairs.numpy()
         self.last_hits_d2h = group.nbytes + pairs.nbytes
+        t.append(time.perf_counter())
         # one C-level conversion of all spans, then list slices per (slice, k); the cycle collector is paused while the
         # millions of small lists are made (it finds nothing and costs 4x)
         gc_was_on = gc.isenabled()
         gc.disable()
         try:
             pairs = pairs.tolist()
+            t.append(time.perf_counter())
             cuts = np.searchsorted(group, np.arange(ns * K + 1, dtype=np.int64)).tolist()
-            return [[pairs[cuts[q * K + k]:cuts[q * K + k + 1]] for k in range(K)] for q in range(ns)]
+            t.append(time.perf_counter())
+            out = [[pairs[cuts[q * K + k]:cuts[q * K + k + 1]] for k in range(K)] for q in range(ns)]
+            t.append(time.perf_counter())
+            self.last_hits_phases = dict(zip(('kernel', 'sort_d2h', 'tolist', 'cuts', 'slices'), np.diff(t).tolist()))
+            return out
         finally:
             if gc_was_on:
                 gc.enable()

@@ -107,12 +107,12 @@ def _tel_repeat_comp_phases(all_read_dat, gtrc_params, get_terminating_tl, index
         return oriented[i]
 
     # ---- phase 2: boundary calling per read (tg_tel.py:276-279) ----
+    t_ph.append(time.perf_counter())
     if get_terminating_tl is None:
         # on the device, from the window counts where they lie (tg_boundary.py)
         term = tg_boundary.terminating_tl_from_counts(d_p, d_q, pr.d_base_off, lens, TEL_WINDOW_SIZE, P_VS_Q_AMP_THRESH,
                                                       gtt_min_tel_score, 'q')
         d2h += term.nbytes
-        t_ph.append(time.perf_counter())
     else:
         # a caller-supplied get_terminating_tl (e.g. the reference's own, for the telomere-signal plots): per read on the
         # host; its get_telomere_kmer_density calls are served from the densities computed above
@@ -120,7 +120,6 @@ def _tel_repeat_comp_phases(all_read_dat, gtrc_params, get_terminating_tl, index
         cnt_p = pr.split_counts(h_p, TEL_WINDOW_SIZE)
         cnt_q = pr.split_counts(h_q, TEL_WINDOW_SIZE)
         d2h += 2 * int(getattr(pr, 'total', 0))
-        t_ph.append(time.perf_counter())
         term = np.full((n_reads, 4), -1, dtype=np.int64)
         for i in range(n_reads):
             my_rdat = rdat_of(i)
@@ -160,6 +159,7 @@ def _tel_repeat_comp_phases(all_read_dat, gtrc_params, get_terminating_tl, index
     t_ph.append(time.perf_counter())
     hits_tvr = pr.hits(tvr_idx, tvr_lo[tvr_idx], lens[tvr_idx], KMER_LIST_REV, KMER_ISSUBSTRING)
     d2h += getattr(pr, 'last_hits_d2h', 0)
+    hits_phases = dict(getattr(pr, 'last_hits_phases', {}))
     hits_ifwd = pr.hits(i_idx, np.zeros_like(i_idx), lens[i_idx], KMER_LIST, KMER_ISSUBSTRING)
     hits_irev = pr.hits(i_idx, np.zeros_like(i_idx), lens[i_idx], KMER_LIST_REV, KMER_ISSUBSTRING)
     t_ph.append(time.perf_counter())
@@ -184,8 +184,9 @@ def _tel_repeat_comp_phases(all_read_dat, gtrc_params, get_terminating_tl, index
     t_ph.append(time.perf_counter())
     LAST_STATS.clear()
     LAST_STATS.update(h2d_bytes=getattr(pr, 'h2d_bytes', 0), d2h_bytes=d2h,
-                      phases={'gpu_pack_count_orient_density': t_ph[1] - t_ph[0], 'boundary_calling': t_ph[2] - t_ph[1],
+                      phases={'gpu_pack_count_orient_density': t_ph[1] - t_ph[0], 'boundary_calling_and_filters': t_ph[2] - t_ph[1],
                               'gpu_hits_and_span_lists': t_ph[3] - t_ph[2], 'result_lists': t_ph[4] - t_ph[3]},
+                      hits_phases=hits_phases,
                       boundary='device' if get_terminating_tl is None else 'callback')
     res = [kmer_hit_dat,
            termtel[tvr_idx].tolist(),
