@@ -136,6 +136,10 @@ typedef struct tg_dist_batch_args {
                                      * (global indices); every matrix uses seeds seed0 + its own combinations index. */
     const int64_t *d_mat_pair_off;  /* [n_mat + 1] */
     const int32_t *d_mat_seq_off;   /* [n_mat + 1] */
+    const uint32_t *d_seq_mask;     /* [n_seq] bit c set = code c occurs in the sequence, or NULL.  With prof_rows > 0 the null-model
+                                     * alignments whose row sequences use fewer than prof_rows letters run with per-job query profiles of
+                                     * prof_rows rows (smaller shared-memory footprint, more resident warps); same results. */
+    int32_t prof_rows, pad_;
 } tg_dist_batch_args;
 
 size_t tg_dist_batch_mt_work_bytes(int64_t n_pairs, int R, int max_len);

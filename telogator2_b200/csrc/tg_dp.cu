@@ -49,12 +49,16 @@ struct WaveParams {
     const uint8_t *flags;       // [q1 - q0] 1 = early-out (phase B skips the pair)
     long long shuf_base, slot;  // shuffle area: pool offset and bytes per pair
     const long long *mat_pair_off; const int *mat_seq_off; int n_mat;   // several matrices in one pair space (0 = one matrix)
+    // phase B with per-job alphabets: seq_mask[s] = set of letters of sequence s; a job whose row sequences use fewer than
+    // prof_rows letters runs in the JOBS_PHASE_B_CPT launch (profiles of prof_rows rows: more resident warps), the others in
+    // the JOBS_PHASE_B launch.  prof_rows = 0: every job runs in JOBS_PHASE_B.
+    const uint32_t *seq_mask; int prof_rows;
 };
 
 // JOBS_PHASE_A_SHCOL: phase A with the two alignments of a job sharing their COLUMN sequence (pairs (a, b), (a, b+1) of the
 // sorted pair space share sequence a; NW is symmetric in its two sequences when the substitution matrix is): one query profile
 // per warp instead of two, so almost twice as many warps are resident.
-enum { JOBS_EXPLICIT = 0, JOBS_PHASE_A = 1, JOBS_PHASE_B = 2, JOBS_PHASE_A_SHCOL = 3 };
+enum { JOBS_EXPLICIT = 0, JOBS_PHASE_A = 1, JOBS_PHASE_B = 2, JOBS_PHASE_A_SHCOL = 3, JOBS_PHASE_B_CPT = 4 };
 
 // pair q of itertools.combinations(range(n), 2) -> (a, b), a < b
 __device__ __forceinline__ void unrank_pair(long long q, int n, int &a, int &b)
@@ -69,7 +73,7 @@ __device__ __forceinline__ void unrank_pair(long long q, int n, int &a, int &b)
     b = (int)(q - r * (2LL * n - r - 1) / 2 + r + 1);
 }
 
-struct PairDesc { long long off_i, off_j; int n, m; long long p; int i, j, mat, n_local, ra; bool a_is_i; };
+struct PairDesc { long long off_i, off_j; int n, m; long long p; int i, j, mat, n_local, ra, gi; bool a_is_i; };
 
 // sorted-space pair q -> original (i < j), length-adjusted shapes (tg_align.py:115-120) and combinations index p.
 // With n_mat > 0 the pair space is the concatenation of the pair spaces of several independent matrices (the per-cluster
@@ -105,7 +109,7 @@ __device__ __forceinline__ PairDesc describe_pair(const PT &P, long long q)
         li = min(li, ml);
         lj = min(lj, ml);
     }
-    d.n = li; d.m = lj; d.i = i - sbase; d.j = j - sbase; d.mat = mat; d.n_local = nloc;
+    d.n = li; d.m = lj; d.i = i - sbase; d.j = j - sbase; d.mat = mat; d.n_local = nloc; d.gi = i;
     d.ra = a; d.a_is_i = (oa == i);            // sorted rank of the longer sequence, and whether it is the pair's first sequence
     d.p = (long long)d.i * (2LL * nloc - d.i - 1) / 2 + (d.j - d.i - 1);
     return d;
@@ -246,13 +250,15 @@ template <int V, int MODE, bool WIDE, bool MM>
 __global__ void __launch_bounds__(WAVE_MAX_WARPS * 32, 1) nw_wave_kernel(const __grid_constant__ WaveParams P)
 {
     constexpr bool SHCOL = (MODE == JOBS_PHASE_A_SHCOL);
+    constexpr bool CPT = (MODE == JOBS_PHASE_B_CPT);                         // per-job alphabets: profile rows = letters that occur
+    static_assert(!(CPT && WIDE), "compact profiles are a 16-bit path");
     constexpr int NH = (WIDE || SHCOL) ? 1 : 2;                              // query profiles per job
     constexpr int C = (V == 0 || V == 3) ? 16 : 8;
     constexpr int RR = (V >= 2) ? 2 : 1;
     constexpr int W = 32 * C;
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int A = P.A, A1 = P.A + 1;
+    const int A = P.A, A1 = CPT ? P.prof_rows : P.A + 1;                     // A1 = rows of one profile in shared memory
     uint8_t *s_sp = smem;                                                    // MAXA*MAXA bytes
     constexpr int ROFF = (RR == 2) ? 64 : 0;                                 // rows[ROFF + r] = letters of row r
     const size_t per_warp = (size_t)NH * A1 * W + (size_t)P.row_cap * 2 + 512;
@@ -283,6 +289,7 @@ __global__ void __launch_bounds__(WAVE_MAX_WARPS * 32, 1) nw_wave_kernel(const _
         }
         long long row0, row1, col0, col1;
         int n0, n1, m0, m1, out0, out1;
+        uint32_t mk0 = 0u, mk1 = 0u;                                         // CPT: letters of the two row sequences
         if (SHCOL) {
             if (pend) {
                 row0 = row1 = pend_row; col0 = col1 = pend_col; n0 = n1 = pend_n; m0 = m1 = pend_m; out0 = pend_out; out1 = -1;
@@ -358,6 +365,11 @@ __global__ void __launch_bounds__(WAVE_MAX_WARPS * 32, 1) nw_wave_kernel(const _
             if (hb) db = (qb == qa) ? da : describe_pair<MM>(P, qb);
             if (!ha) { da = db; qa = qb; ta = tb; }
             if (!hb) { db = da; qb = qa; tb = ta; }
+            if (CPT || P.prof_rows > 0) {
+                mk0 = P.seq_mask[da.gi]; mk1 = P.seq_mask[db.gi];
+                const bool fits = __popc(mk0) < P.prof_rows && __popc(mk1) < P.prof_rows;
+                if (fits != CPT) continue;                                   // the other launch takes it
+            }
             row0 = P.shuf_base + (qa - P.q0) * P.slot + (long long)ta * (da.n + da.m); col0 = row0 + da.n;
             row1 = P.shuf_base + (qb - P.q0) * P.slot + (long long)tb * (db.n + db.m); col1 = row1 + db.n;
             n0 = da.n; m0 = da.m; n1 = db.n; m1 = db.m;
@@ -377,8 +389,12 @@ __global__ void __launch_bounds__(WAVE_MAX_WARPS * 32, 1) nw_wave_kernel(const _
         __syncwarp();
         for (int e = lane; e < N + 4 + 2 * ROFF + (ROFF ? 4 : 0); e += 32) {
             const int r = e - ROFF;
-            const uint32_t a0 = (r >= 0 && r < n0) ? (uint32_t)__ldg(P.pool + row0 + r) : (uint32_t)A;
-            const uint32_t a1 = (r >= 0 && r < n1) ? (uint32_t)__ldg(P.pool + row1 + r) : (uint32_t)A;
+            uint32_t a0 = (r >= 0 && r < n0) ? (uint32_t)__ldg(P.pool + row0 + r) : (uint32_t)A;
+            uint32_t a1 = (r >= 0 && r < n1) ? (uint32_t)__ldg(P.pool + row1 + r) : (uint32_t)A;
+            if (CPT) {                                                       // letter -> its rank among the sequence's letters; padding -> the row behind them
+                a0 = __popc(mk0 & ((a0 < (uint32_t)A) ? ((1u << a0) - 1u) : 0xffffffffu));
+                a1 = __popc(mk1 & ((a1 < (uint32_t)A) ? ((1u << a1) - 1u) : 0xffffffffu));
+            }
             rows[e] = (uint16_t)(a0 | (a1 << 8));
         }
 
@@ -390,12 +406,23 @@ __global__ void __launch_bounds__(WAVE_MAX_WARPS * 32, 1) nw_wave_kernel(const _
                 const int j0 = X - pad0, j1 = X - pad1;
                 const int b0 = (j0 >= 0) ? (int)__ldg(P.pool + col0 + j0) : -1;
                 const int b1 = (j1 >= 0) ? (int)__ldg(P.pool + col1 + j1) : -1;
+                if (CPT) {
+                    int ca = 0;
+                    for (uint32_t mm = mk0; mm; mm &= mm - 1, ca++)
+                        prof[(size_t)ca * W + x] = (b0 >= 0) ? s_sp[(__ffs(mm) - 1) * MAXA + b0] : (uint8_t)0;
+                    prof[(size_t)ca * W + x] = 0;
+                    ca = 0;
+                    for (uint32_t mm = mk1; mm; mm &= mm - 1, ca++)
+                        prof[(size_t)(A1 + ca) * W + x] = (b1 >= 0) ? s_sp[(__ffs(mm) - 1) * MAXA + b1] : (uint8_t)0;
+                    prof[(size_t)(A1 + ca) * W + x] = 0;
+                } else {
                 for (int a = 0; a < A; a++) {
                     prof[(size_t)a * W + x] = (b0 >= 0) ? s_sp[a * MAXA + b0] : (uint8_t)0;
                     if (!WIDE && !SHCOL) prof[(size_t)(A1 + a) * W + x] = (b1 >= 0) ? s_sp[a * MAXA + b1] : (uint8_t)0;
                 }
                 prof[(size_t)A * W + x] = 0;
                 if (!WIDE && !SHCOL) prof[(size_t)(A1 + A) * W + x] = 0;
+                }
             }
             __syncwarp();
 
@@ -1207,6 +1234,10 @@ static int wave_launch_v(const WaveParams &P, int mode, int grid, int warps, siz
 {
     if (mode == JOBS_EXPLICIT) return wave_launch_t<V, JOBS_EXPLICIT, WIDE>(P, grid, warps, smem, st);
     if (mode == JOBS_PHASE_A_SHCOL) return wave_launch_t<3, JOBS_PHASE_A_SHCOL, false, false>(P, grid, warps, smem, st);
+    if (mode == JOBS_PHASE_B_CPT) {          // compact profiles: default geometry, 16-bit cells
+        if (P.n_mat > 0) return wave_launch_t<3, JOBS_PHASE_B_CPT, false, true>(P, grid, warps, smem, st);
+        return wave_launch_t<3, JOBS_PHASE_B_CPT, false, false>(P, grid, warps, smem, st);
+    }
     if (V == 3 && P.n_mat > 0) {              // several matrices in one pair space: default geometry only
         if (mode == JOBS_PHASE_A) return wave_launch_t<3, JOBS_PHASE_A, WIDE, true>(P, grid, warps, smem, st);
         return wave_launch_t<3, JOBS_PHASE_B, WIDE, true>(P, grid, warps, smem, st);
@@ -1246,7 +1277,7 @@ static int wave_launch_inner(const WaveParams &P, int mode, int variant, int gri
 
 // shared set-up of the three job modes
 static int wave_setup(WaveParams &P, const tg_nw_scoring *sc, int max_n, int *C_out, int *warps_out, size_t *smem_out, bool wide = false,
-                      bool one_profile = false)
+                      bool one_profile = false, int prof_rows = 0)
 {
     wave_env();
     int max_sp = 0;
@@ -1260,7 +1291,7 @@ static int wave_setup(WaveParams &P, const tg_nw_scoring *sc, int max_n, int *C_
         for (int b = 0; b < MAXA; b++)
             P.sp[a * MAXA + b] = (a < sc->alphabet && b < sc->alphabet) ? (uint8_t)(sc->sub[a * MAXA + b] - 2 * sc->gap) : 0;
     const int C = (wide || g_wave_variant == 0 || g_wave_variant == 3) ? 16 : 8;
-    const size_t per_warp = (size_t)((wide || one_profile) ? 1 : 2) * (sc->alphabet + 1) * 32 * C + (size_t)P.row_cap * 2 + 512;
+    const size_t per_warp = (size_t)((wide || one_profile) ? 1 : 2) * (prof_rows > 0 ? prof_rows : sc->alphabet + 1) * 32 * C + (size_t)P.row_cap * 2 + 512;
     int warps = (int)((226 * 1024 - MAXA * MAXA) / per_warp);
     if (warps > WAVE_MAX_WARPS) warps = WAVE_MAX_WARPS;
     if (g_wave_warps && warps > g_wave_warps) warps = g_wave_warps;
@@ -1268,6 +1299,17 @@ static int wave_setup(WaveParams &P, const tg_nw_scoring *sc, int max_n, int *C_
     *C_out = wide ? 3 : g_wave_variant; *warps_out = warps;
     *smem_out = MAXA * MAXA + (size_t)warps * per_warp;
     return TG_OK;
+}
+
+// A launch with fewer jobs than warp slots spreads them over all SMs (fewer warps per CTA) instead of filling a few CTAs:
+// a small matrix (per-cluster calls) otherwise runs on a third of the GPU.
+static void wave_spread(long long n_jobs, int warps, int sms, int *grid, int *w)
+{
+    if (n_jobs >= (long long)sms * warps) { *grid = sms; *w = warps; return; }
+    int ww = (int)((n_jobs + sms - 1) / sms);
+    if (ww < 1) ww = 1;
+    *w = ww;
+    *grid = (int)((n_jobs + ww - 1) / ww);
 }
 
 static int nw_scores_wave(const uint8_t *d_pool, const tg_nw_job *d_jobs, int64_t n_jobs, int max_n,
@@ -1289,10 +1331,9 @@ static int nw_scores_wave(const uint8_t *d_pool, const tg_nw_job *d_jobs, int64_
     P.counter = reinterpret_cast<unsigned long long *>(d_counter);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     TG_CUDA_CHECK(cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), st));
-    long long grid = sms;
-    const long long ctas_needed = (P.n_jobs + warps - 1) / warps;
-    if (ctas_needed < grid) grid = ctas_needed;
-    return wave_launch(P, JOBS_EXPLICIT, C, (int)grid, warps, smem, st, wide);
+    int grid, w;
+    wave_spread(P.n_jobs, warps, sms, &grid, &w);
+    return wave_launch(P, JOBS_EXPLICIT, C, grid, w, smem, st, wide);
 }
 
 TG_EXPORT int tg_nw_scores_wave(const uint8_t *d_pool, const tg_nw_job *d_jobs, int64_t n_jobs, int max_n,
@@ -1352,7 +1393,6 @@ TG_EXPORT int tg_dist_batch(const tg_dist_batch_args *a, const tg_nw_scoring *sc
     P.q0 = a->q0; P.q1 = a->q1; P.flags = a->d_flags; P.shuf_base = a->shuf_base; P.slot = a->slot;
     if (a->n_mat < 0 || (a->n_mat > 0 && (!a->d_mat_pair_off || !a->d_mat_seq_off))) return tg_set_err(TG_EINVAL, "bad matrix table");
     P.mat_pair_off = reinterpret_cast<const long long *>(a->d_mat_pair_off); P.mat_seq_off = a->d_mat_seq_off; P.n_mat = a->n_mat;
-    auto grid_for_jobs = [&](long long jobs) { long long g = (jobs + warps - 1) / warps; return (int)(g < sms ? g : sms); };
     // ---- phase A: the real alignment of every pair ----
     P.n_jobs = wide ? npairs : (npairs + 1) / 2;
     TG_CUDA_CHECK(cudaMemsetAsync(a->d_counter, 0, sizeof(unsigned long long), st));
@@ -1364,10 +1404,13 @@ TG_EXPORT int tg_dist_batch(const tg_dist_batch_args *a, const tg_nw_scoring *sc
         size_t smem2;
         rc = wave_setup(P, sc, a->max_len, &C2, &warps2, &smem2, false, true);
         if (rc != TG_OK) return rc;
-        long long g2 = (P.n_jobs + warps2 - 1) / warps2;
-        rc = wave_launch(P, JOBS_PHASE_A_SHCOL, 3, (int)(g2 < sms ? g2 : sms), warps2, smem2, st, false);
+        int g2, w2;
+        wave_spread(P.n_jobs, warps2, sms, &g2, &w2);
+        rc = wave_launch(P, JOBS_PHASE_A_SHCOL, 3, g2, w2, smem2, st, false);
     } else {
-        rc = wave_launch(P, JOBS_PHASE_A, C, grid_for_jobs(P.n_jobs), warps, smem, st, wide);
+        int g1, w1;
+        wave_spread(P.n_jobs, warps, sms, &g1, &w1);
+        rc = wave_launch(P, JOBS_PHASE_A, C, g1, w1, smem, st, wide);
     }
     if (rc != TG_OK) return rc;
     // ---- identity score + early-out flags ----
@@ -1468,7 +1511,22 @@ TG_EXPORT int tg_dist_batch(const tg_dist_batch_args *a, const tg_nw_scoring *sc
     P.scores = a->d_rnd;
     P.n_jobs = wide ? npairs * a->R : (a->R % 2 == 0) ? npairs * (a->R / 2) : ((npairs + 1) / 2) * a->R;
     TG_CUDA_CHECK(cudaMemsetAsync(a->d_counter, 0, sizeof(unsigned long long), st));
-    return wave_launch(P, JOBS_PHASE_B, C, grid_for_jobs(P.n_jobs), warps, smem, st, wide);
+    int gb, wb;
+    P.seq_mask = nullptr; P.prof_rows = 0;
+    if (!wide && C == 3 && a->d_seq_mask && a->prof_rows >= 2 && a->prof_rows < sc->alphabet + 1) {
+        // jobs whose row sequences use fewer than prof_rows letters: compact profiles, more resident warps
+        int Cc, warps_c;
+        size_t smem_c;
+        rc = wave_setup(P, sc, a->max_len, &Cc, &warps_c, &smem_c, false, false, a->prof_rows);
+        if (rc != TG_OK) return rc;
+        P.seq_mask = a->d_seq_mask; P.prof_rows = a->prof_rows;
+        wave_spread(P.n_jobs, warps_c, sms, &gb, &wb);
+        rc = wave_launch(P, JOBS_PHASE_B_CPT, 3, gb, wb, smem_c, st, false);
+        if (rc != TG_OK) return rc;
+        TG_CUDA_CHECK(cudaMemsetAsync(a->d_counter, 0, sizeof(unsigned long long), st));
+    }
+    wave_spread(P.n_jobs, warps, sms, &gb, &wb);
+    return wave_launch(P, JOBS_PHASE_B, C, gb, wb, smem, st, wide);
 }
 
 TG_EXPORT int tg_wave_timing(int enable)

@@ -34,6 +34,11 @@ for _ in range(2):
     sp = pr.hits_device(np.arange(pr.n), np.maximum(pr.lens - 6000, 0), pr.lens, KLR, ISSUB)
 torch.cuda.synchronize()
 print('scan bases', int(pr.lens.sum()), 'reads', pr.n, 'spans', sp.shape[1])
+from telogator2_b200 import tg_boundary  # noqa: E402
+for _ in range(2):
+    term = tg_boundary.terminating_tl_from_counts(ca, cb, pr.d_base_off, pr.lens, 100, 0.5, 100, 'q')
+torch.cuda.synchronize()
+print('boundary reads', len(term), 'with telomere', int((term[:, 0] > 0).sum()))
 from telogator2_b200 import tg_tvr  # noqa: E402
 kd, meta, _flat = bench.make_prep_workload(512)
 for _ in range(2):
