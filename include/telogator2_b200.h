@@ -139,7 +139,12 @@ typedef struct tg_dist_batch_args {
     const uint32_t *d_seq_mask;     /* [n_seq] bit c set = code c occurs in the sequence, or NULL.  With prof_rows > 0 the null-model
                                      * alignments whose row sequences use fewer than prof_rows letters run with per-job query profiles of
                                      * prof_rows rows (smaller shared-memory footprint, more resident warps); same results. */
-    int32_t prof_rows, pad_;
+    int32_t prof_rows;
+    int32_t phases;                 /* bit mask, 0 = everything: 1 = real alignments + early-out flags + MT19937 seeding, 2 = random streams +
+                                     * sampling (the shuffled sequences), 4 = null-model alignments.  Lets the caller run phase 2 of one batch
+                                     * on a second stream under phase 1 of the next batch (separate d_counter / d_mt_work / shuffle areas). */
+    int32_t smem_reserve;           /* shared memory per SM the alignment kernels of this call leave free (for a co-running phase 2) */
+    int32_t pad_;
 } tg_dist_batch_args;
 
 size_t tg_dist_batch_mt_work_bytes(int64_t n_pairs, int R, int max_len);

@@ -32,7 +32,8 @@ class DistBatchArgs(C.Structure):
                 ('match', C.c_double),
                 ('n_seq', C.c_int32), ('adjust_lens', C.c_int32), ('min_viable', C.c_int32), ('R', C.c_int32),
                 ('max_len', C.c_int32), ('n_mat', C.c_int32), ('d_mat_pair_off', C.c_void_p), ('d_mat_seq_off', C.c_void_p),
-                ('d_seq_mask', C.c_void_p), ('prof_rows', C.c_int32), ('pad_', C.c_int32)]
+                ('d_seq_mask', C.c_void_p), ('prof_rows', C.c_int32), ('phases', C.c_int32), ('smem_reserve', C.c_int32),
+                ('pad_', C.c_int32)]
 
 
 class DistEpilogueArgs(C.Structure):

@@ -1277,7 +1277,7 @@ static int wave_launch_inner(const WaveParams &P, int mode, int variant, int gri
 
 // shared set-up of the three job modes
 static int wave_setup(WaveParams &P, const tg_nw_scoring *sc, int max_n, int *C_out, int *warps_out, size_t *smem_out, bool wide = false,
-                      bool one_profile = false, int prof_rows = 0)
+                      bool one_profile = false, int prof_rows = 0, int smem_reserve = 0)
 {
     wave_env();
     int max_sp = 0;
@@ -1292,7 +1292,7 @@ static int wave_setup(WaveParams &P, const tg_nw_scoring *sc, int max_n, int *C_
             P.sp[a * MAXA + b] = (a < sc->alphabet && b < sc->alphabet) ? (uint8_t)(sc->sub[a * MAXA + b] - 2 * sc->gap) : 0;
     const int C = (wide || g_wave_variant == 0 || g_wave_variant == 3) ? 16 : 8;
     const size_t per_warp = (size_t)((wide || one_profile) ? 1 : 2) * (prof_rows > 0 ? prof_rows : sc->alphabet + 1) * 32 * C + (size_t)P.row_cap * 2 + 512;
-    int warps = (int)((226 * 1024 - MAXA * MAXA) / per_warp);
+    int warps = (int)((226 * 1024 - smem_reserve - MAXA * MAXA) / per_warp);
     if (warps > WAVE_MAX_WARPS) warps = WAVE_MAX_WARPS;
     if (g_wave_warps && warps > g_wave_warps) warps = g_wave_warps;
     if (warps < 1) return tg_set_err(TG_ERANGE, "sequences of %d rows do not fit the wave kernel's shared memory", max_n);
@@ -1370,6 +1370,15 @@ TG_EXPORT int tg_dist_batch(const tg_dist_batch_args *a, const tg_nw_scoring *sc
     if (npairs > 0x3fffffff / (a->R > 0 ? a->R : 1)) return tg_set_err(TG_ERANGE, "batch of %lld pairs is too large", npairs);
     const int sms = tg_sm_count();
     if (sms <= 0) return tg_set_err(TG_ECUDA, "no CUDA device");
+    // phases (bit mask, 0 = all): 1 = real alignments + flags + seeding, 2 = random streams + sampling, 4 = null-model alignments.
+    // A caller that pipelines batches runs phase 2 of one batch on a second stream under phase 1 of the next one.
+    const int ph = a->phases ? a->phases : 7;
+    int reserve = a->smem_reserve > 0 ? a->smem_reserve : 0;
+    if (a->smem_reserve < 0) {               // room for one CTA of the stream kernel (static) or of the sampling kernel, whichever is larger
+        const int wstride0 = (a->max_len + 15) / 16 * 16 + MTW_EXTRA;
+        const int need = MTW_WARPS * wstride0 > MTG_WARPS * 624 * 4 ? MTW_WARPS * wstride0 : MTG_WARPS * 624 * 4;
+        reserve = need + 2048;
+    }
     WaveParams P;
     memset(&P, 0, sizeof(P));
     int C, warps;
@@ -1381,7 +1390,7 @@ TG_EXPORT int tg_dist_batch(const tg_dist_batch_args *a, const tg_nw_scoring *sc
         if (rc0 != TG_OK) return rc0;
         wide = (long long)max_sp * a->max_len > 65535;          // 16-bit cells would overflow: one alignment per job, 32-bit cells
     }
-    int rc = wave_setup(P, sc, a->max_len, &C, &warps, &smem, wide);
+    int rc = wave_setup(P, sc, a->max_len, &C, &warps, &smem, wide, false, 0, reserve);
     if (rc != TG_OK) return rc;
     if (a->n_mat > 0 && C != 3) return tg_set_err(TG_EINVAL, "several matrices per call need the default wave variant (TG_WAVE_VARIANT=3)");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -1393,6 +1402,8 @@ TG_EXPORT int tg_dist_batch(const tg_dist_batch_args *a, const tg_nw_scoring *sc
     P.q0 = a->q0; P.q1 = a->q1; P.flags = a->d_flags; P.shuf_base = a->shuf_base; P.slot = a->slot;
     if (a->n_mat < 0 || (a->n_mat > 0 && (!a->d_mat_pair_off || !a->d_mat_seq_off))) return tg_set_err(TG_EINVAL, "bad matrix table");
     P.mat_pair_off = reinterpret_cast<const long long *>(a->d_mat_pair_off); P.mat_seq_off = a->d_mat_seq_off; P.n_mat = a->n_mat;
+    const bool streamed = a->R > 0 && a->d_mt_work && a->max_len < 65536;
+    if (ph & 1) {
     // ---- phase A: the real alignment of every pair ----
     P.n_jobs = wide ? npairs : (npairs + 1) / 2;
     TG_CUDA_CHECK(cudaMemsetAsync(a->d_counter, 0, sizeof(unsigned long long), st));
@@ -1402,7 +1413,7 @@ TG_EXPORT int tg_dist_batch(const tg_dist_batch_args *a, const tg_nw_scoring *sc
     if (shcol) {
         int C2, warps2;
         size_t smem2;
-        rc = wave_setup(P, sc, a->max_len, &C2, &warps2, &smem2, false, true);
+        rc = wave_setup(P, sc, a->max_len, &C2, &warps2, &smem2, false, true, 0, reserve);
         if (rc != TG_OK) return rc;
         int g2, w2;
         wave_spread(P.n_jobs, warps2, sms, &g2, &w2);
@@ -1419,7 +1430,6 @@ TG_EXPORT int tg_dist_batch(const tg_dist_batch_args *a, const tg_nw_scoring *sc
     F.R = a->R; F.q0 = a->q0; F.q1 = a->q1; F.aln = a->d_aln; F.diag_cs = a->d_diag_cs; F.match = a->match;
     F.flags = a->d_flags; F.iden = a->d_iden; F.shape = a->d_shape;
     F.mat_pair_off = P.mat_pair_off; F.mat_seq_off = P.mat_seq_off; F.n_mat = P.n_mat;
-    const bool streamed = a->R > 0 && a->d_mt_work && a->max_len < 65536;
     F.live = streamed ? reinterpret_cast<int *>(a->d_mt_work) : nullptr;
     F.n_live = reinterpret_cast<int *>(a->d_counter) + 6;
     if (streamed) TG_CUDA_CHECK(cudaMemsetAsync(F.n_live, 0, sizeof(int), st));
@@ -1429,6 +1439,7 @@ TG_EXPORT int tg_dist_batch(const tg_dist_batch_args *a, const tg_nw_scoring *sc
         dist_flags_kernel<<<(int)g, 256, 0, st>>>(F);
         TG_CUDA_CHECK(cudaGetLastError());
     }
+    }
     if (a->R <= 0) return TG_OK;
     // ---- null model: MT19937 shuffles of every non-early pair ----
     int stride = (a->max_len + 3) / 4;
@@ -1436,7 +1447,8 @@ TG_EXPORT int tg_dist_batch(const tg_dist_batch_args *a, const tg_nw_scoring *sc
     stride *= 4;
     rc = mt_upload_base();
     if (rc != TG_OK) return rc;
-    if (streamed) {
+    int *const n_live = reinterpret_cast<int *>(a->d_counter) + 6;
+    if (streamed && (ph & 3)) {
         StreamParams S;
         S.pool = a->d_pool; S.seq_off = P.seq_off; S.order = P.order; S.n_seq = P.n_seq; S.adjust_lens = P.adjust_lens;
         S.min_viable = P.min_viable; S.R = a->R; S.q0 = a->q0; S.q1 = a->q1; S.flags = a->d_flags;
@@ -1444,7 +1456,7 @@ TG_EXPORT int tg_dist_batch(const tg_dist_batch_args *a, const tg_nw_scoring *sc
         S.mat_pair_off = P.mat_pair_off; S.mat_seq_off = P.mat_seq_off; S.n_mat = P.n_mat;
         S.cap = mt_blocks_needed(2 * a->R * a->max_len) * 624;
         const size_t live_bytes = ((size_t)npairs * sizeof(int) + 255) / 256 * 256;
-        S.live = F.live; S.n_live = F.n_live;
+        S.live = reinterpret_cast<int *>(a->d_mt_work); S.n_live = n_live;
         S.state = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(a->d_mt_work) + live_bytes);
         S.stream = reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(a->d_mt_work) + live_bytes + (size_t)npairs * 624 * sizeof(uint32_t));
         S.overflow = reinterpret_cast<int *>(a->d_counter) + 4;      // sticky; the caller zeroes and checks it
@@ -1453,6 +1465,7 @@ TG_EXPORT int tg_dist_batch(const tg_dist_batch_args *a, const tg_nw_scoring *sc
         if (psmem > 200 * 1024) return tg_set_err(TG_ERANGE, "max_len %d: the sampling pool does not fit shared memory", a->max_len);
         S.pool_stride = wstride;
         const long long need32 = (npairs + MT_THREADS - 1) / MT_THREADS;
+        if (ph & 1) {
         // seeding
         const size_t ssmem = (size_t)624 * MTS_PAD * sizeof(uint32_t);
         TG_CUDA_CHECK(cudaFuncSetAttribute(mt_seed_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
@@ -1463,6 +1476,8 @@ TG_EXPORT int tg_dist_batch(const tg_dist_batch_args *a, const tg_nw_scoring *sc
             mt_seed_batch_kernel<<<(int)g, MT_THREADS, ssmem, st>>>(S);
             TG_CUDA_CHECK(cudaGetLastError());
         }
+        }
+        if (ph & 2) {
         // stream generation
         TG_CUDA_CHECK(cudaMemsetAsync(a->d_counter, 0, sizeof(unsigned long long), st));
         {
@@ -1485,7 +1500,8 @@ TG_EXPORT int tg_dist_batch(const tg_dist_batch_args *a, const tg_nw_scoring *sc
             mt_sample_warp_kernel<<<(int)g, MTW_WARPS * 32, psmem, st>>>(S);
             TG_CUDA_CHECK(cudaGetLastError());
         }
-    } else {
+        }
+    } else if (!streamed && (ph & 2)) {
     BatchShuffleParams S;
     S.pool = a->d_pool; S.seq_off = P.seq_off; S.order = P.order; S.n_seq = P.n_seq; S.adjust_lens = P.adjust_lens;
     S.min_viable = P.min_viable; S.R = a->R; S.q0 = a->q0; S.q1 = a->q1; S.flags = a->d_flags;
@@ -1507,6 +1523,7 @@ TG_EXPORT int tg_dist_batch(const tg_dist_batch_args *a, const tg_nw_scoring *sc
         TG_CUDA_CHECK(cudaGetLastError());
     }
     }
+    if (!(ph & 4)) return TG_OK;
     // ---- phase B: alignments of the shuffled pairs ----
     P.scores = a->d_rnd;
     P.n_jobs = wide ? npairs * a->R : (a->R % 2 == 0) ? npairs * (a->R / 2) : ((npairs + 1) / 2) * a->R;
@@ -1517,7 +1534,7 @@ TG_EXPORT int tg_dist_batch(const tg_dist_batch_args *a, const tg_nw_scoring *sc
         // jobs whose row sequences use fewer than prof_rows letters: compact profiles, more resident warps
         int Cc, warps_c;
         size_t smem_c;
-        rc = wave_setup(P, sc, a->max_len, &Cc, &warps_c, &smem_c, false, false, a->prof_rows);
+        rc = wave_setup(P, sc, a->max_len, &Cc, &warps_c, &smem_c, false, false, a->prof_rows, reserve);
         if (rc != TG_OK) return rc;
         P.seq_mask = a->d_seq_mask; P.prof_rows = a->prof_rows;
         wave_spread(P.n_jobs, warps_c, sms, &gb, &wb);

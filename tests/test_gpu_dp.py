@@ -326,6 +326,30 @@ def test_full_iter0_matrices_of_the_bundled_sets(tga, colorvecs, key, n):
     assert np.array_equal(a1, a2)
 
 
+@pytest.mark.parametrize('R', [2, 3])
+def test_pipelined_batches_and_per_job_profiles_change_nothing(tga, colorvecs, R, monkeypatch):
+    """Many small batches: the stream + sampling kernels of batch k run on a second stream under the alignments of batch k + 1
+    (two buffer sets); null-model alignments run with per-job query profiles where the row sequences use few letters.  Both
+    are scheduling / layout choices: the matrix must equal the single-stream, full-profile one and the oracle's."""
+    import torch
+    from telogator2_b200.dist_engine import DistEngine, Scoring
+    seqs = [c[:1000] for c in colorvecs['colorvecs']['human_hifi']][:60]
+    aligner = tga.get_aligner_object(tga.get_scoring_matrix('C', 'tvr'), (True, True), 'tvr')
+    Do = oracle.dist_matrix_c(seqs, _P(oracle.scoring_matrix('C', 'tvr'), (True, True)), True, True, R, 777)
+    got = {}
+    for pipe, rows in (('1', None), ('0', None), ('1', '0'), ('1', '9'), ('0', '15')):
+        monkeypatch.setenv('TG_DIST_PIPELINE', pipe)
+        if rows is None:
+            monkeypatch.delenv('TG_WAVE_PROF_ROWS', raising=False)
+        else:
+            monkeypatch.setenv('TG_WAVE_PROF_ROWS', rows)
+        eng = DistEngine(Scoring.from_aligner(aligner), pairs_per_batch=128)
+        D = eng.matrix_device(eng.prepare(seqs), True, True, R, 777)
+        torch.cuda.synchronize()
+        got[(pipe, rows)] = D.cpu().numpy()
+        assert np.array_equal(got[(pipe, rows)], Do), (pipe, rows)
+
+
 def test_against_real_biopython_when_importable(tga, colorvecs):
     """The one unpinned piece: Bio.Align.PairwiseAligner.score.  Skipped where Biopython is absent (the build image and the GPU
     boxes: profiles/r02_pin_biopython_*.log); wherever it is importable this compares the CUDA matrices with the reference's
