@@ -634,8 +634,12 @@ def main():
                 res = tg_tel.get_tel_repeat_comp_parallel(ard, gp)
                 st.append(time.perf_counter() - t0)
             n_spans = sum(len(sp) for khd in res[0] for sp in khd[0])
+            n_kept = len(res[0])
+            del res, ard               # (millions of small lists: leaving them alive makes every later cycle collection slow)
+            import gc
+            gc.collect()
             scan_e2e = {'value': scan_bases / float(np.mean(st)) / 1e6, 'unit': 'Mbases/s', 'ms_per_step': float(np.mean(st)) * 1e3,
-                        'reads': len(ard), 'reads_kept': len(res[0]), 'spans': int(n_spans),
+                        'reads': len(scan_reads), 'reads_kept': n_kept, 'spans': int(n_spans),
                         'h2d_bytes_per_step': int(tg_tel.LAST_STATS.get('h2d_bytes', 0)), 'd2h_bytes_per_step': int(tg_tel.LAST_STATS.get('d2h_bytes', 0)),
                         'phases_ms': {k: float(v) * 1e3 for k, v in tg_tel.LAST_STATS.get('phases', {}).items()},
                         'boundary': tg_tel.LAST_STATS.get('boundary'), 'hits_phases_ms': {k: float(v) * 1e3 for k, v in tg_tel.LAST_STATS.get('hits_phases', {}).items()},

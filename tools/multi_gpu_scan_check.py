@@ -29,11 +29,11 @@ def main():
     reads += [(n, s, None) for n, s in R['synthetic'] if len(s) > 0 and set(s) <= set('ACGTN')]
     reads = [(f'{n}#{k}', s, q) for k in range(3) for (n, s, q) in reads]
     params = [T['read_type'], 60, KL, KLR, ISSUB, CANON, CANON_REV, 100, 0.5, 100, 400, 100, 1000, False, '', 100, 1000]
-    gtt = make_gtt(tg_kmer.get_telomere_kmer_density)
-    got = tg_tel.get_tel_repeat_comp_parallel(reads, params, get_terminating_tl=gtt)
-    want = tg_tel._tel_repeat_comp_local(reads, params, gtt, 0)
-    assert got == want, 'sharded scan result differs from the single-GPU result'
-    assert len(got[0]) > 0
+    for gtt in (None, make_gtt(tg_kmer.get_telomere_kmer_density)):       # boundary calling on the device / through a callback
+        got = tg_tel.get_tel_repeat_comp_parallel(reads, params, get_terminating_tl=gtt)
+        want = tg_tel._tel_repeat_comp_local(reads, params, gtt, 0)
+        assert got == want, 'sharded scan result differs from the single-GPU result'
+        assert len(got[0]) > 0
     dist.barrier()
     print(f'rank {rank}: sharded scan == local scan ({len(reads)} reads, {len(got[0])} tvr entries, {len(got[6])} interstitial)')
     dist.destroy_process_group()

@@ -44,3 +44,11 @@ t0 = time.perf_counter()
 for it in range(n_rep):
     tg_align.get_dist_matrix_parallel(groups[it % len(groups)], aligner, True, True, 3, rng_seed=12345)
 print('public call: %.2f ms each' % ((time.perf_counter() - t0) / n_rep * 1e3))
+# batched: all groups in one pass
+groups64 = (groups * 8)[:64]
+tg_align.get_dist_matrices_parallel(groups64[:2], aligner, True, True, 3, rng_seed=12345)
+for it in range(3):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    tg_align.get_dist_matrices_parallel(groups64, aligner, True, True, 3, rng_seed=12345)
+    print('batched 64 matrices: %.1f ms' % ((time.perf_counter() - t0) * 1e3))
