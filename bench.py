@@ -471,7 +471,10 @@ def main():
     roof, roof_scan = None, None
     if rank == 0:
         dpx, mixed = C.c_double(0), C.c_double(0)
-        _lib.check(L.tg_int_alu_peak(2000, C.byref(dpx), C.byref(mixed)))
+        _lib.check(L.tg_int_alu_peak(1000, C.byref(dpx), C.byref(mixed)))
+        n_sm = C.c_int(0)
+        _lib.check(L.tg_device_sm_count(C.byref(n_sm)))
+        nominal = n_sm.value * 64 * float(clocks.get('sm_max_mhz') or 1965.0) * 1e6     # ALU pipe: 64 lanes per SM per clock
         # dominant kernel: nw_wave_kernel, timed inside the timed steps (CUDA events on the launching stream around every
         # launch: phase A + phase B of every batch).  Algorithmic work = the cells of the steps.
         k_cells = float(cells_step) * args.steps
@@ -480,7 +483,8 @@ def main():
         peak_gcups = dpx.value / instr_per_cell / 1e9
         roof = {'bound': 'int_alu', 'kernel': 'nw_wave_kernel', 'achieved': k_gcups, 'peak': peak_gcups, 'unit': 'GCUPS',
                 'frac': k_gcups / peak_gcups, 'traffic': ncu_traffic('nw_wave_kernel'),
-                'peak_source': f'measured in this run: {dpx.value / 1e12:.2f} T VIMNMX3.U16x2 lane-ops/s (tg_int_alu_peak) / 1.5 instr per cell '
+                'peak_source': f'measured in this run: {dpx.value / 1e12:.2f} T VIMNMX3.U16x2 lane-ops/s (tg_int_alu_peak: '
+                               f'{100 * dpx.value / nominal:.1f} % of SMs x 64 lanes x max clock) / 1.5 instr per cell '
                                f'(SURVEY 8d); add+max3 pair rate {mixed.value / 1e12:.2f} T pairs/s',
                 'launch_ms': wave_ms.value / max(wave_n.value, 1), 'launches': wave_n.value,
                 'cells_per_launch': k_cells / max(wave_n.value, 1),

@@ -1139,20 +1139,21 @@ __global__ void __launch_bounds__(256) dist_epilogue_kernel(const EpiParams P)
 template <int MODE>
 __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t *out, int iters, uint32_t seed)
 {
+    // eight independent chains per thread, nothing but the measured instruction inside the loop (the loop counter's add and
+    // branch are 2 of 66 issue slots; the operands alternate between two register pairs so that no iteration is a no-op the
+    // compiler could drop)
     uint32_t a[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) a[k] = seed * (threadIdx.x + 1) + k;
-    uint32_t b = seed ^ 0x00030005u, c = seed | 0x00010001u;
+    const uint32_t b0 = seed ^ 0x00030005u, c0 = seed | 0x00010001u, b1 = seed + 0x00070009u, c1 = seed ^ 0x01010101u;
     for (int it = 0; it < iters; it++) {
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < 8; u++) {
 #pragma unroll
             for (int k = 0; k < 8; k++) {
-                if (MODE == 0) a[k] = __vimax3_u16x2(a[k], b, c);           // DPX only
-                else a[k] = __vimax3_u16x2(a[k] + b, a[(k + 1) & 7], c);    // add + DPX (cell shape)
+                if (MODE == 0) a[k] = __vimax3_u16x2(a[k], (u & 1) ? b1 : b0, (u & 1) ? c1 : c0);       // DPX only
+                else a[k] = __vimax3_u16x2(a[k] + ((u & 1) ? b1 : b0), a[(k + 1) & 7], c0);              // add + DPX (cell shape)
             }
-            b += 0x00010001u;
-            c ^= b;
         }
     }
     uint32_t r = 0;
@@ -1702,8 +1703,8 @@ TG_EXPORT int tg_int_alu_peak(int iters, double *dpx_lane_ops_per_s, double *iad
             TG_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
             if (rep > 0 && ms < best) best = ms;
         }
-        // per thread per iteration: 4 * 8 DPX ops (mode 0) or 4 * 8 (add + DPX) pairs (mode 1)
-        const double ops = (double)grid * block * (double)iters * 32.0;
+        // per thread per iteration: 8 * 8 DPX ops (mode 0) or 8 * 8 (add + DPX) pairs (mode 1)
+        const double ops = (double)grid * block * (double)iters * 64.0;
         res[mode] = ops / (best * 1e-3);
     }
     cudaEventDestroy(e0);
