@@ -160,6 +160,12 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ uint32_t lds_u16(uint32_t addr)
 {
     uint32_t v;
@@ -479,7 +485,10 @@ __global__ void __launch_bounds__(WAVE_MAX_WARPS * 32, 1) nw_wave_kernel(const _
             uint2 *bw = bord2 + k;
             // border column of the previous block: 32 row pairs per refill, parked in a 64-entry shared-memory ring
             uint2 bnext = (blk > 0 && lane < NP) ? __ldcg(bord2 + lane) : make_uint2(0u, 0u);
-            uint32_t ap2 = lds_u32(rows_s + 2 * ROFF + 4 * k);     // letters of rows 2k (low half) and 2k + 1
+            // letters of rows 2k and 2k + 1 of both alignments: four byte loads (LSU) instead of one word and six mask/shift
+            // instructions -- the loop is bound by the half-rate ALU pipe, the load/store pipe has room
+            const uint32_t rk0 = rows_s + 2 * ROFF;
+            uint32_t a00 = lds_u8(rk0 + 4 * k), a01 = lds_u8(rk0 + 4 * k + 1), a10 = lds_u8(rk0 + 4 * k + 2), a11 = lds_u8(rk0 + 4 * k + 3);
             for (int s = 0; s < steps; s++, k++, bw++) {
                 if ((s & 31) == 0) {
                     sts64(ring_s + 8 * ((s + lane) & 63), bnext);
@@ -487,17 +496,17 @@ __global__ void __launch_bounds__(WAVE_MAX_WARPS * 32, 1) nw_wave_kernel(const _
                     bnext = (blk > 0 && idx < NP) ? __ldcg(bord2 + idx) : make_uint2(0u, 0u);
                     __syncwarp();
                 }
+                // left neighbours: the previous lane's last column of the same row pair (one step ago).  A lane that has not
+                // reached its first row pair (k < 0) receives zeros by itself: its neighbour was on padding rows too.
                 uint32_t L0 = __shfl_up_sync(TG_FULL_MASK, A7, 1);
                 uint32_t L1 = __shfl_up_sync(TG_FULL_MASK, H[C - 1], 1);
                 const uint2 rb = lds64(ring_s + 8 * (k & 63));
-                if (lane == 0) { L0 = rb.x; L1 = rb.y; }
-                if (k < 0) { L0 = 0u; L1 = 0u; }
+                if (lane == 0) { L0 = rb.x; L1 = rb.y; }             // (lane 0 has k = s >= 0)
                 using S2 = typename std::conditional<C == 16, Strip2x16<WIDE>, Strip2x8<WIDE>>::type;
-                A7 = S2::run(H, prevL1, L0, L1,
-                             pb0 + (ap2 & 0xffu) * W, pb1 + ((ap2 >> 8) & 0xffu) * W,
-                             pb0 + ((ap2 >> 16) & 0xffu) * W, pb1 + (ap2 >> 24) * W);
+                A7 = S2::run(H, prevL1, L0, L1, pb0 + a00 * W, pb1 + a01 * W, pb0 + a10 * W, pb1 + a11 * W);
                 if (lane == 31) *bw = make_uint2(A7, H[C - 1]);
-                ap2 = lds_u32(rows_s + 2 * ROFF + 4 * (k + 1));
+                a00 = lds_u8(rk0 + 4 * (k + 1)); a01 = lds_u8(rk0 + 4 * (k + 1) + 1);
+                a10 = lds_u8(rk0 + 4 * (k + 1) + 2); a11 = lds_u8(rk0 + 4 * (k + 1) + 3);
                 prevL1 = L1;
             }
             }
