@@ -147,13 +147,13 @@ def ncu_traffic(kernel, units=None):
     Captures are taken on a smaller launch; for the scan the per-base figure is scaled to this launch."""
     p = os.path.join(ROOT, 'profiles', 'r02_traffic.json')
     if not os.path.exists(p):
-        return None
+        return None, None
     e = json.load(open(p)).get(kernel)
     if e is None:
-        return None
+        return None, None
     if units is not None and 'bytes_per_base' in e:
-        return {'bytes': e['bytes_per_base'] * units, 'how': f"{e['bytes_per_base']:.3f} B/base measured by ncu on {e['launch']}, scaled to this launch"}
-    return {'bytes': e['bytes_per_launch'], 'how': 'ncu capture of ' + e['launch']}
+        return e['bytes_per_base'] * units, f"{e['bytes_per_base']:.3f} B/base measured by ncu on {e['launch']}, scaled to this launch"
+    return e['bytes_per_launch'], 'ncu capture of ' + e['launch']
 
 
 def peaks():
@@ -482,7 +482,7 @@ def main():
         instr_per_cell = 1.5                       # minimal s16x2 cost of the linear-gap cell
         peak_gcups = dpx.value / instr_per_cell / 1e9
         roof = {'bound': 'int_alu', 'kernel': 'nw_wave_kernel', 'achieved': k_gcups, 'peak': peak_gcups, 'unit': 'GCUPS',
-                'frac': k_gcups / peak_gcups, 'traffic': ncu_traffic('nw_wave_kernel'),
+                'frac': k_gcups / peak_gcups, 'traffic': ncu_traffic('nw_wave_kernel')[0], 'traffic_how': ncu_traffic('nw_wave_kernel')[1],
                 'peak_source': f'measured in this run: {dpx.value / 1e12:.2f} T VIMNMX3.U16x2 lane-ops/s (tg_int_alu_peak: '
                                f'{100 * dpx.value / nominal:.1f} % of SMs x 64 lanes x max clock) / 1.5 instr per cell '
                                f'(SURVEY 8d); add+max3 pair rate {mixed.value / 1e12:.2f} T pairs/s',
@@ -502,7 +502,8 @@ def main():
         pk, src = peaks()
         ach = scan_bases * 2.375 / min(ds) / 1e9
         roof_scan = {'bound': 'hbm', 'kernel': 'scan_cov_kernel<density>', 'achieved': ach, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
-                     'frac': ach / pk['hbm_gbs'], 'traffic': ncu_traffic('scan_cov_kernel<density>', scan_bases), 'peak_source': src, 'launch_ms': min(ds) * 1e3,
+                     'frac': ach / pk['hbm_gbs'], 'traffic': ncu_traffic('scan_cov_kernel<density>', scan_bases)[0],
+                     'traffic_how': ncu_traffic('scan_cov_kernel<density>', scan_bases)[1], 'peak_source': src, 'launch_ms': min(ds) * 1e3,
                      'bytes_per_base': 2.375, 'mbases_per_s': scan_bases / min(ds) / 1e6}
 
     # ---------------- D2: many small matrices, iteration-2 shape (N=48, L<=3000, R=3) ----------------
