@@ -633,7 +633,9 @@ def main():
             ard = [(f'read{i}', r, None) for i, r in enumerate(scan_reads)]
             tg_tel.get_tel_repeat_comp_parallel(ard[:64], gp)
             st = []
+            res = None
             for _ in range(2):
+                res = None                            # (dropping the previous pass's ~15 M result objects is the caller's business, not the call's)
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
                 res = tg_tel.get_tel_repeat_comp_parallel(ard, gp)

@@ -22,7 +22,26 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def host_ext_path():
+    import sysconfig
+    return os.path.join(HERE, '_tg_hostlists' + (sysconfig.get_config_var('EXT_SUFFIX') or '.so'))
+
+
+def build_host_ext(force=False):
+    """telogator2_b200/_tg_hostlists*.so: CPython extension that formats span arrays as the reference's nested lists and packs
+    read strings into the upload buffer (chost/tg_hostlists.c; gcc, no third-party headers)."""
+    import sysconfig
+    src = os.path.join(HERE, 'chost', 'tg_hostlists.c')
+    out = host_ext_path()
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(src):
+        return out
+    cc = os.environ.get('CC', 'gcc')
+    subprocess.check_call([cc, '-O2', '-shared', '-fPIC', '-fvisibility=hidden', '-I' + sysconfig.get_paths()['include'], src, '-o', out])
+    return out
+
+
 def build(force=False, verbose=False):
+    build_host_ext(force)
     if not force and not _stale():
         return SO
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')

@@ -140,6 +140,21 @@ def pinned_bytes(slot, nbytes):
     return buf[:nbytes]
 
 
+def _hostlists():
+    """The CPython helper that formats results (chost/tg_hostlists.c); None when it has not been built (pure-Python
+    formatting is used then -- it is the same formatting, only slower)."""
+    global _hostlists_mod
+    if _hostlists_mod is False:
+        try:
+            from . import _tg_hostlists
+            _hostlists_mod = _tg_hostlists
+        except ImportError:
+            _hostlists_mod = None
+    return _hostlists_mod
+
+
+_hostlists_mod = False
+
 _ACGTN = np.zeros(256, dtype=bool)
 _ACGTN[[ord(c) for c in 'ACGTN']] = True
 ALIGN = 128
@@ -161,12 +176,16 @@ class PackedReads:
         self.total = total
         ascii_h = pinned_bytes('ascii', max(total, 16))
         buf = ascii_h.numpy()
-        pad = b'N' * ALIGN
-        joined = b''.join(x for i, r in enumerate(reads)
-                          for x in (r.encode('latin-1', 'replace'), pad[:int(padded[i]) - len(r)]))
-        if len(joined) != total:
-            raise ValueError('reads must be str of single-byte characters')
-        buf[:total] = np.frombuffer(joined, dtype=np.uint8)
+        H = _hostlists()
+        if H is not None:
+            H.pack_reads(reads if isinstance(reads, (list, tuple)) else list(reads), self.base_off, buf[:total], ord('N'))
+        else:
+            pad = b'N' * ALIGN
+            joined = b''.join(x for i, r in enumerate(reads)
+                              for x in (r.encode('latin-1', 'replace'), pad[:int(padded[i]) - len(r)]))
+            if len(joined) != total:
+                raise ValueError('reads must be str of single-byte characters')
+            buf[:total] = np.frombuffer(joined, dtype=np.uint8)
         self._reads = reads
         self._bad_reads = None
         self.h2d_bytes = total + self.base_off.nbytes + self.lens.nbytes
@@ -305,13 +324,19 @@ class PackedReads:
         gc_was_on = gc.isenabled()
         gc.disable()
         try:
-            pairs = pairs.tolist()
+            H = _hostlists()
+            cuts = np.ascontiguousarray(np.searchsorted(group, np.arange(ns * K + 1, dtype=np.int64)), dtype=np.int64)
             t.append(time.perf_counter())
-            cuts = np.searchsorted(group, np.arange(ns * K + 1, dtype=np.int64)).tolist()
+            if H is not None:
+                out = H.hit_lists(np.ascontiguousarray(pairs), cuts, ns, K)
+                t.append(time.perf_counter())
+            else:
+                pairs = pairs.tolist()
+                t.append(time.perf_counter())
+                cuts = cuts.tolist()
+                out = [[pairs[cuts[q * K + k]:cuts[q * K + k + 1]] for k in range(K)] for q in range(ns)]
             t.append(time.perf_counter())
-            out = [[pairs[cuts[q * K + k]:cuts[q * K + k + 1]] for k in range(K)] for q in range(ns)]
-            t.append(time.perf_counter())
-            self.last_hits_phases = dict(zip(('kernel', 'sort_d2h', 'tolist', 'cuts', 'slices'), np.diff(t).tolist()))
+            self.last_hits_phases = dict(zip(('kernel', 'sort_d2h', 'cuts', 'lists', 'rest'), np.diff(t).tolist()))
             return out
         finally:
             if gc_was_on:

@@ -693,3 +693,40 @@ def test_scan_batch_boundary_host_logic_on_cpu(monkeypatch, kmer_tables, golden_
         reads, params = _tel_inputs(kmer_tables, golden_reads, tkey, filters)
         got = tg_tel.get_tel_repeat_comp_parallel(reads, params, max_workers=3, get_terminating_tl=make_gtt(dens))
         assert digest_tel_result(got) == gold[tkey], tkey
+
+
+def test_host_list_helper_formats_like_the_python_code():
+    """chost/tg_hostlists.c (CPython extension, formatting only): nested hit lists and read packing equal the pure-Python code."""
+    import importlib
+    from telogator2_b200 import build
+    build.build_host_ext()
+    H = importlib.import_module('telogator2_b200._tg_hostlists')
+    rng = np.random.default_rng(5)
+    ns, K = 7, 5
+    counts = rng.integers(0, 4, ns * K)
+    counts[3] = 0
+    cuts = np.zeros(ns * K + 1, dtype=np.int64)
+    cuts[1:] = np.cumsum(counts)
+    pairs = rng.integers(0, 70000, (int(cuts[-1]), 2)).astype(np.int32)
+    got = H.hit_lists(pairs, cuts, ns, K)
+    pl = pairs.tolist()
+    want = [[pl[cuts[q * K + k]:cuts[q * K + k + 1]] for k in range(K)] for q in range(ns)]
+    assert got == want and all(type(v) is int for q in got for k in q for sp in k for v in sp)
+    assert H.hit_lists(np.zeros((0, 2), dtype=np.int32), np.zeros(1, dtype=np.int64), 0, K) == []
+    with pytest.raises(ValueError):
+        H.hit_lists(pairs, cuts[::-1].copy(), ns, K)
+    with pytest.raises(ValueError):
+        H.hit_lists(pairs.astype(np.int64), cuts, ns, K)
+    reads = ['ACGT' * 5, '', 'N', 'acgtX', 'ACéGT', 'A中C', 'ACGT' * 40]
+    lens = np.array([len(r) for r in reads])
+    padded = (lens + 128) // 128 * 128
+    off = np.zeros(len(reads) + 1, dtype=np.int64)
+    off[1:] = np.cumsum(padded)
+    out = np.zeros(int(off[-1]), dtype=np.uint8)
+    H.pack_reads(reads, off, out, ord('N'))
+    want = b''.join(r.encode('latin-1', 'replace') + b'N' * int(p - len(r)) for r, p in zip(reads, padded))
+    assert out.tobytes() == want
+    with pytest.raises(ValueError):
+        H.pack_reads(reads, off[:-1].copy(), out, ord('N'))
+    with pytest.raises(TypeError):
+        H.pack_reads([b'ACGT'], off[:2].copy(), out, ord('N'))

@@ -15,7 +15,9 @@ sr = bench.make_scan_workload(reads, int(mbases * 1e6))
 gp = bench.scan_gtrc_params(tables['human_hifi'], tg_kmer.RC)
 ard = [(f'read{i}', r, None) for i, r in enumerate(sr)]
 tg_tel.get_tel_repeat_comp_parallel(ard[:64], gp)
+res = None
 for it in range(3):
+    res = None
     t0 = time.perf_counter()
     res = tg_tel.get_tel_repeat_comp_parallel(ard, gp)
     dt = time.perf_counter() - t0
