@@ -488,6 +488,10 @@ __global__ void __launch_bounds__(WAVE_MAX_WARPS * 32, 1) nw_wave_kernel(const _
             // letters of rows 2k and 2k + 1 of both alignments: four byte loads (LSU) instead of one word and six mask/shift
             // instructions -- the loop is bound by the half-rate ALU pipe, the load/store pipe has room
             const uint32_t rk0 = rows_s + 2 * ROFF;
+            uint32_t is_lane0;
+            asm("mov.u32 %0, %1;" : "=r"(is_lane0) : "r"((uint32_t)(lane == 0)));      // opaque to the optimiser: keep the multiply-adds
+            uint32_t not_lane0;
+            asm("mov.u32 %0, %1;" : "=r"(not_lane0) : "r"((uint32_t)(lane != 0)));
             uint32_t a00 = lds_u8(rk0 + 4 * k), a01 = lds_u8(rk0 + 4 * k + 1), a10 = lds_u8(rk0 + 4 * k + 2), a11 = lds_u8(rk0 + 4 * k + 3);
             for (int s = 0; s < steps; s++, k++, bw++) {
                 if ((s & 31) == 0) {
@@ -501,7 +505,10 @@ __global__ void __launch_bounds__(WAVE_MAX_WARPS * 32, 1) nw_wave_kernel(const _
                 uint32_t L0 = __shfl_up_sync(TG_FULL_MASK, A7, 1);
                 uint32_t L1 = __shfl_up_sync(TG_FULL_MASK, H[C - 1], 1);
                 const uint2 rb = lds64(ring_s + 8 * (k & 63));
-                if (lane == 0) { L0 = rb.x; L1 = rb.y; }             // (lane 0 has k = s >= 0)
+                // lane 0 takes the border of the previous column block instead (it has k = s >= 0).  Written as a multiply-add
+                // with a 0/1 factor so that it runs on the FMA pipe: the loop is bound by the half-rate ALU pipe, where a select lives
+                L0 = rb.x * is_lane0 + L0 * not_lane0;
+                L1 = rb.y * is_lane0 + L1 * not_lane0;
                 using S2 = typename std::conditional<C == 16, Strip2x16<WIDE>, Strip2x8<WIDE>>::type;
                 A7 = S2::run(H, prevL1, L0, L1, pb0 + a00 * W, pb1 + a01 * W, pb0 + a10 * W, pb1 + a11 * W);
                 if (lane == 31) *bw = make_uint2(A7, H[C - 1]);
