@@ -320,13 +320,13 @@ int tg_prefilter_count(const uint8_t *d_ascii, const int64_t *d_base_off, const 
  * Per read r: n = d_sig_n[r] power samples (len(read) - window, or 0), float64 slabs at element offsets d_x_off[r]
  * (even(n) samples), d_a_off[r] (approximations a_1..a_L, each padded to an even length) and d_d_off[r] (details d_1..d_L,
  * contiguous; d_d_off has n_reads + 1 entries), m_0 = n, m_l = ceil(m_(l-1) / 2), L = floor(log2(n / 7)).  max_n = the
- * largest n of the batch (grid sizing).
+ * largest n of the batch, total_n = their sum (grid sizing only: a few blocks per read walk its tiles).
  * ======================================================================================= */
 
 /* X[r][i] = cnt_p[base_off[r] + i] / window - cnt_q[base_off[r] + i] / window, i < n: the p-vs-q power signal from the two
  * window-count planes of tg_scan_density (tg_kmer.py:90, 114-115). */
 int tg_bound_power(const uint8_t *d_cnt_p, const uint8_t *d_cnt_q, const int64_t *d_base_off, const int32_t *d_sig_n,
-                   const int64_t *d_x_off, int n_reads, int max_n, int window, double *d_X, void *stream);
+                   const int64_t *d_x_off, int n_reads, int max_n, int64_t total_n, int window, double *d_X, void *stream);
 
 /* wavelet_smooth(X[r]) in place for every read with n >= window (tg_kmer.py:116-117, 152-170): d_smoothed[r] = 1 and
  * d_out_len[r] = even(n) when the signal was replaced by its reconstruction, 0 and n when one of the two early-outs
@@ -334,7 +334,7 @@ int tg_bound_power(const uint8_t *d_cnt_p, const uint8_t *d_cnt_q, const int64_t
  * (host); d_sigma / d_uthresh receive mad(coeff[-smoothing_level]) and the threshold.  d_scratch / d_sc_off: sort space for
  * reads whose coeff[-smoothing_level] has more than 4096 entries (offset per read, -1 = not needed). */
 int tg_bound_smooth(double *d_X, double *d_A, double *d_D, const int64_t *d_x_off, const int64_t *d_a_off,
-                    const int64_t *d_d_off, const int32_t *d_sig_n, int n_reads, int max_n, int window,
+                    const int64_t *d_d_off, const int32_t *d_sig_n, int n_reads, int max_n, int64_t total_n, int window,
                     int smoothing_level, double fail_sigma, const double *d_log_factor, double *d_scratch,
                     const int64_t *d_sc_off, double *d_uthresh, double *d_sigma, int32_t *d_out_len,
                     uint8_t *d_smoothed, void *stream);

@@ -105,8 +105,8 @@ def load():
     L.tg_cv_denoise.argtypes = [vp, vp, vp, vp, vp, vp, i32, i64, i32, i32, i32, C.c_char_p, i32, C.c_char_p, i32, vp, vp]
     L.tg_prefilter_count.argtypes = [vp, vp, vp, i32, C.c_char_p, C.c_char_p, i32, vp, vp, vp, vp]
     f64 = C.c_double
-    L.tg_bound_power.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp]
-    L.tg_bound_smooth.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f64, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.tg_bound_power.argtypes = [vp, vp, vp, vp, vp, i32, i32, i64, i32, vp, vp]
+    L.tg_bound_smooth.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i64, i32, i32, f64, vp, vp, vp, vp, vp, vp, vp, vp]
     L.tg_bound_regions.argtypes = [vp, vp, vp, vp, i32, i32, f64, vp, vp, vp, vp, vp, vp, vp]
     L.tg_bound_terminating.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, f64, vp, vp]
     _lib = L

@@ -78,13 +78,16 @@ __device__ __forceinline__ LevelGeom bd_level(int n, int lev)
 __global__ void __launch_bounds__(BD_TILE) bd_power_kernel(const uint8_t *__restrict__ cnt_p, const uint8_t *__restrict__ cnt_q,
                                                            const int64_t *__restrict__ base_off, BdParams P, int read0)
 {
+    // c / W for every possible count: the reference's float64 division, done once per block instead of twice per sample
+    __shared__ double s_dens[256];
+    s_dens[threadIdx.x] = __ddiv_rn((double)threadIdx.x, (double)P.window);
+    __syncthreads();
     const int r = read0 + blockIdx.y;
     const int n = P.sig_n[r];
-    const int i = blockIdx.x * BD_TILE + threadIdx.x;
-    if (i >= n) return;
-    const long long b = base_off[r] + i;
-    const double w = (double)P.window;
-    P.X[P.x_off[r] + i] = __dsub_rn(__ddiv_rn((double)cnt_p[b], w), __ddiv_rn((double)cnt_q[b], w));
+    const uint8_t *cp = cnt_p + base_off[r], *cq = cnt_q + base_off[r];
+    double *x = P.X + P.x_off[r];
+    for (int i = blockIdx.x * BD_TILE + threadIdx.x; i < n; i += gridDim.x * BD_TILE)
+        x[i] = __dsub_rn(s_dens[cp[i]], s_dens[cq[i]]);
 }
 
 // ---- one periodised analysis level for every read that has it ----
@@ -93,23 +96,25 @@ __global__ void __launch_bounds__(BD_TILE) bd_dwt_kernel(BdParams P, int lev, in
     const int r = read0 + blockIdx.y;
     const int n = P.sig_n[r];
     if (!bd_decomposed(n, P) || bd_max_level(n) < lev) return;
-    const int o = blockIdx.x * BD_TILE + threadIdx.x;
     const LevelGeom g = bd_level(n, lev);
-    if (o >= g.m_out) return;
     const double *in = lev == 1 ? P.X + P.x_off[r] : P.A + P.a_off[r] + g.a_prev_rel;
+    double *oa = P.A + P.a_off[r] + g.a_rel, *od = P.D + P.d_off[r] + g.d_rel;
     const int np = (g.m_in + 1) & ~1;                     // an odd-length input is padded with a copy of its last sample
-    double ca = 0.0, cd = 0.0;
+    // (the grid has a few blocks per read; each walks its share of the read's tiles)
+    for (int o = blockIdx.x * BD_TILE + threadIdx.x; o < g.m_out; o += gridDim.x * BD_TILE) {
+        double ca = 0.0, cd = 0.0;
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-        int t = 4 + 2 * o - j;
-        if (t < 0) t += np; else if (t >= np) t -= np;
-        if (t >= g.m_in) t = g.m_in - 1;
-        const double v = in[t];
-        ca = __dadd_rn(ca, __dmul_rn(c_lo[j], v));
-        cd = __dadd_rn(cd, __dmul_rn(c_hi[j], v));
+        for (int j = 0; j < 8; j++) {
+            int t = 4 + 2 * o - j;
+            if (t < 0) t += np; else if (t >= np) t -= np;
+            if (t >= g.m_in) t = g.m_in - 1;
+            const double v = in[t];
+            ca = __dadd_rn(ca, __dmul_rn(c_lo[j], v));
+            cd = __dadd_rn(cd, __dmul_rn(c_hi[j], v));
+        }
+        oa[o] = ca;
+        od[o] = cd;
     }
-    P.A[P.a_off[r] + g.a_rel + o] = ca;
-    P.D[P.d_off[r] + g.d_rel + o] = cd;
 }
 
 __device__ void bd_bitonic_sort(double *buf, int npow)
@@ -184,13 +189,15 @@ __global__ void __launch_bounds__(BD_TILE) bd_threshold_kernel(BdParams P, int r
 {
     const int r = read0 + blockIdx.y;
     if (!P.smoothed[r]) return;
-    const long long lo = P.d_off[r], len = P.d_off[r + 1] - lo;
-    const long long i = (long long)blockIdx.x * BD_TILE + threadIdx.x;
-    if (i >= len) return;
-    const double d = P.D[lo + i];
-    double t = __dsub_rn(1.0, __ddiv_rn(P.uthresh[r], fabs(d)));
-    if (t < 0.0) t = 0.0;
-    P.D[lo + i] = __dmul_rn(d, t);
+    double *dd = P.D + P.d_off[r];
+    const long long len = P.d_off[r + 1] - P.d_off[r];
+    const double u = P.uthresh[r];
+    for (long long i = (long long)blockIdx.x * BD_TILE + threadIdx.x; i < len; i += (long long)gridDim.x * BD_TILE) {
+        const double d = dd[i];
+        double t = __dsub_rn(1.0, __ddiv_rn(u, fabs(d)));
+        if (t < 0.0) t = 0.0;
+        dd[i] = __dmul_rn(d, t);
+    }
 }
 
 // ---- one periodised synthesis level: the transpose of bd_dwt_kernel's map ----
@@ -202,21 +209,21 @@ __global__ void __launch_bounds__(BD_TILE) bd_idwt_kernel(BdParams P, int lev, i
     if (bd_max_level(n) < lev) return;
     const LevelGeom g = bd_level(n, lev);
     const int m = g.m_out;
-    const int x = blockIdx.x * BD_TILE + threadIdx.x;
-    if (x >= 2 * m) return;
     const double *a = P.A + P.a_off[r] + g.a_rel;         // (a reconstruction one sample longer than d_l is cut to len(d_l))
     const double *d = P.D + P.d_off[r] + g.d_rel;
     double *out = lev == 1 ? P.X + P.x_off[r] : P.A + P.a_off[r] + g.a_prev_rel;
-    double v = 0.0;
+    for (int x = blockIdx.x * BD_TILE + threadIdx.x; x < 2 * m; x += gridDim.x * BD_TILE) {
+        double v = 0.0;
 #pragma unroll
-    for (int t = 0; t < 4; t++) {
-        const int j = 2 * t + (x & 1);
-        int k = (x + j - 4) >> 1;
-        if (k < 0) k += m; else if (k >= m) k -= m;
-        v = __dadd_rn(v, __dmul_rn(c_lo[j], a[k]));
-        v = __dadd_rn(v, __dmul_rn(c_hi[j], d[k]));
+        for (int t = 0; t < 4; t++) {
+            const int j = 2 * t + (x & 1);
+            int k = (x + j - 4) >> 1;
+            if (k < 0) k += m; else if (k >= m) k -= m;
+            v = __dadd_rn(v, __dmul_rn(c_lo[j], a[k]));
+            v = __dadd_rn(v, __dmul_rn(c_hi[j], d[k]));
+        }
+        out[x] = v;
     }
-    out[x] = v;
 }
 
 // ---- region walk (tg_kmer.py:118-140): maximal runs of one class; count mode (reg_off == nullptr) or fill mode ----
@@ -362,16 +369,28 @@ __global__ void __launch_bounds__(128) bd_terminating_kernel(TermParams P)
 // =====================================================================================================================
 // C ABI
 // =====================================================================================================================
+// Blocks per read for a pass over `avg` elements per read (the longest has `mx`): a few tiles per block, so that reads much
+// shorter than the longest one do not leave most of the grid idle; every kernel walks its read's tiles with a grid stride.
+static int bd_blocks_x(long long avg, long long mx)
+{
+    long long b = (avg + 2 * BD_TILE - 1) / (2 * BD_TILE);
+    const long long cap = (mx + BD_TILE - 1) / BD_TILE;
+    if (b > cap) b = cap;
+    if (b > 64) b = 64;
+    return b < 1 ? 1 : (int)b;
+}
+
 TG_EXPORT int tg_bound_power(const uint8_t *d_cnt_p, const uint8_t *d_cnt_q, const int64_t *d_base_off, const int32_t *d_sig_n,
-                             const int64_t *d_x_off, int n_reads, int max_n, int window, double *d_X, void *stream_)
+                             const int64_t *d_x_off, int n_reads, int max_n, int64_t total_n, int window, double *d_X, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (n_reads < 0 || window < 1) return tg_set_err(TG_EINVAL, "tg_bound_power: bad arguments");
+    if (n_reads < 0 || window < 1 || window > 255) return tg_set_err(TG_EINVAL, "tg_bound_power: bad arguments (window 1..255)");
     if (n_reads == 0 || max_n <= 0) return TG_OK;
+    const long long avg_n = total_n > 0 ? total_n / n_reads : max_n;
     BdParams P = {};
     P.X = d_X; P.x_off = d_x_off; P.sig_n = d_sig_n; P.n_reads = n_reads; P.window = window;
     for (int r0 = 0; r0 < n_reads; r0 += 65535) {
-        dim3 grid((max_n + BD_TILE - 1) / BD_TILE, min(65535, n_reads - r0));
+        dim3 grid(bd_blocks_x(avg_n, max_n), min(65535, n_reads - r0));
         bd_power_kernel<<<grid, BD_TILE, 0, stream>>>(d_cnt_p, d_cnt_q, d_base_off, P, r0);
     }
     TG_CUDA_CHECK(cudaGetLastError());
@@ -379,7 +398,7 @@ TG_EXPORT int tg_bound_power(const uint8_t *d_cnt_p, const uint8_t *d_cnt_q, con
 }
 
 TG_EXPORT int tg_bound_smooth(double *d_X, double *d_A, double *d_D, const int64_t *d_x_off, const int64_t *d_a_off,
-                              const int64_t *d_d_off, const int32_t *d_sig_n, int n_reads, int max_n, int window,
+                              const int64_t *d_d_off, const int32_t *d_sig_n, int n_reads, int max_n, int64_t total_n, int window,
                               int smoothing_level, double fail_sigma, const double *d_log_factor, double *d_scratch,
                               const int64_t *d_sc_off, double *d_uthresh, double *d_sigma, int32_t *d_out_len,
                               uint8_t *d_smoothed, void *stream_)
@@ -395,23 +414,20 @@ TG_EXPORT int tg_bound_smooth(double *d_X, double *d_A, double *d_D, const int64
     int max_lev = 0;
     if (max_n >= 7) { int q = max_n / 7; while (q > 1) { q >>= 1; max_lev++; } }
     const bool any = max_n >= window && max_lev + 1 >= smoothing_level;
+    const long long avg_n = total_n > 0 ? total_n / n_reads : max_n;
     for (int r0 = 0; r0 < n_reads; r0 += 65535) {
         const int nr = min(65535, n_reads - r0);
-        int m = max_n;
         if (any)
             for (int lev = 1; lev <= max_lev; lev++) {
-                m = (m + 1) >> 1;
-                dim3 grid((m + BD_TILE - 1) / BD_TILE, nr);
+                dim3 grid(bd_blocks_x(avg_n >> lev, ((long long)max_n >> lev) + 1), nr);
                 bd_dwt_kernel<<<grid, BD_TILE, 0, stream>>>(P, lev, r0);
             }
         bd_sigma_kernel<<<nr, 256, 0, stream>>>(P, r0);
         if (any) {
-            dim3 tgrid((max_n + max_lev + BD_TILE - 1) / BD_TILE, nr);
+            dim3 tgrid(bd_blocks_x(avg_n, (long long)max_n + max_lev), nr);
             bd_threshold_kernel<<<tgrid, BD_TILE, 0, stream>>>(P, r0);
             for (int lev = max_lev; lev >= 1; lev--) {
-                int mo = max_n;
-                for (int l = 0; l < lev; l++) mo = (mo + 1) >> 1;
-                dim3 grid((2 * mo + BD_TILE - 1) / BD_TILE, nr);
+                dim3 grid(bd_blocks_x(avg_n >> (lev - 1), ((long long)max_n >> (lev - 1)) + 2), nr);
                 bd_idwt_kernel<<<grid, BD_TILE, 0, stream>>>(P, lev, r0);
             }
         }

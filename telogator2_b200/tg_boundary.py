@@ -42,6 +42,7 @@ class BoundaryBatch:
         self.n_reads = int(n.size)
         self.sig_n = n.astype(np.int32)
         self.max_n = int(n.max()) if n.size else 0
+        self.total_n = int(n.sum())
         lev = _levels(n)
         dec = (n >= self.window) & (lev + 1 >= SMOOTHING_LEVEL)        # reads wavelet_smooth decomposes
         a_sz = np.zeros_like(n)
@@ -94,7 +95,7 @@ class BoundaryBatch:
         """X = cnt_p / window - cnt_q / window from the uint8 planes of tg_scan_density (padded base space)."""
         torch = self.torch
         _lib.check(self.L.tg_bound_power(_lib.dptr(d_cnt_p), _lib.dptr(d_cnt_q), _lib.dptr(d_base_off), _lib.dptr(self.d_sig_n),
-                                         _lib.dptr(self.d_x_off), self.n_reads, self.max_n, self.window, _lib.dptr(self.d_X),
+                                         _lib.dptr(self.d_x_off), self.n_reads, self.max_n, self.total_n, self.window, _lib.dptr(self.d_X),
                                          _lib.stream_ptr(torch)))
 
     def power_from_host(self, signals):
@@ -110,7 +111,7 @@ class BoundaryBatch:
         torch = self.torch
         _lib.check(self.L.tg_bound_smooth(_lib.dptr(self.d_X), _lib.dptr(self.d_A), _lib.dptr(self.d_D), _lib.dptr(self.d_x_off),
                                           _lib.dptr(self.d_a_off), _lib.dptr(self.d_d_off), _lib.dptr(self.d_sig_n), self.n_reads,
-                                          self.max_n, self.window, SMOOTHING_LEVEL, FAIL_SIGMA, _lib.dptr(self.d_log_factor),
+                                          self.max_n, self.total_n, self.window, SMOOTHING_LEVEL, FAIL_SIGMA, _lib.dptr(self.d_log_factor),
                                           _lib.dptr(self.d_scratch), _lib.dptr(self.d_sc_off), _lib.dptr(self.d_uthresh),
                                           _lib.dptr(self.d_sigma), _lib.dptr(self.d_out_len), _lib.dptr(self.d_smoothed),
                                           _lib.stream_ptr(torch)))
