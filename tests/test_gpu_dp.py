@@ -350,6 +350,25 @@ def test_pipelined_batches_and_per_job_profiles_change_nothing(tga, colorvecs, R
         assert np.array_equal(got[(pipe, rows)], Do), (pipe, rows)
 
 
+def test_per_job_profiles_with_several_matrices(tga, colorvecs, monkeypatch):
+    """Several matrices in one pair space (multi-matrix instantiation of the kernels) with the per-job query profiles forced on."""
+    ont, hifi = _cases(colorvecs)
+    groups = [[c[:900 + 13 * i] for i, c in enumerate(hifi[:7])], [c[:1000] for c in ont[:5]], [hifi[9][:800]], [c[:1000] for c in hifi[20:26]]]
+    aligner = tga.get_aligner_object(tga.get_scoring_matrix('C', 'tvr'), (True, True), 'tvr')
+    want = None
+    for rows in ('0', '8', '13'):
+        monkeypatch.setenv('TG_WAVE_PROF_ROWS', rows)
+        got = tga.get_dist_matrices_parallel(groups, aligner, True, True, 3, rng_seed=4242)
+        if want is None:
+            want = got
+            P = _P(oracle.scoring_matrix('C', 'tvr'), (True, True))
+            for g, D in zip(groups, got):
+                if len(g) >= 2:
+                    assert np.array_equal(D, oracle.dist_matrix_c(g, P, True, True, 3, 4242))
+        else:
+            assert all(np.array_equal(a, b) for a, b in zip(got, want)), rows
+
+
 def test_against_real_biopython_when_importable(tga, colorvecs):
     """The one unpinned piece: Bio.Align.PairwiseAligner.score.  Skipped where Biopython is absent (the build image and the GPU
     boxes: profiles/r02_pin_biopython_*.log); wherever it is importable this compares the CUDA matrices with the reference's
