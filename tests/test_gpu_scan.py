@@ -141,6 +141,45 @@ def test_scale_properties(tgk, kmer_tables, golden_reads):
     assert np.array_equal(bc[:len(base)], bc[-len(base):])
 
 
+def test_bench_workload_sample_against_oracle(tgk, kmer_tables, reads_all):
+    """The bench's scan workload at 60 Mbases (bundled HiFi + ONT reads replicated with seeded edits: every read different, tile
+    and read boundaries at every alignment): base counts, orientation, both densities, the hits of the last 6000 bases and
+    the boundary calling of a sample of reads, each against the CPU oracle on that read alone."""
+    from oracle import boundary as B
+    from telogator2_b200 import tg_boundary
+    rng = np.random.default_rng(99)
+    base = [r for _, r in reads_all['human_hifi']] + [r for _, r in reads_all['human_ont']]
+    acgt = np.frombuffer(b'ACGTN', dtype=np.uint8)
+    reads, tot, i = [], 0, 0
+    while tot < 60_000_000:
+        a = np.frombuffer(base[i % len(base)].encode(), dtype=np.uint8).copy()
+        k = max(len(a) // 150, 1)
+        a[rng.integers(len(a), size=k)] = acgt[rng.integers(4 + (i % 7 == 0), size=k)]       # (every 7th read also gets Ns)
+        reads.append(a.tobytes().decode())
+        tot += len(a)
+        i += 1
+    T = kmer_tables['human_hifi']
+    KL, ISSUB, CANON = T['KMER_LIST'], T['KMER_ISSUBSTRING'], T['CANONICAL_STRINGS']
+    KLR, CR = [rc_py(k) for k in KL], [rc_py(k) for k in CANON]
+    pr = tgk.PackedReads(reads)
+    bc = pr.basecount(CANON, CR).cpu().numpy()
+    flip = bc[:, 0] > bc[:, 1]
+    pr.orient(flip)
+    d_p, d_q = pr.density_counts(KL, KLR, 100)
+    term = tg_boundary.terminating_tl_from_counts(d_p, d_q, pr.d_base_off, pr.lens, 100, 0.5, 100, 'q')
+    cp, cq = pr.split_counts(d_p.cpu().numpy(), 100), pr.split_counts(d_q.cpu().numpy(), 100)
+    sample = np.sort(rng.choice(len(reads), 150, replace=False))
+    lens = pr.lens.astype(np.int64)
+    hits = pr.hits(sample, np.maximum(lens[sample] - 6000, 0), lens[sample], KLR, ISSUB)
+    for q, r in enumerate(sample.tolist()):
+        fl, ori, c0, c1, obc = oracle.scan_read(reads[r], KL, KLR, CANON, CR, 100)
+        assert bc[r].tolist() == obc.tolist() and bool(flip[r]) == fl, r
+        assert np.array_equal(cp[r], c0) and np.array_equal(cq[r], c1), r
+        assert hits[q] == oracle.nonoverlapping_hits(ori[-6000:], KLR, ISSUB), r
+        (tl, edge, inter) = B.get_terminating_tl(c0.astype(np.float64) / 100, c1.astype(np.float64) / 100, 'q', 100, 0.5, 100)
+        assert term[r].tolist() == [tl, edge] + ([-1, -1] if inter is None else list(inter)), r
+
+
 def test_limits_fail_loudly(tgk, kmer_tables):
     T = kmer_tables['human_hifi']
     KL = T['KMER_LIST']
