@@ -353,6 +353,23 @@ int tg_bound_terminating(const int64_t *d_reg_off, const int32_t *d_reg_count, c
                          const uint8_t *d_reg_cls, const int32_t *d_last_end, int n_reads, int pq_is_p, int window,
                          double min_tel_score, int32_t *d_out, void *stream);
 
+/* =========================================================================================
+ * Hierarchical clustering of the distance matrix ("scipy linkage itself"): scipy.cluster.hierarchy.linkage
+ * as called at tg_tvr.py:166-167 and :397-398, methods ward / single / complete / average / weighted.
+ * The merge list is bit-identical to scipy's (same nearest-neighbour-chain / MST algorithms, same float64 evaluation order).
+ * ======================================================================================= */
+
+/* d_square[i][j] = d_condensed[condensed_index(n, i, j)] (what scipy.spatial.distance.squareform(y) builds), diagonal 0. */
+int tg_linkage_expand(const double *d_condensed, int n, double *d_square, void *stream);
+/* d_square = float64(d_matrix / div) with the division in float32 (tg_tvr.py:154: dist_matrix /= MAX_SEQ_DIST on the float32
+ * matrix), or float64(d_matrix) when div == 0: clustering straight from the device matrix of tg_dist_epilogue. */
+int tg_linkage_widen(const float *d_matrix, int n, float div, double *d_square, void *stream);
+/* Runs the algorithm on d_square (n x n float64, destroyed).  d_size: n int32, all ones (ward .. weighted); d_chain: n int32
+ * scratch; d_near: n float64 scratch; d_Z receives n - 1 rows (x, y, distance, size) in MERGE order with original cluster
+ * indices: the caller sorts them by distance (stable) and relabels them (scipy's `label`), see telogator2_b200/tg_linkage.py. */
+int tg_linkage_run(double *d_square, int n, const char *method, int32_t *d_size, int32_t *d_chain, double *d_near,
+                   double *d_Z, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

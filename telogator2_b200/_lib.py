@@ -60,7 +60,8 @@ EXPORTS = ['tg_last_error', 'tg_version', 'tg_device_sm_count',
            'tg_scan_density', 'tg_scan_hits',
            'tg_cv_paint', 'tg_cv_density_boundary', 'tg_cv_lead_run', 'tg_cv_gather', 'tg_cv_denoise_tile', 'tg_cv_denoise',
            'tg_prefilter_tail_bytes', 'tg_prefilter_count',
-           'tg_bound_power', 'tg_bound_smooth', 'tg_bound_regions', 'tg_bound_terminating']
+           'tg_bound_power', 'tg_bound_smooth', 'tg_bound_regions', 'tg_bound_terminating',
+           'tg_linkage_expand', 'tg_linkage_widen', 'tg_linkage_run']
 
 
 def load():
@@ -109,6 +110,9 @@ def load():
     L.tg_bound_smooth.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i64, i32, i32, f64, vp, vp, vp, vp, vp, vp, vp, vp]
     L.tg_bound_regions.argtypes = [vp, vp, vp, vp, i32, i32, f64, vp, vp, vp, vp, vp, vp, vp]
     L.tg_bound_terminating.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, f64, vp, vp]
+    L.tg_linkage_expand.argtypes = [vp, i32, vp, vp]
+    L.tg_linkage_widen.argtypes = [vp, i32, C.c_float, vp, vp]
+    L.tg_linkage_run.argtypes = [vp, i32, C.c_char_p, vp, vp, vp, vp, vp]
     _lib = L
     return L
 

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, 'csrc')
 SO = os.path.join(HERE, 'libtg_b200.so')
-SOURCES = ['tg_api.cu', 'tg_dp.cu', 'tg_scan.cu', 'tg_cov.cu', 'tg_cv.cu', 'tg_prefilter.cu', 'tg_bound.cu']
+SOURCES = ['tg_api.cu', 'tg_dp.cu', 'tg_scan.cu', 'tg_cov.cu', 'tg_cv.cu', 'tg_prefilter.cu', 'tg_bound.cu', 'tg_linkage.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC,-fvisibility=hidden', '-I' + os.path.join(ROOT, 'include'), '-I' + CSRC]
 

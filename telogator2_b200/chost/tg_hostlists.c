@@ -17,6 +17,7 @@
 #define PY_SSIZE_T_CLEAN
 #include <Python.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 static PyObject *hit_lists(PyObject *self, PyObject *args)
@@ -117,7 +118,59 @@ done:
     return ret;
 }
 
+/* linkage_label(Z, n): scipy _hierarchy.label -- Z float64 C-contiguous [n - 1, 4], rows sorted by distance, columns 0/1 hold
+ * original cluster indices of the merged pair; rewrites them as union-find cluster ids (smaller first) and fills column 3 with
+ * the size of the new cluster. */
+static PyObject *linkage_label(PyObject *self, PyObject *args)
+{
+    PyObject *z_obj;
+    Py_ssize_t n;
+    if (!PyArg_ParseTuple(args, "On", &z_obj, &n)) return NULL;
+    Py_buffer zb;
+    if (PyObject_GetBuffer(z_obj, &zb, PyBUF_C_CONTIGUOUS | PyBUF_WRITABLE) < 0) return NULL;
+    PyObject *ret = NULL;
+    int64_t *parent = NULL, *size = NULL;
+    if (zb.itemsize != 8 || n < 1 || zb.len != (Py_ssize_t)((n - 1) * 4 * 8)) {
+        PyErr_SetString(PyExc_ValueError, "linkage_label: Z must be a writable float64 [n - 1, 4] array");
+        goto done;
+    }
+    parent = (int64_t *)malloc((size_t)(2 * n) * sizeof(int64_t));
+    size = (int64_t *)malloc((size_t)(2 * n) * sizeof(int64_t));
+    if (!parent || !size) { PyErr_NoMemory(); goto done; }
+    for (Py_ssize_t i = 0; i < 2 * n - 1; i++) { parent[i] = i; size[i] = 1; }
+    {
+        double *Z = (double *)zb.buf;
+        int64_t next = n;
+        for (Py_ssize_t i = 0; i < n - 1; i++) {
+            int64_t r[2];
+            for (int s = 0; s < 2; s++) {
+                int64_t x = (int64_t)Z[4 * i + s];
+                if (x < 0 || x >= n) { PyErr_SetString(PyExc_ValueError, "linkage_label: cluster index out of range"); goto done; }
+                int64_t p = x;
+                while (parent[x] != x) x = parent[x];
+                while (parent[p] != x) { const int64_t q = parent[p]; parent[p] = x; p = q; }
+                r[s] = x;
+            }
+            Z[4 * i] = (double)(r[0] < r[1] ? r[0] : r[1]);
+            Z[4 * i + 1] = (double)(r[0] < r[1] ? r[1] : r[0]);
+            parent[r[0]] = next;
+            parent[r[1]] = next;
+            size[next] = size[r[0]] + size[r[1]];
+            Z[4 * i + 3] = (double)size[next];
+            next++;
+        }
+    }
+    ret = Py_None;
+    Py_INCREF(ret);
+done:
+    free(parent);
+    free(size);
+    PyBuffer_Release(&zb);
+    return ret;
+}
+
 static PyMethodDef methods[] = {
+    {"linkage_label", linkage_label, METH_VARARGS, "scipy's union-find relabelling of a sorted merge list, in place"},
     {"hit_lists", hit_lists, METH_VARARGS, "nested [start, end] lists per (slice, k-mer) from sorted span arrays"},
     {"pack_reads", pack_reads, METH_VARARGS, "copy the characters of a list of str into a padded byte buffer"},
     {NULL, NULL, 0, NULL}};

@@ -50,6 +50,11 @@ def main():
         _lib.stream_ptr = lambda t: None
         b200_align.DistEngine = lambda sc: _engine_from_scoring(sc, OracleLib())
         get_sm, get_al = b200_align.get_scoring_matrix, b200_align.get_aligner_object       # Bio is a stub here
+        # no GPU in the build container: the device linkage (bit-identical to scipy's: tests/test_gpu_linkage.py) is answered
+        # by the oracle's restatement of scipy's algorithm, like the two C entry points of the distance matrix above
+        from oracle import linkage as oracle_linkage
+        assert tg_tvr.linkage.__module__ == 'source.tg_tvr' and tg_tvr._scipy_linkage.__module__.startswith('scipy')
+        tg_tvr.linkage = lambda y, method='single', metric='euclidean', optimal_ordering=False: oracle_linkage.linkage(y, method)
     for m in (tg_align, tg_tvr):
         m.get_scoring_matrix, m.get_aligner_object = get_sm, get_al
 
