@@ -543,6 +543,33 @@ def main():
 
         except Exception as exc:                      # an auxiliary line must not cost the headline metric
             d2 = {'error': f'{type(exc).__name__}: {exc}'}
+    # ---------------- hierarchical clustering of the bench matrix ("scipy linkage itself") ----------------
+    linkage_line = None
+    if world == 1:
+        try:
+            from telogator2_b200 import tg_linkage
+            from scipy.cluster.hierarchy import linkage as scipy_linkage
+            from scipy.spatial.distance import squareform
+            d_D = dp_step()                                   # the float32 matrix where the distance kernels leave it
+            torch.cuda.synchronize()
+            tg_linkage.linkage_from_matrix(d_D, 'ward', divide_by=10.0)
+            lt = []
+            for _ in range(3):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                Zg = tg_linkage.linkage_from_matrix(d_D, 'ward', divide_by=10.0)
+                lt.append(time.perf_counter() - t0)
+            Mh = d_D.cpu().numpy()
+            t0 = time.perf_counter()
+            Mh /= 10.0                                        # tg_tvr.py:154
+            Zs = scipy_linkage(squareform(Mh, checks=False), method='ward')       # tg_tvr.py:166-167
+            t_sc = time.perf_counter() - t0
+            assert np.array_equal(Zg, Zs), 'device linkage differs from scipy'
+            linkage_line = {'n': int(n_seq), 'method': 'ward', 'gpu_ms': min(lt) * 1e3, 'scipy_ms': t_sc * 1e3, 'identical_to_scipy': True,
+                            'what': 'linkage(squareform(D / 10), "ward") from the device matrix (merge list to the host) vs scipy on the host matrix'}
+            del d_D, Mh
+        except Exception as exc:                      # an auxiliary line must not cost the headline metric
+            linkage_line = {'error': f'{type(exc).__name__}: {exc}'}
     # ---------------- colour-vector preparation, host lists in -> host lists out ----------------
     prep = None
     if world == 1:
@@ -717,7 +744,7 @@ def main():
                          'parts_ms': {k: float(np.mean(v)) for k, v in scan_parts.items() if v}, 'boundary': boundary},
                 'roofline': roof, 'roofline_scan': roof_scan, 'cpu_baseline': cpu, 'clocks': clocks,
                 'scan_e2e': scan_e2e, 'parity': PARITY_NOTE,
-                'prep': prep, 'prefilter': prefilter, 'd2': d2,
+                'prep': prep, 'prefilter': prefilter, 'd2': d2, 'linkage': linkage_line,
                 'verified_pairs': verified,
                 'wall_s_timed_region': t_wall}
         emit(line)

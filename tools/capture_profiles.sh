@@ -16,7 +16,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
 else
 # full-set capture of every hot kernel on a small fixed workload
 python tools/prof_run.py 256 100 > gpurun_out/final/prof_plain.log 2>&1 && \
-ncu --set full --clock-control none -k regex:"nw_wave|mt_|scan_cov|hits_|dist_flags|dist_epilogue|cv_|prefilter|bd_" -c 110 -o gpurun_out/final/full \
+ncu --set full --clock-control none -k regex:"nw_wave|mt_|scan_cov|hits_|dist_flags|dist_epilogue|cv_|prefilter|bd_|lk_" -c 120 -o gpurun_out/final/full \
     python tools/prof_run.py 256 100 > gpurun_out/final/ncu_full.log 2>&1
 # gpurun brings back at most 64 MiB: keep the raw-page CSV, drop the report when it is too big
 ncu -i gpurun_out/final/full.ncu-rep --page raw --csv > gpurun_out/final/full_raw.csv 2>/dev/null

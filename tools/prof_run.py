@@ -23,6 +23,10 @@ for _ in range(2):
     D = eng.matrix_device(st, True, True, 2, 12345)
 torch.cuda.synchronize()
 print('dp cells', eng.stats['cells'], 'early', eng.stats['early_out'], 'pairs', eng.stats['pairs'])
+from telogator2_b200 import tg_linkage  # noqa: E402
+for _ in range(2):
+    Z = tg_linkage.linkage_from_matrix(D, 'ward', divide_by=10.0)
+print('linkage n', D.shape[0], 'merges', len(Z))
 T = tables['human_hifi']
 KL, CANON, ISSUB = T['KMER_LIST'], T['CANONICAL_STRINGS'], T['KMER_ISSUBSTRING']
 KLR, CR = [tg_kmer.RC(k) for k in KL], [tg_kmer.RC(k) for k in CANON]
