@@ -133,8 +133,9 @@ def main():
     put('hits_kernel', ['hits_kernel'], 'last 6000 bases of 5416 reads (32.4 Mbases of slices)')
     put('nw_wave_kernel', ['nw_wave_kernel<3, 3, 0, 0>'], 'phase A (shared column), N=256 (32640 pairs, 3.26e10 cells): DRAM traffic is noise, the kernel is integer-ALU bound')
     put('nw_wave_kernel<phase B>', ['nw_wave_kernel<3, 2, 0, 0>', 'nw_wave_kernel<3, 4, 0, 0>'], 'phase B (full + per-job profiles), N=256: reads the shuffled strings')
-    for k in ('mt_stream_batch_kernel', 'mt_sample_warp_kernel', 'prefilter_count_kernel<12, 1>'):
-        put(k, [k], 'tools/prof_run.py 256 100')
+    for k in ('mt_stream_batch_kernel', 'mt_sample_warp_kernel', 'prefilter_count_kernel<12, 1>', 'lk_nnchain_kernel'):
+        if k in last:
+            put(k, [k], 'tools/prof_run.py 256 100')
     if bagg:
         b = sum(a['bytes'] for a in bagg.values())
         T['bd_* (boundary calling)'] = {'bytes_per_launch': b, 'launch': '5416 reads / 100.0 Mbases, all levels', 'bytes_per_base': b / nb}
