@@ -1,17 +1,20 @@
-"""Batch boundary of the k-mer scan: drop-in for tg_tel.get_tel_repeat_comp_parallel (tg_tel.py:331-389).
+"""Batch boundary of the k-mer scan: drop-in for tg_tel.get_tel_repeat_comp_parallel (tg_tel.py:331-389) and
+tg_tel.get_terminating_tl (tg_tel.py:156-235).
 
 The reference runs gtrc_parallel_job (tg_tel.py:238-328) once per read inside a process pool; forked
 workers cannot drive a GPU, so the pool is replaced by three phases over ALL reads:
 
   phase 1 (GPU)  pack, canonical base counts fwd/rev, orientation, density x2       tg_tel.py:262-266, 160-161
-  phase 2 (CPU)  the reference's own get_terminating_tl / filters, per read          tg_tel.py:276-303 (unchanged code)
+  phase 2 (GPU)  boundary calling: power signal, wavelet smoothing, region walk,
+                 terminal-telomere scoring (tg_boundary.py); the filters of
+                 tg_tel.py:278-305 as array arithmetic on the host                   tg_tel.py:156-235, 276-305
   phase 3 (GPU)  non-overlapping k-mer hits on every TVR+tel slice (and on whole
                  reads for interstitial-telomere candidates)                         tg_tel.py:287-290, 310
 
 Same signature and the same 9-element return list (including the list-of-two-tuples shape of the
 interstitial entries).  max_workers / max_pending are accepted and ignored.
-get_terminating_tl is the reference's function (tg_tel.py:156-235, pywt wavelet code: outside the hot
-path); it is taken from `source.tg_tel` when the reference package is importable, or passed in.  It
+With a callable `get_terminating_tl` (the reference's own function when the telomere-signal plots are
+requested, or any custom boundary caller) phase 2 runs that function per read on the host instead; it
 keeps calling get_telomere_kmer_density per read -- those calls are served from the densities
 computed in phase 1 (tg_kmer.prime_density_cache).
 """
