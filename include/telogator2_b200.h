@@ -369,6 +369,12 @@ int tg_linkage_widen(const float *d_matrix, int n, float div, double *d_square, 
  * indices: the caller sorts them by distance (stable) and relabels them (scipy's `label`), see telogator2_b200/tg_linkage.py. */
 int tg_linkage_run(double *d_square, int n, const char *method, int32_t *d_size, int32_t *d_chain, double *d_near,
                    double *d_Z, void *stream);
+/* The same run with the row walks spread over `ctas` CTAs (<= SM count, launched cooperatively; grid barrier between the
+ * dependent steps): same merge list, faster once a row is long (n in the tens of thousands).  d_work:
+ * tg_linkage_multi_work_bytes(n, ctas) bytes of scratch. */
+size_t tg_linkage_multi_work_bytes(int n, int ctas);
+int tg_linkage_run_multi(double *d_square, int n, const char *method, int ctas, int32_t *d_size, double *d_near,
+                         double *d_Z, void *d_work, void *stream);
 
 #ifdef __cplusplus
 }

@@ -61,7 +61,7 @@ EXPORTS = ['tg_last_error', 'tg_version', 'tg_device_sm_count',
            'tg_cv_paint', 'tg_cv_density_boundary', 'tg_cv_lead_run', 'tg_cv_gather', 'tg_cv_denoise_tile', 'tg_cv_denoise',
            'tg_prefilter_tail_bytes', 'tg_prefilter_count',
            'tg_bound_power', 'tg_bound_smooth', 'tg_bound_regions', 'tg_bound_terminating',
-           'tg_linkage_expand', 'tg_linkage_widen', 'tg_linkage_run']
+           'tg_linkage_expand', 'tg_linkage_widen', 'tg_linkage_run', 'tg_linkage_multi_work_bytes', 'tg_linkage_run_multi']
 
 
 def load():
@@ -113,6 +113,9 @@ def load():
     L.tg_linkage_expand.argtypes = [vp, i32, vp, vp]
     L.tg_linkage_widen.argtypes = [vp, i32, C.c_float, vp, vp]
     L.tg_linkage_run.argtypes = [vp, i32, C.c_char_p, vp, vp, vp, vp, vp]
+    L.tg_linkage_multi_work_bytes.restype = sz
+    L.tg_linkage_multi_work_bytes.argtypes = [i32, i32]
+    L.tg_linkage_run_multi.argtypes = [vp, i32, C.c_char_p, i32, vp, vp, vp, vp, vp]
     _lib = L
     return L
 

@@ -41,17 +41,40 @@ def _label(Z, n):
         nxt += 1
 
 
+MULTI_CTA_MIN_N = 8192          # below this one CTA is as fast (a grid barrier costs as much as walking a short row)
+
+
+def _multi_ctas(n):
+    """CTAs for the row walks: 1 for short rows, else about one per 1024 columns (TG_LINKAGE_CTAS overrides)."""
+    import os
+    env = os.environ.get('TG_LINKAGE_CTAS')
+    torch = _lib.require_cuda()
+    sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    if env is not None:
+        return max(1, min(int(env), sms))
+    if n < MULTI_CTA_MIN_N:
+        return 1
+    return max(2, min(sms, (n + 1023) // 1024))
+
+
 def _run(d_square, n, method):
     torch = _lib.require_cuda()
     L = _lib.load()
     if method not in METHODS:
         raise NotImplementedError(f"linkage method '{method}' is not on the reference's path (supported: {', '.join(METHODS)})")
     d_size = torch.ones(n, dtype=torch.int32, device='cuda')
-    d_chain = torch.zeros(n, dtype=torch.int32, device='cuda')
     d_near = torch.empty(n, dtype=torch.float64, device='cuda')
     d_Z = torch.empty((n - 1, 4), dtype=torch.float64, device='cuda')
-    _lib.check(L.tg_linkage_run(_lib.dptr(d_square), n, method.encode(), _lib.dptr(d_size), _lib.dptr(d_chain), _lib.dptr(d_near),
-                                _lib.dptr(d_Z), _lib.stream_ptr(torch)))
+    ctas = _multi_ctas(n)
+    if ctas > 1:
+        # long rows: several CTAs walk each row, a grid barrier separates the dependent steps
+        d_work = torch.empty(L.tg_linkage_multi_work_bytes(n, ctas), dtype=torch.uint8, device='cuda')
+        _lib.check(L.tg_linkage_run_multi(_lib.dptr(d_square), n, method.encode(), ctas, _lib.dptr(d_size), _lib.dptr(d_near),
+                                          _lib.dptr(d_Z), _lib.dptr(d_work), _lib.stream_ptr(torch)))
+    else:
+        d_chain = torch.zeros(n, dtype=torch.int32, device='cuda')
+        _lib.check(L.tg_linkage_run(_lib.dptr(d_square), n, method.encode(), _lib.dptr(d_size), _lib.dptr(d_chain), _lib.dptr(d_near),
+                                    _lib.dptr(d_Z), _lib.stream_ptr(torch)))
     Z = d_Z.cpu().numpy()
     Z = np.ascontiguousarray(Z[np.argsort(Z[:, 2], kind='mergesort')])      # _hierarchy: "Sort Z by cluster distances" (stable)
     _label(Z, n)

@@ -67,6 +67,35 @@ def test_linkage_from_the_float32_matrix_and_flat_clusters():
     assert n_checked >= 2
 
 
+@pytest.mark.parametrize('ctas', ['2', '7', '148'])
+def test_multi_cta_runs_equal_scipy(monkeypatch, ctas):
+    """Long rows are walked by several CTAs with a grid barrier between the dependent steps (tg_linkage_run_multi); forced here on
+    small matrices, every method."""
+    from telogator2_b200 import tg_linkage
+    monkeypatch.setenv('TG_LINKAGE_CTAS', ctas)
+    for name, M in cases():
+        if len(M) < 3:
+            continue
+        M = M.copy()
+        np.fill_diagonal(M, 0)
+        y = squareform(M, checks=False)
+        for method in METHODS:
+            assert np.array_equal(tg_linkage.linkage(y, method=method), linkage(y, method=method)), (ctas, method, name)
+
+
+def test_large_matrix_takes_the_multi_cta_path():
+    from telogator2_b200 import tg_linkage
+    n = 9000
+    assert tg_linkage._multi_ctas(n) > 1
+    rng = np.random.default_rng(4)
+    M = (rng.integers(1, 100001, (n, n), dtype=np.int32) / 1e4).astype('<f4')
+    M = np.minimum(M, M.T)
+    np.fill_diagonal(M, 0)
+    ref = M / np.float32(10.0)
+    for method in ('ward', 'single'):
+        assert np.array_equal(tg_linkage.linkage_from_matrix(M, method, divide_by=10.0), linkage(squareform(ref, checks=False), method))
+
+
 def test_unsupported_calls_fail_loudly():
     from telogator2_b200 import tg_linkage
     y = squareform(np.array([[0, 1, 2], [1, 0, 3], [2, 3, 0.0]]))
