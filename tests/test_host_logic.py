@@ -730,3 +730,37 @@ def test_host_list_helper_formats_like_the_python_code():
         H.pack_reads(reads, off[:-1].copy(), out, ord('N'))
     with pytest.raises(TypeError):
         H.pack_reads([b'ACGT'], off[:2].copy(), out, ord('N'))
+
+
+def test_linkage_host_half_sort_and_relabel_equal_scipy():
+    """tg_linkage's host half (stable sort of the merges by distance + scipy's union-find relabelling, C helper and pure-Python
+    fallback) applied to the oracle's merge-ordered list gives scipy's result."""
+    from scipy.cluster.hierarchy import linkage
+    from scipy.spatial.distance import squareform
+    import oracle.linkage as OL
+    from telogator2_b200 import build, tg_kmer, tg_linkage
+    build.build_host_ext()
+    rng = np.random.default_rng(8)
+    for n, method in ((2, 'ward'), (9, 'single'), (40, 'ward'), (75, 'complete')):
+        M = np.round(rng.random((n, n)) * 7) / 7
+        M = np.minimum(M, M.T)
+        np.fill_diagonal(M, 0)
+        y = squareform(M, checks=False)
+        saved = OL.label
+        OL.label = lambda Z, n: None                      # the oracle's list before relabelling = what the device returns, sorted
+        try:
+            Zu = OL.linkage(y, method)
+        finally:
+            OL.label = saved
+        want = linkage(y, method)
+        Zc = np.ascontiguousarray(Zu.copy())
+        tg_linkage._label(Zc, n)
+        assert np.array_equal(Zc, want), (n, method)
+        saved_mod = tg_kmer._hostlists_mod
+        tg_kmer._hostlists_mod = None                     # pure-Python fallback
+        try:
+            Zp = np.ascontiguousarray(Zu.copy())
+            tg_linkage._label(Zp, n)
+        finally:
+            tg_kmer._hostlists_mod = saved_mod
+        assert np.array_equal(Zp, want), (n, method)
